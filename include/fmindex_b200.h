@@ -1,0 +1,271 @@
+/*
+ * fmindex_b200.h -- C ABI of libfmindex_b200.so
+ *
+ * B200-native (sm_100a) batched k-step FM-index backward search, built from
+ * scratch behind the API of achacond/k-step_FM-index so that it drops in for
+ * that one path.  Plain C: pointers and sizes only, no C++/torch types.
+ *
+ * The header has two parts.
+ *
+ *   PART 1  is the reference's own plugin surface for this path -- the
+ *           symbols a search binary links today (common/interface.h:27-41 and
+ *           common/common.h:64-96 of the reference).  Names, argument meaning,
+ *           ownership and error codes are kept; what changes is that k, d and
+ *           the index flavour are read from the file header at run time
+ *           instead of -DK_STEPS/-DNUM_CHUNK/-DNUM_COUNTERS, and that sizes
+ *           are 64-bit clean internally.
+ *
+ *   PART 2  is the thin layer the host C code uses to reach the hand-written
+ *           CUDA (index residency / re-blocking, query packing, the search
+ *           kernels, multi-GPU replicas, the gather roofline probe).  It is
+ *           also what a host written in another language would bind.
+ *
+ * There is NO CPU search path in this library: searchIndexCPU is not
+ * exported, and every entry point fails with FM_E_CUDA when no sm_100 device
+ * is usable.
+ */
+#ifndef FMINDEX_B200_H_
+#define FMINDEX_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------ *
+ * Error codes: values of the reference's error_t (common/common.h:36-62).   *
+ * 100/101/200/201 double as "this index type is required" codes there; here *
+ * loadIndex accepts all four tags, so they are only reported for a file     *
+ * whose tag is none of them.                                                *
+ * ------------------------------------------------------------------------ */
+typedef enum {
+  FM_SUCCESS = 0,
+  FM_E_OPENING_INDEX_FILE = 1,
+  FM_E_ALLOCATING_BWT = 2,
+  FM_E_ALLOCATING_FMI = 3,
+  FM_E_READING_BWT = 4,
+  FM_E_READING_FMI = 5,
+  FM_E_SAVING_INDEX_FILE = 6,
+  FM_E_SAVING_BWT_FILE = 7,
+  FM_E_BUILDING_BWT = 8,
+  FM_E_BUILDING_FMI = 9,
+  FM_E_OPENING_REFERENCE_FILE = 10,
+  FM_E_ALLOCATING_REFERENCE = 11,
+  FM_E_READING_MFASTA_FILE = 12,
+  FM_E_READING_REFERENCE_FILE = 13,
+  FM_E_OPENING_MFASTA_FILE = 14,
+  FM_E_ALLOCATING_MFASTA = 15,
+  FM_E_ALLOCATING_RESULTS = 16,
+  FM_E_OPENING_RESULTS_FILE = 17,
+  FM_E_READING_RESULTS_FILE = 18,
+  FM_E_NOT_IMPLEMENTED = 19,
+  /* new codes (outside the reference's range) */
+  FM_E_CUDA = 50,              /* CUDA runtime error or no usable device        */
+  FM_E_BAD_ARGUMENT = 51,
+  FM_E_UNSUPPORTED_INDEX = 52, /* k not in {1,2} or d not a multiple of 32      */
+  FM_E_QUERY_SHAPE = 53,       /* read length not a multiple of k               */
+  FM_E_INDEX_VER_BASELINE = 100,
+  FM_E_INDEX_VER_INTERLEAVE = 101,
+  FM_E_INDEX_VER_BASELINE_AC = 200,
+  FM_E_INDEX_VER_INTERLEAVE_AC = 201
+} fm_error_t;
+
+/* ======================================================================== *
+ * PART 1 -- the reference's interface for this path                         *
+ * ======================================================================== */
+
+/* Containers: field order of the reference structs is kept so that a caller
+ * compiled against the reference headers sees the same leading layout. */
+
+/* common/common.h:64-69 */
+typedef struct {
+  uint32_t num;        /* reads in the batch                                    */
+  uint32_t size;       /* bases per read                                        */
+  char    *h_queries;  /* num*size ASCII bases, no terminators (plain order)    */
+  char    *d_queries;  /* opaque: device-side batch state (fmgpu_batch_t)       */
+} qrys_t;
+
+/* common/common.h:77-81 */
+typedef struct {
+  uint32_t  num;
+  uint32_t *h_results; /* 2*num: [2q]=L, [2q+1]=R, half-open [L,R) in BWT rows  */
+  uint32_t *d_results; /* opaque: device-side state                             */
+} res_t;
+
+/* src/fmIndexCPUBaseline.c:54-69 (first 14 fields), then extensions */
+typedef struct {
+  uint32_t  steps;      /* k                                                    */
+  uint32_t  bwtsize;    /* n + 1                                                */
+  uint32_t  ncounters;  /* counters per FILE entry: 4^k, or 4^k/2 (AltCounters) */
+  uint32_t  nentries;   /* FILE entries (AltCounters: includes padding entry)   */
+  uint32_t  chunk;      /* d                                                    */
+  uint32_t  nbitmaps;   /* 2*(d/32) (never read by the reference)               */
+  uint32_t *h_dollarPositionBWT;
+  uint32_t *h_dollarBaseBWT;
+  uint32_t *h_modposdollarBWT;
+  void     *h_index;    /* raw file entries (bitcnt_t[nentries])                */
+  uint32_t *d_dollarPositionBWT; /* unused: '$' rows are folded into the device layout */
+  uint32_t *d_dollarBaseBWT;     /* unused                                       */
+  uint32_t *d_modposdollarBWT;   /* unused                                       */
+  void     *d_index;    /* opaque: fmgpu replica set created by transferCPUtoGPU */
+  /* --- extensions --- */
+  uint32_t  tag;        /* 100 | 101 | 200 | 201                                */
+  uint32_t  entry_words;
+} fmi_t;
+
+/* common/interface.h:27 ; loaders src/fmIndexCPUBaseline.c:71-143 and
+ * src/fmIndexCPUBaseline-AltCounters.c:71-143.  Accepts tags 100/101/200/201. */
+int32_t loadIndex(const char *fn, void **index);
+/* common/interface.h:33 ; src/fmIndexCPUBaseline.c:145-155 (frees h_index only) */
+int32_t freeIndex(void **index);
+/* common/common.h:86 ; common/common.c:132-199.  Plain (non-interleaved) order:
+ * the warp interleave of INTERLEAVING_QUERIES is replaced by device-side packing. */
+int32_t loadQueries(char *fn, uint32_t sizeQuery, uint32_t numQueries, void **queries);
+/* common/interface.h:29 ; common/common.c:248-260 */
+int32_t initResults(uint32_t numresults, void **results);
+/* common/common.h:89-90,93 ; common/common.c:201-246,324-341.  saveResults
+ * writes "<fn>.res.gpu" in the reference's text format. */
+int32_t writeResults(char *fn, uint32_t *results, uint32_t numqueries);
+int32_t loadResults(char *fn, void **results);
+int32_t saveResults(char *fn, void *results, void *index);
+/* common/common.h:91-92 ; common/common.c:262-280 */
+int32_t freeQueries(void **queries);
+int32_t freeResults(void **results);
+/* common/common.h:94 ; common/common.c:282-310 */
+char   *errorCommon(int32_t e);
+/* common/common.h:83 ; common/common.c:28-33 */
+double  sampleTime(void);
+
+/* The six symbols a reference .cu object exports (e.g.
+ * src/fmIndexGPU-Coop-2Step.cu:231,250,287,295,319,330).
+ *
+ * transferCPUtoGPU: re-blocks the file entries into the device layout on the
+ *   first configured GPU, replicates it to the others over NVLink peer copies,
+ *   shards the batch contiguously (32-aligned) over the GPUs, uploads the
+ *   ASCII reads and packs them to 2 bit on the device, allocates results.
+ * searchIndexGPU: launches the search on every shard and waits (kernels only,
+ *   like the reference's timed region).  Returns void like the reference;
+ *   a CUDA failure prints file:line and exits (reference HandleError, :88-93).
+ * transferGPUtoCPU: per-GPU D2H of its (L,R) shard straight into h_results.
+ */
+int32_t transferCPUtoGPU(void *index, void *queries, void *results);
+void    searchIndexGPU(void *index, void *queries, void *resIntervals);
+int32_t transferGPUtoCPU(void *results);
+int32_t freeIndexGPU(void **index);
+int32_t freeQueriesGPU(void **queries);
+int32_t freeResultsGPU(void **results);
+
+/* ======================================================================== *
+ * PART 2 -- thin C ABI to the CUDA side                                     *
+ * ======================================================================== */
+
+typedef struct fmgpu_index fmgpu_index_t;   /* device-resident re-blocked index (one GPU) */
+typedef struct fmgpu_batch fmgpu_batch_t;   /* device-resident query shard + its results  */
+
+enum { FMGPU_MODE_TASK = 0, FMGPU_MODE_COOP = 1 };
+
+/* Kernel variant.  Zero-initialised = library defaults. */
+typedef struct {
+  int32_t mode;               /* FMGPU_MODE_TASK: one thread per query (both endpoints);
+                                 FMGPU_MODE_COOP: lane pair per query, L lane + R lane,
+                                 block fetch shared through warp shuffles             */
+  int32_t queries_per_thread; /* independent queries interleaved per thread/lane pair: 1, 2 or 4 */
+  int32_t threads_per_block;  /* 128, 256 or 512                                      */
+  int32_t reserved;
+} fmgpu_variant_t;
+
+/* Shape of the device layout ("SB96": per-symbol blocks of 96 BWT rows,
+ * 16 bytes = {u32 rank at block start, 96 indicator bits}); see DESIGN.md. */
+typedef struct {
+  uint32_t steps;        /* k                                                   */
+  uint32_t bwtsize;
+  uint32_t nsymbols;     /* 4^k                                                 */
+  uint32_t nblocks;      /* blocks per symbol (stride)                          */
+  uint32_t source_tag;   /* tag of the file it was derived from                 */
+  uint32_t quirk_start;  /* first BWT row of the AltCounters padding quirk, or 0xFFFFFFFF */
+  uint32_t quirk_mask;   /* 2 bits per symbol: value the reference AC searcher adds there  */
+  uint32_t reserved;
+  uint64_t nbytes;       /* size of the block table                             */
+} fmgpu_index_meta_t;
+
+/* devices ---------------------------------------------------------------- */
+int32_t fmgpu_device_count(void);                 /* usable sm_100 devices; 0 if none */
+/* devices used by transferCPUtoGPU / searchIndexGPU.  Default: the list in
+ * $FMGPU_DEVICES ("0,1,2"), else device 0. */
+int32_t fmgpu_set_devices(const int32_t *devices, int32_t ndevices);
+int32_t fmgpu_set_variant(const fmgpu_variant_t *v);   /* variant used by searchIndexGPU */
+const char *fmgpu_last_error(void);
+
+/* index residency / layout stage ------------------------------------------ */
+/* Uploads raw file entries (any of the four tags) to `device`, re-blocks them
+ * there into SB96 and frees the raw copy.  Replaces the cudaMalloc+cudaMemcpy
+ * of the reference's transferCPUtoGPU (src/fmIndexGPU-Coop-2Step.cu:250-285). */
+int32_t fmgpu_index_create(int32_t device, uint32_t tag, uint32_t steps, uint32_t chunk, uint32_t bwtsize,
+                           uint32_t ncounters, uint32_t nentries,
+                           const uint32_t *dollarPositionBWT, const uint32_t *dollarBaseBWT,
+                           const uint32_t *h_entries, fmgpu_index_t **out);
+/* same, entries already on `device` (e.g. written by the GPU index builder) */
+int32_t fmgpu_index_create_from_device(int32_t device, uint32_t tag, uint32_t steps, uint32_t chunk, uint32_t bwtsize,
+                                       uint32_t ncounters, uint32_t nentries,
+                                       const uint32_t *dollarPositionBWT, const uint32_t *dollarBaseBWT,
+                                       const uint32_t *d_entries, fmgpu_index_t **out);
+/* replica on another GPU of this process: cudaMemcpyPeer over NVLink */
+int32_t fmgpu_index_replicate(const fmgpu_index_t *src, int32_t device, fmgpu_index_t **out);
+/* replica in another PROCESS: allocate an empty table of the same shape, then
+ * fill fmgpu_index_blocks() with a broadcast (NCCL) from the owner */
+int32_t fmgpu_index_alloc_like(int32_t device, const fmgpu_index_meta_t *meta, fmgpu_index_t **out);
+int32_t fmgpu_index_get_meta(const fmgpu_index_t *idx, fmgpu_index_meta_t *meta);
+void   *fmgpu_index_blocks(const fmgpu_index_t *idx);     /* device pointer */
+int32_t fmgpu_index_device(const fmgpu_index_t *idx);
+int32_t fmgpu_index_free(fmgpu_index_t **idx);
+
+/* query shards ------------------------------------------------------------ */
+int32_t fmgpu_batch_create(int32_t device, uint64_t nqueries, uint32_t len, uint32_t steps, fmgpu_batch_t **out);
+/* H2D of ASCII reads (nqueries*len bytes, plain order) + 2-bit pack kernel */
+int32_t fmgpu_batch_upload_ascii(fmgpu_batch_t *b, const char *h_ascii);
+/* async launch of the search kernels on the shard's stream */
+int32_t fmgpu_batch_search(const fmgpu_index_t *idx, fmgpu_batch_t *b, const fmgpu_variant_t *v);
+int32_t fmgpu_batch_sync(fmgpu_batch_t *b);
+/* D2H of 2*nqueries u32 */
+int32_t fmgpu_batch_download(fmgpu_batch_t *b, uint32_t *h_results);
+/* `iters` searches timed with CUDA events on the shard's stream; ms per search */
+int32_t fmgpu_batch_search_timed(const fmgpu_index_t *idx, fmgpu_batch_t *b, const fmgpu_variant_t *v,
+                                 int32_t iters, float *ms_per_iter);
+/* sum over LF steps of |{block(L), block(R)}| (necessary 16-byte block fetches)
+ * and of |{sector(L), sector(R)}| (necessary 32-byte sectors) for this shard */
+int32_t fmgpu_batch_count_fetches(const fmgpu_index_t *idx, fmgpu_batch_t *b, uint64_t *nblocks, uint64_t *nsectors);
+void   *fmgpu_batch_packed(const fmgpu_batch_t *b);       /* device pointers */
+void   *fmgpu_batch_results(const fmgpu_batch_t *b);
+void   *fmgpu_batch_stream(const fmgpu_batch_t *b);       /* cudaStream_t */
+int32_t fmgpu_batch_free(fmgpu_batch_t **b);
+
+/* caller-owned device memory (e.g. torch tensors) ------------------------- */
+uint32_t fmgpu_words_per_query(uint32_t len);
+int32_t fmgpu_pack_queries_device(int32_t device, const char *d_ascii, uint64_t nqueries, uint32_t len,
+                                  uint32_t *d_packed, void *stream);
+int32_t fmgpu_search_device(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nqueries, uint32_t len,
+                            uint32_t *d_results, const fmgpu_variant_t *v, void *stream);
+
+/* end to end: host ASCII reads in, host (L,R) out; the batch is cut into
+ * chunks and upload / pack / search / download overlap on several streams per
+ * GPU, shards spread over `nreplicas` GPUs */
+int32_t fmgpu_search_host(fmgpu_index_t *const *replicas, int32_t nreplicas, const char *h_ascii,
+                          uint64_t nqueries, uint32_t len, uint32_t *h_results, const fmgpu_variant_t *v);
+
+/* pinned host memory for query / result buffers */
+void   *fmgpu_host_alloc(size_t bytes);
+void    fmgpu_host_free(void *p);
+int32_t fmgpu_host_register(void *p, size_t bytes);
+int32_t fmgpu_host_unregister(void *p);
+
+/* HBM random-access roofline probe: independent uniformly random 16-byte
+ * loads over a table of `table_bytes`, full occupancy.  Returns loads/s. */
+int32_t fmgpu_gather_probe(int32_t device, uint64_t table_bytes, uint64_t loads_per_thread,
+                           int32_t iters, double *loads_per_second);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMINDEX_B200_H_ */

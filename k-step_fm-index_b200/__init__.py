@@ -1,0 +1,349 @@
+"""k-step_fm-index_b200 -- Python host-side mirror of the reference's search interface.
+
+Thin ctypes binding over ``lib/libfmindex_b200.so`` (C host layer + hand-written
+CUDA for sm_100a).  The function names are the reference's own
+(``common/interface.h:27-41``, ``common/common.h:83-94``): ``loadIndex``,
+``loadQueries``, ``initResults``, ``transferCPUtoGPU``, ``searchIndexGPU``,
+``transferGPUtoCPU``, ``saveResults``, ``free*``; the ``fmgpu_*`` functions are
+the thin C ABI to the CUDA side (``include/fmindex_b200.h`` PART 2).
+
+There is no CPU search path here: if the shared library is missing the import
+fails loudly, and on a box without an sm_100 GPU every device entry point
+returns ``FM_E_CUDA``.
+
+The directory name contains hyphens, so import it with
+``importlib.import_module("k-step_fm-index_b200")`` (repo root on ``sys.path``).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfmindex_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+BIN = os.path.join(_HERE, "bin")
+
+FM_SUCCESS = 0
+FM_E_CUDA = 50
+FM_E_BAD_ARGUMENT = 51
+FM_E_UNSUPPORTED_INDEX = 52
+FM_E_QUERY_SHAPE = 53
+MODE_TASK, MODE_COOP = 0, 1
+
+
+def build_native(verbose=False):
+    """Compiles the C host layer and the CUDA kernels for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", CSRC, "-j4"], capture_output=True, text=True)
+    if verbose or out.returncode:
+        print(out.stdout[-4000:], out.stderr[-4000:])
+    if out.returncode:
+        raise RuntimeError("building libfmindex_b200.so failed")
+    return LIB_PATH
+
+
+class qrys_t(C.Structure):          # common/common.h:64-69
+    _fields_ = [("num", C.c_uint32), ("size", C.c_uint32), ("h_queries", C.c_void_p), ("d_queries", C.c_void_p)]
+
+
+class res_t(C.Structure):           # common/common.h:77-81
+    _fields_ = [("num", C.c_uint32), ("h_results", C.c_void_p), ("d_results", C.c_void_p)]
+
+
+class fmi_t(C.Structure):           # src/fmIndexCPUBaseline.c:54-69 + extensions
+    _fields_ = [("steps", C.c_uint32), ("bwtsize", C.c_uint32), ("ncounters", C.c_uint32), ("nentries", C.c_uint32),
+                ("chunk", C.c_uint32), ("nbitmaps", C.c_uint32),
+                ("h_dollarPositionBWT", C.POINTER(C.c_uint32)), ("h_dollarBaseBWT", C.POINTER(C.c_uint32)),
+                ("h_modposdollarBWT", C.POINTER(C.c_uint32)), ("h_index", C.c_void_p),
+                ("d_dollarPositionBWT", C.c_void_p), ("d_dollarBaseBWT", C.c_void_p), ("d_modposdollarBWT", C.c_void_p),
+                ("d_index", C.c_void_p), ("tag", C.c_uint32), ("entry_words", C.c_uint32)]
+
+
+class fmgpu_variant_t(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("queries_per_thread", C.c_int32), ("threads_per_block", C.c_int32), ("reserved", C.c_int32)]
+
+
+class fmgpu_index_meta_t(C.Structure):
+    _fields_ = [("steps", C.c_uint32), ("bwtsize", C.c_uint32), ("nsymbols", C.c_uint32), ("nblocks", C.c_uint32),
+                ("source_tag", C.c_uint32), ("quirk_start", C.c_uint32), ("quirk_mask", C.c_uint32), ("reserved", C.c_uint32),
+                ("nbytes", C.c_uint64)]
+
+
+_VP, _VPP = C.c_void_p, C.POINTER(C.c_void_p)
+_U32P = C.POINTER(C.c_uint32)
+
+# name -> (restype, argtypes): every symbol include/fmindex_b200.h declares
+PROTOTYPES = {
+    # PART 1 -- reference interface
+    "loadIndex": (C.c_int32, [C.c_char_p, _VPP]),
+    "freeIndex": (C.c_int32, [_VPP]),
+    "loadQueries": (C.c_int32, [C.c_char_p, C.c_uint32, C.c_uint32, _VPP]),
+    "initResults": (C.c_int32, [C.c_uint32, _VPP]),
+    "writeResults": (C.c_int32, [C.c_char_p, _VP, C.c_uint32]),
+    "loadResults": (C.c_int32, [C.c_char_p, _VPP]),
+    "saveResults": (C.c_int32, [C.c_char_p, _VP, _VP]),
+    "freeQueries": (C.c_int32, [_VPP]),
+    "freeResults": (C.c_int32, [_VPP]),
+    "errorCommon": (C.c_char_p, [C.c_int32]),
+    "sampleTime": (C.c_double, []),
+    "transferCPUtoGPU": (C.c_int32, [_VP, _VP, _VP]),
+    "searchIndexGPU": (None, [_VP, _VP, _VP]),
+    "transferGPUtoCPU": (C.c_int32, [_VP]),
+    "freeIndexGPU": (C.c_int32, [_VPP]),
+    "freeQueriesGPU": (C.c_int32, [_VPP]),
+    "freeResultsGPU": (C.c_int32, [_VPP]),
+    # PART 2 -- thin C ABI to CUDA
+    "fmgpu_device_count": (C.c_int32, []),
+    "fmgpu_set_devices": (C.c_int32, [C.POINTER(C.c_int32), C.c_int32]),
+    "fmgpu_set_variant": (C.c_int32, [C.POINTER(fmgpu_variant_t)]),
+    "fmgpu_last_error": (C.c_char_p, []),
+    "fmgpu_index_create": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                       _U32P, _U32P, _VP, _VPP]),
+    "fmgpu_index_create_from_device": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                   C.c_uint32, _U32P, _U32P, _VP, _VPP]),
+    "fmgpu_index_replicate": (C.c_int32, [_VP, C.c_int32, _VPP]),
+    "fmgpu_index_alloc_like": (C.c_int32, [C.c_int32, C.POINTER(fmgpu_index_meta_t), _VPP]),
+    "fmgpu_index_get_meta": (C.c_int32, [_VP, C.POINTER(fmgpu_index_meta_t)]),
+    "fmgpu_index_blocks": (_VP, [_VP]),
+    "fmgpu_index_device": (C.c_int32, [_VP]),
+    "fmgpu_index_free": (C.c_int32, [_VPP]),
+    "fmgpu_batch_create": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint32, C.c_uint32, _VPP]),
+    "fmgpu_batch_upload_ascii": (C.c_int32, [_VP, _VP]),
+    "fmgpu_batch_search": (C.c_int32, [_VP, _VP, C.POINTER(fmgpu_variant_t)]),
+    "fmgpu_batch_sync": (C.c_int32, [_VP]),
+    "fmgpu_batch_download": (C.c_int32, [_VP, _VP]),
+    "fmgpu_batch_search_timed": (C.c_int32, [_VP, _VP, C.POINTER(fmgpu_variant_t), C.c_int32, C.POINTER(C.c_float)]),
+    "fmgpu_batch_count_fetches": (C.c_int32, [_VP, _VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "fmgpu_batch_packed": (_VP, [_VP]),
+    "fmgpu_batch_results": (_VP, [_VP]),
+    "fmgpu_batch_stream": (_VP, [_VP]),
+    "fmgpu_batch_free": (C.c_int32, [_VPP]),
+    "fmgpu_words_per_query": (C.c_uint32, [C.c_uint32]),
+    "fmgpu_pack_queries_device": (C.c_int32, [C.c_int32, _VP, C.c_uint64, C.c_uint32, _VP, _VP]),
+    "fmgpu_search_device": (C.c_int32, [_VP, _VP, C.c_uint64, C.c_uint32, _VP, C.POINTER(fmgpu_variant_t), _VP]),
+    "fmgpu_search_host": (C.c_int32, [_VPP, C.c_int32, _VP, C.c_uint64, C.c_uint32, _VP, C.POINTER(fmgpu_variant_t)]),
+    "fmgpu_host_alloc": (_VP, [C.c_size_t]),
+    "fmgpu_host_free": (None, [_VP]),
+    "fmgpu_host_register": (C.c_int32, [_VP, C.c_size_t]),
+    "fmgpu_host_unregister": (C.c_int32, [_VP]),
+    "fmgpu_gather_probe": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.POINTER(C.c_double)]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library (raises if it has not been built: no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+        handle = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, (restype, argtypes) in PROTOTYPES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = restype, argtypes
+        _lib = handle
+    return _lib
+
+
+class FMError(RuntimeError):
+    def __init__(self, code, where):
+        self.code = code
+        msg = lib().errorCommon(code)
+        super().__init__(f"{where}: error {code}: {msg.decode() if msg else '?'}")
+
+
+def check(code, where):
+    if code != FM_SUCCESS:
+        raise FMError(code, where)
+
+
+def variant(mode=MODE_TASK, queries_per_thread=0, threads_per_block=0):
+    return fmgpu_variant_t(mode, queries_per_thread, threads_per_block, 0)
+
+
+# --------------------------------------------------------------------------- #
+# reference-shaped convenience wrappers (same call sequence as
+# common/searchQueries.c:64-125); handles are c_void_p like the reference's void*
+# --------------------------------------------------------------------------- #
+def loadIndex(fn):
+    h = C.c_void_p()
+    check(lib().loadIndex(os.fsencode(fn), C.byref(h)), f"loadIndex({fn})")
+    return h
+
+
+def loadQueries(fn, size, num):
+    h = C.c_void_p()
+    check(lib().loadQueries(os.fsencode(fn), size, num, C.byref(h)), f"loadQueries({fn})")
+    return h
+
+
+def queriesFromArray(ascii_bases, size):
+    """qrys_t around a numpy uint8 array of num*size ASCII bases (no file involved)."""
+    a = np.ascontiguousarray(ascii_bases, dtype=np.uint8).reshape(-1)
+    assert a.size % size == 0
+    q = qrys_t(a.size // size, size, a.ctypes.data, None)
+    q._keep = a
+    return q
+
+
+def initResults(num):
+    h = C.c_void_p()
+    check(lib().initResults(num, C.byref(h)), "initResults")
+    return h
+
+
+def resultsArray(results, copy=True):
+    r = C.cast(results, C.POINTER(res_t)).contents
+    a = np.ctypeslib.as_array(C.cast(r.h_results, _U32P), shape=(2 * r.num,))
+    return a.copy() if copy else a
+
+
+def index_fields(index):
+    return C.cast(index, C.POINTER(fmi_t)).contents
+
+
+def search_files(index_fn, queries_fn, size, num, devices=None, var=None):
+    """The reference main()'s GPU flow; returns the (L,R) array of 2*num uint32."""
+    L = lib()
+    if devices is not None:
+        arr = (C.c_int32 * len(devices))(*devices)
+        check(L.fmgpu_set_devices(arr, len(devices)), "fmgpu_set_devices")
+    L.fmgpu_set_variant(C.byref(var) if var is not None else None)
+    idx = loadIndex(index_fn)
+    qry = loadQueries(queries_fn, size, num)
+    res = initResults(num)
+    try:
+        check(L.transferCPUtoGPU(idx, qry, res), "transferCPUtoGPU")
+        L.searchIndexGPU(idx, qry, res)
+        check(L.transferGPUtoCPU(res), "transferGPUtoCPU")
+        return resultsArray(res)
+    finally:
+        L.freeIndexGPU(C.byref(idx)); L.freeQueriesGPU(C.byref(qry)); L.freeResultsGPU(C.byref(res))
+        L.freeIndex(C.byref(idx)); L.freeQueries(C.byref(qry)); L.freeResults(C.byref(res))
+
+
+class DeviceIndex:
+    """Device-resident SB96 index on one GPU (fmgpu_index_t)."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    @classmethod
+    def from_file(cls, fn, device=0):
+        idx = loadIndex(fn)
+        try:
+            f = index_fields(idx)
+            h = C.c_void_p()
+            check(lib().fmgpu_index_create(device, f.tag, f.steps, f.chunk, f.bwtsize, f.ncounters, f.nentries,
+                                           f.h_dollarPositionBWT, f.h_dollarBaseBWT, f.h_index, C.byref(h)),
+                  "fmgpu_index_create")
+        finally:
+            lib().freeIndex(C.byref(idx))
+        return cls(h)
+
+    @classmethod
+    def from_image(cls, image_u32, device=0):
+        """image = the words of an index FILE (header + entries) as a numpy uint32 array."""
+        im = np.ascontiguousarray(image_u32, dtype=np.uint32)
+        tag, k, bwtsize, ncnt, nent, d = (int(v) for v in im[:6])
+        dpos = (C.c_uint32 * k)(*[int(v) for v in im[6:6 + k]])
+        dbase = (C.c_uint32 * k)(*[int(v) for v in im[6 + k:6 + 2 * k]])
+        h = C.c_void_p()
+        check(lib().fmgpu_index_create(device, tag, k, d, bwtsize, ncnt, nent, dpos, dbase,
+                                       im[6 + 2 * k:].ctypes.data, C.byref(h)), "fmgpu_index_create")
+        return cls(h)
+
+    @classmethod
+    def alloc_like(cls, meta, device=0):
+        h = C.c_void_p()
+        check(lib().fmgpu_index_alloc_like(device, C.byref(meta), C.byref(h)), "fmgpu_index_alloc_like")
+        return cls(h)
+
+    def replicate(self, device):
+        h = C.c_void_p()
+        check(lib().fmgpu_index_replicate(self.handle, device, C.byref(h)), "fmgpu_index_replicate")
+        return DeviceIndex(h)
+
+    @property
+    def meta(self):
+        m = fmgpu_index_meta_t()
+        check(lib().fmgpu_index_get_meta(self.handle, C.byref(m)), "fmgpu_index_get_meta")
+        return m
+
+    @property
+    def device(self):
+        return lib().fmgpu_index_device(self.handle)
+
+    @property
+    def blocks_ptr(self):
+        return lib().fmgpu_index_blocks(self.handle)
+
+    @property
+    def __cuda_array_interface__(self):
+        """The block table as a flat uint8 device array (lets torch wrap it for an NCCL broadcast)."""
+        return {"shape": (int(self.meta.nbytes),), "typestr": "|u1", "data": (int(self.blocks_ptr), False), "version": 2}
+
+    def free(self):
+        if self.handle:
+            lib().fmgpu_index_free(C.byref(self.handle))
+            self.handle = C.c_void_p()
+
+
+class DeviceBatch:
+    """Device-resident query shard + its results (fmgpu_batch_t)."""
+
+    def __init__(self, device, nq, length, steps):
+        self.nq, self.len = nq, length
+        self.handle = C.c_void_p()
+        check(lib().fmgpu_batch_create(device, nq, length, steps, C.byref(self.handle)), "fmgpu_batch_create")
+
+    def upload_ascii(self, ascii_bases):
+        a = np.ascontiguousarray(ascii_bases, dtype=np.uint8).reshape(-1)
+        assert a.size == self.nq * self.len
+        check(lib().fmgpu_batch_upload_ascii(self.handle, a.ctypes.data), "fmgpu_batch_upload_ascii")
+
+    def search(self, index, var=None, sync=True):
+        check(lib().fmgpu_batch_search(index.handle, self.handle, C.byref(var) if var is not None else None), "fmgpu_batch_search")
+        if sync:
+            check(lib().fmgpu_batch_sync(self.handle), "fmgpu_batch_sync")
+
+    def search_timed(self, index, iters, var=None):
+        ms = C.c_float()
+        check(lib().fmgpu_batch_search_timed(index.handle, self.handle, C.byref(var) if var is not None else None, iters, C.byref(ms)),
+              "fmgpu_batch_search_timed")
+        return ms.value
+
+    def count_fetches(self, index):
+        nb, ns = C.c_uint64(), C.c_uint64()
+        check(lib().fmgpu_batch_count_fetches(index.handle, self.handle, C.byref(nb), C.byref(ns)), "fmgpu_batch_count_fetches")
+        return nb.value, ns.value
+
+    def download(self):
+        out = np.empty(2 * self.nq, dtype=np.uint32)
+        check(lib().fmgpu_batch_download(self.handle, out.ctypes.data), "fmgpu_batch_download")
+        return out
+
+    def free(self):
+        if self.handle:
+            lib().fmgpu_batch_free(C.byref(self.handle))
+            self.handle = C.c_void_p()
+
+
+def search_host(replicas, ascii_bases, length, var=None, out=None):
+    """End-to-end: host ASCII reads in, host (L,R) out, pipelined over the replicas' GPUs."""
+    a = np.ascontiguousarray(ascii_bases, dtype=np.uint8).reshape(-1)
+    nq = a.size // length
+    if out is None:
+        out = np.empty(2 * nq, dtype=np.uint32)
+    arr = (C.c_void_p * len(replicas))(*[r.handle for r in replicas])
+    check(lib().fmgpu_search_host(arr, len(replicas), a.ctypes.data, nq, length, out.ctypes.data,
+                                  C.byref(var) if var is not None else None), "fmgpu_search_host")
+    return out
+
+
+def gather_probe(device, table_bytes, loads_per_thread=256, iters=3):
+    v = C.c_double()
+    check(lib().fmgpu_gather_probe(device, table_bytes, loads_per_thread, iters, C.byref(v)), "fmgpu_gather_probe")
+    return v.value

@@ -1,0 +1,584 @@
+/*
+ * fm_gpu.cu -- PART 2 of include/fmindex_b200.h: the thin C ABI over the
+ * hand-written CUDA of fm_kernels.cuh (index residency / re-blocking, query
+ * packing, search launches, replicas, pipelined end-to-end search, probe).
+ *
+ * Replaces the device-side support code every reference .cu carries
+ * (transferCPUtoGPU / searchIndexGPU / transferGPUtoCPU / free*GPU, e.g.
+ * src/fmIndexGPU-Coop-2Step.cu:231-338): one device, default stream,
+ * pageable cudaMemcpy there; explicit devices, streams, pinned staging and
+ * peer copies here.  No CPU fallback: without a usable sm_100 device every
+ * entry point returns FM_E_CUDA.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "../../include/fmindex_b200.h"
+#include "fm_kernels.cuh"
+
+struct fmgpu_index {
+  int                device;
+  fmgpu_index_meta_t meta;
+  uint4             *blocks;
+};
+
+struct fmgpu_batch {
+  int          device;
+  uint64_t     nq;
+  uint32_t     len, steps, wpq;
+  char        *d_ascii;       /* staging for upload_ascii (allocated on first use) */
+  uint32_t    *d_packed;
+  uint32_t    *d_results;
+  unsigned long long *d_counters;
+  cudaStream_t stream;
+  cudaEvent_t  ev0, ev1;
+};
+
+static thread_local char g_err[512] = "no error";
+
+extern "C" const char *fmgpu_last_error(void) { return g_err; }
+
+static int32_t fm_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+  snprintf(g_err, sizeof g_err, "%s: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+  return FM_E_CUDA;
+}
+static int32_t fm_fail_msg(int32_t code, const char *msg)
+{
+  snprintf(g_err, sizeof g_err, "%s", msg);
+  return code;
+}
+#define CU_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fm_fail(e_, #call, __FILE__, __LINE__); } while (0)
+
+/* ------------------------------------------------------------------------ */
+extern "C" int32_t fmgpu_device_count(void)
+{
+  int n = 0, usable = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  for (int i = 0; i < n; i++) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) usable++;
+  }
+  return usable;
+}
+
+static int32_t fm_use_device(int device)
+{
+  int major = 0;
+  CU_TRY(cudaSetDevice(device));
+  CU_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10) return fm_fail_msg(FM_E_CUDA, "device is not sm_100 (this library carries sm_100a code only)");
+  return FM_SUCCESS;
+}
+
+extern "C" uint32_t fmgpu_words_per_query(uint32_t len) { return (len + 15u) / 16u; }
+
+/* ------------------------------------------------------------------------ *
+ * index residency / layout stage
+ * ------------------------------------------------------------------------ */
+static uint32_t fm_nblocks_for(uint32_t bwtsize)
+{
+  uint64_t nb = (uint64_t) bwtsize / FM_SB_ROWS + 1;   /* block of X = bwtsize must exist */
+  return (uint32_t)((nb + 7) & ~7ull);                 /* symbol stride = whole 128-byte lines */
+}
+
+/* AltCounters padding-entry quirk: in the last chunk, a
+ * symbol whose counter lives in the padding entry comes out +1 per '$' row of
+ * that chunk carrying the symbol.  Returns the per-symbol 2-bit table. */
+static void fm_ac_quirk(uint32_t tag, uint32_t steps, uint32_t chunk, uint32_t bwtsize, uint32_t ncounters,
+                        const uint32_t *dpos, const uint32_t *dbase, uint32_t *start, uint32_t *mask)
+{
+  *start = 0xFFFFFFFFu; *mask = 0;
+  if (tag < 200) return;
+  const uint32_t elast = (bwtsize - 1) / chunk;
+  for (uint32_t s = 0; s < steps; s++) {
+    if (dpos[s] / chunk != elast) continue;
+    const uint32_t sigma = dbase[s];
+    const bool next = ((elast & 1u) && sigma < ncounters) || (!(elast & 1u) && sigma >= ncounters);
+    if (next) *mask += 1u << (2 * sigma);
+  }
+  if (*mask) *start = elast * chunk;
+}
+
+static int32_t fm_index_from_device_entries(int device, uint32_t tag, uint32_t steps, uint32_t chunk, uint32_t bwtsize,
+                                            uint32_t ncounters, uint32_t nentries, const uint32_t *dpos,
+                                            const uint32_t *dbase, const uint32_t *d_entries, fmgpu_index_t **out)
+{
+  const bool ac = (tag == 200 || tag == 201);
+  if (!(tag == 100 || tag == 101 || ac)) return fm_fail_msg(FM_E_UNSUPPORTED_INDEX, "unknown index tag");
+  if (steps < 1 || steps > 2) return fm_fail_msg(FM_E_UNSUPPORTED_INDEX, "GPU search supports k in {1,2} (like the reference GPU kernels)");
+  if (chunk == 0 || chunk % 32) return fm_fail_msg(FM_E_UNSUPPORTED_INDEX, "d must be a multiple of 32");
+  const uint32_t nsym = 1u << (2 * steps);
+  if (ncounters != (ac ? nsym / 2 : nsym)) return fm_fail_msg(FM_E_UNSUPPORTED_INDEX, "counter count does not match k");
+  const uint32_t need = (uint32_t)(((uint64_t) bwtsize + chunk - 1) / chunk) + (ac ? 1u : 0u);
+  if (nentries != need || bwtsize < 2) return fm_fail_msg(FM_E_UNSUPPORTED_INDEX, "entry count does not match bwtsize/d");
+
+  fmgpu_index_t *idx = (fmgpu_index_t *) calloc(1, sizeof(*idx));
+  if (!idx) return fm_fail_msg(FM_E_ALLOCATING_FMI, "host allocation failed");
+  idx->device = device;
+  idx->meta.steps = steps; idx->meta.bwtsize = bwtsize; idx->meta.nsymbols = nsym;
+  idx->meta.nblocks = fm_nblocks_for(bwtsize); idx->meta.source_tag = tag;
+  fm_ac_quirk(tag, steps, chunk, bwtsize, ncounters, dpos, dbase, &idx->meta.quirk_start, &idx->meta.quirk_mask);
+  idx->meta.nbytes = (uint64_t) nsym * idx->meta.nblocks * sizeof(uint4);
+
+  cudaError_t e = cudaMalloc((void **) &idx->blocks, idx->meta.nbytes);
+  if (e != cudaSuccess) { free(idx); return fm_fail(e, "cudaMalloc(SB96 table)", __FILE__, __LINE__); }
+
+  FmRawIndex raw;
+  raw.entries = d_entries; raw.tag = tag; raw.k = steps; raw.d = chunk; raw.ncounters = ncounters;
+  raw.nentries = nentries; raw.entry_words = 2 * (chunk / 32) * steps + ncounters; raw.bwtsize = bwtsize;
+  raw.nentries_std = ac ? nentries - 1 : nentries;
+  for (uint32_t s = 0; s < 2; s++) { raw.dpos[s] = s < steps ? dpos[s] : 0xFFFFFFFFu; raw.dbase[s] = s < steps ? dbase[s] : 0xFFFFFFFFu; }
+  raw.quirk_start = idx->meta.quirk_start; raw.quirk_mask = idx->meta.quirk_mask;
+
+  const uint32_t nb = idx->meta.nblocks;
+  fm_reblock_kernel<<<(nb + 127) / 128, 128>>>(raw, idx->blocks, nb);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { cudaFree(idx->blocks); free(idx); return fm_fail(e, "fm_reblock_kernel", __FILE__, __LINE__); }
+  *out = idx;
+  return FM_SUCCESS;
+}
+
+extern "C" int32_t fmgpu_index_create(int32_t device, uint32_t tag, uint32_t steps, uint32_t chunk, uint32_t bwtsize,
+                                      uint32_t ncounters, uint32_t nentries, const uint32_t *dpos, const uint32_t *dbase,
+                                      const uint32_t *h_entries, fmgpu_index_t **out)
+{
+  int32_t rc = fm_use_device(device);
+  if (rc) return rc;
+  if (!h_entries || !out || !dpos || !dbase) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
+  if (steps < 1 || steps > 2 || chunk == 0 || chunk % 32) return fm_fail_msg(FM_E_UNSUPPORTED_INDEX, "GPU search supports k in {1,2}, d multiple of 32");
+  const uint64_t bytes = (uint64_t) nentries * (2 * (chunk / 32) * steps + ncounters) * 4ull;
+  uint32_t *d_raw = NULL;
+  CU_TRY(cudaMalloc((void **) &d_raw, bytes));
+  cudaError_t e = cudaMemcpy(d_raw, h_entries, bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(d_raw); return fm_fail(e, "cudaMemcpy(index H2D)", __FILE__, __LINE__); }
+  rc = fm_index_from_device_entries(device, tag, steps, chunk, bwtsize, ncounters, nentries, dpos, dbase, d_raw, out);
+  cudaFree(d_raw);
+  return rc;
+}
+
+extern "C" int32_t fmgpu_index_create_from_device(int32_t device, uint32_t tag, uint32_t steps, uint32_t chunk, uint32_t bwtsize,
+                                                  uint32_t ncounters, uint32_t nentries, const uint32_t *dpos,
+                                                  const uint32_t *dbase, const uint32_t *d_entries, fmgpu_index_t **out)
+{
+  int32_t rc = fm_use_device(device);
+  if (rc) return rc;
+  if (!d_entries || !out || !dpos || !dbase) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
+  return fm_index_from_device_entries(device, tag, steps, chunk, bwtsize, ncounters, nentries, dpos, dbase, d_entries, out);
+}
+
+extern "C" int32_t fmgpu_index_alloc_like(int32_t device, const fmgpu_index_meta_t *meta, fmgpu_index_t **out)
+{
+  int32_t rc = fm_use_device(device);
+  if (rc) return rc;
+  if (!meta || !out) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
+  if (meta->nbytes != (uint64_t) meta->nsymbols * meta->nblocks * sizeof(uint4)) return fm_fail_msg(FM_E_BAD_ARGUMENT, "inconsistent index meta");
+  fmgpu_index_t *idx = (fmgpu_index_t *) calloc(1, sizeof(*idx));
+  if (!idx) return fm_fail_msg(FM_E_ALLOCATING_FMI, "host allocation failed");
+  idx->device = device; idx->meta = *meta;
+  cudaError_t e = cudaMalloc((void **) &idx->blocks, meta->nbytes);
+  if (e != cudaSuccess) { free(idx); return fm_fail(e, "cudaMalloc(SB96 replica)", __FILE__, __LINE__); }
+  *out = idx;
+  return FM_SUCCESS;
+}
+
+extern "C" int32_t fmgpu_index_replicate(const fmgpu_index_t *src, int32_t device, fmgpu_index_t **out)
+{
+  if (!src || !out) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
+  fmgpu_index_t *dst = NULL;
+  int32_t rc = fmgpu_index_alloc_like(device, &src->meta, &dst);
+  if (rc) return rc;
+  int can = 0;
+  cudaDeviceCanAccessPeer(&can, device, src->device);
+  if (can) { cudaError_t pe = cudaDeviceEnablePeerAccess(src->device, 0); if (pe != cudaSuccess) cudaGetLastError(); }
+  cudaError_t e = cudaMemcpyPeer(dst->blocks, device, src->blocks, src->device, src->meta.nbytes);
+  if (e != cudaSuccess) { cudaFree(dst->blocks); free(dst); return fm_fail(e, "cudaMemcpyPeer(index replica)", __FILE__, __LINE__); }
+  *out = dst;
+  return FM_SUCCESS;
+}
+
+extern "C" int32_t fmgpu_index_get_meta(const fmgpu_index_t *idx, fmgpu_index_meta_t *meta)
+{
+  if (!idx || !meta) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
+  *meta = idx->meta;
+  return FM_SUCCESS;
+}
+extern "C" void *fmgpu_index_blocks(const fmgpu_index_t *idx) { return idx ? (void *) idx->blocks : NULL; }
+extern "C" int32_t fmgpu_index_device(const fmgpu_index_t *idx) { return idx ? idx->device : -1; }
+
+extern "C" int32_t fmgpu_index_free(fmgpu_index_t **pidx)
+{
+  if (!pidx || !*pidx) return FM_SUCCESS;
+  fmgpu_index_t *idx = *pidx;
+  if (idx->blocks) { cudaSetDevice(idx->device); cudaFree(idx->blocks); }
+  free(idx);
+  *pidx = NULL;
+  return FM_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------ *
+ * kernel dispatch
+ * ------------------------------------------------------------------------ */
+typedef void (*fm_kernel_fn)(const FmSearchParams);
+
+template <int K, int QPT, int THREADS, int MINB>
+static fm_kernel_fn fm_pick_task(bool quirk, bool count)
+{
+  if (count) return quirk ? fm_search_task_kernel<K, QPT, THREADS, MINB, true, true> : fm_search_task_kernel<K, QPT, THREADS, MINB, false, true>;
+  return quirk ? fm_search_task_kernel<K, QPT, THREADS, MINB, true, false> : fm_search_task_kernel<K, QPT, THREADS, MINB, false, false>;
+}
+template <int K, int QPT, int THREADS, int MINB>
+static fm_kernel_fn fm_pick_coop(bool quirk)
+{
+  return quirk ? fm_search_coop_kernel<K, QPT, THREADS, MINB, true> : fm_search_coop_kernel<K, QPT, THREADS, MINB, false>;
+}
+
+/* register budgets: QPT=1 -> 32 regs (2048 thr/SM), QPT=2 -> 40, QPT=4 -> 64 */
+template <int K>
+static fm_kernel_fn fm_pick(int mode, int qpt, int tpb, bool quirk, bool count)
+{
+  if (mode == FMGPU_MODE_TASK) {
+    if (qpt == 1 && tpb == 128) return fm_pick_task<K, 1, 128, 16>(quirk, count);
+    if (qpt == 1 && tpb == 256) return fm_pick_task<K, 1, 256, 8>(quirk, count);
+    if (qpt == 1 && tpb == 512) return fm_pick_task<K, 1, 512, 4>(quirk, count);
+    if (qpt == 2 && tpb == 128) return fm_pick_task<K, 2, 128, 12>(quirk, count);
+    if (qpt == 2 && tpb == 256) return fm_pick_task<K, 2, 256, 6>(quirk, count);
+    if (qpt == 2 && tpb == 512) return fm_pick_task<K, 2, 512, 3>(quirk, count);
+    if (qpt == 4 && tpb == 128) return fm_pick_task<K, 4, 128, 8>(quirk, count);
+    if (qpt == 4 && tpb == 256) return fm_pick_task<K, 4, 256, 4>(quirk, count);
+    if (qpt == 4 && tpb == 512) return fm_pick_task<K, 4, 512, 2>(quirk, count);
+  } else if (mode == FMGPU_MODE_COOP && !count) {
+    if (qpt == 1 && tpb == 128) return fm_pick_coop<K, 1, 128, 16>(quirk);
+    if (qpt == 1 && tpb == 256) return fm_pick_coop<K, 1, 256, 8>(quirk);
+    if (qpt == 1 && tpb == 512) return fm_pick_coop<K, 1, 512, 4>(quirk);
+    if (qpt == 2 && tpb == 128) return fm_pick_coop<K, 2, 128, 16>(quirk);
+    if (qpt == 2 && tpb == 256) return fm_pick_coop<K, 2, 256, 8>(quirk);
+    if (qpt == 2 && tpb == 512) return fm_pick_coop<K, 2, 512, 4>(quirk);
+    if (qpt == 4 && tpb == 128) return fm_pick_coop<K, 4, 128, 12>(quirk);
+    if (qpt == 4 && tpb == 256) return fm_pick_coop<K, 4, 256, 6>(quirk);
+    if (qpt == 4 && tpb == 512) return fm_pick_coop<K, 4, 512, 3>(quirk);
+  }
+  return NULL;
+}
+
+static const fmgpu_variant_t FM_DEFAULT_VARIANT = { FMGPU_MODE_TASK, 2, 256, 0 };
+
+static int32_t fm_launch_search(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nq, uint32_t len,
+                                uint32_t *d_results, const fmgpu_variant_t *vin, cudaStream_t stream,
+                                unsigned long long *d_counters)
+{
+  if (!idx || !d_packed || !d_results) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
+  const uint32_t k = idx->meta.steps;
+  if (len == 0 || len % k) return fm_fail_msg(FM_E_QUERY_SHAPE, "read length must be a positive multiple of k (undefined in the reference, SURVEY.md App. C-5)");
+  if (nq == 0) return FM_SUCCESS;
+  if (nq >= (1ull << 31)) return fm_fail_msg(FM_E_BAD_ARGUMENT, "more than 2^31 reads in one launch; shard the batch");
+  fmgpu_variant_t v = vin ? *vin : FM_DEFAULT_VARIANT;
+  if (v.queries_per_thread == 0) v.queries_per_thread = FM_DEFAULT_VARIANT.queries_per_thread;
+  if (v.threads_per_block == 0) v.threads_per_block = FM_DEFAULT_VARIANT.threads_per_block;
+  const bool count = d_counters != NULL;
+  if (count) { v.mode = FMGPU_MODE_TASK; v.queries_per_thread = 1; v.threads_per_block = 256; }
+
+  FmSearchParams p;
+  p.blocks = idx->blocks; p.packed = d_packed; p.results = d_results; p.fetch_counters = d_counters;
+  p.nblocks = idx->meta.nblocks; p.nq = (uint32_t) nq; p.nsteps = len / k;
+  p.wpq = fmgpu_words_per_query(len); p.wpq_pad = p.wpq | 1u;
+  p.bwtsize = idx->meta.bwtsize; p.quirk_start = idx->meta.quirk_start; p.quirk_mask = idx->meta.quirk_mask;
+  const bool quirk = idx->meta.quirk_mask != 0;
+
+  /* shrink the CTA's read count until the staged reads fit in shared memory */
+  uint32_t qper; size_t smem;
+  for (;;) {
+    qper = (v.mode == FMGPU_MODE_COOP ? v.threads_per_block / 2 : v.threads_per_block) * v.queries_per_thread;
+    smem = (size_t) qper * p.wpq_pad * 4;
+    if (smem <= 200 * 1024) break;
+    if (v.queries_per_thread > 1) v.queries_per_thread /= 2;
+    else if (v.threads_per_block > 128) v.threads_per_block /= 2;
+    else return fm_fail_msg(FM_E_QUERY_SHAPE, "reads too long to stage in shared memory");
+  }
+  fm_kernel_fn fn = (k == 1) ? fm_pick<1>(v.mode, v.queries_per_thread, v.threads_per_block, quirk, count)
+                             : fm_pick<2>(v.mode, v.queries_per_thread, v.threads_per_block, quirk, count);
+  if (!fn) return fm_fail_msg(FM_E_BAD_ARGUMENT, "unsupported kernel variant (mode 0/1, queries_per_thread 1/2/4, threads_per_block 128/256/512)");
+  if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  const uint32_t grid = (uint32_t)((nq + qper - 1) / qper);
+  void *args[] = { (void *) &p };
+  CU_TRY(cudaLaunchKernel((const void *) fn, dim3(grid), dim3(v.threads_per_block), args, smem, stream));
+  return FM_SUCCESS;
+}
+
+extern "C" int32_t fmgpu_search_device(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nq, uint32_t len,
+                                       uint32_t *d_results, const fmgpu_variant_t *v, void *stream)
+{
+  if (!idx) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null index");
+  CU_TRY(cudaSetDevice(idx->device));
+  return fm_launch_search(idx, d_packed, nq, len, d_results, v, (cudaStream_t) stream, NULL);
+}
+
+extern "C" int32_t fmgpu_pack_queries_device(int32_t device, const char *d_ascii, uint64_t nq, uint32_t len,
+                                             uint32_t *d_packed, void *stream)
+{
+  if (!d_ascii || !d_packed || len == 0) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
+  CU_TRY(cudaSetDevice(device));
+  if (nq == 0) return FM_SUCCESS;
+  const uint32_t wpq = fmgpu_words_per_query(len);
+  const uint64_t total = nq * wpq;
+  if ((total + 255) / 256 >= (1ull << 31)) return fm_fail_msg(FM_E_BAD_ARGUMENT, "batch too large for one pack launch");
+  fm_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t) stream>>>(d_ascii, nq, len, wpq, d_packed);
+  CU_TRY(cudaGetLastError());
+  return FM_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------ *
+ * query shards
+ * ------------------------------------------------------------------------ */
+extern "C" int32_t fmgpu_batch_create(int32_t device, uint64_t nq, uint32_t len, uint32_t steps, fmgpu_batch_t **out)
+{
+  int32_t rc = fm_use_device(device);
+  if (rc) return rc;
+  if (!out || len == 0) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
+  fmgpu_batch_t *b = (fmgpu_batch_t *) calloc(1, sizeof(*b));
+  if (!b) return fm_fail_msg(FM_E_ALLOCATING_MFASTA, "host allocation failed");
+  b->device = device; b->nq = nq; b->len = len; b->steps = steps; b->wpq = fmgpu_words_per_query(len);
+  const size_t pw = (size_t)(nq ? nq : 1) * b->wpq * 4, rw = (size_t)(nq ? nq : 1) * 8;
+  cudaError_t e = cudaMalloc((void **) &b->d_packed, pw);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &b->d_results, rw);
+  if (e == cudaSuccess) e = cudaMemset(b->d_results, 0, rw);                 /* reference: cudaMemset of results */
+  if (e == cudaSuccess) e = cudaMalloc((void **) &b->d_counters, 16);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
+  if (e != cudaSuccess) { fmgpu_batch_free(&b); return fm_fail(e, "fmgpu_batch_create", __FILE__, __LINE__); }
+  *out = b;
+  return FM_SUCCESS;
+}
+
+extern "C" int32_t fmgpu_batch_upload_ascii(fmgpu_batch_t *b, const char *h_ascii)
+{
+  if (!b || !h_ascii) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
+  CU_TRY(cudaSetDevice(b->device));
+  if (b->nq == 0) return FM_SUCCESS;
+  /* staged in slices so the ASCII staging buffer stays small next to the packed shard */
+  const uint64_t slice = 4ull << 20;                                         /* reads per slice */
+  const uint64_t cap = b->nq < slice ? b->nq : slice;
+  if (!b->d_ascii) CU_TRY(cudaMalloc((void **) &b->d_ascii, cap * b->len));
+  for (uint64_t q0 = 0; q0 < b->nq; q0 += slice) {
+    const uint64_t n = (b->nq - q0 < slice) ? b->nq - q0 : slice;
+    CU_TRY(cudaMemcpyAsync(b->d_ascii, h_ascii + q0 * b->len, n * b->len, cudaMemcpyHostToDevice, b->stream));
+    int32_t rc = fmgpu_pack_queries_device(b->device, b->d_ascii, n, b->len, b->d_packed + q0 * b->wpq, b->stream);
+    if (rc) return rc;
+  }
+  CU_TRY(cudaStreamSynchronize(b->stream));
+  return FM_SUCCESS;
+}
+
+extern "C" int32_t fmgpu_batch_search(const fmgpu_index_t *idx, fmgpu_batch_t *b, const fmgpu_variant_t *v)
+{
+  if (!idx || !b) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
+  if (idx->device != b->device) return fm_fail_msg(FM_E_BAD_ARGUMENT, "index replica and shard live on different devices");
+  CU_TRY(cudaSetDevice(b->device));
+  return fm_launch_search(idx, b->d_packed, b->nq, b->len, b->d_results, v, b->stream, NULL);
+}
+
+extern "C" int32_t fmgpu_batch_sync(fmgpu_batch_t *b)
+{
+  if (!b) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
+  CU_TRY(cudaSetDevice(b->device));
+  CU_TRY(cudaStreamSynchronize(b->stream));
+  return FM_SUCCESS;
+}
+
+extern "C" int32_t fmgpu_batch_download(fmgpu_batch_t *b, uint32_t *h_results)
+{
+  if (!b || !h_results) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
+  CU_TRY(cudaSetDevice(b->device));
+  if (b->nq) CU_TRY(cudaMemcpyAsync(h_results, b->d_results, b->nq * 8, cudaMemcpyDeviceToHost, b->stream));
+  CU_TRY(cudaStreamSynchronize(b->stream));
+  return FM_SUCCESS;
+}
+
+extern "C" int32_t fmgpu_batch_search_timed(const fmgpu_index_t *idx, fmgpu_batch_t *b, const fmgpu_variant_t *v,
+                                            int32_t iters, float *ms_per_iter)
+{
+  if (!idx || !b || !ms_per_iter || iters < 1) return fm_fail_msg(FM_E_BAD_ARGUMENT, "bad argument");
+  CU_TRY(cudaSetDevice(b->device));
+  CU_TRY(cudaEventRecord(b->ev0, b->stream));
+  for (int i = 0; i < iters; i++) {
+    int32_t rc = fmgpu_batch_search(idx, b, v);
+    if (rc) return rc;
+  }
+  CU_TRY(cudaEventRecord(b->ev1, b->stream));
+  CU_TRY(cudaEventSynchronize(b->ev1));
+  float ms = 0.f;
+  CU_TRY(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+  *ms_per_iter = ms / (float) iters;
+  return FM_SUCCESS;
+}
+
+extern "C" int32_t fmgpu_batch_count_fetches(const fmgpu_index_t *idx, fmgpu_batch_t *b, uint64_t *nblocks, uint64_t *nsectors)
+{
+  if (!idx || !b) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
+  if (idx->device != b->device) return fm_fail_msg(FM_E_BAD_ARGUMENT, "index replica and shard live on different devices");
+  CU_TRY(cudaSetDevice(b->device));
+  CU_TRY(cudaMemsetAsync(b->d_counters, 0, 16, b->stream));
+  int32_t rc = fm_launch_search(idx, b->d_packed, b->nq, b->len, b->d_results, NULL, b->stream, b->d_counters);
+  if (rc) return rc;
+  unsigned long long h[2] = { 0, 0 };
+  CU_TRY(cudaMemcpyAsync(h, b->d_counters, 16, cudaMemcpyDeviceToHost, b->stream));
+  CU_TRY(cudaStreamSynchronize(b->stream));
+  if (nblocks) *nblocks = h[0];
+  if (nsectors) *nsectors = h[1];
+  return FM_SUCCESS;
+}
+
+extern "C" void *fmgpu_batch_packed(const fmgpu_batch_t *b)  { return b ? (void *) b->d_packed : NULL; }
+extern "C" void *fmgpu_batch_results(const fmgpu_batch_t *b) { return b ? (void *) b->d_results : NULL; }
+extern "C" void *fmgpu_batch_stream(const fmgpu_batch_t *b)  { return b ? (void *) b->stream : NULL; }
+
+extern "C" int32_t fmgpu_batch_free(fmgpu_batch_t **pb)
+{
+  if (!pb || !*pb) return FM_SUCCESS;
+  fmgpu_batch_t *b = *pb;
+  cudaSetDevice(b->device);
+  if (b->d_ascii) cudaFree(b->d_ascii);
+  if (b->d_packed) cudaFree(b->d_packed);
+  if (b->d_results) cudaFree(b->d_results);
+  if (b->d_counters) cudaFree(b->d_counters);
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  free(b);
+  *pb = NULL;
+  return FM_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------ *
+ * end to end, host buffers in and out: chunks of the batch flow through
+ * H2D -> pack -> search -> D2H on FM_PIPE_STREAMS streams per GPU so the
+ * PCIe copies of one chunk overlap the kernels of another.
+ * ------------------------------------------------------------------------ */
+#define FM_PIPE_STREAMS 3
+#define FM_MAX_DEVICES  16
+
+struct fm_pipe_lane {
+  cudaStream_t stream;
+  char     *d_ascii;
+  uint32_t *d_packed;
+  uint32_t *d_results;
+  size_t    cap_ascii, cap_packed, cap_results;
+};
+static fm_pipe_lane g_pipe[FM_MAX_DEVICES][FM_PIPE_STREAMS];
+
+static int32_t fm_pipe_reserve(int device, fm_pipe_lane *ln, size_t ascii, size_t packed, size_t results)
+{
+  CU_TRY(cudaSetDevice(device));
+  if (!ln->stream) CU_TRY(cudaStreamCreateWithFlags(&ln->stream, cudaStreamNonBlocking));
+  if (ln->cap_ascii < ascii)     { if (ln->d_ascii) cudaFree(ln->d_ascii);     ln->cap_ascii = 0;   CU_TRY(cudaMalloc((void **) &ln->d_ascii, ascii));     ln->cap_ascii = ascii; }
+  if (ln->cap_packed < packed)   { if (ln->d_packed) cudaFree(ln->d_packed);   ln->cap_packed = 0;  CU_TRY(cudaMalloc((void **) &ln->d_packed, packed));   ln->cap_packed = packed; }
+  if (ln->cap_results < results) { if (ln->d_results) cudaFree(ln->d_results); ln->cap_results = 0; CU_TRY(cudaMalloc((void **) &ln->d_results, results)); ln->cap_results = results; }
+  return FM_SUCCESS;
+}
+
+extern "C" int32_t fmgpu_search_host(fmgpu_index_t *const *replicas, int32_t nrep, const char *h_ascii, uint64_t nq,
+                                     uint32_t len, uint32_t *h_results, const fmgpu_variant_t *v)
+{
+  if (!replicas || nrep < 1 || nrep > FM_MAX_DEVICES || !h_ascii || !h_results || len == 0) return fm_fail_msg(FM_E_BAD_ARGUMENT, "bad argument");
+  for (int g = 0; g < nrep; g++)
+    if (!replicas[g] || replicas[g]->device < 0 || replicas[g]->device >= FM_MAX_DEVICES) return fm_fail_msg(FM_E_BAD_ARGUMENT, "bad replica");
+  if (len % replicas[0]->meta.steps) return fm_fail_msg(FM_E_QUERY_SHAPE, "read length must be a multiple of k");
+  if (nq == 0) return FM_SUCCESS;
+  const uint32_t wpq = fmgpu_words_per_query(len);
+  /* chunk: about 1 M reads, 32-aligned; small batches still get one chunk per lane */
+  uint64_t chunk = 1ull << 20;
+  const uint64_t lanes = (uint64_t) nrep * FM_PIPE_STREAMS;
+  if (nq < chunk * lanes) chunk = ((nq + lanes - 1) / lanes + 31) & ~31ull;
+  if (chunk == 0) chunk = 32;
+  for (int g = 0; g < nrep; g++)
+    for (int s = 0; s < FM_PIPE_STREAMS; s++) {
+      int32_t rc = fm_pipe_reserve(replicas[g]->device, &g_pipe[replicas[g]->device][s], chunk * len, chunk * wpq * 4, chunk * 8);
+      if (rc) return rc;
+    }
+  uint64_t c = 0;
+  for (uint64_t q0 = 0; q0 < nq; q0 += chunk, c++) {
+    const uint64_t n = (nq - q0 < chunk) ? nq - q0 : chunk;
+    const int g = (int)(c % nrep), s = (int)((c / nrep) % FM_PIPE_STREAMS);
+    const fmgpu_index_t *idx = replicas[g];
+    fm_pipe_lane *ln = &g_pipe[idx->device][s];
+    CU_TRY(cudaSetDevice(idx->device));
+    CU_TRY(cudaMemcpyAsync(ln->d_ascii, h_ascii + q0 * len, n * len, cudaMemcpyHostToDevice, ln->stream));
+    int32_t rc = fmgpu_pack_queries_device(idx->device, ln->d_ascii, n, len, ln->d_packed, ln->stream);
+    if (rc) return rc;
+    rc = fm_launch_search(idx, ln->d_packed, n, len, ln->d_results, v, ln->stream, NULL);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(h_results + 2 * q0, ln->d_results, n * 8, cudaMemcpyDeviceToHost, ln->stream));
+  }
+  for (int g = 0; g < nrep; g++) {
+    CU_TRY(cudaSetDevice(replicas[g]->device));
+    for (int s = 0; s < FM_PIPE_STREAMS; s++) CU_TRY(cudaStreamSynchronize(g_pipe[replicas[g]->device][s].stream));
+  }
+  return FM_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------ */
+/* page-aligned host memory, pinned when a CUDA device is there to pin it for
+ * (on a box without a GPU the loaders still work; nothing can be searched) */
+extern "C" void *fmgpu_host_alloc(size_t bytes)
+{
+  void *p = NULL;
+  if (posix_memalign(&p, 4096, bytes ? bytes : 1) != 0) return NULL;
+  if (cudaHostRegister(p, bytes ? bytes : 1, cudaHostRegisterPortable) != cudaSuccess) cudaGetLastError();
+  return p;
+}
+extern "C" void fmgpu_host_free(void *p)
+{
+  if (!p) return;
+  if (cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
+  free(p);
+}
+extern "C" int32_t fmgpu_host_register(void *p, size_t bytes)
+{
+  CU_TRY(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+  return FM_SUCCESS;
+}
+extern "C" int32_t fmgpu_host_unregister(void *p)
+{
+  CU_TRY(cudaHostUnregister(p));
+  return FM_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------ */
+extern "C" int32_t fmgpu_gather_probe(int32_t device, uint64_t table_bytes, uint64_t loads_per_thread, int32_t iters,
+                                      double *loads_per_second)
+{
+  int32_t rc = fm_use_device(device);
+  if (rc) return rc;
+  if (!loads_per_second || table_bytes < 4096 || iters < 1) return fm_fail_msg(FM_E_BAD_ARGUMENT, "bad argument");
+  const uint64_t n16 = table_bytes / 16;
+  uint4 *table = NULL; uint32_t *sink = NULL;
+  CU_TRY(cudaMalloc((void **) &table, n16 * 16));
+  CU_TRY(cudaMalloc((void **) &sink, 4));
+  CU_TRY(cudaMemset(table, 0x5A, n16 * 16));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const uint32_t lpt = (uint32_t)((loads_per_thread + 3) & ~3ull);
+  const uint32_t grid = (uint32_t) sms * 8 * 4;                    /* 4 waves of 8 CTAs per SM */
+  cudaEvent_t e0, e1;
+  CU_TRY(cudaEventCreate(&e0)); CU_TRY(cudaEventCreate(&e1));
+  fm_gather_probe_kernel<4><<<grid, 256>>>(table, n16, lpt, sink);  /* warm-up */
+  CU_TRY(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int i = 0; i < iters; i++) {
+    CU_TRY(cudaEventRecord(e0));
+    fm_gather_probe_kernel<4><<<grid, 256>>>(table, n16, lpt, sink);
+    CU_TRY(cudaEventRecord(e1));
+    CU_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  *loads_per_second = (double) grid * 256.0 * lpt / (best * 1e-3);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(table); cudaFree(sink);
+  return FM_SUCCESS;
+}

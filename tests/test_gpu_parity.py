@@ -1,0 +1,264 @@
+"""GPU parity tests (run with -m gpu on a B200).  Everything goes through the C ABI of
+libfmindex_b200.so; the checker is the C oracle, the committed reference outputs, and the reference CPU
+searcher itself run in-process from oracle/_ref.  Integer work: the bar is bit-exact."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(helpers.ROOT, "tests", "golden", "*.npz")))
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+@pytest.fixture(scope="module")
+def pkg(built):
+    p = helpers.pkg()
+    assert p.lib().fmgpu_device_count() >= 1, "no sm_100 GPU: the product has no CPU fallback"
+    return p
+
+
+def gpu_search(pkg, image, reads, length, var=None, device=0):
+    idx = pkg.DeviceIndex.from_image(image, device=device)
+    k = int(image[1])
+    b = pkg.DeviceBatch(device, reads.size // length, length, k)
+    b.upload_ascii(reads)
+    b.search(idx, var)
+    out = b.download()
+    b.free(); idx.free()
+    return out
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_golden_all_tags_all_variants(pkg, path):
+    """Committed outputs of the unmodified reference searchers, incl. the AltCounters quirk fixtures."""
+    g = np.load(path)
+    reads, length, k = g["reads"], int(g["length"]), int(g["k"])
+    nq = reads.size // length
+    for tag, key in ((100, "expected_std"), (101, "expected_std"), (200, "expected_ac"), (201, "expected_ac")):
+        idx = pkg.DeviceIndex.from_image(g[f"image_{tag}"])
+        b = pkg.DeviceBatch(0, nq, length, k)
+        b.upload_ascii(reads)
+        for mode in (pkg.MODE_TASK, pkg.MODE_COOP):
+            for qpt in (1, 2, 4):
+                for tpb in (128, 256, 512):
+                    b.search(idx, pkg.variant(mode, qpt, tpb))
+                    assert np.array_equal(b.download(), g[key]), f"tag {tag} mode {mode} qpt {qpt} tpb {tpb}"
+        b.free(); idx.free()
+
+
+def test_quirk_metadata(pkg):
+    """AltCounters padding-entry quirk is detected only for AC files whose '$' row is in the last chunk."""
+    g = np.load(os.path.join(helpers.ROOT, "tests", "golden", "quirk_k2_n124.npz"))
+    i_std = pkg.DeviceIndex.from_image(g["image_100"]); i_ac = pkg.DeviceIndex.from_image(g["image_201"])
+    assert i_std.meta.quirk_mask == 0 and i_std.meta.quirk_start == 0xFFFFFFFF
+    assert i_ac.meta.quirk_mask != 0 and i_ac.meta.quirk_start == 64
+    g2 = np.load(os.path.join(helpers.ROOT, "tests", "golden", "small_k2_d64.npz"))
+    i2 = pkg.DeviceIndex.from_image(g2["image_200"])
+    assert i2.meta.quirk_mask == 0
+    m = i2.meta
+    assert m.nsymbols == 16 and m.nblocks % 8 == 0 and m.nblocks >= m.bwtsize // 96 + 1
+    assert m.nbytes == 16 * m.nsymbols * m.nblocks
+    for i in (i_std, i_ac, i2):
+        i.free()
+
+
+@pytest.mark.skipif(not helpers.has_ref_tools(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("k,d", [(1, 32), (1, 64), (1, 128), (2, 32), (2, 64), (2, 128)])
+def test_fresh_data_vs_reference_searcher(pkg, tmp_path, k, d):
+    """Fresh seeded text, reference index builder + transformers, reference CPU searcher in-process."""
+    n = 300_007 + 64 * d
+    text = helpers.synth_text(n, seed=40 + k + d)
+    paths = helpers.build_reference_indexes(str(tmp_path), text, k, d)
+    length = 48
+    rng = np.random.default_rng(d)
+    reads = np.concatenate([helpers.synth_reads(text, 6, 20_000, length), text[:length], text[-length:],
+                            ACGT[rng.integers(0, 4, 2_000 * length)]])
+    for ac, tags in ((False, (100, 101)), (True, (200, 201))):
+        ref = helpers.RefSearcher(k, d, ac)
+        want, _ = ref.search(ref.load(paths[tags[0]]), reads, length)
+        for tag in tags:
+            image = np.fromfile(paths[tag], dtype=np.uint32)
+            for mode in (pkg.MODE_TASK, pkg.MODE_COOP):
+                got = gpu_search(pkg, image, reads, length, pkg.variant(mode))
+                assert np.array_equal(got, want), f"k={k} d={d} tag={tag} mode={mode}"
+
+
+@pytest.mark.parametrize("k,length", [(1, 1), (1, 15), (1, 16), (1, 17), (1, 33), (1, 100), (2, 2), (2, 16), (2, 30),
+                                      (2, 32), (2, 34), (2, 100), (2, 128), (2, 250), (1, 250), (2, 1000)])
+def test_read_lengths(pkg, k, length):
+    """Word boundaries of the 2-bit packing (16 bases/word), even word counts (bank padding), long reads."""
+    g = np.load(os.path.join(helpers.ROOT, "tests", "golden", f"small_k{k}_d64.npz"))
+    text = helpers.synth_text(int(g["n"]), seed=7 + k)
+    reads = np.concatenate([helpers.synth_reads(text, 21, 700, length), ACGT[np.random.default_rng(length).integers(0, 4, 68 * length)]])
+    o = helpers.Oracle()
+    for tag in (100, 201):
+        h = o.wrap(g[f"image_{tag}"])
+        want = o.search(h, reads, length)
+        o.free(h)
+        for mode in (pkg.MODE_TASK, pkg.MODE_COOP):
+            for qpt in (1, 4):
+                got = gpu_search(pkg, g[f"image_{tag}"], reads, length, pkg.variant(mode, qpt, 256))
+                assert np.array_equal(got, want), f"k={k} len={length} tag={tag} mode={mode} qpt={qpt}"
+
+
+@pytest.mark.parametrize("nq", [0, 1, 2, 31, 32, 33, 255, 257, 1025])
+def test_ragged_batches(pkg, nq):
+    """Empty and ragged batches (the reference requires num % 32 == 0, common/common.c:143-153)."""
+    g = np.load(os.path.join(helpers.ROOT, "tests", "golden", "small_k2_d64.npz"))
+    length = int(g["length"])
+    reads = g["reads"][: nq * length]
+    want = g["expected_std"][: 2 * nq]
+    for mode in (pkg.MODE_TASK, pkg.MODE_COOP):
+        got = gpu_search(pkg, g["image_101"], reads, length, pkg.variant(mode, 2, 128))
+        assert np.array_equal(got, want)
+
+
+def test_dropin_file_flow_and_logical_shards(pkg, tmp_path):
+    """loadIndex / loadQueries / initResults / transferCPUtoGPU / searchIndexGPU / transferGPUtoCPU /
+    saveResults through files, with the batch sharded over 1, 2 and 3 replicas (all on GPU 0 when the box
+    has one GPU): the result must not depend on the shard count."""
+    g = np.load(os.path.join(helpers.ROOT, "tests", "golden", "small_k2_d64.npz"))
+    length = int(g["length"])
+    nq = 2001                                                   # ragged on purpose
+    reads = g["reads"][: nq * length]
+    qfa = str(tmp_path / "q.fa")
+    helpers.write_fasta_reads(qfa, reads, length)
+    ndev = pkg.lib().fmgpu_device_count()
+    for tag, key in ((100, "expected_std"), (200, "expected_ac")):
+        fn = str(tmp_path / f"i{tag}.fmi")
+        g[f"image_{tag}"].tofile(fn)
+        for shards in (1, 2, 3):
+            devices = [i % ndev for i in range(shards)]
+            got = pkg.search_files(fn, qfa, length, nq, devices=devices, var=pkg.variant(pkg.MODE_COOP if shards == 2 else pkg.MODE_TASK))
+            assert np.array_equal(got, g[key][: 2 * nq]), f"tag {tag} shards {shards}"
+    # the reference-shaped driver binary writes the reference's text format
+    exe = os.path.join(helpers.ROOT, helpers.PKG_NAME, "bin", "fmIndexSearchGPU_b200")
+    out = helpers.run([exe, fn, qfa, str(length), str(nq)])
+    assert "TIME:" in out
+    txt = open(fn + ".res.gpu").read().split("\n")
+    assert txt[0] == str(nq)
+    flat = np.array([int(v) for line in txt[1:nq + 1] for v in line.split()], dtype=np.uint32)
+    assert np.array_equal(flat, g["expected_ac"][: 2 * nq])
+
+
+def test_end_to_end_host_pipeline(pkg):
+    """fmgpu_search_host: host ASCII in, host (L,R) out, chunks overlapped on several streams."""
+    g = np.load(os.path.join(helpers.ROOT, "tests", "golden", "small_k2_d64.npz"))
+    length = int(g["length"])
+    reps = np.tile(g["reads"], 40)                              # ~85k reads
+    want = np.tile(g["expected_std"], 40)
+    idx = pkg.DeviceIndex.from_image(g["image_100"])
+    got = pkg.search_host([idx], reps, length)
+    assert np.array_equal(got, want)
+    rep2 = idx.replicate(0)                                      # second replica (same GPU) = second shard lane
+    got2 = pkg.search_host([idx, rep2], reps[: 1000 * length], length, pkg.variant(pkg.MODE_COOP))
+    assert np.array_equal(got2, want[:2000])
+    rep2.free(); idx.free()
+
+
+def test_pack_kernel_bit_layout(pkg):
+    """Reversed 2-bit packing: field s of the packed read is the k-step symbol of LF step s."""
+    import torch
+    length, nq = 37, 50
+    rng = np.random.default_rng(1)
+    reads = np.frombuffer(b"ACGTacgtN", dtype=np.uint8)[rng.integers(0, 9, nq * length)]
+    d_ascii = torch.from_numpy(reads.copy()).cuda()
+    wpq = pkg.lib().fmgpu_words_per_query(length)
+    assert wpq == 3
+    d_packed = torch.zeros(nq * wpq, dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    pkg.check(pkg.lib().fmgpu_pack_queries_device(0, d_ascii.data_ptr(), nq, length, d_packed.data_ptr(), s), "pack")
+    torch.cuda.synchronize()
+    got = d_packed.cpu().numpy().view(np.uint32).reshape(nq, wpq)
+    code = lambda c: (((c >> 2) & 1) << 1) | (((c >> 2) & 1) ^ ((c >> 1) & 1))
+    r = reads.reshape(nq, length).astype(np.uint32)
+    want = np.zeros((nq, wpq), dtype=np.uint32)
+    for t in range(length):
+        want[:, t // 16] |= code(r[:, length - 1 - t]) << np.uint32(2 * (t % 16))
+    assert np.array_equal(got, want)
+
+
+def test_fetch_counter_matches_oracle(pkg):
+    """The in-kernel count of necessary block / sector fetches (algorithmic bytes of the roofline) equals the
+    oracle's instrumented walk."""
+    g = np.load(os.path.join(helpers.ROOT, "tests", "golden", "small_k2_d64.npz"))
+    length, reads = int(g["length"]), g["reads"]
+    o = helpers.Oracle()
+    h = o.wrap(g["image_100"])
+    idx = pkg.DeviceIndex.from_image(g["image_100"])
+    b = pkg.DeviceBatch(0, reads.size // length, length, 2)
+    b.upload_ascii(reads)
+    nb, ns = b.count_fetches(idx)
+    assert nb == o.count_sectors(h, reads, length, 96, 1)
+    assert ns == o.count_sectors(h, reads, length, 96, 2)
+    assert np.array_equal(b.download(), g["expected_std"])     # the counting variant is still a correct search
+    b.free(); idx.free(); o.free(h)
+
+
+def test_error_paths(pkg):
+    g = np.load(os.path.join(helpers.ROOT, "tests", "golden", "small_k2_d64.npz"))
+    idx = pkg.DeviceIndex.from_image(g["image_100"])
+    b = pkg.DeviceBatch(0, 10, 31, 2)                           # odd length at k=2: undefined in the reference
+    b.upload_ascii(g["reads"][: 310])
+    with pytest.raises(pkg.FMError) as ei:
+        b.search(idx)
+    assert ei.value.code == pkg.FM_E_QUERY_SHAPE
+    with pytest.raises(pkg.FMError) as ei:
+        b.search(idx, pkg.variant(pkg.MODE_TASK, 3, 256))
+    assert ei.value.code == pkg.FM_E_BAD_ARGUMENT
+    b.free()
+    bad = g["image_100"].copy(); bad[1] = 3; bad[3] = 64         # k = 3: CPU-only in the reference too
+    with pytest.raises(pkg.FMError) as ei:
+        pkg.DeviceIndex.from_image(bad)
+    assert ei.value.code == pkg.FM_E_UNSUPPORTED_INDEX
+    bad = g["image_100"].copy(); bad[4] += 1                     # entry count inconsistent with bwtsize/d
+    with pytest.raises(pkg.FMError):
+        pkg.DeviceIndex.from_image(bad)
+    idx.free()
+
+
+@pytest.mark.skipif(not helpers.has_ref_tools(), reason="oracle/_ref not built")
+def test_bwtsize_multiple_of_d(pkg, tmp_path):
+    """bwtsize % d == 0 makes the reference read past its last entry.  The device
+    layout carries a block for X = bwtsize; result = the oracle's defined extension, and no fault."""
+    n = 64 * 40 - 1
+    text = helpers.synth_text(n, seed=77)
+    paths = helpers.build_reference_indexes(str(tmp_path), text, 2, 64)
+    reads = helpers.synth_reads(text, 3, 512, 12)
+    o = helpers.Oracle()
+    h = o.load(paths[100])
+    want = o.search(h, reads, 12)
+    o.free(h)
+    got = gpu_search(pkg, np.fromfile(paths[100], dtype=np.uint32), reads, 12)
+    assert np.array_equal(got, want)
+    assert ((got[1::2] - got[0::2]) >= 1).all()
+
+
+@pytest.mark.skipif(not helpers.has_ref_tools(), reason="oracle/_ref not built")
+def test_config2_full_size(pkg, tmp_path):
+    """BASELINE config 2: 4 Mbp index, 2-step, AltCounters layout, 1M 100-bp reads on one B200, bit-exact vs
+    the reference CPU searchers (std and AC), Task and Coop kernels; checksum of the first 100k pinned."""
+    n, nq, length = 4_000_000, 1_000_000, 100
+    text = helpers.synth_text(n, seed=1)
+    reads = helpers.synth_reads(text, 2, nq, length)
+    paths = helpers.build_reference_indexes(str(tmp_path), text, 2, 64)
+    pinned = open(os.path.join(helpers.ROOT, "tests", "golden", "config1_100k.md5")).read().split()[0]
+    for ac, tags in ((False, (100, 101)), (True, (200, 201))):
+        ref = helpers.RefSearcher(2, 64, ac)
+        want, _ = ref.search(ref.load(paths[tags[0]]), reads, length)
+        assert helpers.results_text_md5(want[:200_000]) == pinned
+        for tag in tags:
+            image = np.fromfile(paths[tag], dtype=np.uint32)
+            for mode in (pkg.MODE_TASK, pkg.MODE_COOP):
+                got = gpu_search(pkg, image, reads, length, pkg.variant(mode))
+                assert np.array_equal(got, want), f"tag {tag} mode {mode}"
+    # 1-step index of the same text gives the same intervals (survey's G1 invariant)
+    p1 = helpers.build_reference_indexes(str(tmp_path / "k1"), text, 1, 64)
+    got1 = gpu_search(pkg, np.fromfile(p1[101], dtype=np.uint32), reads, length)
+    assert np.array_equal(got1, want)

@@ -1,0 +1,128 @@
+"""CPU tests of the host layer: the C-ABI library loads, exports every declared symbol, and the file
+readers/writers keep the reference's formats and error behaviour (no compute calls: no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import helpers
+
+
+def test_library_exports_every_declared_symbol(built):
+    pkg = helpers.pkg()
+    L = pkg.lib()
+    header = open(os.path.join(helpers.ROOT, "include", "fmindex_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{}]*\)\s*;", header))
+    declared -= {"defined"}
+    assert len(declared) >= 45
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/fmindex_b200.h but not exported"
+        assert name in pkg.PROTOTYPES, f"{name} has no ctypes prototype"
+    assert not hasattr(L, "searchIndexCPU"), "the product must not carry a CPU search path"
+
+
+def test_no_oracle_in_product(built):
+    """The product library must not link or reference anything under oracle/."""
+    pkg = helpers.pkg()
+    out = helpers.run(["nm", "-D", pkg.LIB_PATH])
+    assert "fmo_" not in out and "ref_search_parallel" not in out
+    for root, _, files in os.walk(os.path.join(helpers.ROOT, helpers.PKG_NAME)):
+        for f in files:
+            if f.endswith((".c", ".cu", ".cuh", ".h", ".py")):
+                src = open(os.path.join(root, f), errors="ignore").read()
+                assert "fm_oracle" not in src and "liboracle" not in src and "oracle/" not in src.replace("oracle/_ref", ""), f
+
+
+@pytest.mark.parametrize("fixture", ["small_k1_d64", "small_k2_d64", "small_k2_d128"])
+def test_load_index_all_tags(built, tmp_path, fixture):
+    pkg = helpers.pkg()
+    g = np.load(os.path.join(helpers.ROOT, "tests", "golden", fixture + ".npz"))
+    for tag in (100, 101, 200, 201):
+        im = g[f"image_{tag}"]
+        fn = str(tmp_path / f"x{tag}.fmi")
+        im.tofile(fn)
+        h = pkg.loadIndex(fn)
+        f = pkg.index_fields(h)
+        k = int(g["k"])
+        assert (f.tag, f.steps, f.bwtsize, f.chunk) == (tag, k, int(g["n"]) + 1, int(g["d"]))
+        assert f.ncounters == (4 ** k) // (2 if tag >= 200 else 1)
+        assert f.nentries == -(-f.bwtsize // f.chunk) + (1 if tag >= 200 else 0)
+        assert [f.h_dollarPositionBWT[i] for i in range(k)] == [int(v) for v in im[6:6 + k]]
+        assert [f.h_modposdollarBWT[i] for i in range(k)] == [int(v) // f.chunk for v in im[6:6 + k]]
+        raw = np.ctypeslib.as_array(C.cast(f.h_index, C.POINTER(C.c_uint32)), shape=(f.nentries * f.entry_words,))
+        assert np.array_equal(raw, im[6 + 2 * k:])
+        pkg.lib().freeIndex(C.byref(h))
+        assert pkg.index_fields(h).h_index is None
+
+
+def test_load_index_errors(built, tmp_path):
+    pkg = helpers.pkg()
+    L = pkg.lib()
+    h = C.c_void_p()
+    assert L.loadIndex(b"/nonexistent/file.fmi", C.byref(h)) == 1          # E_OPENING_INDEX_FILE
+    bad = tmp_path / "bad.fmi"
+    np.array([777, 1, 100, 4, 2, 64, 0, 0], dtype=np.uint32).tofile(bad)
+    assert L.loadIndex(os.fsencode(str(bad)), C.byref(h)) == 100             # wrong type -> "use gfmiBaseLine"
+    assert b"gfmiBaseLine" in L.errorCommon(100)
+    trunc = tmp_path / "trunc.fmi"
+    np.array([100, 1, 1000, 4, 16, 64, 5, 0, 1, 2, 3], dtype=np.uint32).tofile(trunc)
+    assert L.loadIndex(os.fsencode(str(trunc)), C.byref(h)) == 5            # E_READING_FMI
+    short = tmp_path / "short.fmi"
+    np.array([100, 1], dtype=np.uint32).tofile(short)
+    assert L.loadIndex(os.fsencode(str(short)), C.byref(h)) == 5
+    assert L.errorCommon(0) == b"No error" and L.errorCommon(19) == b"Not implemented"
+    assert b"tfmiAC" in L.errorCommon(201) and L.errorCommon(12345) == b"Unknown error"
+
+
+def test_load_queries_and_results_roundtrip(built, tmp_path):
+    pkg = helpers.pkg()
+    L = pkg.lib()
+    text = helpers.synth_text(5000, 3)
+    reads = helpers.synth_reads(text, 8, 37, 20)                # 37: not a multiple of 32 (ragged batch)
+    fa = str(tmp_path / "q.fa")
+    helpers.write_fasta_reads(fa, reads, 20)
+    q = pkg.loadQueries(fa, 20, 37)
+    qs = C.cast(q, C.POINTER(pkg.qrys_t)).contents
+    assert (qs.num, qs.size) == (37, 20)
+    got = np.ctypeslib.as_array(C.cast(qs.h_queries, C.POINTER(C.c_uint8)), shape=(37 * 20,))
+    assert np.array_equal(got, reads)
+    L.freeQueries(C.byref(q))
+    # wrong length / too few reads are errors, not a silent mis-stride
+    h = C.c_void_p()
+    assert L.loadQueries(os.fsencode(fa), 21, 37, C.byref(h)) == 12
+    assert L.loadQueries(os.fsencode(fa), 20, 38, C.byref(h)) == 12
+    assert L.loadQueries(b"/nonexistent.fa", 20, 1, C.byref(h)) == 14
+
+    r = pkg.initResults(5)
+    arr = pkg.resultsArray(r, copy=False)
+    assert arr.shape == (10,) and (arr == 0).all()
+    arr[:] = np.array([1, 2, 30, 40, 0, 0, 4294967295, 7, 5, 5], dtype=np.uint32)
+    out = str(tmp_path / "idx")
+    assert L.saveResults(os.fsencode(out), r, None) == 0
+    assert open(out + ".res.gpu").read() == "5\n1 2\n30 40\n0 0\n4294967295 7\n5 5\n"
+    back = C.c_void_p()
+    assert L.loadResults(os.fsencode(out + ".res.gpu"), C.byref(back)) == 0
+    assert np.array_equal(pkg.resultsArray(back), arr)
+    L.freeResults(C.byref(r)); L.freeResults(C.byref(back))
+    e = C.c_void_p()
+    assert L.initResults(0, C.byref(e)) == 0                    # empty batch
+    assert pkg.resultsArray(e).size == 0
+
+
+def test_device_entry_points_fail_loudly_without_gpu(built):
+    """No CPU fallback: on a box without an sm_100 device the GPU entry points return FM_E_CUDA."""
+    pkg = helpers.pkg()
+    L = pkg.lib()
+    if L.fmgpu_device_count() > 0:
+        pytest.skip("a GPU is present")
+    g = np.load(os.path.join(helpers.ROOT, "tests", "golden", "small_k2_d64.npz"))
+    with pytest.raises(pkg.FMError) as ei:
+        pkg.DeviceIndex.from_image(g["image_100"], device=0)
+    assert ei.value.code == pkg.FM_E_CUDA
+    h = C.c_void_p()
+    assert L.fmgpu_batch_create(0, 32, 32, 2, C.byref(h)) == pkg.FM_E_CUDA
+    v = C.c_double()
+    assert L.fmgpu_gather_probe(0, 1 << 20, 16, 1, C.byref(v)) == pkg.FM_E_CUDA
