@@ -260,6 +260,25 @@ void    fmgpu_host_free(void *p);
 int32_t fmgpu_host_register(void *p, size_t bytes);
 int32_t fmgpu_host_unregister(void *p);
 
+/* index construction on the GPU -------------------
+ * Builds, on `device`, the image of the reference's tag-100 ".fmi" FILE
+ * (header + entries, byte-identical to what genFMindex writes,
+ * src/genFMindex.c:155-181,457-543) for an ASCII text or for the synthetic
+ * text of fm_synth.h.  k in {1,2}.  Fails with FM_E_BUILDING_BWT on texts with
+ * long repeats (more than 2048 suffixes sharing 32 bases). */
+typedef struct fmgpu_build fmgpu_build_t;
+int32_t  fmgpu_build_from_text(int32_t device, const char *h_ascii, uint64_t n, uint32_t steps, uint32_t chunk, fmgpu_build_t **out);
+int32_t  fmgpu_build_from_synth(int32_t device, uint64_t n, uint64_t seed, uint32_t steps, uint32_t chunk, fmgpu_build_t **out);
+uint64_t fmgpu_build_image_words(const fmgpu_build_t *b);
+void    *fmgpu_build_image_device(const fmgpu_build_t *b);          /* device pointer */
+int32_t  fmgpu_build_download(const fmgpu_build_t *b, uint32_t *h_image);
+int32_t  fmgpu_build_to_index(const fmgpu_build_t *b, fmgpu_index_t **out); /* re-block, no host round trip */
+int32_t  fmgpu_build_free(fmgpu_build_t **b);
+const char *fmgpu_build_last_error(void);
+/* reads of fm_synth.h (exact substrings, uniform start) as ASCII into device memory */
+int32_t  fmgpu_synth_reads_device(int32_t device, uint64_t n, uint64_t seed_ref, uint64_t nqueries, uint32_t len,
+                                  uint64_t seed_reads, uint64_t first, char *d_ascii, void *stream);
+
 /* HBM random-access roofline probe: independent uniformly random 16-byte
  * loads over a table of `table_bytes`, full occupancy.  Returns loads/s. */
 int32_t fmgpu_gather_probe(int32_t device, uint64_t table_bytes, uint64_t loads_per_thread,

@@ -128,6 +128,15 @@ PROTOTYPES = {
     "fmgpu_host_register": (C.c_int32, [_VP, C.c_size_t]),
     "fmgpu_host_unregister": (C.c_int32, [_VP]),
     "fmgpu_gather_probe": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.POINTER(C.c_double)]),
+    "fmgpu_build_from_text": (C.c_int32, [C.c_int32, _VP, C.c_uint64, C.c_uint32, C.c_uint32, _VPP]),
+    "fmgpu_build_from_synth": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, _VPP]),
+    "fmgpu_build_image_words": (C.c_uint64, [_VP]),
+    "fmgpu_build_image_device": (_VP, [_VP]),
+    "fmgpu_build_download": (C.c_int32, [_VP, _VP]),
+    "fmgpu_build_to_index": (C.c_int32, [_VP, _VPP]),
+    "fmgpu_build_free": (C.c_int32, [_VPP]),
+    "fmgpu_build_last_error": (C.c_char_p, []),
+    "fmgpu_synth_reads_device": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, _VP, _VP]),
 }
 
 _lib = None
@@ -328,6 +337,50 @@ class DeviceBatch:
     def free(self):
         if self.handle:
             lib().fmgpu_batch_free(C.byref(self.handle))
+            self.handle = C.c_void_p()
+
+
+class IndexBuild:
+    """Tag-100 index image built on the GPU (fmgpu_build_t)."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    @classmethod
+    def from_text(cls, ascii_text, k, d, device=0):
+        t = np.ascontiguousarray(ascii_text, dtype=np.uint8).reshape(-1)
+        h = C.c_void_p()
+        rc = lib().fmgpu_build_from_text(device, t.ctypes.data, t.size, k, d, C.byref(h))
+        if rc:
+            raise FMError(rc, "fmgpu_build_from_text: " + lib().fmgpu_build_last_error().decode())
+        return cls(h)
+
+    @classmethod
+    def from_synth(cls, n, seed, k, d, device=0):
+        h = C.c_void_p()
+        rc = lib().fmgpu_build_from_synth(device, n, seed, k, d, C.byref(h))
+        if rc:
+            raise FMError(rc, "fmgpu_build_from_synth: " + lib().fmgpu_build_last_error().decode())
+        return cls(h)
+
+    @property
+    def image_words(self):
+        return lib().fmgpu_build_image_words(self.handle)
+
+    def download(self, out=None):
+        if out is None:
+            out = np.empty(self.image_words, dtype=np.uint32)
+        check(lib().fmgpu_build_download(self.handle, out.ctypes.data), "fmgpu_build_download")
+        return out
+
+    def to_index(self):
+        h = C.c_void_p()
+        check(lib().fmgpu_build_to_index(self.handle, C.byref(h)), "fmgpu_build_to_index")
+        return DeviceIndex(h)
+
+    def free(self):
+        if self.handle:
+            lib().fmgpu_build_free(C.byref(self.handle))
             self.handle = C.c_void_p()
 
 

@@ -209,9 +209,13 @@ def test_error_paths(pkg):
     with pytest.raises(pkg.FMError) as ei:
         b.search(idx)
     assert ei.value.code == pkg.FM_E_QUERY_SHAPE
-    with pytest.raises(pkg.FMError) as ei:
-        b.search(idx, pkg.variant(pkg.MODE_TASK, 3, 256))
-    assert ei.value.code == pkg.FM_E_BAD_ARGUMENT
+    b.free()
+    b = pkg.DeviceBatch(0, 10, 32, 2)
+    b.upload_ascii(g["reads"][: 320])
+    for bad_variant in (pkg.variant(pkg.MODE_TASK, 3, 256), pkg.variant(pkg.MODE_TASK, 2, 96), pkg.variant(7, 1, 128)):
+        with pytest.raises(pkg.FMError) as ei:
+            b.search(idx, bad_variant)
+        assert ei.value.code == pkg.FM_E_BAD_ARGUMENT
     b.free()
     bad = g["image_100"].copy(); bad[1] = 3; bad[3] = 64         # k = 3: CPU-only in the reference too
     with pytest.raises(pkg.FMError) as ei:
@@ -262,3 +266,65 @@ def test_config2_full_size(pkg, tmp_path):
     p1 = helpers.build_reference_indexes(str(tmp_path / "k1"), text, 1, 64)
     got1 = gpu_search(pkg, np.fromfile(p1[101], dtype=np.uint32), reads, length)
     assert np.array_equal(got1, want)
+
+
+# --------------------------------------------------------------------------- #
+# GPU index builder: byte-identical to genFMindex's .fmi
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_gpu_builder_reproduces_reference_index_files(pkg, path):
+    g = np.load(path)
+    n, k, d = int(g["n"]), int(g["k"]), int(g["d"])
+    seed = (100 + n) if os.path.basename(path).startswith("quirk") else 7 + k
+    want = g["image_100"]
+    b = pkg.IndexBuild.from_synth(n, seed, k, d)
+    assert np.array_equal(b.download(), want), "synthetic-text build != reference gfmiBaseLine output"
+    b.free()
+    b = pkg.IndexBuild.from_text(helpers.synth_text(n, seed), k, d)
+    assert np.array_equal(b.download(), want), "ASCII-text build != reference gfmiBaseLine output"
+    idx = b.to_index()                                          # straight into the searchable layout
+    length = int(g["length"])
+    batch = pkg.DeviceBatch(0, g["reads"].size // length, length, k)
+    batch.upload_ascii(g["reads"])
+    batch.search(idx)
+    assert np.array_equal(batch.download(), g["expected_std"])
+    batch.free(); idx.free(); b.free()
+
+
+@pytest.mark.skipif(not helpers.has_ref_tools(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("k,d,n", [(1, 64, 4_000_000), (2, 64, 4_000_000), (2, 128, 1_000_003), (1, 32, 777_777)])
+def test_gpu_builder_vs_reference_builder_config1_size(pkg, tmp_path, k, d, n):
+    text = helpers.synth_text(n, seed=1)
+    paths = helpers.build_reference_indexes(str(tmp_path), text, k, d)
+    want = np.fromfile(paths[100], dtype=np.uint32)
+    b = pkg.IndexBuild.from_synth(n, 1, k, d)
+    got = b.download()
+    b.free()
+    assert got.size == want.size and np.array_equal(got[:6 + 2 * k], want[:6 + 2 * k]), "header / '$' rows differ"
+    assert np.array_equal(got, want)
+
+
+def test_gpu_builder_repetitive_text(pkg):
+    """Equal-key runs are ordered by full suffix comparison; hopeless texts fail loudly, not slowly."""
+    unit = helpers.synth_text(500, seed=5)
+    text = np.concatenate([unit, unit, unit[:123], helpers.synth_text(300, seed=6), unit[:77]])   # long repeats
+    b = pkg.IndexBuild.from_text(text, 2, 64)
+    img = b.download()
+    idx = b.to_index()
+    # brute-force suffix order on the host
+    t = text.tobytes()
+    sa = sorted(range(len(t) + 1), key=lambda i: t[i:])
+    reads = np.concatenate([text[i:i + 12] for i in range(0, text.size - 12, 7)])
+    batch = pkg.DeviceBatch(0, reads.size // 12, 12, 2)
+    batch.upload_ascii(reads)
+    batch.search(idx)
+    got = batch.download().reshape(-1, 2)
+    for qi in range(0, got.shape[0], 5):
+        pat = reads[qi * 12:(qi + 1) * 12].tobytes()
+        rows = [r for r, i in enumerate(sa) if t[i:i + 12] == pat]
+        assert (got[qi, 0], got[qi, 1]) == (rows[0], rows[-1] + 1)
+    assert img[0] == 100 and img[2] == text.size + 1
+    batch.free(); idx.free(); b.free()
+    with pytest.raises(pkg.FMError) as ei:
+        pkg.IndexBuild.from_text(np.full(20000, ord("A"), dtype=np.uint8), 1, 64)
+    assert ei.value.code == 8                                   # FM_E_BUILDING_BWT
