@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- batched 2-step FM-index backward search on B200 (the one hot path of this repo).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): synthetic uniform-random
+2 000 000 000-bp reference (fm_synth.h, seed 1), k=2, d=64 index (3.0 GB tag-100 image == what the
+reference's gfmiBaseLine writes, re-blocked to the 5.33 GB SB96 device layout), 10 000 000 exact 100-bp
+reads PER GPU (seed 2; rank r takes reads [r*10M, (r+1)*10M)) -> weak scaling; N=8 is 80 M reads,
+BASELINE configs[3]'s 100 M-read shape.  A "step" = one pass of the search over the rank's 10 M reads.
+
+  value      Mqueries/s, whole job, kernels only, reads packed and resident in HBM (the reference's own
+             timed region, common/searchQueries.c:78-98), CUDA events on the launching stream.
+  e2e        same metric through the C-ABI call fmgpu_search_host with HOST buffers: pinned ASCII reads
+             H2D + 2-bit packing + search + (L,R) D2H inside the timed region, chunk-pipelined.
+  roofline   algorithmic bytes = (exact count of distinct 32-byte sectors an LF step must touch,
+             counted by an instrumented kernel run) x 32 B, over the search kernel's mean duration,
+             against the measured HBM copy bandwidth of MEASURED_PEAKS.json; the measured random-access
+             ceiling (gather probe over the same 5.33 GB footprint) is reported next to it.
+  cpu_baseline / --impl reference
+             the reference's own searchIndexCPU (oracle/_ref/libref_search_k2_d64_std.so, compiled
+             from /root/reference) on all host cores, on a bounded sample of the same reads.
+
+Inputs are larger than L2 (5.33 GB index, 250 MB packed reads vs 126 MB L2), so no flush between steps.
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TEXT = int(float(os.environ.get("FM_BENCH_N", "2e9")))
+NQ_PER_GPU = int(float(os.environ.get("FM_BENCH_NQ", "1e7")))
+READ_LEN = int(os.environ.get("FM_BENCH_LEN", "100"))
+K_STEPS = int(os.environ.get("FM_BENCH_K", "2"))
+CHUNK = 64
+SEED_REF, SEED_READS = 1, 2
+CPU_SAMPLE = int(float(os.environ.get("FM_BENCH_CPU_SAMPLE", "1e6")))
+MODE = os.environ.get("FM_BENCH_MODE", "coop")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while a timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.rows = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, HBM copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the search kernel from the committed ncu capture, if there is one."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))["dram_bytes_per_launch_10m_reads"] * NQ_PER_GPU / 1e7
+    except Exception:
+        return None
+
+
+def reference_search_rate(pkg, image, sample_ascii, steps, warmup, threads=0):
+    """Reference CPU searcher (kind "reference") on `sample_ascii`; returns (Mq/s, seconds/step, cores)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from bindings import RefSearcher
+    ref = RefSearcher(K_STEPS, CHUNK, False)
+    cores = int(ref.lib.ref_max_threads()) if threads == 0 else threads
+    idx = ref.wrap_image(image)
+    nq = sample_ascii.size // READ_LEN
+    out = None
+    for _ in range(warmup):
+        out, _s = ref.search(idx, sample_ascii, READ_LEN, 1, threads)
+    times = []
+    for _ in range(steps):
+        out, secs = ref.search(idx, sample_ascii, READ_LEN, 1, threads)
+        times.append(secs)
+    sec = sum(times) / len(times)
+    return nq / sec / 1e6, sec, cores, out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference" and rank != 0:
+        return 0                                           # rank 0 alone runs the CPU arm
+
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("k-step_fm-index_b200")
+    L = pkg.lib()
+    if L.fmgpu_device_count() < 1:
+        raise SystemExit("bench.py: no sm_100 GPU visible; this product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    distributed = world > 1 and args.impl == "ours"
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if not distributed:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    stream = torch.cuda.current_stream().cuda_stream
+    workload = (f"synthetic {N_TEXT}-bp uniform ACGT reference (seed {SEED_REF}), k={K_STEPS} d={CHUNK} index, "
+                f"{NQ_PER_GPU} exact {READ_LEN}-bp reads per GPU (seed {SEED_READS})")
+
+    # ------------------------------------------------------------------ setup (untimed)
+    t_setup = time.time()
+    image = None
+    setup = {}
+    if rank == 0:
+        t0 = time.time()
+        build = pkg.IndexBuild.from_synth(N_TEXT, SEED_REF, K_STEPS, CHUNK, device=dev)
+        setup["index_build_s"] = round(time.time() - t0, 3)
+        t0 = time.time()
+        index = build.to_index()
+        setup["reblock_s"] = round(time.time() - t0, 3)
+        if world == 1 or args.impl == "reference":
+            image = build.download()                       # host copy of the tag-100 file image for the CPU arm
+        build.free()
+        meta = index.meta
+    if distributed:
+        # one build + NCCL broadcast of the 5.33 GB block table over NVLink to every other GPU
+        holder = [bytes(meta) if rank == 0 else None]
+        dist.broadcast_object_list(holder, src=0)
+        if rank != 0:
+            meta = pkg.fmgpu_index_meta_t.from_buffer_copy(holder[0])
+            index = pkg.DeviceIndex.alloc_like(meta, device=dev)
+        table = torch.as_tensor(index, device=f"cuda:{dev}")
+        t0 = time.time()
+        dist.broadcast(table, src=0)
+        torch.cuda.synchronize()
+        setup["index_broadcast_s"] = round(time.time() - t0, 3)
+
+    nq = NQ_PER_GPU if args.impl == "ours" else CPU_SAMPLE
+    first = rank * NQ_PER_GPU
+    d_ascii = torch.empty(nq * READ_LEN, dtype=torch.uint8, device="cuda")
+    pkg.check(L.fmgpu_synth_reads_device(dev, N_TEXT, SEED_REF, nq, READ_LEN, SEED_READS, first, d_ascii.data_ptr(), stream), "synth reads")
+    h_ascii = torch.empty(nq * READ_LEN, dtype=torch.uint8, pin_memory=True)
+    h_ascii.copy_(d_ascii)
+    torch.cuda.synchronize()
+
+    if args.impl == "reference":
+        # -------------------------------------------------------------- reference arm: CPU, rank 0 only
+        sample = h_ascii.numpy()
+        mq, sec, cores, _ = reference_search_rate(pkg, image, sample, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": "Mqueries/s", "value": mq, "unit": "Mqueries/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "lf_steps_per_s": mq * 1e6 * (READ_LEN // K_STEPS),
+                "config": {"workload": workload, "timing": "reference searchIndexCPU under its own omp parallel region, wall clock per pass"},
+                "cpu_baseline": {"value": mq, "unit": "Mqueries/s", "cores": cores, "kind": "reference",
+                                 "sample": f"first {nq} reads of the workload per step, {cores} OpenMP threads, index image built on the GPU (byte-identical to gfmiBaseLine's)"},
+                "e2e": {"value": mq, "unit": "Mqueries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    wpq = L.fmgpu_words_per_query(READ_LEN)
+    d_packed = torch.empty(nq * wpq, dtype=torch.int32, device="cuda")
+    d_res = torch.zeros(2 * nq, dtype=torch.int32, device="cuda")
+    pkg.check(L.fmgpu_pack_queries_device(dev, d_ascii.data_ptr(), nq, READ_LEN, d_packed.data_ptr(), stream), "pack")
+    torch.cuda.synchronize()
+    del d_ascii
+    var = pkg.variant(pkg.MODE_COOP if MODE == "coop" else pkg.MODE_TASK, int(os.environ.get("FM_BENCH_QPT", "1")),
+                      int(os.environ.get("FM_BENCH_TPB", "256")))
+
+    def search_step():
+        pkg.check(L.fmgpu_search_device(index.handle, d_packed.data_ptr(), nq, READ_LEN, d_res.data_ptr(), C.byref(var), stream), "search")
+
+    # algorithmic bytes: exact count of necessary sector fetches for THIS rank's reads
+    nblk, nsec = C.c_uint64(), C.c_uint64()
+    pkg.check(L.fmgpu_count_fetches_device(index.handle, d_packed.data_ptr(), nq, READ_LEN, d_res.data_ptr(), stream,
+                                           C.byref(nblk), C.byref(nsec)), "count fetches")
+    lf_steps = nq * (READ_LEN // K_STEPS)
+    algo_bytes = nsec.value * 32
+
+    # measured random-access ceiling over the same footprint (rank 0, once)
+    probe = pkg.gather_probe(dev, int(index.meta.nbytes), 512, 3) if rank == 0 else 0.0
+    setup["setup_s"] = round(time.time() - t_setup, 2)
+
+    # ------------------------------------------------------------------ timed: device-resident
+    for _ in range(args.warmup):
+        search_step()
+    barrier()
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        search_step()
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    res_dev = d_res.cpu().numpy().view(np.uint32).copy()
+
+    # ------------------------------------------------------------------ timed: end to end through the C ABI, host buffers
+    h_res = torch.empty(2 * nq, dtype=torch.int32, pin_memory=True)
+    handles = (C.c_void_p * 1)(index.handle)
+
+    def e2e_step():
+        pkg.check(L.fmgpu_search_host(handles, 1, h_ascii.data_ptr(), nq, READ_LEN, h_res.data_ptr(), C.byref(var)), "search_host")
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()                                         # synchronous: returns when the (L,R) are in host memory
+    torch.cuda.synchronize()
+    e2e_ms_step = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    barrier()
+    same = bool(np.array_equal(h_res.numpy().view(np.uint32), res_dev))
+    hits_ok = bool(((res_dev[1::2] - res_dev[0::2]) >= 1).all())      # every exact read occurs in the text
+
+    # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N=1)
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1 and image is not None:
+        ns = min(CPU_SAMPLE, nq)
+        mq_cpu, sec_cpu, cores, out = reference_search_rate(pkg, image, h_ascii.numpy()[: ns * READ_LEN], 2, 1)
+        parity = bool(np.array_equal(out, res_dev[: 2 * ns]))         # GPU (L,R) == reference CPU (L,R) on the sample
+        cpu = {"value": mq_cpu, "unit": "Mqueries/s", "cores": cores, "kind": "reference",
+               "sample": f"first {ns} of the {nq} reads, 2 timed passes after 1 warm-up, {cores} OpenMP threads, reference searchIndexCPU from oracle/_ref",
+               "gpu_matches_reference_on_sample": parity}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        mq = world * nq / ms_step / 1e3
+        achieved = algo_bytes / (ms_step * 1e-3) / 1e9
+        line = {
+            "metric": "Mqueries/s", "value": mq, "unit": "Mqueries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "lf_steps_per_s": world * lf_steps / (ms_step * 1e-3),
+            "config": {"workload": workload, "kernel": f"{MODE} qpt={var.queries_per_thread} tpb={var.threads_per_block}",
+                       "device_layout": "SB96 (16-byte per-symbol blocks: u32 rank + 96 indicator bits)",
+                       "l2": "inputs larger than L2 (5.33 GB block table, 250 MB packed reads), no flush",
+                       "parallelism": f"index replicated, reads sharded x{world}, no collective in the search", "setup": setup},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+                         "sectors_per_lf_step": nsec.value / lf_steps, "blocks_per_lf_step": nblk.value / lf_steps,
+                         "random_access_ceiling": {"loads_per_s": probe, "sector_gbs": probe * 32 / 1e9,
+                                                   "how": "independent uniform random 16-byte loads over a table of the index's size",
+                                                   "lf_steps_per_s_per_gpu_over_ceiling": (lf_steps / (ms_step * 1e-3)) / probe if probe else None},
+                         "frac_of_nominal_8tbs": achieved / 8000.0},
+            "cpu_baseline": cpu,
+            "e2e": {"value": world * nq / e2e_ms_step / 1e3, "unit": "Mqueries/s", "ms_per_step": e2e_ms_step,
+                    "h2d_bytes_per_step": nq * READ_LEN, "d2h_bytes_per_step": nq * 8, "matches_device_resident_result": same},
+            "gpu_launches": args.steps,
+            "clocks": clocks,
+            "checks": {"every_read_found": hits_ok, "e2e_equals_resident": same, "gpu_equals_reference_cpu_on_sample": parity},
+        }
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

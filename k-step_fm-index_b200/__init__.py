@@ -128,6 +128,8 @@ PROTOTYPES = {
     "fmgpu_host_register": (C.c_int32, [_VP, C.c_size_t]),
     "fmgpu_host_unregister": (C.c_int32, [_VP]),
     "fmgpu_gather_probe": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.POINTER(C.c_double)]),
+    "fmgpu_gather_probe_ex": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int32, C.POINTER(C.c_double)]),
+    "fmgpu_count_fetches_device": (C.c_int32, [_VP, _VP, C.c_uint64, C.c_uint32, _VP, _VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "fmgpu_build_from_text": (C.c_int32, [C.c_int32, _VP, C.c_uint64, C.c_uint32, C.c_uint32, _VPP]),
     "fmgpu_build_from_synth": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, _VPP]),
     "fmgpu_build_image_words": (C.c_uint64, [_VP]),
@@ -396,7 +398,8 @@ def search_host(replicas, ascii_bases, length, var=None, out=None):
     return out
 
 
-def gather_probe(device, table_bytes, loads_per_thread=256, iters=3):
+def gather_probe(device, table_bytes, loads_per_thread=256, iters=3, access_bytes=16):
+    """Random-access roofline: independent uniformly random aligned accesses per second."""
     v = C.c_double()
-    check(lib().fmgpu_gather_probe(device, table_bytes, loads_per_thread, iters, C.byref(v)), "fmgpu_gather_probe")
+    check(lib().fmgpu_gather_probe_ex(device, table_bytes, access_bytes, loads_per_thread, iters, C.byref(v)), "fmgpu_gather_probe_ex")
     return v.value

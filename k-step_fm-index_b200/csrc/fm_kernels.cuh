@@ -364,24 +364,28 @@ __global__ void fm_reblock_kernel(const FmRawIndex x, uint4 *__restrict__ blocks
 }
 
 /* ------------------------------------------------------------------------ *
- * Gather roofline probe: independent uniformly random aligned 16-byte loads.
+ * Gather roofline probe: independent uniformly random aligned accesses of
+ * WIDTH consecutive 16-byte loads (16, 32, 64 or 128 bytes per access).
  * ------------------------------------------------------------------------ */
-template <int UNROLL>
-__global__ void __launch_bounds__(256, 8) fm_gather_probe_kernel(const uint4 *__restrict__ table, uint64_t nblocks16,
+template <int UNROLL, int WIDTH>
+__global__ void __launch_bounds__(256, 8) fm_gather_probe_kernel(const uint4 *__restrict__ table, uint64_t naccess,
                                                                    uint32_t loads_per_thread, uint32_t *sink)
 {
   uint64_t s = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
   uint32_t acc = 0;
   for (uint32_t it = 0; it < loads_per_thread; it += UNROLL) {
-    uint4 v[UNROLL];
+    uint4 v[UNROLL][WIDTH];
     #pragma unroll
     for (int u = 0; u < UNROLL; u++) {
       s ^= s << 13; s ^= s >> 7; s ^= s << 17;                        /* xorshift64 */
-      const uint64_t idx = __umul64hi(s, nblocks16);                   /* uniform in [0, nblocks16) */
-      v[u] = fm_ldg16(table + idx);
+      const uint64_t idx = __umul64hi(s, naccess);                     /* uniform in [0, naccess) */
+      #pragma unroll
+      for (int w = 0; w < WIDTH; w++) v[u][w] = fm_ldg16(table + idx * WIDTH + w);
     }
     #pragma unroll
-    for (int u = 0; u < UNROLL; u++) acc += v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+    for (int u = 0; u < UNROLL; u++)
+      #pragma unroll
+      for (int w = 0; w < WIDTH; w++) acc += v[u][w].x ^ v[u][w].y ^ v[u][w].z ^ v[u][w].w;
   }
   if (acc == 0x9E3779B9u) *sink = acc;                                 /* keeps the loads alive */
 }
