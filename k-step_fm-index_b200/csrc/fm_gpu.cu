@@ -600,6 +600,43 @@ extern "C" int32_t fmgpu_gather_probe(int32_t device, uint64_t table_bytes, uint
   return fmgpu_gather_probe_ex(device, table_bytes, 16, loads_per_thread, iters, loads_per_second);
 }
 
+/* locality probe: the 32 lanes of each warp-level load fall in one random window of `window_bytes` */
+extern "C" int32_t fmgpu_gather_probe_local(int32_t device, uint64_t table_bytes, uint64_t window_bytes,
+                                            uint64_t loads_per_thread, int32_t iters, double *loads_per_second)
+{
+  int32_t rc = fm_use_device(device);
+  if (rc) return rc;
+  if (!loads_per_second || window_bytes < 512 || table_bytes < window_bytes || iters < 1 || window_bytes > (1ull << 34))
+    return fm_fail_msg(FM_E_BAD_ARGUMENT, "bad argument");
+  const uint32_t window16 = (uint32_t)(window_bytes / 16);
+  const uint64_t nwindows = table_bytes / window_bytes;
+  uint4 *table = NULL; uint32_t *sink = NULL;
+  CU_TRY(cudaMalloc((void **) &table, nwindows * window_bytes));
+  CU_TRY(cudaMalloc((void **) &sink, 4));
+  CU_TRY(cudaMemset(table, 0x5A, nwindows * window_bytes));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const uint32_t lpt = (uint32_t)((loads_per_thread + 3) & ~3ull);
+  const uint32_t grid = (uint32_t) sms * 8 * 4;
+  cudaEvent_t e0, e1;
+  CU_TRY(cudaEventCreate(&e0)); CU_TRY(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int i = 0; i <= iters; i++) {
+    CU_TRY(cudaEventRecord(e0));
+    fm_gather_probe_local_kernel<4><<<grid, 256>>>(table, nwindows, window16, lpt, sink);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(e1));
+    CU_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (i > 0 && ms < best) best = ms;
+  }
+  *loads_per_second = (double) grid * 256.0 * lpt / (best * 1e-3);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(table); cudaFree(sink);
+  return FM_SUCCESS;
+}
+
 /* fetch counter on caller-owned device memory: one instrumented search (results are written too) */
 extern "C" int32_t fmgpu_count_fetches_device(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nq, uint32_t len,
                                               uint32_t *d_results, void *stream, uint64_t *nblocks, uint64_t *nsectors)
