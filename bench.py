@@ -182,10 +182,9 @@ def main():
         meta = index.meta
     if distributed:
         # one build + NCCL broadcast of the 5.33 GB block table over NVLink to every other GPU
-        holder = [bytes(meta) if rank == 0 else None]
-        dist.broadcast_object_list(holder, src=0)
+        sharding = importlib.import_module("k-step_fm-index_b200.sharding")
+        meta = sharding.broadcast_meta(meta if rank == 0 else None, 0, dist, pkg.fmgpu_index_meta_t)
         if rank != 0:
-            meta = pkg.fmgpu_index_meta_t.from_buffer_copy(holder[0])
             index = pkg.DeviceIndex.alloc_like(meta, device=dev)
         table = torch.as_tensor(index, device=f"cuda:{dev}")
         t0 = time.time()
