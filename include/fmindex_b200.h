@@ -173,7 +173,9 @@ typedef struct {
                                  block fetch shared through warp shuffles             */
   int32_t queries_per_thread; /* independent queries interleaved per thread/lane pair: 1, 2 or 4 */
   int32_t threads_per_block;  /* 128, 256 or 512                                      */
-  int32_t reserved;
+  int32_t reserved;           /* fmgpu_search_host only (also $FMGPU_FEED): 0 = auto, 1 = upload ASCII and pack
+                                 on the GPU, 2 = pack to 2 bit on the host (OpenMP + AVX-512) and upload
+                                 25 B/read, 3 = hybrid (copy engine pulls ASCII chunks while the CPU packs others) */
 } fmgpu_variant_t;
 
 /* Shape of the device layout ("SB96": per-symbol blocks of 96 BWT rows,
@@ -253,6 +255,13 @@ int32_t fmgpu_search_device(const fmgpu_index_t *idx, const uint32_t *d_packed, 
  * GPU, shards spread over `nreplicas` GPUs */
 int32_t fmgpu_search_host(fmgpu_index_t *const *replicas, int32_t nreplicas, const char *h_ascii,
                           uint64_t nqueries, uint32_t len, uint32_t *h_results, const fmgpu_variant_t *v);
+
+/* host-side ASCII -> reversed 2-bit packing (same words as the device pack kernel); OpenMP over reads,
+ * AVX-512 VBMI when the CPU has it.  packed holds nqueries * fmgpu_words_per_query(len) words. */
+void    fm_hostpack_reads(const char *ascii, uint64_t nqueries, uint32_t len, uint32_t *packed, int nthreads);
+void    fm_hostpack_reads_scalar(const char *ascii, uint64_t nqueries, uint32_t len, uint32_t *packed);
+int     fm_hostpack_has_simd(void);
+int     fm_hostpack_threads(void);
 
 /* pinned host memory for query / result buffers */
 void   *fmgpu_host_alloc(size_t bytes);

@@ -129,6 +129,10 @@ PROTOTYPES = {
     "fmgpu_host_unregister": (C.c_int32, [_VP]),
     "fmgpu_gather_probe": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.POINTER(C.c_double)]),
     "fmgpu_gather_probe_ex": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int32, C.POINTER(C.c_double)]),
+    "fm_hostpack_reads": (None, [_VP, C.c_uint64, C.c_uint32, _VP, C.c_int]),
+    "fm_hostpack_reads_scalar": (None, [_VP, C.c_uint64, C.c_uint32, _VP]),
+    "fm_hostpack_has_simd": (C.c_int, []),
+    "fm_hostpack_threads": (C.c_int, []),
     "fmgpu_gather_probe_local": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.POINTER(C.c_double)]),
     "fmgpu_count_fetches_device": (C.c_int32, [_VP, _VP, C.c_uint64, C.c_uint32, _VP, _VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "fmgpu_build_from_text": (C.c_int32, [C.c_int32, _VP, C.c_uint64, C.c_uint32, C.c_uint32, _VPP]),
@@ -171,8 +175,12 @@ def check(code, where):
         raise FMError(code, where)
 
 
-def variant(mode=MODE_TASK, queries_per_thread=0, threads_per_block=0):
-    return fmgpu_variant_t(mode, queries_per_thread, threads_per_block, 0)
+FEED_AUTO, FEED_ASCII, FEED_HOSTPACK, FEED_HYBRID = 0, 1, 2, 3
+
+
+def variant(mode=MODE_TASK, queries_per_thread=0, threads_per_block=0, feed=FEED_AUTO):
+    """feed only matters to search_host: how host ASCII reads reach the GPU (see fmindex_b200.h)."""
+    return fmgpu_variant_t(mode, queries_per_thread, threads_per_block, feed)
 
 
 # --------------------------------------------------------------------------- #

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdint.h>
+#include <time.h>
 #include <cuda_runtime.h>
 #include "../../include/fmindex_b200.h"
 #include "fm_kernels.cuh"
@@ -458,27 +459,63 @@ extern "C" int32_t fmgpu_batch_free(fmgpu_batch_t **pb)
  * H2D -> pack -> search -> D2H on FM_PIPE_STREAMS streams per GPU so the
  * PCIe copies of one chunk overlap the kernels of another.
  * ------------------------------------------------------------------------ */
-#define FM_PIPE_STREAMS 3
+#define FM_PIPE_STREAMS 4
 #define FM_MAX_DEVICES  16
 
 struct fm_pipe_lane {
   cudaStream_t stream;
+  cudaEvent_t  h2d_done;      /* the lane's pinned staging buffer may be overwritten after this */
   char     *d_ascii;
   uint32_t *d_packed;
   uint32_t *d_results;
-  size_t    cap_ascii, cap_packed, cap_results;
+  uint32_t *h_packed;         /* pinned staging for host-packed reads */
+  size_t    cap_ascii, cap_packed, cap_results, cap_hpacked;
 };
 static fm_pipe_lane g_pipe[FM_MAX_DEVICES][FM_PIPE_STREAMS];
 
-static int32_t fm_pipe_reserve(int device, fm_pipe_lane *ln, size_t ascii, size_t packed, size_t results)
+extern "C" int  fm_hostpack_has_simd(void);
+extern "C" int  fm_hostpack_threads(void);
+extern "C" void fm_hostpack_reads(const char *ascii, uint64_t nq, uint32_t len, uint32_t *packed, int nthreads);
+
+static int32_t fm_pipe_reserve(int device, fm_pipe_lane *ln, size_t ascii, size_t packed, size_t results, size_t hpacked)
 {
   CU_TRY(cudaSetDevice(device));
   if (!ln->stream) CU_TRY(cudaStreamCreateWithFlags(&ln->stream, cudaStreamNonBlocking));
+  if (!ln->h2d_done) CU_TRY(cudaEventCreateWithFlags(&ln->h2d_done, cudaEventDisableTiming));
   if (ln->cap_ascii < ascii)     { if (ln->d_ascii) cudaFree(ln->d_ascii);     ln->cap_ascii = 0;   CU_TRY(cudaMalloc((void **) &ln->d_ascii, ascii));     ln->cap_ascii = ascii; }
   if (ln->cap_packed < packed)   { if (ln->d_packed) cudaFree(ln->d_packed);   ln->cap_packed = 0;  CU_TRY(cudaMalloc((void **) &ln->d_packed, packed));   ln->cap_packed = packed; }
   if (ln->cap_results < results) { if (ln->d_results) cudaFree(ln->d_results); ln->cap_results = 0; CU_TRY(cudaMalloc((void **) &ln->d_results, results)); ln->cap_results = results; }
+  if (ln->cap_hpacked < hpacked) { if (ln->h_packed) cudaFreeHost(ln->h_packed); ln->cap_hpacked = 0; CU_TRY(cudaMallocHost((void **) &ln->h_packed, hpacked)); ln->cap_hpacked = hpacked; }
   return FM_SUCCESS;
 }
+
+/* Feeding the GPU from host ASCII reads (variant.reserved, or $FMGPU_FEED):
+ *   1 = ASCII over PCIe, 2-bit packing on the device        (PCIe-bound: 100 B/read)
+ *   2 = 2-bit packing on the host, 25 B/read over PCIe      (CPU-bound)
+ *   3 = hybrid: the copy engine pulls ASCII chunks while the CPU threads pack other chunks; each chunk goes
+ *       to whichever resource would otherwise idle (greedy on a PCIe-busy-until estimate)
+ *   0 = auto: 3 when the CPU has AVX-512 VBMI and >= 8 threads, else 1 */
+enum { FM_FEED_AUTO = 0, FM_FEED_ASCII = 1, FM_FEED_HOSTPACK = 2, FM_FEED_HYBRID = 3 };
+
+static int fm_feed_mode(const fmgpu_variant_t *v)
+{
+  int mode = v ? v->reserved : 0;
+  const char *env = getenv("FMGPU_FEED");
+  if (mode == FM_FEED_AUTO && env && *env) mode = atoi(env);
+  if (mode < FM_FEED_ASCII || mode > FM_FEED_HYBRID)
+    mode = (fm_hostpack_has_simd() && fm_hostpack_threads() >= 8) ? FM_FEED_HYBRID : FM_FEED_ASCII;
+  return mode;
+}
+
+static double fm_now(void)
+{
+  struct timespec tv;
+  clock_gettime(CLOCK_MONOTONIC, &tv);
+  return (double) tv.tv_sec + (double) tv.tv_nsec * 1e-9;
+}
+
+static double g_pack_s_per_read = 1.6e-9;     /* running estimate of the host packer (all threads), seconds per read */
+static const double FM_H2D_BYTES_PER_S = 50e9; /* PCIe gen5 x16 pinned H2D as measured on this pool (47-52 GB/s) */
 
 extern "C" int32_t fmgpu_search_host(fmgpu_index_t *const *replicas, int32_t nrep, const char *h_ascii, uint64_t nq,
                                      uint32_t len, uint32_t *h_results, const fmgpu_variant_t *v)
@@ -489,16 +526,19 @@ extern "C" int32_t fmgpu_search_host(fmgpu_index_t *const *replicas, int32_t nre
   if (len % replicas[0]->meta.steps) return fm_fail_msg(FM_E_QUERY_SHAPE, "read length must be a multiple of k");
   if (nq == 0) return FM_SUCCESS;
   const uint32_t wpq = fmgpu_words_per_query(len);
-  /* chunk: about 1 M reads, 32-aligned; small batches still get one chunk per lane */
-  uint64_t chunk = 1ull << 20;
+  const int feed = fm_feed_mode(v);
+  /* chunk: 512 K reads, 32-aligned; small batches still get one chunk per lane */
+  uint64_t chunk = 1ull << 19;
   const uint64_t lanes = (uint64_t) nrep * FM_PIPE_STREAMS;
   if (nq < chunk * lanes) chunk = ((nq + lanes - 1) / lanes + 31) & ~31ull;
   if (chunk == 0) chunk = 32;
   for (int g = 0; g < nrep; g++)
     for (int s = 0; s < FM_PIPE_STREAMS; s++) {
-      int32_t rc = fm_pipe_reserve(replicas[g]->device, &g_pipe[replicas[g]->device][s], chunk * len, chunk * wpq * 4, chunk * 8);
+      int32_t rc = fm_pipe_reserve(replicas[g]->device, &g_pipe[replicas[g]->device][s], feed != FM_FEED_HOSTPACK ? chunk * len : 0,
+                                   chunk * wpq * 4, chunk * 8, feed != FM_FEED_ASCII ? chunk * wpq * 4 : 0);
       if (rc) return rc;
     }
+  double pcie_free_at = fm_now();
   uint64_t c = 0;
   for (uint64_t q0 = 0; q0 < nq; q0 += chunk, c++) {
     const uint64_t n = (nq - q0 < chunk) ? nq - q0 : chunk;
@@ -506,9 +546,25 @@ extern "C" int32_t fmgpu_search_host(fmgpu_index_t *const *replicas, int32_t nre
     const fmgpu_index_t *idx = replicas[g];
     fm_pipe_lane *ln = &g_pipe[idx->device][s];
     CU_TRY(cudaSetDevice(idx->device));
-    CU_TRY(cudaMemcpyAsync(ln->d_ascii, h_ascii + q0 * len, n * len, cudaMemcpyHostToDevice, ln->stream));
-    int32_t rc = fmgpu_pack_queries_device(idx->device, ln->d_ascii, n, len, ln->d_packed, ln->stream);
-    if (rc) return rc;
+    int32_t rc;
+    double now = fm_now();
+    bool on_host = (feed == FM_FEED_HOSTPACK);
+    if (feed == FM_FEED_HYBRID) on_host = (pcie_free_at - now) >= g_pack_s_per_read * (double) n;   /* PCIe stays busy while we pack */
+    if (on_host) {
+      CU_TRY(cudaEventSynchronize(ln->h2d_done));                     /* staging buffer free again? */
+      const double t0 = fm_now();
+      fm_hostpack_reads(h_ascii + q0 * len, n, len, ln->h_packed, 0);
+      now = fm_now();
+      if (n >= 4096) g_pack_s_per_read = 0.75 * g_pack_s_per_read + 0.25 * (now - t0) / (double) n;
+      CU_TRY(cudaMemcpyAsync(ln->d_packed, ln->h_packed, n * wpq * 4, cudaMemcpyHostToDevice, ln->stream));
+      CU_TRY(cudaEventRecord(ln->h2d_done, ln->stream));
+      pcie_free_at = (pcie_free_at > now ? pcie_free_at : now) + (double)(n * wpq * 4) / FM_H2D_BYTES_PER_S;
+    } else {
+      CU_TRY(cudaMemcpyAsync(ln->d_ascii, h_ascii + q0 * len, n * len, cudaMemcpyHostToDevice, ln->stream));
+      rc = fmgpu_pack_queries_device(idx->device, ln->d_ascii, n, len, ln->d_packed, ln->stream);
+      if (rc) return rc;
+      pcie_free_at = (pcie_free_at > now ? pcie_free_at : now) + (double)(n * len) / FM_H2D_BYTES_PER_S;
+    }
     rc = fm_launch_search(idx, ln->d_packed, n, len, ln->d_results, v, ln->stream, NULL);
     if (rc) return rc;
     CU_TRY(cudaMemcpyAsync(h_results + 2 * q0, ln->d_results, n * 8, cudaMemcpyDeviceToHost, ln->stream));

@@ -1,0 +1,150 @@
+/*
+ * fm_hostpack.c -- host-side ASCII -> reversed 2-bit packing of reads (plain C, OpenMP, AVX-512 VBMI fast path).
+ *
+ * Same output as the device kernel fm_pack_kernel: packed position t of a read is base len-1-t, 16 bases per
+ * 32-bit word, code A=0 C=1 G=2 T=3 from ASCII bits 2 and 1 (the reference's bit trick,
+ * src/fmIndexCPUBaseline.c:213-226; case-insensitive, other bytes alias).  Used by fmgpu_search_host so that
+ * 25 instead of 100 bytes per 100-bp read cross PCIe; replaces the host-side warp interleave of the reference
+ * query loader (common/common.c:175-194).  This is data-format conversion only -- no search arithmetic here.
+ */
+#include <stdint.h>
+#include <string.h>
+#include <immintrin.h>
+#include <omp.h>
+
+static void pack_read_scalar(const unsigned char *rd, uint32_t len, uint32_t wpq, uint32_t *out)
+{
+  uint32_t w, i;
+  for (w = 0; w < wpq; w++) {
+    uint32_t v = 0;
+    for (i = 0; i < 16; i++) {
+      const uint32_t t = 16 * w + i;
+      if (t < len) {
+        const uint32_t c = rd[len - 1 - t];
+        const uint32_t hi = (c >> 2) & 1u, mid = (c >> 1) & 1u;
+        v |= ((hi << 1) | (hi ^ mid)) << (2 * i);
+      }
+    }
+    out[w] = v;
+  }
+}
+
+/* 64 bases per iteration: masked load of the block's bytes, byte reversal with vpermb, 2-bit codes, then
+ * four codes per byte with pmaddubsw / pmaddwd, narrowed with vpmovdb */
+__attribute__((target("avx512f,avx512bw,avx512vl,avx512vbmi")))
+static void pack_read_avx512(const unsigned char *rd, uint32_t len, uint32_t wpq, uint32_t *out)
+{
+  const __m512i iota = _mm512_set_epi8(63, 62, 61, 60, 59, 58, 57, 56, 55, 54, 53, 52, 51, 50, 49, 48, 47, 46, 45, 44, 43, 42, 41, 40,
+                                       39, 38, 37, 36, 35, 34, 33, 32, 31, 30, 29, 28, 27, 26, 25, 24, 23, 22, 21, 20, 19, 18, 17, 16,
+                                       15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+  unsigned char *o = (unsigned char *) out;
+  const uint32_t out_bytes = wpq * 4;
+  uint32_t done = 0, ob = 0;
+  while (done < len) {
+    const uint32_t m = (len - done < 64) ? len - done : 64;          /* reversed positions [done, done+m) */
+    const __mmask64 km = (m == 64) ? ~(__mmask64) 0 : (((__mmask64) 1 << m) - 1);
+    const __m512i x = _mm512_maskz_loadu_epi8(km, rd + (len - done - m));    /* bases len-done-m .. len-done-1, ascending */
+    const __m512i idx = _mm512_sub_epi8(_mm512_set1_epi8((char)(m - 1)), iota);
+    const __m512i r = _mm512_maskz_permutexvar_epi8(km, idx, x);      /* byte j = base len-1-(done+j) */
+    const __m512i u = _mm512_and_si512(_mm512_srli_epi16(r, 1), _mm512_set1_epi8(3));            /* bit2<<1 | bit1 */
+    const __m512i c = _mm512_xor_si512(u, _mm512_and_si512(_mm512_srli_epi16(u, 1), _mm512_set1_epi8(1)));
+    const __m512i cz = _mm512_maskz_mov_epi8(km, c);                  /* positions past the read pack as 0 */
+    const __m512i p16 = _mm512_maddubs_epi16(cz, _mm512_set1_epi16(0x0401));                     /* c0 + 4 c1 */
+    const __m512i p32 = _mm512_madd_epi16(p16, _mm512_set1_epi32(0x00100001));                   /* + 16 c2 + 64 c3 */
+    const __m128i b = _mm512_cvtepi32_epi8(p32);                      /* 16 bytes = 64 bases */
+    const uint32_t nb = (m + 3) / 4;
+    _mm_mask_storeu_epi8(o + ob, (__mmask16)((1u << nb) - 1u), b);
+    ob += nb; done += m;
+  }
+  if (ob < out_bytes) memset(o + ob, 0, out_bytes - ob);
+}
+
+int fm_hostpack_has_simd(void)
+{
+  return __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl") &&
+         __builtin_cpu_supports("avx512vbmi");
+}
+
+int fm_hostpack_threads(void) { return omp_get_max_threads(); }
+
+/* packed must hold nq * ceil(len/16) words; nthreads <= 0 means all OpenMP threads */
+void fm_hostpack_reads(const char *ascii, uint64_t nq, uint32_t len, uint32_t *packed, int nthreads)
+{
+  const uint32_t wpq = (len + 15u) / 16u;
+  const int simd = fm_hostpack_has_simd();
+  int64_t q;
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+  #pragma omp parallel for schedule(static) num_threads(nthreads)
+  for (q = 0; q < (int64_t) nq; q++) {
+    const unsigned char *rd = (const unsigned char *) ascii + (uint64_t) q * len;
+    uint32_t *out = packed + (uint64_t) q * wpq;
+    if (simd) pack_read_avx512(rd, len, wpq, out);
+    else      pack_read_scalar(rd, len, wpq, out);
+  }
+}
+
+/* ------------------------------------------------------------------------ *
+ * Stream packing: the whole batch as ONE sequence of bases, base g (= q*len + i) at bits [2(g%4), 2(g%4)+2) of
+ * byte g/4 -- no per-read work on the host at all (64 ASCII bytes -> 16 packed bytes per iteration); the
+ * per-read reversal / word alignment is done by fm_unstream_kernel on the GPU.
+ * ------------------------------------------------------------------------ */
+static void stream_scalar(const unsigned char *in, uint64_t nbases, unsigned char *out)
+{
+  uint64_t g;
+  for (g = 0; g + 4 <= nbases; g += 4) {
+    uint32_t v = 0, j;
+    for (j = 0; j < 4; j++) {
+      const uint32_t c = in[g + j], hi = (c >> 2) & 1u, mid = (c >> 1) & 1u;
+      v |= ((hi << 1) | (hi ^ mid)) << (2 * j);
+    }
+    out[g / 4] = (unsigned char) v;
+  }
+  if (g < nbases) {
+    uint32_t v = 0, j;
+    for (j = 0; g + j < nbases; j++) {
+      const uint32_t c = in[g + j], hi = (c >> 2) & 1u, mid = (c >> 1) & 1u;
+      v |= ((hi << 1) | (hi ^ mid)) << (2 * j);
+    }
+    out[g / 4] = (unsigned char) v;
+  }
+}
+
+__attribute__((target("avx512f,avx512bw,avx512vl")))
+static void stream_avx512(const unsigned char *in, uint64_t nbases, unsigned char *out)
+{
+  const __m512i three = _mm512_set1_epi8(3), one = _mm512_set1_epi8(1);
+  const __m512i w16 = _mm512_set1_epi16(0x0401), w32 = _mm512_set1_epi32(0x00100001);
+  uint64_t g = 0;
+  for (; g + 64 <= nbases; g += 64) {
+    const __m512i x = _mm512_loadu_si512((const void *)(in + g));
+    const __m512i u = _mm512_and_si512(_mm512_srli_epi16(x, 1), three);
+    const __m512i c = _mm512_xor_si512(u, _mm512_and_si512(_mm512_srli_epi16(u, 1), one));
+    const __m512i p32 = _mm512_madd_epi16(_mm512_maddubs_epi16(c, w16), w32);
+    _mm_storeu_si128((__m128i *)(out + g / 4), _mm512_cvtepi32_epi8(p32));
+  }
+  if (g < nbases) stream_scalar(in + g, nbases - g, out + g / 4);
+}
+
+/* out must hold (nbases + 3) / 4 bytes (+ up to 3 bytes of slack are NOT written); threads split at 64-base
+ * boundaries so every thread writes whole bytes */
+void fm_hostpack_stream(const char *ascii, uint64_t nbases, unsigned char *out, int nthreads)
+{
+  const int simd = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl");
+  const uint64_t nblk = (nbases + 4095) / 4096;                     /* 4096-base slices */
+  int64_t b;
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+  #pragma omp parallel for schedule(static) num_threads(nthreads)
+  for (b = 0; b < (int64_t) nblk; b++) {
+    const uint64_t g0 = (uint64_t) b * 4096, n = (nbases - g0 < 4096) ? nbases - g0 : 4096;
+    if (simd) stream_avx512((const unsigned char *) ascii + g0, n, out + g0 / 4);
+    else      stream_scalar((const unsigned char *) ascii + g0, n, out + g0 / 4);
+  }
+}
+
+/* scalar-only entry point so tests can check the SIMD path against it */
+void fm_hostpack_reads_scalar(const char *ascii, uint64_t nq, uint32_t len, uint32_t *packed)
+{
+  const uint32_t wpq = (len + 15u) / 16u;
+  uint64_t q;
+  for (q = 0; q < nq; q++) pack_read_scalar((const unsigned char *) ascii + q * len, len, wpq, packed + q * wpq);
+}

@@ -156,6 +156,12 @@ def test_end_to_end_host_pipeline(pkg):
     idx = pkg.DeviceIndex.from_image(g["image_100"])
     got = pkg.search_host([idx], reps, length)
     assert np.array_equal(got, want)
+    big = np.tile(g["reads"], 1200)                             # ~2.5 M reads: several 512K-read chunks per lane
+    wantbig = np.tile(g["expected_std"], 1200)
+    for feed in (pkg.FEED_ASCII, pkg.FEED_HOSTPACK, pkg.FEED_HYBRID):
+        for mode in (pkg.MODE_TASK, pkg.MODE_COOP):
+            got = pkg.search_host([idx], big, length, pkg.variant(mode, feed=feed))
+            assert np.array_equal(got, wantbig), f"feed {feed} mode {mode}"
     rep2 = idx.replicate(0)                                      # second replica (same GPU) = second shard lane
     got2 = pkg.search_host([idx, rep2], reps[: 1000 * length], length, pkg.variant(pkg.MODE_COOP))
     assert np.array_equal(got2, want[:2000])

@@ -126,3 +126,26 @@ def test_device_entry_points_fail_loudly_without_gpu(built):
     assert L.fmgpu_batch_create(0, 32, 32, 2, C.byref(h)) == pkg.FM_E_CUDA
     v = C.c_double()
     assert L.fmgpu_gather_probe(0, 1 << 20, 16, 1, C.byref(v)) == pkg.FM_E_CUDA
+
+
+@pytest.mark.parametrize("length", [1, 3, 4, 15, 16, 17, 36, 63, 64, 65, 100, 127, 128, 129, 250, 1000])
+def test_host_packer_simd_equals_scalar_equals_definition(built, length):
+    """fm_hostpack_reads (AVX-512 path when available) == scalar path == the packing definition:
+    packed position t = base len-1-t, 16 codes per word, code from ASCII bits 2 and 1."""
+    pkg = helpers.pkg()
+    L = pkg.lib()
+    nq = 257
+    rng = np.random.default_rng(length)
+    reads = np.frombuffer(b"ACGTacgtNn$", dtype=np.uint8)[rng.integers(0, 11, nq * length)].copy()
+    wpq = L.fmgpu_words_per_query(length)
+    a = np.full(nq * wpq, 0xDEADBEEF, dtype=np.uint32)
+    b = np.full(nq * wpq, 0xDEADBEEF, dtype=np.uint32)
+    L.fm_hostpack_reads(reads.ctypes.data, nq, length, a.ctypes.data, 0)
+    L.fm_hostpack_reads_scalar(reads.ctypes.data, nq, length, b.ctypes.data)
+    r = reads.reshape(nq, length).astype(np.uint32)
+    code = (((r >> 2) & 1) << 1) | (((r >> 2) & 1) ^ ((r >> 1) & 1))
+    want = np.zeros((nq, wpq), dtype=np.uint32)
+    for t in range(length):
+        want[:, t // 16] |= code[:, length - 1 - t] << np.uint32(2 * (t % 16))
+    assert np.array_equal(b.reshape(nq, wpq), want)
+    assert np.array_equal(a, b)
