@@ -282,6 +282,9 @@ uint64_t fmgpu_build_image_words(const fmgpu_build_t *b);
 void    *fmgpu_build_image_device(const fmgpu_build_t *b);          /* device pointer */
 int32_t  fmgpu_build_download(const fmgpu_build_t *b, uint32_t *h_image);
 int32_t  fmgpu_build_to_index(const fmgpu_build_t *b, fmgpu_index_t **out); /* re-block, no host round trip */
+/* the reference's layout transformers on the GPU, byte-identical file images: tag 101
+ * (src/transformIndexBitmaps.c:269-295), 200 and 201 (src/transformIndexAlternateCounters.c:387-479) */
+int32_t  fmgpu_build_transform(const fmgpu_build_t *tag100, uint32_t tag, fmgpu_build_t **out);
 int32_t  fmgpu_build_free(fmgpu_build_t **b);
 const char *fmgpu_build_last_error(void);
 /* reads of fm_synth.h (exact substrings, uniform start) as ASCII into device memory */

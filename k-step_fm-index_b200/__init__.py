@@ -141,6 +141,7 @@ PROTOTYPES = {
     "fmgpu_build_image_device": (_VP, [_VP]),
     "fmgpu_build_download": (C.c_int32, [_VP, _VP]),
     "fmgpu_build_to_index": (C.c_int32, [_VP, _VPP]),
+    "fmgpu_build_transform": (C.c_int32, [_VP, C.c_uint32, _VPP]),
     "fmgpu_build_free": (C.c_int32, [_VPP]),
     "fmgpu_build_last_error": (C.c_char_p, []),
     "fmgpu_synth_reads_device": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, _VP, _VP]),
@@ -388,6 +389,12 @@ class IndexBuild:
         h = C.c_void_p()
         check(lib().fmgpu_build_to_index(self.handle, C.byref(h)), "fmgpu_build_to_index")
         return DeviceIndex(h)
+
+    def transform(self, tag):
+        """Image of the reference's tfmiBMP (101) / tfmiAC (200, 201) output for this tag-100 build."""
+        h = C.c_void_p()
+        check(lib().fmgpu_build_transform(self.handle, tag, C.byref(h)), "fmgpu_build_transform")
+        return IndexBuild(h)
 
     def free(self):
         if self.handle:

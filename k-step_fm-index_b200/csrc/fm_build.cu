@@ -40,6 +40,7 @@
 
 struct fmgpu_build {
   int       device;
+  uint32_t  tag, ncounters;   /* 100 from the builder; 101/200/201 after fmgpu_build_transform */
   uint32_t  k, d, bwtsize, nentries, entry_words;
   uint32_t  dpos[2], dbase[2];
   uint32_t *d_image;     /* header (6 + 2k words) + entries, as in the file */
@@ -261,7 +262,7 @@ static int32_t fmb_build(int device, const char *h_ascii, uint64_t n, uint64_t s
   int32_t rc = FM_SUCCESS;
   fmgpu_build_t *b = (fmgpu_build_t *) calloc(1, sizeof(*b));
   if (!b) return FM_E_ALLOCATING_FMI;
-  b->device = device; b->k = k; b->d = d; b->bwtsize = (uint32_t)(n + 1);
+  b->device = device; b->k = k; b->d = d; b->bwtsize = (uint32_t)(n + 1); b->tag = 100; b->ncounters = 1u << (2 * k);
   b->nentries = (uint32_t)((n + 1 + d - 1) / d);
   b->entry_words = 2 * (d / 32) * k + (1u << (2 * k));
   b->image_words = 6 + 2 * k + (uint64_t) b->nentries * b->entry_words;
@@ -403,8 +404,99 @@ extern "C" int32_t fmgpu_build_download(const fmgpu_build_t *b, uint32_t *h_imag
 extern "C" int32_t fmgpu_build_to_index(const fmgpu_build_t *b, fmgpu_index_t **out)
 {
   if (!b || !out) return FM_E_BAD_ARGUMENT;
-  return fmgpu_index_create_from_device(b->device, 100, b->k, b->d, b->bwtsize, 1u << (2 * b->k), b->nentries,
+  return fmgpu_index_create_from_device(b->device, b->tag, b->k, b->d, b->bwtsize, b->ncounters, b->nentries,
                                         b->dpos, b->dbase, b->d_image + 6 + 2 * b->k, out);
+}
+
+/* ------------------------------------------------------------------------ *
+ * The reference's two layout transformers on the GPU, byte-identical outputs:
+ *   tag 101  per-32-row word interleave of the planes      src/transformIndexBitmaps.c:269-295
+ *   tag 200  half the counters per entry + padding entry   src/transformIndexAlternateCounters.c:434-479
+ *   tag 201  both                                          src/transformIndexAlternateCounters.c:387-432
+ * ------------------------------------------------------------------------ */
+__global__ void fmb_transform_kernel(const uint32_t *__restrict__ src, uint32_t k, uint32_t d, uint32_t nent_src,
+                                     uint32_t ew_src, uint32_t tag_dst, uint32_t *__restrict__ dst, uint32_t ew_dst)
+{
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nent_src) return;
+  const uint32_t W = d / 32, nsym = 1u << (2 * k), H = nsym / 2;
+  const bool ac = tag_dst >= 200, il = (tag_dst & 1u) != 0;
+  const uint32_t *se = src + (size_t) e * ew_src;
+  uint32_t *de = dst + (size_t) e * ew_dst;
+  uint32_t *dplanes = de + (ac ? H : 0u);
+  for (uint32_t s = 0; s < k; s++)
+    for (uint32_t bit = 0; bit < 2; bit++)
+      for (uint32_t n = 0; n < W; n++) {
+        const uint32_t w = se[2 * W * s + W * bit + n];
+        dplanes[il ? (2 * k * n + 2 * s + bit) : (2 * W * s + W * bit + n)] = w;
+      }
+  const uint32_t *scnt = se + 2 * W * k;
+  if (!ac) { for (uint32_t i = 0; i < nsym; i++) de[2 * W * k + i] = scnt[i]; }
+  else     { for (uint32_t i = 0; i < H; i++) de[i] = scnt[((e & 1u) ? H : 0u) + i]; }
+}
+
+/* AltCounters padding entry: zero planes; counters = last real entry's counters + rows of the last chunk
+ * carrying the symbol ('$' rows and the zero tail INCLUDED -- transformIndexAlternateCounters.c:420-431) */
+__global__ void fmb_ac_padding_kernel(const uint32_t *__restrict__ src, uint32_t k, uint32_t d, uint32_t nent_src,
+                                      uint32_t ew_src, uint32_t bwtsize, uint32_t *__restrict__ dst, uint32_t ew_dst)
+{
+  const uint32_t i = threadIdx.x;
+  const uint32_t W = d / 32, nsym = 1u << (2 * k), H = nsym / 2;
+  if (i >= H) return;
+  const uint32_t pad = nent_src, elast = bwtsize / d, r = bwtsize % d;
+  const uint32_t sigma = ((pad & 1u) ? H : 0u) + i;
+  const uint32_t *se = src + (size_t) elast * ew_src;
+  uint32_t cnt = (sigma == 0) ? d - r : 0u;
+  for (uint32_t n = 0; n < W; n++) {
+    const int32_t rem = (int32_t) r - (int32_t)(32 * n);
+    uint32_t m = rem <= 0 ? 0u : (rem >= 32 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> rem));
+    for (uint32_t s = 0; s < k; s++) {
+      const uint32_t c = (sigma >> (2 * s)) & 3u;
+      const uint32_t p0 = se[2 * W * s + n], p1 = se[2 * W * s + W + n];
+      m &= ((c & 1u) ? p0 : ~p0) & ((c & 2u) ? p1 : ~p1);
+    }
+    cnt += __popc(m);
+  }
+  uint32_t *de = dst + (size_t) pad * ew_dst;
+  de[i] = src[(size_t)(nent_src - 1) * ew_src + 2 * W * k + sigma] + cnt;
+  if (i == 0) for (uint32_t w = 0; w < 2 * W * k; w++) de[H + w] = 0u;
+}
+
+extern "C" int32_t fmgpu_build_transform(const fmgpu_build_t *src, uint32_t tag, fmgpu_build_t **out)
+{
+  if (!src || !out || src->tag != 100 || !(tag == 101 || tag == 200 || tag == 201)) return FM_E_BAD_ARGUMENT;
+  const bool ac = tag >= 200;
+  if (ac && src->bwtsize % src->d == 0) {
+    snprintf(g_berr, sizeof g_berr, "fmgpu_build_transform: bwtsize %% d == 0 is undefined in the reference AltCounters transformer");
+    return FM_E_NOT_IMPLEMENTED;
+  }
+  CU_TRY(cudaSetDevice(src->device));
+  fmgpu_build_t *b = (fmgpu_build_t *) calloc(1, sizeof(*b));
+  if (!b) return FM_E_ALLOCATING_FMI;
+  *b = *src;
+  const uint32_t k = src->k, nsym = 1u << (2 * k);
+  b->tag = tag; b->ncounters = ac ? nsym / 2 : nsym; b->nentries = src->nentries + (ac ? 1u : 0u);
+  b->entry_words = 2 * (src->d / 32) * k + b->ncounters;
+  b->image_words = 6 + 2 * k + (uint64_t) b->nentries * b->entry_words;
+  b->d_image = NULL;
+  cudaError_t e = cudaMalloc((void **) &b->d_image, b->image_words * 4);
+  if (e != cudaSuccess) { free(b); return fmb_fail(e, "cudaMalloc(transformed image)", __FILE__, __LINE__); }
+  const uint32_t *se = src->d_image + 6 + 2 * k;
+  uint32_t *de = b->d_image + 6 + 2 * k;
+  fmb_transform_kernel<<<(src->nentries + 127) / 128, 128>>>(se, k, src->d, src->nentries, src->entry_words, tag, de, b->entry_words);
+  e = cudaGetLastError();
+  if (e == cudaSuccess && ac) {
+    fmb_ac_padding_kernel<<<1, 32>>>(se, k, src->d, src->nentries, src->entry_words, src->bwtsize, de, b->entry_words);
+    e = cudaGetLastError();
+  }
+  uint32_t head[10];
+  head[0] = tag; head[1] = k; head[2] = b->bwtsize; head[3] = b->ncounters; head[4] = b->nentries; head[5] = b->d;
+  for (uint32_t s = 0; s < k; s++) { head[6 + s] = b->dpos[s]; head[6 + k + s] = b->dbase[s]; }
+  if (e == cudaSuccess) e = cudaMemcpy(b->d_image, head, (6 + 2 * k) * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { cudaFree(b->d_image); free(b); return fmb_fail(e, "fmgpu_build_transform", __FILE__, __LINE__); }
+  *out = b;
+  return FM_SUCCESS;
 }
 
 extern "C" int32_t fmgpu_build_free(fmgpu_build_t **pb)

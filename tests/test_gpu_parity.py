@@ -334,3 +334,63 @@ def test_gpu_builder_repetitive_text(pkg):
     with pytest.raises(pkg.FMError) as ei:
         pkg.IndexBuild.from_text(np.full(20000, ord("A"), dtype=np.uint8), 1, 64)
     assert ei.value.code == 8                                   # FM_E_BUILDING_BWT
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_gpu_transformers_reproduce_reference_files(pkg, path):
+    """tfmiBMP / tfmiAC on the GPU: tag 101, 200, 201 images byte-identical to the reference tools' files
+    (including the AltCounters padding entry), and searchable with the matching semantics."""
+    g = np.load(path)
+    n, k, d = int(g["n"]), int(g["k"]), int(g["d"])
+    seed = (100 + n) if os.path.basename(path).startswith("quirk") else 7 + k
+    b = pkg.IndexBuild.from_synth(n, seed, k, d)
+    length = int(g["length"])
+    for tag, key in ((101, "expected_std"), (200, "expected_ac"), (201, "expected_ac")):
+        t = b.transform(tag)
+        assert np.array_equal(t.download(), g[f"image_{tag}"]), f"tag {tag} image differs from the reference tool's file"
+        idx = t.to_index()
+        batch = pkg.DeviceBatch(0, g["reads"].size // length, length, k)
+        batch.upload_ascii(g["reads"])
+        batch.search(idx, pkg.variant(pkg.MODE_COOP))
+        assert np.array_equal(batch.download(), g[key])
+        batch.free(); idx.free(); t.free()
+    b.free()
+
+
+def test_config3_full_size_against_reference_checksums(pkg):
+    """BASELINE config 3 at FULL size (2 Gbp, k=2, d=64): the GPU-built index image, its three transformed
+    layouts and the (L,R) of the first 1 M reads must have the md5s recorded from the UNMODIFIED reference
+    tools (27-minute gfmiBaseLine build + tfmiBMP/tfmiAC + fmIndexSearchCPU[-ac]; tests/golden/config3_2g.json)."""
+    import hashlib
+    import json
+    gold = json.load(open(os.path.join(helpers.ROOT, "tests", "golden", "config3_2g.json")))
+    n, k, d = gold["text"]["n"], gold["k"], gold["d"]
+    b = pkg.IndexBuild.from_synth(n, gold["text"]["seed"], k, d)
+    img = b.download()
+    assert [int(v) for v in img[:10]] == gold["header_words"]
+    assert hashlib.md5(img.data).hexdigest() == gold["md5"]["tag100_fmi"]
+    del img
+    nq, length = gold["reads"]["num"], gold["reads"]["len"]
+    import torch
+    d_ascii = torch.empty(nq * length, dtype=torch.uint8, device="cuda")
+    pkg.check(pkg.lib().fmgpu_synth_reads_device(0, n, gold["text"]["seed"], nq, length, gold["reads"]["seed"], 0, d_ascii.data_ptr(), None), "reads")
+    torch.cuda.synchronize()
+    reads = d_ascii.cpu().numpy()
+    del d_ascii
+    batch = pkg.DeviceBatch(0, nq, length, k)
+    batch.upload_ascii(reads)
+    for tag, key in ((100, "res_cpu_std_text"), (101, "res_cpu_std_text"), (200, "res_cpu_ac_text"), (201, "res_cpu_ac_text")):
+        t = b if tag == 100 else b.transform(tag)
+        if tag != 100:
+            timg = t.download()
+            name = {101: "tag101_interleaving", 200: "tag200_ac", 201: "tag201_interleaving_ac"}[tag]
+            assert hashlib.md5(timg.data).hexdigest() == gold["md5"][name], f"tag {tag} image md5"
+            del timg
+        idx = t.to_index()
+        for mode in (pkg.MODE_TASK, pkg.MODE_COOP):
+            batch.search(idx, pkg.variant(mode))
+            assert helpers.results_text_md5(batch.download()) == gold["md5"][key], f"tag {tag} mode {mode}"
+        idx.free()
+        if tag != 100:
+            t.free()
+    batch.free(); b.free()
