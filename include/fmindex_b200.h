@@ -164,13 +164,15 @@ int32_t freeResultsGPU(void **results);
 typedef struct fmgpu_index fmgpu_index_t;   /* device-resident re-blocked index (one GPU) */
 typedef struct fmgpu_batch fmgpu_batch_t;   /* device-resident query shard + its results  */
 
-enum { FMGPU_MODE_TASK = 0, FMGPU_MODE_COOP = 1 };
+enum { FMGPU_MODE_TASK = 0, FMGPU_MODE_COOP = 1, FMGPU_MODE_FUSED = 2 };
 
 /* Kernel variant.  Zero-initialised = library defaults. */
 typedef struct {
   int32_t mode;               /* FMGPU_MODE_TASK: one thread per query (both endpoints);
                                  FMGPU_MODE_COOP: lane pair per query, L lane + R lane,
-                                 block fetch shared through warp shuffles             */
+                                 block fetch shared through warp shuffles;
+                                 FMGPU_MODE_FUSED: fused-step table (fmgpu_index_fuse): a lane group fetches one
+                                 32/64/128-byte block with 256-bit loads and consumes up to 4 bases per step   */
   int32_t queries_per_thread; /* independent queries interleaved per thread/lane pair: 1, 2 or 4 */
   int32_t threads_per_block;  /* 128, 256 or 512                                      */
   int32_t reserved;           /* fmgpu_search_host only (also $FMGPU_FEED): 0 = auto, 1 = upload ASCII and pack
@@ -190,6 +192,9 @@ typedef struct {
   uint32_t quirk_mask;   /* 2 bits per symbol: value the reference AC searcher adds there  */
   uint32_t reserved;
   uint64_t nbytes;       /* size of the block table                             */
+  uint32_t fused_bases;  /* bases per fused step (0 = no fused table), see fmgpu_index_fuse */
+  uint32_t fused_lanes;  /* lanes per fused block (block = 32 bytes per lane)   */
+  uint64_t fused_bytes;  /* size of the fused table                             */
 } fmgpu_index_meta_t;
 
 /* devices ---------------------------------------------------------------- */
@@ -218,6 +223,12 @@ int32_t fmgpu_index_replicate(const fmgpu_index_t *src, int32_t device, fmgpu_in
 /* replica in another PROCESS: allocate an empty table of the same shape, then
  * fill fmgpu_index_blocks() with a broadcast (NCCL) from the owner */
 int32_t fmgpu_index_alloc_like(int32_t device, const fmgpu_index_meta_t *meta, fmgpu_index_t **out);
+/* Fused-step table, composed on the GPU from this replica's own block table: one fused step = fused_bases/k
+ * reference LF steps (exactly), one 256-bit load per lane of a `lanes`-lane group per rank.  fused_bases 0 =
+ * the widest of 4,3,2 that is a multiple of k and fits `budget_bytes` (0 = ~69 GB or free memory); lanes 0 = 2.
+ * FM_E_NOT_IMPLEMENTED when nothing fits or the index carries the AltCounters padding quirk. */
+int32_t fmgpu_index_fuse(fmgpu_index_t *idx, uint32_t fused_bases, uint32_t lanes, uint64_t budget_bytes);
+int32_t fmgpu_index_unfuse(fmgpu_index_t *idx);
 int32_t fmgpu_index_get_meta(const fmgpu_index_t *idx, fmgpu_index_meta_t *meta);
 void   *fmgpu_index_blocks(const fmgpu_index_t *idx);     /* device pointer */
 int32_t fmgpu_index_device(const fmgpu_index_t *idx);

@@ -30,7 +30,7 @@ FM_E_CUDA = 50
 FM_E_BAD_ARGUMENT = 51
 FM_E_UNSUPPORTED_INDEX = 52
 FM_E_QUERY_SHAPE = 53
-MODE_TASK, MODE_COOP = 0, 1
+MODE_TASK, MODE_COOP, MODE_FUSED = 0, 1, 2
 
 
 def build_native(verbose=False):
@@ -67,7 +67,7 @@ class fmgpu_variant_t(C.Structure):
 class fmgpu_index_meta_t(C.Structure):
     _fields_ = [("steps", C.c_uint32), ("bwtsize", C.c_uint32), ("nsymbols", C.c_uint32), ("nblocks", C.c_uint32),
                 ("source_tag", C.c_uint32), ("quirk_start", C.c_uint32), ("quirk_mask", C.c_uint32), ("reserved", C.c_uint32),
-                ("nbytes", C.c_uint64)]
+                ("nbytes", C.c_uint64), ("fused_bases", C.c_uint32), ("fused_lanes", C.c_uint32), ("fused_bytes", C.c_uint64)]
 
 
 _VP, _VPP = C.c_void_p, C.POINTER(C.c_void_p)
@@ -104,6 +104,8 @@ PROTOTYPES = {
                                                    C.c_uint32, _U32P, _U32P, _VP, _VPP]),
     "fmgpu_index_replicate": (C.c_int32, [_VP, C.c_int32, _VPP]),
     "fmgpu_index_alloc_like": (C.c_int32, [C.c_int32, C.POINTER(fmgpu_index_meta_t), _VPP]),
+    "fmgpu_index_fuse": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, C.c_uint64]),
+    "fmgpu_index_unfuse": (C.c_int32, [_VP]),
     "fmgpu_index_get_meta": (C.c_int32, [_VP, C.POINTER(fmgpu_index_meta_t)]),
     "fmgpu_index_blocks": (_VP, [_VP]),
     "fmgpu_index_device": (C.c_int32, [_VP]),
@@ -281,6 +283,14 @@ class DeviceIndex:
         h = C.c_void_p()
         check(lib().fmgpu_index_alloc_like(device, C.byref(meta), C.byref(h)), "fmgpu_index_alloc_like")
         return cls(h)
+
+    def fuse(self, fused_bases=0, lanes=0, budget_bytes=0):
+        """Builds the fused-step table (up to 4 bases per rank, 256-bit loads) for MODE_FUSED searches."""
+        check(lib().fmgpu_index_fuse(self.handle, fused_bases, lanes, budget_bytes), "fmgpu_index_fuse")
+        return self
+
+    def unfuse(self):
+        check(lib().fmgpu_index_unfuse(self.handle), "fmgpu_index_unfuse")
 
     def replicate(self, device):
         h = C.c_void_p()

@@ -18,11 +18,14 @@
 #include <cuda_runtime.h>
 #include "../../include/fmindex_b200.h"
 #include "fm_kernels.cuh"
+#include "fm_fused.cuh"
 
 struct fmgpu_index {
   int                device;
   fmgpu_index_meta_t meta;
   uint4             *blocks;
+  uint4             *fblocks;      /* fused-step table (fmgpu_index_fuse), or NULL */
+  uint32_t           nfblocks;     /* fused blocks per fused symbol */
 };
 
 struct fmgpu_batch {
@@ -214,9 +217,140 @@ extern "C" int32_t fmgpu_index_free(fmgpu_index_t **pidx)
 {
   if (!pidx || !*pidx) return FM_SUCCESS;
   fmgpu_index_t *idx = *pidx;
-  if (idx->blocks) { cudaSetDevice(idx->device); cudaFree(idx->blocks); }
+  if (idx->blocks || idx->fblocks) { cudaSetDevice(idx->device); cudaFree(idx->blocks); cudaFree(idx->fblocks); }
   free(idx);
   *pidx = NULL;
+  return FM_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------ *
+ * fused-step table (fm_fused.cuh)
+ * ------------------------------------------------------------------------ */
+static uint32_t fm_fused_rows(uint32_t lanes) { return 32u * (8u * lanes - 1u); }
+
+template <int LANES>
+static cudaError_t fm_fuse_build(const fmgpu_index_t *idx, const uint16_t *fsym, uint32_t nfsym, uint32_t nfb, uint32_t kbits,
+                                 uint32_t hops, uint4 *fblocks)
+{
+  fm_fuse_write_kernel<LANES><<<nfb, 256, 256 * 8 * LANES * 4>>>(fsym, nfsym, nfb, fblocks);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  fm_fuse_scan_kernel<LANES><<<nfsym, 1024>>>(idx->blocks, idx->meta.nblocks, kbits, hops, nfb, fblocks);
+  return cudaGetLastError();
+}
+
+extern "C" int32_t fmgpu_index_fuse(fmgpu_index_t *idx, uint32_t fused_bases, uint32_t lanes, uint64_t budget_bytes)
+{
+  if (!idx) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null index");
+  if (idx->fblocks) return FM_SUCCESS;
+  if (idx->meta.quirk_mask) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "fused steps are unavailable for an AltCounters index carrying the padding-entry quirk");
+  CU_TRY(cudaSetDevice(idx->device));
+  const uint32_t k = idx->meta.steps;
+  if (lanes == 0) lanes = 2;
+  if (!(lanes == 1 || lanes == 2 || lanes == 4)) return fm_fail_msg(FM_E_BAD_ARGUMENT, "fused block lanes must be 1, 2 or 4");
+  if (budget_bytes == 0) {
+    const char *env = getenv("FMGPU_FUSE_BUDGET_GB");
+    budget_bytes = (uint64_t)((env && *env ? atof(env) : 69.0) * 1e9);       /* flat part of the footprint curve ends near 68-70 GB */
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > (6ull << 30) && budget_bytes > free_b - (6ull << 30)) budget_bytes = free_b - (6ull << 30);
+  }
+  const uint32_t rows = fm_fused_rows(lanes);
+  const uint32_t nfb = idx->meta.bwtsize / rows + 1;
+  uint32_t kf = 0;
+  for (uint32_t cand = 4; cand > k; cand--) {
+    if (fused_bases && cand != fused_bases) continue;
+    if (cand % k) continue;
+    const uint64_t bytes = ((uint64_t) 1 << (2 * cand)) * nfb * 32ull * lanes;
+    /* construction also needs 3 bytes per row of scratch */
+    if (bytes + 3ull * idx->meta.bwtsize <= budget_bytes || fused_bases) { kf = cand; break; }
+  }
+  if (!kf) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "no fused-step table fits the memory budget for this index (or k already is the requested width)");
+  const uint32_t nfsym = 1u << (2 * kf), hops = kf / k, kbits = 2 * k;
+  const uint64_t fbytes = (uint64_t) nfsym * nfb * 32ull * lanes;
+  uint64_t nrows = (uint64_t) idx->meta.nblocks * FM_SB_ROWS;
+  if ((uint64_t) nfb * rows > nrows) nrows = (uint64_t) nfb * rows;
+  uint8_t *sym = NULL; uint16_t *fsym = NULL; uint4 *fblocks = NULL;
+  cudaError_t e = cudaMalloc((void **) &fblocks, fbytes);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &sym, nrows);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &fsym, nrows * 2);
+  if (e == cudaSuccess) {
+    fm_fuse_symbols_kernel<<<(idx->meta.nblocks + 127) / 128, 128>>>(idx->blocks, idx->meta.nblocks, idx->meta.nsymbols, nrows, sym);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) {
+    fm_fuse_compose_kernel<<<(unsigned)((nrows + 255) / 256), 256>>>(idx->blocks, idx->meta.nblocks, sym, idx->meta.bwtsize, kbits, hops, nrows, fsym);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = lanes == 1 ? fm_fuse_build<1>(idx, fsym, nfsym, nfb, kbits, hops, fblocks)
+                          : lanes == 2 ? fm_fuse_build<2>(idx, fsym, nfsym, nfb, kbits, hops, fblocks)
+                                       : fm_fuse_build<4>(idx, fsym, nfsym, nfb, kbits, hops, fblocks);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaFree(sym); cudaFree(fsym);
+  if (e != cudaSuccess) { cudaFree(fblocks); return fm_fail(e, "fmgpu_index_fuse", __FILE__, __LINE__); }
+  idx->fblocks = fblocks; idx->nfblocks = nfb;
+  idx->meta.fused_bases = kf; idx->meta.fused_lanes = lanes; idx->meta.fused_bytes = fbytes;
+  return FM_SUCCESS;
+}
+
+extern "C" int32_t fmgpu_index_unfuse(fmgpu_index_t *idx)
+{
+  if (!idx) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null index");
+  if (idx->fblocks) { CU_TRY(cudaSetDevice(idx->device)); cudaFree(idx->fblocks); idx->fblocks = NULL; }
+  idx->nfblocks = 0; idx->meta.fused_bases = 0; idx->meta.fused_lanes = 0; idx->meta.fused_bytes = 0;
+  return FM_SUCCESS;
+}
+
+typedef void (*fm_fused_fn)(const FmFusedParams);
+
+template <int KF, int K, int LANES>
+static fm_fused_fn fm_pick_fused_q(int qpt)
+{
+  if (qpt == 1) return fm_search_fused_kernel<KF, K, LANES, 1, 256, 6>;
+  if (qpt == 2) return fm_search_fused_kernel<KF, K, LANES, 2, 256, 4>;
+  return NULL;
+}
+template <int KF, int K>
+static fm_fused_fn fm_pick_fused_l(int lanes, int qpt)
+{
+  if (lanes == 1) return fm_pick_fused_q<KF, K, 1>(qpt);
+  if (lanes == 2) return fm_pick_fused_q<KF, K, 2>(qpt);
+  if (lanes == 4) return fm_pick_fused_q<KF, K, 4>(qpt);
+  return NULL;
+}
+static fm_fused_fn fm_pick_fused(uint32_t kf, uint32_t k, int lanes, int qpt)
+{
+  if (kf == 4 && k == 2) return fm_pick_fused_l<4, 2>(lanes, qpt);
+  if (kf == 4 && k == 1) return fm_pick_fused_l<4, 1>(lanes, qpt);
+  if (kf == 3 && k == 1) return fm_pick_fused_l<3, 1>(lanes, qpt);
+  if (kf == 2 && k == 1) return fm_pick_fused_l<2, 1>(lanes, qpt);
+  return NULL;
+}
+
+static int32_t fm_launch_fused(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nq, uint32_t len,
+                               uint32_t *d_results, fmgpu_variant_t v, cudaStream_t stream)
+{
+  if (!idx->fblocks) return fm_fail_msg(FM_E_BAD_ARGUMENT, "FMGPU_MODE_FUSED needs fmgpu_index_fuse() on this replica first");
+  const uint32_t k = idx->meta.steps, kf = idx->meta.fused_bases, lanes = idx->meta.fused_lanes, hops = kf / k;
+  if (v.queries_per_thread != 1 && v.queries_per_thread != 2) v.queries_per_thread = 2;
+  FmFusedParams p;
+  p.fblocks = idx->fblocks; p.blocks = idx->blocks; p.packed = d_packed; p.results = d_results;
+  p.nfblocks = idx->nfblocks; p.nblocks = idx->meta.nblocks; p.nq = (uint32_t) nq;
+  p.nlead = (len / k) % hops; p.nfused = (len / k) / hops;
+  p.wpq = fmgpu_words_per_query(len); p.wpq_pad = (p.wpq + 1) | 1u; p.bwtsize = idx->meta.bwtsize;
+  uint32_t qper; size_t smem;
+  for (;;) {
+    qper = (256 / lanes) * v.queries_per_thread;
+    smem = (size_t) qper * p.wpq_pad * 4;
+    if (smem <= 200 * 1024) break;
+    if (v.queries_per_thread > 1) v.queries_per_thread = 1;
+    else return fm_fail_msg(FM_E_QUERY_SHAPE, "reads too long to stage in shared memory");
+  }
+  fm_fused_fn fn = fm_pick_fused(kf, k, (int) lanes, v.queries_per_thread);
+  if (!fn) return fm_fail_msg(FM_E_BAD_ARGUMENT, "no fused kernel for this (fused bases, k, lanes)");
+  if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  const uint32_t grid = (uint32_t)((nq + qper - 1) / qper);
+  void *args[] = { (void *) &p };
+  CU_TRY(cudaLaunchKernel((const void *) fn, dim3(grid), dim3(256), args, smem, stream));
   return FM_SUCCESS;
 }
 
@@ -281,6 +415,7 @@ static int32_t fm_launch_search(const fmgpu_index_t *idx, const uint32_t *d_pack
   if (v.threads_per_block == 0) v.threads_per_block = FM_DEFAULT_VARIANT.threads_per_block;
   const bool count = d_counters != NULL;
   if (count) { v.mode = FMGPU_MODE_TASK; v.queries_per_thread = 1; v.threads_per_block = 256; }
+  if (v.mode == FMGPU_MODE_FUSED) return fm_launch_fused(idx, d_packed, nq, len, d_results, vin ? *vin : FM_DEFAULT_VARIANT, stream);
 
   FmSearchParams p;
   p.blocks = idx->blocks; p.packed = d_packed; p.results = d_results; p.fetch_counters = d_counters;

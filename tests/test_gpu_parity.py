@@ -394,3 +394,67 @@ def test_config3_full_size_against_reference_checksums(pkg):
         if tag != 100:
             t.free()
     batch.free(); b.free()
+
+
+# --------------------------------------------------------------------------- #
+# fused-step layout (fm_fused.cuh): up to 4 bases per rank, composed from the index's own LF mapping
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("path", [p for p in GOLDEN if "quirk" not in p], ids=lambda p: os.path.basename(p))
+def test_fused_steps_all_widths(pkg, path):
+    g = np.load(path)
+    reads, length, k = g["reads"], int(g["length"]), int(g["k"])
+    nq = reads.size // length
+    for tag, key in ((100, "expected_std"), (201, "expected_ac")):
+        for kf in ([2, 3, 4] if k == 1 else [4]):
+            for lanes in (1, 2, 4):
+                idx = pkg.DeviceIndex.from_image(g[f"image_{tag}"]).fuse(kf, lanes)
+                m = idx.meta
+                assert (m.fused_bases, m.fused_lanes) == (kf, lanes) and m.fused_bytes == 4 ** kf * (m.bwtsize // (32 * (8 * lanes - 1)) + 1) * 32 * lanes
+                b = pkg.DeviceBatch(0, nq, length, k)
+                b.upload_ascii(reads)
+                for qpt in (1, 2):
+                    b.search(idx, pkg.variant(pkg.MODE_FUSED, qpt))
+                    assert np.array_equal(b.download(), g[key]), f"tag {tag} kf {kf} lanes {lanes} qpt {qpt}"
+                b.free(); idx.free()
+
+
+@pytest.mark.parametrize("k,length", [(1, 1), (1, 3), (1, 5), (1, 17), (1, 33), (1, 100), (2, 2), (2, 6), (2, 30), (2, 34), (2, 100),
+                                      (2, 126), (2, 128), (2, 250), (1, 251)])
+def test_fused_steps_read_lengths(pkg, k, length):
+    """Lengths that are not a multiple of the fused width run their leading steps on the SB96 table; bit fields
+    of the packed read straddle 32-bit words."""
+    g = np.load(os.path.join(helpers.ROOT, "tests", "golden", f"small_k{k}_d64.npz"))
+    text = helpers.synth_text(int(g["n"]), seed=7 + k)
+    reads = np.concatenate([helpers.synth_reads(text, 21, 700, length), ACGT[np.random.default_rng(length).integers(0, 4, 68 * length)]])
+    o = helpers.Oracle()
+    h = o.wrap(g["image_101"])
+    want = o.search(h, reads, length)
+    o.free(h)
+    for kf in ([3, 4] if k == 1 else [4]):
+        idx = pkg.DeviceIndex.from_image(g["image_101"]).fuse(kf, 2)
+        b = pkg.DeviceBatch(0, reads.size // length, length, k)
+        b.upload_ascii(reads)
+        b.search(idx, pkg.variant(pkg.MODE_FUSED))
+        assert np.array_equal(b.download(), want), f"k={k} len={length} kf={kf}"
+        b.free(); idx.free()
+
+
+def test_fused_unavailable_cases(pkg):
+    g = np.load(os.path.join(helpers.ROOT, "tests", "golden", "quirk_k2_n124.npz"))
+    idx = pkg.DeviceIndex.from_image(g["image_200"])           # AltCounters padding quirk: not representable
+    with pytest.raises(pkg.FMError) as ei:
+        idx.fuse()
+    assert ei.value.code == 19
+    b = pkg.DeviceBatch(0, 4, 8, 2)
+    b.upload_ascii(g["reads"][:32])
+    with pytest.raises(pkg.FMError) as ei:
+        b.search(idx, pkg.variant(pkg.MODE_FUSED))             # not fused: loud failure, no silent fallback
+    assert ei.value.code == pkg.FM_E_BAD_ARGUMENT
+    b.free(); idx.free()
+    idx = pkg.DeviceIndex.from_image(g["image_100"])           # same text, standard file: fusable
+    idx.fuse(4, 2)
+    b = pkg.DeviceBatch(0, g["reads"].size // 8, 8, 2)
+    b.upload_ascii(g["reads"])
+    b.search(idx, pkg.variant(pkg.MODE_FUSED))
+    assert np.array_equal(b.download(), g["expected_std"])
+    b.free(); idx.free()
