@@ -47,7 +47,7 @@ K_STEPS = int(os.environ.get("FM_BENCH_K", "2"))
 CHUNK = 64
 SEED_REF, SEED_READS = 1, 2
 CPU_SAMPLE = int(float(os.environ.get("FM_BENCH_CPU_SAMPLE", "1e6")))
-MODE = os.environ.get("FM_BENCH_MODE", "coop")
+MODE = os.environ.get("FM_BENCH_MODE", "fused")           # fused | coop | task
 
 
 class ClockSampler:
@@ -93,10 +93,11 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the search kernel from the committed ncu capture, if there is one."""
+def ncu_traffic(fused):
+    """dram bytes per launch of the timed search kernel from the committed ncu capture (profiles/), if there is one."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))["dram_bytes_per_launch_10m_reads"] * NQ_PER_GPU / 1e7
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
+        return d["fused" if fused else "plain"]["dram_bytes_per_launch_10m_reads"] * NQ_PER_GPU / 1e7
     except Exception:
         return None
 
@@ -222,21 +223,51 @@ def main():
     pkg.check(L.fmgpu_pack_queries_device(dev, d_ascii.data_ptr(), nq, READ_LEN, d_packed.data_ptr(), stream), "pack")
     torch.cuda.synchronize()
     del d_ascii
-    var = pkg.variant(pkg.MODE_COOP if MODE == "coop" else pkg.MODE_TASK, int(os.environ.get("FM_BENCH_QPT", "1")),
-                      int(os.environ.get("FM_BENCH_TPB", "256")))
+    plain_var = pkg.variant(pkg.MODE_TASK if MODE == "task" else pkg.MODE_COOP, int(os.environ.get("FM_BENCH_QPT", "1")),
+                            int(os.environ.get("FM_BENCH_TPB", "256")))
+    var, fused = plain_var, False
+    if MODE == "fused":
+        # fused-step table composed on this replica from its own 2-step block table (every rank builds its own)
+        try:
+            t0 = time.time()
+            index.fuse()
+            torch.cuda.synchronize()
+            setup["fuse_s"] = round(time.time() - t0, 3)
+            var, fused = pkg.variant(pkg.MODE_FUSED, int(os.environ.get("FM_BENCH_QPT", "2"))), True
+        except pkg.FMError as ex:
+            setup["fuse_unavailable"] = str(ex)
+    meta = index.meta
 
-    def search_step():
-        pkg.check(L.fmgpu_search_device(index.handle, d_packed.data_ptr(), nq, READ_LEN, d_res.data_ptr(), C.byref(var), stream), "search")
+    def search_step(v=None):
+        pkg.check(L.fmgpu_search_device(index.handle, d_packed.data_ptr(), nq, READ_LEN, d_res.data_ptr(), C.byref(v or var), stream), "search")
 
-    # algorithmic bytes: exact count of necessary sector fetches for THIS rank's reads
+    # algorithmic bytes: exact count of the 32-byte sectors the 2-step search of THIS rank's reads must touch
     nblk, nsec = C.c_uint64(), C.c_uint64()
     pkg.check(L.fmgpu_count_fetches_device(index.handle, d_packed.data_ptr(), nq, READ_LEN, d_res.data_ptr(), stream,
                                            C.byref(nblk), C.byref(nsec)), "count fetches")
     lf_steps = nq * (READ_LEN // K_STEPS)
     algo_bytes = nsec.value * 32
+    nfb, nlb = C.c_uint64(), C.c_uint64()
+    if fused:
+        pkg.check(L.fmgpu_count_fetches_fused_device(index.handle, d_packed.data_ptr(), nq, READ_LEN, d_res.data_ptr(), stream,
+                                                     C.byref(nfb), C.byref(nlb)), "count fused fetches")
 
-    # measured random-access ceiling over the same footprint (rank 0, once)
-    probe = pkg.gather_probe(dev, int(index.meta.nbytes), 512, 3) if rank == 0 else 0.0
+    # measured random-access ceiling over the footprint the timed kernel walks (rank 0, once)
+    footprint = int(meta.fused_bytes) if fused else int(meta.nbytes)
+    probe = pkg.gather_probe(dev, footprint, 256, 2) if rank == 0 else 0.0
+
+    # the plain 2-step kernel on the same reads, for reference next to the fused one (rank-local, not the headline)
+    plain = None
+    if fused:
+        for _ in range(3):
+            search_step(plain_var)
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        for _ in range(5):
+            search_step(plain_var)
+        pe1.record(); torch.cuda.synchronize()
+        plain = {"kernel": "coop" if plain_var.mode == pkg.MODE_COOP else "task", "ms_per_step": pe0.elapsed_time(pe1) / 5,
+                 "mqueries_per_s_per_gpu": nq / (pe0.elapsed_time(pe1) / 5) / 1e3}
     setup["setup_s"] = round(time.time() - t_setup, 2)
 
     # ------------------------------------------------------------------ timed: device-resident
@@ -295,17 +326,25 @@ def main():
             "metric": "Mqueries/s", "value": mq, "unit": "Mqueries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "lf_steps_per_s": world * lf_steps / (ms_step * 1e-3),
-            "config": {"workload": workload, "kernel": f"{MODE} qpt={var.queries_per_thread} tpb={var.threads_per_block}",
-                       "device_layout": "SB96 (16-byte per-symbol blocks: u32 rank + 96 indicator bits)",
-                       "l2": "inputs larger than L2 (5.33 GB block table, 250 MB packed reads), no flush",
+            "config": {"workload": workload,
+                       "kernel": (f"fused: {meta.fused_bases} bases/step, {32 * meta.fused_lanes}-byte blocks, {meta.fused_lanes} x 256-bit loads, qpt={var.queries_per_thread}"
+                                  if fused else f"{MODE} qpt={var.queries_per_thread} tpb={var.threads_per_block}"),
+                       "device_layout": (f"fused-step table {meta.fused_bytes / 1e9:.1f} GB composed on the GPU from the 2-step SB96 table ({meta.nbytes / 1e9:.2f} GB)"
+                                         if fused else "SB96 (16-byte per-symbol blocks: u32 rank + 96 indicator bits)"),
+                       "l2": f"inputs larger than L2 ({footprint / 1e9:.1f} GB table, 250 MB packed reads vs 126 MB L2), no flush",
                        "parallelism": f"index replicated, reads sharded x{world}, no collective in the search", "setup": setup},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(fused),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+                         "algorithmic_model": "SURVEY 8(d): 32 B x exact count of sectors the 2-step search must touch (LF steps x |{sector(L),sector(R)}|)",
                          "sectors_per_lf_step": nsec.value / lf_steps, "blocks_per_lf_step": nblk.value / lf_steps,
-                         "random_access_ceiling": {"loads_per_s": probe, "sector_gbs": probe * 32 / 1e9,
-                                                   "how": "independent uniform random 16-byte loads over a table of the index's size",
-                                                   "lf_steps_per_s_per_gpu_over_ceiling": (lf_steps / (ms_step * 1e-3)) / probe if probe else None},
+                         "fused_blocks_per_launch": nfb.value if fused else None,
+                         "fused_block_bytes_per_launch": nfb.value * 32 * meta.fused_lanes if fused else None,
+                         "dram_line_gbs": (nfb.value if fused else nblk.value) * 128 / (ms_step * 1e-3) / 1e9,
+                         "random_access_ceiling": {"accesses_per_s": probe, "line_gbs": probe * 128 / 1e9,
+                                                   "how": "independent uniform random 16-byte loads over a table of the same footprint; every miss moves a 128-byte line",
+                                                   "block_fetches_per_s_over_ceiling": ((nfb.value if fused else nblk.value) / (ms_step * 1e-3)) / probe if probe else None},
                          "frac_of_nominal_8tbs": achieved / 8000.0},
+            "plain_2step_kernel": plain,
             "cpu_baseline": cpu,
             "e2e": {"value": world * nq / e2e_ms_step / 1e3, "unit": "Mqueries/s", "ms_per_step": e2e_ms_step,
                     "h2d_bytes_per_step": nq * READ_LEN, "d2h_bytes_per_step": nq * 8, "matches_device_resident_result": same},

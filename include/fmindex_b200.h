@@ -309,6 +309,9 @@ int32_t fmgpu_gather_probe(int32_t device, uint64_t table_bytes, uint64_t loads_
 /* same with `access_bytes` (16/32/64/128) consecutive bytes per random access */
 int32_t fmgpu_gather_probe_ex(int32_t device, uint64_t table_bytes, uint32_t access_bytes, uint64_t loads_per_thread,
                               int32_t iters, double *accesses_per_second);
+/* same for FMGPU_MODE_FUSED: fused-table blocks and SB96 blocks (leading steps) one search must fetch */
+int32_t fmgpu_count_fetches_fused_device(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nqueries, uint32_t len,
+                                         uint32_t *d_results, void *stream, uint64_t *nfused_blocks, uint64_t *nlead_blocks);
 /* locality variant: the 32 lanes of every warp-level load fall inside ONE random window of
  * `window_bytes` (e.g. one 2 MB page), random blocks inside it: isolates address-translation cost */
 int32_t fmgpu_gather_probe_local(int32_t device, uint64_t table_bytes, uint64_t window_bytes, uint64_t loads_per_thread,

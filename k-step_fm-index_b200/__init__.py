@@ -137,6 +137,7 @@ PROTOTYPES = {
     "fm_hostpack_threads": (C.c_int, []),
     "fmgpu_gather_probe_local": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.POINTER(C.c_double)]),
     "fmgpu_count_fetches_device": (C.c_int32, [_VP, _VP, C.c_uint64, C.c_uint32, _VP, _VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "fmgpu_count_fetches_fused_device": (C.c_int32, [_VP, _VP, C.c_uint64, C.c_uint32, _VP, _VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "fmgpu_build_from_text": (C.c_int32, [C.c_int32, _VP, C.c_uint64, C.c_uint32, C.c_uint32, _VPP]),
     "fmgpu_build_from_synth": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, _VPP]),
     "fmgpu_build_image_words": (C.c_uint64, [_VP]),

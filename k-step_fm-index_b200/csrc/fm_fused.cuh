@@ -46,6 +46,7 @@ struct FmFusedParams {
   uint32_t nfused;            /* fused steps                                                       */
   uint32_t wpq, wpq_pad;      /* wpq_pad >= wpq + 1: a bit field may straddle into the next word   */
   uint32_t bwtsize;
+  unsigned long long *fetch_counters;  /* COUNT only: [0] = fused blocks fetched, [1] = SB96 blocks of the leading steps */
 };
 
 __device__ __forceinline__ void fm_ldg32(const uint4 *p, uint32_t (&w)[8])
@@ -100,7 +101,7 @@ __device__ __forceinline__ uint32_t fm_read_field(const uint32_t *q, uint32_t po
  * Fused search: a group of LANES lanes owns QPT reads (both endpoints of each).  Per fused step the group
  * issues ONE coalesced fetch of the block of L (and a second one only when R lies in another block).
  * ------------------------------------------------------------------------ */
-template <int KF, int K, int LANES, int QPT, int THREADS, int MINB>
+template <int KF, int K, int LANES, int QPT, int THREADS, int MINB, bool COUNT>
 __global__ void __launch_bounds__(THREADS, MINB) fm_search_fused_kernel(const FmFusedParams p)
 {
   extern __shared__ uint32_t sq[];
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_fused_kernel(const Fm
     L[i] = 0u; R[i] = p.bwtsize;
   }
 
+  unsigned long long nf_fetch = 0, nl_fetch = 0;
   /* leading base-k steps on SB96 (every lane of the group computes them redundantly: same address, one request) */
   uint32_t pos = 0;
   for (uint32_t step = 0; step < p.nlead; step++, pos += BBITS) {
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_fused_kernel(const Fm
       const uint4 *base = p.blocks + (size_t) sig * p.nblocks;
       const uint4 vL = fm_ldg16(base + bL);
       const uint4 vR = (bL == bR) ? vL : fm_ldg16(base + bR);
+      if (COUNT && live[i] && lg == 0) nl_fetch += (bL == bR) ? 1 : 2;
       L[i] = fm_block_rank(vL, L[i] - bL * FM_SB_ROWS);
       R[i] = fm_block_rank(vR, R[i] - bR * FM_SB_ROWS);
     }
@@ -159,6 +162,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_fused_kernel(const Fm
       rL[i] = L[i] - bL * ROWS; rR[i] = R[i] - bR * ROWS;
       const uint4 *base = p.fblocks + ((size_t) sig * p.nfblocks) * (2 * LANES) + 2 * lg;
       same[i] = (bL == bR);
+      if (COUNT && live[i] && lg == 0) nf_fetch += same[i] ? 1 : 2;
       fm_ldg32(base + (size_t) bL * (2 * LANES), wL[i]);
       if (!same[i]) fm_ldg32(base + (size_t) bR * (2 * LANES), wR[i]);
     }
@@ -181,6 +185,13 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_fused_kernel(const Fm
     #pragma unroll
     for (int i = 0; i < QPT; i++)
       if (live[i]) reinterpret_cast<uint2 *>(p.results)[q0 + i * GROUPS + group] = make_uint2(L[i], R[i]);
+  }
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) {
+      nf_fetch += __shfl_xor_sync(0xFFFFFFFFu, nf_fetch, o);
+      nl_fetch += __shfl_xor_sync(0xFFFFFFFFu, nl_fetch, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(p.fetch_counters, nf_fetch); atomicAdd(p.fetch_counters + 1, nl_fetch); }
   }
 }
 

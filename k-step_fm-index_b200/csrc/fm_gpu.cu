@@ -305,8 +305,9 @@ typedef void (*fm_fused_fn)(const FmFusedParams);
 template <int KF, int K, int LANES>
 static fm_fused_fn fm_pick_fused_q(int qpt)
 {
-  if (qpt == 1) return fm_search_fused_kernel<KF, K, LANES, 1, 256, 6>;
-  if (qpt == 2) return fm_search_fused_kernel<KF, K, LANES, 2, 256, 4>;
+  if (qpt == 0) return fm_search_fused_kernel<KF, K, LANES, 1, 256, 6, true>;      /* instrumented */
+  if (qpt == 1) return fm_search_fused_kernel<KF, K, LANES, 1, 256, 6, false>;
+  if (qpt == 2) return fm_search_fused_kernel<KF, K, LANES, 2, 256, 4, false>;
   return NULL;
 }
 template <int KF, int K>
@@ -327,7 +328,7 @@ static fm_fused_fn fm_pick_fused(uint32_t kf, uint32_t k, int lanes, int qpt)
 }
 
 static int32_t fm_launch_fused(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nq, uint32_t len,
-                               uint32_t *d_results, fmgpu_variant_t v, cudaStream_t stream)
+                               uint32_t *d_results, fmgpu_variant_t v, cudaStream_t stream, unsigned long long *d_counters = NULL)
 {
   if (!idx->fblocks) return fm_fail_msg(FM_E_BAD_ARGUMENT, "FMGPU_MODE_FUSED needs fmgpu_index_fuse() on this replica first");
   const uint32_t k = idx->meta.steps, kf = idx->meta.fused_bases, lanes = idx->meta.fused_lanes, hops = kf / k;
@@ -337,6 +338,8 @@ static int32_t fm_launch_fused(const fmgpu_index_t *idx, const uint32_t *d_packe
   p.nfblocks = idx->nfblocks; p.nblocks = idx->meta.nblocks; p.nq = (uint32_t) nq;
   p.nlead = (len / k) % hops; p.nfused = (len / k) / hops;
   p.wpq = fmgpu_words_per_query(len); p.wpq_pad = (p.wpq + 1) | 1u; p.bwtsize = idx->meta.bwtsize;
+  p.fetch_counters = d_counters;
+  if (d_counters) v.queries_per_thread = 1;
   uint32_t qper; size_t smem;
   for (;;) {
     qper = (256 / lanes) * v.queries_per_thread;
@@ -345,7 +348,7 @@ static int32_t fm_launch_fused(const fmgpu_index_t *idx, const uint32_t *d_packe
     if (v.queries_per_thread > 1) v.queries_per_thread = 1;
     else return fm_fail_msg(FM_E_QUERY_SHAPE, "reads too long to stage in shared memory");
   }
-  fm_fused_fn fn = fm_pick_fused(kf, k, (int) lanes, v.queries_per_thread);
+  fm_fused_fn fn = fm_pick_fused(kf, k, (int) lanes, d_counters ? 0 : v.queries_per_thread);
   if (!fn) return fm_fail_msg(FM_E_BAD_ARGUMENT, "no fused kernel for this (fused bases, k, lanes)");
   if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   const uint32_t grid = (uint32_t)((nq + qper - 1) / qper);
@@ -826,6 +829,28 @@ extern "C" int32_t fmgpu_gather_probe_local(int32_t device, uint64_t table_bytes
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaFree(table); cudaFree(sink);
   return FM_SUCCESS;
+}
+
+/* fused-step fetch counter: blocks of the fused table and SB96 blocks of the leading steps that one search must fetch */
+extern "C" int32_t fmgpu_count_fetches_fused_device(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nq, uint32_t len,
+                                                    uint32_t *d_results, void *stream, uint64_t *nfused_blocks, uint64_t *nlead_blocks)
+{
+  if (!idx || !d_packed || !d_results) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
+  if (len == 0 || len % idx->meta.steps) return fm_fail_msg(FM_E_QUERY_SHAPE, "read length must be a positive multiple of k");
+  CU_TRY(cudaSetDevice(idx->device));
+  unsigned long long *d_c = NULL, h[2] = { 0, 0 };
+  CU_TRY(cudaMalloc((void **) &d_c, 16));
+  CU_TRY(cudaMemsetAsync(d_c, 0, 16, (cudaStream_t) stream));
+  int32_t rc = nq ? fm_launch_fused(idx, d_packed, nq, len, d_results, FM_DEFAULT_VARIANT, (cudaStream_t) stream, d_c) : FM_SUCCESS;
+  if (rc == FM_SUCCESS) {
+    cudaError_t e = cudaMemcpyAsync(h, d_c, 16, cudaMemcpyDeviceToHost, (cudaStream_t) stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t) stream);
+    if (e != cudaSuccess) rc = fm_fail(e, "fetch counters D2H", __FILE__, __LINE__);
+  }
+  cudaFree(d_c);
+  if (nfused_blocks) *nfused_blocks = h[0];
+  if (nlead_blocks) *nlead_blocks = h[1];
+  return rc;
 }
 
 /* fetch counter on caller-owned device memory: one instrumented search (results are written too) */
