@@ -251,9 +251,9 @@ extern "C" int32_t fmgpu_index_fuse(fmgpu_index_t *idx, uint32_t fused_bases, ui
   if (budget_bytes == 0) {
     const char *env = getenv("FMGPU_FUSE_BUDGET_GB");
     budget_bytes = (uint64_t)((env && *env ? atof(env) : 69.0) * 1e9);       /* flat part of the footprint curve ends near 68-70 GB */
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > (6ull << 30) && budget_bytes > free_b - (6ull << 30)) budget_bytes = free_b - (6ull << 30);
   }
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = ~(size_t) 0; }
   const uint32_t rows = fm_fused_rows(lanes);
   const uint32_t nfb = idx->meta.bwtsize / rows + 1;
   uint32_t kf = 0;
@@ -261,8 +261,9 @@ extern "C" int32_t fmgpu_index_fuse(fmgpu_index_t *idx, uint32_t fused_bases, ui
     if (fused_bases && cand != fused_bases) continue;
     if (cand % k) continue;
     const uint64_t bytes = ((uint64_t) 1 << (2 * cand)) * nfb * 32ull * lanes;
-    /* construction also needs 3 bytes per row of scratch */
-    if (bytes + 3ull * idx->meta.bwtsize <= budget_bytes || fused_bases) { kf = cand; break; }
+    const uint64_t scratch = 3ull * idx->meta.bwtsize + (1ull << 30);       /* construction: 3 bytes per row, plus slack */
+    if (bytes + scratch > free_b) continue;                                  /* does not fit in HBM right now */
+    if (bytes <= budget_bytes || fused_bases) { kf = cand; break; }
   }
   if (!kf) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "no fused-step table fits the memory budget for this index (or k already is the requested width)");
   const uint32_t nfsym = 1u << (2 * kf), hops = kf / k, kbits = 2 * k;
