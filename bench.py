@@ -136,6 +136,11 @@ def main():
     if args.impl == "reference" and rank != 0:
         return 0                                           # rank 0 alone runs the CPU arm
 
+    # host packer threads: the ranks of one box share its cores
+    if "OMP_NUM_THREADS" not in os.environ and args.impl == "ours":
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, local_world)))
+
     import torch
     import torch.distributed as dist
     pkg = importlib.import_module("k-step_fm-index_b200")
@@ -347,7 +352,10 @@ def main():
             "plain_2step_kernel": plain,
             "cpu_baseline": cpu,
             "e2e": {"value": world * nq / e2e_ms_step / 1e3, "unit": "Mqueries/s", "ms_per_step": e2e_ms_step,
-                    "h2d_bytes_per_step": nq * READ_LEN, "d2h_bytes_per_step": nq * 8, "matches_device_resident_result": same},
+                    "h2d_bytes_per_step": nq * READ_LEN, "d2h_bytes_per_step": nq * 8, "matches_device_resident_result": same,
+                    "feed": os.environ.get("FMGPU_FEED", "auto (hybrid: ASCII over PCIe + AVX-512 host packing)"),
+                    "host_pack_threads_per_rank": int(L.fm_hostpack_threads()),
+                    "note": "h2d_bytes_per_step counts the ASCII reads handed to the call; host-packed chunks cross PCIe as 2-bit (25 B/read)"},
             "gpu_launches": args.steps,
             "clocks": clocks,
             "checks": {"every_read_found": hits_ok, "e2e_equals_resident": same, "gpu_equals_reference_cpu_on_sample": parity},
