@@ -137,9 +137,10 @@ def main():
         return 0                                           # rank 0 alone runs the CPU arm
 
     # host packer threads: the ranks of one box share its cores
-    if "OMP_NUM_THREADS" not in os.environ and args.impl == "ours":
+    # (torchrun forces OMP_NUM_THREADS=1 on its workers; $FM_BENCH_HOST_THREADS overrides our split)
+    if args.impl == "ours" and ("OMP_NUM_THREADS" not in os.environ or "TORCHELASTIC_RUN_ID" in os.environ or "FM_BENCH_HOST_THREADS" in os.environ):
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, local_world)))
+        os.environ["OMP_NUM_THREADS"] = os.environ.get("FM_BENCH_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, local_world))))
 
     import torch
     import torch.distributed as dist

@@ -271,6 +271,11 @@ int32_t fmgpu_search_host(fmgpu_index_t *const *replicas, int32_t nreplicas, con
  * AVX-512 VBMI when the CPU has it.  packed holds nqueries * fmgpu_words_per_query(len) words. */
 void    fm_hostpack_reads(const char *ascii, uint64_t nqueries, uint32_t len, uint32_t *packed, int nthreads);
 void    fm_hostpack_reads_scalar(const char *ascii, uint64_t nqueries, uint32_t len, uint32_t *packed);
+/* stream variant used by fmgpu_search_host: the whole batch as one 2-bit sequence (base g at bits 2(g%4) of byte
+ * g/4), no per-read work on the host; fmgpu_unstream_device cuts / reverses / aligns it into packed reads */
+void    fm_hostpack_stream(const char *ascii, uint64_t nbases, unsigned char *out, int nthreads);
+int32_t fmgpu_unstream_device(int32_t device, const uint32_t *d_stream, uint64_t nqueries, uint32_t len,
+                              uint32_t *d_packed, void *stream);
 int     fm_hostpack_has_simd(void);
 int     fm_hostpack_threads(void);
 

@@ -470,6 +470,19 @@ extern "C" int32_t fmgpu_pack_queries_device(int32_t device, const char *d_ascii
   return FM_SUCCESS;
 }
 
+extern "C" int32_t fmgpu_unstream_device(int32_t device, const uint32_t *d_stream, uint64_t nq, uint32_t len,
+                                         uint32_t *d_packed, void *stream)
+{
+  if (!d_stream || !d_packed || len == 0) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
+  CU_TRY(cudaSetDevice(device));
+  if (nq == 0) return FM_SUCCESS;
+  const uint32_t wpq = fmgpu_words_per_query(len);
+  if ((nq * wpq + 255) / 256 >= (1ull << 31)) return fm_fail_msg(FM_E_BAD_ARGUMENT, "batch too large for one launch");
+  fm_unstream_kernel<<<(unsigned)((nq * wpq + 255) / 256), 256, 0, (cudaStream_t) stream>>>(d_stream, nq, len, wpq, d_packed);
+  CU_TRY(cudaGetLastError());
+  return FM_SUCCESS;
+}
+
 /* ------------------------------------------------------------------------ *
  * query shards
  * ------------------------------------------------------------------------ */
@@ -615,6 +628,7 @@ static fm_pipe_lane g_pipe[FM_MAX_DEVICES][FM_PIPE_STREAMS];
 extern "C" int  fm_hostpack_has_simd(void);
 extern "C" int  fm_hostpack_threads(void);
 extern "C" void fm_hostpack_reads(const char *ascii, uint64_t nq, uint32_t len, uint32_t *packed, int nthreads);
+extern "C" void fm_hostpack_stream(const char *ascii, uint64_t nbases, unsigned char *out, int nthreads);
 
 static int32_t fm_pipe_reserve(int device, fm_pipe_lane *ln, size_t ascii, size_t packed, size_t results, size_t hpacked)
 {
@@ -673,8 +687,10 @@ extern "C" int32_t fmgpu_search_host(fmgpu_index_t *const *replicas, int32_t nre
   if (chunk == 0) chunk = 32;
   for (int g = 0; g < nrep; g++)
     for (int s = 0; s < FM_PIPE_STREAMS; s++) {
-      int32_t rc = fm_pipe_reserve(replicas[g]->device, &g_pipe[replicas[g]->device][s], feed != FM_FEED_HOSTPACK ? chunk * len : 0,
-                                   chunk * wpq * 4, chunk * 8, feed != FM_FEED_ASCII ? chunk * wpq * 4 : 0);
+      /* d_ascii doubles as the landing buffer of host-packed streams (len/4 bytes per read) */
+      int32_t rc = fm_pipe_reserve(replicas[g]->device, &g_pipe[replicas[g]->device][s],
+                                   feed != FM_FEED_HOSTPACK ? chunk * len + 64 : chunk * len / 4 + 64,
+                                   chunk * wpq * 4, chunk * 8, feed != FM_FEED_ASCII ? chunk * wpq * 4 + 64 : 0);
       if (rc) return rc;
     }
   double pcie_free_at = fm_now();
@@ -692,12 +708,17 @@ extern "C" int32_t fmgpu_search_host(fmgpu_index_t *const *replicas, int32_t nre
     if (on_host) {
       CU_TRY(cudaEventSynchronize(ln->h2d_done));                     /* staging buffer free again? */
       const double t0 = fm_now();
-      fm_hostpack_reads(h_ascii + q0 * len, n, len, ln->h_packed, 0);
+      /* the host only streams ASCII -> 2 bit (64 bases per AVX-512 iteration, no per-read work);
+       * cutting into reads, reversal and word alignment happen on the GPU (fm_unstream_kernel) */
+      const uint64_t sbytes = (((n * len + 3) / 4) + 19) & ~15ull;
+      fm_hostpack_stream(h_ascii + q0 * len, n * len, (unsigned char *) ln->h_packed, 0);
       now = fm_now();
       if (n >= 4096) g_pack_s_per_read = 0.75 * g_pack_s_per_read + 0.25 * (now - t0) / (double) n;
-      CU_TRY(cudaMemcpyAsync(ln->d_packed, ln->h_packed, n * wpq * 4, cudaMemcpyHostToDevice, ln->stream));
+      CU_TRY(cudaMemcpyAsync(ln->d_ascii, ln->h_packed, sbytes, cudaMemcpyHostToDevice, ln->stream));
       CU_TRY(cudaEventRecord(ln->h2d_done, ln->stream));
-      pcie_free_at = (pcie_free_at > now ? pcie_free_at : now) + (double)(n * wpq * 4) / FM_H2D_BYTES_PER_S;
+      fm_unstream_kernel<<<(unsigned)((n * wpq + 255) / 256), 256, 0, ln->stream>>>((const uint32_t *) ln->d_ascii, n, len, wpq, ln->d_packed);
+      CU_TRY(cudaGetLastError());
+      pcie_free_at = (pcie_free_at > now ? pcie_free_at : now) + (double) sbytes / FM_H2D_BYTES_PER_S;
     } else {
       CU_TRY(cudaMemcpyAsync(ln->d_ascii, h_ascii + q0 * len, n * len, cudaMemcpyHostToDevice, ln->stream));
       rc = fmgpu_pack_queries_device(idx->device, ln->d_ascii, n, len, ln->d_packed, ln->stream);

@@ -270,6 +270,28 @@ __global__ void fm_pack_kernel(const char *__restrict__ ascii, uint64_t nq, uint
   packed[idx] = out;
 }
 
+/* Host-packed stream -> per-read reversed words.  The host packer (fm_hostpack_stream) emits the whole chunk as one
+ * 2-bit sequence, base g = q*len + i at bits [2(g%16), 2(g%16)+2) of 32-bit word g/16, doing no per-read work; this
+ * kernel cuts it into reads, reverses each and aligns it to words: out field i of word w = base len-1-(16w+i). */
+__global__ void fm_unstream_kernel(const uint32_t *__restrict__ stream, uint64_t nq, uint32_t len, uint32_t wpq,
+                                   uint32_t *__restrict__ packed)
+{
+  const uint64_t idx = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nq * wpq) return;
+  const uint64_t q = idx / wpq;
+  const uint32_t w = (uint32_t)(idx - q * wpq);
+  const uint64_t first = q * len, hi = first + len - 16ull * w;        /* bases [lo, hi) of the stream feed this word */
+  const uint64_t lo = (hi >= first + 16) ? hi - 16 : first;
+  const uint32_t nv = (uint32_t)(hi - lo);                             /* 1..16 valid bases */
+  const uint64_t bit0 = 2 * lo;
+  const uint32_t a = stream[bit0 >> 5], b = stream[(bit0 >> 5) + 1];
+  uint32_t x = __funnelshift_r(a, b, (uint32_t)(bit0 & 31));
+  if (nv < 16) x &= (1u << (2 * nv)) - 1u;
+  x <<= 2 * (16 - nv);
+  x = __brev(x);                                                        /* reverses the 16 fields and the 2 bits inside each */
+  packed[idx] = ((x & 0xAAAAAAAAu) >> 1) | ((x & 0x55555555u) << 1);    /* put the 2 bits of every field back in order */
+}
+
 /* ------------------------------------------------------------------------ *
  * Re-blocker: raw file entries (tags 100/101/200/201) -> SB96.
  * ------------------------------------------------------------------------ */

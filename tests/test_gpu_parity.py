@@ -458,3 +458,28 @@ def test_fused_unavailable_cases(pkg):
     b.search(idx, pkg.variant(pkg.MODE_FUSED))
     assert np.array_equal(b.download(), g["expected_std"])
     b.free(); idx.free()
+
+
+@pytest.mark.parametrize("length", [1, 2, 15, 16, 17, 31, 33, 100, 101, 250])
+def test_unstream_kernel_equals_pack_kernel(pkg, length):
+    """host stream packer + fm_unstream_kernel == fm_pack_kernel (device ASCII packer) == host per-read packer."""
+    import torch
+    L = pkg.lib()
+    nq = 1237
+    rng = np.random.default_rng(length)
+    reads = np.frombuffer(b"ACGTacgtN", dtype=np.uint8)[rng.integers(0, 9, nq * length)].copy()
+    wpq = L.fmgpu_words_per_query(length)
+    want = np.zeros(nq * wpq, dtype=np.uint32)
+    L.fm_hostpack_reads_scalar(reads.ctypes.data, nq, length, want.ctypes.data)
+    stream_bytes = np.zeros(((nq * length + 3) // 4 + 19) & ~15, dtype=np.uint8)
+    L.fm_hostpack_stream(reads.ctypes.data, nq * length, stream_bytes.ctypes.data, 0)
+    d_stream = torch.from_numpy(stream_bytes).cuda()
+    d_packed = torch.zeros(nq * wpq, dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    pkg.check(L.fmgpu_unstream_device(0, d_stream.data_ptr(), nq, length, d_packed.data_ptr(), s), "unstream")
+    d_ascii = torch.from_numpy(reads).cuda()
+    d_packed2 = torch.zeros(nq * wpq, dtype=torch.int32, device="cuda")
+    pkg.check(L.fmgpu_pack_queries_device(0, d_ascii.data_ptr(), nq, length, d_packed2.data_ptr(), s), "pack")
+    torch.cuda.synchronize()
+    assert np.array_equal(d_packed.cpu().numpy().view(np.uint32), want)
+    assert np.array_equal(d_packed2.cpu().numpy().view(np.uint32), want)

@@ -149,3 +149,20 @@ def test_host_packer_simd_equals_scalar_equals_definition(built, length):
         want[:, t // 16] |= code[:, length - 1 - t] << np.uint32(2 * (t % 16))
     assert np.array_equal(b.reshape(nq, wpq), want)
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("nbases", [1, 3, 4, 63, 64, 65, 4095, 4096, 4097, 100_003])
+def test_host_stream_packer(built, nbases):
+    """fm_hostpack_stream: base g at bits 2(g%4) of byte g/4, threads split at 4096-base slices."""
+    pkg = helpers.pkg()
+    L = pkg.lib()
+    rng = np.random.default_rng(nbases)
+    a = np.frombuffer(b"ACGTacgtN", dtype=np.uint8)[rng.integers(0, 9, nbases)].copy()
+    out = np.zeros((nbases + 3) // 4 + 8, dtype=np.uint8)
+    L.fm_hostpack_stream(a.ctypes.data, nbases, out.ctypes.data, 0)
+    r = np.zeros(((nbases + 3) // 4) * 4, dtype=np.uint32)
+    r[:nbases] = a
+    code = (((r >> 2) & 1) << 1) | (((r >> 2) & 1) ^ ((r >> 1) & 1))
+    code[nbases:] = 0
+    want = (code[0::4] | code[1::4] << 2 | code[2::4] << 4 | code[3::4] << 6).astype(np.uint8)
+    assert np.array_equal(out[: want.size], want)
