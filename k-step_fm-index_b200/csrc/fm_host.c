@@ -291,6 +291,18 @@ int32_t fmgpu_set_variant(const fmgpu_variant_t *v)
   return FM_SUCCESS;
 }
 
+/* $FMGPU_MODE = task | coop | fused | auto (default): kernel family used by searchIndexGPU */
+#define FM_MODE_AUTO (-1)
+static int fm_mode_from_env(void)
+{
+  const char *env = getenv("FMGPU_MODE");
+  if (!env || !*env || !strcmp(env, "auto")) return FM_MODE_AUTO;
+  if (!strcmp(env, "task")) return FMGPU_MODE_TASK;
+  if (!strcmp(env, "coop")) return FMGPU_MODE_COOP;
+  if (!strcmp(env, "fused")) return FMGPU_MODE_FUSED;
+  return FM_MODE_AUTO;
+}
+
 /* configured devices, else $FMGPU_DEVICES ("0,1,2,3"), else device 0 */
 static int32_t fm_resolve_devices(int32_t *dev)
 {
@@ -344,6 +356,13 @@ int32_t transferCPUtoGPU(void *index, void *queries, void *results)
                              fmi->h_dollarPositionBWT, fmi->h_dollarBaseBWT, (const uint32_t *) fmi->h_index, &rs->replica[0]);
     for (g = 1; g < rs->ndev && !err; g++) err = fmgpu_index_replicate(rs->replica[0], rs->dev[g], &rs->replica[g]);
     if (err) { for (g = 0; g < rs->ndev; g++) fmgpu_index_free(&rs->replica[g]); free(rs); return err; }
+    /* fused-step table on every replica unless $FMGPU_MODE asks for the plain kernels; an index that cannot be
+     * fused (AltCounters padding quirk, no memory) simply keeps the plain 2-step kernels -- still on the GPU */
+    if (fm_mode_from_env() == FM_MODE_AUTO || fm_mode_from_env() == FMGPU_MODE_FUSED)
+      for (g = 0; g < rs->ndev; g++) {
+        err = fmgpu_index_fuse(rs->replica[g], 0, 0, 0);
+        if (err && err != FM_E_NOT_IMPLEMENTED) { for (g = 0; g < rs->ndev; g++) fmgpu_index_free(&rs->replica[g]); free(rs); return err; }
+      }
     fmi->d_index = rs;
   }
 
@@ -381,7 +400,19 @@ void searchIndexGPU(void *index, void *queries, void *resIntervals)
     fprintf(stderr, "searchIndexGPU: transferCPUtoGPU has not been called for this index/queries (%s:%d)\n", __FILE__, __LINE__);
     exit(EXIT_FAILURE);
   }
-  for (g = 0; g < ss->ndev && !err; g++) err = fmgpu_batch_search(rs->replica[g], ss->shard[g], g_variant_set ? &g_variant : NULL);
+  for (g = 0; g < ss->ndev && !err; g++) {
+    fmgpu_variant_t v = g_variant;
+    if (!g_variant_set) {                      /* $FMGPU_MODE, else fused when the replica has a fused table, else Coop */
+      fmgpu_index_meta_t meta;
+      const int mode = fm_mode_from_env();
+      memset(&v, 0, sizeof v);
+      err = fmgpu_index_get_meta(rs->replica[g], &meta);
+      if (err) break;
+      v.mode = (mode == FM_MODE_AUTO) ? (meta.fused_bases ? FMGPU_MODE_FUSED : FMGPU_MODE_COOP) : mode;
+      if (v.mode == FMGPU_MODE_FUSED && !meta.fused_bases) v.mode = FMGPU_MODE_COOP;
+    }
+    err = fmgpu_batch_search(rs->replica[g], ss->shard[g], &v);
+  }
   for (g = 0; g < ss->ndev && !err; g++) err = fmgpu_batch_sync(ss->shard[g]);
   if (err) {
     fprintf(stderr, "searchIndexGPU: %s (%s:%d)\n", errorCommon(err), __FILE__, __LINE__);
