@@ -1,0 +1,45 @@
+"""BASELINE config 5 on one B200: Task vs Coop vs Fused over read lengths 12/25/50/100/250 and k in {1,2} on the
+2 Gbp index (10 M reads per point).  Every point is checked: all reads found, and Task == Coop == Fused.
+Writes gpurun_out/config5_sweep.jsonl."""
+import importlib, json, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import torch
+pkg = importlib.import_module("k-step_fm-index_b200")
+L = pkg.lib()
+OUT = open(os.path.join(ROOT, "gpurun_out", "config5_sweep.jsonl"), "a")
+def emit(**kw):
+    print(json.dumps(kw), flush=True); OUT.write(json.dumps(kw) + "\n"); OUT.flush()
+n, nq = int(float(os.environ.get("FM_N", "2e9"))), int(float(os.environ.get("FM_NQ", "1e7")))
+stream = torch.cuda.current_stream().cuda_stream
+for k in (2, 1):
+    b = pkg.IndexBuild.from_synth(n, 1, k, 64); idx = b.to_index(); b.free()
+    idx.fuse()
+    m = idx.meta
+    emit(what="index", k=k, sb96_gb=m.nbytes / 1e9, fused_bases=m.fused_bases, fused_gb=m.fused_bytes / 1e9)
+    for length in (12, 25, 50, 100, 250):
+        if length % k:
+            emit(what="skipped", k=k, len=length, why="read length not a multiple of k: undefined in the reference (SURVEY App. C-5)")
+            continue
+        d_ascii = torch.empty(nq * length, dtype=torch.uint8, device="cuda")
+        pkg.check(L.fmgpu_synth_reads_device(0, n, 1, nq, length, 2, 0, d_ascii.data_ptr(), None), "reads")
+        wpq = L.fmgpu_words_per_query(length)
+        d_packed = torch.empty(nq * wpq, dtype=torch.int32, device="cuda"); d_res = torch.zeros(2 * nq, dtype=torch.int32, device="cuda")
+        pkg.check(L.fmgpu_pack_queries_device(0, d_ascii.data_ptr(), nq, length, d_packed.data_ptr(), stream), "pack"); torch.cuda.synchronize(); del d_ascii
+        ref = None
+        for name, v in (("task", pkg.variant(pkg.MODE_TASK, 2, 512)), ("coop", pkg.variant(pkg.MODE_COOP, 1, 256)), ("fused", pkg.variant(pkg.MODE_FUSED, 2))):
+            ts = []
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); pkg.check(L.fmgpu_search_device(idx.handle, d_packed.data_ptr(), nq, length, d_res.data_ptr(), v, stream), "search"); e1.record()
+                torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+            res = d_res.cpu().numpy().view(np.uint32)
+            if ref is None:
+                ref = res.copy()
+            ms = min(ts[2:])
+            emit(what="search", k=k, len=length, kernel=name, ms=ms, mq_per_s=nq / ms / 1e3, g_ref_lf_steps_per_s=nq * (length // k) / ms / 1e6,
+                 all_found=bool(((res[1::2] - res[0::2]) >= 1).all()), same_as_task=bool(np.array_equal(res, ref)),
+                 mean_hits=float((res[1::2] - res[0::2]).astype(np.float64).mean()))
+        del d_packed, d_res
+    idx.free()
