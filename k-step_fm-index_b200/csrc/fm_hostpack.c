@@ -114,14 +114,19 @@ static void stream_avx512(const unsigned char *in, uint64_t nbases, unsigned cha
 {
   const __m512i three = _mm512_set1_epi8(3), one = _mm512_set1_epi8(1);
   const __m512i w16 = _mm512_set1_epi16(0x0401), w32 = _mm512_set1_epi32(0x00100001);
+  const int nt = (((uintptr_t) out) & 15u) == 0;
   uint64_t g = 0;
   for (; g + 64 <= nbases; g += 64) {
     const __m512i x = _mm512_loadu_si512((const void *)(in + g));
     const __m512i u = _mm512_and_si512(_mm512_srli_epi16(x, 1), three);
     const __m512i c = _mm512_xor_si512(u, _mm512_and_si512(_mm512_srli_epi16(u, 1), one));
     const __m512i p32 = _mm512_madd_epi16(_mm512_maddubs_epi16(c, w16), w32);
-    _mm_storeu_si128((__m128i *)(out + g / 4), _mm512_cvtepi32_epi8(p32));
+    /* non-temporal when the destination is 16-byte aligned: the packed bytes are only read back by the DMA
+     * engine, so skip the read-for-ownership of the output lines */
+    if (nt) _mm_stream_si128((__m128i *)(out + g / 4), _mm512_cvtepi32_epi8(p32));
+    else    _mm_storeu_si128((__m128i *)(out + g / 4), _mm512_cvtepi32_epi8(p32));
   }
+  if (nt) _mm_sfence();
   if (g < nbases) stream_scalar(in + g, nbases - g, out + g / 4);
 }
 
