@@ -195,6 +195,14 @@ typedef struct {
   uint32_t fused_bases;  /* bases per fused step (0 = no fused table), see fmgpu_index_fuse */
   uint32_t fused_lanes;  /* lanes per fused block (block = 32 bytes per lane)   */
   uint64_t fused_bytes;  /* size of the fused table                             */
+  /* odd read lengths on a 2-step index: the last base is consumed by a 1-step rank derived from the 2-step
+   * table (result = what the 1-step index of the same text gives; the reference itself is undefined there,
+   * SURVEY.md App. C-5).  Valid for k = 2 indexes without the AltCounters padding quirk. */
+  uint32_t tail_valid;
+  uint32_t tail_row;      /* row whose layer-1 char is '$' (dollarPositionBWT[1])             */
+  uint32_t tail_base;     /* its layer-0 char (dollarBaseBWT[1] & 3)                           */
+  uint32_t tail_const[4]; /* C1[c] - sum over c1 of rank2(c | c1<<2, 0)                         */
+  uint32_t reserved2;
 } fmgpu_index_meta_t;
 
 /* devices ---------------------------------------------------------------- */

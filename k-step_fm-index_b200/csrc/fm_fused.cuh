@@ -47,6 +47,7 @@ struct FmFusedParams {
   uint32_t wpq, wpq_pad;      /* wpq_pad >= wpq + 1: a bit field may straddle into the next word   */
   uint32_t bwtsize;
   unsigned long long *fetch_counters;  /* COUNT only: [0] = fused blocks fetched, [1] = SB96 blocks of the leading steps */
+  uint32_t has_tail, tail_row, tail_base, tail_const[4];   /* odd read length on a 2-step index, see fm_tail_rank */
 };
 
 __device__ __forceinline__ void fm_ldg32(const uint4 *p, uint32_t (&w)[8])
@@ -178,6 +179,15 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_fused_kernel(const Fm
       cR += fm_fused_partial(wR[i], rR[i], lg);
       L[i] = fm_group_sum<LANES>(cL);
       R[i] = fm_group_sum<LANES>(cR);
+    }
+  }
+
+  if (K == 2 && p.has_tail) {                     /* last base of an odd-length read (every lane of the group, same addresses) */
+    #pragma unroll
+    for (int i = 0; i < QPT; i++) {
+      const uint32_t c = fm_read_field(myq[i], pos, 3u);
+      L[i] = fm_tail_rank(p.blocks, p.nblocks, c, L[i], p.tail_const[c], p.tail_row, p.tail_base);
+      R[i] = fm_tail_rank(p.blocks, p.nblocks, c, R[i], p.tail_const[c], p.tail_row, p.tail_base);
     }
   }
 

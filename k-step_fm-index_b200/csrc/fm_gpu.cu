@@ -142,6 +142,37 @@ static int32_t fm_index_from_device_entries(int device, uint32_t tag, uint32_t s
   e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { cudaFree(idx->blocks); free(idx); return fm_fail(e, "fm_reblock_kernel", __FILE__, __LINE__); }
+
+  /* constants of the derived 1-step rank that serves the last base of odd-length reads on a 2-step index */
+  if (steps == 2 && idx->meta.quirk_mask == 0) {
+    uint4 first[16], last[16];
+    const uint32_t bl = bwtsize / FM_SB_ROWS, rl = bwtsize - bl * FM_SB_ROWS;
+    for (uint32_t s = 0; s < 16 && e == cudaSuccess; s++) {
+      e = cudaMemcpy(&first[s], idx->blocks + (size_t) s * nb, sizeof(uint4), cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemcpy(&last[s], idx->blocks + (size_t) s * nb + bl, sizeof(uint4), cudaMemcpyDeviceToHost);
+    }
+    if (e != cudaSuccess) { cudaFree(idx->blocks); free(idx); return fm_fail(e, "tail constants", __FILE__, __LINE__); }
+    uint32_t at0[16], total1[4] = { 0, 0, 0, 0 };
+    for (uint32_t s = 0; s < 16; s++) {
+      const uint32_t w[3] = { last[s].y, last[s].z, last[s].w };
+      uint32_t end = last[s].x;
+      for (uint32_t j = 0; j < 3; j++) {
+        const int32_t nbits = (int32_t) rl - 32 * (int32_t) j;
+        const uint32_t m = nbits <= 0 ? 0u : (nbits >= 32 ? 0xFFFFFFFFu : ((1u << nbits) - 1u));
+        end += (uint32_t) __builtin_popcount(w[j] & m);
+      }
+      at0[s] = first[s].x;                                  /* rank2(s, 0)        */
+      total1[s & 3u] += end - at0[s];                       /* rows with 2-step symbol s, by layer-0 char */
+    }
+    const uint32_t t0 = dbase[1] & 3u;
+    total1[t0] += 1;                                        /* the row whose layer-1 char is '$' still has a layer-0 char */
+    uint32_t c1 = 1;                                        /* the '$' suffix precedes everything */
+    for (uint32_t c = 0; c < 4; c++) {
+      idx->meta.tail_const[c] = c1 - (at0[c] + at0[c | 4u] + at0[c | 8u] + at0[c | 12u]);
+      c1 += total1[c];
+    }
+    idx->meta.tail_row = dpos[1]; idx->meta.tail_base = t0; idx->meta.tail_valid = 1;
+  }
   *out = idx;
   return FM_SUCCESS;
 }
@@ -340,6 +371,8 @@ static int32_t fm_launch_fused(const fmgpu_index_t *idx, const uint32_t *d_packe
   p.nlead = (len / k) % hops; p.nfused = (len / k) / hops;
   p.wpq = fmgpu_words_per_query(len); p.wpq_pad = (p.wpq + 1) | 1u; p.bwtsize = idx->meta.bwtsize;
   p.fetch_counters = d_counters;
+  p.has_tail = len % k; p.tail_row = idx->meta.tail_row; p.tail_base = idx->meta.tail_base;
+  for (int c = 0; c < 4; c++) p.tail_const[c] = idx->meta.tail_const[c];
   if (d_counters) v.queries_per_thread = 1;
   uint32_t qper; size_t smem;
   for (;;) {
@@ -411,7 +444,9 @@ static int32_t fm_launch_search(const fmgpu_index_t *idx, const uint32_t *d_pack
 {
   if (!idx || !d_packed || !d_results) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
   const uint32_t k = idx->meta.steps;
-  if (len == 0 || len % k) return fm_fail_msg(FM_E_QUERY_SHAPE, "read length must be a positive multiple of k (undefined in the reference, SURVEY.md App. C-5)");
+  if (len == 0 || (len % k && !idx->meta.tail_valid))
+    return fm_fail_msg(FM_E_QUERY_SHAPE, "read length must be a positive multiple of k (undefined in the reference, SURVEY.md App. C-5; "
+                                         "odd lengths are served on 2-step indexes without the AltCounters quirk only)");
   if (nq == 0) return FM_SUCCESS;
   if (nq >= (1ull << 31)) return fm_fail_msg(FM_E_BAD_ARGUMENT, "more than 2^31 reads in one launch; shard the batch");
   fmgpu_variant_t v = vin ? *vin : FM_DEFAULT_VARIANT;
@@ -426,6 +461,8 @@ static int32_t fm_launch_search(const fmgpu_index_t *idx, const uint32_t *d_pack
   p.nblocks = idx->meta.nblocks; p.nq = (uint32_t) nq; p.nsteps = len / k;
   p.wpq = fmgpu_words_per_query(len); p.wpq_pad = p.wpq | 1u;
   p.bwtsize = idx->meta.bwtsize; p.quirk_start = idx->meta.quirk_start; p.quirk_mask = idx->meta.quirk_mask;
+  p.has_tail = len % k; p.tail_row = idx->meta.tail_row; p.tail_base = idx->meta.tail_base;
+  for (int c = 0; c < 4; c++) p.tail_const[c] = idx->meta.tail_const[c];
   const bool quirk = idx->meta.quirk_mask != 0;
 
   /* shrink the CTA's read count until the staged reads fit in shared memory */
@@ -676,7 +713,7 @@ extern "C" int32_t fmgpu_search_host(fmgpu_index_t *const *replicas, int32_t nre
   if (!replicas || nrep < 1 || nrep > FM_MAX_DEVICES || !h_ascii || !h_results || len == 0) return fm_fail_msg(FM_E_BAD_ARGUMENT, "bad argument");
   for (int g = 0; g < nrep; g++)
     if (!replicas[g] || replicas[g]->device < 0 || replicas[g]->device >= FM_MAX_DEVICES) return fm_fail_msg(FM_E_BAD_ARGUMENT, "bad replica");
-  if (len % replicas[0]->meta.steps) return fm_fail_msg(FM_E_QUERY_SHAPE, "read length must be a multiple of k");
+  if (len % replicas[0]->meta.steps && !replicas[0]->meta.tail_valid) return fm_fail_msg(FM_E_QUERY_SHAPE, "read length must be a multiple of k");
   if (nq == 0) return FM_SUCCESS;
   const uint32_t wpq = fmgpu_words_per_query(len);
   const int feed = fm_feed_mode(v);
@@ -858,7 +895,7 @@ extern "C" int32_t fmgpu_count_fetches_fused_device(const fmgpu_index_t *idx, co
                                                     uint32_t *d_results, void *stream, uint64_t *nfused_blocks, uint64_t *nlead_blocks)
 {
   if (!idx || !d_packed || !d_results) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
-  if (len == 0 || len % idx->meta.steps) return fm_fail_msg(FM_E_QUERY_SHAPE, "read length must be a positive multiple of k");
+  if (len == 0 || (len % idx->meta.steps && !idx->meta.tail_valid)) return fm_fail_msg(FM_E_QUERY_SHAPE, "read length must be a positive multiple of k");
   CU_TRY(cudaSetDevice(idx->device));
   unsigned long long *d_c = NULL, h[2] = { 0, 0 };
   CU_TRY(cudaMalloc((void **) &d_c, 16));

@@ -344,7 +344,7 @@ int32_t transferCPUtoGPU(void *index, void *queries, void *results)
 
   if (!fmi || !qrys || !res || !fmi->h_index || !qrys->h_queries || !res->h_results) return FM_E_BAD_ARGUMENT;
   if (res->num < qrys->num) return FM_E_BAD_ARGUMENT;
-  if (qrys->size % fmi->steps) return FM_E_QUERY_SHAPE;
+  if (qrys->size % fmi->steps && fmi->steps != 2) return FM_E_QUERY_SHAPE;   /* k=2: the device layer serves odd lengths */
 
   /* index: one H2D + re-block on the first GPU, peer copies to the others */
   rs = (fm_replica_set_t *) fmi->d_index;

@@ -46,6 +46,11 @@ struct FmSearchParams {
   uint32_t bwtsize;
   uint32_t quirk_start;
   uint32_t quirk_mask;
+  /* odd read length on a 2-step index: after nsteps 2-base steps one base is left; it is consumed by a 1-step
+   * rank DERIVED from the 2-step table (fm_tail_rank) -- the result is what a 1-step index of the same text gives */
+  uint32_t has_tail;
+  uint32_t tail_row, tail_base;   /* row whose layer-1 char is '$' (it has a layer-0 char but no 2-step symbol), and that char */
+  uint32_t tail_const[4];         /* C1[c] - sum_c1 rank2(c | c1<<2, 0) */
 };
 
 /* raw (file-order) index as uploaded, for the re-blocker */
@@ -80,6 +85,22 @@ __device__ __forceinline__ uint32_t fm_block_rank(const uint4 v, uint32_t r)
   const uint32_t r1 = (uint32_t) max((int) r - 32, 0);
   const uint32_t r2 = (uint32_t) max((int) r - 64, 0);
   return v.x + __popc(v.y & fm_lowmask(r)) + __popc(v.z & fm_lowmask(r1)) + __popc(v.w & fm_lowmask(r2));
+}
+
+/* 1-step LF of row boundary X for base c on a 2-step table: rows below X whose layer-0 char is c are those
+ * carrying one of the four 2-step symbols (c1, c), plus the row whose layer-1 char is '$' when it lies below X
+ * and has layer-0 char c.  tail_const[c] folds the 1-step C table and the four block ranks at X = 0. */
+__device__ __forceinline__ uint32_t fm_tail_rank(const uint4 *__restrict__ blocks, uint32_t nblocks, uint32_t c, uint32_t X,
+                                                 uint32_t tail_const, uint32_t tail_row, uint32_t tail_base)
+{
+  const uint32_t b = fm_div96(X), r = X - b * FM_SB_ROWS;
+  uint4 v[4];
+  #pragma unroll
+  for (int c1 = 0; c1 < 4; c1++) v[c1] = fm_ldg16(blocks + (size_t)(c | (c1 << 2)) * nblocks + b);
+  uint32_t sum = tail_const + ((X > tail_row && c == tail_base) ? 1u : 0u);
+  #pragma unroll
+  for (int c1 = 0; c1 < 4; c1++) sum += fm_block_rank(v[c1], r);
+  return sum;
 }
 
 /* cooperative staging of this CTA's packed reads: global [q][wpq] -> smem [q][wpq_pad] */
@@ -159,6 +180,16 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_task_kernel(const FmS
     }
   }
 
+  if (K == 2 && p.has_tail) {                     /* last base of an odd-length read */
+    const uint32_t pos = 4u * p.nsteps;
+    #pragma unroll
+    for (int i = 0; i < QPT; i++) {
+      const uint32_t c = (myq[i][pos >> 5] >> (pos & 31u)) & 3u;
+      L[i] = fm_tail_rank(p.blocks, p.nblocks, c, L[i], p.tail_const[c], p.tail_row, p.tail_base);
+      R[i] = fm_tail_rank(p.blocks, p.nblocks, c, R[i], p.tail_const[c], p.tail_row, p.tail_base);
+    }
+  }
+
   #pragma unroll
   for (int i = 0; i < QPT; i++)
     if (live[i]) {
@@ -234,6 +265,15 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_coop_kernel(const FmS
       uint32_t nX = fm_block_rank(v[i], r[i]);
       if (QUIRK) { if (X[i] >= p.quirk_start) nX += (p.quirk_mask >> (2u * sig[i])) & 3u; }
       X[i] = nX;
+    }
+  }
+
+  if (K == 2 && p.has_tail) {                     /* last base of an odd-length read */
+    const uint32_t pos = 4u * p.nsteps;
+    #pragma unroll
+    for (int i = 0; i < QPT; i++) {
+      const uint32_t c = (myq[i][pos >> 5] >> (pos & 31u)) & 3u;
+      X[i] = fm_tail_rank(p.blocks, p.nblocks, c, X[i], p.tail_const[c], p.tail_row, p.tail_base);
     }
   }
 

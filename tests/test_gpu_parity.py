@@ -213,12 +213,14 @@ def test_fetch_counter_matches_oracle(pkg):
 def test_error_paths(pkg):
     g = np.load(os.path.join(helpers.ROOT, "tests", "golden", "small_k2_d64.npz"))
     idx = pkg.DeviceIndex.from_image(g["image_100"])
-    b = pkg.DeviceBatch(0, 10, 31, 2)                           # odd length at k=2: undefined in the reference
-    b.upload_ascii(g["reads"][: 310])
+    gq = np.load(os.path.join(helpers.ROOT, "tests", "golden", "quirk_k2_n124.npz"))
+    qidx = pkg.DeviceIndex.from_image(gq["image_200"])          # odd length at k=2 on an index with the AC quirk: refused
+    b = pkg.DeviceBatch(0, 10, 7, 2)
+    b.upload_ascii(gq["reads"][: 70])
     with pytest.raises(pkg.FMError) as ei:
-        b.search(idx)
+        b.search(qidx)
     assert ei.value.code == pkg.FM_E_QUERY_SHAPE
-    b.free()
+    b.free(); qidx.free()
     b = pkg.DeviceBatch(0, 10, 32, 2)
     b.upload_ascii(g["reads"][: 320])
     for bad_variant in (pkg.variant(pkg.MODE_TASK, 3, 256), pkg.variant(pkg.MODE_TASK, 2, 96), pkg.variant(7, 1, 128)):
@@ -486,3 +488,31 @@ def test_unstream_kernel_equals_pack_kernel(pkg, length):
     torch.cuda.synchronize()
     assert np.array_equal(d_packed.cpu().numpy().view(np.uint32), want)
     assert np.array_equal(d_packed2.cpu().numpy().view(np.uint32), want)
+
+
+@pytest.mark.skipif(not helpers.has_ref_tools(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("length", [1, 3, 15, 17, 25, 33, 99, 101])
+def test_odd_read_length_on_2step_index_equals_1step_index(pkg, tmp_path, length):
+    """len % 2 == 1 on a 2-step index is undefined in the reference (it reads query[-1]).  Here the
+    last base is consumed by a 1-step rank derived from the 2-step table; the result must be what the reference
+    searcher returns on the 1-step index of the SAME text (k=1 and k=2 agree wherever both are defined)."""
+    n = 40_009
+    text = helpers.synth_text(n, seed=31)
+    p1 = helpers.build_reference_indexes(str(tmp_path / "k1"), text, 1, 64)
+    p2 = helpers.build_reference_indexes(str(tmp_path / "k2"), text, 2, 64)
+    rng = np.random.default_rng(length)
+    reads = np.concatenate([helpers.synth_reads(text, 9, 3000, length), text[:length], text[-length:], text[1:length + 1],
+                            ACGT[rng.integers(0, 4, 1500 * length)]])
+    ref = helpers.RefSearcher(1, 64, False)
+    want, _ = ref.search(ref.load(p1[100]), reads, length)
+    for tag in (100, 101, 200, 201):
+        idx = pkg.DeviceIndex.from_image(np.fromfile(p2[tag], dtype=np.uint32))
+        assert idx.meta.tail_valid == 1
+        idx.fuse(4, 2)
+        b = pkg.DeviceBatch(0, reads.size // length, length, 2)
+        b.upload_ascii(reads)
+        for v in (pkg.variant(pkg.MODE_TASK, 1), pkg.variant(pkg.MODE_TASK, 4), pkg.variant(pkg.MODE_COOP, 2), pkg.variant(pkg.MODE_FUSED, 1),
+                  pkg.variant(pkg.MODE_FUSED, 2)):
+            b.search(idx, v)
+            assert np.array_equal(b.download(), want), f"len {length} tag {tag} mode {v.mode} qpt {v.queries_per_thread}"
+        b.free(); idx.free()
