@@ -115,8 +115,10 @@ static void stream_avx512(const unsigned char *in, uint64_t nbases, unsigned cha
 {
   const __m512i three = _mm512_set1_epi8(3), one = _mm512_set1_epi8(1);
   const __m512i w16 = _mm512_set1_epi16(0x0401), w32 = _mm512_set1_epi32(0x00100001);
-  static int nt_allowed = -1;                                  /* $FM_HOSTPACK_NT=0 turns non-temporal stores off */
-  if (nt_allowed < 0) { const char *e = getenv("FM_HOSTPACK_NT"); nt_allowed = !(e && e[0] == '0'); }
+  /* non-temporal 16-byte stores measured SLOWER than plain stores on the benchmark host (hybrid feed 977 vs
+   * 1100 M reads/s, profiles/r01_e2e_ab.jsonl): partial-line write combining.  Off unless $FM_HOSTPACK_NT=1. */
+  static int nt_allowed = -1;
+  if (nt_allowed < 0) { const char *e = getenv("FM_HOSTPACK_NT"); nt_allowed = (e && e[0] == '1'); }
   const int nt = nt_allowed && (((uintptr_t) out) & 15u) == 0;
   uint64_t g = 0;
   for (; g + 64 <= nbases; g += 64) {
