@@ -658,6 +658,7 @@ struct fm_pipe_lane {
   uint32_t *d_packed;
   uint32_t *d_results;
   uint32_t *h_packed;         /* pinned staging for host-packed reads */
+  uint64_t  h2d_pending;      /* H2D bytes queued on this lane since h2d_done was last seen complete */
   size_t    cap_ascii, cap_packed, cap_results, cap_hpacked;
 };
 static fm_pipe_lane g_pipe[FM_MAX_DEVICES][FM_PIPE_STREAMS];
@@ -684,7 +685,7 @@ static int32_t fm_pipe_reserve(int device, fm_pipe_lane *ln, size_t ascii, size_
  *   2 = 2-bit packing on the host, 25 B/read over PCIe      (CPU-bound)
  *   3 = hybrid: the copy engine pulls ASCII chunks while the CPU threads pack other chunks; each chunk goes
  *       to whichever resource would otherwise idle (greedy on a PCIe-busy-until estimate)
- *   0 = auto: 3 when the CPU has AVX-512 VBMI and >= 8 threads, else 1 */
+ *   0 = auto: 3 when the CPU has AVX-512 and >= 2 threads, else 1 */
 enum { FM_FEED_AUTO = 0, FM_FEED_ASCII = 1, FM_FEED_HOSTPACK = 2, FM_FEED_HYBRID = 3 };
 
 static int fm_feed_mode(const fmgpu_variant_t *v)
@@ -693,7 +694,7 @@ static int fm_feed_mode(const fmgpu_variant_t *v)
   const char *env = getenv("FMGPU_FEED");
   if (mode == FM_FEED_AUTO && env && *env) mode = atoi(env);
   if (mode < FM_FEED_ASCII || mode > FM_FEED_HYBRID)
-    mode = (fm_hostpack_has_simd() && fm_hostpack_threads() >= 8) ? FM_FEED_HYBRID : FM_FEED_ASCII;
+    mode = (fm_hostpack_has_simd() && fm_hostpack_threads() >= 2) ? FM_FEED_HYBRID : FM_FEED_ASCII;
   return mode;
 }
 
@@ -730,7 +731,12 @@ extern "C" int32_t fmgpu_search_host(fmgpu_index_t *const *replicas, int32_t nre
                                    chunk * wpq * 4, chunk * 8, feed != FM_FEED_ASCII ? chunk * wpq * 4 + 64 : 0);
       if (rc) return rc;
     }
-  double pcie_free_at = fm_now();
+  /* hybrid feed: keep each GPU's PCIe link fed with just enough ASCII chunks that it does not idle while the CPU
+   * threads pack the next chunk; everything else is packed on the host.  The bytes still queued on a link are
+   * tracked with the lanes' H2D events, so a slower link (shared host memory, several ranks) shifts work to the
+   * CPU by itself and a slower CPU shifts it to the link. */
+  for (int g = 0; g < nrep; g++)
+    for (int s = 0; s < FM_PIPE_STREAMS; s++) g_pipe[replicas[g]->device][s].h2d_pending = 0;
   uint64_t c = 0;
   for (uint64_t q0 = 0; q0 < nq; q0 += chunk, c++) {
     const uint64_t n = (nq - q0 < chunk) ? nq - q0 : chunk;
@@ -739,28 +745,40 @@ extern "C" int32_t fmgpu_search_host(fmgpu_index_t *const *replicas, int32_t nre
     fm_pipe_lane *ln = &g_pipe[idx->device][s];
     CU_TRY(cudaSetDevice(idx->device));
     int32_t rc;
-    double now = fm_now();
     bool on_host = (feed == FM_FEED_HOSTPACK);
-    if (feed == FM_FEED_HYBRID) on_host = (pcie_free_at - now) >= g_pack_s_per_read * (double) n;   /* PCIe stays busy while we pack */
+    if (feed == FM_FEED_HYBRID) {
+      uint64_t pending = 0;
+      for (int t = 0; t < FM_PIPE_STREAMS; t++) {
+        fm_pipe_lane *o = &g_pipe[idx->device][t];
+        if (o->h2d_pending && cudaEventQuery(o->h2d_done) == cudaSuccess) o->h2d_pending = 0;
+        pending += o->h2d_pending;
+      }
+      cudaGetLastError();                                             /* cudaErrorNotReady from the queries is not an error */
+      double need = FM_H2D_BYTES_PER_S * g_pack_s_per_read * (double) n;   /* bytes the link moves while one chunk is packed */
+      const double lo = 0.5 * (double)(n * len), hi = 2.0 * (double)(n * len);
+      need = need < lo ? lo : (need > hi ? hi : need);
+      on_host = (double) pending >= need;
+    }
     if (on_host) {
       CU_TRY(cudaEventSynchronize(ln->h2d_done));                     /* staging buffer free again? */
+      ln->h2d_pending = 0;
       const double t0 = fm_now();
       /* the host only streams ASCII -> 2 bit (64 bases per AVX-512 iteration, no per-read work);
        * cutting into reads, reversal and word alignment happen on the GPU (fm_unstream_kernel) */
       const uint64_t sbytes = (((n * len + 3) / 4) + 19) & ~15ull;
       fm_hostpack_stream(h_ascii + q0 * len, n * len, (unsigned char *) ln->h_packed, 0);
-      now = fm_now();
-      if (n >= 4096) g_pack_s_per_read = 0.75 * g_pack_s_per_read + 0.25 * (now - t0) / (double) n;
+      if (n >= 4096) g_pack_s_per_read = 0.75 * g_pack_s_per_read + 0.25 * (fm_now() - t0) / (double) n;
       CU_TRY(cudaMemcpyAsync(ln->d_ascii, ln->h_packed, sbytes, cudaMemcpyHostToDevice, ln->stream));
       CU_TRY(cudaEventRecord(ln->h2d_done, ln->stream));
+      ln->h2d_pending += sbytes;
       fm_unstream_kernel<<<(unsigned)((n * wpq + 255) / 256), 256, 0, ln->stream>>>((const uint32_t *) ln->d_ascii, n, len, wpq, ln->d_packed);
       CU_TRY(cudaGetLastError());
-      pcie_free_at = (pcie_free_at > now ? pcie_free_at : now) + (double) sbytes / FM_H2D_BYTES_PER_S;
     } else {
       CU_TRY(cudaMemcpyAsync(ln->d_ascii, h_ascii + q0 * len, n * len, cudaMemcpyHostToDevice, ln->stream));
+      CU_TRY(cudaEventRecord(ln->h2d_done, ln->stream));
+      ln->h2d_pending += n * len;
       rc = fmgpu_pack_queries_device(idx->device, ln->d_ascii, n, len, ln->d_packed, ln->stream);
       if (rc) return rc;
-      pcie_free_at = (pcie_free_at > now ? pcie_free_at : now) + (double)(n * len) / FM_H2D_BYTES_PER_S;
     }
     rc = fm_launch_search(idx, ln->d_packed, n, len, ln->d_results, v, ln->stream, NULL);
     if (rc) return rc;
