@@ -17,6 +17,10 @@
 
 #define FM_MAX_GPUS 16
 
+/* fm_ingest.c */
+int32_t fm_parse_queries_mmap(const char *fn, uint32_t len, uint64_t num, char *out);
+int32_t fm_write_results_fast(const char *fn, const uint32_t *results, uint32_t num);
+
 /* device-side state hung off fmi_t.d_index */
 typedef struct {
   int32_t        ndev;
@@ -173,6 +177,17 @@ int32_t loadQueries(char *fn, uint32_t sizeQuery, uint32_t numQueries, void **qu
   qrys->num = numQueries; qrys->size = sizeQuery;
   qrys->h_queries = (char *) fmgpu_host_alloc(bytes ? bytes : 1);
   if (qrys->h_queries == NULL) { fclose(fp); free(qrys); return FM_E_ALLOCATING_MFASTA; }
+  {
+    /* fast path: mmap + all threads (fm_ingest.c); same contract as the stdio loop below, which stays as the
+     * fallback for files that cannot be mapped */
+    const int32_t fast = fm_parse_queries_mmap(fn, sizeQuery, numQueries, qrys->h_queries);
+    if (fast != FM_E_NOT_IMPLEMENTED) {
+      fclose(fp);
+      if (fast != FM_SUCCESS) { fmgpu_host_free(qrys->h_queries); free(qrys); return fast; }
+      *queries = qrys;
+      return FM_SUCCESS;
+    }
+  }
   while (got < numQueries && fgets(line, sizeof line, fp) != NULL) {
     size_t m;
     if (line[0] == '>') continue;
@@ -227,19 +242,8 @@ int32_t freeResults(void **results)
 
 int32_t writeResults(char *fn, uint32_t *results, uint32_t numqueries)
 {
-  FILE *fp;
-  uint32_t i;
-  char *buf;
   if (!fn || !results) return FM_E_OPENING_RESULTS_FILE;
-  fp = fopen(fn, "w");
-  if (fp == NULL) return FM_E_OPENING_RESULTS_FILE;
-  buf = (char *) malloc(1 << 22);
-  if (buf) setvbuf(fp, buf, _IOFBF, 1 << 22);
-  fprintf(fp, "%u\n", numqueries);
-  for (i = 0; i < numqueries; i++) fprintf(fp, "%u %u\n", results[2 * (size_t) i], results[2 * (size_t) i + 1]);
-  fclose(fp);
-  free(buf);
-  return FM_SUCCESS;
+  return fm_write_results_fast(fn, results, numqueries);     /* all threads format, bytes identical to the reference's */
 }
 
 int32_t loadResults(char *fn, void **results)

@@ -166,3 +166,47 @@ def test_host_stream_packer(built, nbases):
     code[nbases:] = 0
     want = (code[0::4] | code[1::4] << 2 | code[2::4] << 4 | code[3::4] << 6).astype(np.uint8)
     assert np.array_equal(out[: want.size], want)
+
+
+def test_fast_ingest_matches_reference_reader_semantics(built, tmp_path):
+    """mmap/OpenMP query parser: headers skipped, CRLF tolerated, missing final newline, extra reads ignored,
+    short file / wrong length rejected; large enough to be cut into per-thread slices."""
+    pkg = helpers.pkg()
+    L = pkg.lib()
+    text = helpers.synth_text(200_000, 3)
+    nq, length = 60_000, 37
+    reads = helpers.synth_reads(text, 8, nq, length)
+    r = reads.reshape(nq, length)
+    fa = tmp_path / "big.fa"
+    with open(fa, "wb") as f:
+        for i in range(nq):
+            f.write(b">rid%d %d-%d\n" % (i + 1, i, i + length))
+            f.write(r[i].tobytes() + (b"\r\n" if i % 7 == 0 else b"\n"))
+        f.seek(f.tell() - 1); f.truncate()                      # no newline at the end of the file
+    assert os.path.getsize(fa) > (1 << 20)
+    for want_n in (nq, nq - 12345, 1):
+        q = pkg.loadQueries(str(fa), length, want_n)
+        qs = C.cast(q, C.POINTER(pkg.qrys_t)).contents
+        got = np.ctypeslib.as_array(C.cast(qs.h_queries, C.POINTER(C.c_uint8)), shape=(want_n * length,))
+        assert np.array_equal(got, reads[: want_n * length])
+        L.freeQueries(C.byref(q))
+    h = C.c_void_p()
+    assert L.loadQueries(os.fsencode(str(fa)), length, nq + 1, C.byref(h)) == 12      # too few reads
+    assert L.loadQueries(os.fsencode(str(fa)), length + 1, nq, C.byref(h)) == 12      # wrong length
+    empty = tmp_path / "empty.fa"
+    empty.write_bytes(b"")
+    assert L.loadQueries(os.fsencode(str(empty)), 10, 1, C.byref(h)) == 12
+
+
+def test_fast_result_writer_is_byte_identical(built, tmp_path):
+    pkg = helpers.pkg()
+    L = pkg.lib()
+    rng = np.random.default_rng(0)
+    n = 300_001
+    res = rng.integers(0, 2 ** 32, 2 * n, dtype=np.uint64).astype(np.uint32)
+    res[:6] = [0, 0, 4294967295, 4294967295, 10, 9]
+    out = str(tmp_path / "r.txt")
+    assert L.writeResults(os.fsencode(out), res.ctypes.data, n) == 0
+    want = "%d\n" % n + "".join(f"{a} {b}\n" for a, b in res.reshape(-1, 2).tolist())
+    assert open(out).read() == want
+    assert helpers.results_text_md5(res) == __import__("hashlib").md5(want.encode()).hexdigest()
