@@ -275,6 +275,9 @@ int32_t fmgpu_search_device(const fmgpu_index_t *idx, const uint32_t *d_packed, 
 int32_t fmgpu_search_host(fmgpu_index_t *const *replicas, int32_t nreplicas, const char *h_ascii,
                           uint64_t nqueries, uint32_t len, uint32_t *h_results, const fmgpu_variant_t *v);
 
+/* frees the streams / staging buffers fmgpu_search_host keeps between calls (neither is re-entrant) */
+int32_t fmgpu_release_pipeline(void);
+
 /* host-side ASCII -> reversed 2-bit packing (same words as the device pack kernel); OpenMP over reads,
  * AVX-512 VBMI when the CPU has it.  packed holds nqueries * fmgpu_words_per_query(len) words. */
 void    fm_hostpack_reads(const char *ascii, uint64_t nqueries, uint32_t len, uint32_t *packed, int nthreads);

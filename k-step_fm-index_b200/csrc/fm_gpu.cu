@@ -791,6 +791,26 @@ extern "C" int32_t fmgpu_search_host(fmgpu_index_t *const *replicas, int32_t nre
   return FM_SUCCESS;
 }
 
+/* releases the streams and staging buffers fmgpu_search_host keeps between calls (they are re-created on demand).
+ * fmgpu_search_host and this function are not re-entrant: one caller thread at a time, like the reference driver. */
+extern "C" int32_t fmgpu_release_pipeline(void)
+{
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); return FM_SUCCESS; }
+  for (int d = 0; d < ndev && d < FM_MAX_DEVICES; d++)
+    for (int s = 0; s < FM_PIPE_STREAMS; s++) {
+      fm_pipe_lane *ln = &g_pipe[d][s];
+      if (!ln->stream && !ln->d_ascii && !ln->d_packed && !ln->d_results && !ln->h_packed) continue;
+      CU_TRY(cudaSetDevice(d));
+      if (ln->stream) { cudaStreamSynchronize(ln->stream); cudaStreamDestroy(ln->stream); }
+      if (ln->h2d_done) cudaEventDestroy(ln->h2d_done);
+      cudaFree(ln->d_ascii); cudaFree(ln->d_packed); cudaFree(ln->d_results);
+      if (ln->h_packed) cudaFreeHost(ln->h_packed);
+      memset(ln, 0, sizeof(*ln));
+    }
+  return FM_SUCCESS;
+}
+
 /* ------------------------------------------------------------------------ */
 /* page-aligned host memory, pinned when a CUDA device is there to pin it for
  * (on a box without a GPU the loaders still work; nothing can be searched) */

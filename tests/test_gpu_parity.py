@@ -169,6 +169,11 @@ def test_end_to_end_host_pipeline(pkg):
     got2 = pkg.search_host([idx, rep2], reps[: 1000 * length], length, pkg.variant(pkg.MODE_COOP))
     assert np.array_equal(got2, want[:2000])
     rep2.free(); idx.free()
+    assert pkg.lib().fmgpu_release_pipeline() == 0                 # staging buffers are re-created on demand
+    idx = pkg.DeviceIndex.from_image(g["image_100"])
+    assert np.array_equal(pkg.search_host([idx], reps[: 5000 * length], length), want[:10000])
+    idx.free()
+    assert pkg.lib().fmgpu_release_pipeline() == 0
 
 
 def test_pack_kernel_bit_layout(pkg):
