@@ -107,7 +107,10 @@ def reference_search_rate(pkg, image, sample_ascii, steps, warmup, threads=0):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     from bindings import RefSearcher
     ref = RefSearcher(K_STEPS, CHUNK, False)
-    cores = int(ref.lib.ref_max_threads()) if threads == 0 else threads
+    if threads == 0:
+        # all host cores, whatever OMP_NUM_THREADS says (torchrun forces it to 1 on its workers)
+        threads = int(os.environ.get("FM_BENCH_CPU_THREADS", str(os.cpu_count() or 1)))
+    cores = threads
     idx = ref.wrap_image(image)
     nq = sample_ascii.size // READ_LEN
     out = None
