@@ -143,10 +143,13 @@ double  sampleTime(void);
  *
  * transferCPUtoGPU: re-blocks the file entries into the device layout on the
  *   first configured GPU, replicates it to the others over NVLink peer copies,
+ *   builds the fused-step table on every replica (unless $FMGPU_MODE=task|coop),
  *   shards the batch contiguously (32-aligned) over the GPUs, uploads the
  *   ASCII reads and packs them to 2 bit on the device, allocates results.
  * searchIndexGPU: launches the search on every shard and waits (kernels only,
- *   like the reference's timed region).  Returns void like the reference;
+ *   like the reference's timed region); kernel family = $FMGPU_MODE, else the
+ *   fused-step kernel when the replica has a fused table, else Coop; or whatever
+ *   fmgpu_set_variant selected.  Returns void like the reference;
  *   a CUDA failure prints file:line and exits (reference HandleError, :88-93).
  * transferGPUtoCPU: per-GPU D2H of its (L,R) shard straight into h_results.
  */

@@ -1,7 +1,8 @@
 /*
  * fm_gpu.cu -- PART 2 of include/fmindex_b200.h: the thin C ABI over the
- * hand-written CUDA of fm_kernels.cuh (index residency / re-blocking, query
- * packing, search launches, replicas, pipelined end-to-end search, probe).
+ * hand-written CUDA of fm_kernels.cuh / fm_fused.cuh (index residency /
+ * re-blocking, fused-step table, query packing, search launches, replicas,
+ * pipelined end-to-end search with the hybrid host feed, roofline probes).
  *
  * Replaces the device-side support code every reference .cu carries
  * (transferCPUtoGPU / searchIndexGPU / transferGPUtoCPU / free*GPU, e.g.

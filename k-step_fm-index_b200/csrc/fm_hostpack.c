@@ -1,11 +1,15 @@
 /*
- * fm_hostpack.c -- host-side ASCII -> reversed 2-bit packing of reads (plain C, OpenMP, AVX-512 VBMI fast path).
+ * fm_hostpack.c -- host-side ASCII -> 2-bit packing of reads (plain C, OpenMP, AVX-512 fast paths).
  *
- * Same output as the device kernel fm_pack_kernel: packed position t of a read is base len-1-t, 16 bases per
- * 32-bit word, code A=0 C=1 G=2 T=3 from ASCII bits 2 and 1 (the reference's bit trick,
- * src/fmIndexCPUBaseline.c:213-226; case-insensitive, other bytes alias).  Used by fmgpu_search_host so that
- * 25 instead of 100 bytes per 100-bp read cross PCIe; replaces the host-side warp interleave of the reference
- * query loader (common/common.c:175-194).  This is data-format conversion only -- no search arithmetic here.
+ * Code A=0 C=1 G=2 T=3 from ASCII bits 2 and 1 (the reference's bit trick, src/fmIndexCPUBaseline.c:213-226;
+ * case-insensitive, other bytes alias).  Two packers:
+ *   fm_hostpack_stream  the whole batch as one 2-bit sequence, 64 bases per AVX-512 iteration and no per-read
+ *                       work; used by fmgpu_search_host so that 25 instead of 100 bytes per 100-bp read cross
+ *                       PCIe (the GPU's fm_unstream_kernel cuts, reverses and word-aligns the reads);
+ *   fm_hostpack_reads   per-read reversed words, byte-identical to the device kernel fm_pack_kernel (packed
+ *                       position t = base len-1-t, 16 bases per word); for callers that upload packed batches.
+ * Both replace the host-side warp interleave of the reference query loader (common/common.c:175-194).  This is
+ * data-format conversion only -- no search arithmetic here.
  */
 #include <stdint.h>
 #include <string.h>
