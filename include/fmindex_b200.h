@@ -278,6 +278,10 @@ int32_t fmgpu_search_device(const fmgpu_index_t *idx, const uint32_t *d_packed, 
 int32_t fmgpu_search_host(fmgpu_index_t *const *replicas, int32_t nreplicas, const char *h_ascii,
                           uint64_t nqueries, uint32_t len, uint32_t *h_results, const fmgpu_variant_t *v);
 
+/* same for reads that already are 2-bit packed on the host (binary read format = nqueries *
+ * fmgpu_words_per_query(len) words as written by fm_hostpack_reads): no conversion, 28 B per 100-bp read over PCIe */
+int32_t fmgpu_search_host_packed(fmgpu_index_t *const *replicas, int32_t nreplicas, const uint32_t *h_packed,
+                                 uint64_t nqueries, uint32_t len, uint32_t *h_results, const fmgpu_variant_t *v);
 /* frees the streams / staging buffers fmgpu_search_host keeps between calls (neither is re-entrant) */
 int32_t fmgpu_release_pipeline(void);
 

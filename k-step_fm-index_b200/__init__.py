@@ -135,6 +135,7 @@ PROTOTYPES = {
     "fmgpu_gather_probe_ex": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_int32, C.POINTER(C.c_double)]),
     "fm_hostpack_reads": (None, [_VP, C.c_uint64, C.c_uint32, _VP, C.c_int]),
     "fm_hostpack_reads_scalar": (None, [_VP, C.c_uint64, C.c_uint32, _VP]),
+    "fmgpu_search_host_packed": (C.c_int32, [_VPP, C.c_int32, _VP, C.c_uint64, C.c_uint32, _VP, C.POINTER(fmgpu_variant_t)]),
     "fmgpu_release_pipeline": (C.c_int32, []),
     "fm_hostpack_stream": (None, [_VP, C.c_uint64, _VP, C.c_int]),
     "fmgpu_unstream_device": (C.c_int32, [C.c_int32, _VP, C.c_uint64, C.c_uint32, _VP, _VP]),

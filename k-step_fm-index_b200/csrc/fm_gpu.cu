@@ -792,6 +792,45 @@ extern "C" int32_t fmgpu_search_host(fmgpu_index_t *const *replicas, int32_t nre
   return FM_SUCCESS;
 }
 
+/* Same pipeline for reads that already are 2-bit packed on the host (binary read format: per-read reversed
+ * words as produced by fm_hostpack_reads / the device pack kernel): 28 instead of 100 bytes per 100-bp read over
+ * PCIe and no conversion anywhere. */
+extern "C" int32_t fmgpu_search_host_packed(fmgpu_index_t *const *replicas, int32_t nrep, const uint32_t *h_packed, uint64_t nq,
+                                            uint32_t len, uint32_t *h_results, const fmgpu_variant_t *v)
+{
+  if (!replicas || nrep < 1 || nrep > FM_MAX_DEVICES || !h_packed || !h_results || len == 0) return fm_fail_msg(FM_E_BAD_ARGUMENT, "bad argument");
+  for (int g = 0; g < nrep; g++)
+    if (!replicas[g] || replicas[g]->device < 0 || replicas[g]->device >= FM_MAX_DEVICES) return fm_fail_msg(FM_E_BAD_ARGUMENT, "bad replica");
+  if (len % replicas[0]->meta.steps && !replicas[0]->meta.tail_valid) return fm_fail_msg(FM_E_QUERY_SHAPE, "read length must be a multiple of k");
+  if (nq == 0) return FM_SUCCESS;
+  const uint32_t wpq = fmgpu_words_per_query(len);
+  uint64_t chunk = 1ull << 19;
+  const uint64_t lanes = (uint64_t) nrep * FM_PIPE_STREAMS;
+  if (nq < chunk * lanes) chunk = ((nq + lanes - 1) / lanes + 31) & ~31ull;
+  if (chunk == 0) chunk = 32;
+  for (int g = 0; g < nrep; g++)
+    for (int s = 0; s < FM_PIPE_STREAMS; s++) {
+      int32_t rc = fm_pipe_reserve(replicas[g]->device, &g_pipe[replicas[g]->device][s], 0, chunk * wpq * 4, chunk * 8, 0);
+      if (rc) return rc;
+    }
+  uint64_t c = 0;
+  for (uint64_t q0 = 0; q0 < nq; q0 += chunk, c++) {
+    const uint64_t n = (nq - q0 < chunk) ? nq - q0 : chunk;
+    const fmgpu_index_t *idx = replicas[c % nrep];
+    fm_pipe_lane *ln = &g_pipe[idx->device][(c / nrep) % FM_PIPE_STREAMS];
+    CU_TRY(cudaSetDevice(idx->device));
+    CU_TRY(cudaMemcpyAsync(ln->d_packed, h_packed + q0 * wpq, n * wpq * 4, cudaMemcpyHostToDevice, ln->stream));
+    int32_t rc = fm_launch_search(idx, ln->d_packed, n, len, ln->d_results, v, ln->stream, NULL);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(h_results + 2 * q0, ln->d_results, n * 8, cudaMemcpyDeviceToHost, ln->stream));
+  }
+  for (int g = 0; g < nrep; g++) {
+    CU_TRY(cudaSetDevice(replicas[g]->device));
+    for (int s = 0; s < FM_PIPE_STREAMS; s++) CU_TRY(cudaStreamSynchronize(g_pipe[replicas[g]->device][s].stream));
+  }
+  return FM_SUCCESS;
+}
+
 /* releases the streams and staging buffers fmgpu_search_host keeps between calls (they are re-created on demand).
  * fmgpu_search_host and this function are not re-entrant: one caller thread at a time, like the reference driver. */
 extern "C" int32_t fmgpu_release_pipeline(void)

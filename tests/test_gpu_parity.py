@@ -521,3 +521,24 @@ def test_odd_read_length_on_2step_index_equals_1step_index(pkg, tmp_path, length
             b.search(idx, v)
             assert np.array_equal(b.download(), want), f"len {length} tag {tag} mode {v.mode} qpt {v.queries_per_thread}"
         b.free(); idx.free()
+
+
+def test_end_to_end_packed_input(pkg):
+    """fmgpu_search_host_packed: host reads already in the 2-bit binary format (fm_hostpack_reads words)."""
+    g = np.load(os.path.join(helpers.ROOT, "tests", "golden", "small_k2_d64.npz"))
+    length = int(g["length"])
+    reads = np.tile(g["reads"], 300)
+    want = np.tile(g["expected_std"], 300)
+    nq = reads.size // length
+    L = pkg.lib()
+    wpq = L.fmgpu_words_per_query(length)
+    packed = np.zeros(nq * wpq, dtype=np.uint32)
+    L.fm_hostpack_reads(reads.ctypes.data, nq, length, packed.ctypes.data, 0)
+    idx = pkg.DeviceIndex.from_image(g["image_100"]).fuse()
+    out = np.zeros(2 * nq, dtype=np.uint32)
+    for mode in (pkg.MODE_TASK, pkg.MODE_COOP, pkg.MODE_FUSED):
+        handles = (C.c_void_p * 1)(idx.handle)
+        v = pkg.variant(mode)
+        pkg.check(L.fmgpu_search_host_packed(handles, 1, packed.ctypes.data, nq, length, out.ctypes.data, C.byref(v)), "packed e2e")
+        assert np.array_equal(out, want), f"mode {mode}"
+    idx.free()
