@@ -319,6 +319,9 @@ int32_t  fmgpu_build_to_index(const fmgpu_build_t *b, fmgpu_index_t **out); /* r
 /* the reference's layout transformers on the GPU, byte-identical file images: tag 101
  * (src/transformIndexBitmaps.c:269-295), 200 and 201 (src/transformIndexAlternateCounters.c:387-479) */
 int32_t  fmgpu_build_transform(const fmgpu_build_t *tag100, uint32_t tag, fmgpu_build_t **out);
+/* writes the image as an index file readable by the reference tools and by loadIndex (saveIndex of
+ * src/genFMindex.c:155-181); bin/gfmi_b200 is the reference's generateIndex main rebuilt on these calls */
+int32_t  fmgpu_build_save(const fmgpu_build_t *b, const char *path);
 int32_t  fmgpu_build_free(fmgpu_build_t **b);
 const char *fmgpu_build_last_error(void);
 /* reads of fm_synth.h (exact substrings, uniform start) as ASCII into device memory */

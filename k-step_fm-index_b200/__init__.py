@@ -151,6 +151,7 @@ PROTOTYPES = {
     "fmgpu_build_download": (C.c_int32, [_VP, _VP]),
     "fmgpu_build_to_index": (C.c_int32, [_VP, _VPP]),
     "fmgpu_build_transform": (C.c_int32, [_VP, C.c_uint32, _VPP]),
+    "fmgpu_build_save": (C.c_int32, [_VP, C.c_char_p]),
     "fmgpu_build_free": (C.c_int32, [_VPP]),
     "fmgpu_build_last_error": (C.c_char_p, []),
     "fmgpu_synth_reads_device": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, _VP, _VP]),

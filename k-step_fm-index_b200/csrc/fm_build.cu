@@ -400,6 +400,28 @@ extern "C" int32_t fmgpu_build_download(const fmgpu_build_t *b, uint32_t *h_imag
   return FM_SUCCESS;
 }
 
+/* writes the image as an index FILE the reference tools (and loadIndex) read: same bytes as saveIndex of
+ * src/genFMindex.c:155-181 / src/transformIndexBitmaps.c:96-123 / src/transformIndexAlternateCounters.c:163-217 */
+extern "C" int32_t fmgpu_build_save(const fmgpu_build_t *b, const char *path)
+{
+  if (!b || !path) return FM_E_BAD_ARGUMENT;
+  CU_TRY(cudaSetDevice(b->device));
+  FILE *fp = fopen(path, "wb");
+  if (!fp) return FM_E_SAVING_INDEX_FILE;
+  const uint64_t slice = 64ull << 20;                       /* words per staging slice (256 MB) */
+  uint32_t *h = (uint32_t *) malloc((size_t)((b->image_words < slice ? b->image_words : slice) * 4));
+  if (!h) { fclose(fp); return FM_E_ALLOCATING_FMI; }
+  int32_t rc = FM_SUCCESS;
+  for (uint64_t w0 = 0; w0 < b->image_words && rc == FM_SUCCESS; w0 += slice) {
+    const uint64_t n = (b->image_words - w0 < slice) ? b->image_words - w0 : slice;
+    if (cudaMemcpy(h, b->d_image + w0, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); rc = FM_E_CUDA; break; }
+    if (fwrite(h, 4, n, fp) != n) rc = FM_E_SAVING_INDEX_FILE;
+  }
+  free(h);
+  if (fclose(fp) != 0 && rc == FM_SUCCESS) rc = FM_E_SAVING_INDEX_FILE;
+  return rc;
+}
+
 /* re-block the built image into the searchable device layout (no host round trip) */
 extern "C" int32_t fmgpu_build_to_index(const fmgpu_build_t *b, fmgpu_index_t **out)
 {

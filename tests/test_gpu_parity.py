@@ -542,3 +542,27 @@ def test_end_to_end_packed_input(pkg):
         pkg.check(L.fmgpu_search_host_packed(handles, 1, packed.ctypes.data, nq, length, out.ctypes.data, C.byref(v)), "packed e2e")
         assert np.array_equal(out, want), f"mode {mode}"
     idx.free()
+
+
+@pytest.mark.skipif(not helpers.has_ref_tools(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("k,d", [(1, 64), (2, 64), (2, 128)])
+def test_index_build_cli_writes_the_reference_files(pkg, tmp_path, k, d):
+    """bin/gfmi_b200 (the reference's generateIndex main rebuilt on the GPU builder): same file names, same bytes as
+    gfmiBaseLine_* + tfmiBMP_* + tfmiAC_*, and the reference CPU searcher accepts the files."""
+    n = 123_457
+    text = helpers.synth_text(n, seed=17)
+    refdir, mydir = tmp_path / "ref", tmp_path / "mine"
+    paths = helpers.build_reference_indexes(str(refdir), text, k, d)
+    os.makedirs(mydir)
+    fa = str(mydir / "ref.fa")
+    helpers.write_fasta_ref(fa, text)
+    exe = os.path.join(helpers.ROOT, helpers.PKG_NAME, "bin", "gfmi_b200")
+    out = helpers.run([exe, fa, str(n), str(k), str(d), "--all"])
+    assert "BUILD TIME" in out
+    for tag, suf in helpers.TAG_SUFFIX.items():
+        mine = f"{fa}.{n}.{d}fmi{k}steps.fmi{suf}"
+        assert open(mine, "rb").read() == open(paths[tag], "rb").read(), f"tag {tag} file differs"
+    reads = helpers.synth_reads(text, 4, 2000, 20 if k == 1 else 24)
+    ref = helpers.RefSearcher(k, d, False)
+    got, _ = ref.search(ref.load(f"{fa}.{n}.{d}fmi{k}steps.fmi"), reads, reads.size // 2000)
+    assert ((got[1::2] - got[0::2]) >= 1).all()
