@@ -23,9 +23,9 @@
  *                  '$' rows excluded}, acc = C table + '$' adjustments
  *                  (precalculateBasesKSteps, :184-260).
  *
- * Texts with long repeats defeat the prefix-key sort (equal-key runs are
- * ordered by one thread each); the builder then fails loudly with
- * FM_E_BUILDING_BWT instead of taking minutes -- use gfmiBaseLine for those.
+ * Runs of suffixes sharing their first 32 bases are rare in random text (ordered by
+ * one thread each, fmb_fix_runs_kernel); repetitive texts (runs > 64) take the general
+ * path, prefix doubling over the tied rows (fmb_prefix_doubling), so any text works.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -36,7 +36,7 @@
 #include "../../include/fmindex_b200.h"
 #include "fm_synth.h"
 
-#define FMB_MAX_RUN 2048u
+#define FMB_MAX_RUN 64u        /* longer runs of equal 32-base keys go to the prefix-doubling path */
 
 struct fmgpu_build {
   int       device;
@@ -245,6 +245,147 @@ __global__ void fmb_row_symbols_kernel(const uint64_t *__restrict__ pt, const ui
   syms[s] = sym;
 }
 
+/* ------------------------------------------------------------------------ *
+ * General path for repetitive texts: prefix doubling over the rows that are still tied after the 32-base sort.
+ * rank[p] (ISA) = first row of the group of suffix p; a tied suffix p gets the secondary key rank[p+h] (or, when
+ * p+h is past the end, "ended": before every live suffix, shorter first), groups are re-sorted with a segmented
+ * sort, split, and h doubles -- O(log n) rounds whatever the repeat structure.  Zero padding of the first key
+ * never contradicts the true order (end of text < A), it only leaves ties, which the rounds resolve.
+ * ------------------------------------------------------------------------ */
+__global__ void fmb_pd_heads_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint32_t *__restrict__ head)
+{
+  const uint64_t r = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  head[r] = (r == 0 || keys[r] != keys[r - 1]) ? (uint32_t) r : 0u;      /* max-scan turns this into the group's first row */
+}
+
+__global__ void fmb_pd_isa_kernel(const uint32_t *__restrict__ sa, const uint32_t *__restrict__ grp, uint64_t n, uint32_t *__restrict__ isa,
+                                  uint8_t *__restrict__ tied)
+{
+  const uint64_t r = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  isa[sa[r]] = grp[r];
+  tied[r] = (uint8_t)((r > 0 && grp[r - 1] == grp[r]) || (r + 1 < n && grp[r + 1] == grp[r]));
+}
+
+__global__ void fmb_pd_gather_kernel(const uint32_t *__restrict__ rows, uint32_t m, const uint32_t *__restrict__ sa,
+                                     const uint32_t *__restrict__ grp, uint32_t *__restrict__ t_sa, uint32_t *__restrict__ t_grp)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  t_sa[i] = sa[rows[i]]; t_grp[i] = grp[rows[i]];
+}
+
+__global__ void fmb_pd_sec_kernel(const uint32_t *__restrict__ t_sa, const uint32_t *__restrict__ t_grp, uint32_t m, uint64_t n,
+                                  uint64_t h, const uint32_t *__restrict__ isa, uint64_t *__restrict__ sec, uint32_t *__restrict__ seg_flag)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const uint64_t p = (uint64_t) t_sa[i] + h;
+  sec[i] = p < n ? (1ull << 32) + isa[p] : (n - t_sa[i]);              /* ended suffixes first, shorter first */
+  seg_flag[i] = (i == 0 || t_grp[i] != t_grp[i - 1]) ? 1u : 0u;
+}
+
+__global__ void fmb_pd_split_kernel(const uint64_t *__restrict__ sec_sorted, const uint32_t *__restrict__ seg_flag,
+                                    const uint32_t *__restrict__ rows, uint32_t m, uint32_t *__restrict__ newhead_row)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const bool head = seg_flag[i] || sec_sorted[i] != sec_sorted[i - 1];
+  newhead_row[i] = head ? rows[i] : 0u;
+}
+
+__global__ void fmb_pd_commit_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ sa_sorted,
+                                     const uint32_t *__restrict__ newgrp, uint32_t m, uint32_t *__restrict__ sa,
+                                     uint32_t *__restrict__ grp, uint32_t *__restrict__ isa, uint8_t *__restrict__ still)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  sa[rows[i]] = sa_sorted[i];
+  grp[rows[i]] = newgrp[i];
+  isa[sa_sorted[i]] = newgrp[i];
+  still[i] = (uint8_t)((i > 0 && newgrp[i - 1] == newgrp[i]) || (i + 1 < m && newgrp[i + 1] == newgrp[i]));
+}
+
+struct FmbMaxOp { __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; } };
+
+#define PD_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fmb_fail(e_, #call, __FILE__, __LINE__); goto pd_done; } } while (0)
+
+static int32_t fmb_prefix_doubling(uint64_t n, const uint64_t *keys_sorted, uint32_t *sa)
+{
+  int32_t rc = FM_SUCCESS;
+  uint32_t *grp = NULL, *isa = NULL, *rows = NULL, *rows2 = NULL, *t_sa = NULL, *t_sa2 = NULL, *t_grp = NULL, *seg_flag = NULL;
+  uint32_t *seg_off = NULL, *newhead = NULL, *newgrp = NULL, *d_count = NULL;
+  uint64_t *sec = NULL, *sec2 = NULL;
+  uint8_t *tied = NULL, *still = NULL;
+  void *tmp = NULL; size_t tmp_bytes = 0, need = 0;
+  uint32_t m = 0, nseg = 0;
+  const unsigned gb = (unsigned)((n + 255) / 256);
+  {
+    PD_TRY(cudaMalloc((void **) &grp, n * 4)); PD_TRY(cudaMalloc((void **) &isa, n * 4)); PD_TRY(cudaMalloc((void **) &tied, n));
+    PD_TRY(cudaMalloc((void **) &d_count, 8));
+    fmb_pd_heads_kernel<<<gb, 256>>>(keys_sorted, n, grp);
+    PD_TRY(cudaGetLastError());
+    PD_TRY(cub::DeviceScan::InclusiveScan(NULL, need, grp, grp, FmbMaxOp(), (int64_t) n));
+    tmp_bytes = need; PD_TRY(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+    PD_TRY(cub::DeviceScan::InclusiveScan(tmp, need, grp, grp, FmbMaxOp(), (int64_t) n));
+    fmb_pd_isa_kernel<<<gb, 256>>>(sa, grp, n, isa, tied);
+    PD_TRY(cudaGetLastError());
+    /* rows still tied, ascending */
+    PD_TRY(cudaMalloc((void **) &rows, n * 4));
+    {
+      cub::CountingInputIterator<uint32_t> iota(0);
+      PD_TRY(cub::DeviceSelect::Flagged(NULL, need, iota, tied, rows, d_count, (int64_t) n));
+      if (need > tmp_bytes) { cudaFree(tmp); tmp = NULL; tmp_bytes = need; PD_TRY(cudaMalloc(&tmp, tmp_bytes)); }
+      PD_TRY(cub::DeviceSelect::Flagged(tmp, need, iota, tied, rows, d_count, (int64_t) n));
+    }
+    PD_TRY(cudaMemcpy(&m, d_count, 4, cudaMemcpyDeviceToHost));
+    cudaFree(tied); tied = NULL;
+    if (m == 0) goto pd_done;
+    PD_TRY(cudaMalloc((void **) &rows2, (size_t) m * 4)); PD_TRY(cudaMalloc((void **) &t_sa, (size_t) m * 4)); PD_TRY(cudaMalloc((void **) &t_sa2, (size_t) m * 4));
+    PD_TRY(cudaMalloc((void **) &t_grp, (size_t) m * 4)); PD_TRY(cudaMalloc((void **) &seg_flag, (size_t) m * 4)); PD_TRY(cudaMalloc((void **) &seg_off, ((size_t) m + 1) * 4));
+    PD_TRY(cudaMalloc((void **) &newhead, (size_t) m * 4)); PD_TRY(cudaMalloc((void **) &newgrp, (size_t) m * 4));
+    PD_TRY(cudaMalloc((void **) &sec, (size_t) m * 8)); PD_TRY(cudaMalloc((void **) &sec2, (size_t) m * 8)); PD_TRY(cudaMalloc((void **) &still, m));
+    for (uint64_t h = 32; m > 0; h *= 2) {
+      const unsigned mb = (m + 255) / 256;
+      fmb_pd_gather_kernel<<<mb, 256>>>(rows, m, sa, grp, t_sa, t_grp);
+      fmb_pd_sec_kernel<<<mb, 256>>>(t_sa, t_grp, m, n, h, isa, sec, seg_flag);
+      PD_TRY(cudaGetLastError());
+      /* segment offsets = positions of the group heads inside the tied list */
+      {
+        cub::CountingInputIterator<uint32_t> iota(0);
+        PD_TRY(cub::DeviceSelect::Flagged(NULL, need, iota, seg_flag, seg_off, d_count, (int) m));
+        if (need > tmp_bytes) { cudaFree(tmp); tmp = NULL; tmp_bytes = need; PD_TRY(cudaMalloc(&tmp, tmp_bytes)); }
+        PD_TRY(cub::DeviceSelect::Flagged(tmp, need, iota, seg_flag, seg_off, d_count, (int) m));
+      }
+      PD_TRY(cudaMemcpy(&nseg, d_count, 4, cudaMemcpyDeviceToHost));
+      PD_TRY(cudaMemcpy(seg_off + nseg, &m, 4, cudaMemcpyHostToDevice));
+      PD_TRY(cub::DeviceSegmentedSort::SortPairs(NULL, need, sec, sec2, t_sa, t_sa2, (int) m, (int) nseg, seg_off, seg_off + 1));
+      if (need > tmp_bytes) { cudaFree(tmp); tmp = NULL; tmp_bytes = need; PD_TRY(cudaMalloc(&tmp, tmp_bytes)); }
+      PD_TRY(cub::DeviceSegmentedSort::SortPairs(tmp, need, sec, sec2, t_sa, t_sa2, (int) m, (int) nseg, seg_off, seg_off + 1));
+      fmb_pd_split_kernel<<<mb, 256>>>(sec2, seg_flag, rows, m, newhead);
+      PD_TRY(cudaGetLastError());
+      PD_TRY(cub::DeviceScan::InclusiveScan(NULL, need, newhead, newgrp, FmbMaxOp(), (int) m));
+      if (need > tmp_bytes) { cudaFree(tmp); tmp = NULL; tmp_bytes = need; PD_TRY(cudaMalloc(&tmp, tmp_bytes)); }
+      PD_TRY(cub::DeviceScan::InclusiveScan(tmp, need, newhead, newgrp, FmbMaxOp(), (int) m));
+      fmb_pd_commit_kernel<<<mb, 256>>>(rows, t_sa2, newgrp, m, sa, grp, isa, still);
+      PD_TRY(cudaGetLastError());
+      PD_TRY(cub::DeviceSelect::Flagged(NULL, need, rows, still, rows2, d_count, (int) m));
+      if (need > tmp_bytes) { cudaFree(tmp); tmp = NULL; tmp_bytes = need; PD_TRY(cudaMalloc(&tmp, tmp_bytes)); }
+      PD_TRY(cub::DeviceSelect::Flagged(tmp, need, rows, still, rows2, d_count, (int) m));
+      PD_TRY(cudaMemcpy(&m, d_count, 4, cudaMemcpyDeviceToHost));
+      { uint32_t *t = rows; rows = rows2; rows2 = t; }
+      if (h > 2 * n) break;                                             /* cannot happen: every suffix has ended by then */
+    }
+  }
+pd_done:
+  cudaFree(grp); cudaFree(isa); cudaFree(tied); cudaFree(rows); cudaFree(rows2); cudaFree(t_sa); cudaFree(t_sa2); cudaFree(t_grp);
+  cudaFree(seg_flag); cudaFree(seg_off); cudaFree(newhead); cudaFree(newgrp); cudaFree(sec); cudaFree(sec2); cudaFree(still);
+  cudaFree(d_count); cudaFree(tmp);
+  return rc;
+}
+#undef PD_TRY
+
 /* ------------------------------------------------------------------------ */
 static int32_t fmb_build(int device, const char *h_ascii, uint64_t n, uint64_t seed, uint32_t k, uint32_t d,
                          fmgpu_build_t **out)
@@ -295,12 +436,13 @@ static int32_t fmb_build(int device, const char *h_ascii, uint64_t n, uint64_t s
     BTRY(cudaGetLastError());
     uint32_t longest = 0;
     BTRY(cudaMemcpy(&longest, d_status, 4, cudaMemcpyDeviceToHost));
+    cudaFree(keys_a); keys_a = NULL; cudaFree(vals_a); vals_a = NULL;
     if (longest > FMB_MAX_RUN) {
-      snprintf(g_berr, sizeof g_berr, "fmgpu_build: text too repetitive for the prefix-key sorter (run of %u+ suffixes sharing 32 bases); use gfmiBaseLine", longest);
-      fprintf(stderr, "%s\n", g_berr);
-      rc = FM_E_BUILDING_BWT; goto done;
+      /* repetitive text: runs longer than FMB_MAX_RUN were left alone; order all tied rows by prefix doubling */
+      rc = fmb_prefix_doubling(n, keys_b, vals_b);
+      if (rc != FM_SUCCESS) goto done;
     }
-    cudaFree(keys_a); keys_a = NULL; cudaFree(keys_b); keys_b = NULL; cudaFree(vals_a); vals_a = NULL;
+    cudaFree(keys_b); keys_b = NULL;
 
     /* 3. '$' rows */
     BTRY(cudaMalloc((void **) &d_dpos, 2 * 4)); BTRY(cudaMalloc((void **) &d_dbase, 2 * 4));
