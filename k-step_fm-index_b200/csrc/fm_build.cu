@@ -37,6 +37,7 @@
 #include "fm_synth.h"
 
 #define FMB_MAX_RUN 64u        /* longer runs of equal 32-base keys go to the prefix-doubling path */
+#define FMB_MAX_DEPTH 8u       /* ... and so do runs whose members share more than 32*8 further bases */
 
 struct fmgpu_build {
   int       device;
@@ -104,9 +105,10 @@ __global__ void fmb_keys_kernel(const uint64_t *__restrict__ pt, uint64_t n, uin
 }
 
 /* suffix a < suffix b, both known to agree on their first 32 (padded) bases; end of text is smallest */
-__device__ bool fmb_suffix_less(const uint64_t *__restrict__ pt, uint64_t n, uint64_t a, uint64_t b)
+__device__ bool fmb_suffix_less(const uint64_t *__restrict__ pt, uint64_t n, uint64_t a, uint64_t b, bool *too_deep)
 {
   for (uint64_t off = 0;; off += 32) {
+    if (off > 32 * FMB_MAX_DEPTH) { *too_deep = true; return false; }   /* long common prefix: leave it to prefix doubling */
     const uint64_t ra = a + off, rb = b + off;
     if (ra >= n || rb >= n) return ra > rb;           /* the one that ended (larger position) is smaller */
     const uint64_t ka = fmb_key_at(pt, ra), kb = fmb_key_at(pt, rb);
@@ -135,12 +137,14 @@ __global__ void fmb_fix_runs_kernel(const uint64_t *__restrict__ pt, uint64_t n,
   const uint32_t len = (uint32_t)(end - r);
   atomicMax(status, len);
   if (len > FMB_MAX_RUN) return;
-  for (uint64_t i = r + 1; i < end; i++) {                            /* insertion sort by full comparison */
+  bool too_deep = false;
+  for (uint64_t i = r + 1; i < end && !too_deep; i++) {               /* insertion sort by full comparison */
     const uint32_t v = vals[i];
     uint64_t j = i;
-    while (j > r && fmb_suffix_less(pt, n, v, vals[j - 1])) { vals[j] = vals[j - 1]; j--; }
+    while (j > r && fmb_suffix_less(pt, n, v, vals[j - 1], &too_deep)) { vals[j] = vals[j - 1]; j--; }
     vals[j] = v;
   }
+  if (too_deep) atomicMax(status, 0xFFFFFFFFu);                       /* still a permutation of the run; doubling finishes it */
 }
 
 /* SA of row r (row 0 is the '$' suffix) */
