@@ -210,3 +210,16 @@ def test_fast_result_writer_is_byte_identical(built, tmp_path):
     want = "%d\n" % n + "".join(f"{a} {b}\n" for a, b in res.reshape(-1, 2).tolist())
     assert open(out).read() == want
     assert helpers.results_text_md5(res) == __import__("hashlib").md5(want.encode()).hexdigest()
+
+
+def test_header_is_plain_c(built, tmp_path):
+    """include/fmindex_b200.h must compile as C99 with no C++/CUDA/torch types, and link against the library."""
+    src = tmp_path / "use.c"
+    src.write_text('#include "fmindex_b200.h"\n'
+                   'int main(void) { fmgpu_variant_t v = {0, 0, 0, 0}; fmgpu_index_meta_t m; (void) v; (void) m;\n'
+                   '  return fmgpu_device_count() < 0 || errorCommon(0) == 0 || sizeof(fmi_t) < 14 * 4; }\n')
+    pkg = helpers.pkg()
+    exe = tmp_path / "use"
+    helpers.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(helpers.ROOT, "include"), str(src),
+                 "-L", os.path.dirname(pkg.LIB_PATH), "-lfmindex_b200", "-Wl,-rpath," + os.path.dirname(pkg.LIB_PATH), "-o", str(exe)])
+    helpers.run([str(exe)])
