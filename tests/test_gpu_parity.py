@@ -590,3 +590,47 @@ def test_gpu_builder_general_texts_prefix_doubling(pkg, tmp_path, name, k):
     b.free()
     assert np.array_equal(got[:6 + 2 * k], want[:6 + 2 * k]), "header / '$' rows differ"
     assert np.array_equal(got, want)
+
+
+@pytest.mark.skipif(not helpers.has_ref_tools(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", range(36))
+def test_fuzz_tiny_references(pkg, tmp_path, case):
+    """The survey's fuzz, on the GPU: tiny references (62...5000 bp; ACGT, AC and A-rich alphabets), d in {32,64,128},
+    k in {1,2}, read lengths 2...20 (random, prefixes and suffixes of the text).  Index files come from the reference
+    tools; every tag, every kernel family, against the reference searcher of that flavour -- '$' rows in every
+    position, AltCounters quirk cases included -- and the GPU builder / transformers must reproduce the files."""
+    rng = np.random.default_rng(1000 + case)
+    k = 1 + case % 2
+    d = (32, 64, 128)[(case // 2) % 3]
+    n = int(rng.integers(62, 5000))
+    if (n + 1) % d == 0:
+        n += 1                                                   # reference reads past its last entry there (App. C-2)
+    alphabet = (b"ACGT", b"AC", b"AAAAAACGT")[(case // 6) % 3]
+    text = np.frombuffer(alphabet, dtype=np.uint8)[rng.integers(0, len(alphabet), n)]
+    paths = helpers.build_reference_indexes(str(tmp_path), text, k, d)
+    length = int(rng.integers(1, 11)) * 2
+    starts = rng.integers(0, n - length + 1, 300)
+    reads = np.concatenate([text[s:s + length] for s in starts] + [text[:length], text[-length:], text[1:length + 1],
+                           np.frombuffer(alphabet, dtype=np.uint8)[rng.integers(0, len(alphabet), 200 * length)]])
+    b = pkg.IndexBuild.from_text(text, k, d)
+    for ac, tags in ((False, (100, 101)), (True, (200, 201))):
+        ref = helpers.RefSearcher(k, d, ac)
+        want, _ = ref.search(ref.load(paths[tags[0]]), reads, length)
+        for tag in tags:
+            image = np.fromfile(paths[tag], dtype=np.uint32)
+            mine = b if tag == 100 else b.transform(tag)
+            assert np.array_equal(mine.download(), image), f"case {case}: GPU-built tag {tag} differs from the reference file"
+            if tag != 100:
+                mine.free()
+            idx = pkg.DeviceIndex.from_image(image)
+            modes = [pkg.MODE_TASK, pkg.MODE_COOP]
+            if idx.meta.quirk_mask == 0:
+                idx.fuse(4, 2)
+                modes.append(pkg.MODE_FUSED)
+            batch = pkg.DeviceBatch(0, reads.size // length, length, k)
+            batch.upload_ascii(reads)
+            for mode in modes:
+                batch.search(idx, pkg.variant(mode))
+                assert np.array_equal(batch.download(), want), f"case {case}: k={k} d={d} n={n} tag={tag} mode={mode}"
+            batch.free(); idx.free()
+    b.free()
