@@ -669,8 +669,11 @@ extern "C" int  fm_hostpack_threads(void);
 extern "C" void fm_hostpack_reads(const char *ascii, uint64_t nq, uint32_t len, uint32_t *packed, int nthreads);
 extern "C" void fm_hostpack_stream(const char *ascii, uint64_t nbases, unsigned char *out, int nthreads);
 
+static bool g_pipe_allocated = false;          /* set when a call had to (re)allocate lane buffers: its timing is not representative */
+
 static int32_t fm_pipe_reserve(int device, fm_pipe_lane *ln, size_t ascii, size_t packed, size_t results, size_t hpacked)
 {
+  if (!ln->stream || ln->cap_ascii < ascii || ln->cap_packed < packed || ln->cap_results < results || ln->cap_hpacked < hpacked) g_pipe_allocated = true;
   CU_TRY(cudaSetDevice(device));
   if (!ln->stream) CU_TRY(cudaStreamCreateWithFlags(&ln->stream, cudaStreamNonBlocking));
   if (!ln->h2d_done) CU_TRY(cudaEventCreateWithFlags(&ln->h2d_done, cudaEventDisableTiming));
@@ -686,17 +689,31 @@ static int32_t fm_pipe_reserve(int device, fm_pipe_lane *ln, size_t ascii, size_
  *   2 = 2-bit packing on the host, 25 B/read over PCIe      (CPU-bound)
  *   3 = hybrid: the copy engine pulls ASCII chunks while the CPU threads pack other chunks; each chunk goes
  *       to whichever resource would otherwise idle (greedy on a PCIe-busy-until estimate)
- *   0 = auto: 3 when the CPU has AVX-512 and >= 2 threads, else 1 */
+ *   0 = auto: self-tuning.  Which of 1 and 3 wins depends on the host (with one rank on a 16-core box the hybrid
+ *       is 2x faster; with 8 ranks sharing a 32-core box's memory the plain ASCII copy is 8 % faster, because a
+ *       host-packed read costs 150 B of host memory traffic against 100 B): the first large calls time mode 3
+ *       and mode 1 once each and later calls use the faster one, re-probing the other every 64 calls. */
 enum { FM_FEED_AUTO = 0, FM_FEED_ASCII = 1, FM_FEED_HOSTPACK = 2, FM_FEED_HYBRID = 3 };
 
-static int fm_feed_mode(const fmgpu_variant_t *v)
+static double g_feed_rate[4] = { 0, 0, 0, 0 };   /* reads/s last measured per mode on large calls */
+static unsigned g_feed_calls = 0;
+
+static int fm_feed_mode(const fmgpu_variant_t *v, uint64_t nq, bool *probe)
 {
   int mode = v ? v->reserved : 0;
   const char *env = getenv("FMGPU_FEED");
+  *probe = false;
   if (mode == FM_FEED_AUTO && env && *env) mode = atoi(env);
-  if (mode < FM_FEED_ASCII || mode > FM_FEED_HYBRID)
-    mode = (fm_hostpack_has_simd() && fm_hostpack_threads() >= 2) ? FM_FEED_HYBRID : FM_FEED_ASCII;
-  return mode;
+  if (mode >= FM_FEED_ASCII && mode <= FM_FEED_HYBRID) return mode;
+  if (!(fm_hostpack_has_simd() && fm_hostpack_threads() >= 2)) return FM_FEED_ASCII;
+  if (nq < (1ull << 20)) return g_feed_rate[FM_FEED_ASCII] > g_feed_rate[FM_FEED_HYBRID] ? FM_FEED_ASCII : FM_FEED_HYBRID;
+  *probe = true;                                  /* large call: its rate is recorded */
+  const unsigned c = g_feed_calls++;
+  if (g_feed_rate[FM_FEED_HYBRID] == 0) return FM_FEED_HYBRID;
+  if (g_feed_rate[FM_FEED_ASCII] == 0) return FM_FEED_ASCII;
+  const int best = g_feed_rate[FM_FEED_ASCII] > g_feed_rate[FM_FEED_HYBRID] ? FM_FEED_ASCII : FM_FEED_HYBRID;
+  if (c % 64 == 63) return best == FM_FEED_ASCII ? FM_FEED_HYBRID : FM_FEED_ASCII;     /* re-probe the loser now and then */
+  return best;
 }
 
 static double fm_now(void)
@@ -718,7 +735,10 @@ extern "C" int32_t fmgpu_search_host(fmgpu_index_t *const *replicas, int32_t nre
   if (len % replicas[0]->meta.steps && !replicas[0]->meta.tail_valid) return fm_fail_msg(FM_E_QUERY_SHAPE, "read length must be a multiple of k");
   if (nq == 0) return FM_SUCCESS;
   const uint32_t wpq = fmgpu_words_per_query(len);
-  const int feed = fm_feed_mode(v);
+  bool probe = false;
+  const int feed = fm_feed_mode(v, nq, &probe);
+  const double t_call = fm_now();
+  g_pipe_allocated = false;
   /* chunk: 512 K reads, 32-aligned; small batches still get one chunk per lane */
   uint64_t chunk = 1ull << 19;
   const uint64_t lanes = (uint64_t) nrep * FM_PIPE_STREAMS;
@@ -789,6 +809,7 @@ extern "C" int32_t fmgpu_search_host(fmgpu_index_t *const *replicas, int32_t nre
     CU_TRY(cudaSetDevice(replicas[g]->device));
     for (int s = 0; s < FM_PIPE_STREAMS; s++) CU_TRY(cudaStreamSynchronize(g_pipe[replicas[g]->device][s].stream));
   }
+  if (probe && !g_pipe_allocated) g_feed_rate[feed] = (double) nq / (fm_now() - t_call);   /* self-tuning of the auto feed */
   return FM_SUCCESS;
 }
 

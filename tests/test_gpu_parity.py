@@ -165,6 +165,8 @@ def test_end_to_end_host_pipeline(pkg):
         for mode in (pkg.MODE_TASK, pkg.MODE_COOP):
             got = pkg.search_host([idx], big, length, pkg.variant(mode, feed=feed))
             assert np.array_equal(got, wantbig), f"feed {feed} mode {mode}"
+    for _ in range(4):                                           # auto feed: probes hybrid and ASCII, then keeps the faster
+        assert np.array_equal(pkg.search_host([idx], big, length, pkg.variant(pkg.MODE_COOP)), wantbig)
     rep2 = idx.replicate(0)                                      # second replica (same GPU) = second shard lane
     got2 = pkg.search_host([idx, rep2], reps[: 1000 * length], length, pkg.variant(pkg.MODE_COOP))
     assert np.array_equal(got2, want[:2000])
