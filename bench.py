@@ -377,7 +377,7 @@ def main():
             "cpu_baseline": cpu,
             "e2e": {"value": world * nq / e2e_ms_step / 1e3, "unit": "Mqueries/s", "ms_per_step": e2e_ms_step,
                     "h2d_bytes_per_step": nq * READ_LEN, "d2h_bytes_per_step": nq * 8, "matches_device_resident_result": same,
-                    "feed": os.environ.get("FMGPU_FEED", "auto (hybrid: ASCII over PCIe + AVX-512 host packing)"),
+                    "feed": os.environ.get("FMGPU_FEED", "auto (self-tuning during warm-up: hybrid of ASCII-over-PCIe and AVX-512 host packing, or ASCII only)"),
                     "host_pack_threads_per_rank": int(L.fm_hostpack_threads()),
                     "note": "h2d_bytes_per_step counts the ASCII reads handed to the call; host-packed chunks cross PCIe as 2-bit (25 B/read)"},
             "e2e_packed_input": {"value": world * nq / e2e_packed_ms_step / 1e3, "unit": "Mqueries/s", "ms_per_step": e2e_packed_ms_step,
