@@ -48,6 +48,7 @@ CHUNK = 64
 SEED_REF, SEED_READS = 1, 2
 CPU_SAMPLE = int(float(os.environ.get("FM_BENCH_CPU_SAMPLE", "1e6")))
 MODE = os.environ.get("FM_BENCH_MODE", "fused")           # fused | coop | task
+INDEX_TAG = int(os.environ.get("FM_BENCH_TAG", "100"))    # on-disk layout the device index is derived from
 
 
 class ClockSampler:
@@ -184,8 +185,15 @@ def main():
         build = pkg.IndexBuild.from_synth(N_TEXT, SEED_REF, K_STEPS, CHUNK, device=dev)
         setup["index_build_s"] = round(time.time() - t0, 3)
         t0 = time.time()
-        index = build.to_index()
+        if INDEX_TAG != 100:
+            # search a transformed layout (101 interleaved, 200/201 AltCounters): same files tfmiBMP_* / tfmiAC_* write
+            tbuild = build.transform(INDEX_TAG)
+            index = tbuild.to_index()
+            tbuild.free()
+        else:
+            index = build.to_index()
         setup["reblock_s"] = round(time.time() - t0, 3)
+        setup["index_tag"] = INDEX_TAG
         if world == 1 or args.impl == "reference":
             image = build.download()                       # host copy of the tag-100 file image for the CPU arm
         build.free()
