@@ -137,9 +137,14 @@ def test_dropin_file_flow_and_logical_shards(pkg, tmp_path):
             devices = [i % ndev for i in range(shards)]
             got = pkg.search_files(fn, qfa, length, nq, devices=devices, var=pkg.variant(pkg.MODE_COOP if shards == 2 else pkg.MODE_TASK))
             assert np.array_equal(got, g[key][: 2 * nq]), f"tag {tag} shards {shards}"
-            # default driver behaviour: replicas get a fused-step table, searchIndexGPU picks the fused kernel
-            got = pkg.search_files(fn, qfa, length, nq, devices=devices, var=None)
-            assert np.array_equal(got, g[key][: 2 * nq]), f"tag {tag} shards {shards} (auto mode)"
+            # driver defaults: $FMGPU_MODE auto (small index -> plain Coop) and fused (fused-step table on every replica)
+            for env_mode in ("auto", "fused", "task"):
+                os.environ["FMGPU_MODE"] = env_mode
+                try:
+                    got = pkg.search_files(fn, qfa, length, nq, devices=devices, var=None)
+                finally:
+                    del os.environ["FMGPU_MODE"]
+                assert np.array_equal(got, g[key][: 2 * nq]), f"tag {tag} shards {shards} (FMGPU_MODE={env_mode})"
     # the reference-shaped driver binary writes the reference's text format
     exe = os.path.join(helpers.ROOT, helpers.PKG_NAME, "bin", "fmIndexSearchGPU_b200")
     out = helpers.run([exe, fn, qfa, str(length), str(nq)])
