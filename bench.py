@@ -11,18 +11,23 @@ reads PER GPU (seed 2; rank r takes reads [r*10M, (r+1)*10M)) -> weak scaling; N
 BASELINE configs[3]'s 100 M-read shape.  A "step" = one pass of the search over the rank's 10 M reads.
 
   value      Mqueries/s, whole job, kernels only, reads packed and resident in HBM (the reference's own
-             timed region, common/searchQueries.c:78-98), CUDA events on the launching stream.
+             timed region, common/searchQueries.c:78-98), CUDA events on the launching stream.  Timed
+             kernel: the fused-step kernel (4 bases per fetch, table composed on the GPU from the 2-step
+             index; $FM_BENCH_MODE=coop|task times the plain 2-step kernels, which are also reported
+             beside it as plain_2step_kernel).
   e2e        same metric through the C-ABI call fmgpu_search_host with HOST buffers: pinned ASCII reads
-             H2D + 2-bit packing + search + (L,R) D2H inside the timed region, chunk-pipelined.
-  roofline   algorithmic bytes = (exact count of distinct 32-byte sectors an LF step must touch,
-             counted by an instrumented kernel run) x 32 B, over the search kernel's mean duration,
+             in, (L,R) in pinned host memory out, everything in between (H2D, 2-bit packing on the GPU
+             and/or the host, search, D2H) inside the timed region, chunk-pipelined.
+  roofline   algorithmic bytes = (exact count of distinct 32-byte sectors the 2-step search must touch,
+             counted by an instrumented kernel run) x 32 B, over the timed kernel's mean duration,
              against the measured HBM copy bandwidth of MEASURED_PEAKS.json; the measured random-access
-             ceiling (gather probe over the same 5.33 GB footprint) is reported next to it.
+             ceiling (gather probe over the same footprint) is reported next to it.
   cpu_baseline / --impl reference
              the reference's own searchIndexCPU (oracle/_ref/libref_search_k2_d64_std.so, compiled
              from /root/reference) on all host cores, on a bounded sample of the same reads.
 
-Inputs are larger than L2 (5.33 GB index, 250 MB packed reads vs 126 MB L2), so no flush between steps.
+Inputs are larger than L2 (68 GB fused table / 5.33 GB index, 250 MB packed reads vs 126 MB L2), so no flush
+between steps.
 """
 import argparse
 import ctypes as C
