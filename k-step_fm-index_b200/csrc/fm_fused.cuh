@@ -44,7 +44,7 @@ struct FmFusedParams {
   uint32_t nq;
   uint32_t nlead;             /* leading base-k steps                                              */
   uint32_t nfused;            /* fused steps                                                       */
-  uint32_t wpq, wpq_pad;      /* wpq_pad >= wpq + 1: a bit field may straddle into the next word   */
+  uint32_t wpq, wpq_pad;      /* words per packed read (wpq_pad unused: reads keep their natural stride) */
   uint32_t bwtsize;
   unsigned long long *fetch_counters;  /* COUNT only: [0] = fused blocks fetched, [1] = SB96 blocks of the leading steps */
   uint32_t has_tail, tail_row, tail_base, tail_const[4];   /* odd read length on a 2-step index, see fm_tail_rank */
@@ -105,7 +105,8 @@ __device__ __forceinline__ uint32_t fm_read_field(const uint32_t *q, uint32_t po
 template <int KF, int K, int LANES, int QPT, int THREADS, int MINB, bool COUNT>
 __global__ void __launch_bounds__(THREADS, MINB) fm_search_fused_kernel(const FmFusedParams p)
 {
-  extern __shared__ uint32_t sq[];
+  extern __shared__ __align__(16) uint32_t fsm[];             /* [0..3]: mbarrier (8 B) + pad; [4..): packed reads, natural stride */
+  uint32_t *sq = fsm + 4;
   constexpr uint32_t FBITS = 2 * KF, FMASK = (1u << FBITS) - 1u, BBITS = 2 * K, BMASK = (1u << BBITS) - 1u;
   constexpr uint32_t ROWS = FmFusedGeom<LANES>::ROWS;
   constexpr int GROUPS = THREADS / LANES;
@@ -113,17 +114,35 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_fused_kernel(const Fm
   const uint32_t nqb = min((uint32_t)(GROUPS * QPT), p.nq - q0);
   const uint32_t lg = threadIdx.x % LANES, group = threadIdx.x / LANES;
 
+  /* Stage this CTA's packed reads (one contiguous piece of the batch) in shared memory with ONE TMA bulk copy
+   * (cp.async.bulk global -> shared, completion on an mbarrier); a tail CTA whose piece is not a multiple of
+   * 16 bytes copies it with plain loads.  Reads keep their natural stride: a bit field never straddles out of a
+   * read, so the word after a read may be anything. */
   {
-    const uint32_t total = nqb * p.wpq;
+    const uint32_t bytes = nqb * p.wpq * 4u;
     const uint32_t *src = p.packed + (size_t) q0 * p.wpq;
-    for (uint32_t i = threadIdx.x; i < total; i += THREADS) {
-      const uint32_t q = i / p.wpq, w = i - q * p.wpq;
-      sq[q * p.wpq_pad + w] = __ldg(src + i);
+    const bool bulk = (bytes % 16u) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+    const uint32_t mbar = (uint32_t) __cvta_generic_to_shared(fsm);
+    if (bulk) {
+      if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"((uint32_t) __cvta_generic_to_shared(sq)), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+      }
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(mbar) : "memory");
+    } else {
+      for (uint32_t i = threadIdx.x; i < nqb * p.wpq; i += THREADS) sq[i] = __ldg(src + i);
+      __syncthreads();
     }
-    for (uint32_t q = threadIdx.x; q < nqb; q += THREADS)
-      for (uint32_t w = p.wpq; w < p.wpq_pad; w++) sq[q * p.wpq_pad + w] = 0u;
   }
-  __syncthreads();
 
   uint32_t L[QPT], R[QPT];
   const uint32_t *myq[QPT];
@@ -132,7 +151,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_fused_kernel(const Fm
   for (int i = 0; i < QPT; i++) {
     const uint32_t lq = i * GROUPS + group;
     live[i] = lq < nqb;
-    myq[i] = sq + (live[i] ? lq : 0u) * p.wpq_pad;
+    myq[i] = sq + (live[i] ? lq : 0u) * p.wpq;
     L[i] = 0u; R[i] = p.bwtsize;
   }
 

@@ -378,7 +378,7 @@ static int32_t fm_launch_fused(const fmgpu_index_t *idx, const uint32_t *d_packe
   uint32_t qper; size_t smem;
   for (;;) {
     qper = (256 / lanes) * v.queries_per_thread;
-    smem = (size_t) qper * p.wpq_pad * 4;
+    smem = 16 + ((size_t) qper * p.wpq + 4) * 4;             /* mbarrier + reads + one readable spare word */
     if (smem <= 200 * 1024) break;
     if (v.queries_per_thread > 1) v.queries_per_thread = 1;
     else return fm_fail_msg(FM_E_QUERY_SHAPE, "reads too long to stage in shared memory");
