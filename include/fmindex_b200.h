@@ -205,7 +205,7 @@ typedef struct {
   uint32_t tail_row;      /* row whose layer-1 char is '$' (dollarPositionBWT[1])             */
   uint32_t tail_base;     /* its layer-0 char (dollarBaseBWT[1] & 3)                           */
   uint32_t tail_const[4]; /* C1[c] - sum over c1 of rank2(c | c1<<2, 0)                         */
-  uint32_t reserved2;
+  uint32_t start_bases;   /* bases covered by the fused kernel's start table (12), 0 = none    */
 } fmgpu_index_meta_t;
 
 /* devices ---------------------------------------------------------------- */

@@ -69,7 +69,7 @@ class fmgpu_index_meta_t(C.Structure):
                 ("source_tag", C.c_uint32), ("quirk_start", C.c_uint32), ("quirk_mask", C.c_uint32), ("reserved", C.c_uint32),
                 ("nbytes", C.c_uint64), ("fused_bases", C.c_uint32), ("fused_lanes", C.c_uint32), ("fused_bytes", C.c_uint64),
                 ("tail_valid", C.c_uint32), ("tail_row", C.c_uint32), ("tail_base", C.c_uint32), ("tail_const", C.c_uint32 * 4),
-                ("reserved2", C.c_uint32)]
+                ("start_bases", C.c_uint32)]
 
 
 _VP, _VPP = C.c_void_p, C.POINTER(C.c_void_p)

@@ -48,7 +48,14 @@ struct FmFusedParams {
   uint32_t bwtsize;
   unsigned long long *fetch_counters;  /* COUNT only: [0] = fused blocks fetched, [1] = SB96 blocks of the leading steps */
   uint32_t has_tail, tail_row, tail_base, tail_const[4];   /* odd read length on a 2-step index, see fm_tail_rank */
+  /* start table: (L,R) after the first FM_START_BASES bases, indexed by their 24 packed bits -- the intervals this
+   * very kernel computes for all 4^12 12-mers, so looking them up instead of stepping changes nothing in the result;
+   * it replaces the L2-resident steps and the first DRAM step (two fetches) by one mostly-L2 lookup */
+  const uint2 *start;
+  uint32_t start_steps;       /* fused steps the table stands for (FM_START_BASES / KF), 0 = no table */
 };
+
+#define FM_START_BASES 12u
 
 __device__ __forceinline__ void fm_ldg32(const uint4 *p, uint32_t (&w)[8])
 {
@@ -172,7 +179,17 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_fused_kernel(const Fm
     }
   }
 
-  for (uint32_t step = 0; step < p.nfused; step++, pos += FBITS) {
+  uint32_t step0 = 0;
+  if (p.start_steps && p.nlead == 0 && p.nfused >= p.start_steps) {
+    #pragma unroll
+    for (int i = 0; i < QPT; i++) {
+      const uint2 lr = __ldg(p.start + (myq[i][0] & 0xFFFFFFu));
+      L[i] = lr.x; R[i] = lr.y;
+    }
+    step0 = p.start_steps; pos = 2u * FM_START_BASES;
+  }
+
+  for (uint32_t step = step0; step < p.nfused; step++, pos += FBITS) {
     uint32_t wL[QPT][8], wR[QPT][8], rL[QPT], rR[QPT];
     bool same[QPT];
     #pragma unroll

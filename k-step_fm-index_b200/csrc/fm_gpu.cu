@@ -27,6 +27,7 @@ struct fmgpu_index {
   uint4             *blocks;
   uint4             *fblocks;      /* fused-step table (fmgpu_index_fuse), or NULL */
   uint32_t           nfblocks;     /* fused blocks per fused symbol */
+  uint2             *start;        /* (L,R) of all 4^12 12-mers (start table of the fused kernel), or NULL */
 };
 
 struct fmgpu_batch {
@@ -249,7 +250,7 @@ extern "C" int32_t fmgpu_index_free(fmgpu_index_t **pidx)
 {
   if (!pidx || !*pidx) return FM_SUCCESS;
   fmgpu_index_t *idx = *pidx;
-  if (idx->blocks || idx->fblocks) { cudaSetDevice(idx->device); cudaFree(idx->blocks); cudaFree(idx->fblocks); }
+  if (idx->blocks || idx->fblocks || idx->start) { cudaSetDevice(idx->device); cudaFree(idx->blocks); cudaFree(idx->fblocks); cudaFree(idx->start); }
   free(idx);
   *pidx = NULL;
   return FM_SUCCESS;
@@ -259,6 +260,14 @@ extern "C" int32_t fmgpu_index_free(fmgpu_index_t **pidx)
  * fused-step table (fm_fused.cuh)
  * ------------------------------------------------------------------------ */
 static uint32_t fm_fused_rows(uint32_t lanes) { return 32u * (8u * lanes - 1u); }
+static const fmgpu_variant_t FM_DEFAULT_VARIANT = { FMGPU_MODE_TASK, 2, 256, 0 };
+static int32_t fm_launch_fused(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nq, uint32_t len,
+                               uint32_t *d_results, fmgpu_variant_t v, cudaStream_t stream, unsigned long long *d_counters = NULL);
+__global__ void fm_iota_kernel(uint32_t *out, uint32_t n)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
+}
 
 template <int LANES>
 static cudaError_t fm_fuse_build(const fmgpu_index_t *idx, const uint16_t *fsym, uint32_t nfsym, uint32_t nfb, uint32_t kbits,
@@ -322,14 +331,34 @@ extern "C" int32_t fmgpu_index_fuse(fmgpu_index_t *idx, uint32_t fused_bases, ui
   if (e != cudaSuccess) { cudaFree(fblocks); return fm_fail(e, "fmgpu_index_fuse", __FILE__, __LINE__); }
   idx->fblocks = fblocks; idx->nfblocks = nfb;
   idx->meta.fused_bases = kf; idx->meta.fused_lanes = lanes; idx->meta.fused_bytes = fbytes;
+
+  /* start table: the fused kernel itself searches all 4^12 12-mers once (a packed 12-mer IS its 24-bit key);
+   * only worth it when the table (134 MB) is small next to the index, and FM_START_BASES must be whole fused steps */
+  {
+    const char *env = getenv("FMGPU_START_TABLE");
+    const bool want = env && *env ? atoi(env) != 0 : idx->meta.nbytes >= (1ull << 30);
+    if (want && FM_START_BASES % kf == 0 && idx->meta.bwtsize > (1u << 24)) {
+      const uint32_t nkeys = 1u << (2 * FM_START_BASES);
+      uint32_t *keys = NULL; uint2 *table = NULL;
+      e = cudaMalloc((void **) &keys, (size_t) nkeys * 4);
+      if (e == cudaSuccess) e = cudaMalloc((void **) &table, (size_t) nkeys * 8);
+      if (e == cudaSuccess) { fm_iota_kernel<<<(nkeys + 255) / 256, 256>>>(keys, nkeys); e = cudaGetLastError(); }
+      int32_t rc = FM_SUCCESS;
+      if (e == cudaSuccess) rc = fm_launch_fused(idx, keys, nkeys, FM_START_BASES, (uint32_t *) table, FM_DEFAULT_VARIANT, 0);
+      if (e == cudaSuccess && rc == FM_SUCCESS) e = cudaDeviceSynchronize();
+      cudaFree(keys);
+      if (e != cudaSuccess || rc != FM_SUCCESS) { cudaFree(table); cudaGetLastError(); }   /* the table is optional */
+      else { idx->start = table; idx->meta.start_bases = FM_START_BASES; }
+    }
+  }
   return FM_SUCCESS;
 }
 
 extern "C" int32_t fmgpu_index_unfuse(fmgpu_index_t *idx)
 {
   if (!idx) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null index");
-  if (idx->fblocks) { CU_TRY(cudaSetDevice(idx->device)); cudaFree(idx->fblocks); idx->fblocks = NULL; }
-  idx->nfblocks = 0; idx->meta.fused_bases = 0; idx->meta.fused_lanes = 0; idx->meta.fused_bytes = 0;
+  if (idx->fblocks || idx->start) { CU_TRY(cudaSetDevice(idx->device)); cudaFree(idx->fblocks); cudaFree(idx->start); idx->fblocks = NULL; idx->start = NULL; }
+  idx->nfblocks = 0; idx->meta.fused_bases = 0; idx->meta.fused_lanes = 0; idx->meta.fused_bytes = 0; idx->meta.start_bases = 0;
   return FM_SUCCESS;
 }
 
@@ -361,7 +390,7 @@ static fm_fused_fn fm_pick_fused(uint32_t kf, uint32_t k, int lanes, int qpt)
 }
 
 static int32_t fm_launch_fused(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nq, uint32_t len,
-                               uint32_t *d_results, fmgpu_variant_t v, cudaStream_t stream, unsigned long long *d_counters = NULL)
+                               uint32_t *d_results, fmgpu_variant_t v, cudaStream_t stream, unsigned long long *d_counters)
 {
   if (!idx->fblocks) return fm_fail_msg(FM_E_BAD_ARGUMENT, "FMGPU_MODE_FUSED needs fmgpu_index_fuse() on this replica first");
   const uint32_t k = idx->meta.steps, kf = idx->meta.fused_bases, lanes = idx->meta.fused_lanes, hops = kf / k;
@@ -372,6 +401,7 @@ static int32_t fm_launch_fused(const fmgpu_index_t *idx, const uint32_t *d_packe
   p.nlead = (len / k) % hops; p.nfused = (len / k) / hops;
   p.wpq = fmgpu_words_per_query(len); p.wpq_pad = (p.wpq + 1) | 1u; p.bwtsize = idx->meta.bwtsize;
   p.fetch_counters = d_counters;
+  p.start = idx->start; p.start_steps = idx->start ? FM_START_BASES / kf : 0u;
   p.has_tail = len % k; p.tail_row = idx->meta.tail_row; p.tail_base = idx->meta.tail_base;
   for (int c = 0; c < 4; c++) p.tail_const[c] = idx->meta.tail_const[c];
   if (d_counters) v.queries_per_thread = 1;
@@ -436,8 +466,6 @@ static fm_kernel_fn fm_pick(int mode, int qpt, int tpb, bool quirk, bool count)
   }
   return NULL;
 }
-
-static const fmgpu_variant_t FM_DEFAULT_VARIANT = { FMGPU_MODE_TASK, 2, 256, 0 };
 
 static int32_t fm_launch_search(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nq, uint32_t len,
                                 uint32_t *d_results, const fmgpu_variant_t *vin, cudaStream_t stream,

@@ -402,7 +402,12 @@ def test_config3_full_size_against_reference_checksums(pkg):
             assert hashlib.md5(timg.data).hexdigest() == gold["md5"][name], f"tag {tag} image md5"
             del timg
         idx = t.to_index()
-        for mode in (pkg.MODE_TASK, pkg.MODE_COOP):
+        modes = [pkg.MODE_TASK, pkg.MODE_COOP]
+        if tag in (100, 201):
+            idx.fuse()                                           # 68 GB fused table + start table (auto at this size)
+            assert idx.meta.fused_bases == 4 and idx.meta.start_bases == 12
+            modes.append(pkg.MODE_FUSED)
+        for mode in modes:
             batch.search(idx, pkg.variant(mode))
             assert helpers.results_text_md5(batch.download()) == gold["md5"][key], f"tag {tag} mode {mode}"
         idx.free()
@@ -641,3 +646,40 @@ def test_fuzz_tiny_references(pkg, tmp_path, case):
                 assert np.array_equal(batch.download(), want), f"case {case}: k={k} d={d} n={n} tag={tag} mode={mode}"
             batch.free(); idx.free()
     b.free()
+
+
+@pytest.mark.parametrize("k", [1, 2])
+def test_fused_start_table(pkg, k):
+    """The fused kernel's start table ((L,R) of all 4^12 12-mers, computed by the kernel itself) must not change
+    any result: exact, mutated and random reads of several lengths (table used when len % fused width == 0 and
+    len >= 12), against the plain Coop kernel on the same index."""
+    n = 20_000_003                                               # bwtsize > 4^12, so the table is meaningful
+    os.environ["FMGPU_START_TABLE"] = "1"
+    try:
+        b = pkg.IndexBuild.from_synth(n, 3, k, 64)
+        idx = b.to_index().fuse(4, 2)
+        b.free()
+    finally:
+        del os.environ["FMGPU_START_TABLE"]
+    assert idx.meta.start_bases == 12
+    text_seed = 3
+    import torch
+    L = pkg.lib()
+    rng = np.random.default_rng(5)
+    for length in (12, 16, 24, 52, 100, 14, 10, 101 if k == 2 else 99):
+        nq = 200_000
+        d_ascii = torch.empty(nq * length, dtype=torch.uint8, device="cuda")
+        pkg.check(L.fmgpu_synth_reads_device(0, n, text_seed, nq, length, 2, 0, d_ascii.data_ptr(), None), "reads")
+        torch.cuda.synchronize()
+        reads = d_ascii.cpu().numpy().copy()
+        mut = rng.integers(0, nq * length, nq // 3)              # a third of the reads get one random base: many empty intervals
+        reads[mut] = ACGT[rng.integers(0, 4, mut.size)]
+        batch = pkg.DeviceBatch(0, nq, length, k)
+        batch.upload_ascii(reads)
+        batch.search(idx, pkg.variant(pkg.MODE_COOP))
+        want = batch.download()
+        for qpt in (1, 2):
+            batch.search(idx, pkg.variant(pkg.MODE_FUSED, qpt))
+            assert np.array_equal(batch.download(), want), f"k={k} len={length} qpt={qpt}"
+        batch.free()
+    idx.free()
