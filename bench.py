@@ -400,9 +400,11 @@ def main():
                          "sectors_per_lf_step": nsec.value / lf_steps, "blocks_per_lf_step": nblk.value / lf_steps,
                          "fused_blocks_per_launch": nfb.value if fused else None,
                          "fused_block_bytes_per_launch": nfb.value * 32 * meta.fused_lanes if fused else None,
-                         "dram_line_gbs": (nfb.value if fused else nblk.value) * 128 / (ms_step * 1e-3) / 1e9,
-                         "random_access_ceiling": {"accesses_per_s": probe, "line_gbs": probe * 128 / 1e9,
-                                                   "how": "independent uniform random 16-byte loads over a table of the same footprint; every miss moves a 128-byte line",
+                         "block_fetches_per_s": (nfb.value if fused else nblk.value) / (ms_step * 1e-3),
+                         "dram_fill_bytes_per_fetch": 64 if fused else 128,
+                         "random_access_ceiling": {"accesses_per_s": probe,
+                                                   "how": "independent uniform random 16-byte loads over a table of the same footprint; the ceiling is a miss RATE "
+                                                          "(requests/s), the same for 64- and 128-byte fills (profiles/r01_prefetch_variants.md)",
                                                    "block_fetches_per_s_over_ceiling": ((nfb.value if fused else nblk.value) / (ms_step * 1e-3)) / probe if probe else None},
                          "frac_of_nominal_8tbs": achieved / 8000.0},
             "plain_2step_kernel": plain,

@@ -57,9 +57,11 @@ struct FmFusedParams {
 
 #define FM_START_BASES 12u
 
+/* .L2::64B: an L2 miss then fills 64 bytes (the whole LANES=2 block) instead of the 128-byte line every other
+ * flavour pulls from HBM (profiles/r01_prefetch_variants.md) -- same fetch rate, half the DRAM traffic */
 __device__ __forceinline__ void fm_ldg32(const uint4 *p, uint32_t (&w)[8])
 {
-  asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  asm volatile("ld.global.L1::no_allocate.L2::evict_first.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
 }
 

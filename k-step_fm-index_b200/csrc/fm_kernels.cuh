@@ -64,6 +64,8 @@ struct FmRawIndex {
 __device__ __forceinline__ uint4 fm_ldg16(const uint4 *p)
 {
   uint4 v;
+  /* no .L2::64B here: the 128-byte fill an L2 miss triggers by default brings the 7 neighbouring blocks along, which
+   * the narrowing (L,R) interval of the next steps hits (profiles/r01_prefetch_variants.md) */
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
