@@ -12,9 +12,10 @@ BASELINE configs[3]'s 100 M-read shape.  A "step" = one pass of the search over 
 
   value      Mqueries/s, whole job, kernels only, reads packed and resident in HBM (the reference's own
              timed region, common/searchQueries.c:78-98), CUDA events on the launching stream.  Timed
-             kernel: the fused-step kernel (4 bases per fetch, table composed on the GPU from the 2-step
-             index; $FM_BENCH_MODE=coop|task times the plain 2-step kernels, which are also reported
-             beside it as plain_2step_kernel).
+             kernel: the sparse-step kernel (10 bases per 128-byte block fetch, table built on the GPU from
+             the 2-step index); the fused-step kernel (4 bases per fetch) and the plain 2-step Coop kernel
+             are timed beside it as fused_4base_kernel / plain_2step_kernel; $FM_BENCH_MODE=fused|coop|task
+             makes one of those the timed kernel instead.
   e2e        same metric through the C-ABI call fmgpu_search_host with HOST buffers: pinned ASCII reads
              in, (L,R) in pinned host memory out, everything in between (H2D, 2-bit packing on the GPU
              and/or the host, search, D2H) inside the timed region, chunk-pipelined.
@@ -26,8 +27,8 @@ BASELINE configs[3]'s 100 M-read shape.  A "step" = one pass of the search over 
              the reference's own searchIndexCPU (oracle/_ref/libref_search_k2_d64_std.so, compiled
              from /root/reference) on all host cores, on a bounded sample of the same reads.
 
-Inputs are larger than L2 (68 GB fused table / 5.33 GB index, 250 MB packed reads vs 126 MB L2), so no flush
-between steps.
+Inputs are larger than L2 (16 GB sparse table / 68 GB fused table / 5.33 GB index, 250 MB packed reads vs 126 MB
+L2), so no flush between steps.
 """
 import argparse
 import ctypes as C
@@ -52,7 +53,7 @@ K_STEPS = int(os.environ.get("FM_BENCH_K", "2"))
 CHUNK = 64
 SEED_REF, SEED_READS = 1, 2
 CPU_SAMPLE = int(float(os.environ.get("FM_BENCH_CPU_SAMPLE", "1e6")))
-MODE = os.environ.get("FM_BENCH_MODE", "fused")           # fused | coop | task
+MODE = os.environ.get("FM_BENCH_MODE", "sparse")          # sparse | fused | coop | task
 INDEX_TAG = int(os.environ.get("FM_BENCH_TAG", "100"))    # on-disk layout the device index is derived from
 
 
@@ -99,11 +100,11 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(fused):
+def ncu_traffic(which):
     """dram bytes per launch of the timed search kernel from the committed ncu capture (profiles/), if there is one."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
-        return d["fused" if fused else "plain"]["dram_bytes_per_launch_10m_reads"] * NQ_PER_GPU / 1e7
+        return d[which]["dram_bytes_per_launch_10m_reads"] * NQ_PER_GPU / 1e7
     except Exception:
         return None
 
@@ -266,7 +267,17 @@ def main():
     del d_ascii
     plain_var = pkg.variant(pkg.MODE_TASK if MODE == "task" else pkg.MODE_COOP, int(os.environ.get("FM_BENCH_QPT", "1")),
                             int(os.environ.get("FM_BENCH_TPB", "256")))
-    var, fused = plain_var, False
+    var, fused, sparse = plain_var, False, False
+    if MODE == "sparse":
+        # sparse-step table built on this replica from its own 2-step block table (every rank builds its own)
+        try:
+            t0 = time.time()
+            index.sparsify(int(os.environ.get("FM_BENCH_SPARSE_BASES", "0")), int(os.environ.get("FM_BENCH_SPARSE_LAMBDA", "12")))
+            torch.cuda.synchronize()
+            setup["sparsify_s"] = round(time.time() - t0, 3)
+            var, sparse = pkg.variant(pkg.MODE_SPARSE, int(os.environ.get("FM_BENCH_QPT", "2"))), True
+        except pkg.FMError as ex:
+            setup["sparse_unavailable"] = str(ex)
     if MODE == "fused":
         # fused-step table composed on this replica from its own 2-step block table (every rank builds its own)
         try:
@@ -289,17 +300,38 @@ def main():
     lf_steps = nq * (READ_LEN // K_STEPS)
     algo_bytes = nsec.value * 32
     nfb, nlb = C.c_uint64(), C.c_uint64()
+    novf = C.c_uint64()
     if fused:
         pkg.check(L.fmgpu_count_fetches_fused_device(index.handle, d_packed.data_ptr(), nq, READ_LEN, d_res.data_ptr(), stream,
                                                      C.byref(nfb), C.byref(nlb)), "count fused fetches")
+    if sparse:
+        pkg.check(L.fmgpu_count_fetches_sparse_device(index.handle, d_packed.data_ptr(), nq, READ_LEN, d_res.data_ptr(), stream,
+                                                      C.byref(nfb), C.byref(nlb), C.byref(novf)), "count sparse fetches")
 
     # measured random-access ceiling over the footprint the timed kernel walks (rank 0, once)
-    footprint = int(meta.fused_bytes) if fused else int(meta.nbytes)
+    footprint = int(meta.sparse_bytes) if sparse else int(meta.fused_bytes) if fused else int(meta.nbytes)
     probe = pkg.gather_probe(dev, footprint, 256, 2) if rank == 0 else 0.0
 
     # the plain 2-step kernel on the same reads, for reference next to the fused one (rank-local, not the headline)
-    plain = None
-    if fused:
+    plain, fused_extra = None, None
+    if sparse and os.environ.get("FM_BENCH_ALSO_FUSED", "1") != "0":
+        # the fused-step kernel (previous headline kernel) on the same reads; its 68 GB table is released again
+        try:
+            index.fuse()
+            fv = pkg.variant(pkg.MODE_FUSED, 2)
+            for _ in range(3):
+                search_step(fv)
+            fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            fe0.record()
+            for _ in range(5):
+                search_step(fv)
+            fe1.record(); torch.cuda.synchronize()
+            fused_extra = {"kernel": "fused: 4 bases/step, 64-byte blocks", "table_gb": index.meta.fused_bytes / 1e9,
+                           "ms_per_step": fe0.elapsed_time(fe1) / 5, "mqueries_per_s_per_gpu": nq / (fe0.elapsed_time(fe1) / 5) / 1e3}
+            index.unfuse()
+        except pkg.FMError as ex:
+            fused_extra = {"unavailable": str(ex)}
+    if fused or sparse:
         for _ in range(3):
             search_step(plain_var)
         pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -388,26 +420,36 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "lf_steps_per_s": world * lf_steps / (ms_step * 1e-3),
             "config": {"workload": workload,
-                       "kernel": (f"fused: {meta.fused_bases} bases/step, {32 * meta.fused_lanes}-byte blocks, {meta.fused_lanes} x 256-bit loads, qpt={var.queries_per_thread}"
+                       "kernel": (f"sparse: {meta.sparse_bases} bases/step, 128-byte blocks of occurrence rows (lambda {meta.sparse_lambda}), 4 x 256-bit loads, "
+                                  f"{meta.sparse_start_bases}-base start table, qpt={var.queries_per_thread}" if sparse else
+                                  f"fused: {meta.fused_bases} bases/step, {32 * meta.fused_lanes}-byte blocks, {meta.fused_lanes} x 256-bit loads, qpt={var.queries_per_thread}"
                                   if fused else f"{MODE} qpt={var.queries_per_thread} tpb={var.threads_per_block}"),
-                       "device_layout": (f"fused-step table {meta.fused_bytes / 1e9:.1f} GB composed on the GPU from the 2-step SB96 table ({meta.nbytes / 1e9:.2f} GB)"
+                       "device_layout": (f"sparse-step table {meta.sparse_bytes / 1e9:.1f} GB ({meta.sparse_blocks} blocks, {meta.sparse_overflow} overfull -> SB96 steps) "
+                                         f"built on the GPU from the 2-step SB96 table ({meta.nbytes / 1e9:.2f} GB)" if sparse else
+                                         f"fused-step table {meta.fused_bytes / 1e9:.1f} GB composed on the GPU from the 2-step SB96 table ({meta.nbytes / 1e9:.2f} GB)"
                                          if fused else "SB96 (16-byte per-symbol blocks: u32 rank + 96 indicator bits)"),
                        "l2": f"inputs larger than L2 ({footprint / 1e9:.1f} GB table, 250 MB packed reads vs 126 MB L2), no flush",
                        "parallelism": f"index replicated, reads sharded x{world}, no collective in the search", "setup": setup},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(fused),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("sparse" if sparse else "fused" if fused else "plain"),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                          "algorithmic_model": "SURVEY 8(d): 32 B x exact count of sectors the 2-step search must touch (LF steps x |{sector(L),sector(R)}|)",
+                         "note": ("the algorithmic bytes are those of the reference's 2-step algorithm; the sparse-step layout needs fewer block fetches than that "
+                                  "algorithm has LF steps, so frac may exceed 1 -- table_block_bytes_per_launch and traffic are what this kernel really moves, "
+                                  "block_fetches_per_s_over_ceiling is its distance from the measured random-access ceiling") if sparse else None,
                          "sectors_per_lf_step": nsec.value / lf_steps, "blocks_per_lf_step": nblk.value / lf_steps,
-                         "fused_blocks_per_launch": nfb.value if fused else None,
-                         "fused_block_bytes_per_launch": nfb.value * 32 * meta.fused_lanes if fused else None,
-                         "block_fetches_per_s": (nfb.value if fused else nblk.value) / (ms_step * 1e-3),
+                         "table_blocks_per_launch": nfb.value if (fused or sparse) else None,
+                         "table_block_bytes_per_launch": nfb.value * (128 if sparse else 32 * meta.fused_lanes) if (fused or sparse) else None,
+                         "sb96_blocks_per_launch": nlb.value if (fused or sparse) else nblk.value,
+                         "overflow_fallbacks_per_launch": novf.value if sparse else None,
+                         "block_fetches_per_s": ((nfb.value + nlb.value) if (fused or sparse) else nblk.value) / (ms_step * 1e-3),
                          "dram_fill_bytes_per_fetch": 64 if fused else 128,
                          "random_access_ceiling": {"accesses_per_s": probe,
                                                    "how": "independent uniform random 16-byte loads over a table of the same footprint; the ceiling is a miss RATE "
                                                           "(requests/s), the same for 64- and 128-byte fills (profiles/r01_prefetch_variants.md)",
-                                                   "block_fetches_per_s_over_ceiling": ((nfb.value if fused else nblk.value) / (ms_step * 1e-3)) / probe if probe else None},
+                                                   "block_fetches_per_s_over_ceiling": (((nfb.value + nlb.value) if (fused or sparse) else nblk.value) / (ms_step * 1e-3)) / probe if probe else None},
                          "frac_of_nominal_8tbs": achieved / 8000.0},
             "plain_2step_kernel": plain,
+            "fused_4base_kernel": fused_extra,
             "cpu_baseline": cpu,
             "e2e": {"value": world * nq / e2e_ms_step / 1e3, "unit": "Mqueries/s", "ms_per_step": e2e_ms_step,
                     "h2d_bytes_per_step": nq * READ_LEN, "d2h_bytes_per_step": nq * 8, "matches_device_resident_result": same,

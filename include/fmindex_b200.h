@@ -167,7 +167,7 @@ int32_t freeResultsGPU(void **results);
 typedef struct fmgpu_index fmgpu_index_t;   /* device-resident re-blocked index (one GPU) */
 typedef struct fmgpu_batch fmgpu_batch_t;   /* device-resident query shard + its results  */
 
-enum { FMGPU_MODE_TASK = 0, FMGPU_MODE_COOP = 1, FMGPU_MODE_FUSED = 2 };
+enum { FMGPU_MODE_TASK = 0, FMGPU_MODE_COOP = 1, FMGPU_MODE_FUSED = 2, FMGPU_MODE_SPARSE = 3 };
 
 /* Kernel variant.  Zero-initialised = library defaults. */
 typedef struct {
@@ -175,7 +175,9 @@ typedef struct {
                                  FMGPU_MODE_COOP: lane pair per query, L lane + R lane,
                                  block fetch shared through warp shuffles;
                                  FMGPU_MODE_FUSED: fused-step table (fmgpu_index_fuse): a lane group fetches one
-                                 32/64/128-byte block with 256-bit loads and consumes up to 4 bases per step   */
+                                 32/64/128-byte block with 256-bit loads and consumes up to 4 bases per step;
+                                 FMGPU_MODE_SPARSE: sparse-step table (fmgpu_index_sparsify): one 128-byte block
+                                 of occurrence rows per fetch, up to 12 bases per step                         */
   int32_t queries_per_thread; /* independent queries interleaved per thread/lane pair: 1, 2 or 4 */
   int32_t threads_per_block;  /* 128, 256 or 512                                      */
   int32_t reserved;           /* fmgpu_search_host only (also $FMGPU_FEED): 0 = auto, 1 = upload ASCII and pack
@@ -206,6 +208,14 @@ typedef struct {
   uint32_t tail_base;     /* its layer-0 char (dollarBaseBWT[1] & 3)                           */
   uint32_t tail_const[4]; /* C1[c] - sum over c1 of rank2(c | c1<<2, 0)                         */
   uint32_t start_bases;   /* bases covered by the fused kernel's start table (12), 0 = none    */
+  /* sparse-step table (fmgpu_index_sparsify), 0 = none */
+  uint32_t sparse_bases;       /* bases per sparse step                                         */
+  uint32_t sparse_lambda;      /* target occurrences per 128-byte block                         */
+  uint64_t sparse_bytes;       /* blocks + directory (+ start table)                            */
+  uint64_t sparse_blocks;      /* number of 128-byte blocks                                     */
+  uint64_t sparse_overflow;    /* blocks holding more than 31 occurrences (served by SB96 steps) */
+  uint32_t sparse_start_bases; /* bases covered by the sparse kernel's start table, 0 = none    */
+  uint32_t reserved2;
 } fmgpu_index_meta_t;
 
 /* devices ---------------------------------------------------------------- */
@@ -240,6 +250,14 @@ int32_t fmgpu_index_alloc_like(int32_t device, const fmgpu_index_meta_t *meta, f
  * FM_E_NOT_IMPLEMENTED when nothing fits or the index carries the AltCounters padding quirk. */
 int32_t fmgpu_index_fuse(fmgpu_index_t *idx, uint32_t fused_bases, uint32_t lanes, uint64_t budget_bytes);
 int32_t fmgpu_index_unfuse(fmgpu_index_t *idx);
+/* Sparse-step table, built on the GPU from this replica's own block table: one sparse step = sparse_bases/k
+ * reference LF steps (exactly); per wide symbol the occurrence rows are cut into 128-byte blocks of ~lambda rows,
+ * one block fetch per rank (csrc/fm_sparse.cuh).  sparse_bases 0 = the widest multiple of k up to 10 that leaves
+ * at least 64 rows per symbol; lambda 0 = 16; the table takes ~128/lambda bytes per text base whatever the width.
+ * Blocks with more than 31 occurrences (repeats) are served by ordinary steps on the block table.
+ * FM_E_NOT_IMPLEMENTED when memory does not suffice or the index carries the AltCounters padding quirk. */
+int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_bases, uint32_t lambda);
+int32_t fmgpu_index_unsparsify(fmgpu_index_t *idx);
 int32_t fmgpu_index_get_meta(const fmgpu_index_t *idx, fmgpu_index_meta_t *meta);
 void   *fmgpu_index_blocks(const fmgpu_index_t *idx);     /* device pointer */
 int32_t fmgpu_index_device(const fmgpu_index_t *idx);
@@ -338,6 +356,10 @@ int32_t fmgpu_gather_probe_ex(int32_t device, uint64_t table_bytes, uint32_t acc
 /* same for FMGPU_MODE_FUSED: fused-table blocks and SB96 blocks (leading steps) one search must fetch */
 int32_t fmgpu_count_fetches_fused_device(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nqueries, uint32_t len,
                                          uint32_t *d_results, void *stream, uint64_t *nfused_blocks, uint64_t *nlead_blocks);
+/* same for FMGPU_MODE_SPARSE: sparse blocks, SB96 blocks (leading steps + overflow fallback), overflow events */
+int32_t fmgpu_count_fetches_sparse_device(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nqueries, uint32_t len,
+                                          uint32_t *d_results, void *stream, uint64_t *nsparse_blocks, uint64_t *nsb96_blocks,
+                                          uint64_t *noverflows);
 /* locality variant: the 32 lanes of every warp-level load fall inside ONE random window of
  * `window_bytes` (e.g. one 2 MB page), random blocks inside it: isolates address-translation cost */
 int32_t fmgpu_gather_probe_local(int32_t device, uint64_t table_bytes, uint64_t window_bytes, uint64_t loads_per_thread,

@@ -30,7 +30,7 @@ FM_E_CUDA = 50
 FM_E_BAD_ARGUMENT = 51
 FM_E_UNSUPPORTED_INDEX = 52
 FM_E_QUERY_SHAPE = 53
-MODE_TASK, MODE_COOP, MODE_FUSED = 0, 1, 2
+MODE_TASK, MODE_COOP, MODE_FUSED, MODE_SPARSE = 0, 1, 2, 3
 
 
 def build_native(verbose=False):
@@ -69,7 +69,10 @@ class fmgpu_index_meta_t(C.Structure):
                 ("source_tag", C.c_uint32), ("quirk_start", C.c_uint32), ("quirk_mask", C.c_uint32), ("reserved", C.c_uint32),
                 ("nbytes", C.c_uint64), ("fused_bases", C.c_uint32), ("fused_lanes", C.c_uint32), ("fused_bytes", C.c_uint64),
                 ("tail_valid", C.c_uint32), ("tail_row", C.c_uint32), ("tail_base", C.c_uint32), ("tail_const", C.c_uint32 * 4),
-                ("start_bases", C.c_uint32)]
+                ("start_bases", C.c_uint32),
+                ("sparse_bases", C.c_uint32), ("sparse_lambda", C.c_uint32), ("sparse_bytes", C.c_uint64),
+                ("sparse_blocks", C.c_uint64), ("sparse_overflow", C.c_uint64), ("sparse_start_bases", C.c_uint32),
+                ("reserved2", C.c_uint32)]
 
 
 _VP, _VPP = C.c_void_p, C.POINTER(C.c_void_p)
@@ -108,6 +111,8 @@ PROTOTYPES = {
     "fmgpu_index_alloc_like": (C.c_int32, [C.c_int32, C.POINTER(fmgpu_index_meta_t), _VPP]),
     "fmgpu_index_fuse": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, C.c_uint64]),
     "fmgpu_index_unfuse": (C.c_int32, [_VP]),
+    "fmgpu_index_sparsify": (C.c_int32, [_VP, C.c_uint32, C.c_uint32]),
+    "fmgpu_index_unsparsify": (C.c_int32, [_VP]),
     "fmgpu_index_get_meta": (C.c_int32, [_VP, C.POINTER(fmgpu_index_meta_t)]),
     "fmgpu_index_blocks": (_VP, [_VP]),
     "fmgpu_index_device": (C.c_int32, [_VP]),
@@ -144,6 +149,8 @@ PROTOTYPES = {
     "fmgpu_gather_probe_local": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.POINTER(C.c_double)]),
     "fmgpu_count_fetches_device": (C.c_int32, [_VP, _VP, C.c_uint64, C.c_uint32, _VP, _VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "fmgpu_count_fetches_fused_device": (C.c_int32, [_VP, _VP, C.c_uint64, C.c_uint32, _VP, _VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "fmgpu_count_fetches_sparse_device": (C.c_int32, [_VP, _VP, C.c_uint64, C.c_uint32, _VP, _VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                                      C.POINTER(C.c_uint64)]),
     "fmgpu_build_from_text": (C.c_int32, [C.c_int32, _VP, C.c_uint64, C.c_uint32, C.c_uint32, _VPP]),
     "fmgpu_build_from_synth": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, _VPP]),
     "fmgpu_build_image_words": (C.c_uint64, [_VP]),
@@ -299,6 +306,14 @@ class DeviceIndex:
 
     def unfuse(self):
         check(lib().fmgpu_index_unfuse(self.handle), "fmgpu_index_unfuse")
+
+    def sparsify(self, sparse_bases=0, lam=0):
+        """Builds the sparse-step table (up to 12 bases per 128-byte block fetch) for MODE_SPARSE searches."""
+        check(lib().fmgpu_index_sparsify(self.handle, sparse_bases, lam), "fmgpu_index_sparsify")
+        return self
+
+    def unsparsify(self):
+        check(lib().fmgpu_index_unsparsify(self.handle), "fmgpu_index_unsparsify")
 
     def replicate(self, device):
         h = C.c_void_p()

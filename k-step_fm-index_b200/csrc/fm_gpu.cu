@@ -18,8 +18,11 @@
 #include <time.h>
 #include <cuda_runtime.h>
 #include "../../include/fmindex_b200.h"
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include "fm_kernels.cuh"
 #include "fm_fused.cuh"
+#include "fm_sparse.cuh"
 
 struct fmgpu_index {
   int                device;
@@ -28,6 +31,9 @@ struct fmgpu_index {
   uint4             *fblocks;      /* fused-step table (fmgpu_index_fuse), or NULL */
   uint32_t           nfblocks;     /* fused blocks per fused symbol */
   uint2             *start;        /* (L,R) of all 4^12 12-mers (start table of the fused kernel), or NULL */
+  uint4             *sblocks;      /* sparse-step table (fmgpu_index_sparsify), or NULL */
+  uint2             *sdir;         /* its directory: { first block, scale } per wide symbol */
+  uint2             *sstart;       /* start table of the sparse kernel, or NULL */
 };
 
 struct fmgpu_batch {
@@ -216,6 +222,10 @@ extern "C" int32_t fmgpu_index_alloc_like(int32_t device, const fmgpu_index_meta
   fmgpu_index_t *idx = (fmgpu_index_t *) calloc(1, sizeof(*idx));
   if (!idx) return fm_fail_msg(FM_E_ALLOCATING_FMI, "host allocation failed");
   idx->device = device; idx->meta = *meta;
+  /* derived tables are per replica: a fresh replica has none until fmgpu_index_fuse / fmgpu_index_sparsify run on it */
+  idx->meta.fused_bases = 0; idx->meta.fused_lanes = 0; idx->meta.fused_bytes = 0; idx->meta.start_bases = 0;
+  idx->meta.sparse_bases = 0; idx->meta.sparse_lambda = 0; idx->meta.sparse_bytes = 0; idx->meta.sparse_blocks = 0;
+  idx->meta.sparse_overflow = 0; idx->meta.sparse_start_bases = 0;
   cudaError_t e = cudaMalloc((void **) &idx->blocks, meta->nbytes);
   if (e != cudaSuccess) { free(idx); return fm_fail(e, "cudaMalloc(SB96 replica)", __FILE__, __LINE__); }
   *out = idx;
@@ -250,7 +260,11 @@ extern "C" int32_t fmgpu_index_free(fmgpu_index_t **pidx)
 {
   if (!pidx || !*pidx) return FM_SUCCESS;
   fmgpu_index_t *idx = *pidx;
-  if (idx->blocks || idx->fblocks || idx->start) { cudaSetDevice(idx->device); cudaFree(idx->blocks); cudaFree(idx->fblocks); cudaFree(idx->start); }
+  if (idx->blocks || idx->fblocks || idx->start || idx->sblocks) {
+    cudaSetDevice(idx->device);
+    cudaFree(idx->blocks); cudaFree(idx->fblocks); cudaFree(idx->start);
+    cudaFree(idx->sblocks); cudaFree(idx->sdir); cudaFree(idx->sstart);
+  }
   free(idx);
   *pidx = NULL;
   return FM_SUCCESS;
@@ -422,6 +436,207 @@ static int32_t fm_launch_fused(const fmgpu_index_t *idx, const uint32_t *d_packe
   return FM_SUCCESS;
 }
 
+
+/* ------------------------------------------------------------------------ *
+ * sparse-step table (fm_sparse.cuh)
+ * ------------------------------------------------------------------------ */
+static int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nq, uint32_t len,
+                                uint32_t *d_results, fmgpu_variant_t v, cudaStream_t stream, unsigned long long *d_counters = NULL);
+
+extern "C" int32_t fmgpu_index_unsparsify(fmgpu_index_t *idx)
+{
+  if (!idx) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null index");
+  if (idx->sblocks || idx->sdir || idx->sstart) {
+    CU_TRY(cudaSetDevice(idx->device));
+    cudaFree(idx->sblocks); cudaFree(idx->sdir); cudaFree(idx->sstart);
+    idx->sblocks = NULL; idx->sdir = NULL; idx->sstart = NULL;
+  }
+  idx->meta.sparse_bases = 0; idx->meta.sparse_lambda = 0; idx->meta.sparse_bytes = 0; idx->meta.sparse_blocks = 0;
+  idx->meta.sparse_overflow = 0; idx->meta.sparse_start_bases = 0;
+  return FM_SUCCESS;
+}
+
+extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_bases, uint32_t lambda)
+{
+  if (!idx) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null index");
+  if (idx->sblocks) return FM_SUCCESS;
+  if (idx->meta.quirk_mask) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "sparse steps are unavailable for an AltCounters index carrying the padding-entry quirk");
+  if (idx->meta.bwtsize >= FM_SP_OVF) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "text too long for the sparse-step table");
+  CU_TRY(cudaSetDevice(idx->device));
+  const uint32_t k = idx->meta.steps, n = idx->meta.bwtsize;
+  if (lambda == 0) lambda = 16;
+  if (lambda > FM_SP_SLOTS) return fm_fail_msg(FM_E_BAD_ARGUMENT, "lambda must be 1..31");
+  uint32_t ks = sparse_bases;
+  if (ks == 0) {                                               /* widest multiple of k up to 10 with >= 64 rows per symbol */
+    for (uint32_t cand = 10; cand >= 2 * k; cand--)
+      if (cand % k == 0 && (((uint64_t) 64) << (2 * cand)) <= n) { ks = cand; break; }
+    if (ks == 0) ks = 2 * k;
+  }
+  if (ks % k || ks <= k || ks > 12) return fm_fail_msg(FM_E_BAD_ARGUMENT, "sparse bases must be a multiple of k, larger than k and at most 12");
+  const uint32_t nsym = 1u << (2 * ks), hops = ks / k, kbits = 2 * k;
+  const uint64_t nrows = (uint64_t) idx->meta.nblocks * FM_SB_ROWS;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = ~(size_t) 0; }
+  const uint64_t est_blocks = (uint64_t) n / lambda + nsym;
+  const uint64_t need = 16ull * n + nrows + est_blocks * 128ull + 32ull * nsym + (1ull << 30);
+  if (need > free_b) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "not enough free device memory to build the sparse-step table");
+
+  uint8_t *sym = NULL; uint32_t *keys = NULL, *rows = NULL, *keys2 = NULL, *rows2 = NULL, *symstart = NULL, *nb = NULL, *first = NULL, *rank0 = NULL;
+  uint2 *dir = NULL; uint4 *sblocks = NULL; void *tmp = NULL; unsigned long long *d_novf = NULL;
+  size_t tmp_bytes = 0, tmp2 = 0;
+  uint64_t total_blocks = 0; unsigned long long novf = 0;
+  cudaError_t e = cudaMalloc((void **) &sym, nrows);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &keys, 4ull * n);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &rows, 4ull * n);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &keys2, 4ull * n);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &rows2, 4ull * n);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &symstart, 4ull * (nsym + 1));
+  if (e == cudaSuccess) e = cudaMalloc((void **) &nb, 4ull * nsym);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &first, 4ull * nsym);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &rank0, 4ull * nsym);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &dir, 8ull * nsym);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &d_novf, 8);
+  if (e == cudaSuccess) e = cudaMemset(d_novf, 0, 8);
+  if (e == cudaSuccess) {
+    fm_fuse_symbols_kernel<<<(idx->meta.nblocks + 127) / 128, 128>>>(idx->blocks, idx->meta.nblocks, idx->meta.nsymbols, nrows, sym);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) {
+    fm_sparse_compose_kernel<<<(unsigned)(((uint64_t) n + 255) / 256), 256>>>(idx->blocks, idx->meta.nblocks, sym, n, kbits, hops, nsym, keys, rows);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(NULL, tmp_bytes, keys, keys2, rows, rows2, (int64_t) n, 0, (int)(2 * ks + 1));
+  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(NULL, tmp2, nb, first, (int) nsym);
+  if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
+  if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16);
+  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, rows, rows2, (int64_t) n, 0, (int)(2 * ks + 1));
+  if (e == cudaSuccess) {
+    fm_sparse_symstart_kernel<<<(nsym + 1 + 255) / 256, 256>>>(keys2, n, nsym, symstart);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) {
+    fm_sparse_nblocks_kernel<<<(nsym + 255) / 256, 256>>>(symstart, nsym, lambda, nb);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, nb, first, (int) nsym);
+  if (e == cudaSuccess) {
+    uint32_t last_first = 0, last_nb = 0;
+    e = cudaMemcpy(&last_first, first + (nsym - 1), 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(&last_nb, nb + (nsym - 1), 4, cudaMemcpyDeviceToHost);
+    total_blocks = (uint64_t) last_first + last_nb;
+  }
+  /* the sort's input buffers are dead now: release them before the table is allocated */
+  cudaFree(keys); keys = NULL; cudaFree(rows); rows = NULL; cudaFree(sym); sym = NULL;
+  if (e == cudaSuccess && total_blocks >= (1ull << 32)) e = cudaErrorInvalidValue;
+  if (e == cudaSuccess) e = cudaMalloc((void **) &sblocks, total_blocks * 128ull);
+  if (e == cudaSuccess) {
+    fm_sparse_dir_kernel<<<(nsym + 255) / 256, 256>>>(idx->blocks, idx->meta.nblocks, kbits, hops, nsym, n, nb, first, dir, rank0);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) {
+    fm_sparse_fill_kernel<<<nsym, 128>>>(rows2, symstart, dir, nb, rank0, sblocks, d_novf);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(&novf, d_novf, 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaFree(sym); cudaFree(keys); cudaFree(rows); cudaFree(keys2); cudaFree(rows2); cudaFree(symstart); cudaFree(nb); cudaFree(first);
+  cudaFree(rank0); cudaFree(tmp); cudaFree(d_novf);
+  if (e != cudaSuccess) { cudaFree(sblocks); cudaFree(dir); return fm_fail(e, "fmgpu_index_sparsify", __FILE__, __LINE__); }
+  idx->sblocks = sblocks; idx->sdir = dir;
+  idx->meta.sparse_bases = ks; idx->meta.sparse_lambda = lambda; idx->meta.sparse_blocks = total_blocks;
+  idx->meta.sparse_overflow = novf; idx->meta.sparse_bytes = total_blocks * 128ull + 8ull * nsym;
+
+  /* start table: the sparse kernel itself searches every SB-mer once (a packed SB-mer IS its key); SB = the
+   * largest whole number of sparse steps within 12 bases */
+  {
+    const char *env = getenv("FMGPU_START_TABLE");
+    const bool want = env && *env ? atoi(env) != 0 : idx->meta.nbytes >= (1ull << 30);
+    const uint32_t ssteps = 12 / ks, sb = ssteps * ks;
+    if (want && ssteps && ((uint64_t) 1 << (2 * sb)) < n) {
+      const uint32_t nkeys = 1u << (2 * sb);
+      uint32_t *skeys = NULL; uint2 *table = NULL;
+      e = cudaMalloc((void **) &skeys, (size_t) nkeys * 4);
+      if (e == cudaSuccess) e = cudaMalloc((void **) &table, (size_t) nkeys * 8);
+      if (e == cudaSuccess) { fm_iota_kernel<<<(nkeys + 255) / 256, 256>>>(skeys, nkeys); e = cudaGetLastError(); }
+      int32_t rc = FM_SUCCESS;
+      if (e == cudaSuccess) rc = fm_launch_sparse(idx, skeys, nkeys, sb, (uint32_t *) table, FM_DEFAULT_VARIANT, 0);
+      if (e == cudaSuccess && rc == FM_SUCCESS) e = cudaDeviceSynchronize();
+      cudaFree(skeys);
+      if (e != cudaSuccess || rc != FM_SUCCESS) { cudaFree(table); cudaGetLastError(); }   /* the table is optional */
+      else { idx->sstart = table; idx->meta.sparse_start_bases = sb; idx->meta.sparse_bytes += (uint64_t) nkeys * 8; }
+    }
+  }
+  return FM_SUCCESS;
+}
+
+typedef void (*fm_sparse_fn)(const FmSparseParams);
+template <int K>
+static fm_sparse_fn fm_pick_sparse(int qpt)
+{
+  if (qpt == 0) return fm_search_sparse_kernel<K, 1, 256, 6, true>;               /* instrumented */
+  if (qpt == 1) return fm_search_sparse_kernel<K, 1, 256, 6, false>;
+  if (qpt == 2) return fm_search_sparse_kernel<K, 2, 256, 4, false>;
+  if (qpt == 4) return fm_search_sparse_kernel<K, 4, 256, 2, false>;
+  return NULL;
+}
+
+static int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nq, uint32_t len,
+                                uint32_t *d_results, fmgpu_variant_t v, cudaStream_t stream, unsigned long long *d_counters)
+{
+  if (!idx->sblocks) return fm_fail_msg(FM_E_BAD_ARGUMENT, "FMGPU_MODE_SPARSE needs fmgpu_index_sparsify() on this replica first");
+  const uint32_t k = idx->meta.steps, ks = idx->meta.sparse_bases, hops = ks / k;
+  if (v.queries_per_thread != 1 && v.queries_per_thread != 2 && v.queries_per_thread != 4) v.queries_per_thread = 2;
+  FmSparseParams p;
+  p.sblocks = idx->sblocks; p.dir = idx->sdir; p.blocks = idx->blocks; p.packed = d_packed; p.results = d_results;
+  p.nblocks = idx->meta.nblocks; p.nq = (uint32_t) nq;
+  p.nlead = (len / k) % hops; p.nsteps = (len / k) / hops;
+  p.wpq = fmgpu_words_per_query(len); p.bwtsize = idx->meta.bwtsize;
+  p.sbits = 2 * ks; p.hops = hops;
+  p.fetch_counters = d_counters;
+  p.start = idx->sstart; p.start_steps = idx->sstart ? idx->meta.sparse_start_bases / ks : 0u;
+  p.has_tail = len % k; p.tail_row = idx->meta.tail_row; p.tail_base = idx->meta.tail_base;
+  for (int c = 0; c < 4; c++) p.tail_const[c] = idx->meta.tail_const[c];
+  if (d_counters) v.queries_per_thread = 1;
+  uint32_t qper; size_t smem;
+  for (;;) {
+    qper = (256 / FM_SP_LANES) * v.queries_per_thread;
+    smem = 16 + ((size_t) qper * p.wpq + 4) * 4;
+    if (smem <= 200 * 1024) break;
+    if (v.queries_per_thread > 1) v.queries_per_thread /= 2;
+    else return fm_fail_msg(FM_E_QUERY_SHAPE, "reads too long to stage in shared memory");
+  }
+  fm_sparse_fn fn = k == 2 ? fm_pick_sparse<2>(d_counters ? 0 : v.queries_per_thread) : fm_pick_sparse<1>(d_counters ? 0 : v.queries_per_thread);
+  if (!fn) return fm_fail_msg(FM_E_BAD_ARGUMENT, "no sparse kernel for this variant");
+  if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  const uint32_t grid = (uint32_t)((nq + qper - 1) / qper);
+  void *args[] = { (void *) &p };
+  CU_TRY(cudaLaunchKernel((const void *) fn, dim3(grid), dim3(256), args, smem, stream));
+  return FM_SUCCESS;
+}
+
+extern "C" int32_t fmgpu_count_fetches_sparse_device(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nq, uint32_t len,
+                                                     uint32_t *d_results, void *stream, uint64_t *nsparse_blocks, uint64_t *nsb96_blocks,
+                                                     uint64_t *noverflows)
+{
+  if (!idx || !d_packed || !d_results) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
+  if (len == 0 || (len % idx->meta.steps && !idx->meta.tail_valid)) return fm_fail_msg(FM_E_QUERY_SHAPE, "read length must be a positive multiple of k");
+  CU_TRY(cudaSetDevice(idx->device));
+  unsigned long long *d_c = NULL, h[3] = { 0, 0, 0 };
+  CU_TRY(cudaMalloc((void **) &d_c, 24));
+  CU_TRY(cudaMemsetAsync(d_c, 0, 24, (cudaStream_t) stream));
+  int32_t rc = nq ? fm_launch_sparse(idx, d_packed, nq, len, d_results, FM_DEFAULT_VARIANT, (cudaStream_t) stream, d_c) : FM_SUCCESS;
+  if (rc == FM_SUCCESS) {
+    cudaError_t e = cudaMemcpyAsync(h, d_c, 24, cudaMemcpyDeviceToHost, (cudaStream_t) stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t) stream);
+    if (e != cudaSuccess) rc = fm_fail(e, "fetch counters D2H", __FILE__, __LINE__);
+  }
+  cudaFree(d_c);
+  if (nsparse_blocks) *nsparse_blocks = h[0];
+  if (nsb96_blocks) *nsb96_blocks = h[1];
+  if (noverflows) *noverflows = h[2];
+  return rc;
+}
+
 /* ------------------------------------------------------------------------ *
  * kernel dispatch
  * ------------------------------------------------------------------------ */
@@ -484,6 +699,7 @@ static int32_t fm_launch_search(const fmgpu_index_t *idx, const uint32_t *d_pack
   const bool count = d_counters != NULL;
   if (count) { v.mode = FMGPU_MODE_TASK; v.queries_per_thread = 1; v.threads_per_block = 256; }
   if (v.mode == FMGPU_MODE_FUSED) return fm_launch_fused(idx, d_packed, nq, len, d_results, vin ? *vin : FM_DEFAULT_VARIANT, stream);
+  if (v.mode == FMGPU_MODE_SPARSE) return fm_launch_sparse(idx, d_packed, nq, len, d_results, vin ? *vin : FM_DEFAULT_VARIANT, stream);
 
   FmSearchParams p;
   p.blocks = idx->blocks; p.packed = d_packed; p.results = d_results; p.fetch_counters = d_counters;
