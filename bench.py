@@ -272,10 +272,11 @@ def main():
         # sparse-step table built on this replica from its own 2-step block table (every rank builds its own)
         try:
             t0 = time.time()
-            index.sparsify(int(os.environ.get("FM_BENCH_SPARSE_BASES", "0")), int(os.environ.get("FM_BENCH_SPARSE_LAMBDA", "12")))
+            index.sparsify(int(os.environ.get("FM_BENCH_SPARSE_BASES", "0")), int(os.environ.get("FM_BENCH_SPARSE_LAMBDA", "0")),
+                           int(os.environ.get("FM_BENCH_SPARSE_LANES", "0")))
             torch.cuda.synchronize()
             setup["sparsify_s"] = round(time.time() - t0, 3)
-            var, sparse = pkg.variant(pkg.MODE_SPARSE, int(os.environ.get("FM_BENCH_QPT", "2"))), True
+            var, sparse = pkg.variant(pkg.MODE_SPARSE, int(os.environ.get("FM_BENCH_QPT", "4"))), True
         except pkg.FMError as ex:
             setup["sparse_unavailable"] = str(ex)
     if MODE == "fused":
@@ -420,7 +421,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "lf_steps_per_s": world * lf_steps / (ms_step * 1e-3),
             "config": {"workload": workload,
-                       "kernel": (f"sparse: {meta.sparse_bases} bases/step, 128-byte blocks of occurrence rows (lambda {meta.sparse_lambda}), 4 x 256-bit loads, "
+                       "kernel": (f"sparse: {meta.sparse_bases} bases/step, {32 * meta.sparse_lanes}-byte blocks of occurrence rows (lambda {meta.sparse_lambda}), {meta.sparse_lanes} x 256-bit loads, "
                                   f"{meta.sparse_start_bases}-base start table, qpt={var.queries_per_thread}" if sparse else
                                   f"fused: {meta.fused_bases} bases/step, {32 * meta.fused_lanes}-byte blocks, {meta.fused_lanes} x 256-bit loads, qpt={var.queries_per_thread}"
                                   if fused else f"{MODE} qpt={var.queries_per_thread} tpb={var.threads_per_block}"),
@@ -438,11 +439,11 @@ def main():
                                   "block_fetches_per_s_over_ceiling is its distance from the measured random-access ceiling") if sparse else None,
                          "sectors_per_lf_step": nsec.value / lf_steps, "blocks_per_lf_step": nblk.value / lf_steps,
                          "table_blocks_per_launch": nfb.value if (fused or sparse) else None,
-                         "table_block_bytes_per_launch": nfb.value * (128 if sparse else 32 * meta.fused_lanes) if (fused or sparse) else None,
+                         "table_block_bytes_per_launch": nfb.value * 32 * (meta.sparse_lanes if sparse else meta.fused_lanes) if (fused or sparse) else None,
                          "sb96_blocks_per_launch": nlb.value if (fused or sparse) else nblk.value,
                          "overflow_fallbacks_per_launch": novf.value if sparse else None,
                          "block_fetches_per_s": ((nfb.value + nlb.value) if (fused or sparse) else nblk.value) / (ms_step * 1e-3),
-                         "dram_fill_bytes_per_fetch": 64 if fused else 128,
+                         "dram_fill_bytes_per_fetch": 64 if (fused or (sparse and meta.sparse_lanes == 2)) else 128,
                          "random_access_ceiling": {"accesses_per_s": probe,
                                                    "how": "independent uniform random 16-byte loads over a table of the same footprint; the ceiling is a miss RATE "
                                                           "(requests/s), the same for 64- and 128-byte fills (profiles/r01_prefetch_variants.md)",

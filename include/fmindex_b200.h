@@ -143,13 +143,14 @@ double  sampleTime(void);
  *
  * transferCPUtoGPU: re-blocks the file entries into the device layout on the
  *   first configured GPU, replicates it to the others over NVLink peer copies,
- *   builds the fused-step table on every replica (unless $FMGPU_MODE=task|coop),
+ *   builds the sparse-step table on every replica of an index larger than L2
+ *   ($FMGPU_MODE=sparse|fused|task|coop forces a kernel family),
  *   shards the batch contiguously (32-aligned) over the GPUs, uploads the
  *   ASCII reads and packs them to 2 bit on the device, allocates results.
  * searchIndexGPU: launches the search on every shard and waits (kernels only,
  *   like the reference's timed region); kernel family = $FMGPU_MODE, else the
- *   fused-step kernel when the replica has a fused table, else Coop; or whatever
- *   fmgpu_set_variant selected.  Returns void like the reference;
+ *   sparse-step (or fused-step) kernel when the replica has that table, else Coop;
+ *   or whatever fmgpu_set_variant selected.  Returns void like the reference;
  *   a CUDA failure prints file:line and exits (reference HandleError, :88-93).
  * transferGPUtoCPU: per-GPU D2H of its (L,R) shard straight into h_results.
  */
@@ -210,12 +211,12 @@ typedef struct {
   uint32_t start_bases;   /* bases covered by the fused kernel's start table (12), 0 = none    */
   /* sparse-step table (fmgpu_index_sparsify), 0 = none */
   uint32_t sparse_bases;       /* bases per sparse step                                         */
-  uint32_t sparse_lambda;      /* target occurrences per 128-byte block                         */
+  uint32_t sparse_lambda;      /* target occurrences per block                                  */
   uint64_t sparse_bytes;       /* blocks + directory (+ start table)                            */
-  uint64_t sparse_blocks;      /* number of 128-byte blocks                                     */
-  uint64_t sparse_overflow;    /* blocks holding more than 31 occurrences (served by SB96 steps) */
+  uint64_t sparse_blocks;      /* number of blocks                                              */
+  uint64_t sparse_overflow;    /* blocks holding more occurrences than slots (served by SB96 steps) */
   uint32_t sparse_start_bases; /* bases covered by the sparse kernel's start table, 0 = none    */
-  uint32_t reserved2;
+  uint32_t sparse_lanes;       /* lanes per block: 2 = 64-byte blocks (15 slots), 4 = 128-byte blocks (31 slots) */
 } fmgpu_index_meta_t;
 
 /* devices ---------------------------------------------------------------- */
@@ -251,12 +252,13 @@ int32_t fmgpu_index_alloc_like(int32_t device, const fmgpu_index_meta_t *meta, f
 int32_t fmgpu_index_fuse(fmgpu_index_t *idx, uint32_t fused_bases, uint32_t lanes, uint64_t budget_bytes);
 int32_t fmgpu_index_unfuse(fmgpu_index_t *idx);
 /* Sparse-step table, built on the GPU from this replica's own block table: one sparse step = sparse_bases/k
- * reference LF steps (exactly); per wide symbol the occurrence rows are cut into 128-byte blocks of ~lambda rows,
- * one block fetch per rank (csrc/fm_sparse.cuh).  sparse_bases 0 = the widest multiple of k up to 10 that leaves
- * at least 64 rows per symbol; lambda 0 = 16; the table takes ~128/lambda bytes per text base whatever the width.
- * Blocks with more than 31 occurrences (repeats) are served by ordinary steps on the block table.
+ * reference LF steps (exactly); per wide symbol the occurrence rows are cut into blocks of ~lambda rows, one block
+ * fetch per rank (csrc/fm_sparse.cuh).  sparse_bases 0 = the widest multiple of k up to 10 that leaves at least
+ * 64 rows per symbol; lanes 0 = 2 (64-byte blocks, 15 slots; 4 = 128-byte blocks, 31 slots); lambda 0 = 5 / 12;
+ * the table takes ~32*lanes/lambda bytes per text base whatever the width.  Blocks with more occurrences than
+ * slots (repeats) are served by ordinary steps on the block table.
  * FM_E_NOT_IMPLEMENTED when memory does not suffice or the index carries the AltCounters padding quirk. */
-int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_bases, uint32_t lambda);
+int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_bases, uint32_t lambda, uint32_t lanes);
 int32_t fmgpu_index_unsparsify(fmgpu_index_t *idx);
 int32_t fmgpu_index_get_meta(const fmgpu_index_t *idx, fmgpu_index_meta_t *meta);
 void   *fmgpu_index_blocks(const fmgpu_index_t *idx);     /* device pointer */

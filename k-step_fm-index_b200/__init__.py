@@ -72,7 +72,7 @@ class fmgpu_index_meta_t(C.Structure):
                 ("start_bases", C.c_uint32),
                 ("sparse_bases", C.c_uint32), ("sparse_lambda", C.c_uint32), ("sparse_bytes", C.c_uint64),
                 ("sparse_blocks", C.c_uint64), ("sparse_overflow", C.c_uint64), ("sparse_start_bases", C.c_uint32),
-                ("reserved2", C.c_uint32)]
+                ("sparse_lanes", C.c_uint32)]
 
 
 _VP, _VPP = C.c_void_p, C.POINTER(C.c_void_p)
@@ -111,7 +111,7 @@ PROTOTYPES = {
     "fmgpu_index_alloc_like": (C.c_int32, [C.c_int32, C.POINTER(fmgpu_index_meta_t), _VPP]),
     "fmgpu_index_fuse": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, C.c_uint64]),
     "fmgpu_index_unfuse": (C.c_int32, [_VP]),
-    "fmgpu_index_sparsify": (C.c_int32, [_VP, C.c_uint32, C.c_uint32]),
+    "fmgpu_index_sparsify": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, C.c_uint32]),
     "fmgpu_index_unsparsify": (C.c_int32, [_VP]),
     "fmgpu_index_get_meta": (C.c_int32, [_VP, C.POINTER(fmgpu_index_meta_t)]),
     "fmgpu_index_blocks": (_VP, [_VP]),
@@ -307,9 +307,9 @@ class DeviceIndex:
     def unfuse(self):
         check(lib().fmgpu_index_unfuse(self.handle), "fmgpu_index_unfuse")
 
-    def sparsify(self, sparse_bases=0, lam=0):
-        """Builds the sparse-step table (up to 12 bases per 128-byte block fetch) for MODE_SPARSE searches."""
-        check(lib().fmgpu_index_sparsify(self.handle, sparse_bases, lam), "fmgpu_index_sparsify")
+    def sparsify(self, sparse_bases=0, lam=0, lanes=0):
+        """Builds the sparse-step table (up to 12 bases per 64/128-byte block fetch) for MODE_SPARSE searches."""
+        check(lib().fmgpu_index_sparsify(self.handle, sparse_bases, lam, lanes), "fmgpu_index_sparsify")
         return self
 
     def unsparsify(self):

@@ -225,7 +225,7 @@ extern "C" int32_t fmgpu_index_alloc_like(int32_t device, const fmgpu_index_meta
   /* derived tables are per replica: a fresh replica has none until fmgpu_index_fuse / fmgpu_index_sparsify run on it */
   idx->meta.fused_bases = 0; idx->meta.fused_lanes = 0; idx->meta.fused_bytes = 0; idx->meta.start_bases = 0;
   idx->meta.sparse_bases = 0; idx->meta.sparse_lambda = 0; idx->meta.sparse_bytes = 0; idx->meta.sparse_blocks = 0;
-  idx->meta.sparse_overflow = 0; idx->meta.sparse_start_bases = 0;
+  idx->meta.sparse_overflow = 0; idx->meta.sparse_start_bases = 0; idx->meta.sparse_lanes = 0;
   cudaError_t e = cudaMalloc((void **) &idx->blocks, meta->nbytes);
   if (e != cudaSuccess) { free(idx); return fm_fail(e, "cudaMalloc(SB96 replica)", __FILE__, __LINE__); }
   *out = idx;
@@ -452,11 +452,11 @@ extern "C" int32_t fmgpu_index_unsparsify(fmgpu_index_t *idx)
     idx->sblocks = NULL; idx->sdir = NULL; idx->sstart = NULL;
   }
   idx->meta.sparse_bases = 0; idx->meta.sparse_lambda = 0; idx->meta.sparse_bytes = 0; idx->meta.sparse_blocks = 0;
-  idx->meta.sparse_overflow = 0; idx->meta.sparse_start_bases = 0;
+  idx->meta.sparse_overflow = 0; idx->meta.sparse_start_bases = 0; idx->meta.sparse_lanes = 0;
   return FM_SUCCESS;
 }
 
-extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_bases, uint32_t lambda)
+extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_bases, uint32_t lambda, uint32_t lanes)
 {
   if (!idx) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null index");
   if (idx->sblocks) return FM_SUCCESS;
@@ -464,8 +464,11 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
   if (idx->meta.bwtsize >= FM_SP_OVF) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "text too long for the sparse-step table");
   CU_TRY(cudaSetDevice(idx->device));
   const uint32_t k = idx->meta.steps, n = idx->meta.bwtsize;
-  if (lambda == 0) lambda = 16;
-  if (lambda > FM_SP_SLOTS) return fm_fail_msg(FM_E_BAD_ARGUMENT, "lambda must be 1..31");
+  if (lanes == 0) lanes = 2;
+  if (lanes != 2 && lanes != 4) return fm_fail_msg(FM_E_BAD_ARGUMENT, "sparse block lanes must be 2 (64-byte blocks) or 4 (128-byte blocks)");
+  const uint32_t slots = 8 * lanes - 1, bbytes = 32 * lanes;
+  if (lambda == 0) lambda = lanes == 4 ? 12 : 5;
+  if (lambda > slots) return fm_fail_msg(FM_E_BAD_ARGUMENT, "lambda must not exceed the slots of a block (15 or 31)");
   uint32_t ks = sparse_bases;
   if (ks == 0) {                                               /* widest multiple of k up to 10 with >= 64 rows per symbol */
     for (uint32_t cand = 10; cand >= 2 * k; cand--)
@@ -478,7 +481,7 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = ~(size_t) 0; }
   const uint64_t est_blocks = (uint64_t) n / lambda + nsym;
-  const uint64_t need = 16ull * n + nrows + est_blocks * 128ull + 32ull * nsym + (1ull << 30);
+  const uint64_t need = 16ull * n + nrows + est_blocks * bbytes + 32ull * nsym + (1ull << 30);
   if (need > free_b) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "not enough free device memory to build the sparse-step table");
 
   uint8_t *sym = NULL; uint32_t *keys = NULL, *rows = NULL, *keys2 = NULL, *rows2 = NULL, *symstart = NULL, *nb = NULL, *first = NULL, *rank0 = NULL;
@@ -528,13 +531,14 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
   /* the sort's input buffers are dead now: release them before the table is allocated */
   cudaFree(keys); keys = NULL; cudaFree(rows); rows = NULL; cudaFree(sym); sym = NULL;
   if (e == cudaSuccess && total_blocks >= (1ull << 32)) e = cudaErrorInvalidValue;
-  if (e == cudaSuccess) e = cudaMalloc((void **) &sblocks, total_blocks * 128ull);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &sblocks, total_blocks * bbytes);
   if (e == cudaSuccess) {
     fm_sparse_dir_kernel<<<(nsym + 255) / 256, 256>>>(idx->blocks, idx->meta.nblocks, kbits, hops, nsym, n, nb, first, dir, rank0);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) {
-    fm_sparse_fill_kernel<<<nsym, 128>>>(rows2, symstart, dir, nb, rank0, sblocks, d_novf);
+    if (lanes == 4) fm_sparse_fill_kernel<4><<<nsym, 128>>>(rows2, symstart, dir, nb, rank0, sblocks, d_novf);
+    else            fm_sparse_fill_kernel<2><<<nsym, 128>>>(rows2, symstart, dir, nb, rank0, sblocks, d_novf);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(&novf, d_novf, 8, cudaMemcpyDeviceToHost);
@@ -544,7 +548,7 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
   if (e != cudaSuccess) { cudaFree(sblocks); cudaFree(dir); return fm_fail(e, "fmgpu_index_sparsify", __FILE__, __LINE__); }
   idx->sblocks = sblocks; idx->sdir = dir;
   idx->meta.sparse_bases = ks; idx->meta.sparse_lambda = lambda; idx->meta.sparse_blocks = total_blocks;
-  idx->meta.sparse_overflow = novf; idx->meta.sparse_bytes = total_blocks * 128ull + 8ull * nsym;
+  idx->meta.sparse_overflow = novf; idx->meta.sparse_bytes = total_blocks * bbytes + 8ull * nsym; idx->meta.sparse_lanes = lanes;
 
   /* start table: the sparse kernel itself searches every SB-mer once (a packed SB-mer IS its key); SB = the
    * largest whole number of sparse steps within 12 bases */
@@ -570,13 +574,14 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
 }
 
 typedef void (*fm_sparse_fn)(const FmSparseParams);
-template <int K>
+template <int K, int LANES>
 static fm_sparse_fn fm_pick_sparse(int qpt)
 {
-  if (qpt == 0) return fm_search_sparse_kernel<K, 1, 256, 6, true>;               /* instrumented */
-  if (qpt == 1) return fm_search_sparse_kernel<K, 1, 256, 6, false>;
-  if (qpt == 2) return fm_search_sparse_kernel<K, 2, 256, 4, false>;
-  if (qpt == 4) return fm_search_sparse_kernel<K, 4, 256, 2, false>;
+  if (qpt == 0) return fm_search_sparse_kernel<K, LANES, 1, 256, 6, true>;        /* instrumented */
+  if (qpt == 1) return fm_search_sparse_kernel<K, LANES, 1, 256, 6, false>;
+  if (qpt == 2) return fm_search_sparse_kernel<K, LANES, 2, 256, 4, false>;
+  if (qpt == 3) return fm_search_sparse_kernel<K, LANES, 3, 256, 4, false>;
+  if (qpt == 4) return fm_search_sparse_kernel<K, LANES, 4, 256, 3, false>;
   return NULL;
 }
 
@@ -584,8 +589,8 @@ static int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_pack
                                 uint32_t *d_results, fmgpu_variant_t v, cudaStream_t stream, unsigned long long *d_counters)
 {
   if (!idx->sblocks) return fm_fail_msg(FM_E_BAD_ARGUMENT, "FMGPU_MODE_SPARSE needs fmgpu_index_sparsify() on this replica first");
-  const uint32_t k = idx->meta.steps, ks = idx->meta.sparse_bases, hops = ks / k;
-  if (v.queries_per_thread != 1 && v.queries_per_thread != 2 && v.queries_per_thread != 4) v.queries_per_thread = 2;
+  const uint32_t k = idx->meta.steps, ks = idx->meta.sparse_bases, hops = ks / k, lanes = idx->meta.sparse_lanes;
+  if (v.queries_per_thread < 1 || v.queries_per_thread > 4) v.queries_per_thread = 4;
   FmSparseParams p;
   p.sblocks = idx->sblocks; p.dir = idx->sdir; p.blocks = idx->blocks; p.packed = d_packed; p.results = d_results;
   p.nblocks = idx->meta.nblocks; p.nq = (uint32_t) nq;
@@ -599,13 +604,15 @@ static int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_pack
   if (d_counters) v.queries_per_thread = 1;
   uint32_t qper; size_t smem;
   for (;;) {
-    qper = (256 / FM_SP_LANES) * v.queries_per_thread;
+    qper = (256 / lanes) * v.queries_per_thread;
     smem = 16 + ((size_t) qper * p.wpq + 4) * 4;
     if (smem <= 200 * 1024) break;
-    if (v.queries_per_thread > 1) v.queries_per_thread /= 2;
+    if (v.queries_per_thread > 1) v.queries_per_thread -= 1;
     else return fm_fail_msg(FM_E_QUERY_SHAPE, "reads too long to stage in shared memory");
   }
-  fm_sparse_fn fn = k == 2 ? fm_pick_sparse<2>(d_counters ? 0 : v.queries_per_thread) : fm_pick_sparse<1>(d_counters ? 0 : v.queries_per_thread);
+  const int qsel = d_counters ? 0 : v.queries_per_thread;
+  fm_sparse_fn fn = k == 2 ? (lanes == 4 ? fm_pick_sparse<2, 4>(qsel) : fm_pick_sparse<2, 2>(qsel))
+                           : (lanes == 4 ? fm_pick_sparse<1, 4>(qsel) : fm_pick_sparse<1, 2>(qsel));
   if (!fn) return fm_fail_msg(FM_E_BAD_ARGUMENT, "no sparse kernel for this variant");
   if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   const uint32_t grid = (uint32_t)((nq + qper - 1) / qper);

@@ -295,7 +295,7 @@ int32_t fmgpu_set_variant(const fmgpu_variant_t *v)
   return FM_SUCCESS;
 }
 
-/* $FMGPU_MODE = task | coop | fused | auto (default): kernel family used by searchIndexGPU */
+/* $FMGPU_MODE = task | coop | fused | sparse | auto (default): kernel family used by searchIndexGPU */
 #define FM_MODE_AUTO (-1)
 static int fm_mode_from_env(void)
 {
@@ -304,6 +304,7 @@ static int fm_mode_from_env(void)
   if (!strcmp(env, "task")) return FMGPU_MODE_TASK;
   if (!strcmp(env, "coop")) return FMGPU_MODE_COOP;
   if (!strcmp(env, "fused")) return FMGPU_MODE_FUSED;
+  if (!strcmp(env, "sparse")) return FMGPU_MODE_SPARSE;
   return FM_MODE_AUTO;
 }
 
@@ -360,18 +361,19 @@ int32_t transferCPUtoGPU(void *index, void *queries, void *results)
                              fmi->h_dollarPositionBWT, fmi->h_dollarBaseBWT, (const uint32_t *) fmi->h_index, &rs->replica[0]);
     for (g = 1; g < rs->ndev && !err; g++) err = fmgpu_index_replicate(rs->replica[0], rs->dev[g], &rs->replica[g]);
     if (err) { for (g = 0; g < rs->ndev; g++) fmgpu_index_free(&rs->replica[g]); free(rs); return err; }
-    /* fused-step table on every replica unless $FMGPU_MODE asks for the plain kernels; an index that cannot be
-     * fused (AltCounters padding quirk, no memory) simply keeps the plain 2-step kernels -- still on the GPU */
+    /* derived table on every replica unless $FMGPU_MODE asks for the plain kernels: the sparse-step table (auto and
+     * "sparse"), or the fused-step table ("fused", and auto when the sparse one cannot be built); an index that admits
+     * neither (AltCounters padding quirk, no memory) simply keeps the plain 2-step kernels -- still on the GPU */
     {
-      /* auto: an index whose plain table stays L2-resident (config 1/2: 10.7 MB) is faster on the plain kernels
-       * (4.6 vs 3.1 G reads/s measured: the fused kernel's extra popcounts are no longer hidden behind HBM) */
+      /* auto: an index whose plain table stays L2-resident (config 1/2: 10.7 MB) is not worth a table build for one
+       * batch: the plain kernels already run at 3-4.6 G reads/s there */
       fmgpu_index_meta_t meta0;
       const int mode = fm_mode_from_env();
-      int want_fused = (mode == FMGPU_MODE_FUSED);
-      if (mode == FM_MODE_AUTO && fmgpu_index_get_meta(rs->replica[0], &meta0) == FM_SUCCESS) want_fused = meta0.nbytes > (96ull << 20);
-      if (want_fused)
-      for (g = 0; g < rs->ndev; g++) {
-        err = fmgpu_index_fuse(rs->replica[g], 0, 0, 0);
+      int want_sparse = (mode == FMGPU_MODE_SPARSE), want_fused = (mode == FMGPU_MODE_FUSED);
+      if (mode == FM_MODE_AUTO && fmgpu_index_get_meta(rs->replica[0], &meta0) == FM_SUCCESS) want_sparse = meta0.nbytes > (96ull << 20);
+      for (g = 0; g < rs->ndev && (want_sparse || want_fused); g++) {
+        err = want_sparse ? fmgpu_index_sparsify(rs->replica[g], 0, 0, 0) : FM_E_NOT_IMPLEMENTED;
+        if (err == FM_E_NOT_IMPLEMENTED && (want_fused || mode == FM_MODE_AUTO)) err = fmgpu_index_fuse(rs->replica[g], 0, 0, 0);
         if (err && err != FM_E_NOT_IMPLEMENTED) { for (g = 0; g < rs->ndev; g++) fmgpu_index_free(&rs->replica[g]); free(rs); return err; }
       }
     }
@@ -414,14 +416,16 @@ void searchIndexGPU(void *index, void *queries, void *resIntervals)
   }
   for (g = 0; g < ss->ndev && !err; g++) {
     fmgpu_variant_t v = g_variant;
-    if (!g_variant_set) {                      /* $FMGPU_MODE, else fused when the replica has a fused table, else Coop */
+    if (!g_variant_set) {                      /* $FMGPU_MODE, else the best table the replica has, else Coop */
       fmgpu_index_meta_t meta;
       const int mode = fm_mode_from_env();
       memset(&v, 0, sizeof v);
       err = fmgpu_index_get_meta(rs->replica[g], &meta);
       if (err) break;
-      v.mode = (mode == FM_MODE_AUTO) ? (meta.fused_bases ? FMGPU_MODE_FUSED : FMGPU_MODE_COOP) : mode;
+      v.mode = (mode == FM_MODE_AUTO) ? (meta.sparse_bases ? FMGPU_MODE_SPARSE : meta.fused_bases ? FMGPU_MODE_FUSED : FMGPU_MODE_COOP) : mode;
+      if (v.mode == FMGPU_MODE_SPARSE && !meta.sparse_bases) v.mode = meta.fused_bases ? FMGPU_MODE_FUSED : FMGPU_MODE_COOP;
       if (v.mode == FMGPU_MODE_FUSED && !meta.fused_bases) v.mode = FMGPU_MODE_COOP;
+      if (v.mode == FMGPU_MODE_SPARSE) v.queries_per_thread = 4;
     }
     err = fmgpu_batch_search(rs->replica[g], ss->shard[g], &v);
   }

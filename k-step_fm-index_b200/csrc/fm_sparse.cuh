@@ -14,13 +14,14 @@
  *   buckets                 symbol sigma owns nb(sigma) = max(1, ceil(count(sigma) / lambda)) blocks;
  *                           row X belongs to bucket umulhi(X, scale(sigma)) -- a monotone map of [0, bwtsize] onto
  *                           [0, nb) -- so a bucket holds ~lambda occurrences whatever the symbol's frequency
- *   block (128 bytes)       word 0      = rank_F(sigma, first row of the bucket)
- *                           words 1..31 = the bucket's occurrence rows, ascending, padded with 0xFFFFFFFF
- *                           a bucket with more than 31 occurrences stores 0xFFFFFFFE in word 31 instead
+ *   block (32*LANES bytes)  word 0      = rank_F(sigma, first row of the bucket)
+ *                           words 1..   = the bucket's occurrence rows, ascending, padded with 0xFFFFFFFF
+ *                           (31 slots in a 128-byte block, LANES = 4; 15 in a 64-byte block, LANES = 2)
+ *                           a bucket with more occurrences than slots stores 0xFFFFFFFE in the last word instead
  *   directory               dir[sigma] = { first block, scale }     (8 bytes x 4^KS: L2-resident for KS <= 10)
  *
  *   one rank     = dir[sigma] (L2 hit; sigma is known in advance, the lookup is issued one step ahead)
- *                  + ONE 128-byte block fetch by 4 lanes x 256 bits;  rank = word 0 + #{ entries < X }
+ *                  + ONE block fetch by LANES lanes x 256 bits;  rank = word 0 + #{ entries < X }
  *   L and R      almost always share the block (a bucket spans bwtsize / nb rows), so a step is one fetch
  *   overflow     a block marked 0xFFFFFFFE sends that read through `hops` ordinary steps on the SB96 table for
  *                this symbol -- exact, and rare by construction (Poisson tail for lambda = 16: 2e-4 per fetch on a
@@ -35,14 +36,12 @@
 
 #include "fm_fused.cuh"
 
-#define FM_SP_SLOTS 31u
 #define FM_SP_PAD   0xFFFFFFFFu
 #define FM_SP_OVF   0xFFFFFFFEu
-#define FM_SP_LANES 4
 #define FM_SP_NONE  0xFFFFFFFFu            /* compose output of a row without a wide symbol (sorted last) */
 
 struct FmSparseParams {
-  const uint4    *sblocks;    /* sparse table, 8 uint4 per block                                   */
+  const uint4    *sblocks;    /* sparse table, 2*LANES uint4 per block                             */
   const uint2    *dir;        /* per wide symbol: { first block, scale }                           */
   const uint4    *blocks;     /* SB96: leading steps, overflow fallback, odd tail                  */
   const uint32_t *packed;
@@ -76,13 +75,20 @@ __device__ __forceinline__ uint32_t fm_sparse_partial(const uint32_t (&w)[8], ui
   return c;
 }
 
-template <int K, int QPT, int THREADS, int MINB, bool COUNT>
+template <int LANES> __device__ __forceinline__ void fm_sparse_load(const uint4 *p, uint32_t (&w)[8])
+{
+  if (LANES == 2) fm_ldg32(p, w);          /* 64-byte block: 64-byte L2 fill */
+  else            fm_ldg32_line(p, w);
+}
+
+template <int K, int LANES, int QPT, int THREADS, int MINB, bool COUNT>
 __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_kernel(const FmSparseParams p)
 {
   extern __shared__ __align__(16) uint32_t fsm[];             /* [0..3]: mbarrier + pad; [4..): packed reads, natural stride */
   uint32_t *sq = fsm + 4;
   constexpr uint32_t BBITS = 2 * K, BMASK = (1u << BBITS) - 1u;
-  constexpr int LANES = FM_SP_LANES, GROUPS = THREADS / LANES;
+  constexpr int GROUPS = THREADS / LANES;
+  constexpr uint32_t BU4 = 2u * LANES;                        /* uint4 per block */
   const uint32_t smask = (p.sbits >= 32u) ? 0xFFFFFFFFu : ((1u << p.sbits) - 1u);
   const uint32_t q0 = blockIdx.x * (GROUPS * QPT);
   const uint32_t nqb = min((uint32_t)(GROUPS * QPT), p.nq - q0);
@@ -167,11 +173,11 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_kernel(const F
     #pragma unroll
     for (int i = 0; i < QPT; i++) {
       const uint32_t bL = __umulhi(L[i], d[i].y), bR = __umulhi(R[i], d[i].y);
-      const uint4 *base = p.sblocks + (size_t) d[i].x * 8u + 2u * lg;
+      const uint4 *base = p.sblocks + (size_t) d[i].x * BU4 + 2u * lg;
       same[i] = (bL == bR);
-      aR[i] = base + (size_t) bR * 8u;
+      aR[i] = base + (size_t) bR * BU4;
       if (COUNT && live[i] && lg == 0) n_sp += same[i] ? 1 : 2;
-      fm_ldg32_line(base + (size_t) bL * 8u, w[i]);
+      fm_sparse_load<LANES>(base + (size_t) bL * BU4, w[i]);
     }
     /* directory entries of the NEXT step (independent of L,R): in flight together with the block fetches */
     uint32_t sig_now[QPT];
@@ -197,7 +203,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_kernel(const F
       for (int i = 0; i < QPT; i++) {
         if (!same[i]) {
           uint32_t v[8];
-          fm_ldg32_line(aR[i], v);
+          fm_sparse_load<LANES>(aR[i], v);
           cR[i] = fm_sparse_partial(v, R[i], lg) + (lg == 0 ? v[0] : 0u);
           ovf[i] |= (lg == LANES - 1) && (v[7] == FM_SP_OVF);
         }
@@ -322,6 +328,7 @@ __global__ void fm_sparse_dir_kernel(const uint4 *__restrict__ blocks, uint32_t 
 }
 
 /* one CTA per symbol, one thread per block of the symbol */
+template <int LANES>
 __global__ void __launch_bounds__(128) fm_sparse_fill_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ symstart,
                                                              const uint2 *__restrict__ dir, const uint32_t *__restrict__ nb,
                                                              const uint32_t *__restrict__ rank0, uint4 *__restrict__ sblocks,
@@ -336,14 +343,15 @@ __global__ void __launch_bounds__(128) fm_sparse_fill_kernel(const uint32_t *__r
     hi = s1;                                                   /* first occurrence whose bucket is > j */
     while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__umulhi(rows[mid], scale) <= j) lo = mid + 1; else hi = mid; }
     const uint32_t cnt = lo - t0;
-    uint32_t w[32];
+    constexpr uint32_t WORDS = 8u * LANES, SLOTS = WORDS - 1u;
+    uint32_t w[WORDS];
     w[0] = r0 + (t0 - s0);
     #pragma unroll
-    for (uint32_t c = 1; c < 32; c++) w[c] = (c - 1 < cnt && cnt <= FM_SP_SLOTS) ? rows[t0 + c - 1] : FM_SP_PAD;
-    if (cnt > FM_SP_SLOTS) { w[31] = FM_SP_OVF; atomicAdd(novf, 1ull); }
-    uint4 *dst = sblocks + (size_t)(first + j) * 8u;
+    for (uint32_t c = 1; c < WORDS; c++) w[c] = (c - 1 < cnt && cnt <= SLOTS) ? rows[t0 + c - 1] : FM_SP_PAD;
+    if (cnt > SLOTS) { w[WORDS - 1] = FM_SP_OVF; atomicAdd(novf, 1ull); }
+    uint4 *dst = sblocks + (size_t)(first + j) * (2u * LANES);
     #pragma unroll
-    for (uint32_t c = 0; c < 8; c++) dst[c] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+    for (uint32_t c = 0; c < 2u * LANES; c++) dst[c] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
   }
 }
 

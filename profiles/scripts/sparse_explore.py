@@ -14,7 +14,7 @@ def emit(**kw):
     print(json.dumps(kw), flush=True); OUT.write(json.dumps(kw) + "\n"); OUT.flush()
 gold = json.load(open(os.path.join(ROOT, "tests", "golden", "config3_2g.json")))
 n, nq, k = int(float(os.environ.get("FM_N", "2e9"))), int(float(os.environ.get("FM_NQ", "1e7"))), int(os.environ.get("FM_K", "2"))
-CONFIGS = [tuple(int(x) for x in c.split(":")) for c in os.environ.get("FM_SPARSE", "10:16,10:12,8:16").split(",")]
+CONFIGS = [tuple(int(x) for x in c.split(":")) for c in os.environ.get("FM_SPARSE", "10:6:2,10:5:2,10:7:2,10:12:4").split(",")]
 L = pkg.lib()
 b = pkg.IndexBuild.from_synth(n, 1, k, 64); idx = b.to_index(); b.free()
 stream = torch.cuda.current_stream().cuda_stream
@@ -49,23 +49,25 @@ for key, dp in packed.items():
 md5 = helpers.results_text_md5(want[(100, True)].cpu().numpy().view(np.uint32)[:2_000_000])
 emit(what="plain md5 equals reference", ok=(md5 == gold["md5"]["res_cpu_std_text"]) if (n == 2_000_000_000 and k == 2) else None)
 
-for ks, lam in CONFIGS:
+for ci, (ks, lam, lanes) in enumerate(CONFIGS):
     t0 = time.time()
     try:
-        idx.sparsify(ks, lam)
+        idx.sparsify(ks, lam, lanes)
     except Exception as ex:
-        emit(what="sparsify failed", bases=ks, lam=lam, err=str(ex)); continue
+        emit(what="sparsify failed", bases=ks, lam=lam, lanes=lanes, err=str(ex)); continue
     torch.cuda.synchronize(); t1 = time.time()
     m = idx.meta
-    emit(what="sparsify", bases=ks, lam=lam, seconds=t1 - t0, sparse_gb=m.sparse_bytes / 1e9, blocks=m.sparse_blocks, overflow_blocks=m.sparse_overflow,
+    emit(what="sparsify", bases=ks, lam=lam, lanes=lanes, seconds=t1 - t0, sparse_gb=m.sparse_bytes / 1e9, blocks=m.sparse_blocks, overflow_blocks=m.sparse_overflow,
          start_bases=m.sparse_start_bases)
     for key, dp in packed.items():
-        for qpt in ((1, 2, 4) if key == (100, True) else (2,)):
+        if ci and key != (100, True) and os.environ.get("FM_SPARSE_ALLSETS", "0") == "0":
+            continue
+        for qpt in ((1, 2, 3, 4) if key == (100, True) else (4,)):
             ms = run(dp, key[0], pkg.variant(pkg.MODE_SPARSE, qpt), d_res)
             same = bool(torch.equal(d_res, want[key]))
-            emit(what="sparse search", bases=ks, lam=lam, length=key[0], exact=key[1], qpt=qpt, ms=ms, mq_per_s=nq / ms / 1e3, equals_plain=same)
+            emit(what="sparse search", bases=ks, lam=lam, lanes=lanes, length=key[0], exact=key[1], qpt=qpt, ms=ms, mq_per_s=nq / ms / 1e3, equals_plain=same)
         a, bb, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         pkg.check(L.fmgpu_count_fetches_sparse_device(idx.handle, dp.data_ptr(), nq, key[0], d_res.data_ptr(), stream, C.byref(a), C.byref(bb), C.byref(c)), "count")
-        emit(what="sparse fetches", bases=ks, lam=lam, length=key[0], exact=key[1], sparse_blocks_per_read=a.value / nq, sb96_blocks_per_read=bb.value / nq,
+        emit(what="sparse fetches", bases=ks, lam=lam, lanes=lanes, length=key[0], exact=key[1], sparse_blocks_per_read=a.value / nq, sb96_blocks_per_read=bb.value / nq,
              overflows_per_read=c.value / nq, equals_plain=bool(torch.equal(d_res, want[key])))
     idx.unsparsify()

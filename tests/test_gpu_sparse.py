@@ -1,0 +1,260 @@
+"""GPU parity tests of the sparse-step layout (csrc/fm_sparse.cuh): up to 12 bases per block fetch, blocks of
+occurrence rows + a per-symbol directory, overfull blocks served by ordinary steps on the SB96 table.  Everything
+goes through the C ABI (ctypes) and is compared bit for bit with committed reference outputs, the oracle, the
+reference searcher itself, or the plain kernels on the same index at sizes the CPU cannot reach.   pytest -m gpu"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(os.path.join(helpers.ROOT, "tests", "golden", f) for f in os.listdir(os.path.join(helpers.ROOT, "tests", "golden")) if f.endswith(".npz"))
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+@pytest.fixture(scope="module")
+def pkg(built):
+    p = helpers.pkg()
+    assert p.lib().fmgpu_device_count() >= 1, "no sm_100 GPU: the product has no CPU fallback"
+    return p
+
+
+def widths(k):
+    return [2, 3, 5, 6, 10, 12] if k == 1 else [4, 6, 10, 12]
+
+
+@pytest.mark.parametrize("path", [p for p in GOLDEN if "quirk" not in p], ids=lambda p: os.path.basename(p))
+def test_sparse_steps_golden_all_widths(pkg, path):
+    """Committed outputs of the unmodified reference searchers; every width, both block sizes, every qpt,
+    lambda from 1 (almost no overflow) to the slot count (many overfull blocks -> SB96 fallback)."""
+    g = np.load(path)
+    reads, length, k = g["reads"], int(g["length"]), int(g["k"])
+    nq = reads.size // length
+    b = pkg.DeviceBatch(0, nq, length, k)
+    b.upload_ascii(reads)
+    for tag, key in ((100, "expected_std"), (101, "expected_std"), (200, "expected_ac"), (201, "expected_ac")):
+        for ks in widths(k):
+            for lanes, lams in ((2, (1, 5, 15)), (4, (12, 31))):
+                for lam in lams:
+                    idx = pkg.DeviceIndex.from_image(g[f"image_{tag}"]).sparsify(ks, lam, lanes)
+                    m = idx.meta
+                    assert (m.sparse_bases, m.sparse_lambda, m.sparse_lanes) == (ks, lam, lanes)
+                    assert m.sparse_bytes == m.sparse_blocks * 32 * lanes + 8 * 4 ** ks + (8 * 4 ** m.sparse_start_bases if m.sparse_start_bases else 0)
+                    for qpt in (1, 2, 3, 4):
+                        b.search(idx, pkg.variant(pkg.MODE_SPARSE, qpt))
+                        assert np.array_equal(b.download(), g[key]), f"tag {tag} ks {ks} lanes {lanes} lambda {lam} qpt {qpt}"
+                    idx.free()
+    b.free()
+
+
+@pytest.mark.parametrize("k,length", [(1, 1), (1, 3), (1, 5), (1, 10), (1, 17), (1, 33), (1, 100), (2, 2), (2, 6), (2, 10), (2, 20), (2, 30), (2, 34),
+                                      (2, 100), (2, 126), (2, 128), (2, 250), (1, 251), (2, 25), (2, 101)])
+def test_sparse_steps_read_lengths(pkg, k, length):
+    """Lengths that are not a multiple of the sparse width run their leading steps on the SB96 table, odd lengths on a
+    2-step index end with the derived 1-step rank; bit fields of the packed read straddle 32-bit words."""
+    g = np.load(os.path.join(helpers.ROOT, "tests", "golden", f"small_k{k}_d64.npz"))
+    text = helpers.synth_text(int(g["n"]), seed=7 + k)
+    reads = np.concatenate([helpers.synth_reads(text, 21, 700, length), ACGT[np.random.default_rng(length).integers(0, 4, 68 * length)]])
+    idx = pkg.DeviceIndex.from_image(g["image_101"])
+    b = pkg.DeviceBatch(0, reads.size // length, length, k)
+    b.upload_ascii(reads)
+    if length % k == 0:
+        o = helpers.Oracle()
+        h = o.wrap(g["image_101"])
+        want = o.search(h, reads, length)
+        o.free(h)
+    else:                                                        # defined by the plain kernels (tested against the 1-step reference elsewhere)
+        b.search(idx, pkg.variant(pkg.MODE_COOP))
+        want = b.download()
+    for ks in ([3, 10] if k == 1 else [4, 10]):
+        for lanes in (2, 4):
+            idx.sparsify(ks, 0, lanes)
+            b.search(idx, pkg.variant(pkg.MODE_SPARSE))
+            assert np.array_equal(b.download(), want), f"k={k} len={length} ks={ks} lanes={lanes}"
+            idx.unsparsify()
+    b.free(); idx.free()
+
+
+def test_sparse_unavailable_and_errors(pkg):
+    g = np.load(os.path.join(helpers.ROOT, "tests", "golden", "quirk_k2_n124.npz"))
+    idx = pkg.DeviceIndex.from_image(g["image_200"])           # AltCounters padding quirk: not representable
+    with pytest.raises(pkg.FMError) as ei:
+        idx.sparsify()
+    assert ei.value.code == 19
+    b = pkg.DeviceBatch(0, 4, 8, 2)
+    b.upload_ascii(g["reads"][:32])
+    with pytest.raises(pkg.FMError) as ei:
+        b.search(idx, pkg.variant(pkg.MODE_SPARSE))            # no table: loud failure, no silent fallback
+    assert ei.value.code == pkg.FM_E_BAD_ARGUMENT
+    b.free(); idx.free()
+    idx = pkg.DeviceIndex.from_image(g["image_100"])           # same text, standard file: fine
+    for bad in ((3, 0, 0), (2, 0, 0), (14, 0, 0), (4, 16, 2), (4, 32, 4), (4, 0, 3)):
+        with pytest.raises(pkg.FMError) as ei:
+            idx.sparsify(*bad)
+        assert ei.value.code == pkg.FM_E_BAD_ARGUMENT, bad
+    idx.sparsify(4, 0, 2)
+    assert idx.meta.sparse_bases == 4
+    b = pkg.DeviceBatch(0, g["reads"].size // 8, 8, 2)
+    b.upload_ascii(g["reads"])
+    b.search(idx, pkg.variant(pkg.MODE_SPARSE))
+    assert np.array_equal(b.download(), g["expected_std"])
+    idx.unsparsify()
+    assert idx.meta.sparse_bases == 0 and idx.meta.sparse_bytes == 0
+    b.free(); idx.free()
+
+
+@pytest.mark.skipif(not helpers.has_ref_tools(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", ["polyA", "ACGT_period4", "two_letter", "repeat_x40", "random_plus_repeat"])
+@pytest.mark.parametrize("k", [1, 2])
+def test_sparse_steps_repetitive_texts_overflow_fallback(pkg, tmp_path, name, k):
+    """Repeats put hundreds of occurrences of one wide symbol into consecutive BWT rows: those blocks are overfull and
+    the kernel must serve them through ordinary steps on the SB96 table.  Index files and expected (L,R) from the
+    unmodified reference tools."""
+    rng = np.random.default_rng(11)
+    n = 30011
+    unit = ACGT[rng.integers(0, 4, 700)]
+    text = {"polyA": np.full(n, ord("A"), dtype=np.uint8),
+            "ACGT_period4": np.tile(ACGT, n // 4 + 1)[:n],
+            "two_letter": np.frombuffer(b"AC", dtype=np.uint8)[rng.integers(0, 2, n)],
+            "repeat_x40": np.tile(unit, n // 700 + 1)[:n],
+            "random_plus_repeat": np.concatenate([ACGT[rng.integers(0, 4, n // 2)], np.tile(unit, n // 1400 + 1)])[:n]}[name].copy()
+    d = 64
+    if (n + 1) % d == 0:
+        text = text[:-1]
+    paths = helpers.build_reference_indexes(str(tmp_path), text, k, d)
+    length = 20
+    starts = rng.integers(0, text.size - length + 1, 2000)
+    reads = np.concatenate([text[s:s + length] for s in starts] + [ACGT[rng.integers(0, 4, 500 * length)]])
+    ref = helpers.RefSearcher(k, d, False)
+    want, _ = ref.search(ref.load(paths[100]), reads, length)
+    image = np.fromfile(paths[101], dtype=np.uint32)
+    idx = pkg.DeviceIndex.from_image(image)
+    b = pkg.DeviceBatch(0, reads.size // length, length, k)
+    b.upload_ascii(reads)
+    saw_overflow = False
+    for ks in ([5, 10] if k == 1 else [4, 10]):
+        for lanes in (2, 4):
+            idx.sparsify(ks, 0, lanes)
+            saw_overflow |= idx.meta.sparse_overflow > 0
+            for qpt in (1, 4):
+                b.search(idx, pkg.variant(pkg.MODE_SPARSE, qpt))
+                assert np.array_equal(b.download(), want), f"{name} k={k} ks={ks} lanes={lanes} qpt={qpt}"
+            idx.unsparsify()
+    # (polyA is one symbol spread evenly over all rows, and the two-letter text is random: no overfull blocks there)
+    assert saw_overflow or name in ("polyA", "two_letter"), "these texts are meant to overflow blocks"
+    b.free(); idx.free()
+
+
+@pytest.mark.parametrize("k", [1, 2])
+def test_sparse_start_table_and_fetch_counter(pkg, k):
+    """The sparse kernel's start table ((L,R) of every 10-mer, computed by the kernel itself) must not change any
+    result: exact, mutated and random reads of several lengths against the plain Coop kernel on the same index; the
+    instrumented kernel counts one block fetch per sparse step once L and R share a bucket."""
+    import torch
+    n = 20_000_003
+    os.environ["FMGPU_START_TABLE"] = "1"
+    try:
+        b = pkg.IndexBuild.from_synth(n, 3, k, 64)
+        idx = b.to_index().sparsify(10, 0, 0)
+        b.free()
+    finally:
+        del os.environ["FMGPU_START_TABLE"]
+    m = idx.meta
+    assert (m.sparse_bases, m.sparse_lanes, m.sparse_lambda, m.sparse_start_bases) == (10, 2, 5, 10)
+    L = pkg.lib()
+    rng = np.random.default_rng(5)
+    stream = torch.cuda.current_stream().cuda_stream
+    for length in (10, 20, 100, 12, 14, 16, 50, 101 if k == 2 else 99):
+        nq = 200_000
+        d_ascii = torch.empty(nq * length, dtype=torch.uint8, device="cuda")
+        pkg.check(L.fmgpu_synth_reads_device(0, n, 3, nq, length, 2, 0, d_ascii.data_ptr(), None), "reads")
+        torch.cuda.synchronize()
+        reads = d_ascii.cpu().numpy().copy()
+        mut = rng.integers(0, nq * length, nq // 3)
+        reads[mut] = ACGT[rng.integers(0, 4, mut.size)]
+        batch = pkg.DeviceBatch(0, nq, length, k)
+        batch.upload_ascii(reads)
+        batch.search(idx, pkg.variant(pkg.MODE_COOP))
+        want = batch.download()
+        for qpt in (1, 2, 3, 4):
+            batch.search(idx, pkg.variant(pkg.MODE_SPARSE, qpt))
+            assert np.array_equal(batch.download(), want), f"k={k} len={length} qpt={qpt}"
+        batch.free()
+        if length == 100:
+            d_ascii.copy_(torch.from_numpy(reads))
+            wpq = L.fmgpu_words_per_query(length)
+            d_packed = torch.empty(nq * wpq, dtype=torch.int32, device="cuda")
+            d_res = torch.zeros(2 * nq, dtype=torch.int32, device="cuda")
+            pkg.check(L.fmgpu_pack_queries_device(0, d_ascii.data_ptr(), nq, length, d_packed.data_ptr(), stream), "pack")
+            a, s, o = C.c_uint64(), C.c_uint64(), C.c_uint64()
+            pkg.check(L.fmgpu_count_fetches_sparse_device(idx.handle, d_packed.data_ptr(), nq, length, d_res.data_ptr(), stream,
+                                                          C.byref(a), C.byref(s), C.byref(o)), "count")
+            assert np.array_equal(d_res.cpu().numpy().view(np.uint32), want)
+            assert 9 * nq <= a.value <= 9.05 * nq                # 10-base start table + 9 sparse steps, L and R in one bucket
+            assert s.value <= 0.2 * nq and o.value <= 0.05 * nq  # overfull blocks are rare on a random text
+    idx.free()
+
+
+def test_sparse_config3_full_size_against_reference_checksums(pkg):
+    """BASELINE config 3 at FULL size (2 Gbp, k=2, d=64): (L,R) of the first 1 M reads from the sparse-step kernel,
+    default table (10 bases per step, 64-byte blocks, start table), must have the md5 recorded from the UNMODIFIED
+    reference searcher (tests/golden/config3_2g.json); tags 100 and 201."""
+    import torch
+    gold = json.load(open(os.path.join(helpers.ROOT, "tests", "golden", "config3_2g.json")))
+    n, k, d = gold["text"]["n"], gold["k"], gold["d"]
+    b = pkg.IndexBuild.from_synth(n, gold["text"]["seed"], k, d)
+    nq, length = gold["reads"]["num"], gold["reads"]["len"]
+    d_ascii = torch.empty(nq * length, dtype=torch.uint8, device="cuda")
+    pkg.check(pkg.lib().fmgpu_synth_reads_device(0, n, gold["text"]["seed"], nq, length, gold["reads"]["seed"], 0, d_ascii.data_ptr(), None), "reads")
+    torch.cuda.synchronize()
+    reads = d_ascii.cpu().numpy()
+    del d_ascii
+    batch = pkg.DeviceBatch(0, nq, length, k)
+    batch.upload_ascii(reads)
+    for tag, key in ((100, "res_cpu_std_text"), (201, "res_cpu_ac_text")):
+        t = b if tag == 100 else b.transform(tag)
+        idx = t.to_index().sparsify()
+        m = idx.meta
+        assert (m.sparse_bases, m.sparse_lanes, m.sparse_start_bases) == (10, 2, 10) and m.sparse_bytes < 30e9
+        for qpt in (2, 4):
+            batch.search(idx, pkg.variant(pkg.MODE_SPARSE, qpt))
+            assert helpers.results_text_md5(batch.download()) == gold["md5"][key], f"tag {tag} qpt {qpt}"
+        idx.free()
+        if tag != 100:
+            t.free()
+    batch.free(); b.free()
+
+
+def test_sparse_end_to_end_host_calls(pkg):
+    """fmgpu_search_host / fmgpu_search_host_packed with the sparse-step variant: host buffers in, host (L,R) out."""
+    g = np.load(os.path.join(helpers.ROOT, "tests", "golden", "small_k2_d64.npz"))
+    reads, length = g["reads"], int(g["length"])
+    idx = pkg.DeviceIndex.from_image(g["image_100"]).sparsify()
+    got = pkg.search_host([idx], reads, length, var=pkg.variant(pkg.MODE_SPARSE, 4))
+    assert np.array_equal(got, g["expected_std"])
+    idx.free()
+
+
+def test_sparse_dropin_flow_env_modes(pkg, tmp_path):
+    """The reference-shaped file flow with $FMGPU_MODE=sparse (table on every replica), 1 and 2 logical shards."""
+    g = np.load(os.path.join(helpers.ROOT, "tests", "golden", "small_k2_d64.npz"))
+    length = int(g["length"])
+    nq = 2001
+    reads = g["reads"][: nq * length]
+    qfa = str(tmp_path / "q.fa")
+    helpers.write_fasta_reads(qfa, reads, length)
+    ndev = pkg.lib().fmgpu_device_count()
+    for tag, key in ((101, "expected_std"), (200, "expected_ac")):
+        fn = str(tmp_path / f"i{tag}.fmi")
+        g[f"image_{tag}"].tofile(fn)
+        for shards in (1, 2):
+            os.environ["FMGPU_MODE"] = "sparse"
+            try:
+                got = pkg.search_files(fn, qfa, length, nq, devices=[i % ndev for i in range(shards)], var=None)
+            finally:
+                del os.environ["FMGPU_MODE"]
+            assert np.array_equal(got, g[key][: 2 * nq]), f"tag {tag} shards {shards}"
