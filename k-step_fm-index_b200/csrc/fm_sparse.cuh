@@ -48,7 +48,7 @@ struct FmSparseParams {
   uint32_t       *results;
   uint32_t nblocks;           /* SB96 stride                                                       */
   uint32_t nq;
-  uint32_t nlead;             /* leading base-k steps                                              */
+  uint32_t nlead;             /* base-k steps on SB96 (in front of, or behind, the sparse steps)   */
   uint32_t nsteps;            /* sparse steps                                                      */
   uint32_t wpq;
   uint32_t bwtsize;
@@ -134,22 +134,29 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_kernel(const F
 
   unsigned long long n_sp = 0, n_sb = 0, n_ovf = 0;
   uint32_t pos = 0;
-  for (uint32_t step = 0; step < p.nlead; step++, pos += BBITS) {      /* leading base-k steps on SB96 */
-    #pragma unroll
-    for (int i = 0; i < QPT; i++) {
-      const uint32_t sig = fm_read_field(myq[i], pos, BMASK);
-      const uint32_t bL = fm_div96(L[i]), bR = fm_div96(R[i]);
-      const uint4 *base = p.blocks + (size_t) sig * p.nblocks;
-      const uint4 vL = fm_ldg16(base + bL);
-      const uint4 vR = (bL == bR) ? vL : fm_ldg16(base + bR);
-      if (COUNT && live[i] && lg == 0) n_sb += (bL == bR) ? 1 : 2;
-      L[i] = fm_block_rank(vL, L[i] - bL * FM_SB_ROWS);
-      R[i] = fm_block_rank(vR, R[i] - bR * FM_SB_ROWS);
+  /* the (len/k) % hops base-k steps that do not fill a sparse step run on SB96: in FRONT of the sparse steps (wide
+   * interval, upper levels of the table, L2 hits) when there is no start table to use, BEHIND them when there is
+   * (one DRAM block per step there, but the start table keeps replacing the first sparse steps) */
+  auto base_steps = [&](uint32_t count) {
+    for (uint32_t step = 0; step < count; step++, pos += BBITS) {
+      #pragma unroll
+      for (int i = 0; i < QPT; i++) {
+        const uint32_t sg = fm_read_field(myq[i], pos, BMASK);
+        const uint32_t bL = fm_div96(L[i]), bR = fm_div96(R[i]);
+        const uint4 *base = p.blocks + (size_t) sg * p.nblocks;
+        const uint4 vL = fm_ldg16(base + bL);
+        const uint4 vR = (bL == bR) ? vL : fm_ldg16(base + bR);
+        if (COUNT && live[i] && lg == 0) n_sb += (bL == bR) ? 1 : 2;
+        L[i] = fm_block_rank(vL, L[i] - bL * FM_SB_ROWS);
+        R[i] = fm_block_rank(vR, R[i] - bR * FM_SB_ROWS);
+      }
     }
-  }
+  };
+  const bool use_start = p.start_steps && p.nsteps >= p.start_steps;
+  if (!use_start) base_steps(p.nlead);
 
   uint32_t step0 = 0;
-  if (p.start_steps && p.nlead == 0 && p.nsteps >= p.start_steps) {
+  if (use_start) {
     const uint32_t sb = p.start_steps * p.sbits;
     const uint32_t kmask = (sb >= 32u) ? 0xFFFFFFFFu : ((1u << sb) - 1u);
     #pragma unroll
@@ -243,6 +250,8 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_kernel(const F
     #pragma unroll
     for (int i = 0; i < QPT; i++) { L[i] = nL[i]; R[i] = nR[i]; }
   }
+
+  if (use_start) base_steps(p.nlead);
 
   if (K == 2 && p.has_tail) {                     /* last base of an odd-length read */
     #pragma unroll
