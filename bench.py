@@ -12,7 +12,7 @@ BASELINE configs[3]'s 100 M-read shape.  A "step" = one pass of the search over 
 
   value      Mqueries/s, whole job, kernels only, reads packed and resident in HBM (the reference's own
              timed region, common/searchQueries.c:78-98), CUDA events on the launching stream.  Timed
-             kernel: the sparse-step kernel (10 bases per 128-byte block fetch, table built on the GPU from
+             kernel: the sparse-step kernel (10 bases per 64-byte block fetch, table built on the GPU from
              the 2-step index); the fused-step kernel (4 bases per fetch) and the plain 2-step Coop kernel
              are timed beside it as fused_4base_kernel / plain_2step_kernel; $FM_BENCH_MODE=fused|coop|task
              makes one of those the timed kernel instead.
@@ -27,7 +27,7 @@ BASELINE configs[3]'s 100 M-read shape.  A "step" = one pass of the search over 
              the reference's own searchIndexCPU (oracle/_ref/libref_search_k2_d64_std.so, compiled
              from /root/reference) on all host cores, on a bounded sample of the same reads.
 
-Inputs are larger than L2 (16 GB sparse table / 68 GB fused table / 5.33 GB index, 250 MB packed reads vs 126 MB
+Inputs are larger than L2 (26 GB sparse table / 68 GB fused table / 5.33 GB index, 250 MB packed reads vs 126 MB
 L2), so no flush between steps.
 """
 import argparse
@@ -157,6 +157,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: whatever libraries print there (NCCL's version banner under
+    # torchrun, for one) is sent to stderr, and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -256,7 +265,7 @@ def main():
                                  "sample": f"first {nq} reads of the workload per step, {cores} OpenMP threads, index image built on the GPU (byte-identical to gfmiBaseLine's)"},
                 "e2e": {"value": mq, "unit": "Mqueries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     wpq = L.fmgpu_words_per_query(READ_LEN)
@@ -464,7 +473,7 @@ def main():
             "clocks": clocks,
             "checks": {"every_read_found": hits_ok, "e2e_equals_resident": same, "gpu_equals_reference_cpu_on_sample": parity},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if distributed:
         dist.destroy_process_group()
     return 0
