@@ -1,5 +1,5 @@
-"""BASELINE config 5 on one B200: Task vs Coop vs Fused over read lengths 12/25/50/100/250 and k in {1,2} on the
-2 Gbp index (10 M reads per point).  Every point is checked: all reads found, and Task == Coop == Fused.
+"""BASELINE config 5 on one B200: Task vs Coop vs Fused vs Sparse over read lengths 12/25/50/100/250 and k in {1,2} on the
+2 Gbp index (10 M reads per point).  Every point is checked: all reads found, and Task == Coop == Fused == Sparse.
 Writes gpurun_out/config5_sweep.jsonl."""
 import importlib, json, os, sys
 import numpy as np
@@ -16,8 +16,10 @@ stream = torch.cuda.current_stream().cuda_stream
 for k in (2, 1):
     b = pkg.IndexBuild.from_synth(n, 1, k, 64); idx = b.to_index(); b.free()
     idx.fuse()
+    idx.sparsify()
     m = idx.meta
-    emit(what="index", k=k, sb96_gb=m.nbytes / 1e9, fused_bases=m.fused_bases, fused_gb=m.fused_bytes / 1e9)
+    emit(what="index", k=k, sb96_gb=m.nbytes / 1e9, fused_bases=m.fused_bases, fused_gb=m.fused_bytes / 1e9,
+         sparse_bases=m.sparse_bases, sparse_gb=m.sparse_bytes / 1e9)
     for length in (12, 25, 50, 100, 250):
         # odd lengths at k=2: undefined in the reference; served here by the derived 1-step tail
         d_ascii = torch.empty(nq * length, dtype=torch.uint8, device="cuda")
@@ -26,7 +28,8 @@ for k in (2, 1):
         d_packed = torch.empty(nq * wpq, dtype=torch.int32, device="cuda"); d_res = torch.zeros(2 * nq, dtype=torch.int32, device="cuda")
         pkg.check(L.fmgpu_pack_queries_device(0, d_ascii.data_ptr(), nq, length, d_packed.data_ptr(), stream), "pack"); torch.cuda.synchronize(); del d_ascii
         ref = None
-        for name, v in (("task", pkg.variant(pkg.MODE_TASK, 2, 512)), ("coop", pkg.variant(pkg.MODE_COOP, 1, 256)), ("fused", pkg.variant(pkg.MODE_FUSED, 2))):
+        for name, v in (("task", pkg.variant(pkg.MODE_TASK, 2, 512)), ("coop", pkg.variant(pkg.MODE_COOP, 1, 256)), ("fused", pkg.variant(pkg.MODE_FUSED, 2)),
+                        ("sparse", pkg.variant(pkg.MODE_SPARSE, 4))):
             ts = []
             for _ in range(5):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
