@@ -373,9 +373,18 @@ int32_t transferCPUtoGPU(void *index, void *queries, void *results)
       if (mode == FM_MODE_AUTO && fmgpu_index_get_meta(rs->replica[0], &meta0) == FM_SUCCESS) want_sparse = meta0.nbytes > (96ull << 20);
       for (g = 0; g < rs->ndev && (want_sparse || want_fused); g++) {
         err = want_sparse ? fmgpu_index_sparsify(rs->replica[g], 0, 0, 0) : FM_E_NOT_IMPLEMENTED;
+        if (!err && mode == FM_MODE_AUTO && fmgpu_index_get_meta(rs->replica[g], &meta0) == FM_SUCCESS &&
+            meta0.sparse_overflow * 1000ull > meta0.sparse_blocks) {
+          /* repeat-rich text: more than 0.1 % of the sparse blocks are overfull, reads from the repeats would take the
+           * SB96 fallback in every few steps (profiles/r01_repeat_text.md) -- the fused-step table does not care */
+          if (fmgpu_index_fuse(rs->replica[g], 0, 0, 0) == FM_SUCCESS) fmgpu_index_unsparsify(rs->replica[g]);
+        }
         if (err == FM_E_NOT_IMPLEMENTED && (want_fused || mode == FM_MODE_AUTO)) err = fmgpu_index_fuse(rs->replica[g], 0, 0, 0);
         if (err && err != FM_E_NOT_IMPLEMENTED) { for (g = 0; g < rs->ndev; g++) fmgpu_index_free(&rs->replica[g]); free(rs); return err; }
       }
+      if (getenv("FMGPU_VERBOSE") && fmgpu_index_get_meta(rs->replica[0], &meta0) == FM_SUCCESS)
+        fprintf(stderr, "fmindex_b200: %d replica(s), SB96 %.1f MB, search table: %s\n", rs->ndev, meta0.nbytes / 1e6,
+                meta0.sparse_bases ? "sparse-step" : meta0.fused_bases ? "fused-step" : "none (plain kernels)");
     }
     fmi->d_index = rs;
   }

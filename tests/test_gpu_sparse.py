@@ -258,3 +258,38 @@ def test_sparse_dropin_flow_env_modes(pkg, tmp_path):
             finally:
                 del os.environ["FMGPU_MODE"]
             assert np.array_equal(got, g[key][: 2 * nq]), f"tag {tag} shards {shards}"
+
+
+def test_dropin_auto_mode_picks_table_by_text(pkg, tmp_path, capfd):
+    """transferCPUtoGPU in auto mode on indexes larger than L2: sparse-step table for a random text, fused-step table
+    when the sparse blocks of a repeat-rich text overflow (profiles/r01_repeat_text.md); same (L,R) as the plain kernel."""
+    rng = np.random.default_rng(23)
+    n, length, nq = 48_000_001, 60, 20_000
+    for kind in ("random", "repeats"):
+        text = ACGT[rng.integers(0, 4, n, dtype=np.uint8)]
+        if kind == "repeats":
+            unit = ACGT[rng.integers(0, 4, 300)]
+            for pos in rng.integers(0, n - 300, n // 600):       # half of the text: 10 %-diverged copies of one family
+                copy = unit.copy()
+                mut = rng.random(300) < 0.10
+                copy[mut] = ACGT[rng.integers(0, 4, int(mut.sum()))]
+                text[pos:pos + 300] = copy
+        b = pkg.IndexBuild.from_text(text, 2, 64)
+        fn = str(tmp_path / f"{kind}.fmi")
+        b.download().tofile(fn)
+        b.free()
+        starts = rng.integers(0, n - length, nq)
+        reads = text[(starts[:, None] + np.arange(length)[None, :])].reshape(-1)
+        qfa = str(tmp_path / f"{kind}.fa")
+        helpers.write_fasta_reads(qfa, reads, length)
+        want = pkg.search_files(fn, qfa, length, nq, devices=[0], var=pkg.variant(pkg.MODE_COOP))
+        assert ((want[1::2] - want[0::2]) >= 1).all()
+        capfd.readouterr()
+        os.environ["FMGPU_VERBOSE"] = "1"
+        try:
+            got = pkg.search_files(fn, qfa, length, nq, devices=[0], var=None)
+        finally:
+            del os.environ["FMGPU_VERBOSE"]
+        err = capfd.readouterr().err
+        assert np.array_equal(got, want), kind
+        assert ("search table: sparse-step" if kind == "random" else "search table: fused-step") in err, err
