@@ -114,6 +114,17 @@ static void stream_scalar(const unsigned char *in, uint64_t nbases, unsigned cha
   }
 }
 
+/* software prefetch distance of the stream packer in bytes: $FM_HOSTPACK_PREFETCH or fm_hostpack_set_prefetch(),
+ * default 8192; 0 = off.  Worth ~5 % on the hybrid end-to-end feed of the benchmark host (1 041 -> 1 107 M reads/s,
+ * means of three alternating rounds, profiles/r01_hostpack_prefetch.md); the packer alone is within noise. */
+static int g_pf_dist = -1;
+static int fm_hostpack_prefetch_distance(void)
+{
+  if (g_pf_dist < 0) { const char *e = getenv("FM_HOSTPACK_PREFETCH"); g_pf_dist = e && *e ? atoi(e) : 8192; }
+  return g_pf_dist;
+}
+void fm_hostpack_set_prefetch(int bytes) { g_pf_dist = bytes < 0 ? 0 : bytes; }
+
 __attribute__((target("avx512f,avx512bw,avx512vl")))
 static void stream_avx512(const unsigned char *in, uint64_t nbases, unsigned char *out)
 {
@@ -124,8 +135,10 @@ static void stream_avx512(const unsigned char *in, uint64_t nbases, unsigned cha
   static int nt_allowed = -1;
   if (nt_allowed < 0) { const char *e = getenv("FM_HOSTPACK_NT"); nt_allowed = (e && e[0] == '1'); }
   const int nt = nt_allowed && (((uintptr_t) out) & 15u) == 0;
+  const int pf_dist = fm_hostpack_prefetch_distance();
   uint64_t g = 0;
   for (; g + 64 <= nbases; g += 64) {
+    if (pf_dist) _mm_prefetch((const char *)(in + g + pf_dist), _MM_HINT_NTA);
     const __m512i x = _mm512_loadu_si512((const void *)(in + g));
     const __m512i u = _mm512_and_si512(_mm512_srli_epi16(x, 1), three);
     const __m512i c = _mm512_xor_si512(u, _mm512_and_si512(_mm512_srli_epi16(u, 1), one));
