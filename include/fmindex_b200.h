@@ -64,7 +64,7 @@ typedef enum {
   /* new codes (outside the reference's range) */
   FM_E_CUDA = 50,              /* CUDA runtime error or no usable device        */
   FM_E_BAD_ARGUMENT = 51,
-  FM_E_UNSUPPORTED_INDEX = 52, /* k not in {1,2} or d not a multiple of 32      */
+  FM_E_UNSUPPORTED_INDEX = 52, /* k not in {1..4}, d not a multiple of 32, ...     */
   FM_E_QUERY_SHAPE = 53,       /* read length not a multiple of k               */
   FM_E_INDEX_VER_BASELINE = 100,
   FM_E_INDEX_VER_INTERLEAVE = 101,
@@ -196,7 +196,8 @@ typedef struct {
   uint32_t source_tag;   /* tag of the file it was derived from                 */
   uint32_t quirk_start;  /* first BWT row of the AltCounters padding quirk, or 0xFFFFFFFF */
   uint32_t quirk_mask;   /* 2 bits per symbol: value the reference AC searcher adds there  */
-  uint32_t reserved;
+  uint32_t source_steps; /* k of the file it was derived from (files with k = 3, 4 are searched through the
+                            2-step index their first two BWT layers define; steps is 2 then)              */
   uint64_t nbytes;       /* size of the block table                             */
   uint32_t fused_bases;  /* bases per fused step (0 = no fused table), see fmgpu_index_fuse */
   uint32_t fused_lanes;  /* lanes per fused block (block = 32 bytes per lane)   */

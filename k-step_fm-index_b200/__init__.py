@@ -66,7 +66,7 @@ class fmgpu_variant_t(C.Structure):
 
 class fmgpu_index_meta_t(C.Structure):
     _fields_ = [("steps", C.c_uint32), ("bwtsize", C.c_uint32), ("nsymbols", C.c_uint32), ("nblocks", C.c_uint32),
-                ("source_tag", C.c_uint32), ("quirk_start", C.c_uint32), ("quirk_mask", C.c_uint32), ("reserved", C.c_uint32),
+                ("source_tag", C.c_uint32), ("quirk_start", C.c_uint32), ("quirk_mask", C.c_uint32), ("source_steps", C.c_uint32),
                 ("nbytes", C.c_uint64), ("fused_bases", C.c_uint32), ("fused_lanes", C.c_uint32), ("fused_bytes", C.c_uint64),
                 ("tail_valid", C.c_uint32), ("tail_row", C.c_uint32), ("tail_base", C.c_uint32), ("tail_const", C.c_uint32 * 4),
                 ("start_bases", C.c_uint32),

@@ -237,6 +237,54 @@ __global__ void fmb_counters_kernel(const uint32_t *__restrict__ scan, const uin
   for (uint32_t sigma = 0; sigma < nsym; sigma++) cnt[sigma] = scan[(size_t) sigma * nentries + e] + acc[sigma];
 }
 
+/* Counter stage shared by the builder and by the k >= 3 -> 2-step projection of fm_gpu.cu: fills cnt[] of every
+ * tag-100 entry from the planes already in `entries` (device), k <= 2.  dpos / dbase are host arrays. */
+cudaError_t fmb_counter_stage(uint32_t *entries, uint32_t k, uint32_t d, uint32_t entry_words, uint32_t nentries, uint32_t bwtsize,
+                              const uint32_t *dpos, const uint32_t *dbase)
+{
+  const uint32_t nsym = 1u << (2 * k);
+  uint32_t *hist = NULL, *d_acc = NULL, *d_dpos = NULL;
+  void *d_temp = NULL;
+  cudaError_t e = cudaMalloc((void **) &hist, (size_t) nsym * nentries * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &d_acc, nsym * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &d_dpos, 2 * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(d_dpos, dpos, k * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    fmb_hist_kernel<<<(nentries + 127) / 128, 128>>>(entries, k, d, entry_words, nentries, bwtsize, d_dpos, hist);
+    e = cudaGetLastError();
+  }
+  uint32_t totals[16], acc[16];
+  for (uint32_t sigma = 0; sigma < nsym && e == cudaSuccess; sigma++) {
+    uint32_t *h = hist + (size_t) sigma * nentries, last_in = 0, last_out = 0;
+    e = cudaMemcpy(&last_in, h + nentries - 1, 4, cudaMemcpyDeviceToHost);
+    size_t tb = 0;
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(NULL, tb, h, h, (int) nentries);
+    if (e == cudaSuccess) e = cudaMalloc(&d_temp, tb ? tb : 16);
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(d_temp, tb, h, h, (int) nentries);
+    if (e == cudaSuccess) e = cudaMemcpy(&last_out, h + nentries - 1, 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_temp); d_temp = NULL;
+    totals[sigma] = last_in + last_out;
+  }
+  if (e == cudaSuccess) {
+    uint32_t run = 0;
+    for (uint32_t sigma = 0; sigma < nsym; sigma++) { acc[sigma] = run; run += totals[sigma]; }
+    /* '$' adjustments of src/genFMindex.c:245-250: the suffix that starts with the '$'-row's symbol
+     * (its layers below s cleared) gets one extra predecessor */
+    for (uint32_t s = 0; s < k; s++) {
+      const uint32_t from = dbase[s] & (0xFFFFFFFFu << (2 * s));
+      for (uint32_t sigma = from; sigma < nsym; sigma++) acc[sigma]++;
+    }
+    e = cudaMemcpy(d_acc, acc, nsym * 4, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess) {
+    fmb_counters_kernel<<<(nentries + 127) / 128, 128>>>(hist, d_acc, k, d, entry_words, nentries, entries);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaFree(hist); cudaFree(d_acc); cudaFree(d_dpos);
+  return e;
+}
+
 /* k-step symbol stored at a row ('$' as A) */
 __global__ void fmb_row_symbols_kernel(const uint64_t *__restrict__ pt, const uint32_t *__restrict__ sorted, uint64_t n,
                                        uint32_t k, const uint32_t *__restrict__ rows, uint32_t *__restrict__ syms)
@@ -469,40 +517,7 @@ static int32_t fmb_build(int device, const char *h_ascii, uint64_t n, uint64_t s
     cudaFree(vals_b); vals_b = NULL; cudaFree(pt); pt = NULL;
 
     /* 5. counters: per-entry histogram, exclusive scan per symbol, C table */
-    uint32_t *hist = NULL, *d_acc = NULL;
-    BTRY(cudaMalloc((void **) &hist, (size_t) nsym * b->nentries * 4));
-    BTRY(cudaMalloc((void **) &d_acc, nsym * 4));
-    fmb_hist_kernel<<<(b->nentries + 127) / 128, 128>>>(entries, k, d, b->entry_words, b->nentries, b->bwtsize, d_dpos, hist);
-    cudaError_t e = cudaGetLastError();
-    uint32_t totals[16], acc[16];
-    for (uint32_t sigma = 0; sigma < nsym && e == cudaSuccess; sigma++) {
-      uint32_t *h = hist + (size_t) sigma * b->nentries, last_in = 0, last_out = 0;
-      e = cudaMemcpy(&last_in, h + b->nentries - 1, 4, cudaMemcpyDeviceToHost);
-      size_t tb = 0;
-      if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(NULL, tb, h, h, (int) b->nentries);
-      if (e == cudaSuccess) e = cudaMalloc(&d_temp, tb ? tb : 16);
-      if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(d_temp, tb, h, h, (int) b->nentries);
-      if (e == cudaSuccess) e = cudaMemcpy(&last_out, h + b->nentries - 1, 4, cudaMemcpyDeviceToHost);
-      cudaFree(d_temp); d_temp = NULL;
-      totals[sigma] = last_in + last_out;
-    }
-    if (e == cudaSuccess) {
-      uint32_t run = 0;
-      for (uint32_t sigma = 0; sigma < nsym; sigma++) { acc[sigma] = run; run += totals[sigma]; }
-      /* '$' adjustments of src/genFMindex.c:245-250: the suffix that starts with the '$'-row's symbol
-       * (its layers below s cleared) gets one extra predecessor */
-      for (uint32_t s = 0; s < k; s++) {
-        const uint32_t from = b->dbase[s] & (0xFFFFFFFFu << (2 * s));
-        for (uint32_t sigma = from; sigma < nsym; sigma++) acc[sigma]++;
-      }
-      e = cudaMemcpy(d_acc, acc, nsym * 4, cudaMemcpyHostToDevice);
-    }
-    if (e == cudaSuccess) {
-      fmb_counters_kernel<<<(b->nentries + 127) / 128, 128>>>(hist, d_acc, k, d, b->entry_words, b->nentries, entries);
-      e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaDeviceSynchronize();
-    cudaFree(hist); cudaFree(d_acc);
+    cudaError_t e = fmb_counter_stage(entries, k, d, b->entry_words, b->nentries, b->bwtsize, b->dpos, b->dbase);
     if (e != cudaSuccess) { rc = fmb_fail(e, "counter stage", __FILE__, __LINE__); goto done; }
 
     /* 6. header (src/genFMindex.c:167-176) */

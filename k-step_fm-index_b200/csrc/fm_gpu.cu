@@ -114,14 +114,82 @@ static void fm_ac_quirk(uint32_t tag, uint32_t steps, uint32_t chunk, uint32_t b
   if (*mask) *start = elast * chunk;
 }
 
+/* fm_build.cu */
+cudaError_t fmb_counter_stage(uint32_t *entries, uint32_t k, uint32_t d, uint32_t entry_words, uint32_t nentries, uint32_t bwtsize,
+                              const uint32_t *dpos, const uint32_t *dbase);
+
+/* planes of BWT layers 0 and 1 of a k-step file entry (any tag) -> planes of a 2-step tag-100 entry */
+__global__ void fm_project_planes_kernel(const FmRawIndex x, uint32_t *__restrict__ out, uint32_t out_entry_words)
+{
+  const uint32_t W = x.d / 32;
+  const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint64_t) x.nentries_std * W) return;
+  const uint32_t e = (uint32_t)(t / W), n = (uint32_t)(t % W);
+  uint32_t *o = out + (size_t) e * out_entry_words;
+  for (uint32_t s = 0; s < 2; s++)
+    for (uint32_t bit = 0; bit < 2; bit++) o[2 * W * s + W * bit + n] = fm_raw_plane(x, e, s, bit, n);
+}
+
+static int32_t fm_index_from_device_entries(int device, uint32_t tag, uint32_t steps, uint32_t chunk, uint32_t bwtsize,
+                                            uint32_t ncounters, uint32_t nentries, const uint32_t *dpos,
+                                            const uint32_t *dbase, const uint32_t *d_entries, fmgpu_index_t **out);
+
+/* k = 3 or 4 files (CPU-only in the reference, makefile:226-230): the device layout does not depend on the file's k --
+ * the first two BWT layers of the file ARE the 2-step index of the same text, so its planes are copied, the 2-step
+ * counters are recomputed from them exactly as src/genFMindex.c:210-256 does (fmb_counter_stage, byte-identical to
+ * gfmiBaseLine's 2-step file), and the search runs on that; the reference searchers of all k agree on (L,R) wherever
+ * the read length is a multiple of k.  An AltCounters file whose padding-entry quirk is active cannot be reproduced
+ * this way and is refused. */
+static int32_t fm_index_from_wide_file(int device, uint32_t tag, uint32_t steps, uint32_t chunk, uint32_t bwtsize,
+                                       uint32_t ncounters, uint32_t nentries, const uint32_t *dpos,
+                                       const uint32_t *dbase, const uint32_t *d_entries, fmgpu_index_t **out)
+{
+  const bool ac = (tag == 200 || tag == 201);
+  const uint32_t nsym = 1u << (2 * steps), W = chunk / 32;
+  if (ncounters != (ac ? nsym / 2 : nsym)) return fm_fail_msg(FM_E_UNSUPPORTED_INDEX, "counter count does not match k");
+  const uint32_t nstd = (uint32_t)(((uint64_t) bwtsize + chunk - 1) / chunk);
+  if (nentries != nstd + (ac ? 1u : 0u) || bwtsize < 2) return fm_fail_msg(FM_E_UNSUPPORTED_INDEX, "entry count does not match bwtsize/d");
+  uint32_t qstart, qmask;
+  {                                                          /* padding-entry quirk of a wide AltCounters file (any symbol) */
+    qstart = 0xFFFFFFFFu; qmask = 0;
+    const uint32_t elast = (bwtsize - 1) / chunk;
+    for (uint32_t s = 0; ac && s < steps; s++)
+      if (dpos[s] / chunk == elast) {
+        const uint32_t sigma = dbase[s];
+        if (((elast & 1u) && sigma < ncounters) || (!(elast & 1u) && sigma >= ncounters)) qmask = 1;
+      }
+  }
+  if (qmask) return fm_fail_msg(FM_E_UNSUPPORTED_INDEX, "k >= 3 AltCounters file with an active padding-entry quirk");
+  const uint32_t ew2 = 4 * W + 16;
+  uint32_t *proj = NULL;
+  cudaError_t e = cudaMalloc((void **) &proj, (size_t) nstd * ew2 * 4);
+  if (e != cudaSuccess) return fm_fail(e, "cudaMalloc(2-step projection)", __FILE__, __LINE__);
+  FmRawIndex raw;
+  raw.entries = d_entries; raw.tag = tag; raw.k = steps; raw.d = chunk; raw.ncounters = ncounters;
+  raw.nentries = nentries; raw.entry_words = 2 * W * steps + ncounters; raw.bwtsize = bwtsize; raw.nentries_std = nstd;
+  for (uint32_t s = 0; s < 2; s++) { raw.dpos[s] = dpos[s]; raw.dbase[s] = dbase[s]; }
+  raw.quirk_start = 0xFFFFFFFFu; raw.quirk_mask = 0;
+  const uint64_t nthreads = (uint64_t) nstd * W;
+  fm_project_planes_kernel<<<(unsigned)((nthreads + 255) / 256), 256>>>(raw, proj, ew2);
+  e = cudaGetLastError();
+  const uint32_t dpos2[2] = { dpos[0], dpos[1] }, dbase2[2] = { dbase[0] & 15u, dbase[1] & 15u };
+  if (e == cudaSuccess) e = fmb_counter_stage(proj, 2, chunk, ew2, nstd, bwtsize, dpos2, dbase2);
+  if (e != cudaSuccess) { cudaFree(proj); return fm_fail(e, "2-step projection of a k >= 3 file", __FILE__, __LINE__); }
+  int32_t rc = fm_index_from_device_entries(device, 100, 2, chunk, bwtsize, 16, nstd, dpos2, dbase2, proj, out);
+  cudaFree(proj);
+  if (rc == FM_SUCCESS) { (*out)->meta.source_tag = tag; (*out)->meta.source_steps = steps; }
+  return rc;
+}
+
 static int32_t fm_index_from_device_entries(int device, uint32_t tag, uint32_t steps, uint32_t chunk, uint32_t bwtsize,
                                             uint32_t ncounters, uint32_t nentries, const uint32_t *dpos,
                                             const uint32_t *dbase, const uint32_t *d_entries, fmgpu_index_t **out)
 {
   const bool ac = (tag == 200 || tag == 201);
   if (!(tag == 100 || tag == 101 || ac)) return fm_fail_msg(FM_E_UNSUPPORTED_INDEX, "unknown index tag");
-  if (steps < 1 || steps > 2) return fm_fail_msg(FM_E_UNSUPPORTED_INDEX, "GPU search supports k in {1,2} (like the reference GPU kernels)");
+  if (steps < 1 || steps > 4) return fm_fail_msg(FM_E_UNSUPPORTED_INDEX, "index files with k in {1,2,3,4} are supported (like the reference builders)");
   if (chunk == 0 || chunk % 32) return fm_fail_msg(FM_E_UNSUPPORTED_INDEX, "d must be a multiple of 32");
+  if (steps > 2) return fm_index_from_wide_file(device, tag, steps, chunk, bwtsize, ncounters, nentries, dpos, dbase, d_entries, out);
   const uint32_t nsym = 1u << (2 * steps);
   if (ncounters != (ac ? nsym / 2 : nsym)) return fm_fail_msg(FM_E_UNSUPPORTED_INDEX, "counter count does not match k");
   const uint32_t need = (uint32_t)(((uint64_t) bwtsize + chunk - 1) / chunk) + (ac ? 1u : 0u);
@@ -131,7 +199,7 @@ static int32_t fm_index_from_device_entries(int device, uint32_t tag, uint32_t s
   if (!idx) return fm_fail_msg(FM_E_ALLOCATING_FMI, "host allocation failed");
   idx->device = device;
   idx->meta.steps = steps; idx->meta.bwtsize = bwtsize; idx->meta.nsymbols = nsym;
-  idx->meta.nblocks = fm_nblocks_for(bwtsize); idx->meta.source_tag = tag;
+  idx->meta.nblocks = fm_nblocks_for(bwtsize); idx->meta.source_tag = tag; idx->meta.source_steps = steps;
   fm_ac_quirk(tag, steps, chunk, bwtsize, ncounters, dpos, dbase, &idx->meta.quirk_start, &idx->meta.quirk_mask);
   idx->meta.nbytes = (uint64_t) nsym * idx->meta.nblocks * sizeof(uint4);
 
@@ -192,7 +260,7 @@ extern "C" int32_t fmgpu_index_create(int32_t device, uint32_t tag, uint32_t ste
   int32_t rc = fm_use_device(device);
   if (rc) return rc;
   if (!h_entries || !out || !dpos || !dbase) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
-  if (steps < 1 || steps > 2 || chunk == 0 || chunk % 32) return fm_fail_msg(FM_E_UNSUPPORTED_INDEX, "GPU search supports k in {1,2}, d multiple of 32");
+  if (steps < 1 || steps > 4 || chunk == 0 || chunk % 32) return fm_fail_msg(FM_E_UNSUPPORTED_INDEX, "index files need k in {1,2,3,4}, d multiple of 32");
   const uint64_t bytes = (uint64_t) nentries * (2 * (chunk / 32) * steps + ncounters) * 4ull;
   uint32_t *d_raw = NULL;
   CU_TRY(cudaMalloc((void **) &d_raw, bytes));

@@ -77,7 +77,7 @@ char *errorCommon(int32_t e)
     case FM_E_NOT_IMPLEMENTED:          return "Not implemented";
     case FM_E_CUDA:                     return (char *) fmgpu_last_error();
     case FM_E_BAD_ARGUMENT:             return (char *) fmgpu_last_error();
-    case FM_E_UNSUPPORTED_INDEX:        return "Unsupported index (GPU search needs k in {1,2} and d a multiple of 32)";
+    case FM_E_UNSUPPORTED_INDEX:        return "Unsupported index (needs k in {1,2,3,4}, d a multiple of 32, no active AltCounters quirk for k >= 3)";
     case FM_E_QUERY_SHAPE:              return "Read length must be a positive multiple of k";
     case FM_E_INDEX_VER_BASELINE:       return "Error in the index type, use gfmiBaseLine_*Bases_*Step to generate an index_name.fmi type";
     case FM_E_INDEX_VER_INTERLEAVE:     return "Error in the index type, use tfmiBMP_*Bases_*Step to generate an index_name.fmi.interleaving type";

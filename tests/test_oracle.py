@@ -29,7 +29,7 @@ def test_golden_set_contains_altcounters_quirk(built):
 
 
 @pytest.mark.skipif(not helpers.has_ref_tools(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("k", [1, 2])
+@pytest.mark.parametrize("k", [1, 2, 3, 4])
 @pytest.mark.parametrize("d", [32, 64, 128])
 def test_oracle_matches_reference_in_process(built, tmp_path, k, d):
     n = 50021 + 13 * d
