@@ -26,6 +26,7 @@ CSRC = os.path.join(_HERE, "csrc")
 BIN = os.path.join(_HERE, "bin")
 
 FM_SUCCESS = 0
+FM_E_READING_FMI = 5
 FM_E_CUDA = 50
 FM_E_BAD_ARGUMENT = 51
 FM_E_UNSUPPORTED_INDEX = 52
@@ -286,7 +287,14 @@ class DeviceIndex:
     def from_image(cls, image_u32, device=0):
         """image = the words of an index FILE (header + entries) as a numpy uint32 array."""
         im = np.ascontiguousarray(image_u32, dtype=np.uint32)
+        if im.ndim != 1 or im.size < 6:
+            raise FMError(FM_E_READING_FMI, "DeviceIndex.from_image (image shorter than a header)")
         tag, k, bwtsize, ncnt, nent, d = (int(v) for v in im[:6])
+        if not 1 <= k <= 4 or d == 0 or d % 32:
+            raise FMError(FM_E_UNSUPPORTED_INDEX, "DeviceIndex.from_image")
+        # fmgpu_index_create takes a bare pointer: the words it will read must be there (loadIndex checks the file the same way)
+        if im.size != 6 + 2 * k + nent * (2 * (d // 32) * k + ncnt):
+            raise FMError(FM_E_READING_FMI, "DeviceIndex.from_image (image size does not match its header)")
         dpos = (C.c_uint32 * k)(*[int(v) for v in im[6:6 + k]])
         dbase = (C.c_uint32 * k)(*[int(v) for v in im[6 + k:6 + 2 * k]])
         h = C.c_void_p()

@@ -240,7 +240,11 @@ def test_error_paths(pkg):
             b.search(idx, bad_variant)
         assert ei.value.code == pkg.FM_E_BAD_ARGUMENT
     b.free()
-    bad = g["image_100"].copy(); bad[1] = 3; bad[3] = 64         # k = 3: CPU-only in the reference too
+    bad = g["image_100"].copy(); bad[1] = 3; bad[3] = 64         # k = 3 header over a k = 2 body: size mismatch
+    with pytest.raises(pkg.FMError) as ei:
+        pkg.DeviceIndex.from_image(bad)
+    assert ei.value.code == pkg.FM_E_READING_FMI
+    bad = g["image_100"].copy(); bad[1] = 5; bad[3] = 1024       # k = 5: no such index anywhere in the reference
     with pytest.raises(pkg.FMError) as ei:
         pkg.DeviceIndex.from_image(bad)
     assert ei.value.code == pkg.FM_E_UNSUPPORTED_INDEX
