@@ -218,6 +218,10 @@ typedef struct {
   uint64_t sparse_overflow;    /* blocks holding more occurrences than slots (served by SB96 steps) */
   uint32_t sparse_start_bases; /* bases covered by the sparse kernel's start table, 0 = none    */
   uint32_t sparse_lanes;       /* lanes per block: 2 = 64-byte blocks (15 slots), 4 = 128-byte blocks (31 slots) */
+  /* tail table: the derived 1-step rank above re-blocked so that the last base of an odd-length read costs one
+   * block fetch instead of four; built on this replica by its first odd-length search (a quarter of nbytes), 0 = not
+   * built (yet, or $FMGPU_TAIL_TABLE=0, or no memory: the four-fetch derivation is used) */
+  uint64_t tail_bytes;
 } fmgpu_index_meta_t;
 
 /* devices ---------------------------------------------------------------- */

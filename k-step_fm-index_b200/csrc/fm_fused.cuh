@@ -48,6 +48,7 @@ struct FmFusedParams {
   uint32_t bwtsize;
   unsigned long long *fetch_counters;  /* COUNT only: [0] = fused blocks fetched, [1] = SB96 blocks of the leading steps */
   uint32_t has_tail, tail_row, tail_base, tail_const[4];   /* odd read length on a 2-step index, see fm_tail_rank */
+  const uint4 *tail1;         /* tail table (fm_tail_table_kernel) or NULL */
   /* start table: (L,R) after the first FM_START_BASES bases, indexed by their 24 packed bits -- the intervals this
    * very kernel computes for all 4^12 12-mers, so looking them up instead of stepping changes nothing in the result;
    * it replaces the L2-resident steps and the first DRAM step (two fetches) by one mostly-L2 lookup */
@@ -224,8 +225,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_fused_kernel(const Fm
     #pragma unroll
     for (int i = 0; i < QPT; i++) {
       const uint32_t c = fm_read_field(myq[i], pos, 3u);
-      L[i] = fm_tail_rank(p.blocks, p.nblocks, c, L[i], p.tail_const[c], p.tail_row, p.tail_base);
-      R[i] = fm_tail_rank(p.blocks, p.nblocks, c, R[i], p.tail_const[c], p.tail_row, p.tail_base);
+      fm_tail_step(p.tail1, p.blocks, p.nblocks, c, L[i], R[i], p.tail_const[c], p.tail_row, p.tail_base);
     }
   }
 

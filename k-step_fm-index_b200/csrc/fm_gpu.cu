@@ -16,6 +16,7 @@
 #include <string.h>
 #include <stdint.h>
 #include <time.h>
+#include <mutex>
 #include <cuda_runtime.h>
 #include "../../include/fmindex_b200.h"
 #include <cub/device/device_radix_sort.cuh>
@@ -34,6 +35,8 @@ struct fmgpu_index {
   uint4             *sblocks;      /* sparse-step table (fmgpu_index_sparsify), or NULL */
   uint2             *sdir;         /* its directory: { first block, scale } per wide symbol */
   uint2             *sstart;       /* start table of the sparse kernel, or NULL */
+  uint4             *tail1;        /* tail table (fm_tail_table_kernel): built by the first odd-length search on this replica */
+  int                tail1_tried;  /* 1 once that build was attempted (a failed allocation is not retried)               */
 };
 
 struct fmgpu_batch {
@@ -293,7 +296,7 @@ extern "C" int32_t fmgpu_index_alloc_like(int32_t device, const fmgpu_index_meta
   /* derived tables are per replica: a fresh replica has none until fmgpu_index_fuse / fmgpu_index_sparsify run on it */
   idx->meta.fused_bases = 0; idx->meta.fused_lanes = 0; idx->meta.fused_bytes = 0; idx->meta.start_bases = 0;
   idx->meta.sparse_bases = 0; idx->meta.sparse_lambda = 0; idx->meta.sparse_bytes = 0; idx->meta.sparse_blocks = 0;
-  idx->meta.sparse_overflow = 0; idx->meta.sparse_start_bases = 0; idx->meta.sparse_lanes = 0;
+  idx->meta.sparse_overflow = 0; idx->meta.sparse_start_bases = 0; idx->meta.sparse_lanes = 0; idx->meta.tail_bytes = 0;
   cudaError_t e = cudaMalloc((void **) &idx->blocks, meta->nbytes);
   if (e != cudaSuccess) { free(idx); return fm_fail(e, "cudaMalloc(SB96 replica)", __FILE__, __LINE__); }
   *out = idx;
@@ -328,14 +331,39 @@ extern "C" int32_t fmgpu_index_free(fmgpu_index_t **pidx)
 {
   if (!pidx || !*pidx) return FM_SUCCESS;
   fmgpu_index_t *idx = *pidx;
-  if (idx->blocks || idx->fblocks || idx->start || idx->sblocks) {
+  if (idx->blocks || idx->fblocks || idx->start || idx->sblocks || idx->tail1) {
     cudaSetDevice(idx->device);
     cudaFree(idx->blocks); cudaFree(idx->fblocks); cudaFree(idx->start);
-    cudaFree(idx->sblocks); cudaFree(idx->sdir); cudaFree(idx->sstart);
+    cudaFree(idx->sblocks); cudaFree(idx->sdir); cudaFree(idx->sstart); cudaFree(idx->tail1);
   }
   free(idx);
   *pidx = NULL;
   return FM_SUCCESS;
+}
+
+/* Tail table of a 2-step replica (fm_tail_table_kernel, a quarter of the SB96 table): built by the first search with an
+ * odd read length, on that replica's device, from its own block table (so replicas filled by a broadcast get theirs
+ * when they first need it).  Returns NULL -- the kernels then derive the rank from four SB96 fetches -- when the
+ * index has no valid tail ($FMGPU_TAIL_TABLE=0 also forces that path) or the allocation fails. */
+static std::mutex g_tail_mutex;
+static const uint4 *fm_ensure_tail(const fmgpu_index_t *cidx, cudaStream_t stream)
+{
+  fmgpu_index_t *idx = const_cast<fmgpu_index_t *>(cidx);
+  if (!idx->meta.tail_valid) return NULL;
+  std::lock_guard<std::mutex> lock(g_tail_mutex);
+  if (idx->tail1_tried) return idx->tail1;
+  idx->tail1_tried = 1;
+  const char *env = getenv("FMGPU_TAIL_TABLE");
+  if (env && *env && atoi(env) == 0) return NULL;
+  const uint32_t nb = idx->meta.nblocks;
+  uint4 *t = NULL;
+  if (cudaMalloc((void **) &t, (size_t) 4 * nb * sizeof(uint4)) != cudaSuccess) { cudaGetLastError(); return NULL; }
+  const uint32_t *tc = idx->meta.tail_const;
+  fm_tail_table_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(idx->blocks, nb, tc[0], tc[1], tc[2], tc[3], idx->meta.tail_row, idx->meta.tail_base, t);
+  /* waited for once: later searches may come on other streams */
+  if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) { cudaGetLastError(); cudaFree(t); return NULL; }
+  idx->tail1 = t; idx->meta.tail_bytes = (uint64_t) 4 * nb * sizeof(uint4);
+  return t;
 }
 
 /* ------------------------------------------------------------------------ *
@@ -486,6 +514,7 @@ static int32_t fm_launch_fused(const fmgpu_index_t *idx, const uint32_t *d_packe
   p.start = idx->start; p.start_steps = idx->start ? FM_START_BASES / kf : 0u;
   p.has_tail = len % k; p.tail_row = idx->meta.tail_row; p.tail_base = idx->meta.tail_base;
   for (int c = 0; c < 4; c++) p.tail_const[c] = idx->meta.tail_const[c];
+  p.tail1 = p.has_tail ? fm_ensure_tail(idx, stream) : NULL;
   if (d_counters) v.queries_per_thread = 1;
   uint32_t qper; size_t smem;
   for (;;) {
@@ -669,6 +698,7 @@ static int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_pack
   p.start = idx->sstart; p.start_steps = idx->sstart ? idx->meta.sparse_start_bases / ks : 0u;
   p.has_tail = len % k; p.tail_row = idx->meta.tail_row; p.tail_base = idx->meta.tail_base;
   for (int c = 0; c < 4; c++) p.tail_const[c] = idx->meta.tail_const[c];
+  p.tail1 = p.has_tail ? fm_ensure_tail(idx, stream) : NULL;
   if (d_counters) v.queries_per_thread = 1;
   uint32_t qper; size_t smem;
   for (;;) {
@@ -783,6 +813,7 @@ static int32_t fm_launch_search(const fmgpu_index_t *idx, const uint32_t *d_pack
   p.bwtsize = idx->meta.bwtsize; p.quirk_start = idx->meta.quirk_start; p.quirk_mask = idx->meta.quirk_mask;
   p.has_tail = len % k; p.tail_row = idx->meta.tail_row; p.tail_base = idx->meta.tail_base;
   for (int c = 0; c < 4; c++) p.tail_const[c] = idx->meta.tail_const[c];
+  p.tail1 = p.has_tail ? fm_ensure_tail(idx, stream) : NULL;
   const bool quirk = idx->meta.quirk_mask != 0;
 
   /* shrink the CTA's read count until the staged reads fit in shared memory */

@@ -51,6 +51,7 @@ struct FmSearchParams {
   uint32_t has_tail;
   uint32_t tail_row, tail_base;   /* row whose layer-1 char is '$' (it has a layer-0 char but no 2-step symbol), and that char */
   uint32_t tail_const[4];         /* C1[c] - sum_c1 rank2(c | c1<<2, 0) */
+  const uint4 *tail1;             /* [4][nblocks] tail table (fm_tail_table_kernel): that rank in ONE block fetch, or NULL */
 };
 
 /* raw (file-order) index as uploaded, for the re-blocker */
@@ -103,6 +104,50 @@ __device__ __forceinline__ uint32_t fm_tail_rank(const uint4 *__restrict__ block
   #pragma unroll
   for (int c1 = 0; c1 < 4; c1++) sum += fm_block_rank(v[c1], r);
   return sum;
+}
+
+/* Tail table: the derived 1-step rank re-blocked like SB96, tail1[c * nblocks + b] = { fm_tail_rank(c, 96 b), the 96
+ * indicator bits "layer-0 char of the row is c" } -- the OR of the four 2-step indicators (c1, c), which are disjoint,
+ * plus the bit of the row whose layer-1 char is '$' (it carries no 2-step symbol).  For X = 96 b + r,
+ * fm_block_rank(tail1[c][b], r) == fm_tail_rank(c, X) term by term, with one block fetch instead of four. */
+__global__ void fm_tail_table_kernel(const uint4 *__restrict__ blocks, uint32_t nblocks, uint32_t tc0, uint32_t tc1, uint32_t tc2,
+                                     uint32_t tc3, uint32_t tail_row, uint32_t tail_base, uint4 *__restrict__ tail1)
+{
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  const uint32_t tc[4] = { tc0, tc1, tc2, tc3 };
+  const uint32_t tb = tail_row / FM_SB_ROWS, to = tail_row - tb * FM_SB_ROWS;
+  #pragma unroll
+  for (uint32_t c = 0; c < 4; c++) {
+    uint4 o = make_uint4(tc[c] + ((b * FM_SB_ROWS > tail_row && c == tail_base) ? 1u : 0u), 0u, 0u, 0u);
+    #pragma unroll
+    for (uint32_t c1 = 0; c1 < 4; c1++) {
+      const uint4 v = blocks[(size_t)(c | (c1 << 2)) * nblocks + b];
+      o.x += v.x; o.y |= v.y; o.z |= v.z; o.w |= v.w;
+    }
+    if (b == tb && c == tail_base) {
+      if (to < 32u) o.y |= 1u << to; else if (to < 64u) o.z |= 1u << (to - 32u); else o.w |= 1u << (to - 64u);
+    }
+    tail1[(size_t) c * nblocks + b] = o;
+  }
+}
+
+/* last base of an odd-length read for both interval ends: one fetch from the tail table (the second only when R lies
+ * in another block), or the four-fetch derivation when the table could not be allocated */
+__device__ __forceinline__ void fm_tail_step(const uint4 *__restrict__ tail1, const uint4 *__restrict__ blocks, uint32_t nblocks, uint32_t c,
+                                             uint32_t &L, uint32_t &R, uint32_t tail_const, uint32_t tail_row, uint32_t tail_base)
+{
+  if (tail1) {
+    const uint32_t bL = fm_div96(L), bR = fm_div96(R);
+    const uint4 *base = tail1 + (size_t) c * nblocks;
+    const uint4 vL = fm_ldg16(base + bL);
+    const uint4 vR = (bL == bR) ? vL : fm_ldg16(base + bR);
+    L = fm_block_rank(vL, L - bL * FM_SB_ROWS);
+    R = fm_block_rank(vR, R - bR * FM_SB_ROWS);
+  } else {
+    L = fm_tail_rank(blocks, nblocks, c, L, tail_const, tail_row, tail_base);
+    R = fm_tail_rank(blocks, nblocks, c, R, tail_const, tail_row, tail_base);
+  }
 }
 
 /* cooperative staging of this CTA's packed reads: global [q][wpq] -> smem [q][wpq_pad] */
@@ -187,8 +232,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_task_kernel(const FmS
     #pragma unroll
     for (int i = 0; i < QPT; i++) {
       const uint32_t c = (myq[i][pos >> 5] >> (pos & 31u)) & 3u;
-      L[i] = fm_tail_rank(p.blocks, p.nblocks, c, L[i], p.tail_const[c], p.tail_row, p.tail_base);
-      R[i] = fm_tail_rank(p.blocks, p.nblocks, c, R[i], p.tail_const[c], p.tail_row, p.tail_base);
+      fm_tail_step(p.tail1, p.blocks, p.nblocks, c, L[i], R[i], p.tail_const[c], p.tail_row, p.tail_base);
     }
   }
 
@@ -275,7 +319,12 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_coop_kernel(const FmS
     #pragma unroll
     for (int i = 0; i < QPT; i++) {
       const uint32_t c = (myq[i][pos >> 5] >> (pos & 31u)) & 3u;
-      X[i] = fm_tail_rank(p.blocks, p.nblocks, c, X[i], p.tail_const[c], p.tail_row, p.tail_base);
+      if (p.tail1) {                                  /* the lanes of a pair share the fetch when L and R fall in one block */
+        const uint32_t b = fm_div96(X[i]);
+        X[i] = fm_block_rank(fm_ldg16(p.tail1 + (size_t) c * p.nblocks + b), X[i] - b * FM_SB_ROWS);
+      } else {
+        X[i] = fm_tail_rank(p.blocks, p.nblocks, c, X[i], p.tail_const[c], p.tail_row, p.tail_base);
+      }
     }
   }
 

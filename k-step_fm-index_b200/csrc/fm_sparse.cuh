@@ -56,6 +56,7 @@ struct FmSparseParams {
   uint32_t hops;              /* KS / k                                                            */
   unsigned long long *fetch_counters;  /* COUNT only: [0] sparse blocks, [1] SB96 blocks (leading + fallback), [2] overflow fallbacks */
   uint32_t has_tail, tail_row, tail_base, tail_const[4];
+  const uint4 *tail1;         /* tail table (fm_tail_table_kernel) or NULL */
   const uint2 *start;         /* (L,R) after the first start_steps sparse steps, indexed by their packed bits, or NULL */
   uint32_t start_steps;
 };
@@ -257,8 +258,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_kernel(const F
     #pragma unroll
     for (int i = 0; i < QPT; i++) {
       const uint32_t c = fm_read_field(myq[i], pos, 3u);
-      L[i] = fm_tail_rank(p.blocks, p.nblocks, c, L[i], p.tail_const[c], p.tail_row, p.tail_base);
-      R[i] = fm_tail_rank(p.blocks, p.nblocks, c, R[i], p.tail_const[c], p.tail_row, p.tail_base);
+      fm_tail_step(p.tail1, p.blocks, p.nblocks, c, L[i], R[i], p.tail_const[c], p.tail_row, p.tail_base);
     }
   }
 

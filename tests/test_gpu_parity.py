@@ -510,11 +510,15 @@ def test_unstream_kernel_equals_pack_kernel(pkg, length):
 
 
 @pytest.mark.skipif(not helpers.has_ref_tools(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("tail_table", [True, False])
 @pytest.mark.parametrize("length", [1, 3, 15, 17, 25, 33, 99, 101])
-def test_odd_read_length_on_2step_index_equals_1step_index(pkg, tmp_path, length):
+def test_odd_read_length_on_2step_index_equals_1step_index(pkg, tmp_path, monkeypatch, length, tail_table):
     """len % 2 == 1 on a 2-step index is undefined in the reference (it reads query[-1]).  Here the
     last base is consumed by a 1-step rank derived from the 2-step table; the result must be what the reference
-    searcher returns on the 1-step index of the SAME text (k=1 and k=2 agree wherever both are defined)."""
+    searcher returns on the 1-step index of the SAME text (k=1 and k=2 agree wherever both are defined).
+    Both forms of that rank are checked: the tail table (one block fetch, built by the first odd-length search on the
+    replica) and the four-fetch derivation it is made from ($FMGPU_TAIL_TABLE=0, or no memory for the table)."""
+    monkeypatch.setenv("FMGPU_TAIL_TABLE", "1" if tail_table else "0")
     n = 40_009
     text = helpers.synth_text(n, seed=31)
     p1 = helpers.build_reference_indexes(str(tmp_path / "k1"), text, 1, 64)
@@ -528,12 +532,15 @@ def test_odd_read_length_on_2step_index_equals_1step_index(pkg, tmp_path, length
         idx = pkg.DeviceIndex.from_image(np.fromfile(p2[tag], dtype=np.uint32))
         assert idx.meta.tail_valid == 1
         idx.fuse(4, 2)
+        idx.sparsify(4, 0, 0)
+        assert idx.meta.tail_bytes == 0                          # nothing is built before an odd length asks for it
         b = pkg.DeviceBatch(0, reads.size // length, length, 2)
         b.upload_ascii(reads)
         for v in (pkg.variant(pkg.MODE_TASK, 1), pkg.variant(pkg.MODE_TASK, 4), pkg.variant(pkg.MODE_COOP, 2), pkg.variant(pkg.MODE_FUSED, 1),
-                  pkg.variant(pkg.MODE_FUSED, 2)):
+                  pkg.variant(pkg.MODE_FUSED, 2), pkg.variant(pkg.MODE_SPARSE, 1), pkg.variant(pkg.MODE_SPARSE, 4)):
             b.search(idx, v)
             assert np.array_equal(b.download(), want), f"len {length} tag {tag} mode {v.mode} qpt {v.queries_per_thread}"
+        assert idx.meta.tail_bytes == (idx.meta.nbytes // 4 if tail_table else 0)
         b.free(); idx.free()
 
 

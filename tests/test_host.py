@@ -3,6 +3,7 @@ readers/writers keep the reference's formats and error behaviour (no compute cal
 import ctypes as C
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -223,3 +224,20 @@ def test_header_is_plain_c(built, tmp_path):
     helpers.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(helpers.ROOT, "include"), str(src),
                  "-L", os.path.dirname(pkg.LIB_PATH), "-lfmindex_b200", "-Wl,-rpath," + os.path.dirname(pkg.LIB_PATH), "-o", str(exe)])
     helpers.run([str(exe)])
+
+
+def test_ctypes_mirrors_match_the_header(built, tmp_path):
+    """The ctypes structures in the package must have the size and field offsets of include/fmindex_b200.h."""
+    import ctypes as C
+    pkg = helpers.pkg()
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "fmindex_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(fmgpu_index_meta_t), offsetof(fmgpu_index_meta_t, nbytes),\n'
+                   '  offsetof(fmgpu_index_meta_t, tail_const), offsetof(fmgpu_index_meta_t, sparse_bytes), offsetof(fmgpu_index_meta_t, tail_bytes),\n'
+                   '  sizeof(fmgpu_variant_t), sizeof(fmi_t), sizeof(qrys_t)); return 0; }\n')
+    exe = tmp_path / "sizes"
+    helpers.run(["gcc", "-std=c99", "-I", os.path.join(helpers.ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    m = pkg.fmgpu_index_meta_t
+    assert got == [C.sizeof(m), m.nbytes.offset, m.tail_const.offset, m.sparse_bytes.offset, m.tail_bytes.offset,
+                   C.sizeof(pkg.fmgpu_variant_t), C.sizeof(pkg.fmi_t), C.sizeof(pkg.qrys_t)]
