@@ -36,12 +36,27 @@ def launches(tag):
         a = agg.setdefault(r[ix["Kernel Name"]], [0, 0.0]); a[0] += 1; a[1] += ns; total += ns
     with open(os.path.join(PR, f"{tag}_launches.md"), "w") as f:
         f.write(f"# {tag}: ncu launch list of `python bench.py --steps 2 --warmup 3` (1 GPU, 2 Gbp index, 10 M reads)\n\n"
-                "`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` -- per-launch times are cold-cache and serialised;\n"
+                "`ncu --metrics gpu__time_duration.sum --clock-control none -c 3000` -- per-launch times are cold-cache and serialised;\n"
                 "compare SHARES.  Setup kernels (index build, re-block, probe, read synthesis) are outside bench.py's timed regions.\n\n"
                 "| total ms | launches | share | kernel |\n|---:|---:|---:|---|\n")
         for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| {t / 1e6:.3f} | {c} | {100 * t / total:.1f}% | `{k[:110]}` |\n")
         f.write(f"\nprofiled launches: {sum(c for c, _ in agg.values())}, total {total / 1e6:.1f} ms\n")
+        # the timed kernel by launch shape: whole-batch launches are bench.py's `value` region (one launch = one step, nothing else
+        # is launched there), the small grids are the 512 K-read chunks of the end-to-end pipeline
+        per = collections.OrderedDict()
+        for r in rows[1:]:
+            if r[ix["Metric Name"]] == "gpu__time_duration.sum" and "fm_search_sparse_kernel<2, 2, 4" in r[ix["Kernel Name"]]:
+                ns = float(r[ix["Metric Value"]]) * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}.get(r[ix["Metric Unit"]], 1)
+                per.setdefault(r[ix["Grid Size"]], []).append(ns)
+        if per:
+            f.write("\n## The timed kernel, `fm_search_sparse_kernel<2, 2, 4, 256, 3, 0>`, by grid\n\n"
+                    "| grid | launches | mean ms per launch | where |\n|---|---:|---:|---|\n")
+            for g, v in sorted(per.items(), key=lambda kv: -max(kv[1])):
+                big = max(v) > 1e6
+                f.write(f"| {g} | {len(v)} | {sum(v) / len(v) / 1e6:.3f} | "
+                        + ("`value` region: one launch over the rank's 10 M reads = one step (warm-up + timed steps); it is the only kernel "
+                           "launched there, i.e. 100 % of the step" if big else "end-to-end pipeline (`e2e`), one launch per 512 K-read chunk (or tail chunk)") + " |\n")
 
 
 def full(tag, name):
