@@ -58,14 +58,48 @@ INDEX_TAG = int(os.environ.get("FM_BENCH_TAG", "100"))    # on-disk layout the d
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while a timed region runs."""
+    """SM clock and throttle reasons of one GPU sampled WHILE a timed region runs.  The `value` region lasts tens of
+    milliseconds, so the sampler polls NVML from a thread every millisecond (nvidia_ml_py); if NVML cannot be loaded it
+    falls back to `nvidia-smi -lms 200`, started early enough to be running when the region begins."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu, self.proc, self.rows = gpu_index, None, []
+        self.nvml, self.handle, self.thread, self.run, self.samples, self.reason_bits = None, None, None, False, [], 0
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                phys = int(vis.split(",")[gpu_index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu_index
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        while self.run:
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.reason_bits |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def start(self):
+        if self.nvml:
+            self.run = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -78,6 +112,15 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml:
+            self.run = False
+            self.thread.join(timeout=1.0)
+            n, bits = self.nvml, self.reason_bits
+            names = (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                     ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap"))
+            reasons = sorted(name for name, const in names if bits & int(getattr(n, const, 0)))
+            return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": reasons, "samples": len(self.samples), "how": "NVML polled every ms during the timed region"}
         if self.proc:
             time.sleep(0.25)
             self.proc.terminate()
@@ -90,7 +133,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "how": "nvidia-smi -lms 200"}
 
 
 def measured_peak():
@@ -431,7 +474,10 @@ def main():
             "lf_steps_per_s": world * lf_steps / (ms_step * 1e-3),
             "config": {"workload": workload,
                        "kernel": (f"sparse: {meta.sparse_bases} bases/step, {32 * meta.sparse_lanes}-byte blocks of occurrence rows (lambda {meta.sparse_lambda}), {meta.sparse_lanes} x 256-bit loads, "
-                                  f"{meta.sparse_start_bases}-base start table, qpt={var.queries_per_thread}" if sparse else
+                                  f"{meta.sparse_start_bases}-base start table, "
+                                  + (f"uniform grid ({meta.sparse_uniform_nb} blocks per symbol, no directory lookup: the text's symbol counts are even), " if meta.sparse_uniform_nb
+                                     else "per-symbol block counts + L2-resident directory, ")
+                                  + f"qpt={var.queries_per_thread}" if sparse else
                                   f"fused: {meta.fused_bases} bases/step, {32 * meta.fused_lanes}-byte blocks, {meta.fused_lanes} x 256-bit loads, qpt={var.queries_per_thread}"
                                   if fused else f"{MODE} qpt={var.queries_per_thread} tpb={var.threads_per_block}"),
                        "device_layout": (f"sparse-step table {meta.sparse_bytes / 1e9:.1f} GB ({meta.sparse_blocks} blocks, {meta.sparse_overflow} overfull -> SB96 steps) "

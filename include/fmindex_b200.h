@@ -222,6 +222,11 @@ typedef struct {
    * block fetch instead of four; built on this replica by its first odd-length search (a quarter of nbytes), 0 = not
    * built (yet, or $FMGPU_TAIL_TABLE=0, or no memory: the four-fetch derivation is used) */
   uint64_t tail_bytes;
+  /* sparse-step table laid out as a uniform grid: every wide symbol owns this many blocks and the kernel computes a
+   * symbol's first block instead of looking it up (chosen when all symbols occur about equally often, i.e. on
+   * uniformly random texts; $FMGPU_SPARSE_UNIFORM=0/1 forces); 0 = per-symbol block counts and a directory */
+  uint32_t sparse_uniform_nb;
+  uint32_t reserved0;
 } fmgpu_index_meta_t;
 
 /* devices ---------------------------------------------------------------- */

@@ -36,6 +36,7 @@ struct fmgpu_index {
   uint2             *sdir;         /* its directory: { first block, scale } per wide symbol */
   uint2             *sstart;       /* start table of the sparse kernel, or NULL */
   uint4             *tail1;        /* tail table (fm_tail_table_kernel): built by the first odd-length search on this replica */
+  uint32_t           s_uni_nb, s_uni_scale;   /* sparse table is a uniform grid: blocks per symbol and the one scale (0 = directory) */
   int                tail1_tried;  /* 1 once that build was attempted (a failed allocation is not retried)               */
 };
 
@@ -297,6 +298,7 @@ extern "C" int32_t fmgpu_index_alloc_like(int32_t device, const fmgpu_index_meta
   idx->meta.fused_bases = 0; idx->meta.fused_lanes = 0; idx->meta.fused_bytes = 0; idx->meta.start_bases = 0;
   idx->meta.sparse_bases = 0; idx->meta.sparse_lambda = 0; idx->meta.sparse_bytes = 0; idx->meta.sparse_blocks = 0;
   idx->meta.sparse_overflow = 0; idx->meta.sparse_start_bases = 0; idx->meta.sparse_lanes = 0; idx->meta.tail_bytes = 0;
+  idx->meta.sparse_uniform_nb = 0;
   cudaError_t e = cudaMalloc((void **) &idx->blocks, meta->nbytes);
   if (e != cudaSuccess) { free(idx); return fm_fail(e, "cudaMalloc(SB96 replica)", __FILE__, __LINE__); }
   *out = idx;
@@ -548,6 +550,7 @@ extern "C" int32_t fmgpu_index_unsparsify(fmgpu_index_t *idx)
     cudaFree(idx->sblocks); cudaFree(idx->sdir); cudaFree(idx->sstart);
     idx->sblocks = NULL; idx->sdir = NULL; idx->sstart = NULL;
   }
+  idx->s_uni_nb = 0; idx->s_uni_scale = 0; idx->meta.sparse_uniform_nb = 0;
   idx->meta.sparse_bases = 0; idx->meta.sparse_lambda = 0; idx->meta.sparse_bytes = 0; idx->meta.sparse_blocks = 0;
   idx->meta.sparse_overflow = 0; idx->meta.sparse_start_bases = 0; idx->meta.sparse_lanes = 0;
   return FM_SUCCESS;
@@ -614,8 +617,30 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
     fm_sparse_symstart_kernel<<<(nsym + 1 + 255) / 256, 256>>>(keys2, n, nsym, symstart);
     e = cudaGetLastError();
   }
+  /* uniform grid or per-symbol block counts?  $FMGPU_SPARSE_UNIFORM = 0 / 1 forces; default: uniform when every symbol's
+   * occurrence count lies within 20 % of the mean (then a uniform grid overflows no more blocks than per-symbol counts) */
+  uint32_t uni_nb = 0, uni_scale = 0;
   if (e == cudaSuccess) {
-    fm_sparse_nblocks_kernel<<<(nsym + 255) / 256, 256>>>(symstart, nsym, lambda, nb);
+    uint32_t range[2] = { 0xFFFFFFFFu, 0u }, carrying = 0;
+    uint32_t *d_range = first;                                 /* scratch: `first` is written by the scan below */
+    e = cudaMemcpy(d_range, range, 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { fm_sparse_count_range_kernel<<<(nsym + 255) / 256, 256>>>(symstart, nsym, d_range); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpy(range, d_range, 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(&carrying, symstart + nsym, 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) {
+      const double mean = (double) carrying / nsym;
+      const char *env = getenv("FMGPU_SPARSE_UNIFORM");
+      const bool want = env && *env ? atoi(env) != 0 : (mean >= lambda && range[0] >= 0.8 * mean && range[1] <= 1.2 * mean);
+      const uint64_t per = ((uint64_t) carrying + (uint64_t) nsym * lambda - 1) / ((uint64_t) nsym * lambda);
+      if (want && per >= 1 && per * nsym < (1ull << 32)) {
+        uni_nb = (uint32_t) per;
+        unsigned long long sc = ((((unsigned long long) uni_nb) << 32) - 1ull) / n;    /* as fm_sparse_dir_kernel */
+        uni_scale = sc > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t) sc;
+      }
+    }
+  }
+  if (e == cudaSuccess) {
+    fm_sparse_nblocks_kernel<<<(nsym + 255) / 256, 256>>>(symstart, nsym, lambda, uni_nb, nb);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, nb, first, (int) nsym);
@@ -643,7 +668,7 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
   cudaFree(sym); cudaFree(keys); cudaFree(rows); cudaFree(keys2); cudaFree(rows2); cudaFree(symstart); cudaFree(nb); cudaFree(first);
   cudaFree(rank0); cudaFree(tmp); cudaFree(d_novf);
   if (e != cudaSuccess) { cudaFree(sblocks); cudaFree(dir); return fm_fail(e, "fmgpu_index_sparsify", __FILE__, __LINE__); }
-  idx->sblocks = sblocks; idx->sdir = dir;
+  idx->sblocks = sblocks; idx->sdir = dir; idx->s_uni_nb = uni_nb; idx->s_uni_scale = uni_scale; idx->meta.sparse_uniform_nb = uni_nb;
   idx->meta.sparse_bases = ks; idx->meta.sparse_lambda = lambda; idx->meta.sparse_blocks = total_blocks;
   idx->meta.sparse_overflow = novf; idx->meta.sparse_bytes = total_blocks * bbytes + 8ull * nsym; idx->meta.sparse_lanes = lanes;
 
@@ -694,6 +719,7 @@ static int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_pack
   p.nlead = (len / k) % hops; p.nsteps = (len / k) / hops;
   p.wpq = fmgpu_words_per_query(len); p.bwtsize = idx->meta.bwtsize;
   p.sbits = 2 * ks; p.hops = hops;
+  p.uni_nb = idx->s_uni_nb; p.uni_scale = idx->s_uni_scale;
   p.fetch_counters = d_counters;
   p.start = idx->sstart; p.start_steps = idx->sstart ? idx->meta.sparse_start_bases / ks : 0u;
   p.has_tail = len % k; p.tail_row = idx->meta.tail_row; p.tail_base = idx->meta.tail_base;

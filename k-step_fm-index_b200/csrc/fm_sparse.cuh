@@ -19,6 +19,10 @@
  *                           (31 slots in a 128-byte block, LANES = 4; 15 in a 64-byte block, LANES = 2)
  *                           a bucket with more occurrences than slots stores 0xFFFFFFFE in the last word instead
  *   directory               dir[sigma] = { first block, scale }     (8 bytes x 4^KS: L2-resident for KS <= 10)
+ *   uniform grid            when every symbol occurs about equally often (a uniformly random text: counts within 20 % of
+ *                           their mean) all symbols get the SAME number of blocks, first block = sigma * nb, one scale:
+ *                           the directory lookup -- an L2 request per step that costs 15 % of the fetch rate -- is
+ *                           replaced by a multiplication.  Skewed texts (any real genome) keep per-symbol block counts.
  *
  *   one rank     = dir[sigma] (L2 hit; sigma is known in advance, the lookup is issued one step ahead)
  *                  + ONE block fetch by LANES lanes x 256 bits;  rank = word 0 + #{ entries < X }
@@ -57,9 +61,18 @@ struct FmSparseParams {
   unsigned long long *fetch_counters;  /* COUNT only: [0] sparse blocks, [1] SB96 blocks (leading + fallback), [2] overflow fallbacks */
   uint32_t has_tail, tail_row, tail_base, tail_const[4];
   const uint4 *tail1;         /* tail table (fm_tail_table_kernel) or NULL */
+  uint32_t uni_nb, uni_scale; /* uniform grid (every symbol owns uni_nb blocks, first block = sigma * uni_nb): no directory
+                                 lookup; 0 = per-symbol block counts, read from dir                                  */
   const uint2 *start;         /* (L,R) after the first start_steps sparse steps, indexed by their packed bits, or NULL */
   uint32_t start_steps;
 };
+
+/* directory entry { first block, scale } of a wide symbol: computed when the table is a uniform grid, else one L2-resident
+ * lookup (which costs request slots beside the block fetches: profiles/r01_hit_miss_mix.md) */
+__device__ __forceinline__ uint2 fm_sparse_dir(const FmSparseParams &p, uint32_t sig)
+{
+  return p.uni_nb ? make_uint2(sig * p.uni_nb, p.uni_scale) : __ldg(p.dir + sig);
+}
 
 __device__ __forceinline__ void fm_ldg32_line(const uint4 *p, uint32_t (&w)[8])
 {
@@ -172,7 +185,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_kernel(const F
   uint2 d[QPT];
   if (step0 < p.nsteps) {
     #pragma unroll
-    for (int i = 0; i < QPT; i++) { sig[i] = fm_read_field(myq[i], pos, smask); d[i] = __ldg(p.dir + sig[i]); }
+    for (int i = 0; i < QPT; i++) { sig[i] = fm_read_field(myq[i], pos, smask); d[i] = fm_sparse_dir(p, sig[i]); }
   }
   for (uint32_t step = step0; step < p.nsteps; step++) {
     uint32_t w[QPT][8];
@@ -193,7 +206,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_kernel(const F
     #pragma unroll
     for (int i = 0; i < QPT; i++) {
       sig_now[i] = sig[i];
-      if (step + 1 < p.nsteps) { sig[i] = fm_read_field(myq[i], pos, smask); d[i] = __ldg(p.dir + sig[i]); }
+      if (step + 1 < p.nsteps) { sig[i] = fm_read_field(myq[i], pos, smask); d[i] = fm_sparse_dir(p, sig[i]); }
     }
     uint32_t cL[QPT], cR[QPT];
     bool ovf[QPT];
@@ -311,13 +324,27 @@ __global__ void fm_sparse_symstart_kernel(const uint32_t *__restrict__ keys, uin
   symstart[s] = lo;
 }
 
-/* blocks per symbol */
-__global__ void fm_sparse_nblocks_kernel(const uint32_t *__restrict__ symstart, uint32_t nsym, uint32_t lambda, uint32_t *__restrict__ nb)
+/* smallest and largest occurrence count over the symbols: range[0] (preset to 0xFFFFFFFF) and range[1] (preset to 0) */
+__global__ void fm_sparse_count_range_kernel(const uint32_t *__restrict__ symstart, uint32_t nsym, uint32_t *__restrict__ range)
+{
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+  if (s < nsym) lo = hi = symstart[s + 1] - symstart[s];
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
+  }
+  if ((threadIdx.x & 31u) == 0) { atomicMin(range, lo); atomicMax(range + 1, hi); }
+}
+
+/* blocks per symbol: ceil(count / lambda), or the same `uniform_nb` for every symbol (uniform grid) */
+__global__ void fm_sparse_nblocks_kernel(const uint32_t *__restrict__ symstart, uint32_t nsym, uint32_t lambda, uint32_t uniform_nb,
+                                         uint32_t *__restrict__ nb)
 {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nsym) return;
   const uint32_t cnt = symstart[s + 1] - symstart[s];
-  nb[s] = cnt ? (cnt + lambda - 1) / lambda : 1u;
+  nb[s] = uniform_nb ? uniform_nb : (cnt ? (cnt + lambda - 1) / lambda : 1u);
 }
 
 /* directory entry and rank_F(sigma, 0) of every symbol */

@@ -27,10 +27,13 @@ def widths(k):
     return [2, 3, 5, 6, 10, 12] if k == 1 else [4, 6, 10, 12]
 
 
+@pytest.mark.parametrize("uniform", ["0", "1"], ids=["directory", "uniform_grid"])
 @pytest.mark.parametrize("path", [p for p in GOLDEN if "quirk" not in p], ids=lambda p: os.path.basename(p))
-def test_sparse_steps_golden_all_widths(pkg, path):
+def test_sparse_steps_golden_all_widths(pkg, monkeypatch, path, uniform):
     """Committed outputs of the unmodified reference searchers; every width, both block sizes, every qpt,
-    lambda from 1 (almost no overflow) to the slot count (many overfull blocks -> SB96 fallback)."""
+    lambda from 1 (almost no overflow) to the slot count (many overfull blocks -> SB96 fallback); per-symbol block
+    counts with a directory, and the uniform grid (same block count for every symbol, no directory lookup)."""
+    monkeypatch.setenv("FMGPU_SPARSE_UNIFORM", uniform)
     g = np.load(path)
     reads, length, k = g["reads"], int(g["length"]), int(g["k"])
     nq = reads.size // length
@@ -43,6 +46,9 @@ def test_sparse_steps_golden_all_widths(pkg, path):
                     idx = pkg.DeviceIndex.from_image(g[f"image_{tag}"]).sparsify(ks, lam, lanes)
                     m = idx.meta
                     assert (m.sparse_bases, m.sparse_lambda, m.sparse_lanes) == (ks, lam, lanes)
+                    assert (m.sparse_uniform_nb > 0) == (uniform == "1")
+                    if m.sparse_uniform_nb:
+                        assert m.sparse_blocks == m.sparse_uniform_nb * 4 ** ks
                     assert m.sparse_bytes == m.sparse_blocks * 32 * lanes + 8 * 4 ** ks + (8 * 4 ** m.sparse_start_bases if m.sparse_start_bases else 0)
                     for qpt in (1, 2, 3, 4):
                         b.search(idx, pkg.variant(pkg.MODE_SPARSE, qpt))
@@ -110,10 +116,15 @@ def test_sparse_unavailable_and_errors(pkg):
 @pytest.mark.skipif(not helpers.has_ref_tools(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("name", ["polyA", "ACGT_period4", "two_letter", "repeat_x40", "random_plus_repeat"])
 @pytest.mark.parametrize("k", [1, 2])
-def test_sparse_steps_repetitive_texts_overflow_fallback(pkg, tmp_path, name, k):
+@pytest.mark.parametrize("uniform", ["auto", "1"], ids=["auto", "uniform_grid_forced"])
+def test_sparse_steps_repetitive_texts_overflow_fallback(pkg, tmp_path, monkeypatch, name, k, uniform):
     """Repeats put hundreds of occurrences of one wide symbol into consecutive BWT rows: those blocks are overfull and
     the kernel must serve them through ordinary steps on the SB96 table.  Index files and expected (L,R) from the
     unmodified reference tools."""
+    if uniform == "1":
+        monkeypatch.setenv("FMGPU_SPARSE_UNIFORM", "1")
+    else:
+        monkeypatch.delenv("FMGPU_SPARSE_UNIFORM", raising=False)
     rng = np.random.default_rng(11)
     n = 30011
     unit = ACGT[rng.integers(0, 4, 700)]
@@ -140,6 +151,8 @@ def test_sparse_steps_repetitive_texts_overflow_fallback(pkg, tmp_path, name, k)
         for lanes in (2, 4):
             idx.sparsify(ks, 0, lanes)
             saw_overflow |= idx.meta.sparse_overflow > 0
+            if uniform == "auto":                                  # skewed symbol counts: never a uniform grid by default
+                assert idx.meta.sparse_uniform_nb == 0, name
             for qpt in (1, 4):
                 b.search(idx, pkg.variant(pkg.MODE_SPARSE, qpt))
                 assert np.array_equal(b.download(), want), f"{name} k={k} ks={ks} lanes={lanes} qpt={qpt}"
@@ -197,6 +210,38 @@ def test_sparse_start_table_and_fetch_counter(pkg, k):
             assert 9 * nq <= a.value <= 9.05 * nq                # 10-base start table + 9 sparse steps, L and R in one bucket
             assert s.value <= 0.2 * nq and o.value <= 0.05 * nq  # overfull blocks are rare on a random text
     idx.free()
+
+
+def test_sparse_uniform_grid_is_chosen_for_even_symbol_counts_only(pkg, monkeypatch):
+    """Default choice of the layout: a uniform grid (no directory lookups) when every wide symbol occurs within 20 % of
+    the mean -- a uniformly random text with many rows per symbol -- and per-symbol block counts otherwise.  Same (L,R)."""
+    monkeypatch.delenv("FMGPU_SPARSE_UNIFORM", raising=False)
+    n = 4_000_000
+    build = pkg.IndexBuild.from_synth(n, 1, 2, 64)
+    idx = build.to_index()
+    build.free()
+    reads = np.concatenate([ACGT[np.random.default_rng(3).integers(0, 4, 40_000 * 50)]])
+    import torch
+    d_ascii = torch.empty(60_000 * 50, dtype=torch.uint8, device="cuda")
+    pkg.check(pkg.lib().fmgpu_synth_reads_device(0, n, 1, 60_000, 50, 2, 0, d_ascii.data_ptr(), None), "reads")
+    torch.cuda.synchronize()
+    reads = np.concatenate([d_ascii.cpu().numpy(), reads])
+    b = pkg.DeviceBatch(0, reads.size // 50, 50, 2)
+    b.upload_ascii(reads)
+    b.search(idx, pkg.variant(pkg.MODE_COOP))
+    want = b.download()
+    assert (want[1:120_000:2] > want[0:120_000:2]).all()         # the exact reads are found
+    for ks, expect_uniform in ((6, True), (10, False)):          # 977 rows per 6-mer (+-3 %), 3.8 per 10-mer (+-50 %)
+        idx.sparsify(ks, 0, 0)
+        m = idx.meta
+        assert (m.sparse_uniform_nb > 0) == expect_uniform, (ks, m.sparse_uniform_nb)
+        if expect_uniform:
+            assert m.sparse_blocks == m.sparse_uniform_nb * 4 ** ks and m.sparse_overflow < m.sparse_blocks // 1000
+        for qpt in (1, 4):
+            b.search(idx, pkg.variant(pkg.MODE_SPARSE, qpt))
+            assert np.array_equal(b.download(), want), (ks, qpt)
+        idx.unsparsify()
+    b.free(); idx.free()
 
 
 def test_sparse_config3_full_size_against_reference_checksums(pkg):
