@@ -617,8 +617,9 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
     fm_sparse_symstart_kernel<<<(nsym + 1 + 255) / 256, 256>>>(keys2, n, nsym, symstart);
     e = cudaGetLastError();
   }
-  /* uniform grid or per-symbol block counts?  $FMGPU_SPARSE_UNIFORM = 0 / 1 forces; default: uniform when every symbol's
-   * occurrence count lies within 20 % of the mean (then a uniform grid overflows no more blocks than per-symbol counts) */
+  /* uniform grid or per-symbol block counts?  $FMGPU_SPARSE_UNIFORM = 0 / 1 forces; default: uniform when no symbol occurs
+   * more than 1.35 x as often as the mean (its blocks then expect <= 6.75 rows at lambda 5: < 0.2 % of them overflow 15
+   * slots, far cheaper than a directory lookup in every step) nor less than half as often (wasted blocks) */
   uint32_t uni_nb = 0, uni_scale = 0;
   if (e == cudaSuccess) {
     uint32_t range[2] = { 0xFFFFFFFFu, 0u }, carrying = 0;
@@ -630,7 +631,7 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
     if (e == cudaSuccess) {
       const double mean = (double) carrying / nsym;
       const char *env = getenv("FMGPU_SPARSE_UNIFORM");
-      const bool want = env && *env ? atoi(env) != 0 : (mean >= lambda && range[0] >= 0.8 * mean && range[1] <= 1.2 * mean);
+      const bool want = env && *env ? atoi(env) != 0 : (mean >= lambda && range[0] >= 0.5 * mean && range[1] <= 1.35 * mean);
       const uint64_t per = ((uint64_t) carrying + (uint64_t) nsym * lambda - 1) / ((uint64_t) nsym * lambda);
       if (want && per >= 1 && per * nsym < (1ull << 32)) {
         uni_nb = (uint32_t) per;

@@ -213,8 +213,9 @@ def test_sparse_start_table_and_fetch_counter(pkg, k):
 
 
 def test_sparse_uniform_grid_is_chosen_for_even_symbol_counts_only(pkg, monkeypatch):
-    """Default choice of the layout: a uniform grid (no directory lookups) when every wide symbol occurs within 20 % of
-    the mean -- a uniformly random text with many rows per symbol -- and per-symbol block counts otherwise.  Same (L,R)."""
+    """Default choice of the layout: a uniform grid (no directory lookups) when no wide symbol occurs more than 1.35 x as
+    often as the mean (nor less than half) -- a uniformly random text with many rows per symbol -- and per-symbol block
+    counts otherwise.  Same (L,R)."""
     monkeypatch.delenv("FMGPU_SPARSE_UNIFORM", raising=False)
     n = 4_000_000
     build = pkg.IndexBuild.from_synth(n, 1, 2, 64)
