@@ -359,7 +359,7 @@ static const uint4 *fm_ensure_tail(const fmgpu_index_t *cidx, cudaStream_t strea
   if (env && *env && atoi(env) == 0) return NULL;
   const uint32_t nb = idx->meta.nblocks;
   uint4 *t = NULL;
-  if (cudaMalloc((void **) &t, (size_t) 4 * nb * sizeof(uint4)) != cudaSuccess) { cudaGetLastError(); return NULL; }
+  if (cudaSetDevice(idx->device) != cudaSuccess || cudaMalloc((void **) &t, (size_t) 4 * nb * sizeof(uint4)) != cudaSuccess) { cudaGetLastError(); return NULL; }
   const uint32_t *tc = idx->meta.tail_const;
   fm_tail_table_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(idx->blocks, nb, tc[0], tc[1], tc[2], tc[3], idx->meta.tail_row, idx->meta.tail_base, t);
   /* waited for once: later searches may come on other streams */
