@@ -453,6 +453,48 @@ def main():
     same_packed = bool(np.array_equal(h_res2.numpy().view(np.uint32), res_dev))
     hits_ok = bool(((res_dev[1::2] - res_dev[0::2]) >= 1).all())      # every exact read occurs in the text
 
+    # extra (not the headline): locate -- (L,R) -> text positions through the suffix array derived from the index table
+    locate = None
+    if os.environ.get("FM_BENCH_LOCATE", "1") != "0":
+        try:
+            t0 = time.time()
+            index.build_sa()
+            torch.cuda.synchronize()
+            sa_s = time.time() - t0
+            d_pos = torch.empty(nq, dtype=torch.int32, device="cuda")
+            d_cnt = torch.empty(nq, dtype=torch.int32, device="cuda")
+
+            def locate_step():
+                pkg.check(L.fmgpu_locate_device(index.handle, d_res.data_ptr(), nq, 1, d_pos.data_ptr(), d_cnt.data_ptr(), stream), "locate")
+
+            for _ in range(3):
+                locate_step()
+            le0, le1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            le0.record()
+            for _ in range(5):
+                locate_step()
+            le1.record(); torch.cuda.synchronize()
+            # reads found exactly once must be located where they were cut from (fm_synth.h: fm_synth_read_start)
+            j = np.arange(first, first + nq, dtype=np.uint64)
+            with np.errstate(over="ignore"):
+                x = ((np.uint64(SEED_READS) ^ np.uint64(0xA5A5A5A55A5A5A5A)) + j + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+                x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+                x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+                x = x ^ (x >> np.uint64(31))
+            starts = x % np.uint64(N_TEXT - READ_LEN + 1)
+            cnt = d_cnt.cpu().numpy().view(np.uint32)
+            pos = d_pos.cpu().numpy().view(np.uint32)
+            once = cnt == 1
+            locate = {"suffix_array_build_s": round(sa_s, 3), "suffix_array_gb": index.meta.sa_bytes / 1e9,
+                      "ms_per_step": le0.elapsed_time(le1) / 5, "mqueries_per_s_per_gpu": nq / (le0.elapsed_time(le1) / 5) / 1e3,
+                      "reads_found_once": float(once.mean()),
+                      "positions_equal_read_starts": bool(np.array_equal(pos[once].astype(np.uint64), starts[once])),
+                      "note": "extra, not the headline: SA derived on the GPU from the index table by list ranking over its LF mapping "
+                              "(no SA in the reference's files), one gather per read"}
+            index.drop_sa()
+        except pkg.FMError as ex:
+            locate = {"unavailable": str(ex)}
+
     # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N=1)
     cpu = None
     parity = None
@@ -515,6 +557,7 @@ def main():
             "e2e_packed_input": {"value": world * nq / e2e_packed_ms_step / 1e3, "unit": "Mqueries/s", "ms_per_step": e2e_packed_ms_step,
                                  "h2d_bytes_per_step": nq * wpq * 4, "d2h_bytes_per_step": nq * 8, "matches_device_resident_result": same_packed,
                                  "note": "extra, not the headline: fmgpu_search_host_packed, host reads already in the 2-bit binary format (28 B per 100-bp read)"},
+            "locate": locate,
             "gpu_launches": args.steps,
             "clocks": clocks,
             "checks": {"every_read_found": hits_ok, "e2e_equals_resident": same, "gpu_equals_reference_cpu_on_sample": parity},

@@ -227,6 +227,7 @@ typedef struct {
    * uniformly random texts; $FMGPU_SPARSE_UNIFORM=0/1 forces); 0 = per-symbol block counts and a directory */
   uint32_t sparse_uniform_nb;
   uint32_t reserved0;
+  uint64_t sa_bytes;           /* suffix array kept for locate (fmgpu_index_build_sa): 4 bytes per BWT row, 0 = none */
 } fmgpu_index_meta_t;
 
 /* devices ---------------------------------------------------------------- */
@@ -358,6 +359,24 @@ const char *fmgpu_build_last_error(void);
 /* reads of fm_synth.h (exact substrings, uniform start) as ASCII into device memory */
 int32_t  fmgpu_synth_reads_device(int32_t device, uint64_t n, uint64_t seed_ref, uint64_t nqueries, uint32_t len,
                                   uint64_t seed_reads, uint64_t first, char *d_ascii, void *stream);
+
+/* locate (the reference stops at (L,R)) ----------------------
+ * fmgpu_index_build_sa derives the full suffix array SA[0 .. bwtsize) of the indexed text from the replica's own
+ * table -- so it works for index FILES, which carry no SA: SA[r] = number of 1-step LF steps from row r to the '$'
+ * row, by list ranking over the LF permutation on the GPU (csrc/fm_locate.cuh).  4 bytes per row stay resident
+ * (8 GB for 2 Gbp), 16 bytes per row of scratch while it is built.  FM_E_NOT_IMPLEMENTED for an AltCounters index
+ * carrying the padding quirk, or when memory does not suffice.
+ * fmgpu_locate_device turns intervals into text positions: positions[q * max_hits + j] = start (0-based) of the
+ * j-th occurrence of read q in suffix-array order, 0xFFFFFFFF beyond min(R - L, max_hits); nhits[q] = R - L (may
+ * be NULL).  d_results is what the search wrote ([2q] = L, [2q+1] = R). */
+int32_t fmgpu_index_build_sa(fmgpu_index_t *idx);
+int32_t fmgpu_index_drop_sa(fmgpu_index_t *idx);
+void   *fmgpu_index_sa(const fmgpu_index_t *idx);          /* device pointer to SA, or NULL */
+int32_t fmgpu_locate_device(const fmgpu_index_t *idx, const uint32_t *d_results, uint64_t nqueries, uint32_t max_hits,
+                            uint32_t *d_positions, uint32_t *d_nhits, void *stream);
+/* the same for a shard (its own (L,R), its stream), positions [nqueries][max_hits] and hit counts to host memory */
+int32_t fmgpu_batch_locate(const fmgpu_index_t *idx, fmgpu_batch_t *b, uint32_t max_hits, uint32_t *h_positions, uint32_t *h_nhits);
+int32_t fmgpu_index_download_sa(const fmgpu_index_t *idx, uint32_t *h_sa);   /* bwtsize words */
 
 /* HBM random-access roofline probe: independent uniformly random 16-byte
  * loads over a table of `table_bytes`, full occupancy.  Returns loads/s. */

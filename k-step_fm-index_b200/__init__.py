@@ -74,7 +74,7 @@ class fmgpu_index_meta_t(C.Structure):
                 ("sparse_bases", C.c_uint32), ("sparse_lambda", C.c_uint32), ("sparse_bytes", C.c_uint64),
                 ("sparse_blocks", C.c_uint64), ("sparse_overflow", C.c_uint64), ("sparse_start_bases", C.c_uint32),
                 ("sparse_lanes", C.c_uint32), ("tail_bytes", C.c_uint64),
-                ("sparse_uniform_nb", C.c_uint32), ("reserved0", C.c_uint32)]
+                ("sparse_uniform_nb", C.c_uint32), ("reserved0", C.c_uint32), ("sa_bytes", C.c_uint64)]
 
 
 _VP, _VPP = C.c_void_p, C.POINTER(C.c_void_p)
@@ -115,6 +115,12 @@ PROTOTYPES = {
     "fmgpu_index_unfuse": (C.c_int32, [_VP]),
     "fmgpu_index_sparsify": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, C.c_uint32]),
     "fmgpu_index_unsparsify": (C.c_int32, [_VP]),
+    "fmgpu_index_build_sa": (C.c_int32, [_VP]),
+    "fmgpu_index_drop_sa": (C.c_int32, [_VP]),
+    "fmgpu_index_sa": (_VP, [_VP]),
+    "fmgpu_index_download_sa": (C.c_int32, [_VP, _VP]),
+    "fmgpu_locate_device": (C.c_int32, [_VP, _VP, C.c_uint64, C.c_uint32, _VP, _VP, _VP]),
+    "fmgpu_batch_locate": (C.c_int32, [_VP, _VP, C.c_uint32, _VP, _VP]),
     "fmgpu_index_get_meta": (C.c_int32, [_VP, C.POINTER(fmgpu_index_meta_t)]),
     "fmgpu_index_blocks": (_VP, [_VP]),
     "fmgpu_index_device": (C.c_int32, [_VP]),
@@ -325,6 +331,19 @@ class DeviceIndex:
     def unsparsify(self):
         check(lib().fmgpu_index_unsparsify(self.handle), "fmgpu_index_unsparsify")
 
+    def build_sa(self):
+        """Derives the suffix array of the indexed text from this replica's own table (needed by locate)."""
+        check(lib().fmgpu_index_build_sa(self.handle), "fmgpu_index_build_sa")
+        return self
+
+    def drop_sa(self):
+        check(lib().fmgpu_index_drop_sa(self.handle), "fmgpu_index_drop_sa")
+
+    def download_sa(self):
+        out = np.empty(int(self.meta.bwtsize), dtype=np.uint32)
+        check(lib().fmgpu_index_download_sa(self.handle, out.ctypes.data), "fmgpu_index_download_sa")
+        return out
+
     def replicate(self, device):
         h = C.c_void_p()
         check(lib().fmgpu_index_replicate(self.handle, device, C.byref(h)), "fmgpu_index_replicate")
@@ -388,6 +407,14 @@ class DeviceBatch:
         out = np.empty(2 * self.nq, dtype=np.uint32)
         check(lib().fmgpu_batch_download(self.handle, out.ctypes.data), "fmgpu_batch_download")
         return out
+
+    def locate(self, index, max_hits):
+        """Text positions of the occurrences of every read after a search: (positions [nq, max_hits] in suffix-array
+        order, 0xFFFFFFFF beyond the hits; nhits [nq] = R - L)."""
+        pos = np.empty((self.nq, max_hits), dtype=np.uint32)
+        nhits = np.empty(self.nq, dtype=np.uint32)
+        check(lib().fmgpu_batch_locate(index.handle, self.handle, max_hits, pos.ctypes.data, nhits.ctypes.data), "fmgpu_batch_locate")
+        return pos, nhits
 
     def free(self):
         if self.handle:

@@ -1,0 +1,154 @@
+"""GPU tests of locate (csrc/fm_locate.cuh): the suffix array derived from the index table by list ranking over its LF
+mapping, and SA[L..R) gathers.  The reference stops at (L,R) (src/fmIndexCPUBaseline.c:288-290), so the checker here is
+brute force on the text: sorted suffixes for the suffix array, a scan for the occurrences of a read.   pytest -m gpu"""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+@pytest.fixture(scope="module")
+def pkg(built):
+    p = helpers.pkg()
+    assert p.lib().fmgpu_device_count() >= 1, "no sm_100 GPU: the product has no CPU fallback"
+    return p
+
+
+def brute_force_sa(text):
+    """Suffix array of text + '$' with '$' (end of text) smallest: row 0 is the empty suffix n."""
+    t = text.tobytes()
+    return np.array(sorted(range(len(t) + 1), key=lambda i: t[i:]), dtype=np.uint32)
+
+
+def occurrences(text_bytes, read_bytes):
+    out, i = [], text_bytes.find(read_bytes)
+    while i >= 0:
+        out.append(i)
+        i = text_bytes.find(read_bytes, i + 1)
+    return out
+
+
+@pytest.mark.parametrize("k", [1, 2])
+def test_suffix_array_from_index_files_equals_sorted_suffixes(pkg, k):
+    """Committed index files written by the reference tools (all four layouts): the SA derived from the device table
+    must be the suffix array of the text they index; reads cut to 6 bases occur several times each."""
+    g = np.load(os.path.join(helpers.ROOT, "tests", "golden", f"small_k{k}_d64.npz"))
+    n = int(g["n"])
+    text = helpers.synth_text(n, seed=7 + k)
+    want = brute_force_sa(text)
+    tb = text.tobytes()
+    length = int(g["length"])
+    short = np.ascontiguousarray(g["reads"].reshape(-1, length)[:600, :6]).reshape(-1)
+    for tag in (100, 101, 200, 201):
+        idx = pkg.DeviceIndex.from_image(g[f"image_{tag}"])
+        assert idx.meta.sa_bytes == 0
+        idx.build_sa()
+        assert idx.meta.sa_bytes == 4 * (n + 1)
+        assert np.array_equal(idx.download_sa(), want), f"tag {tag}"
+        b = pkg.DeviceBatch(0, 600, 6, k)
+        b.upload_ascii(short)
+        b.search(idx)
+        lr = b.download().reshape(-1, 2)
+        pos, nhits = b.locate(idx, 64)
+        assert np.array_equal(nhits, np.maximum(lr[:, 1].astype(np.int64) - lr[:, 0], 0).astype(np.uint32))
+        for q in range(600):
+            occ = occurrences(tb, short[6 * q: 6 * q + 6].tobytes())
+            assert nhits[q] == len(occ)
+            got = pos[q, : min(len(occ), 64)]
+            if len(occ) <= 64:
+                assert sorted(got.tolist()) == occ, f"tag {tag} read {q}"
+                assert (pos[q, len(occ):] == 0xFFFFFFFF).all()
+            else:
+                assert set(got.tolist()) <= set(occ)
+        b.free()
+        idx.drop_sa()
+        assert idx.meta.sa_bytes == 0
+        idx.free()
+
+
+@pytest.mark.skipif(not helpers.has_ref_tools(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", ["polyA", "ACGT_period4", "two_letter", "random_plus_repeat"])
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_suffix_array_repetitive_texts_and_wide_k(pkg, tmp_path, name, k):
+    """Texts whose LF chains run through long BWT runs, index files from the unmodified reference builder; k = 3 files
+    are located through their 2-step projection."""
+    rng = np.random.default_rng(3)
+    n = 3001
+    unit = ACGT[rng.integers(0, 4, 150)]
+    text = {"polyA": np.full(n, ord("A"), dtype=np.uint8),
+            "ACGT_period4": np.tile(ACGT, n // 4 + 1)[:n],
+            "two_letter": np.frombuffer(b"AC", dtype=np.uint8)[rng.integers(0, 2, n)],
+            "random_plus_repeat": np.concatenate([ACGT[rng.integers(0, 4, n // 2)], np.tile(unit, n // 300 + 1)])[:n]}[name].copy()
+    paths = helpers.build_reference_indexes(str(tmp_path), text, k, 64)
+    want = brute_force_sa(text)
+    for tag in (100, 201):
+        idx = pkg.DeviceIndex.from_image(np.fromfile(paths[tag], dtype=np.uint32))
+        if idx.meta.quirk_mask:                                   # AltCounters padding quirk: refused, never answered wrong
+            with pytest.raises(pkg.FMError) as ei:
+                idx.build_sa()
+            assert ei.value.code == 19
+        else:
+            assert np.array_equal(idx.build_sa().download_sa(), want), f"{name} k={k} tag {tag}"
+        idx.free()
+
+
+def test_locate_errors(pkg):
+    g = np.load(os.path.join(helpers.ROOT, "tests", "golden", "quirk_k2_n124.npz"))
+    idx = pkg.DeviceIndex.from_image(g["image_200"])           # padding quirk
+    with pytest.raises(pkg.FMError) as ei:
+        idx.build_sa()
+    assert ei.value.code == 19
+    idx.free()
+    idx = pkg.DeviceIndex.from_image(g["image_100"])
+    b = pkg.DeviceBatch(0, g["reads"].size // 8, 8, 2)
+    b.upload_ascii(g["reads"])
+    b.search(idx)
+    with pytest.raises(pkg.FMError) as ei:
+        b.locate(idx, 4)                                         # no suffix array yet: loud failure
+    assert ei.value.code == pkg.FM_E_BAD_ARGUMENT
+    idx.build_sa()
+    pos, nhits = b.locate(idx, 4)
+    lr = b.download().reshape(-1, 2)
+    assert np.array_equal(nhits, np.maximum(lr[:, 1].astype(np.int64) - lr[:, 0], 0).astype(np.uint32))
+    b.free(); idx.free()
+
+
+def test_locate_config3_full_size(pkg):
+    """2 Gbp index built on the GPU, 1 M exact 100-bp reads: every read found exactly once must be located at the
+    position it was cut from (fm_synth.h read starts); the suffix array is a permutation of 0..n."""
+    import torch
+    n, nq, length = 2_000_000_000, 1_000_000, 100
+    build = pkg.IndexBuild.from_synth(n, 1, 2, 64)
+    idx = build.to_index()
+    build.free()
+    idx.sparsify(0, 0, 0)
+    idx.build_sa()
+    L = pkg.lib()
+    d_ascii = torch.empty(nq * length, dtype=torch.uint8, device="cuda")
+    pkg.check(L.fmgpu_synth_reads_device(0, n, 1, nq, length, 2, 0, d_ascii.data_ptr(), None), "reads")
+    torch.cuda.synchronize()
+    b = pkg.DeviceBatch(0, nq, length, 2)
+    b.upload_ascii(d_ascii.cpu().numpy())
+    b.search(idx, pkg.variant(pkg.MODE_SPARSE, 4))
+    pos, nhits = b.locate(idx, 2)
+    starts = helpers.synth_read_starts(2, nq, n, length)
+    assert (nhits >= 1).all()
+    once = nhits == 1
+    assert once.mean() > 0.99                                    # 100-mers of a random 2 Gbp text are unique
+    assert np.array_equal(pos[once, 0].astype(np.uint64), starts[once].astype(np.uint64))
+    twice = nhits == 2
+    if twice.any():                                              # a repeated 100-mer: the start is one of the two
+        assert ((pos[twice, 0] == starts[twice]) | (pos[twice, 1] == starts[twice])).all()
+    # permutation check on the device: every value 0..n exactly once
+    cai = {"shape": (n + 1,), "typestr": "<i4", "data": (int(L.fmgpu_index_sa(idx.handle)), False), "version": 2}
+    holder = type("SA", (), {"__cuda_array_interface__": cai})()
+    sa = torch.as_tensor(holder, device="cuda")
+    seen = torch.zeros(n + 1, dtype=torch.uint8, device="cuda")
+    seen[sa.to(torch.int64)] = 1
+    assert int(seen.sum(dtype=torch.int64)) == n + 1
+    b.free(); idx.free()
