@@ -152,3 +152,35 @@ def test_locate_config3_full_size(pkg):
     seen[sa.to(torch.int64)] = 1
     assert int(seen.sum(dtype=torch.int64)) == n + 1
     b.free(); idx.free()
+
+
+def test_text_beyond_2_31_rows(pkg):
+    """hg38-sized text (3.1 Gbp: BWT rows above 2^31, where the reference's builder stops): GPU-built index, plain Coop
+    and sparse-step kernels agree, every exact read is found, and locate returns the position each read was cut from."""
+    import torch
+    n, nq, length = 3_100_000_000, 2_000_000, 100
+    build = pkg.IndexBuild.from_synth(n, 1, 2, 64)
+    idx = build.to_index()
+    build.free()
+    assert idx.meta.bwtsize == n + 1
+    idx.sparsify(0, 0, 0)
+    L = pkg.lib()
+    d_ascii = torch.empty(nq * length, dtype=torch.uint8, device="cuda")
+    pkg.check(L.fmgpu_synth_reads_device(0, n, 1, nq, length, 2, 0, d_ascii.data_ptr(), None), "reads")
+    torch.cuda.synchronize()
+    b = pkg.DeviceBatch(0, nq, length, 2)
+    b.upload_ascii(d_ascii.cpu().numpy())
+    b.search(idx, pkg.variant(pkg.MODE_COOP))
+    want = b.download()
+    assert (want[1::2] > want[0::2]).all()
+    assert (want[0::2] >= 2 ** 31).any()                         # rows in the upper half of the 32-bit range are exercised
+    b.search(idx, pkg.variant(pkg.MODE_SPARSE, 4))
+    assert np.array_equal(b.download(), want)
+    idx.build_sa()
+    pos, nhits = b.locate(idx, 1)
+    starts = helpers.synth_read_starts(2, nq, n, length)
+    once = nhits == 1
+    assert once.mean() > 0.99
+    assert np.array_equal(pos[once, 0].astype(np.uint64), starts[once].astype(np.uint64))
+    assert (pos[once, 0] >= 2 ** 31).any()
+    b.free(); idx.free()
