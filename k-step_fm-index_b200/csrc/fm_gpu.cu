@@ -36,6 +36,7 @@ struct fmgpu_index {
   uint4             *sblocks;      /* sparse-step table (fmgpu_index_sparsify), or NULL */
   uint2             *sdir;         /* its directory: { first block, scale } per wide symbol */
   uint2             *sstart;       /* start table of the sparse kernel, or NULL */
+  uint2             *slead[16];    /* lead tables: (L,R) of all b-mers, b = 6 .. sparse_bases - 1 (multiples of k), or NULL */
   uint4             *tail1;        /* tail table (fm_tail_table_kernel): built by the first odd-length search on this replica */
   uint32_t          *sa;           /* suffix array derived from the table (fmgpu_index_build_sa), or NULL */
   uint32_t           s_uni_nb, s_uni_scale;   /* sparse table is a uniform grid: blocks per symbol and the one scale (0 = directory) */
@@ -339,6 +340,7 @@ extern "C" int32_t fmgpu_index_free(fmgpu_index_t **pidx)
     cudaSetDevice(idx->device);
     cudaFree(idx->blocks); cudaFree(idx->fblocks); cudaFree(idx->start);
     cudaFree(idx->sblocks); cudaFree(idx->sdir); cudaFree(idx->sstart); cudaFree(idx->tail1); cudaFree(idx->sa);
+    for (int b = 0; b < 16; b++) cudaFree(idx->slead[b]);
   }
   free(idx);
   *pidx = NULL;
@@ -551,6 +553,7 @@ extern "C" int32_t fmgpu_index_unsparsify(fmgpu_index_t *idx)
     CU_TRY(cudaSetDevice(idx->device));
     cudaFree(idx->sblocks); cudaFree(idx->sdir); cudaFree(idx->sstart);
     idx->sblocks = NULL; idx->sdir = NULL; idx->sstart = NULL;
+    for (int b = 0; b < 16; b++) { cudaFree(idx->slead[b]); idx->slead[b] = NULL; }
   }
   idx->s_uni_nb = 0; idx->s_uni_scale = 0; idx->meta.sparse_uniform_nb = 0;
   idx->meta.sparse_bases = 0; idx->meta.sparse_lambda = 0; idx->meta.sparse_bytes = 0; idx->meta.sparse_blocks = 0;
@@ -694,6 +697,25 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
       if (e != cudaSuccess || rc != FM_SUCCESS) { cudaFree(table); cudaGetLastError(); }   /* the table is optional */
       else { idx->sstart = table; idx->meta.sparse_start_bases = sb; idx->meta.sparse_bytes += (uint64_t) nkeys * 8; }
     }
+    /* lead tables: (L,R) of every b-mer for the leftover lengths b = 6 .. ks-1 a read can have (multiples of k), computed
+     * by the same kernel (b bases = base steps only).  A read with that many leftover bases starts from the table and
+     * then runs ALL its sparse steps, instead of the start table + one SB96 fetch per k leftover bases behind them. */
+    if (want && idx->sstart) {
+      for (uint32_t b = 6; b < ks && b < 16; b++) {
+        if (b % k || ((uint64_t) 1 << (2 * b)) >= n) continue;
+        const uint32_t nkeys = 1u << (2 * b);
+        uint32_t *skeys = NULL; uint2 *table = NULL;
+        e = cudaMalloc((void **) &skeys, (size_t) nkeys * 4);
+        if (e == cudaSuccess) e = cudaMalloc((void **) &table, (size_t) nkeys * 8);
+        if (e == cudaSuccess) { fm_iota_kernel<<<(nkeys + 255) / 256, 256>>>(skeys, nkeys); e = cudaGetLastError(); }
+        int32_t rc = FM_SUCCESS;
+        if (e == cudaSuccess) rc = fm_launch_sparse(idx, skeys, nkeys, b, (uint32_t *) table, FM_DEFAULT_VARIANT, 0);
+        if (e == cudaSuccess && rc == FM_SUCCESS) e = cudaDeviceSynchronize();
+        cudaFree(skeys);
+        if (e != cudaSuccess || rc != FM_SUCCESS) { cudaFree(table); cudaGetLastError(); }
+        else { idx->slead[b] = table; idx->meta.sparse_bytes += (uint64_t) nkeys * 8; }
+      }
+    }
   }
   return FM_SUCCESS;
 }
@@ -719,12 +741,20 @@ static int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_pack
   FmSparseParams p;
   p.sblocks = idx->sblocks; p.dir = idx->sdir; p.blocks = idx->blocks; p.packed = d_packed; p.results = d_results;
   p.nblocks = idx->meta.nblocks; p.nq = (uint32_t) nq;
-  p.nlead = (len / k) % hops; p.nsteps = (len / k) / hops;
+  /* plan: S whole sparse steps + rem base-k steps (+ an odd tail base).  (A) the start table replaces the first sparse
+   * step(s) and the rem steps follow the sparse ones: S - m + rem block fetches from DRAM; (B) 6 or more leftover bases
+   * are taken first from their lead table and all S sparse steps run: S fetches (the interval is already narrower than
+   * a bucket); (C) no table: the rem steps run first on the upper (L2-resident) levels of SB96. */
+  const uint32_t S = (len / k) / hops, rem = (len / k) % hops;
+  const uint32_t m = idx->sstart ? idx->meta.sparse_start_bases / ks : 0u;
+  p.nfront = 0; p.nback = 0; p.nsteps = S; p.start = NULL; p.start_bits = 0;
+  if (rem * k >= 6 && rem * k < 16 && idx->slead[rem * k] && S >= 1) { p.start = idx->slead[rem * k]; p.start_bits = 2 * k * rem; }
+  else if (m && S >= m) { p.start = idx->sstart; p.start_bits = 2 * ks * m; p.nsteps = S - m; p.nback = rem; }
+  else p.nfront = rem;
   p.wpq = fmgpu_words_per_query(len); p.bwtsize = idx->meta.bwtsize;
   p.sbits = 2 * ks; p.hops = hops;
   p.uni_nb = idx->s_uni_nb; p.uni_scale = idx->s_uni_scale;
   p.fetch_counters = d_counters;
-  p.start = idx->sstart; p.start_steps = idx->sstart ? idx->meta.sparse_start_bases / ks : 0u;
   p.has_tail = len % k; p.tail_row = idx->meta.tail_row; p.tail_base = idx->meta.tail_base;
   for (int c = 0; c < 4; c++) p.tail_const[c] = idx->meta.tail_const[c];
   p.tail1 = p.has_tail ? fm_ensure_tail(idx, stream) : NULL;

@@ -52,8 +52,8 @@ struct FmSparseParams {
   uint32_t       *results;
   uint32_t nblocks;           /* SB96 stride                                                       */
   uint32_t nq;
-  uint32_t nlead;             /* base-k steps on SB96 (in front of, or behind, the sparse steps)   */
-  uint32_t nsteps;            /* sparse steps                                                      */
+  uint32_t nfront, nback;     /* base-k steps on SB96 in front of / behind the sparse steps       */
+  uint32_t nsteps;            /* sparse steps (after the start table's bases, if one is used)     */
   uint32_t wpq;
   uint32_t bwtsize;
   uint32_t sbits;             /* 2 * KS                                                            */
@@ -63,8 +63,9 @@ struct FmSparseParams {
   const uint4 *tail1;         /* tail table (fm_tail_table_kernel) or NULL */
   uint32_t uni_nb, uni_scale; /* uniform grid (every symbol owns uni_nb blocks, first block = sigma * uni_nb): no directory
                                  lookup; 0 = per-symbol block counts, read from dir                                  */
-  const uint2 *start;         /* (L,R) after the first start_steps sparse steps, indexed by their packed bits, or NULL */
-  uint32_t start_steps;
+  const uint2 *start;         /* (L,R) after the first start_bits / 2 bases, indexed by those packed bits, or NULL: the start
+                                 table (a whole number of sparse steps) or a lead table (the leftover bases, taken first) */
+  uint32_t start_bits;
 };
 
 /* directory entry { first block, scale } of a wide symbol: computed when the table is a uniform grid, else one L2-resident
@@ -149,8 +150,9 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_kernel(const F
   unsigned long long n_sp = 0, n_sb = 0, n_ovf = 0;
   uint32_t pos = 0;
   /* the (len/k) % hops base-k steps that do not fill a sparse step run on SB96: in FRONT of the sparse steps (wide
-   * interval, upper levels of the table, L2 hits) when there is no start table to use, BEHIND them when there is
-   * (one DRAM block per step there, but the start table keeps replacing the first sparse steps) */
+   * interval, upper levels of the table, L2 hits) when there is no table to start from, BEHIND them when the start
+   * table replaces the first sparse step (one DRAM block per step there); with 6 or more leftover bases a lead
+   * table takes them first instead and every sparse step runs (fm_launch_sparse) */
   auto base_steps = [&](uint32_t count) {
     for (uint32_t step = 0; step < count; step++, pos += BBITS) {
       #pragma unroll
@@ -166,20 +168,17 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_kernel(const F
       }
     }
   };
-  const bool use_start = p.start_steps && p.nsteps >= p.start_steps;
-  if (!use_start) base_steps(p.nlead);
-
-  uint32_t step0 = 0;
-  if (use_start) {
-    const uint32_t sb = p.start_steps * p.sbits;
-    const uint32_t kmask = (sb >= 32u) ? 0xFFFFFFFFu : ((1u << sb) - 1u);
+  if (p.start) {                                               /* the host picked the plan (fm_launch_sparse) */
+    const uint32_t kmask = (p.start_bits >= 32u) ? 0xFFFFFFFFu : ((1u << p.start_bits) - 1u);
     #pragma unroll
     for (int i = 0; i < QPT; i++) {
       const uint2 lr = __ldg(p.start + (myq[i][0] & kmask));
       L[i] = lr.x; R[i] = lr.y;
     }
-    step0 = p.start_steps; pos = sb;
+    pos = p.start_bits;
   }
+  base_steps(p.nfront);
+  const uint32_t step0 = 0;
 
   uint32_t sig[QPT];
   uint2 d[QPT];
@@ -265,7 +264,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_kernel(const F
     for (int i = 0; i < QPT; i++) { L[i] = nL[i]; R[i] = nR[i]; }
   }
 
-  if (use_start) base_steps(p.nlead);
+  base_steps(p.nback);
 
   if (K == 2 && p.has_tail) {                     /* last base of an odd-length read */
     #pragma unroll
