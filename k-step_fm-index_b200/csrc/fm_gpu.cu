@@ -701,8 +701,11 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
      * by the same kernel (b bases = base steps only).  A read with that many leftover bases starts from the table and
      * then runs ALL its sparse steps, instead of the start table + one SB96 fetch per k leftover bases behind them. */
     if (want && idx->sstart) {
-      for (uint32_t b = 6; b < ks && b < 16; b++) {
-        if (b % k || ((uint64_t) 1 << (2 * b)) >= n) continue;
+      /* widths 6 .. ks+1, any parity: an odd width on a 2-step index ends with the derived 1-step rank while the TABLE is
+       * computed, so reads of odd length that start from it need no tail fetch at all (bases may be grouped into steps
+       * in any way: every grouping composes the same LF steps); ks+1 (33 MB at ks = 10) serves lengths = 1 mod ks: 101, 151 */
+      for (uint32_t b = 6; b <= ks + 1 && b < 16; b++) {
+        if (b == sb || (b % k && !(k == 2 && idx->meta.tail_valid)) || ((uint64_t) 1 << (2 * b)) >= n) continue;
         const uint32_t nkeys = 1u << (2 * b);
         uint32_t *skeys = NULL; uint2 *table = NULL;
         e = cudaMalloc((void **) &skeys, (size_t) nkeys * 4);
@@ -747,15 +750,19 @@ static int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_pack
    * a bucket); (C) no table: the rem steps run first on the upper (L2-resident) levels of SB96. */
   const uint32_t S = (len / k) / hops, rem = (len / k) % hops;
   const uint32_t m = idx->sstart ? idx->meta.sparse_start_bases / ks : 0u;
+  const uint32_t lb = len - S * ks;                            /* leftover bases, the odd one included */
+  const uint32_t lead = (lb >= 6 && lb < 16 && idx->slead[lb] && S >= 1) ? lb
+                      : (S >= 2 && lb + ks < 16 && lb + ks > idx->meta.sparse_start_bases && idx->slead[lb + ks]) ? lb + ks : 0u;
   p.nfront = 0; p.nback = 0; p.nsteps = S; p.start = NULL; p.start_bits = 0;
-  if (rem * k >= 6 && rem * k < 16 && idx->slead[rem * k] && S >= 1) { p.start = idx->slead[rem * k]; p.start_bits = 2 * k * rem; }
+  if (lead) { p.start = idx->slead[lead]; p.start_bits = 2 * lead; p.nsteps = S - (lead > lb ? 1u : 0u); }
   else if (m && S >= m) { p.start = idx->sstart; p.start_bits = 2 * ks * m; p.nsteps = S - m; p.nback = rem; }
   else p.nfront = rem;
   p.wpq = fmgpu_words_per_query(len); p.bwtsize = idx->meta.bwtsize;
   p.sbits = 2 * ks; p.hops = hops;
   p.uni_nb = idx->s_uni_nb; p.uni_scale = idx->s_uni_scale;
   p.fetch_counters = d_counters;
-  p.has_tail = len % k; p.tail_row = idx->meta.tail_row; p.tail_base = idx->meta.tail_base;
+  p.has_tail = lead ? 0u : len % k;                            /* a lead table already holds the odd base */
+  p.tail_row = idx->meta.tail_row; p.tail_base = idx->meta.tail_base;
   for (int c = 0; c < 4; c++) p.tail_const[c] = idx->meta.tail_const[c];
   p.tail1 = p.has_tail ? fm_ensure_tail(idx, stream) : NULL;
   if (d_counters) v.queries_per_thread = 1;
