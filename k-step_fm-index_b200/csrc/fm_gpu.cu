@@ -36,6 +36,7 @@ struct fmgpu_index {
   uint4             *sblocks;      /* sparse-step table (fmgpu_index_sparsify), or NULL */
   uint2             *sdir;         /* its directory: { first block, scale } per wide symbol */
   uint2             *sstart;       /* start table of the sparse kernel, or NULL */
+  uint32_t           slead_tried;  /* bit b: building slead[b] was attempted */
   uint2             *slead[16];    /* lead tables: (L,R) of all b-mers, b = 6 .. sparse_bases - 1 (multiples of k), or NULL */
   uint4             *tail1;        /* tail table (fm_tail_table_kernel): built by the first odd-length search on this replica */
   uint32_t          *sa;           /* suffix array derived from the table (fmgpu_index_build_sa), or NULL */
@@ -545,6 +546,7 @@ static int32_t fm_launch_fused(const fmgpu_index_t *idx, const uint32_t *d_packe
  * ------------------------------------------------------------------------ */
 static int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nq, uint32_t len,
                                 uint32_t *d_results, fmgpu_variant_t v, cudaStream_t stream, unsigned long long *d_counters = NULL);
+static const uint2 *fm_ensure_lead(const fmgpu_index_t *cidx, uint32_t b);
 
 extern "C" int32_t fmgpu_index_unsparsify(fmgpu_index_t *idx)
 {
@@ -554,6 +556,7 @@ extern "C" int32_t fmgpu_index_unsparsify(fmgpu_index_t *idx)
     cudaFree(idx->sblocks); cudaFree(idx->sdir); cudaFree(idx->sstart);
     idx->sblocks = NULL; idx->sdir = NULL; idx->sstart = NULL;
     for (int b = 0; b < 16; b++) { cudaFree(idx->slead[b]); idx->slead[b] = NULL; }
+    idx->slead_tried = 0;
   }
   idx->s_uni_nb = 0; idx->s_uni_scale = 0; idx->meta.sparse_uniform_nb = 0;
   idx->meta.sparse_bases = 0; idx->meta.sparse_lambda = 0; idx->meta.sparse_bytes = 0; idx->meta.sparse_blocks = 0;
@@ -697,30 +700,49 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
       if (e != cudaSuccess || rc != FM_SUCCESS) { cudaFree(table); cudaGetLastError(); }   /* the table is optional */
       else { idx->sstart = table; idx->meta.sparse_start_bases = sb; idx->meta.sparse_bytes += (uint64_t) nkeys * 8; }
     }
-    /* lead tables: (L,R) of every b-mer for the leftover lengths b = 6 .. ks-1 a read can have (multiples of k), computed
-     * by the same kernel (b bases = base steps only).  A read with that many leftover bases starts from the table and
-     * then runs ALL its sparse steps, instead of the start table + one SB96 fetch per k leftover bases behind them. */
-    if (want && idx->sstart) {
-      /* widths 6 .. ks+1, any parity: an odd width on a 2-step index ends with the derived 1-step rank while the TABLE is
-       * computed, so reads of odd length that start from it need no tail fetch at all (bases may be grouped into steps
-       * in any way: every grouping composes the same LF steps); ks+1 (33 MB at ks = 10) serves lengths = 1 mod ks: 101, 151 */
-      for (uint32_t b = 6; b <= ks + 1 && b < 16; b++) {
-        if (b == sb || (b % k && !(k == 2 && idx->meta.tail_valid)) || ((uint64_t) 1 << (2 * b)) >= n) continue;
-        const uint32_t nkeys = 1u << (2 * b);
-        uint32_t *skeys = NULL; uint2 *table = NULL;
-        e = cudaMalloc((void **) &skeys, (size_t) nkeys * 4);
-        if (e == cudaSuccess) e = cudaMalloc((void **) &table, (size_t) nkeys * 8);
-        if (e == cudaSuccess) { fm_iota_kernel<<<(nkeys + 255) / 256, 256>>>(skeys, nkeys); e = cudaGetLastError(); }
-        int32_t rc = FM_SUCCESS;
-        if (e == cudaSuccess) rc = fm_launch_sparse(idx, skeys, nkeys, b, (uint32_t *) table, FM_DEFAULT_VARIANT, 0);
-        if (e == cudaSuccess && rc == FM_SUCCESS) e = cudaDeviceSynchronize();
-        cudaFree(skeys);
-        if (e != cudaSuccess || rc != FM_SUCCESS) { cudaFree(table); cudaGetLastError(); }
-        else { idx->slead[b] = table; idx->meta.sparse_bytes += (uint64_t) nkeys * 8; }
-      }
-    }
+    /* lead tables (fm_ensure_lead): the small ones now, the wide ones (12 .. 15 bases, up to 8.6 GB) when a read length asks */
+    if (want && idx->sstart)
+      for (uint32_t b = 6; b <= ks + 1 && b < 12; b++) fm_ensure_lead(idx, b);
   }
   return FM_SUCCESS;
+}
+
+/* Lead table of width b: (L,R) of every b-mer, computed by the search kernel itself (a packed b-mer is its own key).
+ * A read whose length leaves b bases over -- or b - KS, giving up one sparse step -- starts from it and then runs only
+ * whole sparse steps: no SB96 fetches behind them and no tail fetch.  Any parity: on a 2-step index an odd width ends
+ * with the derived 1-step rank while the TABLE is computed (bases may be grouped into steps in any way; every grouping
+ * composes the same LF steps).  Widths 6 .. 11 are built with the sparse table, 12 .. 15 (134 MB .. 8.6 GB) by the first
+ * search that needs them.  NULL when tables are off for this index, the width is not representable or memory is short. */
+static std::mutex g_lead_mutex;
+static thread_local bool g_building_lead = false;
+static const uint2 *fm_ensure_lead(const fmgpu_index_t *cidx, uint32_t b)
+{
+  fmgpu_index_t *idx = const_cast<fmgpu_index_t *>(cidx);
+  if (b < 6 || b >= 16 || !idx->sstart) return NULL;
+  std::lock_guard<std::mutex> lock(g_lead_mutex);
+  if (idx->slead[b]) return idx->slead[b];
+  if (idx->slead_tried & (1u << b)) return NULL;
+  idx->slead_tried |= 1u << b;
+  const uint32_t k = idx->meta.steps, n = idx->meta.bwtsize;
+  if (b == idx->meta.sparse_start_bases || (b % k && !(k == 2 && idx->meta.tail_valid)) || ((uint64_t) 1 << (2 * b)) >= n) return NULL;
+  if (cudaSetDevice(idx->device) != cudaSuccess) { cudaGetLastError(); return NULL; }
+  const uint32_t nkeys = 1u << (2 * b);
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return NULL; }
+  if ((uint64_t) nkeys * 12 + (2ull << 30) > free_b) return NULL;
+  uint32_t *skeys = NULL; uint2 *table = NULL;
+  cudaError_t e = cudaMalloc((void **) &skeys, (size_t) nkeys * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &table, (size_t) nkeys * 8);
+  if (e == cudaSuccess) { fm_iota_kernel<<<(nkeys + 255) / 256, 256>>>(skeys, nkeys); e = cudaGetLastError(); }
+  int32_t rc = FM_SUCCESS;
+  g_building_lead = true;
+  if (e == cudaSuccess) rc = fm_launch_sparse(idx, skeys, nkeys, b, (uint32_t *) table, FM_DEFAULT_VARIANT, 0);
+  g_building_lead = false;
+  if (e == cudaSuccess && rc == FM_SUCCESS) e = cudaDeviceSynchronize();
+  cudaFree(skeys);
+  if (e != cudaSuccess || rc != FM_SUCCESS) { cudaFree(table); cudaGetLastError(); return NULL; }
+  idx->slead[b] = table; idx->meta.sparse_bytes += (uint64_t) nkeys * 8;
+  return table;
 }
 
 typedef void (*fm_sparse_fn)(const FmSparseParams);
@@ -751,8 +773,11 @@ static int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_pack
   const uint32_t S = (len / k) / hops, rem = (len / k) % hops;
   const uint32_t m = idx->sstart ? idx->meta.sparse_start_bases / ks : 0u;
   const uint32_t lb = len - S * ks;                            /* leftover bases, the odd one included */
-  const uint32_t lead = (lb >= 6 && lb < 16 && idx->slead[lb] && S >= 1) ? lb
-                      : (S >= 2 && lb + ks < 16 && lb + ks > idx->meta.sparse_start_bases && idx->slead[lb + ks]) ? lb + ks : 0u;
+  uint32_t lead = 0;
+  if (idx->sstart && !g_building_lead) {                       /* (a lead table is computed without lead tables) */
+    if (lb >= 6 && lb < 16 && S >= 1 && fm_ensure_lead(idx, lb)) lead = lb;
+    else if (lb >= 1 && lb < 6 && S >= 2 && lb + ks < 16 && lb + ks > idx->meta.sparse_start_bases && fm_ensure_lead(idx, lb + ks)) lead = lb + ks;
+  }
   p.nfront = 0; p.nback = 0; p.nsteps = S; p.start = NULL; p.start_bits = 0;
   if (lead) { p.start = idx->slead[lead]; p.start_bits = 2 * lead; p.nsteps = S - (lead > lb ? 1u : 0u); }
   else if (m && S >= m) { p.start = idx->sstart; p.start_bits = 2 * ks * m; p.nsteps = S - m; p.nback = rem; }

@@ -183,7 +183,8 @@ def test_sparse_start_table_and_fetch_counter(pkg, k):
     stream = torch.cuda.current_stream().cuda_stream
     # 36..39, 76, 77, 126: 6 or more leftover bases start from their lead table; 6, 8: shorter than one sparse step
     # and odd widths / 11 bases (lengths = 1 mod 10) come out of a lead table without any tail fetch
-    for length in (10, 20, 100, 12, 14, 16, 50, 101, 99, 36, 37, 38, 39, 76, 77, 126, 6, 8, 11, 21, 31, 151, 75):
+    # lengths = 2 .. 5 mod 10 with two sparse steps or more build the wide tables (12 .. 13 bases here) on first use
+    for length in (10, 20, 100, 12, 14, 16, 50, 101, 99, 36, 37, 38, 39, 76, 77, 126, 6, 8, 11, 21, 31, 151, 75, 32, 33, 22, 23, 15):
         nq = 200_000
         d_ascii = torch.empty(nq * length, dtype=torch.uint8, device="cuda")
         pkg.check(L.fmgpu_synth_reads_device(0, n, 3, nq, length, 2, 0, d_ascii.data_ptr(), None), "reads")
