@@ -20,7 +20,7 @@ for k in (2, 1):
     m = idx.meta
     emit(what="index", k=k, sb96_gb=m.nbytes / 1e9, fused_bases=m.fused_bases, fused_gb=m.fused_bytes / 1e9,
          sparse_bases=m.sparse_bases, sparse_gb=m.sparse_bytes / 1e9)
-    for length in (12, 25, 50, 100, 250):
+    for length in (12, 25, 50, 75, 100, 101, 150, 250):
         # odd lengths at k=2: undefined in the reference; served here by the derived 1-step tail
         d_ascii = torch.empty(nq * length, dtype=torch.uint8, device="cuda")
         pkg.check(L.fmgpu_synth_reads_device(0, n, 1, nq, length, 2, 0, d_ascii.data_ptr(), None), "reads")
