@@ -137,6 +137,31 @@ static void stream_avx512(const unsigned char *in, uint64_t nbases, unsigned cha
   const int nt = nt_allowed && (((uintptr_t) out) & 15u) == 0;
   const int pf_dist = fm_hostpack_prefetch_distance();
   uint64_t g = 0;
+  /* whole output lines: 256 bases -> one 64-byte non-temporal store (no read-for-ownership, no partial-line write
+   * combining).  Measured SLOWER too on the benchmark host (hybrid feed 960-1030 vs 1070-1160 M reads/s, host packing
+   * alone equal, profiles/r01_e2e_line_nt.jsonl): with plain stores the 50 MB of staging buffers stay in the 60 MB L3 and
+   * the DMA engine reads them from there, non-temporal stores send them through DRAM.  Off unless $FM_HOSTPACK_LINE=1. */
+  static int line_nt = -1;
+  if (line_nt < 0) { const char *e = getenv("FM_HOSTPACK_LINE"); line_nt = (e && e[0] == '1'); }
+  if (line_nt && (((uintptr_t) out) & 63u) == 0) {
+    for (; g + 256 <= nbases; g += 256) {
+      if (pf_dist) {
+        _mm_prefetch((const char *)(in + g + pf_dist), _MM_HINT_NTA);       _mm_prefetch((const char *)(in + g + pf_dist + 64), _MM_HINT_NTA);
+        _mm_prefetch((const char *)(in + g + pf_dist + 128), _MM_HINT_NTA); _mm_prefetch((const char *)(in + g + pf_dist + 192), _MM_HINT_NTA);
+      }
+      __m128i q[4];
+      for (int j = 0; j < 4; j++) {
+        const __m512i x = _mm512_loadu_si512((const void *)(in + g + 64 * j));
+        const __m512i u = _mm512_and_si512(_mm512_srli_epi16(x, 1), three);
+        const __m512i c = _mm512_xor_si512(u, _mm512_and_si512(_mm512_srli_epi16(u, 1), one));
+        q[j] = _mm512_cvtepi32_epi8(_mm512_madd_epi16(_mm512_maddubs_epi16(c, w16), w32));
+      }
+      __m512i line = _mm512_castsi128_si512(q[0]);
+      line = _mm512_inserti32x4(line, q[1], 1); line = _mm512_inserti32x4(line, q[2], 2); line = _mm512_inserti32x4(line, q[3], 3);
+      _mm512_stream_si512((void *)(out + g / 4), line);
+    }
+    _mm_sfence();
+  }
   for (; g + 64 <= nbases; g += 64) {
     if (pf_dist) _mm_prefetch((const char *)(in + g + pf_dist), _MM_HINT_NTA);
     const __m512i x = _mm512_loadu_si512((const void *)(in + g));

@@ -19,3 +19,7 @@ def built():
     import helpers
     helpers.ensure_built()
     return helpers
+
+# the host stream packer reads this knob once per process: the tests run with its whole-line non-temporal path on (aligned
+# outputs) so that it stays covered; unaligned outputs in test_host_stream_packer cover the default 16-byte path
+os.environ.setdefault("FM_HOSTPACK_LINE", "1")

@@ -152,14 +152,20 @@ def test_host_packer_simd_equals_scalar_equals_definition(built, length):
     assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("nbases", [1, 3, 4, 63, 64, 65, 4095, 4096, 4097, 100_003])
-def test_host_stream_packer(built, nbases):
-    """fm_hostpack_stream: base g at bits 2(g%4) of byte g/4, threads split at 4096-base slices."""
+@pytest.mark.parametrize("out_offset", [0, 16, 5])
+@pytest.mark.parametrize("nbases", [1, 3, 4, 63, 64, 65, 255, 256, 257, 4095, 4096, 4097, 100_003])
+def test_host_stream_packer(built, nbases, out_offset):
+    """fm_hostpack_stream: base g at bits 2(g%4) of byte g/4, threads split at 4096-base slices; with
+    $FM_HOSTPACK_LINE=1 (read once per process, so set for the whole test module) a 64-byte aligned output takes the
+    whole-line non-temporal path (256 bases per store), other alignments the 16-byte path."""
     pkg = helpers.pkg()
     L = pkg.lib()
     rng = np.random.default_rng(nbases)
     a = np.frombuffer(b"ACGTacgtN", dtype=np.uint8)[rng.integers(0, 9, nbases)].copy()
-    out = np.zeros((nbases + 3) // 4 + 8, dtype=np.uint8)
+    buf = np.zeros((nbases + 3) // 4 + 8 + 128, dtype=np.uint8)
+    shift = (-buf.ctypes.data) % 64 + out_offset
+    out = buf[shift:]
+    assert (out.ctypes.data - out_offset) % 64 == 0
     L.fm_hostpack_stream(a.ctypes.data, nbases, out.ctypes.data, 0)
     r = np.zeros(((nbases + 3) // 4) * 4, dtype=np.uint32)
     r[:nbases] = a
