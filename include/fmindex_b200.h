@@ -327,6 +327,7 @@ void    fm_hostpack_reads_scalar(const char *ascii, uint64_t nqueries, uint32_t 
 void    fm_hostpack_stream(const char *ascii, uint64_t nbases, unsigned char *out, int nthreads);
 int32_t fmgpu_unstream_device(int32_t device, const uint32_t *d_stream, uint64_t nqueries, uint32_t len,
                               uint32_t *d_packed, void *stream);
+void    fm_hostpack_set_streams(int streams);  /* interleaved sub-streams per packer thread (default 4, 1 = one; $FM_HOSTPACK_STREAMS) */
 void    fm_hostpack_set_prefetch(int bytes);   /* software prefetch distance of the stream packer (default 8192, 0 = off) */
 int     fm_hostpack_has_simd(void);
 int     fm_hostpack_threads(void);

@@ -153,6 +153,7 @@ PROTOTYPES = {
     "fm_hostpack_stream": (None, [_VP, C.c_uint64, _VP, C.c_int]),
     "fmgpu_unstream_device": (C.c_int32, [C.c_int32, _VP, C.c_uint64, C.c_uint32, _VP, _VP]),
     "fm_hostpack_set_prefetch": (None, [C.c_int]),
+    "fm_hostpack_set_streams": (None, [C.c_int]),
     "fm_hostpack_has_simd": (C.c_int, []),
     "fm_hostpack_threads": (C.c_int, []),
     "fmgpu_gather_probe_local": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.POINTER(C.c_double)]),

@@ -177,14 +177,62 @@ static void stream_avx512(const unsigned char *in, uint64_t nbases, unsigned cha
   if (g < nbases) stream_scalar(in + g, nbases - g, out + g / 4);
 }
 
-/* out must hold (nbases + 3) / 4 bytes (+ up to 3 bytes of slack are NOT written); threads split at 64-base
+/* Several interleaved sub-streams per thread: one sequential stream per core leaves the core's line-fill buffers and the
+ * L2 streamer under-used (a core reads ~9 GB/s from one stream, ~12 from four), so every thread cuts its range into
+ * `streams` pieces and converts 64 bases of each in turn, with a software prefetch into L1 `pf_dist` bytes ahead of every
+ * piece.  $FM_HOSTPACK_STREAMS / fm_hostpack_set_streams(): default 4, 1 = one stream per thread (the 4096-base slice loop). */
+static int g_streams = -1;
+static int fm_hostpack_streams(void)
+{
+  if (g_streams < 0) { const char *e = getenv("FM_HOSTPACK_STREAMS"); g_streams = e && *e ? atoi(e) : 4; if (g_streams < 1) g_streams = 1; if (g_streams > 8) g_streams = 8; }
+  return g_streams;
+}
+void fm_hostpack_set_streams(int streams) { g_streams = streams < 1 ? 1 : (streams > 8 ? 8 : streams); }
+
+__attribute__((target("avx512f,avx512bw,avx512vl")))
+static void stream_avx512_multi(const unsigned char *in, uint64_t nbases, unsigned char *out, int K, int pf_dist)
+{
+  const __m512i three = _mm512_set1_epi8(3), one = _mm512_set1_epi8(1);
+  const __m512i w16 = _mm512_set1_epi16(0x0401), w32 = _mm512_set1_epi32(0x00100001);
+  const uint64_t seg = (nbases / (uint64_t) K) & ~(uint64_t) 255;    /* bases per piece: whole 64-byte output lines */
+  uint64_t g;
+  int k;
+  for (g = 0; g < seg; g += 64)
+    for (k = 0; k < K; k++) {
+      const unsigned char *p = in + (uint64_t) k * seg + g;
+      if (pf_dist) _mm_prefetch((const char *)(p + pf_dist), _MM_HINT_T0);
+      const __m512i x = _mm512_loadu_si512((const void *) p);
+      const __m512i u = _mm512_and_si512(_mm512_srli_epi16(x, 1), three);
+      const __m512i c = _mm512_xor_si512(u, _mm512_and_si512(_mm512_srli_epi16(u, 1), one));
+      _mm_storeu_si128((__m128i *)(out + ((uint64_t) k * seg + g) / 4), _mm512_cvtepi32_epi8(_mm512_madd_epi16(_mm512_maddubs_epi16(c, w16), w32)));
+    }
+  if ((uint64_t) K * seg < nbases) stream_avx512(in + (uint64_t) K * seg, nbases - (uint64_t) K * seg, out + (uint64_t) K * seg / 4);
+}
+
+/* out must hold (nbases + 3) / 4 bytes (+ up to 3 bytes of slack are NOT written); threads split at 4096-base
  * boundaries so every thread writes whole bytes */
 void fm_hostpack_stream(const char *ascii, uint64_t nbases, unsigned char *out, int nthreads)
 {
   const int simd = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl");
   const uint64_t nblk = (nbases + 4095) / 4096;                     /* 4096-base slices */
+  const int streams = fm_hostpack_streams();
   int64_t b;
   if (nthreads <= 0) nthreads = omp_get_max_threads();
+  if (simd && streams > 1 && nblk >= (uint64_t) nthreads * 8) {
+    /* one contiguous range of slices per thread, several sub-streams inside it */
+    const uint64_t per = (nblk + (uint64_t) nthreads - 1) / (uint64_t) nthreads;
+    int pf = fm_hostpack_prefetch_distance();
+    if (pf > 4096) pf = 4096;                                       /* the single-stream default (8192, non-temporal hint) is too far for L1 */
+    #pragma omp parallel for schedule(static, 1) num_threads(nthreads)
+    for (b = 0; b < (int64_t) nthreads; b++) {
+      const uint64_t b0 = (uint64_t) b * per, b1 = (b0 + per < nblk) ? b0 + per : nblk;
+      if (b0 < b1) {
+        const uint64_t g0 = b0 * 4096, g1 = (b1 * 4096 < nbases) ? b1 * 4096 : nbases;
+        stream_avx512_multi((const unsigned char *) ascii + g0, g1 - g0, out + g0 / 4, streams, pf);
+      }
+    }
+    return;
+  }
   #pragma omp parallel for schedule(static) num_threads(nthreads)
   for (b = 0; b < (int64_t) nblk; b++) {
     const uint64_t g0 = (uint64_t) b * 4096, n = (nbases - g0 < 4096) ? nbases - g0 : 4096;
