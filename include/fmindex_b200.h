@@ -215,7 +215,7 @@ typedef struct {
   uint32_t sparse_lambda;      /* target occurrences per block                                  */
   uint64_t sparse_bytes;       /* blocks + directory (+ start table)                            */
   uint64_t sparse_blocks;      /* number of blocks                                              */
-  uint64_t sparse_overflow;    /* overfull buckets too big for extension blocks (served by SB96 steps) */
+  uint64_t sparse_overflow;    /* blocks holding more occurrences than slots (served by SB96 steps) */
   uint32_t sparse_start_bases; /* bases covered by the sparse kernel's start table, 0 = none    */
   uint32_t sparse_lanes;       /* lanes per block: 2 = 64-byte blocks (15 slots), 4 = 128-byte blocks (31 slots) */
   /* tail table: the derived 1-step rank above re-blocked so that the last base of an odd-length read costs one
@@ -226,10 +226,8 @@ typedef struct {
    * symbol's first block instead of looking it up (chosen when all symbols occur about equally often, i.e. on
    * uniformly random texts; $FMGPU_SPARSE_UNIFORM=0/1 forces); 0 = per-symbol block counts and a directory */
   uint32_t sparse_uniform_nb;
-  uint32_t sparse_ext_blocks;  /* extension blocks behind the table: an overfull bucket keeps its rows there and is served by ONE
-                                  extra block fetch; only buckets too big for that (sparse_overflow) take steps on the block table */
+  uint32_t reserved0;
   uint64_t sa_bytes;           /* suffix array kept for locate (fmgpu_index_build_sa): 4 bytes per BWT row, 0 = none */
-  uint64_t sparse_overfull;    /* buckets with more occurrences than slots (extension-served + sparse_overflow) */
 } fmgpu_index_meta_t;
 
 /* devices ---------------------------------------------------------------- */

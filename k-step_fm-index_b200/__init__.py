@@ -74,8 +74,7 @@ class fmgpu_index_meta_t(C.Structure):
                 ("sparse_bases", C.c_uint32), ("sparse_lambda", C.c_uint32), ("sparse_bytes", C.c_uint64),
                 ("sparse_blocks", C.c_uint64), ("sparse_overflow", C.c_uint64), ("sparse_start_bases", C.c_uint32),
                 ("sparse_lanes", C.c_uint32), ("tail_bytes", C.c_uint64),
-                ("sparse_uniform_nb", C.c_uint32), ("sparse_ext_blocks", C.c_uint32), ("sa_bytes", C.c_uint64),
-                ("sparse_overfull", C.c_uint64)]
+                ("sparse_uniform_nb", C.c_uint32), ("reserved0", C.c_uint32), ("sa_bytes", C.c_uint64)]
 
 
 _VP, _VPP = C.c_void_p, C.POINTER(C.c_void_p)

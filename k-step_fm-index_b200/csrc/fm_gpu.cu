@@ -302,7 +302,7 @@ extern "C" int32_t fmgpu_index_alloc_like(int32_t device, const fmgpu_index_meta
   idx->meta.fused_bases = 0; idx->meta.fused_lanes = 0; idx->meta.fused_bytes = 0; idx->meta.start_bases = 0;
   idx->meta.sparse_bases = 0; idx->meta.sparse_lambda = 0; idx->meta.sparse_bytes = 0; idx->meta.sparse_blocks = 0;
   idx->meta.sparse_overflow = 0; idx->meta.sparse_start_bases = 0; idx->meta.sparse_lanes = 0; idx->meta.tail_bytes = 0;
-  idx->meta.sparse_uniform_nb = 0; idx->meta.sa_bytes = 0; idx->meta.sparse_ext_blocks = 0; idx->meta.sparse_overfull = 0;
+  idx->meta.sparse_uniform_nb = 0; idx->meta.sa_bytes = 0;
   cudaError_t e = cudaMalloc((void **) &idx->blocks, meta->nbytes);
   if (e != cudaSuccess) { free(idx); return fm_fail(e, "cudaMalloc(SB96 replica)", __FILE__, __LINE__); }
   *out = idx;
@@ -558,7 +558,7 @@ extern "C" int32_t fmgpu_index_unsparsify(fmgpu_index_t *idx)
     for (int b = 0; b < 16; b++) { cudaFree(idx->slead[b]); idx->slead[b] = NULL; }
     idx->slead_tried = 0;
   }
-  idx->s_uni_nb = 0; idx->s_uni_scale = 0; idx->meta.sparse_uniform_nb = 0; idx->meta.sparse_ext_blocks = 0; idx->meta.sparse_overfull = 0;
+  idx->s_uni_nb = 0; idx->s_uni_scale = 0; idx->meta.sparse_uniform_nb = 0;
   idx->meta.sparse_bases = 0; idx->meta.sparse_lambda = 0; idx->meta.sparse_bytes = 0; idx->meta.sparse_blocks = 0;
   idx->meta.sparse_overflow = 0; idx->meta.sparse_start_bases = 0; idx->meta.sparse_lanes = 0;
   return FM_SUCCESS;
@@ -606,8 +606,8 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
   if (e == cudaSuccess) e = cudaMalloc((void **) &first, 4ull * nsym);
   if (e == cudaSuccess) e = cudaMalloc((void **) &rank0, 4ull * nsym);
   if (e == cudaSuccess) e = cudaMalloc((void **) &dir, 8ull * nsym);
-  if (e == cudaSuccess) e = cudaMalloc((void **) &d_novf, 24);
-  if (e == cudaSuccess) e = cudaMemset(d_novf, 0, 24);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &d_novf, 8);
+  if (e == cudaSuccess) e = cudaMemset(d_novf, 0, 8);
   if (e == cudaSuccess) {
     fm_fuse_symbols_kernel<<<(idx->meta.nblocks + 127) / 128, 128>>>(idx->blocks, idx->meta.nblocks, idx->meta.nsymbols, nrows, sym);
     e = cudaGetLastError();
@@ -661,36 +661,25 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
   }
   /* the sort's input buffers are dead now: release them before the table is allocated */
   cudaFree(keys); keys = NULL; cudaFree(rows); rows = NULL; cudaFree(sym); sym = NULL;
+  if (e == cudaSuccess && total_blocks >= (1ull << 32)) e = cudaErrorInvalidValue;
+  if (e == cudaSuccess) e = cudaMalloc((void **) &sblocks, total_blocks * bbytes);
   if (e == cudaSuccess) {
     fm_sparse_dir_kernel<<<(nsym + 255) / 256, 256>>>(idx->blocks, idx->meta.nblocks, kbits, hops, nsym, n, nb, first, dir, rank0);
     e = cudaGetLastError();
   }
-  /* overfull buckets: how many extension blocks they need (those too big for an extension are left to SB96 steps) */
-  unsigned long long ovc[3] = { 0, 0, 0 };
   if (e == cudaSuccess) {
-    if (lanes == 4) fm_sparse_ext_count_kernel<4><<<nsym, 128>>>(rows2, symstart, dir, nb, d_novf);
-    else            fm_sparse_ext_count_kernel<2><<<nsym, 128>>>(rows2, symstart, dir, nb, d_novf);
+    if (lanes == 4) fm_sparse_fill_kernel<4><<<nsym, 128>>>(rows2, symstart, dir, nb, rank0, sblocks, d_novf);
+    else            fm_sparse_fill_kernel<2><<<nsym, 128>>>(rows2, symstart, dir, nb, rank0, sblocks, d_novf);
     e = cudaGetLastError();
   }
-  if (e == cudaSuccess) e = cudaMemcpy(ovc, d_novf, 24, cudaMemcpyDeviceToHost);
-  const uint64_t ext_blocks = ovc[0];
-  novf = ovc[1];
-  if (e == cudaSuccess && total_blocks + ext_blocks >= (1ull << 32)) e = cudaErrorInvalidValue;
-  if (e == cudaSuccess) e = cudaMalloc((void **) &sblocks, (total_blocks + ext_blocks) * bbytes);
-  if (e == cudaSuccess) e = cudaMemset(d_novf, 0, 8);                                  /* now the extension cursor */
-  if (e == cudaSuccess) {
-    if (lanes == 4) fm_sparse_fill_kernel<4><<<nsym, 128>>>(rows2, symstart, dir, nb, rank0, sblocks, (uint32_t) total_blocks, d_novf);
-    else            fm_sparse_fill_kernel<2><<<nsym, 128>>>(rows2, symstart, dir, nb, rank0, sblocks, (uint32_t) total_blocks, d_novf);
-    e = cudaGetLastError();
-  }
+  if (e == cudaSuccess) e = cudaMemcpy(&novf, d_novf, 8, cudaMemcpyDeviceToHost);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   cudaFree(sym); cudaFree(keys); cudaFree(rows); cudaFree(keys2); cudaFree(rows2); cudaFree(symstart); cudaFree(nb); cudaFree(first);
   cudaFree(rank0); cudaFree(tmp); cudaFree(d_novf);
   if (e != cudaSuccess) { cudaFree(sblocks); cudaFree(dir); return fm_fail(e, "fmgpu_index_sparsify", __FILE__, __LINE__); }
   idx->sblocks = sblocks; idx->sdir = dir; idx->s_uni_nb = uni_nb; idx->s_uni_scale = uni_scale; idx->meta.sparse_uniform_nb = uni_nb;
   idx->meta.sparse_bases = ks; idx->meta.sparse_lambda = lambda; idx->meta.sparse_blocks = total_blocks;
-  idx->meta.sparse_overflow = novf; idx->meta.sparse_bytes = (total_blocks + ext_blocks) * bbytes + 8ull * nsym; idx->meta.sparse_lanes = lanes;
-  idx->meta.sparse_ext_blocks = (uint32_t) ext_blocks; idx->meta.sparse_overfull = ovc[2];
+  idx->meta.sparse_overflow = novf; idx->meta.sparse_bytes = total_blocks * bbytes + 8ull * nsym; idx->meta.sparse_lanes = lanes;
 
   /* start table: the sparse kernel itself searches every SB-mer once (a packed SB-mer IS its key); SB = the
    * largest whole number of sparse steps within 12 bases */

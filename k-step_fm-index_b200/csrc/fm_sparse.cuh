@@ -27,11 +27,9 @@
  *   one rank     = dir[sigma] (L2 hit; sigma is known in advance, the lookup is issued one step ahead)
  *                  + ONE block fetch by LANES lanes x 256 bits;  rank = word 0 + #{ entries < X }
  *   L and R      almost always share the block (a bucket spans bwtsize / nb rows), so a step is one fetch
- *   overflow     a bucket with more occurrences than slots keeps them in EXTENSION blocks (8*LANES rows each) behind the
- *                table; its own block holds the first row of every extension block, so ONE more fetch finds the
- *                boundary (fm_sparse_rank_ext).  Buckets beyond 8*LANES - 3 extension blocks (208 rows at 64-byte
- *                blocks) are marked E = 0 and send that read through `hops` ordinary steps on the SB96 table -- exact
- *                either way; repeats of a real genome cost speed, never correctness
+ *   overflow     a block marked 0xFFFFFFFE sends that read through `hops` ordinary steps on the SB96 table for
+ *                this symbol -- exact, and rare by construction (Poisson tail for lambda = 16: 2e-4 per fetch on a
+ *                random text; repeats of a real genome cost speed, never correctness)
  *
  * Table size is ~128 / lambda bytes per text base for ANY KS (8 B/base at lambda = 16: 16 GB for 2 Gbp, a quarter
  * of the fused table) and a 100-bp read needs 10 fetches at KS = 10 instead of 25 (9 after the start table).
@@ -96,48 +94,6 @@ template <int LANES> __device__ __forceinline__ void fm_sparse_load(const uint4 
 {
   if (LANES == 2) fm_ldg32(p, w);          /* 64-byte block: 64-byte L2 fill */
   else            fm_ldg32_line(p, w);
-}
-
-/* rank of X in a bucket whose block words are w (this lane's 8 of them), for normal blocks and for overfull ones that carry
- * an EXTENSION: header block = { rank at bucket start, pivots (first row of extension block 1, 2, ..), .., E, first extension
- * block, 0xFFFFFFFE }, extension blocks = the bucket's rows, 8*LANES per block, no header.  e = #{ pivots < X } selects the
- * one extension block that holds the boundary: rank = start rank + 8*LANES*e + #{ its rows < X } -- ONE more fetch instead
- * of `hops` SB96 steps.  Returns false for a bucket too big for an extension (E = 0): the caller takes the SB96 steps.
- * Shuffles use the lane group's own mask: groups enter here independently of each other. */
-template <int LANES, bool COUNT>
-__device__ __forceinline__ bool fm_sparse_rank_ext(const FmSparseParams &p, const uint32_t (&w)[8], uint32_t X, uint32_t lg, uint32_t gmask,
-                                                   uint32_t &rank, unsigned long long &n_sp)
-{
-  const uint32_t lane = threadIdx.x & 31u, g0 = lane & ~(uint32_t)(LANES - 1), glast = g0 + LANES - 1;
-  const bool is_ovf = __shfl_sync(gmask, w[7], glast) == FM_SP_OVF;
-  const uint32_t start = __shfl_sync(gmask, w[0], g0);
-  uint32_t c = 0;
-  if (!is_ovf) {
-    c = fm_sparse_partial(w, X, lg);
-    #pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) c += __shfl_xor_sync(gmask, c, o);
-    rank = start + c;
-    return true;
-  }
-  const uint32_t E = __shfl_sync(gmask, w[5], glast), ext0 = __shfl_sync(gmask, w[6], glast);
-  if (E == 0u) return false;
-  #pragma unroll
-  for (int j = 0; j < 8; j++) {
-    const bool skip = (lg == 0u && j == 0) || (lg == (uint32_t)(LANES - 1) && j >= 5);
-    c += (!skip && w[j] < X) ? 1u : 0u;
-  }
-  #pragma unroll
-  for (int o = LANES / 2; o > 0; o >>= 1) c += __shfl_xor_sync(gmask, c, o);        /* c = extension block holding the boundary */
-  uint32_t v[8];
-  fm_sparse_load<LANES>(p.sblocks + (size_t)(ext0 + c) * (2u * LANES) + 2u * lg, v);
-  if (COUNT && lg == 0) n_sp += 1;
-  uint32_t c2 = 0;
-  #pragma unroll
-  for (int j = 0; j < 8; j++) c2 += (v[j] < X) ? 1u : 0u;
-  #pragma unroll
-  for (int o = LANES / 2; o > 0; o >>= 1) c2 += __shfl_xor_sync(gmask, c2, o);
-  rank = start + 8u * LANES * c + c2;
-  return true;
 }
 
 template <int K, int LANES, int QPT, int THREADS, int MINB, bool COUNT>
@@ -283,35 +239,20 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_kernel(const F
       ob[i] = (__ballot_sync(0xFFFFFFFFu, ovf[i]) >> ((threadIdx.x & 31u) & ~(uint32_t)(LANES - 1))) & ((1u << LANES) - 1u);
       any_ovf |= (ob[i] != 0u);
     }
-    if (__any_sync(0xFFFFFFFFu, any_ovf)) {
-      /* overfull bucket (L's, R's or both): ranks through its extension block, or -- too big for an extension -- the same
-       * `hops` ordinary steps on SB96.  The bucket blocks are fetched again here (L2 hits) instead of being kept: holding
-       * 8 words per read across the test above would spill registers in the loop every read runs. */
-      const uint32_t gmask = ((1u << LANES) - 1u) << ((threadIdx.x & 31u) & ~(uint32_t)(LANES - 1));
+    if (__any_sync(0xFFFFFFFFu, any_ovf)) {                   /* rare: overfull bucket -> the same `hops` steps on SB96 */
       #pragma unroll
       for (int i = 0; i < QPT; i++) {
         if (ob[i]) {
-          const uint2 dn = fm_sparse_dir(p, sig_now[i]);
-          const uint32_t bL = __umulhi(L[i], dn.y), bR = __umulhi(R[i], dn.y);
-          const uint4 *base = p.sblocks + (size_t) dn.x * BU4 + 2u * lg;
-          uint32_t xl = L[i], xr = R[i], v[8];
-          unsigned long long ext_fetches = 0;
-          fm_sparse_load<LANES>(base + (size_t) bL * BU4, v);
-          const bool okL = fm_sparse_rank_ext<LANES, COUNT>(p, v, L[i], lg, gmask, xl, ext_fetches);
-          if (bL != bR) fm_sparse_load<LANES>(base + (size_t) bR * BU4, v);
-          const bool okR = fm_sparse_rank_ext<LANES, COUNT>(p, v, R[i], lg, gmask, xr, ext_fetches);
-          if (COUNT && live[i]) n_sp += ext_fetches;
-          if (okL && okR) { nL[i] = xl; nR[i] = xr; continue; }
-          xl = L[i]; xr = R[i];
+          uint32_t xl = L[i], xr = R[i];
           for (uint32_t h = 0; h < p.hops; h++) {
             const uint32_t s = (sig_now[i] >> (BBITS * h)) & BMASK;
-            const uint32_t cL = fm_div96(xl), cR = fm_div96(xr);
-            const uint4 *sb = p.blocks + (size_t) s * p.nblocks;
-            const uint4 vL = fm_ldg16(sb + cL);
-            const uint4 vR = (cL == cR) ? vL : fm_ldg16(sb + cR);
-            if (COUNT && live[i] && lg == 0) n_sb += (cL == cR) ? 1 : 2;
-            xl = fm_block_rank(vL, xl - cL * FM_SB_ROWS);
-            xr = fm_block_rank(vR, xr - cR * FM_SB_ROWS);
+            const uint32_t bL = fm_div96(xl), bR = fm_div96(xr);
+            const uint4 *base = p.blocks + (size_t) s * p.nblocks;
+            const uint4 vL = fm_ldg16(base + bL);
+            const uint4 vR = (bL == bR) ? vL : fm_ldg16(base + bR);
+            if (COUNT && live[i] && lg == 0) n_sb += (bL == bR) ? 1 : 2;
+            xl = fm_block_rank(vL, xl - bL * FM_SB_ROWS);
+            xr = fm_block_rank(vR, xr - bR * FM_SB_ROWS);
           }
           nL[i] = xl; nR[i] = xr;
           if (COUNT && live[i] && lg == 0) n_ovf += 1;
@@ -421,74 +362,28 @@ __global__ void fm_sparse_dir_kernel(const uint4 *__restrict__ blocks, uint32_t 
   rank0[s] = x;
 }
 
-/* bucket j of a symbol: [t0, t0 + cnt) = its occurrences in the symbol's sorted row list */
-__device__ __forceinline__ void fm_sparse_bucket(const uint32_t *__restrict__ rows, uint32_t s0, uint32_t s1, uint32_t scale, uint32_t j,
-                                                 uint32_t &t0, uint32_t &cnt)
-{
-  uint32_t lo = s0, hi = s1;                                   /* first occurrence whose bucket is >= j */
-  while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__umulhi(rows[mid], scale) < j) lo = mid + 1; else hi = mid; }
-  t0 = lo;
-  hi = s1;                                                     /* first occurrence whose bucket is > j */
-  while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__umulhi(rows[mid], scale) <= j) lo = mid + 1; else hi = mid; }
-  cnt = lo - t0;
-}
-
-/* extension blocks the overfull buckets need: counters[0] += E per bucket with slots < cnt <= 8*LANES*(8*LANES - 3),
- * counters[1] += 1 per bucket bigger than that (served by SB96 steps), counters[2] += 1 per overfull bucket */
-template <int LANES>
-__global__ void __launch_bounds__(128) fm_sparse_ext_count_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ symstart,
-                                                                  const uint2 *__restrict__ dir, const uint32_t *__restrict__ nb,
-                                                                  unsigned long long *__restrict__ counters)
-{
-  constexpr uint32_t WORDS = 8u * LANES, SLOTS = WORDS - 1u, EMAX = WORDS - 3u;
-  const uint32_t s = blockIdx.x;
-  const uint32_t s0 = symstart[s], s1 = symstart[s + 1], scale = dir[s].y, n = nb[s];
-  if (s1 - s0 <= SLOTS) return;                                /* no bucket of this symbol can overflow */
-  for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
-    uint32_t t0, cnt;
-    fm_sparse_bucket(rows, s0, s1, scale, j, t0, cnt);
-    if (cnt > SLOTS) {
-      const uint32_t E = (cnt + WORDS - 1u) / WORDS;
-      atomicAdd(counters + 2, 1ull);
-      if (E <= EMAX) atomicAdd(counters, (unsigned long long) E); else atomicAdd(counters + 1, 1ull);
-    }
-  }
-}
-
-/* one CTA per symbol, one thread per block of the symbol; extension blocks are carved from [ext_base, ..) with a cursor */
+/* one CTA per symbol, one thread per block of the symbol */
 template <int LANES>
 __global__ void __launch_bounds__(128) fm_sparse_fill_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ symstart,
                                                              const uint2 *__restrict__ dir, const uint32_t *__restrict__ nb,
                                                              const uint32_t *__restrict__ rank0, uint4 *__restrict__ sblocks,
-                                                             uint32_t ext_base, unsigned long long *__restrict__ ext_cursor)
+                                                             unsigned long long *__restrict__ novf)
 {
-  constexpr uint32_t WORDS = 8u * LANES, SLOTS = WORDS - 1u, EMAX = WORDS - 3u;
   const uint32_t s = blockIdx.x;
   const uint32_t s0 = symstart[s], s1 = symstart[s + 1], scale = dir[s].y, first = dir[s].x, n = nb[s], r0 = rank0[s];
   for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
-    uint32_t t0, cnt;
-    fm_sparse_bucket(rows, s0, s1, scale, j, t0, cnt);
+    uint32_t lo = s0, hi = s1;                                 /* first occurrence whose bucket is >= j */
+    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__umulhi(rows[mid], scale) < j) lo = mid + 1; else hi = mid; }
+    const uint32_t t0 = lo;
+    hi = s1;                                                   /* first occurrence whose bucket is > j */
+    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__umulhi(rows[mid], scale) <= j) lo = mid + 1; else hi = mid; }
+    const uint32_t cnt = lo - t0;
+    constexpr uint32_t WORDS = 8u * LANES, SLOTS = WORDS - 1u;
     uint32_t w[WORDS];
     w[0] = r0 + (t0 - s0);
     #pragma unroll
     for (uint32_t c = 1; c < WORDS; c++) w[c] = (c - 1 < cnt && cnt <= SLOTS) ? rows[t0 + c - 1] : FM_SP_PAD;
-    if (cnt > SLOTS) {
-      const uint32_t E = (cnt + WORDS - 1u) / WORDS;
-      w[WORDS - 1] = FM_SP_OVF; w[WORDS - 2] = 0u; w[WORDS - 3] = 0u;          /* E = 0: too big, SB96 steps */
-      if (E <= EMAX) {
-        const uint32_t ext0 = ext_base + (uint32_t) atomicAdd(ext_cursor, (unsigned long long) E);
-        w[WORDS - 3] = E; w[WORDS - 2] = ext0;
-        for (uint32_t m = 1; m < E; m++) w[m] = rows[t0 + m * WORDS];            /* pivots: first row of extension block m */
-        for (uint32_t m = 0; m < E; m++) {
-          uint4 *dst = sblocks + (size_t)(ext0 + m) * (2u * LANES);
-          for (uint32_t c = 0; c < 2u * LANES; c++) {
-            uint32_t x[4];
-            for (uint32_t z = 0; z < 4; z++) { const uint32_t o = m * WORDS + 4 * c + z; x[z] = o < cnt ? rows[t0 + o] : FM_SP_PAD; }
-            dst[c] = make_uint4(x[0], x[1], x[2], x[3]);
-          }
-        }
-      }
-    }
+    if (cnt > SLOTS) { w[WORDS - 1] = FM_SP_OVF; atomicAdd(novf, 1ull); }
     uint4 *dst = sblocks + (size_t)(first + j) * (2u * LANES);
     #pragma unroll
     for (uint32_t c = 0; c < 2u * LANES; c++) dst[c] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
