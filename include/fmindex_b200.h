@@ -342,8 +342,8 @@ int32_t fmgpu_host_unregister(void *p);
  * Builds, on `device`, the image of the reference's tag-100 ".fmi" FILE
  * (header + entries, byte-identical to what genFMindex writes,
  * src/genFMindex.c:155-181,457-543) for an ASCII text or for the synthetic
- * text of fm_synth.h.  k in {1,2}.  Fails with FM_E_BUILDING_BWT on texts with
- * long repeats (more than 2048 suffixes sharing 32 bases). */
+ * text of fm_synth.h.  k in {1,2}; any text (repetitive texts take a prefix-doubling
+ * pass over their tied suffixes); 2k <= n < 2^32 - 2. */
 typedef struct fmgpu_build fmgpu_build_t;
 int32_t  fmgpu_build_from_text(int32_t device, const char *h_ascii, uint64_t n, uint32_t steps, uint32_t chunk, fmgpu_build_t **out);
 int32_t  fmgpu_build_from_synth(int32_t device, uint64_t n, uint64_t seed, uint32_t steps, uint32_t chunk, fmgpu_build_t **out);
