@@ -564,6 +564,7 @@ extern "C" int32_t fmgpu_index_unsparsify(fmgpu_index_t *idx)
   return FM_SUCCESS;
 }
 
+static thread_local bool g_require_uniform = false;          /* set while the automatic choice tries 12 bases per step */
 extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_bases, uint32_t lambda, uint32_t lanes)
 {
   if (!idx) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null index");
@@ -578,7 +579,16 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
   if (lambda == 0) lambda = lanes == 4 ? 12 : 5;
   if (lambda > slots) return fm_fail_msg(FM_E_BAD_ARGUMENT, "lambda must not exceed the slots of a block (15 or 31)");
   uint32_t ks = sparse_bases;
-  if (ks == 0) {                                               /* widest multiple of k up to 10 with >= 64 rows per symbol */
+  if (ks == 0) {
+    /* 12 bases per step when that table can be a uniform grid (a directory of 4^12 entries would not stay in L2): tried first,
+     * given up as soon as the symbol counts turn out uneven.  Else the widest multiple of k up to 10 with >= 64 rows per symbol. */
+    const char *env = getenv("FMGPU_SPARSE_UNIFORM");
+    if (12 % k == 0 && (((uint64_t) 64) << 24) <= n && !g_require_uniform && !(env && *env && atoi(env) == 0)) {
+      g_require_uniform = true;
+      const int32_t rc12 = fmgpu_index_sparsify(idx, 12, lambda, lanes);
+      g_require_uniform = false;
+      if (rc12 == FM_SUCCESS) return FM_SUCCESS;
+    }
     for (uint32_t cand = 10; cand >= 2 * k; cand--)
       if (cand % k == 0 && (((uint64_t) 64) << (2 * cand)) <= n) { ks = cand; break; }
     if (ks == 0) ks = 2 * k;
@@ -626,8 +636,8 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
     e = cudaGetLastError();
   }
   /* uniform grid or per-symbol block counts?  $FMGPU_SPARSE_UNIFORM = 0 / 1 forces; default: uniform when no symbol occurs
-   * more than 1.35 x as often as the mean (its blocks then expect <= 6.75 rows at lambda 5: < 0.2 % of them overflow 15
-   * slots, far cheaper than a directory lookup in every step) nor less than half as often (wasted blocks) */
+   * more than 1.6 x as often as the mean (its blocks then expect <= 8 rows at lambda 5: < 1 % of THOSE symbols' blocks
+   * overflow 15 slots, far cheaper than a directory lookup in every step) nor less than 0.4 x as often (wasted blocks) */
   uint32_t uni_nb = 0, uni_scale = 0;
   if (e == cudaSuccess) {
     uint32_t range[2] = { 0xFFFFFFFFu, 0u }, carrying = 0;
@@ -639,7 +649,7 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
     if (e == cudaSuccess) {
       const double mean = (double) carrying / nsym;
       const char *env = getenv("FMGPU_SPARSE_UNIFORM");
-      const bool want = env && *env ? atoi(env) != 0 : (mean >= lambda && range[0] >= 0.5 * mean && range[1] <= 1.35 * mean);
+      const bool want = env && *env ? atoi(env) != 0 : (mean >= lambda && range[0] >= 0.4 * mean && range[1] <= 1.6 * mean);
       const uint64_t per = ((uint64_t) carrying + (uint64_t) nsym * lambda - 1) / ((uint64_t) nsym * lambda);
       if (want && per >= 1 && per * nsym < (1ull << 32)) {
         uni_nb = (uint32_t) per;
@@ -647,6 +657,11 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
         uni_scale = sc > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t) sc;
       }
     }
+  }
+  if (e == cudaSuccess && g_require_uniform && !uni_nb) {      /* the 12-base attempt of the automatic choice: counts are uneven */
+    cudaFree(sym); cudaFree(keys); cudaFree(rows); cudaFree(keys2); cudaFree(rows2); cudaFree(symstart); cudaFree(nb); cudaFree(first);
+    cudaFree(rank0); cudaFree(tmp); cudaFree(d_novf); cudaFree(dir);
+    return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "symbol counts too uneven for a uniform grid");
   }
   if (e == cudaSuccess) {
     fm_sparse_nblocks_kernel<<<(nsym + 255) / 256, 256>>>(symstart, nsym, lambda, uni_nb, nb);
@@ -702,7 +717,7 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
     }
     /* lead tables (fm_ensure_lead): the small ones now, the wide ones (12 .. 15 bases, up to 8.6 GB) when a read length asks */
     if (want && idx->sstart)
-      for (uint32_t b = 6; b <= ks + 1 && b < 12; b++) fm_ensure_lead(idx, b);
+      for (uint32_t b = 1; b <= ks + 1 && b < 12; b++) fm_ensure_lead(idx, b);
   }
   return FM_SUCCESS;
 }
@@ -718,7 +733,7 @@ static thread_local bool g_building_lead = false;
 static const uint2 *fm_ensure_lead(const fmgpu_index_t *cidx, uint32_t b)
 {
   fmgpu_index_t *idx = const_cast<fmgpu_index_t *>(cidx);
-  if (b < 6 || b >= 16 || !idx->sstart) return NULL;
+  if (b < 1 || b >= 16 || !idx->sstart) return NULL;
   std::lock_guard<std::mutex> lock(g_lead_mutex);
   if (idx->slead[b]) return idx->slead[b];
   if (idx->slead_tried & (1u << b)) return NULL;
@@ -774,9 +789,13 @@ static int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_pack
   const uint32_t m = idx->sstart ? idx->meta.sparse_start_bases / ks : 0u;
   const uint32_t lb = len - S * ks;                            /* leftover bases, the odd one included */
   uint32_t lead = 0;
-  if (idx->sstart && !g_building_lead) {                       /* (a lead table is computed without lead tables) */
-    if (lb >= 6 && lb < 16 && S >= 1 && fm_ensure_lead(idx, lb)) lead = lb;
-    else if (lb >= 1 && lb < 6 && S >= 2 && lb + ks < 16 && lb + ks > idx->meta.sparse_start_bases && fm_ensure_lead(idx, lb + ks)) lead = lb + ks;
+  if (idx->sstart && !g_building_lead && lb >= 1) {            /* (a lead table is computed without lead tables) */
+    /* the leftover bases themselves when the interval they leave is much narrower than a bucket (4^lb >= 8 x blocks per
+     * symbol: the first sparse step then rarely needs two fetches), else leftover + one sparse step's bases (12 .. 15) */
+    const uint64_t nb_mean = idx->meta.sparse_blocks >> (2 * ks);
+    const bool narrow = lb < 16 && ((uint64_t) 1 << (2 * lb)) >= 8 * (nb_mean ? nb_mean : 1);
+    if (narrow && S >= 1 && fm_ensure_lead(idx, lb)) lead = lb;
+    else if (!narrow && S >= 2 && lb + ks < 16 && lb + ks > idx->meta.sparse_start_bases && fm_ensure_lead(idx, lb + ks)) lead = lb + ks;
   }
   p.nfront = 0; p.nback = 0; p.nsteps = S; p.start = NULL; p.start_bits = 0;
   if (lead) { p.start = idx->slead[lead]; p.start_bits = 2 * lead; p.nsteps = S - (lead > lb ? 1u : 0u); }

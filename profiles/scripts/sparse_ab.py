@@ -13,7 +13,7 @@ lengths = [int(x) for x in os.environ.get("FM_LENS", "100").split(",")]
 qpts = [int(x) for x in os.environ.get("FM_QPTS", "4,3,5,6,8").split(",")]
 L = pkg.lib()
 b = pkg.IndexBuild.from_synth(n, 1, 2, 64); idx = b.to_index(); b.free()
-idx.sparsify(0, 0, 0)
+idx.sparsify(int(os.environ.get("FM_KS", "0")), 0, 0); print(json.dumps({"ks": idx.meta.sparse_bases, "uniform_nb": idx.meta.sparse_uniform_nb, "overflow": int(idx.meta.sparse_overflow), "blocks": int(idx.meta.sparse_blocks), "gb": idx.meta.sparse_bytes / 1e9}), flush=True)
 stream = torch.cuda.current_stream().cuda_stream
 d_res = torch.zeros(2 * nq, dtype=torch.int32, device="cuda")
 for length in lengths:

@@ -267,11 +267,17 @@ def test_sparse_config3_full_size_against_reference_checksums(pkg):
     for tag, key in ((100, "res_cpu_std_text"), (201, "res_cpu_ac_text")):
         t = b if tag == 100 else b.transform(tag)
         idx = t.to_index().sparsify()
-        m = idx.meta
-        assert (m.sparse_bases, m.sparse_lanes, m.sparse_start_bases) == (10, 2, 10) and m.sparse_bytes < 30e9
+        m = idx.meta                                             # automatic choice on this text: 12 bases per step, uniform grid
+        assert (m.sparse_bases, m.sparse_lanes, m.sparse_start_bases) == (12, 2, 12) and m.sparse_uniform_nb > 0 and m.sparse_bytes < 30e9
         for qpt in (2, 4):
             batch.search(idx, pkg.variant(pkg.MODE_SPARSE, qpt))
             assert helpers.results_text_md5(batch.download()) == gold["md5"][key], f"tag {tag} qpt {qpt}"
+        idx.unsparsify()
+        idx.sparsify(10, 0, 0)                                   # and the 10-base table (what uneven symbol counts get, with a directory then)
+        m = idx.meta
+        assert (m.sparse_bases, m.sparse_lanes, m.sparse_start_bases) == (10, 2, 10) and m.sparse_bytes < 30e9
+        batch.search(idx, pkg.variant(pkg.MODE_SPARSE, 4))
+        assert helpers.results_text_md5(batch.download()) == gold["md5"][key], f"tag {tag} 10 bases"
         idx.free()
         if tag != 100:
             t.free()
