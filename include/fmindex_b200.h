@@ -264,10 +264,10 @@ int32_t fmgpu_index_fuse(fmgpu_index_t *idx, uint32_t fused_bases, uint32_t lane
 int32_t fmgpu_index_unfuse(fmgpu_index_t *idx);
 /* Sparse-step table, built on the GPU from this replica's own block table: one sparse step = sparse_bases/k
  * reference LF steps (exactly); per wide symbol the occurrence rows are cut into blocks of ~lambda rows, one block
- * fetch per rank (csrc/fm_sparse.cuh).  sparse_bases 0 = the widest multiple of k up to 10 that leaves at least
- * 64 rows per symbol; lanes 0 = 2 (64-byte blocks, 15 slots; 4 = 128-byte blocks, 31 slots); lambda 0 = 5 / 12;
+ * fetch per rank (csrc/fm_sparse.cuh).  sparse_bases 0 = 12 when the table can then be a uniform grid (see below; needs
+ * >= 64 rows per 12-mer), else the widest multiple of k up to 10 that leaves at least 64 rows per symbol; lanes 0 = 2 (64-byte blocks, 15 slots; 4 = 128-byte blocks, 31 slots); lambda 0 = 5 / 12;
  * the table takes ~32*lanes/lambda bytes per text base whatever the width.  Blocks with more occurrences than
- * slots (repeats) are served by ordinary steps on the block table.  When no wide symbol occurs more than 1.35 x as
+ * slots (repeats) are served by ordinary steps on the block table.  When no wide symbol occurs more than 1.6 x as
  * often as the mean (uniformly random texts) the table is a uniform grid -- the same block count for every symbol,
  * no directory lookup in the kernel (meta.sparse_uniform_nb; $FMGPU_SPARSE_UNIFORM=0/1 forces).
  * FM_E_NOT_IMPLEMENTED when memory does not suffice or the index carries the AltCounters padding quirk. */

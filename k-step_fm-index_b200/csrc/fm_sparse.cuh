@@ -19,8 +19,8 @@
  *                           (31 slots in a 128-byte block, LANES = 4; 15 in a 64-byte block, LANES = 2)
  *                           a bucket with more occurrences than slots stores 0xFFFFFFFE in the last word instead
  *   directory               dir[sigma] = { first block, scale }     (8 bytes x 4^KS: L2-resident for KS <= 10)
- *   uniform grid            when every symbol occurs about equally often (a uniformly random text: no count above 1.35 x the
- *                           mean or below half of it) all symbols get the SAME number of blocks, first block = sigma * nb, one scale:
+ *   uniform grid            when every symbol occurs about equally often (a uniformly random text: no count above 1.6 x the
+ *                           mean or below 0.4 x of it) all symbols get the SAME number of blocks, first block = sigma * nb, one scale:
  *                           the directory lookup -- an L2 request per step that costs 15 % of the fetch rate -- is
  *                           replaced by a multiplication.  Skewed texts (any real genome) keep per-symbol block counts.
  *

@@ -216,7 +216,7 @@ def test_sparse_start_table_and_fetch_counter(pkg, k):
 
 
 def test_sparse_uniform_grid_is_chosen_for_even_symbol_counts_only(pkg, monkeypatch):
-    """Default choice of the layout: a uniform grid (no directory lookups) when no wide symbol occurs more than 1.35 x as
+    """Default choice of the layout: a uniform grid (no directory lookups) when no wide symbol occurs more than 1.6 x as
     often as the mean (nor less than half) -- a uniformly random text with many rows per symbol -- and per-symbol block
     counts otherwise.  Same (L,R)."""
     monkeypatch.delenv("FMGPU_SPARSE_UNIFORM", raising=False)
