@@ -36,6 +36,7 @@ struct fmgpu_index {
   uint4             *sblocks;      /* sparse-step table (fmgpu_index_sparsify), or NULL */
   uint2             *sdir;         /* its directory: { first block, scale } per wide symbol */
   uint2             *sstart;       /* start table of the sparse kernel, or NULL */
+  int                stables;      /* start / lead tables are in use for this replica's sparse table (large indexes, or $FMGPU_START_TABLE=1) */
   uint32_t           slead_tried;  /* bit b: building slead[b] was attempted */
   uint2             *slead[16];    /* lead tables: (L,R) of all b-mers, b = 6 .. sparse_bases - 1 (multiples of k), or NULL */
   uint4             *tail1;        /* tail table (fm_tail_table_kernel): built by the first odd-length search on this replica */
@@ -558,6 +559,7 @@ extern "C" int32_t fmgpu_index_unsparsify(fmgpu_index_t *idx)
     for (int b = 0; b < 16; b++) { cudaFree(idx->slead[b]); idx->slead[b] = NULL; }
     idx->slead_tried = 0;
   }
+  idx->stables = 0;
   idx->s_uni_nb = 0; idx->s_uni_scale = 0; idx->meta.sparse_uniform_nb = 0;
   idx->meta.sparse_bases = 0; idx->meta.sparse_lambda = 0; idx->meta.sparse_bytes = 0; idx->meta.sparse_blocks = 0;
   idx->meta.sparse_overflow = 0; idx->meta.sparse_start_bases = 0; idx->meta.sparse_lanes = 0;
@@ -583,17 +585,23 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
     /* 12 bases per step when that table can be a uniform grid (a directory of 4^12 entries would not stay in L2): tried first,
      * given up as soon as the symbol counts turn out uneven.  Else the widest multiple of k up to 10 with >= 64 rows per symbol. */
     const char *env = getenv("FMGPU_SPARSE_UNIFORM");
-    if (12 % k == 0 && (((uint64_t) 64) << 24) <= n && !g_require_uniform && !(env && *env && atoi(env) == 0)) {
-      g_require_uniform = true;
-      const int32_t rc12 = fmgpu_index_sparsify(idx, 12, lambda, lanes);
-      g_require_uniform = false;
-      if (rc12 == FM_SUCCESS) return FM_SUCCESS;
+    if (!g_require_uniform && !(env && *env && atoi(env) == 0)) {
+      /* 14 bases need >= lambda rows per 14-mer on average, 12 bases >= 64 rows per 12-mer */
+      const uint32_t wide[2] = { 14, 12 };
+      const uint64_t least[2] = { (uint64_t) lambda << 28, (uint64_t) 64 << 24 };
+      for (int c = 0; c < 2; c++) {
+        if (wide[c] % k || least[c] > n) continue;
+        g_require_uniform = true;
+        const int32_t rcw = fmgpu_index_sparsify(idx, wide[c], lambda, lanes);
+        g_require_uniform = false;
+        if (rcw == FM_SUCCESS) return FM_SUCCESS;
+      }
     }
     for (uint32_t cand = 10; cand >= 2 * k; cand--)
       if (cand % k == 0 && (((uint64_t) 64) << (2 * cand)) <= n) { ks = cand; break; }
     if (ks == 0) ks = 2 * k;
   }
-  if (ks % k || ks <= k || ks > 12) return fm_fail_msg(FM_E_BAD_ARGUMENT, "sparse bases must be a multiple of k, larger than k and at most 12");
+  if (ks % k || ks <= k || ks > 14) return fm_fail_msg(FM_E_BAD_ARGUMENT, "sparse bases must be a multiple of k, larger than k and at most 14");
   const uint32_t nsym = 1u << (2 * ks), hops = ks / k, kbits = 2 * k;
   const uint64_t nrows = (uint64_t) idx->meta.nblocks * FM_SB_ROWS;
   size_t free_b = 0, total_b = 0;
@@ -649,8 +657,16 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
     if (e == cudaSuccess) {
       const double mean = (double) carrying / nsym;
       const char *env = getenv("FMGPU_SPARSE_UNIFORM");
-      const bool want = env && *env ? atoi(env) != 0 : (mean >= lambda && range[0] >= 0.4 * mean && range[1] <= 1.6 * mean);
       const uint64_t per = ((uint64_t) carrying + (uint64_t) nsym * lambda - 1) / ((uint64_t) nsym * lambda);
+      /* rows living in symbols that cannot fit their share of the grid even if spread perfectly (count > slots x blocks) */
+      unsigned long long heavy = 0, *d_heavy = d_novf;            /* (d_novf is zero here: the fill kernel runs later) */
+      fm_sparse_heavy_rows_kernel<<<(nsym + 255) / 256, 256>>>(symstart, nsym, (uint32_t)(slots * (per ? per : 1)), d_heavy);
+      e = cudaGetLastError();
+      if (e == cudaSuccess) e = cudaMemcpy(&heavy, d_heavy, 8, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemset(d_heavy, 0, 8);
+      const bool even = mean >= lambda && range[1] <= 1.6 * mean && range[0] >= 0.4 * mean;          /* many rows per symbol: tight counts */
+      const bool sparse_even = mean >= lambda && mean < 64 && heavy * 1000ull <= carrying;           /* few rows per symbol (Poisson scatter): no heavy tail */
+      const bool want = env && *env ? atoi(env) != 0 : (even || sparse_even);
       if (want && per >= 1 && per * nsym < (1ull << 32)) {
         uni_nb = (uint32_t) per;
         unsigned long long sc = ((((unsigned long long) uni_nb) << 32) - 1ull) / n;    /* as fm_sparse_dir_kernel */
@@ -683,8 +699,12 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) {
-    if (lanes == 4) fm_sparse_fill_kernel<4><<<nsym, 128>>>(rows2, symstart, dir, nb, rank0, sblocks, d_novf);
-    else            fm_sparse_fill_kernel<2><<<nsym, 128>>>(rows2, symstart, dir, nb, rank0, sblocks, d_novf);
+    if (uni_nb && uni_nb < 32) {                               /* many symbols, few blocks each: one thread per block */
+      const unsigned grid = (unsigned)((total_blocks + 255) / 256);
+      if (lanes == 4) fm_sparse_fill_uniform_kernel<4><<<grid, 256>>>(rows2, symstart, nsym, uni_nb, uni_scale, rank0, sblocks, d_novf);
+      else            fm_sparse_fill_uniform_kernel<2><<<grid, 256>>>(rows2, symstart, nsym, uni_nb, uni_scale, rank0, sblocks, d_novf);
+    } else if (lanes == 4) fm_sparse_fill_kernel<4><<<nsym, 128>>>(rows2, symstart, dir, nb, rank0, sblocks, d_novf);
+    else                   fm_sparse_fill_kernel<2><<<nsym, 128>>>(rows2, symstart, dir, nb, rank0, sblocks, d_novf);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(&novf, d_novf, 8, cudaMemcpyDeviceToHost);
@@ -716,7 +736,8 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
       else { idx->sstart = table; idx->meta.sparse_start_bases = sb; idx->meta.sparse_bytes += (uint64_t) nkeys * 8; }
     }
     /* lead tables (fm_ensure_lead): the small ones now, the wide ones (12 .. 15 bases, up to 8.6 GB) when a read length asks */
-    if (want && idx->sstart)
+    idx->stables = want ? 1 : 0;
+    if (want)
       for (uint32_t b = 1; b <= ks + 1 && b < 12; b++) fm_ensure_lead(idx, b);
   }
   return FM_SUCCESS;
@@ -733,13 +754,13 @@ static thread_local bool g_building_lead = false;
 static const uint2 *fm_ensure_lead(const fmgpu_index_t *cidx, uint32_t b)
 {
   fmgpu_index_t *idx = const_cast<fmgpu_index_t *>(cidx);
-  if (b < 1 || b >= 16 || !idx->sstart) return NULL;
+  if (b < 1 || b >= 16 || !idx->stables) return NULL;
   std::lock_guard<std::mutex> lock(g_lead_mutex);
   if (idx->slead[b]) return idx->slead[b];
   if (idx->slead_tried & (1u << b)) return NULL;
   idx->slead_tried |= 1u << b;
   const uint32_t k = idx->meta.steps, n = idx->meta.bwtsize;
-  if (b == idx->meta.sparse_start_bases || (b % k && !(k == 2 && idx->meta.tail_valid)) || ((uint64_t) 1 << (2 * b)) >= n) return NULL;
+  if ((idx->sstart && b == idx->meta.sparse_start_bases) || (b % k && !(k == 2 && idx->meta.tail_valid)) || ((uint64_t) 1 << (2 * b)) >= n) return NULL;
   if (cudaSetDevice(idx->device) != cudaSuccess) { cudaGetLastError(); return NULL; }
   const uint32_t nkeys = 1u << (2 * b);
   size_t free_b = 0, total_b = 0;
@@ -789,13 +810,16 @@ static int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_pack
   const uint32_t m = idx->sstart ? idx->meta.sparse_start_bases / ks : 0u;
   const uint32_t lb = len - S * ks;                            /* leftover bases, the odd one included */
   uint32_t lead = 0;
-  if (idx->sstart && !g_building_lead && lb >= 1) {            /* (a lead table is computed without lead tables) */
+  if (idx->stables && !g_building_lead && (lb >= 1 || !m)) {   /* (a lead table is computed without lead tables) */
     /* the leftover bases themselves when the interval they leave is much narrower than a bucket (4^lb >= 8 x blocks per
-     * symbol: the first sparse step then rarely needs two fetches), else leftover + one sparse step's bases (12 .. 15) */
+     * symbol: the first sparse step then rarely needs two fetches), else leftover + one sparse step's bases (12 .. 15;
+     * with no leftover and no start table -- 14 bases per step -- the table of all 14-mers IS the start table) */
     const uint64_t nb_mean = idx->meta.sparse_blocks >> (2 * ks);
-    const bool narrow = lb < 16 && ((uint64_t) 1 << (2 * lb)) >= 8 * (nb_mean ? nb_mean : 1);
+    const bool narrow = lb >= 1 && lb < 16 && ((uint64_t) 1 << (2 * lb)) >= 8 * (nb_mean ? nb_mean : 1);
     if (narrow && S >= 1 && fm_ensure_lead(idx, lb)) lead = lb;
     else if (!narrow && S >= 2 && lb + ks < 16 && lb + ks > idx->meta.sparse_start_bases && fm_ensure_lead(idx, lb + ks)) lead = lb + ks;
+    else if (!narrow && lb >= 1 && S >= 1 && !m && fm_ensure_lead(idx, lb)) lead = lb;      /* better two fetches in the first step than SB96 steps */
+    else if (S == 0 && lb >= 1 && lb < 16 && fm_ensure_lead(idx, lb)) lead = lb;            /* a read shorter than one sparse step: one lookup */
   }
   p.nfront = 0; p.nback = 0; p.nsteps = S; p.start = NULL; p.start_bits = 0;
   if (lead) { p.start = idx->slead[lead]; p.start_bits = 2 * lead; p.nsteps = S - (lead > lb ? 1u : 0u); }

@@ -390,4 +390,41 @@ __global__ void __launch_bounds__(128) fm_sparse_fill_kernel(const uint32_t *__r
   }
 }
 
+/* the same for a uniform grid with many symbols and few blocks each (14 bases: 2^28 symbols x 2 blocks): one THREAD per block */
+template <int LANES>
+__global__ void __launch_bounds__(256) fm_sparse_fill_uniform_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ symstart,
+                                                                     uint32_t nsym, uint32_t nbu, uint32_t scale, const uint32_t *__restrict__ rank0,
+                                                                     uint4 *__restrict__ sblocks, unsigned long long *__restrict__ novf)
+{
+  const uint64_t g = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (uint64_t) nsym * nbu) return;
+  const uint32_t s = (uint32_t)(g / nbu), j = (uint32_t)(g - (uint64_t) s * nbu);
+  const uint32_t s0 = symstart[s], s1 = symstart[s + 1], r0 = rank0[s];
+  uint32_t lo = s0, hi = s1;
+  while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__umulhi(rows[mid], scale) < j) lo = mid + 1; else hi = mid; }
+  const uint32_t t0 = lo;
+  hi = s1;
+  while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__umulhi(rows[mid], scale) <= j) lo = mid + 1; else hi = mid; }
+  const uint32_t cnt = lo - t0;
+  constexpr uint32_t WORDS = 8u * LANES, SLOTS = WORDS - 1u;
+  uint32_t w[WORDS];
+  w[0] = r0 + (t0 - s0);
+  #pragma unroll
+  for (uint32_t c = 1; c < WORDS; c++) w[c] = (c - 1 < cnt && cnt <= SLOTS) ? rows[t0 + c - 1] : FM_SP_PAD;
+  if (cnt > SLOTS) { w[WORDS - 1] = FM_SP_OVF; atomicAdd(novf, 1ull); }
+  uint4 *dst = sblocks + (size_t) g * (2u * LANES);
+  #pragma unroll
+  for (uint32_t c = 0; c < 2u * LANES; c++) dst[c] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+}
+
+/* rows that live in symbols a uniform grid of nbu blocks per symbol cannot hold (count > slots * nbu): out[0] += count */
+__global__ void fm_sparse_heavy_rows_kernel(const uint32_t *__restrict__ symstart, uint32_t nsym, uint32_t limit, unsigned long long *__restrict__ out)
+{
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long c = 0;
+  if (s < nsym) { const uint32_t cnt = symstart[s + 1] - symstart[s]; if (cnt > limit) c = cnt; }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+  if ((threadIdx.x & 31u) == 0 && c) atomicAdd(out, c);
+}
+
 #endif /* FM_SPARSE_CUH_ */

@@ -24,7 +24,7 @@ def pkg(built):
 
 
 def widths(k):
-    return [2, 3, 5, 6, 10, 12] if k == 1 else [4, 6, 10, 12]
+    return [2, 3, 5, 6, 10, 12] if k == 1 else [4, 6, 10, 12]          # (14 bases: test_sparse_steps_read_lengths and the full-size test)
 
 
 @pytest.mark.parametrize("uniform", ["0", "1"], ids=["directory", "uniform_grid"])
@@ -76,8 +76,8 @@ def test_sparse_steps_read_lengths(pkg, k, length):
     else:                                                        # defined by the plain kernels (tested against the 1-step reference elsewhere)
         b.search(idx, pkg.variant(pkg.MODE_COOP))
         want = b.download()
-    for ks in ([3, 10] if k == 1 else [4, 10]):
-        for lanes in (2, 4):
+    for ks in ([3, 10, 14] if k == 1 else [4, 10, 14]):
+        for lanes in ((2, 4) if ks < 14 else (2,)):
             idx.sparsify(ks, 0, lanes)
             b.search(idx, pkg.variant(pkg.MODE_SPARSE))
             assert np.array_equal(b.download(), want), f"k={k} len={length} ks={ks} lanes={lanes}"
@@ -98,7 +98,7 @@ def test_sparse_unavailable_and_errors(pkg):
     assert ei.value.code == pkg.FM_E_BAD_ARGUMENT
     b.free(); idx.free()
     idx = pkg.DeviceIndex.from_image(g["image_100"])           # same text, standard file: fine
-    for bad in ((3, 0, 0), (2, 0, 0), (14, 0, 0), (4, 16, 2), (4, 32, 4), (4, 0, 3)):
+    for bad in ((3, 0, 0), (2, 0, 0), (16, 0, 0), (4, 16, 2), (4, 32, 4), (4, 0, 3)):
         with pytest.raises(pkg.FMError) as ei:
             idx.sparsify(*bad)
         assert ei.value.code == pkg.FM_E_BAD_ARGUMENT, bad
@@ -267,11 +267,17 @@ def test_sparse_config3_full_size_against_reference_checksums(pkg):
     for tag, key in ((100, "res_cpu_std_text"), (201, "res_cpu_ac_text")):
         t = b if tag == 100 else b.transform(tag)
         idx = t.to_index().sparsify()
-        m = idx.meta                                             # automatic choice on this text: 12 bases per step, uniform grid
-        assert (m.sparse_bases, m.sparse_lanes, m.sparse_start_bases) == (12, 2, 12) and m.sparse_uniform_nb > 0 and m.sparse_bytes < 30e9
+        m = idx.meta                                             # automatic choice on this text: 14 bases per step, uniform grid
+        assert (m.sparse_bases, m.sparse_lanes, m.sparse_start_bases) == (14, 2, 0) and m.sparse_uniform_nb == 2 and m.sparse_bytes < 45e9
         for qpt in (2, 4):
             batch.search(idx, pkg.variant(pkg.MODE_SPARSE, qpt))
             assert helpers.results_text_md5(batch.download()) == gold["md5"][key], f"tag {tag} qpt {qpt}"
+        idx.unsparsify()
+        idx.sparsify(12, 0, 0)                                   # 12 bases: uniform grid too on this text
+        m = idx.meta
+        assert (m.sparse_bases, m.sparse_start_bases) == (12, 12) and m.sparse_uniform_nb > 0
+        batch.search(idx, pkg.variant(pkg.MODE_SPARSE, 4))
+        assert helpers.results_text_md5(batch.download()) == gold["md5"][key], f"tag {tag} 12 bases"
         idx.unsparsify()
         idx.sparsify(10, 0, 0)                                   # and the 10-base table (what uneven symbol counts get, with a directory then)
         m = idx.meta
