@@ -178,7 +178,7 @@ typedef struct {
                                  FMGPU_MODE_FUSED: fused-step table (fmgpu_index_fuse): a lane group fetches one
                                  32/64/128-byte block with 256-bit loads and consumes up to 4 bases per step;
                                  FMGPU_MODE_SPARSE: sparse-step table (fmgpu_index_sparsify): one 128-byte block
-                                 of occurrence rows per fetch, up to 12 bases per step                         */
+                                 of occurrence rows per fetch, up to 14 bases per step                         */
   int32_t queries_per_thread; /* independent queries interleaved per thread/lane pair: 1, 2 or 4 */
   int32_t threads_per_block;  /* 128, 256 or 512                                      */
   int32_t reserved;           /* fmgpu_search_host only (also $FMGPU_FEED): 0 = auto, 1 = upload ASCII and pack
@@ -264,8 +264,9 @@ int32_t fmgpu_index_fuse(fmgpu_index_t *idx, uint32_t fused_bases, uint32_t lane
 int32_t fmgpu_index_unfuse(fmgpu_index_t *idx);
 /* Sparse-step table, built on the GPU from this replica's own block table: one sparse step = sparse_bases/k
  * reference LF steps (exactly); per wide symbol the occurrence rows are cut into blocks of ~lambda rows, one block
- * fetch per rank (csrc/fm_sparse.cuh).  sparse_bases 0 = 12 when the table can then be a uniform grid (see below; needs
- * >= 64 rows per 12-mer), else the widest multiple of k up to 10 that leaves at least 64 rows per symbol; lanes 0 = 2 (64-byte blocks, 15 slots; 4 = 128-byte blocks, 31 slots); lambda 0 = 5 / 12;
+ * fetch per rank (csrc/fm_sparse.cuh).  sparse_bases 0 = 14 or 12 when the table can then be a uniform grid (see below;
+ * needs >= 5 rows per 14-mer / >= 64 per 12-mer on average and even symbol counts), else the widest multiple of k up
+ * to 10 that leaves at least 64 rows per symbol (explicit widths: multiples of k up to 14); lanes 0 = 2 (64-byte blocks, 15 slots; 4 = 128-byte blocks, 31 slots); lambda 0 = 5 / 12;
  * the table takes ~32*lanes/lambda bytes per text base whatever the width.  Blocks with more occurrences than
  * slots (repeats) are served by ordinary steps on the block table.  When no wide symbol occurs more than 1.6 x as
  * often as the mean (uniformly random texts) the table is a uniform grid -- the same block count for every symbol,

@@ -325,7 +325,7 @@ class DeviceIndex:
         check(lib().fmgpu_index_unfuse(self.handle), "fmgpu_index_unfuse")
 
     def sparsify(self, sparse_bases=0, lam=0, lanes=0):
-        """Builds the sparse-step table (up to 12 bases per 64/128-byte block fetch) for MODE_SPARSE searches."""
+        """Builds the sparse-step table (up to 14 bases per 64/128-byte block fetch) for MODE_SPARSE searches."""
         check(lib().fmgpu_index_sparsify(self.handle, sparse_bases, lam, lanes), "fmgpu_index_sparsify")
         return self
 

@@ -1,5 +1,5 @@
 /*
- * fm_sparse.cuh -- "sparse-step" device layout and search kernel: KS (up to 12) query bases per block fetch.
+ * fm_sparse.cuh -- "sparse-step" device layout and search kernel: KS (up to 14) query bases per block fetch.
  *
  * Measured on B200 (profiles/r01_miss_ceiling.md): the memory system serves ~46 G random block fetches per second
  * whatever their size up to a 128-byte line, and nothing else limits the search.  The fused-step layout
