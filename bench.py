@@ -520,7 +520,7 @@ def main():
             "lf_steps_per_s": world * lf_steps / (ms_step * 1e-3),
             "config": {"workload": workload,
                        "kernel": (f"sparse: {meta.sparse_bases} bases/step, {32 * meta.sparse_lanes}-byte blocks of occurrence rows (lambda {meta.sparse_lambda}), {meta.sparse_lanes} x 256-bit loads, "
-                                  (f"{meta.sparse_start_bases}-base start table + lead tables, " if meta.sparse_start_bases else "lead tables (no start table at this width), ")
+                                  + (f"{meta.sparse_start_bases}-base start table + lead tables, " if meta.sparse_start_bases else "lead tables (no start table at this width), ")
                                   + (f"uniform grid ({meta.sparse_uniform_nb} blocks per symbol, no directory lookup: the text's symbol counts are even), " if meta.sparse_uniform_nb
                                      else "per-symbol block counts + L2-resident directory, ")
                                   + f"qpt={var.queries_per_thread}" if sparse else
