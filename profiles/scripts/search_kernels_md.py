@@ -4,7 +4,7 @@ import csv, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 PR = os.path.join(ROOT, "profiles")
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-names = [("coop", "plain 2-step Coop"), ("fused", "fused-step (4 bases / 64-byte block)"), ("sparse", "sparse-step, the timed kernel (12 bases / 64-byte block, uniform grid)")]
+names = [("coop", "plain 2-step Coop"), ("fused", "fused-step (4 bases / 64-byte block)"), ("sparse", "sparse-step, the timed kernel (14 bases / 64-byte block, uniform grid)")]
 recs = {}
 for n, _ in names:
     d = json.load(open(os.path.join(PR, f"{tag}_prof_{n}.json")))
@@ -33,7 +33,7 @@ def short(v):
 with open(os.path.join(PR, f"{tag}_search_kernels.md"), "w") as f:
     f.write(f"# {tag}: the three search kernels under `ncu --set full --clock-control none --import-source on` (config 3: 2 Gbp index, 10 M x 100 bp reads, 1 B200)\n\n"
             f"Raw metric dumps: `{tag}_prof_coop.json`, `{tag}_prof_fused.json`, `{tag}_prof_sparse.json`; SASS with stall samples: `{tag}_prof_*_source.csv`.\n"
-            "Captured with `ncu ... -k regex:fm_search_<kernel> -s 4 -c 2 python bench.py --steps 2 --warmup 3` (the sparse kernel, re-captured after the uniform grid / 12-base\n"
+            "Captured with `ncu ... -k regex:fm_search_<kernel> -s 4 -c 2 python bench.py --steps 2 --warmup 3` (the sparse kernel, re-captured after the uniform grid / 14-base\n"
             "change: `--kernel-name-base demangled -k 'regex:fm_search_sparse_kernel<\\(int\\)2, \\(int\\)2, \\(int\\)4' -s 3 -c 2`) after the same command had exited 0 without ncu.\n"
             "The reference's 2-step algorithm must touch 18.2 GB of 32-byte sectors for these reads (SURVEY 8d, counted by the instrumented kernel).\n\n")
     f.write("| metric | " + " | ".join(f"{t} (`{recs[n]['kernel'][5:48]}`)" for n, t in names) + " |\n|---|" + "---:|" * len(names) + "\n")
@@ -44,8 +44,8 @@ with open(os.path.join(PR, f"{tag}_search_kernels.md"), "w") as f:
             f.write(f"| {label} | " + " | ".join(short(recs[n].get(key, "")) for n, _ in names) + " |\n")
     f.write("| warp stalls, cycles per issue | " + " | ".join(", ".join(f"{k} {v:.1f}" for k, v in list(recs[n]["warp_stall_cycles_per_issue"].items())[:5]) for n, _ in names) + " |\n")
     f.write("\nReading.  All three are bound by the rate of random block fetches (~46 G/s, `r01_miss_ceiling.md`), not by DRAM bytes or issue slots; they differ in\n"
-            "how many fetches a read needs: ~57 x 2 sectors (Coop, L and R lanes), 22.3 (fused, after the 12-base start table), 8.1 (sparse: a 4-base lead table, then\n"
-            "8 steps of 12 bases).  The sparse kernel reads 5.5 GB from DRAM for 10 M reads -- under a third of the bytes the reference algorithm must touch -- at 39 % DRAM utilisation;\n"
+            "how many fetches a read needs: ~57 x 2 sectors (Coop, L and R lanes), 22.3 (fused, after the 12-base start table), 7.1 (sparse: a 2-base lead table, then\n"
+            "7 steps of 14 bases).  The sparse kernel reads 4.8 GB from DRAM for 10 M reads -- about a quarter of the bytes the reference algorithm must touch;\n"
             "its stalls are the dependent block fetch (long_scoreboard) and the shared-memory read of the next symbol plus shuffles (short_scoreboard / mio).\n\n")
     for n, t in names:
         path = os.path.join(PR, f"{tag}_prof_{n}_source.csv")
