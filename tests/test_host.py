@@ -247,3 +247,18 @@ def test_ctypes_mirrors_match_the_header(built, tmp_path):
     m = pkg.fmgpu_index_meta_t
     assert got == [C.sizeof(m), m.nbytes.offset, m.tail_const.offset, m.sparse_bytes.offset, m.tail_bytes.offset,
                    C.sizeof(pkg.fmgpu_variant_t), C.sizeof(pkg.fmi_t), C.sizeof(pkg.qrys_t)]
+
+
+def test_bench_and_entry_scripts_compile_without_warnings():
+    """bench.py and __graft_entry__.py must byte-compile with warnings as errors (a missing '+' between string pieces
+    is only a SyntaxWarning until the line runs on the GPU box), and bench.py --help must work without a GPU."""
+    import warnings
+    for name in ("bench.py", "__graft_entry__.py"):
+        path = os.path.join(helpers.ROOT, name)
+        with open(path) as f:
+            src = f.read()
+        with warnings.catch_warnings():
+            warnings.simplefilter("error")
+            compile(src, path, "exec")
+    out = subprocess.run([os.sys.executable, os.path.join(helpers.ROOT, "bench.py"), "--help"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "--impl" in out.stdout
