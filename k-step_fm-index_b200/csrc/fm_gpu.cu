@@ -802,10 +802,11 @@ static int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_pack
   FmSparseParams p;
   p.sblocks = idx->sblocks; p.dir = idx->sdir; p.blocks = idx->blocks; p.packed = d_packed; p.results = d_results;
   p.nblocks = idx->meta.nblocks; p.nq = (uint32_t) nq;
-  /* plan: S whole sparse steps + rem base-k steps (+ an odd tail base).  (A) the start table replaces the first sparse
-   * step(s) and the rem steps follow the sparse ones: S - m + rem block fetches from DRAM; (B) 6 or more leftover bases
-   * are taken first from their lead table and all S sparse steps run: S fetches (the interval is already narrower than
-   * a bucket); (C) no table: the rem steps run first on the upper (L2-resident) levels of SB96. */
+  /* plan: S whole sparse steps + lb leftover bases (rem base-k steps + an odd tail base).  (B) the leftover bases -- or
+   * leftover + one sparse step's bases -- are taken first from their lead table and only whole sparse steps follow:
+   * S (or S - 1) block fetches plus one lookup, no tail fetch; (A) no such table: the start table replaces the first
+   * sparse step(s) and the rem steps follow the sparse ones, S - m + rem block fetches from DRAM (+ tail); (C) no
+   * tables at all (small indexes): the rem steps run first on the upper (L2-resident) levels of SB96. */
   const uint32_t S = (len / k) / hops, rem = (len / k) % hops;
   const uint32_t m = idx->sstart ? idx->meta.sparse_start_bases / ks : 0u;
   const uint32_t lb = len - S * ks;                            /* leftover bases, the odd one included */
