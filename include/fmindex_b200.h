@@ -181,10 +181,11 @@ typedef struct {
                                  of occurrence rows per fetch, up to 14 bases per step                         */
   int32_t queries_per_thread; /* independent queries interleaved per thread/lane pair: 1, 2 or 4 */
   int32_t threads_per_block;  /* 128, 256 or 512                                      */
-  int32_t reserved;           /* fmgpu_search_host only (also $FMGPU_FEED): 0 = auto, 1 = upload ASCII and pack
-                                 on the GPU, 2 = pack to 2 bit on the host (OpenMP + AVX-512) and upload
-                                 25 B/read, 3 = hybrid (copy engine pulls ASCII chunks while the CPU packs others) */
+  int32_t feed;               /* fmgpu_search_host only (also $FMGPU_FEED): FMGPU_FEED_AUTO, _ASCII (upload ASCII, pack
+                                 on the GPU), _HOSTPACK (pack to 2 bit on the host with OpenMP + AVX-512, upload
+                                 25 B/read), _HYBRID (copy engine pulls ASCII chunks while the CPU packs others) */
 } fmgpu_variant_t;
+enum { FMGPU_FEED_AUTO = 0, FMGPU_FEED_ASCII = 1, FMGPU_FEED_HOSTPACK = 2, FMGPU_FEED_HYBRID = 3 };
 
 /* Shape of the device layout ("SB96": per-symbol blocks of 96 BWT rows,
  * 16 bytes = {u32 rank at block start, 96 indicator bits}); see DESIGN.md. */
@@ -226,9 +227,29 @@ typedef struct {
    * symbol's first block instead of looking it up (chosen when all symbols occur about equally often, i.e. on
    * uniformly random texts; $FMGPU_SPARSE_UNIFORM=0/1 forces); 0 = per-symbol block counts and a directory */
   uint32_t sparse_uniform_nb;
-  uint32_t reserved0;
-  uint64_t sa_bytes;           /* suffix array kept for locate (fmgpu_index_build_sa): 4 bytes per BWT row, 0 = none */
+  uint32_t sa_rate;            /* suffix array kept for locate: 1 = every row (fmgpu_index_build_sa), s > 1 = the rows whose
+                                  text position is a multiple of s (fmgpu_index_build_sa_sampled), 0 = none */
+  uint64_t sa_bytes;           /* its size: 4 bytes per BWT row when full, ~4/s + 1/6 bytes per row when sampled */
+  uint64_t derived_bytes;      /* everything this replica derived from its SB96 table: sparse + fused + tail + SA tables */
+  uint64_t budget_bytes;       /* the limit derived_bytes is kept under ($FMGPU_TABLE_BUDGET_GB / fmgpu_set_table_budget), 0 = none */
 } fmgpu_index_meta_t;
+
+/* what the last transferCPUtoGPU / searchIndexGPU / transferGPUtoCPU sequence of this process did (wall-clock seconds of
+ * each stage, CUDA-event milliseconds of each GPU's search kernels): the numbers the reference main() cannot print */
+typedef struct {
+  int32_t  ndev;
+  int32_t  searches;              /* searchIndexGPU calls since the index was transferred                          */
+  double   index_h2d_reblock_s;   /* file entries H2D + re-block on the first GPU                                  */
+  double   peer_copy_s[16];       /* [g]: cudaMemcpyPeer of the block table to GPU g (g >= 1)                       */
+  double   table_build_s[16];     /* [g]: sparse-step / fused-step table built on GPU g                             */
+  double   queries_h2d_pack_s;    /* all shards: ASCII H2D + 2-bit pack                                            */
+  double   results_d2h_s;         /* all shards: (L,R) D2H                                                         */
+  float    search_ms[16];         /* [g]: kernels of the last searchIndexGPU on GPU g, CUDA events on its stream   */
+  uint64_t index_file_bytes, table_bytes, query_bytes, result_bytes;
+} fmgpu_transfer_stats_t;
+int32_t fmgpu_get_transfer_stats(fmgpu_transfer_stats_t *out);
+/* searchIndexGPU with an error code instead of exit(): FM_E_BAD_ARGUMENT when transferCPUtoGPU was not called for this pair */
+int32_t fmgpu_search_index(void *index, void *queries, void *resIntervals);
 
 /* devices ---------------------------------------------------------------- */
 int32_t fmgpu_device_count(void);                 /* usable sm_100 devices; 0 if none */
@@ -274,6 +295,14 @@ int32_t fmgpu_index_unfuse(fmgpu_index_t *idx);
  * FM_E_NOT_IMPLEMENTED when memory does not suffice or the index carries the AltCounters padding quirk. */
 int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_bases, uint32_t lambda, uint32_t lanes);
 int32_t fmgpu_index_unsparsify(fmgpu_index_t *idx);
+/* Builds NOW (synchronously) whatever a search of `len`-base reads on this replica may use: the tail table for odd
+ * lengths on a 2-step index, the lead tables of the sparse-step plan.  The search entry points themselves never build
+ * or allocate: they pick among the tables that exist (same results, more fetches when one is missing).
+ * transferCPUtoGPU and fmgpu_search_host call this; callers of fmgpu_batch_search / fmgpu_search_device may. */
+int32_t fmgpu_index_prepare(fmgpu_index_t *idx, uint32_t len);
+/* one budget for all derived tables of a replica (sparse, fused, tail, lead tables, suffix array); a table that would
+ * exceed it is not built (FM_E_NOT_IMPLEMENTED from the explicit builders).  0 = no limit ($FMGPU_TABLE_BUDGET_GB). */
+int32_t fmgpu_set_table_budget(uint64_t bytes);
 int32_t fmgpu_index_get_meta(const fmgpu_index_t *idx, fmgpu_index_meta_t *meta);
 void   *fmgpu_index_blocks(const fmgpu_index_t *idx);     /* device pointer */
 int32_t fmgpu_index_device(const fmgpu_index_t *idx);
@@ -286,6 +315,10 @@ int32_t fmgpu_batch_upload_ascii(fmgpu_batch_t *b, const char *h_ascii);
 /* async launch of the search kernels on the shard's stream */
 int32_t fmgpu_batch_search(const fmgpu_index_t *idx, fmgpu_batch_t *b, const fmgpu_variant_t *v);
 int32_t fmgpu_batch_sync(fmgpu_batch_t *b);
+/* the same launch bracketed by the shard's two CUDA events (no host wait); after fmgpu_batch_sync,
+ * fmgpu_batch_last_ms gives the milliseconds between them */
+int32_t fmgpu_batch_search_timed_async(const fmgpu_index_t *idx, fmgpu_batch_t *b, const fmgpu_variant_t *v);
+int32_t fmgpu_batch_last_ms(fmgpu_batch_t *b, float *ms);
 /* D2H of 2*nqueries u32 */
 int32_t fmgpu_batch_download(fmgpu_batch_t *b, uint32_t *h_results);
 /* `iters` searches timed with CUDA events on the shard's stream; ms per search */
@@ -316,8 +349,28 @@ int32_t fmgpu_search_host(fmgpu_index_t *const *replicas, int32_t nreplicas, con
  * fmgpu_words_per_query(len) words as written by fm_hostpack_reads): no conversion, 28 B per 100-bp read over PCIe */
 int32_t fmgpu_search_host_packed(fmgpu_index_t *const *replicas, int32_t nreplicas, const uint32_t *h_packed,
                                  uint64_t nqueries, uint32_t len, uint32_t *h_results, const fmgpu_variant_t *v);
-/* frees the streams / staging buffers fmgpu_search_host keeps between calls (neither is re-entrant) */
+/* frees the process-default pipeline the two calls above keep between calls (they serialise on one mutex) */
 int32_t fmgpu_release_pipeline(void);
+
+/* the same two calls on an explicit pipeline handle (streams, staging buffers and the self-tuning state of the host
+ * feed live in it): one caller thread per handle at a time, any number of handles */
+typedef struct fmgpu_pipeline fmgpu_pipeline_t;
+typedef struct {
+  uint64_t calls;
+  int32_t  last_feed;                    /* FMGPU_FEED_* the last call used */
+  int32_t  pad;
+  double   last_seconds;
+  uint64_t last_reads_host_packed;       /* reads the CPU packed / reads that crossed the link as ASCII in the last call */
+  uint64_t last_reads_ascii_over_link;
+  double   host_pack_seconds_per_read;
+} fmgpu_pipeline_stats_t;
+int32_t fmgpu_pipeline_create(fmgpu_pipeline_t **out);
+int32_t fmgpu_pipeline_search_host(fmgpu_pipeline_t *p, fmgpu_index_t *const *replicas, int32_t nreplicas, const char *h_ascii,
+                                   uint64_t nqueries, uint32_t len, uint32_t *h_results, const fmgpu_variant_t *v);
+int32_t fmgpu_pipeline_search_host_packed(fmgpu_pipeline_t *p, fmgpu_index_t *const *replicas, int32_t nreplicas, const uint32_t *h_packed,
+                                          uint64_t nqueries, uint32_t len, uint32_t *h_results, const fmgpu_variant_t *v);
+int32_t fmgpu_pipeline_get_stats(const fmgpu_pipeline_t *p, fmgpu_pipeline_stats_t *out);
+int32_t fmgpu_pipeline_free(fmgpu_pipeline_t **p);
 
 /* host-side ASCII -> reversed 2-bit packing (same words as the device pack kernel); OpenMP over reads,
  * AVX-512 VBMI when the CPU has it.  packed holds nqueries * fmgpu_words_per_query(len) words. */

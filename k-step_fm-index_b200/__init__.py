@@ -62,7 +62,7 @@ class fmi_t(C.Structure):           # src/fmIndexCPUBaseline.c:54-69 + extension
 
 
 class fmgpu_variant_t(C.Structure):
-    _fields_ = [("mode", C.c_int32), ("queries_per_thread", C.c_int32), ("threads_per_block", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("mode", C.c_int32), ("queries_per_thread", C.c_int32), ("threads_per_block", C.c_int32), ("feed", C.c_int32)]
 
 
 class fmgpu_index_meta_t(C.Structure):
@@ -74,7 +74,21 @@ class fmgpu_index_meta_t(C.Structure):
                 ("sparse_bases", C.c_uint32), ("sparse_lambda", C.c_uint32), ("sparse_bytes", C.c_uint64),
                 ("sparse_blocks", C.c_uint64), ("sparse_overflow", C.c_uint64), ("sparse_start_bases", C.c_uint32),
                 ("sparse_lanes", C.c_uint32), ("tail_bytes", C.c_uint64),
-                ("sparse_uniform_nb", C.c_uint32), ("reserved0", C.c_uint32), ("sa_bytes", C.c_uint64)]
+                ("sparse_uniform_nb", C.c_uint32), ("sa_rate", C.c_uint32), ("sa_bytes", C.c_uint64),
+                ("derived_bytes", C.c_uint64), ("budget_bytes", C.c_uint64)]
+
+
+class fmgpu_transfer_stats_t(C.Structure):
+    _fields_ = [("ndev", C.c_int32), ("searches", C.c_int32), ("index_h2d_reblock_s", C.c_double), ("peer_copy_s", C.c_double * 16),
+                ("table_build_s", C.c_double * 16), ("queries_h2d_pack_s", C.c_double), ("results_d2h_s", C.c_double),
+                ("search_ms", C.c_float * 16), ("index_file_bytes", C.c_uint64), ("table_bytes", C.c_uint64),
+                ("query_bytes", C.c_uint64), ("result_bytes", C.c_uint64)]
+
+
+class fmgpu_pipeline_stats_t(C.Structure):
+    _fields_ = [("calls", C.c_uint64), ("last_feed", C.c_int32), ("pad", C.c_int32), ("last_seconds", C.c_double),
+                ("last_reads_host_packed", C.c_uint64), ("last_reads_ascii_over_link", C.c_uint64),
+                ("host_pack_seconds_per_read", C.c_double)]
 
 
 _VP, _VPP = C.c_void_p, C.POINTER(C.c_void_p)
@@ -150,6 +164,17 @@ PROTOTYPES = {
     "fm_hostpack_reads_scalar": (None, [_VP, C.c_uint64, C.c_uint32, _VP]),
     "fmgpu_search_host_packed": (C.c_int32, [_VPP, C.c_int32, _VP, C.c_uint64, C.c_uint32, _VP, C.POINTER(fmgpu_variant_t)]),
     "fmgpu_release_pipeline": (C.c_int32, []),
+    "fmgpu_pipeline_create": (C.c_int32, [_VPP]),
+    "fmgpu_pipeline_search_host": (C.c_int32, [_VP, _VPP, C.c_int32, _VP, C.c_uint64, C.c_uint32, _VP, C.POINTER(fmgpu_variant_t)]),
+    "fmgpu_pipeline_search_host_packed": (C.c_int32, [_VP, _VPP, C.c_int32, _VP, C.c_uint64, C.c_uint32, _VP, C.POINTER(fmgpu_variant_t)]),
+    "fmgpu_pipeline_get_stats": (C.c_int32, [_VP, C.POINTER(fmgpu_pipeline_stats_t)]),
+    "fmgpu_pipeline_free": (C.c_int32, [_VPP]),
+    "fmgpu_index_prepare": (C.c_int32, [_VP, C.c_uint32]),
+    "fmgpu_set_table_budget": (C.c_int32, [C.c_uint64]),
+    "fmgpu_get_transfer_stats": (C.c_int32, [C.POINTER(fmgpu_transfer_stats_t)]),
+    "fmgpu_search_index": (C.c_int32, [_VP, _VP, _VP]),
+    "fmgpu_batch_search_timed_async": (C.c_int32, [_VP, _VP, C.POINTER(fmgpu_variant_t)]),
+    "fmgpu_batch_last_ms": (C.c_int32, [_VP, C.POINTER(C.c_float)]),
     "fm_hostpack_stream": (None, [_VP, C.c_uint64, _VP, C.c_int]),
     "fmgpu_unstream_device": (C.c_int32, [C.c_int32, _VP, C.c_uint64, C.c_uint32, _VP, _VP]),
     "fm_hostpack_set_prefetch": (None, [C.c_int]),
@@ -345,6 +370,11 @@ class DeviceIndex:
         check(lib().fmgpu_index_download_sa(self.handle, out.ctypes.data), "fmgpu_index_download_sa")
         return out
 
+    def prepare(self, length):
+        """Builds whatever tables a search of `length`-base reads uses (tail table, lead tables); searches never build."""
+        check(lib().fmgpu_index_prepare(self.handle, length), "fmgpu_index_prepare")
+        return self
+
     def replicate(self, device):
         h = C.c_void_p()
         check(lib().fmgpu_index_replicate(self.handle, device, C.byref(h)), "fmgpu_index_replicate")
@@ -388,12 +418,15 @@ class DeviceBatch:
         assert a.size == self.nq * self.len
         check(lib().fmgpu_batch_upload_ascii(self.handle, a.ctypes.data), "fmgpu_batch_upload_ascii")
 
-    def search(self, index, var=None, sync=True):
+    def search(self, index, var=None, sync=True, prepare=True):
+        if prepare:
+            index.prepare(self.len)
         check(lib().fmgpu_batch_search(index.handle, self.handle, C.byref(var) if var is not None else None), "fmgpu_batch_search")
         if sync:
             check(lib().fmgpu_batch_sync(self.handle), "fmgpu_batch_sync")
 
     def search_timed(self, index, iters, var=None):
+        index.prepare(self.len)
         ms = C.c_float()
         check(lib().fmgpu_batch_search_timed(index.handle, self.handle, C.byref(var) if var is not None else None, iters, C.byref(ms)),
               "fmgpu_batch_search_timed")

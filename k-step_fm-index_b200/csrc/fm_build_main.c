@@ -7,6 +7,10 @@
  * writes "<reference.fa>.<n>.<d>fmi<k>steps.fmi" -- the file name and the bytes gfmiBaseLine_<d>bases_<k>step
  * writes (src/genFMindex.c:155-181).  With --all it also writes the three transformed layouts tfmiBMP_* / tfmiAC_*
  * would produce: ".interleaving", ".ac", ".interleaving.ac".
+ *
+ * gfmi_b200 --synth <out prefix> <n> <seed> <k> <d> [--all]
+ *   the same for the synthetic text of fm_synth.h (what `fmsynth ref <out prefix> <n> <seed>` would write), generated on
+ *   the GPU: no FASTA file is read.  Output name "<out prefix>.<n>.<d>fmi<k>steps.fmi".
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -48,8 +52,19 @@ int main(int argc, char **argv)
   static const uint32_t tags[3] = { 101, 200, 201 };
   static const char *suffix[3] = { ".interleaving", ".ac", ".interleaving.ac" };
   double t0;
+  const char *prefix;
+  int all;
+  if (argc >= 7 && !strcmp(argv[1], "--synth")) {
+    const uint64_t seed = strtoull(argv[4], NULL, 10);
+    n = strtoull(argv[3], NULL, 10); k = (uint32_t) atoi(argv[5]); d = (uint32_t) atoi(argv[6]);
+    t0 = sampleTime();
+    CHECK(fmgpu_build_from_synth(0, n, seed, k, d, &b));
+    printf("BUILD TIME: \t %f \n", sampleTime() - t0);
+    prefix = argv[2]; all = argc > 7 && !strcmp(argv[7], "--all");
+    goto save;
+  }
   if (argc < 5) {
-    fprintf(stderr, "usage: %s <reference.fa> <n> <k> <d> [--all]\n", argv[0]);
+    fprintf(stderr, "usage: %s <reference.fa> <n> <k> <d> [--all]\n       %s --synth <out prefix> <n> <seed> <k> <d> [--all]\n", argv[0], argv[0]);
     return EXIT_FAILURE;
   }
   n = strtoull(argv[2], NULL, 10); k = (uint32_t) atoi(argv[3]); d = (uint32_t) atoi(argv[4]);
@@ -58,9 +73,11 @@ int main(int argc, char **argv)
   CHECK(fmgpu_build_from_text(0, ref, n, k, d, &b));
   printf("BUILD TIME: \t %f \n", sampleTime() - t0);
   free(ref);
-  snprintf(name, sizeof name, "%s.%llu.%ufmi%usteps.fmi", argv[1], (unsigned long long) n, d, k);
+  prefix = argv[1]; all = argc > 5 && !strcmp(argv[5], "--all");
+save:
+  snprintf(name, sizeof name, "%s.%llu.%ufmi%usteps.fmi", prefix, (unsigned long long) n, d, k);
   CHECK(fmgpu_build_save(b, name));
-  if (argc > 5 && !strcmp(argv[5], "--all"))
+  if (all)
     for (i = 0; i < 3; i++) {
       char tn[2100];
       CHECK(fmgpu_build_transform(b, tags[i], &t));

@@ -29,10 +29,7 @@
 #ifndef FM_FUSED_CUH_
 #define FM_FUSED_CUH_
 
-#include "fm_kernels.cuh"
-
-#define FM_SYM_NONE  0xFFu
-#define FM_FSYM_NONE 0xFFFFu
+#include "fm_device.cuh"
 
 struct FmFusedParams {
   const uint4    *fblocks;    /* fused table                                                       */
@@ -58,13 +55,6 @@ struct FmFusedParams {
 
 #define FM_START_BASES 12u
 
-/* .L2::64B: an L2 miss then fills 64 bytes (the whole LANES=2 block) instead of the 128-byte line every other
- * flavour pulls from HBM (profiles/r01_prefetch_variants.md) -- same fetch rate, half the DRAM traffic */
-__device__ __forceinline__ void fm_ldg32(const uint4 *p, uint32_t (&w)[8])
-{
-  asm volatile("ld.global.L1::no_allocate.L2::evict_first.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
-}
 
 /* rows per fused block = 32 * (8*LANES - 1); exact division of X < 2^32 by it */
 template <int LANES> struct FmFusedGeom {
@@ -94,19 +84,6 @@ __device__ __forceinline__ uint32_t fm_fused_partial(const uint32_t (&w)[8], uin
   return sum;
 }
 
-template <int LANES> __device__ __forceinline__ uint32_t fm_group_sum(uint32_t v)
-{
-  #pragma unroll
-  for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-  return v;
-}
-
-/* bits [pos, pos+nbits) of a packed read kept in shared memory (one readable spare word after the read) */
-__device__ __forceinline__ uint32_t fm_read_field(const uint32_t *q, uint32_t pos, uint32_t mask)
-{
-  const uint32_t i = pos >> 5;
-  return __funnelshift_r(q[i], q[i + 1], pos & 31u) & mask;
-}
 
 /* ------------------------------------------------------------------------ *
  * Fused search: a group of LANES lanes owns QPT reads (both endpoints of each).  Per fused step the group
@@ -268,11 +245,6 @@ __global__ void fm_fuse_symbols_kernel(const uint4 *__restrict__ blocks, uint32_
   }
 }
 
-__device__ __forceinline__ uint32_t fm_sb96_rank(const uint4 *__restrict__ blocks, uint32_t nblocks, uint32_t s, uint32_t X)
-{
-  const uint32_t b = fm_div96(X);
-  return fm_block_rank(blocks[(size_t) s * nblocks + b], X - b * FM_SB_ROWS);
-}
 
 /* fused symbol of every row: follow the index's own LF mapping hops-1 times */
 __global__ void fm_fuse_compose_kernel(const uint4 *__restrict__ blocks, uint32_t nblocks, const uint8_t *__restrict__ sym,
@@ -366,3 +338,4 @@ __global__ void __launch_bounds__(1024) fm_fuse_scan_kernel(const uint4 *__restr
 }
 
 #endif /* FM_FUSED_CUH_ */
+

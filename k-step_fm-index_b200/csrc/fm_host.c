@@ -28,20 +28,22 @@ typedef struct {
   fmgpu_index_t *replica[FM_MAX_GPUS];
 } fm_replica_set_t;
 
-/* device-side state hung off qrys_t.d_queries and res_t.d_results */
+/* device-side state hung off qrys_t.d_queries and res_t.d_results: ONE shard set per (queries, results) pair, owned
+ * by both handles; it is released when both have let go (free*GPU) or when either is transferred again */
 typedef struct {
   int32_t        ndev;
   uint64_t       first[FM_MAX_GPUS + 1];   /* shard g = reads [first[g], first[g+1]) */
   fmgpu_batch_t *shard[FM_MAX_GPUS];
   fm_replica_set_t *index;                 /* replicas the shards were created for */
-  uint32_t      *h_results;                /* where transferGPUtoCPU lands          */
-  int            queries_released, results_released;
+  qrys_t        *owner_q;                  /* the handles whose d_* fields point here (NULL once released) */
+  res_t         *owner_r;
 } fm_shard_set_t;
 
 static int32_t g_ndev = 0;
 static int32_t g_dev[FM_MAX_GPUS];
 static fmgpu_variant_t g_variant = { 0, 0, 0, 0 };
 static int g_variant_set = 0;
+static fmgpu_transfer_stats_t g_stats;
 
 /* common/common.c:28-33 */
 double sampleTime(void)
@@ -330,11 +332,56 @@ static int32_t fm_resolve_devices(int32_t *dev)
   return 1;
 }
 
+/* detaches both owners (their d_* fields never dangle) and frees the shards */
 static void fm_release_shards(fm_shard_set_t *ss)
 {
   int32_t g;
+  if (!ss) return;
+  if (ss->owner_q && ss->owner_q->d_queries == (char *) ss) ss->owner_q->d_queries = NULL;
+  if (ss->owner_r && ss->owner_r->d_results == (uint32_t *) ss) ss->owner_r->d_results = NULL;
   for (g = 0; g < ss->ndev; g++) fmgpu_batch_free(&ss->shard[g]);
   free(ss);
+}
+
+static double fm_wall(void)
+{
+  struct timespec tv;
+  clock_gettime(CLOCK_MONOTONIC, &tv);
+  return (double) tv.tv_sec + (double) tv.tv_nsec * 1e-9;
+}
+
+/* $FMGPU_STATS_FILE: the stats as one JSON line, written when the index leaves the GPUs (freeIndexGPU) -- the way to get
+ * them out of a caller that cannot ask, like the reference's own main() */
+static void fm_dump_stats(void)
+{
+  const char *fn = getenv("FMGPU_STATS_FILE");
+  FILE *fp;
+  int32_t g;
+  if (!fn || !*fn || g_stats.ndev == 0) return;
+  fp = fopen(fn, "a");
+  if (!fp) return;
+  fprintf(fp, "{\"ndev\": %d, \"searches\": %d, \"index_file_bytes\": %llu, \"table_bytes\": %llu, \"index_h2d_reblock_s\": %.6f, "
+              "\"index_h2d_reblock_gbs\": %.3f, \"queries_h2d_pack_s\": %.6f, \"query_bytes\": %llu, \"results_d2h_s\": %.6f, \"result_bytes\": %llu",
+          g_stats.ndev, g_stats.searches, (unsigned long long) g_stats.index_file_bytes, (unsigned long long) g_stats.table_bytes,
+          g_stats.index_h2d_reblock_s, g_stats.index_h2d_reblock_s > 0 ? g_stats.index_file_bytes / g_stats.index_h2d_reblock_s / 1e9 : 0.0,
+          g_stats.queries_h2d_pack_s, (unsigned long long) g_stats.query_bytes, g_stats.results_d2h_s, (unsigned long long) g_stats.result_bytes);
+  fprintf(fp, ", \"peer_copy_s\": [");
+  for (g = 1; g < g_stats.ndev; g++) fprintf(fp, "%s%.6f", g > 1 ? ", " : "", g_stats.peer_copy_s[g]);
+  fprintf(fp, "], \"peer_copy_gbs\": [");
+  for (g = 1; g < g_stats.ndev; g++) fprintf(fp, "%s%.2f", g > 1 ? ", " : "", g_stats.peer_copy_s[g] > 0 ? g_stats.table_bytes / g_stats.peer_copy_s[g] / 1e9 : 0.0);
+  fprintf(fp, "], \"table_build_s\": [");
+  for (g = 0; g < g_stats.ndev; g++) fprintf(fp, "%s%.4f", g ? ", " : "", g_stats.table_build_s[g]);
+  fprintf(fp, "], \"search_ms_per_gpu\": [");
+  for (g = 0; g < g_stats.ndev; g++) fprintf(fp, "%s%.4f", g ? ", " : "", g_stats.search_ms[g]);
+  fprintf(fp, "]}\n");
+  fclose(fp);
+}
+
+int32_t fmgpu_get_transfer_stats(fmgpu_transfer_stats_t *out)
+{
+  if (!out) return FM_E_BAD_ARGUMENT;
+  *out = g_stats;
+  return FM_SUCCESS;
 }
 
 int32_t transferCPUtoGPU(void *index, void *queries, void *results)
@@ -354,24 +401,37 @@ int32_t transferCPUtoGPU(void *index, void *queries, void *results)
   /* index: one H2D + re-block on the first GPU, peer copies to the others */
   rs = (fm_replica_set_t *) fmi->d_index;
   if (rs == NULL) {
+    double t0;
+    fmgpu_index_meta_t meta0;
+    memset(&g_stats, 0, sizeof g_stats);
     rs = (fm_replica_set_t *) calloc(1, sizeof(*rs));
     if (!rs) return FM_E_ALLOCATING_FMI;
     rs->ndev = fm_resolve_devices(rs->dev);
+    g_stats.ndev = rs->ndev;
+    t0 = fm_wall();
     err = fmgpu_index_create(rs->dev[0], fmi->tag, fmi->steps, fmi->chunk, fmi->bwtsize, fmi->ncounters, fmi->nentries,
                              fmi->h_dollarPositionBWT, fmi->h_dollarBaseBWT, (const uint32_t *) fmi->h_index, &rs->replica[0]);
-    for (g = 1; g < rs->ndev && !err; g++) err = fmgpu_index_replicate(rs->replica[0], rs->dev[g], &rs->replica[g]);
+    g_stats.index_h2d_reblock_s = fm_wall() - t0;
+    g_stats.index_file_bytes = (uint64_t) fmi->nentries * fmi->entry_words * 4ull;
+    for (g = 1; g < rs->ndev && !err; g++) {
+      t0 = fm_wall();
+      err = fmgpu_index_replicate(rs->replica[0], rs->dev[g], &rs->replica[g]);
+      g_stats.peer_copy_s[g] = fm_wall() - t0;
+    }
     if (err) { for (g = 0; g < rs->ndev; g++) fmgpu_index_free(&rs->replica[g]); free(rs); return err; }
+    if (fmgpu_index_get_meta(rs->replica[0], &meta0) == FM_SUCCESS) g_stats.table_bytes = meta0.nbytes;
     /* derived table on every replica unless $FMGPU_MODE asks for the plain kernels: the sparse-step table (auto and
-     * "sparse"), or the fused-step table ("fused", and auto when the sparse one cannot be built); an index that admits
-     * neither (AltCounters padding quirk, no memory) simply keeps the plain 2-step kernels -- still on the GPU */
+     * "sparse"), or the fused-step table ("fused", and auto when the sparse one cannot be built).  A table that cannot
+     * be built -- no memory, over the table budget -- is never fatal: that replica keeps the plain 2-step kernels,
+     * still on the GPU.  Only a broken context (FM_E_CUDA from anything but an allocation) aborts. */
     {
       /* auto: an index whose plain table stays L2-resident (config 1/2: 10.7 MB) is not worth a table build for one
        * batch: the plain kernels already run at 3-4.6 G reads/s there */
-      fmgpu_index_meta_t meta0;
       const int mode = fm_mode_from_env();
       int want_sparse = (mode == FMGPU_MODE_SPARSE), want_fused = (mode == FMGPU_MODE_FUSED);
-      if (mode == FM_MODE_AUTO && fmgpu_index_get_meta(rs->replica[0], &meta0) == FM_SUCCESS) want_sparse = meta0.nbytes > (96ull << 20);
+      if (mode == FM_MODE_AUTO) want_sparse = g_stats.table_bytes > (96ull << 20);
       for (g = 0; g < rs->ndev && (want_sparse || want_fused); g++) {
+        t0 = fm_wall();
         err = want_sparse ? fmgpu_index_sparsify(rs->replica[g], 0, 0, 0) : FM_E_NOT_IMPLEMENTED;
         if (!err && mode == FM_MODE_AUTO && fmgpu_index_get_meta(rs->replica[g], &meta0) == FM_SUCCESS &&
             meta0.sparse_overflow * 1000ull > meta0.sparse_blocks) {
@@ -380,6 +440,7 @@ int32_t transferCPUtoGPU(void *index, void *queries, void *results)
           if (fmgpu_index_fuse(rs->replica[g], 0, 0, 0) == FM_SUCCESS) fmgpu_index_unsparsify(rs->replica[g]);
         }
         if (err == FM_E_NOT_IMPLEMENTED && (want_fused || mode == FM_MODE_AUTO)) err = fmgpu_index_fuse(rs->replica[g], 0, 0, 0);
+        g_stats.table_build_s[g] = fm_wall() - t0;
         if (err && err != FM_E_NOT_IMPLEMENTED) { for (g = 0; g < rs->ndev; g++) fmgpu_index_free(&rs->replica[g]); free(rs); return err; }
       }
       if (getenv("FMGPU_VERBOSE") && fmgpu_index_get_meta(rs->replica[0], &meta0) == FM_SUCCESS)
@@ -388,30 +449,42 @@ int32_t transferCPUtoGPU(void *index, void *queries, void *results)
     }
     fmi->d_index = rs;
   }
+  /* tables this read length uses (tail table for odd lengths, lead tables of the sparse plan): built here, never by a launch */
+  for (g = 0; g < rs->ndev; g++) {
+    err = fmgpu_index_prepare(rs->replica[g], qrys->size);
+    if (err) return err;
+  }
 
-  /* queries + results: contiguous 32-aligned shards, one per GPU */
-  if (qrys->d_queries) { fm_release_shards((fm_shard_set_t *) qrys->d_queries); qrys->d_queries = NULL; res->d_results = NULL; }
+  /* queries + results: contiguous 32-aligned shards, one per GPU.  Whatever set either handle still holds is released
+   * first, with BOTH of its owners detached -- a queries handle may come back with another results handle or vice versa */
+  if (qrys->d_queries) fm_release_shards((fm_shard_set_t *) qrys->d_queries);
+  if (res->d_results) fm_release_shards((fm_shard_set_t *) res->d_results);
   ss = (fm_shard_set_t *) calloc(1, sizeof(*ss));
   if (!ss) return FM_E_ALLOCATING_MFASTA;
-  ss->ndev = rs->ndev; ss->index = rs; ss->h_results = res->h_results;
+  ss->ndev = rs->ndev; ss->index = rs;
   per = (((uint64_t) qrys->num + rs->ndev - 1) / rs->ndev + 31) & ~31ull;
   for (g = 0; g <= rs->ndev; g++) {
     uint64_t f = per * (uint64_t) g;
     ss->first[g] = f < qrys->num ? f : qrys->num;
   }
-  for (g = 0; g < rs->ndev; g++) {
-    err = fmgpu_batch_create(rs->dev[g], ss->first[g + 1] - ss->first[g], qrys->size, fmi->steps, &ss->shard[g]);
-    if (!err) err = fmgpu_batch_upload_ascii(ss->shard[g], qrys->h_queries + ss->first[g] * qrys->size);
-    if (err) { fm_release_shards(ss); return err; }
+  {
+    const double t0 = fm_wall();
+    for (g = 0; g < rs->ndev; g++) {
+      err = fmgpu_batch_create(rs->dev[g], ss->first[g + 1] - ss->first[g], qrys->size, fmi->steps, &ss->shard[g]);
+      if (!err) err = fmgpu_batch_upload_ascii(ss->shard[g], qrys->h_queries + ss->first[g] * qrys->size);
+      if (err) { fm_release_shards(ss); return err; }
+    }
+    g_stats.queries_h2d_pack_s = fm_wall() - t0;
+    g_stats.query_bytes = (uint64_t) qrys->num * qrys->size;
   }
+  ss->owner_q = qrys; ss->owner_r = res;
   qrys->d_queries = (char *) ss;
   res->d_results = (uint32_t *) ss;
   return FM_SUCCESS;
 }
 
-/* kernels only, all shards in flight at once; void like the reference, so a
- * failure prints and exits (reference HandleError, src/fmIndexGPU-Coop-2Step.cu:88-93) */
-void searchIndexGPU(void *index, void *queries, void *resIntervals)
+/* kernels only, all shards in flight at once.  Error-code form of searchIndexGPU for callers of the fmgpu_* layer. */
+int32_t fmgpu_search_index(void *index, void *queries, void *resIntervals)
 {
   fmi_t *fmi = (fmi_t *) index;
   qrys_t *qrys = (qrys_t *) queries;
@@ -419,10 +492,7 @@ void searchIndexGPU(void *index, void *queries, void *resIntervals)
   fm_shard_set_t *ss = qrys ? (fm_shard_set_t *) qrys->d_queries : NULL;
   int32_t g, err = FM_SUCCESS;
   (void) resIntervals;
-  if (!rs || !ss || ss->index != rs) {
-    fprintf(stderr, "searchIndexGPU: transferCPUtoGPU has not been called for this index/queries (%s:%d)\n", __FILE__, __LINE__);
-    exit(EXIT_FAILURE);
-  }
+  if (!rs || !ss || ss->index != rs) return FM_E_BAD_ARGUMENT;    /* transferCPUtoGPU has not been called for this pair */
   for (g = 0; g < ss->ndev && !err; g++) {
     fmgpu_variant_t v = g_variant;
     if (!g_variant_set) {                      /* $FMGPU_MODE, else the best table the replica has, else Coop */
@@ -436,11 +506,21 @@ void searchIndexGPU(void *index, void *queries, void *resIntervals)
       if (v.mode == FMGPU_MODE_FUSED && !meta.fused_bases) v.mode = FMGPU_MODE_COOP;
       if (v.mode == FMGPU_MODE_SPARSE) v.queries_per_thread = 4;
     }
-    err = fmgpu_batch_search(rs->replica[g], ss->shard[g], &v);
+    err = fmgpu_batch_search_timed_async(rs->replica[g], ss->shard[g], &v);
   }
   for (g = 0; g < ss->ndev && !err; g++) err = fmgpu_batch_sync(ss->shard[g]);
+  for (g = 0; g < ss->ndev && !err; g++) err = fmgpu_batch_last_ms(ss->shard[g], &g_stats.search_ms[g]);
+  if (!err) g_stats.searches += 1;
+  return err;
+}
+
+/* void like the reference, so a failure prints and exits (reference HandleError, src/fmIndexGPU-Coop-2Step.cu:88-93) */
+void searchIndexGPU(void *index, void *queries, void *resIntervals)
+{
+  const int32_t err = fmgpu_search_index(index, queries, resIntervals);
   if (err) {
-    fprintf(stderr, "searchIndexGPU: %s (%s:%d)\n", errorCommon(err), __FILE__, __LINE__);
+    fprintf(stderr, "searchIndexGPU: %s (%s:%d)\n",
+            err == FM_E_BAD_ARGUMENT ? "transferCPUtoGPU has not been called for this index/queries" : errorCommon(err), __FILE__, __LINE__);
     exit(EXIT_FAILURE);
   }
 }
@@ -451,10 +531,15 @@ int32_t transferGPUtoCPU(void *results)
   fm_shard_set_t *ss = res ? (fm_shard_set_t *) res->d_results : NULL;
   int32_t g, err;
   if (!ss || !res->h_results) return FM_E_BAD_ARGUMENT;
-  for (g = 0; g < ss->ndev; g++) {
-    if (ss->first[g + 1] == ss->first[g]) continue;
-    err = fmgpu_batch_download(ss->shard[g], res->h_results + 2 * ss->first[g]);
-    if (err) return err;
+  {
+    const double t0 = fm_wall();
+    for (g = 0; g < ss->ndev; g++) {
+      if (ss->first[g + 1] == ss->first[g]) continue;
+      err = fmgpu_batch_download(ss->shard[g], res->h_results + 2 * ss->first[g]);
+      if (err) return err;
+    }
+    g_stats.results_d2h_s = fm_wall() - t0;
+    g_stats.result_bytes = 8ull * ss->first[ss->ndev];
   }
   return FM_SUCCESS;
 }
@@ -468,6 +553,7 @@ int32_t freeIndexGPU(void **index)
   fmi = (fmi_t *) *index;
   rs = (fm_replica_set_t *) fmi->d_index;
   if (rs) {
+    fm_dump_stats();
     for (g = 0; g < rs->ndev; g++) fmgpu_index_free(&rs->replica[g]);
     free(rs);
     fmi->d_index = NULL;
@@ -475,7 +561,7 @@ int32_t freeIndexGPU(void **index)
   return FM_SUCCESS;
 }
 
-/* queries and results share one shard set: it is released when both sides let go */
+/* queries and results share one shard set: it is released when both sides have let go */
 int32_t freeQueriesGPU(void **queries)
 {
   qrys_t *qrys;
@@ -485,8 +571,8 @@ int32_t freeQueriesGPU(void **queries)
   ss = (fm_shard_set_t *) qrys->d_queries;
   if (ss) {
     qrys->d_queries = NULL;
-    ss->queries_released = 1;
-    if (ss->results_released) fm_release_shards(ss);
+    ss->owner_q = NULL;
+    if (!ss->owner_r) fm_release_shards(ss);
   }
   return FM_SUCCESS;
 }
@@ -500,8 +586,8 @@ int32_t freeResultsGPU(void **results)
   ss = (fm_shard_set_t *) res->d_results;
   if (ss) {
     res->d_results = NULL;
-    ss->results_released = 1;
-    if (ss->queries_released) fm_release_shards(ss);
+    ss->owner_r = NULL;
+    if (!ss->owner_q) fm_release_shards(ss);
   }
   return FM_SUCCESS;
 }

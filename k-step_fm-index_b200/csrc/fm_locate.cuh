@@ -17,7 +17,7 @@
 #ifndef FM_LOCATE_CUH_
 #define FM_LOCATE_CUH_
 
-#include "fm_kernels.cuh"
+#include "fm_device.cuh"
 
 /* node[r] = { LF(r), 1 } for every row carrying a char, { r, 0 } for the row that carries none (the '$' row: the end of
  * the list); term[0] = that row, term[1] = how many such rows were seen (must be 1).  One thread per 96-row block. */

@@ -38,7 +38,7 @@
 #ifndef FM_SPARSE_CUH_
 #define FM_SPARSE_CUH_
 
-#include "fm_fused.cuh"
+#include "fm_device.cuh"
 
 #define FM_SP_PAD   0xFFFFFFFFu
 #define FM_SP_OVF   0xFFFFFFFEu

@@ -238,15 +238,19 @@ def test_ctypes_mirrors_match_the_header(built, tmp_path):
     pkg = helpers.pkg()
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "fmindex_b200.h"\n'
-                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(fmgpu_index_meta_t), offsetof(fmgpu_index_meta_t, nbytes),\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(fmgpu_index_meta_t), offsetof(fmgpu_index_meta_t, nbytes),\n'
                    '  offsetof(fmgpu_index_meta_t, tail_const), offsetof(fmgpu_index_meta_t, sparse_bytes), offsetof(fmgpu_index_meta_t, tail_bytes),\n'
-                   '  sizeof(fmgpu_variant_t), sizeof(fmi_t), sizeof(qrys_t)); return 0; }\n')
+                   '  sizeof(fmgpu_variant_t), sizeof(fmi_t), sizeof(qrys_t), offsetof(fmgpu_index_meta_t, derived_bytes),\n'
+                   '  sizeof(fmgpu_transfer_stats_t), offsetof(fmgpu_transfer_stats_t, search_ms), offsetof(fmgpu_transfer_stats_t, result_bytes),\n'
+                   '  sizeof(fmgpu_pipeline_stats_t)); return 0; }\n')
     exe = tmp_path / "sizes"
     helpers.run(["gcc", "-std=c99", "-I", os.path.join(helpers.ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     m = pkg.fmgpu_index_meta_t
     assert got == [C.sizeof(m), m.nbytes.offset, m.tail_const.offset, m.sparse_bytes.offset, m.tail_bytes.offset,
-                   C.sizeof(pkg.fmgpu_variant_t), C.sizeof(pkg.fmi_t), C.sizeof(pkg.qrys_t)]
+                   C.sizeof(pkg.fmgpu_variant_t), C.sizeof(pkg.fmi_t), C.sizeof(pkg.qrys_t), m.derived_bytes.offset,
+                   C.sizeof(pkg.fmgpu_transfer_stats_t), pkg.fmgpu_transfer_stats_t.search_ms.offset,
+                   pkg.fmgpu_transfer_stats_t.result_bytes.offset, C.sizeof(pkg.fmgpu_pipeline_stats_t)]
 
 
 def test_bench_and_entry_scripts_compile_without_warnings():
