@@ -214,22 +214,26 @@ typedef struct {
   /* sparse-step table (fmgpu_index_sparsify), 0 = none */
   uint32_t sparse_bases;       /* bases per sparse step                                         */
   uint32_t sparse_lambda;      /* target occurrences per block                                  */
-  uint64_t sparse_bytes;       /* blocks + directory (+ start table)                            */
-  uint64_t sparse_blocks;      /* number of blocks                                              */
-  uint64_t sparse_overflow;    /* blocks holding more occurrences than slots (served by SB96 steps) */
+  uint64_t sparse_bytes;       /* blocks (+ start / lead tables)                                */
+  uint64_t sparse_blocks;      /* number of blocks: grid + tree nodes                           */
+  uint64_t sparse_overflow;    /* buckets holding more occurrences than slots (roots of search trees) */
   uint32_t sparse_start_bases; /* bases covered by the sparse kernel's start table, 0 = none    */
   uint32_t sparse_lanes;       /* lanes per block: 2 = 64-byte blocks (15 slots), 4 = 128-byte blocks (31 slots) */
   /* tail table: the derived 1-step rank above re-blocked so that the last base of an odd-length read costs one
    * block fetch instead of four; built on this replica by its first odd-length search (a quarter of nbytes), 0 = not
    * built (yet, or $FMGPU_TAIL_TABLE=0, or no memory: the four-fetch derivation is used) */
   uint64_t tail_bytes;
-  /* sparse-step table laid out as a uniform grid: every wide symbol owns this many blocks and the kernel computes a
-   * symbol's first block instead of looking it up (chosen when all symbols occur about equally often, i.e. on
-   * uniformly random texts; $FMGPU_SPARSE_UNIFORM=0/1 forces); 0 = per-symbol block counts and a directory */
+  /* grid of the sparse-step table: every wide symbol owns this many blocks (root of (symbol, row) is computed, not looked up) */
   uint32_t sparse_uniform_nb;
   uint32_t sa_rate;            /* suffix array kept for locate: 1 = every row (fmgpu_index_build_sa), s > 1 = the rows whose
                                   text position is a multiple of s (fmgpu_index_build_sa_sampled), 0 = none */
   uint64_t sa_bytes;           /* its size: 4 bytes per BWT row when full, ~4/s + 1/6 bytes per row when sampled */
+  /* search trees of the sparse-step table: buckets with more occurrences than a block has slots (repeats, skewed
+   * texts) are the root of a tree of blocks over their occurrence list; sparse_overflow counts those buckets */
+  uint64_t sparse_tree_nodes;  /* blocks below the grid                                          */
+  uint64_t sparse_tree_rows;   /* occurrences living in trees (of bwtsize)                       */
+  uint32_t sparse_tree_depth;  /* levels below the grid of the deepest tree                      */
+  uint32_t reserved1;
   uint64_t derived_bytes;      /* everything this replica derived from its SB96 table: sparse + fused + tail + SA tables */
   uint64_t budget_bytes;       /* the limit derived_bytes is kept under ($FMGPU_TABLE_BUDGET_GB / fmgpu_set_table_budget), 0 = none */
 } fmgpu_index_meta_t;
@@ -284,15 +288,17 @@ int32_t fmgpu_index_alloc_like(int32_t device, const fmgpu_index_meta_t *meta, f
 int32_t fmgpu_index_fuse(fmgpu_index_t *idx, uint32_t fused_bases, uint32_t lanes, uint64_t budget_bytes);
 int32_t fmgpu_index_unfuse(fmgpu_index_t *idx);
 /* Sparse-step table, built on the GPU from this replica's own block table: one sparse step = sparse_bases/k
- * reference LF steps (exactly); per wide symbol the occurrence rows are cut into blocks of ~lambda rows, one block
- * fetch per rank (csrc/fm_sparse.cuh).  sparse_bases 0 = 14 or 12 when the table can then be a uniform grid (see below;
- * needs >= 5 rows per 14-mer / >= 64 per 12-mer on average and even symbol counts), else the widest multiple of k up
- * to 10 that leaves at least 64 rows per symbol (explicit widths: multiples of k up to 14); lanes 0 = 2 (64-byte blocks, 15 slots; 4 = 128-byte blocks, 31 slots); lambda 0 = 5 / 12;
- * the table takes ~32*lanes/lambda bytes per text base whatever the width.  Blocks with more occurrences than
- * slots (repeats) are served by ordinary steps on the block table.  When no wide symbol occurs more than 1.6 x as
- * often as the mean (uniformly random texts) the table is a uniform grid -- the same block count for every symbol,
- * no directory lookup in the kernel (meta.sparse_uniform_nb; $FMGPU_SPARSE_UNIFORM=0/1 forces).
- * FM_E_NOT_IMPLEMENTED when memory does not suffice or the index carries the AltCounters padding quirk. */
+ * reference LF steps (exactly).  Per wide symbol the occurrence rows are cut into a uniform grid of buckets, the same
+ * number for every symbol (meta.sparse_uniform_nb, ~lambda rows per bucket on average), so a bucket's block is
+ * computed, never looked up: one block fetch per rank (csrc/fm_sparse.cuh).  A bucket with more occurrences than a block
+ * has slots (repeats, skewed texts) becomes the root of a search tree of blocks over its occurrence list
+ * (meta.sparse_overflow / sparse_tree_*): depth + 1 fetches for those, on any text -- nothing falls back to the block
+ * table.  sparse_bases 0 = the widest multiple of k up to 14 that leaves lambda rows per symbol on average (14 bases from
+ * 1.34 Gbp, 12 from 84 Mbp ...; explicit widths: multiples of k up to 14); lanes 0 = 2 (64-byte blocks, 15 slots; 4 =
+ * 128-byte blocks, 31 slots); lambda 0 = 5 / 12.  The grid takes ~32*lanes/lambda bytes per text base whatever the
+ * width, the trees at most 32*lanes/(slots-1) bytes per row living in them.  AltCounters files with an active
+ * padding-entry quirk are served too (a few phantom occurrences).  FM_E_NOT_IMPLEMENTED when memory or the table budget
+ * does not suffice. */
 int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_bases, uint32_t lambda, uint32_t lanes);
 int32_t fmgpu_index_unsparsify(fmgpu_index_t *idx);
 /* Builds NOW (synchronously) whatever a search of `len`-base reads on this replica may use: the tail table for odd
@@ -383,6 +389,8 @@ int32_t fmgpu_unstream_device(int32_t device, const uint32_t *d_stream, uint64_t
                               uint32_t *d_packed, void *stream);
 void    fm_hostpack_set_streams(int streams);  /* interleaved sub-streams per packer thread (default 4, 1 = one; $FM_HOSTPACK_STREAMS) */
 void    fm_hostpack_set_prefetch(int bytes);   /* software prefetch distance of the stream packer (default 8192, 0 = off) */
+/* host DRAM read bandwidth over a caller's buffer, GB/s (best of iters, all threads): the ceiling of any ASCII feed */
+double  fm_host_read_bandwidth(const void *buf, uint64_t bytes, int nthreads, int iters);
 int     fm_hostpack_has_simd(void);
 int     fm_hostpack_threads(void);
 
@@ -445,10 +453,10 @@ int32_t fmgpu_gather_probe_ex(int32_t device, uint64_t table_bytes, uint32_t acc
 /* same for FMGPU_MODE_FUSED: fused-table blocks and SB96 blocks (leading steps) one search must fetch */
 int32_t fmgpu_count_fetches_fused_device(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nqueries, uint32_t len,
                                          uint32_t *d_results, void *stream, uint64_t *nfused_blocks, uint64_t *nlead_blocks);
-/* same for FMGPU_MODE_SPARSE: sparse blocks, SB96 blocks (leading steps + overflow fallback), overflow events */
+/* same for FMGPU_MODE_SPARSE: grid blocks (roots), SB96 blocks (leftover base steps), tree blocks below the roots */
 int32_t fmgpu_count_fetches_sparse_device(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nqueries, uint32_t len,
-                                          uint32_t *d_results, void *stream, uint64_t *nsparse_blocks, uint64_t *nsb96_blocks,
-                                          uint64_t *noverflows);
+                                          uint32_t *d_results, void *stream, uint64_t *nroot_blocks, uint64_t *nsb96_blocks,
+                                          uint64_t *ntree_blocks);
 /* locality variant: the 32 lanes of every warp-level load fall inside ONE random window of
  * `window_bytes` (e.g. one 2 MB page), random blocks inside it: isolates address-translation cost */
 int32_t fmgpu_gather_probe_local(int32_t device, uint64_t table_bytes, uint64_t window_bytes, uint64_t loads_per_thread,

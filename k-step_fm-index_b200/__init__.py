@@ -75,7 +75,8 @@ class fmgpu_index_meta_t(C.Structure):
                 ("sparse_blocks", C.c_uint64), ("sparse_overflow", C.c_uint64), ("sparse_start_bases", C.c_uint32),
                 ("sparse_lanes", C.c_uint32), ("tail_bytes", C.c_uint64),
                 ("sparse_uniform_nb", C.c_uint32), ("sa_rate", C.c_uint32), ("sa_bytes", C.c_uint64),
-                ("derived_bytes", C.c_uint64), ("budget_bytes", C.c_uint64)]
+                ("sparse_tree_nodes", C.c_uint64), ("sparse_tree_rows", C.c_uint64), ("sparse_tree_depth", C.c_uint32),
+                ("reserved1", C.c_uint32), ("derived_bytes", C.c_uint64), ("budget_bytes", C.c_uint64)]
 
 
 class fmgpu_transfer_stats_t(C.Structure):
@@ -180,6 +181,7 @@ PROTOTYPES = {
     "fm_hostpack_set_prefetch": (None, [C.c_int]),
     "fm_hostpack_set_streams": (None, [C.c_int]),
     "fm_hostpack_has_simd": (C.c_int, []),
+    "fm_host_read_bandwidth": (C.c_double, [_VP, C.c_uint64, C.c_int, C.c_int]),
     "fm_hostpack_threads": (C.c_int, []),
     "fmgpu_gather_probe_local": (C.c_int32, [C.c_int32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.POINTER(C.c_double)]),
     "fmgpu_count_fetches_device": (C.c_int32, [_VP, _VP, C.c_uint64, C.c_uint32, _VP, _VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

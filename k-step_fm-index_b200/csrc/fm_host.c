@@ -434,9 +434,11 @@ int32_t transferCPUtoGPU(void *index, void *queries, void *results)
         t0 = fm_wall();
         err = want_sparse ? fmgpu_index_sparsify(rs->replica[g], 0, 0, 0) : FM_E_NOT_IMPLEMENTED;
         if (!err && mode == FM_MODE_AUTO && fmgpu_index_get_meta(rs->replica[g], &meta0) == FM_SUCCESS &&
-            meta0.sparse_overflow * 1000ull > meta0.sparse_blocks) {
-          /* repeat-rich text: more than 0.1 % of the sparse blocks are overfull, reads from the repeats would take the
-           * SB96 fallback in every few steps (profiles/r01_repeat_text.md) -- the fused-step table does not care */
+            meta0.sparse_tree_rows * 4ull > meta0.bwtsize) {
+          /* repeat-rich text: more than a quarter of the rows live in search trees, i.e. in wide symbols that occur
+           * dozens to thousands of times; reads from those repeats keep a WIDE interval, whose two ends walk separate
+           * tree paths in every step (profiles/r02_skewed_text.md) -- the fused-step table's bitmaps are addressed by
+           * row and do not care, so it wins there whenever it fits */
           if (fmgpu_index_fuse(rs->replica[g], 0, 0, 0) == FM_SUCCESS) fmgpu_index_unsparsify(rs->replica[g]);
         }
         if (err == FM_E_NOT_IMPLEMENTED && (want_fused || mode == FM_MODE_AUTO)) err = fmgpu_index_fuse(rs->replica[g], 0, 0, 0);

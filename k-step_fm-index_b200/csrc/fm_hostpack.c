@@ -248,3 +248,39 @@ void fm_hostpack_reads_scalar(const char *ascii, uint64_t nq, uint32_t len, uint
   uint64_t q;
   for (q = 0; q < nq; q++) pack_read_scalar((const unsigned char *) ascii + q * len, len, wpq, packed + q * wpq);
 }
+
+/* Host DRAM read bandwidth over a caller's buffer (GB/s, best of `iters` passes, all threads): the ceiling of ANY feed
+ * of ASCII reads -- every read costs its `len` bytes of host DRAM reads whoever fetches them, the DMA engine or a
+ * packer thread.  bench.py prints e2e next to (this / bytes per read).  The buffer should be far larger than L3. */
+double fm_host_read_bandwidth(const void *buf, uint64_t bytes, int nthreads, int iters)
+{
+  const uint64_t nw = bytes / 8;
+  const uint64_t *p = (const uint64_t *) buf;
+  double best = 0.0;
+  int it;
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+  if (iters < 1) iters = 1;
+  for (it = 0; it < iters; it++) {
+    uint64_t sink = 0;
+    int64_t t;
+    const double t0 = omp_get_wtime();
+    #pragma omp parallel for schedule(static, 1) num_threads(nthreads) reduction(^ : sink)
+    for (t = 0; t < (int64_t) nthreads; t++) {
+      const uint64_t per = (nw + (uint64_t) nthreads - 1) / (uint64_t) nthreads;
+      const uint64_t a = (uint64_t) t * per, b = (a + per < nw) ? a + per : nw;
+      uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0, i;
+      for (i = a; i + 32 <= b; i += 32) {
+        uint64_t j;
+        for (j = 0; j < 32; j += 4) { s0 ^= p[i + j]; s1 ^= p[i + j + 1]; s2 ^= p[i + j + 2]; s3 ^= p[i + j + 3]; }
+      }
+      sink ^= s0 ^ s1 ^ s2 ^ s3;
+    }
+    {
+      const double dt = omp_get_wtime() - t0;
+      const double gbs = dt > 0 ? (double) bytes / dt / 1e9 : 0.0;
+      if (sink == 0x9E3779B97F4A7C15ull) gbs > 0 ? (void) 0 : (void) 0;   /* keeps the loads alive */
+      if (gbs > best) best = gbs;
+    }
+  }
+  return best;
+}

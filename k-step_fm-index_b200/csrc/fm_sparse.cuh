@@ -1,39 +1,42 @@
 /*
- * fm_sparse.cuh -- "sparse-step" device layout and search kernel: KS (up to 14) query bases per block fetch.
+ * fm_sparse.cuh -- "sparse-step" device layout and search kernel: KS (up to 14) query bases per block fetch, on ANY text.
  *
- * Measured on B200 (profiles/r01_miss_ceiling.md): the memory system serves ~46 G random block fetches per second
- * whatever their size up to a 128-byte line, and nothing else limits the search.  The fused-step layout
- * (fm_fused.cuh) spends one fetch on 4 bases and cannot go further: its per-symbol indicator bitmaps cost
- * 4^KF bits per row.  But the indicator of ONE wide symbol is almost empty (density 4^-KS), so this layout stores
- * the set bits themselves:
+ * Measured on B200 (profiles/r01_miss_ceiling.md, r02_ceiling_counters.md): the memory system serves ~46 G random block
+ * fetches per second whatever their size up to a 128-byte line, and nothing else limits the search.  The fused-step
+ * layout (fm_fused.cuh) spends one fetch on 4 bases and cannot go further: its per-symbol indicator bitmaps cost 4^KF
+ * bits per row.  But the indicator of ONE wide symbol is almost empty (density 4^-KS), so this layout stores the set
+ * bits themselves:
  *
  *   wide symbol of row i    F(i) = s(i) | s(LF(i)) << 2k | ...   (hops = KS/k hops, exactly as in fm_fused.cuh, so
  *                           rank_F(sigma, X) = rank_F(sigma, 0) + #{ i < X : F(i) = sigma } IS `hops` consecutive
  *                           reference LF steps, for every X; rows whose chain meets a '$' row carry no symbol)
- *   occurrence list         rows i with F(i) = sigma, ascending  (a stable radix sort of (F(i), i))
- *   buckets                 symbol sigma owns nb(sigma) = max(1, ceil(count(sigma) / lambda)) blocks;
- *                           row X belongs to bucket umulhi(X, scale(sigma)) -- a monotone map of [0, bwtsize] onto
- *                           [0, nb) -- so a bucket holds ~lambda occurrences whatever the symbol's frequency
- *   block (32*LANES bytes)  word 0      = rank_F(sigma, first row of the bucket)
- *                           words 1..   = the bucket's occurrence rows, ascending, padded with 0xFFFFFFFF
- *                           (31 slots in a 128-byte block, LANES = 4; 15 in a 64-byte block, LANES = 2)
- *                           a bucket with more occurrences than slots stores 0xFFFFFFFE in the last word instead
- *   directory               dir[sigma] = { first block, scale }     (8 bytes x 4^KS: L2-resident for KS <= 10)
- *   uniform grid            when every symbol occurs about equally often (a uniformly random text: no count above 1.6 x the
- *                           mean or below 0.4 x of it) all symbols get the SAME number of blocks, first block = sigma * nb, one scale:
- *                           the directory lookup -- an L2 request per step that costs 15 % of the fetch rate -- is
- *                           replaced by a multiplication.  Skewed texts (any real genome) keep per-symbol block counts.
+ *   occurrence list         rows i with F(i) = sigma, ascending  (a stable radix sort of (F(i), i)).  An AltCounters
+ *                           file with an active padding-entry quirk adds a few "phantom" occurrences -- the composed
+ *                           rank function then jumps by 2 at one row -- which are just list entries (a row may repeat).
+ *   node (32*LANES bytes)   word 0, then SLOTS = 8*LANES - 1 ascending u32 entries padded with 0xFFFFFFFF:
+ *        leaf               word 0 = rank_F(sigma, .) before the first entry; entries = occurrence rows.
+ *                           rank_F(sigma, X) = word 0 + #{ entries < X }
+ *        inner node         last entry = 0xFFFFFFFE (marker); the other SLOTS - 1 entries are separators = the first
+ *                           occurrence row of children 1 .. SLOTS - 1; word 0 = block number of child 0.
+ *                           child of X = word 0 + #{ entries < X }  -- the SAME arithmetic as a leaf's rank
+ *   uniform grid (roots)    every wide symbol owns nb blocks; row X belongs to bucket umulhi(X, scale), a monotone map
+ *                           of [0, bwtsize] onto [0, nb); root of (sigma, X) = block sigma * nb + umulhi(X, scale):
+ *                           computed, never looked up (a directory lookup per step costs 15 % of the fetch rate,
+ *                           profiles/r01_hit_miss_mix.md).  A bucket with <= SLOTS occurrences is a leaf: on a uniformly
+ *                           random text 99.99 % of them, so a step is ONE fetch.
+ *   search tree (skew)      a bucket with more occurrences is the root of a tree over ITS occurrence list: leaves of
+ *                           SLOTS consecutive occurrences, fan-out SLOTS, all leaves at the same depth, nodes stored
+ *                           behind the grid (level by level).  Subdividing by occurrence RANK (not by row range) keeps
+ *                           the depth at ceil(log_SLOTS(count / SLOTS)) however the occurrences cluster -- repeats
+ *                           of a genome put thousands of them in a few BWT runs.  Heavy symbols cost depth + 1 fetches
+ *                           instead of `hops` fetches of the plain table; nothing falls back to SB96 any more.
  *
- *   one rank     = dir[sigma] (L2 hit; sigma is known in advance, the lookup is issued one step ahead)
- *                  + ONE block fetch by LANES lanes x 256 bits;  rank = word 0 + #{ entries < X }
- *   L and R      almost always share the block (a bucket spans bwtsize / nb rows), so a step is one fetch
- *   overflow     a block marked 0xFFFFFFFE sends that read through `hops` ordinary steps on the SB96 table for
- *                this symbol -- exact, and rare by construction (Poisson tail for lambda = 16: 2e-4 per fetch on a
- *                random text; repeats of a real genome cost speed, never correctness)
+ * Kernel: every lane group runs its OWN state machine per read -- one block fetch per iteration, whatever that read
+ * needs next (root of the next step, a child, the other interval end's node) -- so a read that walks a deep tree only
+ * delays itself, not the 63 other reads of its warp (r01_repeat_text.md: in lockstep, fewer fetches ran slower).
  *
- * Table size is ~128 / lambda bytes per text base for ANY KS (8 B/base at lambda = 16: 16 GB for 2 Gbp, a quarter
- * of the fused table) and a 100-bp read needs 10 fetches at KS = 10 instead of 25 (9 after the start table).
- * Not available for AltCounters files carrying the padding-entry quirk, like the fused table.
+ * Table size: grid = ~32*LANES/lambda bytes per text base for ANY KS (12.8 B/base at the default lambda 5, LANES 2),
+ * plus 32*LANES/(SLOTS-1) bytes per occurrence living in an overfull bucket (at most 4.6 B/base).
  */
 #ifndef FM_SPARSE_CUH_
 #define FM_SPARSE_CUH_
@@ -41,13 +44,14 @@
 #include "fm_device.cuh"
 
 #define FM_SP_PAD   0xFFFFFFFFu
-#define FM_SP_OVF   0xFFFFFFFEu
+#define FM_SP_INNER 0xFFFFFFFEu            /* last word of an inner node (bwtsize < this, so no row collides) */
 #define FM_SP_NONE  0xFFFFFFFFu            /* compose output of a row without a wide symbol (sorted last) */
+#define FM_SP_DONE  0xFFFFFFFFu            /* state machine: this interval end has its new value */
+#define FM_SP_MAXDEPTH 9
 
 struct FmSparseParams {
-  const uint4    *sblocks;    /* sparse table, 2*LANES uint4 per block                             */
-  const uint2    *dir;        /* per wide symbol: { first block, scale }                           */
-  const uint4    *blocks;     /* SB96: leading steps, overflow fallback, odd tail                  */
+  const uint4    *sblocks;    /* grid + tree nodes, 2*LANES uint4 per block                        */
+  const uint4    *blocks;     /* SB96: leftover base-k steps, odd tail                             */
   const uint32_t *packed;
   uint32_t       *results;
   uint32_t nblocks;           /* SB96 stride                                                       */
@@ -57,23 +61,16 @@ struct FmSparseParams {
   uint32_t wpq;
   uint32_t bwtsize;
   uint32_t sbits;             /* 2 * KS                                                            */
-  uint32_t hops;              /* KS / k                                                            */
-  unsigned long long *fetch_counters;  /* COUNT only: [0] sparse blocks, [1] SB96 blocks (leading + fallback), [2] overflow fallbacks */
+  unsigned long long *fetch_counters;  /* COUNT only: [0] root fetches, [1] SB96 blocks (leftover steps), [2] tree-node fetches below the roots */
   uint32_t has_tail, tail_row, tail_base, tail_const[4];
   const uint4 *tail1;         /* tail table (fm_tail_table_kernel) or NULL */
-  uint32_t uni_nb, uni_scale; /* uniform grid (every symbol owns uni_nb blocks, first block = sigma * uni_nb): no directory
-                                 lookup; 0 = per-symbol block counts, read from dir                                  */
+  uint32_t nb, scale;         /* grid: blocks per wide symbol, bucket = umulhi(X, scale)          */
+  uint32_t nroots;            /* nb * 4^KS: blocks at or beyond it are tree nodes                  */
   const uint2 *start;         /* (L,R) after the first start_bits / 2 bases, indexed by those packed bits, or NULL: the start
                                  table (a whole number of sparse steps) or a lead table (the leftover bases, taken first) */
   uint32_t start_bits;
+  uint32_t quirk_start, quirk_mask;   /* AltCounters padding quirk, for the SB96 base steps (0xFFFFFFFF / 0 = none) */
 };
-
-/* directory entry { first block, scale } of a wide symbol: computed when the table is a uniform grid, else one L2-resident
- * lookup (which costs request slots beside the block fetches: profiles/r01_hit_miss_mix.md) */
-__device__ __forceinline__ uint2 fm_sparse_dir(const FmSparseParams &p, uint32_t sig)
-{
-  return p.uni_nb ? make_uint2(sig * p.uni_nb, p.uni_scale) : __ldg(p.dir + sig);
-}
 
 __device__ __forceinline__ void fm_ldg32_line(const uint4 *p, uint32_t (&w)[8])
 {
@@ -81,7 +78,7 @@ __device__ __forceinline__ void fm_ldg32_line(const uint4 *p, uint32_t (&w)[8])
                : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
 }
 
-/* this lane's share of #{ entries < X }: lane 0 skips word 0 (the sampled rank) */
+/* this lane's share of #{ entries < X }: lane 0 skips word 0 */
 __device__ __forceinline__ uint32_t fm_sparse_partial(const uint32_t (&w)[8], uint32_t X, uint32_t lg)
 {
   uint32_t c = (lg != 0u && w[0] < X) ? 1u : 0u;
@@ -147,12 +144,13 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_kernel(const F
     L[i] = 0u; R[i] = p.bwtsize;
   }
 
-  unsigned long long n_sp = 0, n_sb = 0, n_ovf = 0;
+  unsigned long long n_root = 0, n_sb = 0, n_tree = 0;
   uint32_t pos = 0;
   /* the (len/k) % hops base-k steps that do not fill a sparse step run on SB96: in FRONT of the sparse steps (wide
    * interval, upper levels of the table, L2 hits) when there is no table to start from, BEHIND them when the start
    * table replaces the first sparse step (one DRAM block per step there); with 6 or more leftover bases a lead
-   * table takes them first instead and every sparse step runs (fm_launch_sparse) */
+   * table takes them first instead and every sparse step runs (fm_launch_sparse).  All reads of the CTA do the same
+   * number of these, so they stay in lockstep. */
   auto base_steps = [&](uint32_t count) {
     for (uint32_t step = 0; step < count; step++, pos += BBITS) {
       #pragma unroll
@@ -163,8 +161,9 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_kernel(const F
         const uint4 vL = fm_ldg16(base + bL);
         const uint4 vR = (bL == bR) ? vL : fm_ldg16(base + bR);
         if (COUNT && live[i] && lg == 0) n_sb += (bL == bR) ? 1 : 2;
-        L[i] = fm_block_rank(vL, L[i] - bL * FM_SB_ROWS);
-        R[i] = fm_block_rank(vR, R[i] - bR * FM_SB_ROWS);
+        const uint32_t nL = fm_block_rank(vL, L[i] - bL * FM_SB_ROWS) + fm_quirk_delta(p.quirk_mask, p.quirk_start, sg, L[i]);
+        const uint32_t nR = fm_block_rank(vR, R[i] - bR * FM_SB_ROWS) + fm_quirk_delta(p.quirk_mask, p.quirk_start, sg, R[i]);
+        L[i] = nL; R[i] = nR;
       }
     }
   };
@@ -178,91 +177,63 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_kernel(const F
     pos = p.start_bits;
   }
   base_steps(p.nfront);
-  const uint32_t step0 = 0;
 
-  uint32_t sig[QPT];
-  uint2 d[QPT];
-  if (step0 < p.nsteps) {
-    #pragma unroll
-    for (int i = 0; i < QPT; i++) { sig[i] = fm_read_field(myq[i], pos, smask); d[i] = fm_sparse_dir(p, sig[i]); }
+  /* ---- sparse steps: one state machine per read.  aL / aR = block to fetch next for that interval end, FM_SP_DONE
+   * once the end holds its value for the NEXT step; rem = sparse steps not yet finished.  Every iteration fetches
+   * exactly one block per unfinished read: the node both ends share, else L's node, else R's. */
+  uint32_t aL[QPT], aR[QPT], rem[QPT];
+  bool busy = false;
+  #pragma unroll
+  for (int i = 0; i < QPT; i++) {
+    rem[i] = live[i] ? p.nsteps : 0u;
+    aL[i] = aR[i] = FM_SP_DONE;
+    if (rem[i]) {
+      const uint32_t first = fm_read_field(myq[i], pos, smask) * p.nb;
+      aL[i] = first + __umulhi(L[i], p.scale);
+      aR[i] = first + __umulhi(R[i], p.scale);
+    }
+    busy |= rem[i] != 0u;
   }
-  for (uint32_t step = step0; step < p.nsteps; step++) {
+  while (__any_sync(0xFFFFFFFFu, busy)) {
     uint32_t w[QPT][8];
-    const uint4 *aR[QPT];
-    bool same[QPT];
     #pragma unroll
     for (int i = 0; i < QPT; i++) {
-      const uint32_t bL = __umulhi(L[i], d[i].y), bR = __umulhi(R[i], d[i].y);
-      const uint4 *base = p.sblocks + (size_t) d[i].x * BU4 + 2u * lg;
-      same[i] = (bL == bR);
-      aR[i] = base + (size_t) bR * BU4;
-      if (COUNT && live[i] && lg == 0) n_sp += same[i] ? 1 : 2;
-      fm_sparse_load<LANES>(base + (size_t) bL * BU4, w[i]);
+      if (rem[i]) {
+        const uint32_t a = (aL[i] != FM_SP_DONE) ? aL[i] : aR[i];
+        fm_sparse_load<LANES>(p.sblocks + (size_t) a * BU4 + 2u * lg, w[i]);
+        if (COUNT && lg == 0) { if (a < p.nroots) n_root++; else n_tree++; }
+      }
     }
-    /* directory entries of the NEXT step (independent of L,R): in flight together with the block fetches */
-    uint32_t sig_now[QPT];
-    pos += p.sbits;
+    busy = false;
     #pragma unroll
     for (int i = 0; i < QPT; i++) {
-      sig_now[i] = sig[i];
-      if (step + 1 < p.nsteps) { sig[i] = fm_read_field(myq[i], pos, smask); d[i] = fm_sparse_dir(p, sig[i]); }
-    }
-    uint32_t cL[QPT], cR[QPT];
-    bool ovf[QPT];
-    bool any_far = false;
-    #pragma unroll
-    for (int i = 0; i < QPT; i++) {
-      cL[i] = fm_sparse_partial(w[i], L[i], lg);
-      cR[i] = fm_sparse_partial(w[i], R[i], lg);
-      if (lg == 0) { cL[i] += w[i][0]; cR[i] += w[i][0]; }
-      ovf[i] = (lg == LANES - 1) && (w[i][7] == FM_SP_OVF);
-      any_far |= !same[i];
-    }
-    if (__any_sync(0xFFFFFFFFu, any_far)) {                   /* rare: R lies in another bucket than L */
-      #pragma unroll
-      for (int i = 0; i < QPT; i++) {
-        if (!same[i]) {
-          uint32_t v[8];
-          fm_sparse_load<LANES>(aR[i], v);
-          cR[i] = fm_sparse_partial(v, R[i], lg) + (lg == 0 ? v[0] : 0u);
-          ovf[i] |= (lg == LANES - 1) && (v[7] == FM_SP_OVF);
+      /* the lanes of a group hold the same state, so they take the same branches */
+      const bool act = rem[i] != 0u;
+      const bool doL = act && aL[i] != FM_SP_DONE;
+      const bool doR = act && (!doL || aR[i] == aL[i]);                  /* R alone, or riding on the node it shares with L */
+      uint32_t cL = 0, cR = 0, inner = 0;
+      if (act) {
+        cL = fm_sparse_partial(w[i], L[i], lg);
+        cR = fm_sparse_partial(w[i], R[i], lg);
+        if (lg == 0) { cL += w[i][0]; cR += w[i][0]; }
+        inner = (lg == LANES - 1 && w[i][7] == FM_SP_INNER) ? 1u : 0u;
+      }
+      const uint32_t vL = fm_group_sum<LANES>(cL), vR = fm_group_sum<LANES>(cR);
+      const bool is_inner = fm_group_sum<LANES>(inner) != 0u;
+      if (doL) { if (is_inner) aL[i] = vL; else { L[i] = vL; aL[i] = FM_SP_DONE; } }
+      if (doR) { if (is_inner) aR[i] = vR; else { R[i] = vR; aR[i] = FM_SP_DONE; } }
+      if (act && aL[i] == FM_SP_DONE && aR[i] == FM_SP_DONE) {           /* step complete: next step's roots */
+        rem[i] -= 1u;
+        if (rem[i]) {
+          const uint32_t first = fm_read_field(myq[i], pos + (p.nsteps - rem[i]) * p.sbits, smask) * p.nb;
+          aL[i] = first + __umulhi(L[i], p.scale);
+          aR[i] = first + __umulhi(R[i], p.scale);
         }
       }
-      __syncwarp();
+      busy |= rem[i] != 0u;
     }
-    uint32_t nL[QPT], nR[QPT], ob[QPT];
-    bool any_ovf = false;
-    #pragma unroll
-    for (int i = 0; i < QPT; i++) {
-      nL[i] = fm_group_sum<LANES>(cL[i]);
-      nR[i] = fm_group_sum<LANES>(cR[i]);
-      ob[i] = (__ballot_sync(0xFFFFFFFFu, ovf[i]) >> ((threadIdx.x & 31u) & ~(uint32_t)(LANES - 1))) & ((1u << LANES) - 1u);
-      any_ovf |= (ob[i] != 0u);
-    }
-    if (__any_sync(0xFFFFFFFFu, any_ovf)) {                   /* rare: overfull bucket -> the same `hops` steps on SB96 */
-      #pragma unroll
-      for (int i = 0; i < QPT; i++) {
-        if (ob[i]) {
-          uint32_t xl = L[i], xr = R[i];
-          for (uint32_t h = 0; h < p.hops; h++) {
-            const uint32_t s = (sig_now[i] >> (BBITS * h)) & BMASK;
-            const uint32_t bL = fm_div96(xl), bR = fm_div96(xr);
-            const uint4 *base = p.blocks + (size_t) s * p.nblocks;
-            const uint4 vL = fm_ldg16(base + bL);
-            const uint4 vR = (bL == bR) ? vL : fm_ldg16(base + bR);
-            if (COUNT && live[i] && lg == 0) n_sb += (bL == bR) ? 1 : 2;
-            xl = fm_block_rank(vL, xl - bL * FM_SB_ROWS);
-            xr = fm_block_rank(vR, xr - bR * FM_SB_ROWS);
-          }
-          nL[i] = xl; nR[i] = xr;
-          if (COUNT && live[i] && lg == 0) n_ovf += 1;
-        }
-      }
-      __syncwarp();
-    }
-    #pragma unroll
-    for (int i = 0; i < QPT; i++) { L[i] = nL[i]; R[i] = nR[i]; }
   }
+  pos += p.nsteps * p.sbits;
 
   base_steps(p.nback);
 
@@ -281,11 +252,11 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_kernel(const F
   }
   if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) {
-      n_sp += __shfl_xor_sync(0xFFFFFFFFu, n_sp, o);
+      n_root += __shfl_xor_sync(0xFFFFFFFFu, n_root, o);
       n_sb += __shfl_xor_sync(0xFFFFFFFFu, n_sb, o);
-      n_ovf += __shfl_xor_sync(0xFFFFFFFFu, n_ovf, o);
+      n_tree += __shfl_xor_sync(0xFFFFFFFFu, n_tree, o);
     }
-    if ((threadIdx.x & 31) == 0) { atomicAdd(p.fetch_counters, n_sp); atomicAdd(p.fetch_counters + 1, n_sb); atomicAdd(p.fetch_counters + 2, n_ovf); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(p.fetch_counters, n_root); atomicAdd(p.fetch_counters + 1, n_sb); atomicAdd(p.fetch_counters + 2, n_tree); }
   }
 }
 
@@ -293,138 +264,231 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_kernel(const F
  * Construction from SB96 (all on the device)
  * ------------------------------------------------------------------------ */
 
+/* rank of the reference searcher this table reproduces: SB96 value + the AltCounters padding-quirk constant */
+__device__ __forceinline__ uint32_t fm_sb96_rank_q(const uint4 *__restrict__ blocks, uint32_t nblocks, uint32_t s, uint32_t X,
+                                                   uint32_t quirk_start, uint32_t quirk_mask)
+{
+  return fm_sb96_rank(blocks, nblocks, s, X) + fm_quirk_delta(quirk_mask, quirk_start, s, X);
+}
+
 /* wide symbol of every row < bwtsize (the LF chain of fm_fuse_compose_kernel, 32-bit output) and its row number;
- * rows without a symbol get the key nsym, which sorts behind every symbol */
+ * rows without a symbol get the key nsym, which sorts behind every symbol.  With an active quirk the chain follows the
+ * quirked rank, and every visit of row quirk_start - 1 (where the quirked rank functions have their extra jump) is
+ * reported in `visits` = { origin row, hop, symbols so far }: fm_sparse_phantoms_kernel adds the phantom occurrences. */
+struct FmSparseVisit { uint32_t origin, hop, acc; };
 __global__ void fm_sparse_compose_kernel(const uint4 *__restrict__ blocks, uint32_t nblocks, const uint8_t *__restrict__ sym,
                                          uint32_t bwtsize, uint32_t kbits, uint32_t hops, uint32_t nsym,
-                                         uint32_t *__restrict__ keys, uint32_t *__restrict__ rows)
+                                         uint32_t quirk_start, uint32_t quirk_mask, FmSparseVisit *__restrict__ visits, uint32_t *__restrict__ nvisits,
+                                         uint32_t max_visits, uint32_t *__restrict__ keys, uint32_t *__restrict__ rows)
 {
   const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= bwtsize) return;
   uint32_t row = (uint32_t) i, acc = 0;
   bool ok = true;
   for (uint32_t h = 0; h < hops; h++) {
+    if (quirk_mask && quirk_start != 0u && row == quirk_start - 1u) {
+      const uint32_t slot = atomicAdd(nvisits, 1u);
+      if (slot < max_visits) { visits[slot].origin = (uint32_t) i; visits[slot].hop = h; visits[slot].acc = acc; }
+    }
     const uint32_t s = sym[row];
     if (s == FM_SYM_NONE) { ok = false; break; }
     acc |= s << (kbits * h);
-    if (h + 1 < hops) row = fm_sb96_rank(blocks, nblocks, s, row);
+    if (h + 1 < hops) row = fm_sb96_rank_q(blocks, nblocks, s, row, quirk_start, quirk_mask);
   }
   keys[i] = ok ? acc : nsym;
   rows[i] = (uint32_t) i;
 }
 
+/* Phantom occurrences of an active AltCounters quirk (one thread; a handful of chains).
+ * The quirked rank of symbol s is rank'(s, X) = rank(s, X) + delta_s [X >= Q]: as a counting function it is
+ * "base + #{ m in M_s : m < X }" with M_s = occ(s) plus delta_s extra copies of row Q - 1.  Composing such functions
+ * gives base + #{ elements < X } again, where an element is a chain  row -> s0 -> rank'-image -> s1 -> ...  and a chain
+ * may take, at any hop where it stands on row Q - 1, a phantom copy instead of the row's real symbol.  Chains through
+ * real symbols only are what fm_sparse_compose_kernel emits; this kernel enumerates every chain that takes at least
+ * one phantom copy (depth-first from the recorded visits of row Q - 1) and writes its (key, origin row) pair.
+ * Image of copy c of phantom symbol s at row Q - 1:  rank(s, Q - 1) + [real symbol of the row is s] + c. */
+__global__ void fm_sparse_phantoms_kernel(const uint4 *__restrict__ blocks, uint32_t nblocks, const uint8_t *__restrict__ sym,
+                                          uint32_t kbits, uint32_t hops, uint32_t quirk_start, uint32_t quirk_mask,
+                                          const FmSparseVisit *__restrict__ visits, uint32_t nvisits,
+                                          uint32_t *__restrict__ keys, uint32_t *__restrict__ rows, uint32_t max_out, uint32_t *__restrict__ nout)
+{
+  if (blockIdx.x || threadIdx.x) return;
+  const uint32_t Q1 = quirk_start - 1u, nsym_k = 1u << kbits;
+  struct Item { uint32_t origin, hop, acc, row, from_visit; };
+  Item stack[64];
+  uint32_t out = 0;
+  for (uint32_t v = 0; v < nvisits; v++) {
+    int sp = 0;
+    stack[sp++] = Item{ visits[v].origin, visits[v].hop, visits[v].acc, Q1, 1u };
+    while (sp) {
+      const Item it = stack[--sp];
+      if (it.hop == hops) {                                     /* a complete chain that used a phantom copy */
+        if (out < max_out) { keys[out] = it.acc; rows[out] = it.origin; }
+        out++;
+        continue;
+      }
+      /* the row's real symbol: only for chains that already took a phantom copy (the all-real chain of a recorded
+       * visit is the compose kernel's own output) */
+      if (!it.from_visit) {
+        const uint32_t s = sym[it.row];
+        if (s != FM_SYM_NONE && sp < 63) {
+          const uint32_t nrow = it.hop + 1 < hops ? fm_sb96_rank_q(blocks, nblocks, s, it.row, quirk_start, quirk_mask) : 0u;
+          stack[sp++] = Item{ it.origin, it.hop + 1, it.acc | (s << (kbits * it.hop)), nrow, 0u };
+        }
+      }
+      if (it.row != Q1) continue;
+      /* phantom copies at row Q - 1 */
+      const uint32_t real = sym[Q1];
+      for (uint32_t s = 0; s < nsym_k; s++) {
+        const uint32_t d = (quirk_mask >> (2u * s)) & 3u;
+        for (uint32_t c = 0; c < d && sp < 63; c++) {
+          const uint32_t nrow = fm_sb96_rank(blocks, nblocks, s, Q1) + (real == s ? 1u : 0u) + c;
+          stack[sp++] = Item{ it.origin, it.hop + 1, it.acc | (s << (kbits * it.hop)), nrow, 0u };
+        }
+      }
+    }
+  }
+  *nout = out;
+}
+
 /* symstart[s] = first position of key >= s in the sorted key array, s = 0..nsym (symstart[nsym] = rows carrying a symbol) */
-__global__ void fm_sparse_symstart_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t nsym, uint32_t *__restrict__ symstart)
+__global__ void fm_sparse_symstart_kernel(const uint32_t *__restrict__ keys, uint64_t n, uint32_t nsym, uint32_t *__restrict__ symstart)
 {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s > nsym) return;
-  uint32_t lo = 0, hi = n;
-  while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (keys[mid] < s) lo = mid + 1; else hi = mid; }
-  symstart[s] = lo;
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) { const uint64_t mid = lo + ((hi - lo) >> 1); if (keys[mid] < s) lo = mid + 1; else hi = mid; }
+  symstart[s] = (uint32_t) lo;
 }
 
-/* smallest and largest occurrence count over the symbols: range[0] (preset to 0xFFFFFFFF) and range[1] (preset to 0) */
-__global__ void fm_sparse_count_range_kernel(const uint32_t *__restrict__ symstart, uint32_t nsym, uint32_t *__restrict__ range)
-{
-  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t lo = 0xFFFFFFFFu, hi = 0u;
-  if (s < nsym) lo = hi = symstart[s + 1] - symstart[s];
-  for (int o = 16; o > 0; o >>= 1) {
-    lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
-    hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
-  }
-  if ((threadIdx.x & 31u) == 0) { atomicMin(range, lo); atomicMax(range + 1, hi); }
-}
-
-/* blocks per symbol: ceil(count / lambda), or the same `uniform_nb` for every symbol (uniform grid) */
-__global__ void fm_sparse_nblocks_kernel(const uint32_t *__restrict__ symstart, uint32_t nsym, uint32_t lambda, uint32_t uniform_nb,
-                                         uint32_t *__restrict__ nb)
+/* rank_F(sigma, 0) of every wide symbol: the composed (quirked) rank at X = 0 */
+__global__ void fm_sparse_rank0_kernel(const uint4 *__restrict__ blocks, uint32_t nblocks, uint32_t kbits, uint32_t hops, uint32_t nsym,
+                                       uint32_t quirk_start, uint32_t quirk_mask, uint32_t *__restrict__ rank0)
 {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nsym) return;
-  const uint32_t cnt = symstart[s + 1] - symstart[s];
-  nb[s] = uniform_nb ? uniform_nb : (cnt ? (cnt + lambda - 1) / lambda : 1u);
-}
-
-/* directory entry and rank_F(sigma, 0) of every symbol */
-__global__ void fm_sparse_dir_kernel(const uint4 *__restrict__ blocks, uint32_t nblocks, uint32_t kbits, uint32_t hops, uint32_t nsym,
-                                     uint32_t bwtsize, const uint32_t *__restrict__ nb, const uint32_t *__restrict__ first,
-                                     uint2 *__restrict__ dir, uint32_t *__restrict__ rank0)
-{
-  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nsym) return;
-  /* largest scale with umulhi(bwtsize, scale) <= nb - 1, i.e. bwtsize * scale < nb * 2^32 */
-  unsigned long long sc = ((((unsigned long long) nb[s]) << 32) - 1ull) / bwtsize;
-  if (sc > 0xFFFFFFFFull) sc = 0xFFFFFFFFull;
-  dir[s] = make_uint2(first[s], (uint32_t) sc);
   uint32_t x = 0;
-  for (uint32_t h = 0; h < hops; h++) x = fm_sb96_rank(blocks, nblocks, (s >> (kbits * h)) & ((1u << kbits) - 1u), x);
+  for (uint32_t h = 0; h < hops; h++) x = fm_sb96_rank_q(blocks, nblocks, (s >> (kbits * h)) & ((1u << kbits) - 1u), x, quirk_start, quirk_mask);
   rank0[s] = x;
 }
 
-/* one CTA per symbol, one thread per block of the symbol */
-template <int LANES>
-__global__ void __launch_bounds__(128) fm_sparse_fill_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ symstart,
-                                                             const uint2 *__restrict__ dir, const uint32_t *__restrict__ nb,
-                                                             const uint32_t *__restrict__ rank0, uint4 *__restrict__ sblocks,
-                                                             unsigned long long *__restrict__ novf)
+/* occurrences [t0, t0 + cnt) of the sorted row list that fall in bucket j of symbol s */
+__device__ __forceinline__ void fm_sparse_bucket_range(const uint32_t *__restrict__ rows, uint32_t s0, uint32_t s1, uint32_t scale, uint32_t j,
+                                                       uint32_t &t0, uint32_t &cnt)
 {
-  const uint32_t s = blockIdx.x;
-  const uint32_t s0 = symstart[s], s1 = symstart[s + 1], scale = dir[s].y, first = dir[s].x, n = nb[s], r0 = rank0[s];
-  for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
-    uint32_t lo = s0, hi = s1;                                 /* first occurrence whose bucket is >= j */
-    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__umulhi(rows[mid], scale) < j) lo = mid + 1; else hi = mid; }
-    const uint32_t t0 = lo;
-    hi = s1;                                                   /* first occurrence whose bucket is > j */
-    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__umulhi(rows[mid], scale) <= j) lo = mid + 1; else hi = mid; }
-    const uint32_t cnt = lo - t0;
-    constexpr uint32_t WORDS = 8u * LANES, SLOTS = WORDS - 1u;
-    uint32_t w[WORDS];
-    w[0] = r0 + (t0 - s0);
-    #pragma unroll
-    for (uint32_t c = 1; c < WORDS; c++) w[c] = (c - 1 < cnt && cnt <= SLOTS) ? rows[t0 + c - 1] : FM_SP_PAD;
-    if (cnt > SLOTS) { w[WORDS - 1] = FM_SP_OVF; atomicAdd(novf, 1ull); }
-    uint4 *dst = sblocks + (size_t)(first + j) * (2u * LANES);
-    #pragma unroll
-    for (uint32_t c = 0; c < 2u * LANES; c++) dst[c] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-  }
+  uint32_t lo = s0, hi = s1;                                   /* first occurrence whose bucket is >= j */
+  while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__umulhi(rows[mid], scale) < j) lo = mid + 1; else hi = mid; }
+  t0 = lo;
+  hi = s1;                                                     /* first occurrence whose bucket is > j */
+  while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__umulhi(rows[mid], scale) <= j) lo = mid + 1; else hi = mid; }
+  cnt = lo - t0;
 }
 
-/* the same for a uniform grid with many symbols and few blocks each (14 bases: 2^28 symbols x 2 blocks): one THREAD per block */
+/* shape of the tree over cnt > SLOTS occurrences: N[v] = nodes of level v (0 = leaves), depth D with N[D] = 1 (the root,
+ * which lives in the grid); nodes below the root = sum of N[0 .. D-1] */
+template <int LANES> struct FmSparseTree {
+  static constexpr uint32_t SLOTS = 8u * LANES - 1u, FAN = SLOTS;
+  uint32_t N[FM_SP_MAXDEPTH + 1];
+  uint32_t D;
+  __host__ __device__ explicit FmSparseTree(uint32_t cnt)
+  {
+    N[0] = (cnt + SLOTS - 1) / SLOTS;
+    D = 0;
+    while (N[D] > 1 && D < FM_SP_MAXDEPTH) { N[D + 1] = (N[D] + FAN - 1) / FAN; D++; }
+  }
+  __host__ __device__ uint32_t below_root() const { uint32_t t = 0; for (uint32_t v = 0; v < D; v++) t += N[v]; return t; }
+  /* offset of level v's first node inside the root's extension area (levels stored top-down: D-1 first, leaves last) */
+  __host__ __device__ uint32_t level_offset(uint32_t v) const { uint32_t t = 0; for (uint32_t u = v + 1; u < D; u++) t += N[u]; return t; }
+};
+
+/* pass 1: extension nodes every root needs (0 for a bucket that fits its block); one thread per root */
 template <int LANES>
-__global__ void __launch_bounds__(256) fm_sparse_fill_uniform_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ symstart,
-                                                                     uint32_t nsym, uint32_t nbu, uint32_t scale, const uint32_t *__restrict__ rank0,
-                                                                     uint4 *__restrict__ sblocks, unsigned long long *__restrict__ novf)
+__global__ void __launch_bounds__(256) fm_sparse_count_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ symstart,
+                                                              uint32_t nsym, uint32_t nb, uint32_t scale, uint32_t *__restrict__ ext,
+                                                              unsigned long long *__restrict__ stats)
 {
   const uint64_t g = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= (uint64_t) nsym * nbu) return;
-  const uint32_t s = (uint32_t)(g / nbu), j = (uint32_t)(g - (uint64_t) s * nbu);
-  const uint32_t s0 = symstart[s], s1 = symstart[s + 1], r0 = rank0[s];
-  uint32_t lo = s0, hi = s1;
-  while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__umulhi(rows[mid], scale) < j) lo = mid + 1; else hi = mid; }
-  const uint32_t t0 = lo;
-  hi = s1;
-  while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__umulhi(rows[mid], scale) <= j) lo = mid + 1; else hi = mid; }
-  const uint32_t cnt = lo - t0;
-  constexpr uint32_t WORDS = 8u * LANES, SLOTS = WORDS - 1u;
+  if (g >= (uint64_t) nsym * nb) return;
+  const uint32_t s = (uint32_t)(g / nb), j = (uint32_t)(g - (uint64_t) s * nb);
+  uint32_t t0, cnt;
+  fm_sparse_bucket_range(rows, symstart[s], symstart[s + 1], scale, j, t0, cnt);
+  uint32_t e = 0;
+  if (cnt > FmSparseTree<LANES>::SLOTS) {
+    const FmSparseTree<LANES> t(cnt);
+    e = t.below_root();
+    atomicAdd(stats, 1ull);                                    /* overfull buckets */
+    atomicAdd(stats + 1, (unsigned long long) cnt);            /* occurrences living in them */
+    atomicMax(stats + 2, (unsigned long long) t.D);            /* deepest tree */
+  }
+  ext[g] = e;
+}
+
+/* one node of a tree: level v, index m, over occurrences occ[0 .. cnt) of its root; `area` = first block of the root's
+ * extension area, rank_before = rank_F before occ[0] */
+template <int LANES>
+__device__ __forceinline__ void fm_sparse_write_node(const FmSparseTree<LANES> &t, uint32_t v, uint32_t m, const uint32_t *__restrict__ occ,
+                                                     uint32_t cnt, uint32_t area, uint32_t rank_before, uint4 *__restrict__ dst)
+{
+  constexpr uint32_t WORDS = 8u * LANES, SLOTS = WORDS - 1u, FAN = SLOTS;
   uint32_t w[WORDS];
-  w[0] = r0 + (t0 - s0);
-  #pragma unroll
-  for (uint32_t c = 1; c < WORDS; c++) w[c] = (c - 1 < cnt && cnt <= SLOTS) ? rows[t0 + c - 1] : FM_SP_PAD;
-  if (cnt > SLOTS) { w[WORDS - 1] = FM_SP_OVF; atomicAdd(novf, 1ull); }
-  uint4 *dst = sblocks + (size_t) g * (2u * LANES);
+  if (v == 0) {
+    const uint64_t first = (uint64_t) m * SLOTS;
+    w[0] = rank_before + (uint32_t) first;
+    #pragma unroll
+    for (uint32_t c = 1; c < WORDS; c++) w[c] = (first + c - 1 < cnt) ? occ[first + c - 1] : FM_SP_PAD;
+  } else {
+    uint64_t span = SLOTS;                                     /* occurrences under one child: SLOTS * FAN^(v-1) */
+    for (uint32_t u = 1; u < v; u++) span *= FAN;
+    w[0] = area + t.level_offset(v - 1) + m * FAN;             /* block of child 0 */
+    #pragma unroll
+    for (uint32_t c = 1; c < WORDS - 1; c++) {
+      const uint64_t child = (uint64_t) m * FAN + c, at = child * span;
+      w[c] = (child < t.N[v - 1] && at < cnt) ? occ[at] : FM_SP_PAD;
+    }
+    w[WORDS - 1] = FM_SP_INNER;
+  }
   #pragma unroll
   for (uint32_t c = 0; c < 2u * LANES; c++) dst[c] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
 }
 
-/* rows that live in symbols a uniform grid of nbu blocks per symbol cannot hold (count > slots * nbu): out[0] += count */
-__global__ void fm_sparse_heavy_rows_kernel(const uint32_t *__restrict__ symstart, uint32_t nsym, uint32_t limit, unsigned long long *__restrict__ out)
+/* pass 2a: the grid -- a leaf, or the root of a tree; one thread per root.  extoff = exclusive scan of ext. */
+template <int LANES>
+__global__ void __launch_bounds__(256) fm_sparse_fill_roots_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ symstart,
+                                                                   uint32_t nsym, uint32_t nb, uint32_t scale, const uint32_t *__restrict__ rank0,
+                                                                   const uint32_t *__restrict__ extoff, uint4 *__restrict__ sblocks)
 {
-  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long c = 0;
-  if (s < nsym) { const uint32_t cnt = symstart[s + 1] - symstart[s]; if (cnt > limit) c = cnt; }
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
-  if ((threadIdx.x & 31u) == 0 && c) atomicAdd(out, c);
+  const uint64_t g = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t nroots = (uint64_t) nsym * nb;
+  if (g >= nroots) return;
+  const uint32_t s = (uint32_t)(g / nb), j = (uint32_t)(g - (uint64_t) s * nb);
+  const uint32_t s0 = symstart[s];
+  uint32_t t0, cnt;
+  fm_sparse_bucket_range(rows, s0, symstart[s + 1], scale, j, t0, cnt);
+  const FmSparseTree<LANES> t(cnt);
+  fm_sparse_write_node<LANES>(t, t.D, 0u, rows + t0, cnt, (uint32_t) nroots + extoff[g], rank0[s] + (t0 - s0), sblocks + g * (2u * LANES));
+}
+
+/* pass 2b: the tree nodes below the roots; one thread per node.  The owning root is found by binary search in extoff. */
+template <int LANES>
+__global__ void __launch_bounds__(256) fm_sparse_fill_ext_kernel(const uint32_t *__restrict__ rows, const uint32_t *__restrict__ symstart,
+                                                                 uint32_t nsym, uint32_t nb, uint32_t scale, const uint32_t *__restrict__ rank0,
+                                                                 const uint32_t *__restrict__ extoff, uint32_t total_ext, uint4 *__restrict__ sblocks)
+{
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total_ext) return;
+  const uint64_t nroots = (uint64_t) nsym * nb;
+  uint64_t lo = 0, hi = nroots;                                /* last root with extoff <= e: the owner (roots without extension before it share its offset) */
+  while (hi - lo > 1) { const uint64_t mid = lo + ((hi - lo) >> 1); if (extoff[mid] <= e) lo = mid; else hi = mid; }
+  const uint64_t g = lo;
+  const uint32_t s = (uint32_t)(g / nb), j = (uint32_t)(g - (uint64_t) s * nb);
+  const uint32_t s0 = symstart[s];
+  uint32_t t0, cnt;
+  fm_sparse_bucket_range(rows, s0, symstart[s + 1], scale, j, t0, cnt);
+  const FmSparseTree<LANES> t(cnt);
+  uint32_t local = e - extoff[g], v = t.D;                     /* levels are stored top-down */
+  while (v > 0) { v--; if (local < t.N[v]) break; local -= t.N[v]; }
+  fm_sparse_write_node<LANES>(t, v, local, rows + t0, cnt, (uint32_t) nroots + extoff[g], rank0[s] + (t0 - s0),
+                              sblocks + (nroots + e) * (2u * LANES));
 }
 
 #endif /* FM_SPARSE_CUH_ */

@@ -12,15 +12,14 @@
  * sparse-step table (fm_sparse.cuh)
  * ------------------------------------------------------------------------ */
 static const uint2 *fm_build_lead(fmgpu_index_t *idx, uint32_t b);
-static int32_t fm_sparsify(fmgpu_index_t *idx, uint32_t sparse_bases, uint32_t lambda, uint32_t lanes, bool require_uniform);
 
 extern "C" int32_t fmgpu_index_unsparsify(fmgpu_index_t *idx)
 {
   if (!idx) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null index");
-  if (idx->sblocks || idx->sdir || idx->sstart) {
+  if (idx->sblocks || idx->sstart) {
     CU_TRY(cudaSetDevice(idx->device));
-    cudaFree(idx->sblocks); cudaFree(idx->sdir); cudaFree(idx->sstart);
-    idx->sblocks = NULL; idx->sdir = NULL; idx->sstart = NULL;
+    cudaFree(idx->sblocks); cudaFree(idx->sstart);
+    idx->sblocks = NULL; idx->sstart = NULL;
     for (int b = 0; b < 16; b++) { cudaFree(idx->slead[b]); idx->slead[b] = NULL; }
     idx->slead_tried = 0;
   }
@@ -28,23 +27,40 @@ extern "C" int32_t fmgpu_index_unsparsify(fmgpu_index_t *idx)
   idx->s_uni_nb = 0; idx->s_uni_scale = 0; idx->meta.sparse_uniform_nb = 0;
   idx->meta.sparse_bases = 0; idx->meta.sparse_lambda = 0; idx->meta.sparse_bytes = 0; idx->meta.sparse_blocks = 0;
   idx->meta.sparse_overflow = 0; idx->meta.sparse_start_bases = 0; idx->meta.sparse_lanes = 0;
+  idx->meta.sparse_tree_nodes = 0; idx->meta.sparse_tree_rows = 0; idx->meta.sparse_tree_depth = 0;
+  fm_budget_account(idx);
   return FM_SUCCESS;
+}
+
+template <int LANES>
+static cudaError_t fm_sparse_fill(const uint32_t *rows, const uint32_t *symstart, uint32_t nsym, uint32_t nb, uint32_t scale,
+                                  const uint32_t *rank0, const uint32_t *extoff, uint32_t total_ext, uint4 *sblocks)
+{
+  const uint64_t nroots = (uint64_t) nsym * nb;
+  fm_sparse_fill_roots_kernel<LANES><<<(unsigned)((nroots + 255) / 256), 256>>>(rows, symstart, nsym, nb, scale, rank0, extoff, sblocks);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && total_ext) {
+    fm_sparse_fill_ext_kernel<LANES><<<(total_ext + 255) / 256, 256>>>(rows, symstart, nsym, nb, scale, rank0, extoff, total_ext, sblocks);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+/* Widest step the automatic choice takes: the widest multiple of k up to 14 bases that still leaves lambda rows per wide
+ * symbol on average (the grid then costs ~32*lanes/lambda bytes per text base whatever the width; wider would only add
+ * empty blocks): 14 bases from 1.34 Gbp, 12 from 84 Mbp, 10 from 5.2 Mbp ... at lambda 5. */
+static uint32_t fm_sparse_auto_bases(uint32_t k, uint32_t n, uint32_t lambda)
+{
+  for (uint32_t cand = 14; cand >= 2 * k; cand--)
+    if (cand % k == 0 && (((uint64_t) lambda) << (2 * cand)) <= n) return cand;
+  return 2 * k;
 }
 
 extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_bases, uint32_t lambda, uint32_t lanes)
 {
-  const int32_t rc = fm_sparsify(idx, sparse_bases, lambda, lanes, false);
-  if (idx) fm_budget_account(idx);
-  return rc;
-}
-
-/* require_uniform: the automatic choice is trying a wide (14 / 12 bases) table, which only exists as a uniform grid */
-static int32_t fm_sparsify(fmgpu_index_t *idx, uint32_t sparse_bases, uint32_t lambda, uint32_t lanes, bool require_uniform)
-{
   if (!idx) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null index");
   if (idx->sblocks) return FM_SUCCESS;
-  if (idx->meta.quirk_mask) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "sparse steps are unavailable for an AltCounters index carrying the padding-entry quirk");
-  if (idx->meta.bwtsize >= FM_SP_OVF) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "text too long for the sparse-step table");
+  if (idx->meta.bwtsize >= FM_SP_INNER - 4096u) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "text too long for the sparse-step table");
   CU_TRY(cudaSetDevice(idx->device));
   const uint32_t k = idx->meta.steps, n = idx->meta.bwtsize;
   if (lanes == 0) lanes = 2;
@@ -52,144 +68,132 @@ static int32_t fm_sparsify(fmgpu_index_t *idx, uint32_t sparse_bases, uint32_t l
   const uint32_t slots = 8 * lanes - 1, bbytes = 32 * lanes;
   if (lambda == 0) lambda = lanes == 4 ? 12 : 5;
   if (lambda > slots) return fm_fail_msg(FM_E_BAD_ARGUMENT, "lambda must not exceed the slots of a block (15 or 31)");
-  uint32_t ks = sparse_bases;
-  if (ks == 0) {
-    /* 12 bases per step when that table can be a uniform grid (a directory of 4^12 entries would not stay in L2): tried first,
-     * given up as soon as the symbol counts turn out uneven.  Else the widest multiple of k up to 10 with >= 64 rows per symbol. */
-    const char *env = getenv("FMGPU_SPARSE_UNIFORM");
-    if (!require_uniform && !(env && *env && atoi(env) == 0)) {
-      /* 14 bases need >= lambda rows per 14-mer on average, 12 bases >= 64 rows per 12-mer */
-      const uint32_t wide[2] = { 14, 12 };
-      const uint64_t least[2] = { (uint64_t) lambda << 28, (uint64_t) 64 << 24 };
-      for (int c = 0; c < 2; c++) {
-        if (wide[c] % k || least[c] > n) continue;
-        const int32_t rcw = fm_sparsify(idx, wide[c], lambda, lanes, true);
-        if (rcw == FM_SUCCESS) return FM_SUCCESS;
-      }
-    }
-    for (uint32_t cand = 10; cand >= 2 * k; cand--)
-      if (cand % k == 0 && (((uint64_t) 64) << (2 * cand)) <= n) { ks = cand; break; }
-    if (ks == 0) ks = 2 * k;
-  }
+  const uint32_t ks = sparse_bases ? sparse_bases : fm_sparse_auto_bases(k, n, lambda);
   if (ks % k || ks <= k || ks > 14) return fm_fail_msg(FM_E_BAD_ARGUMENT, "sparse bases must be a multiple of k, larger than k and at most 14");
   const uint32_t nsym = 1u << (2 * ks), hops = ks / k, kbits = 2 * k;
+  const uint32_t qstart = idx->meta.quirk_start, qmask = idx->meta.quirk_mask;
+  /* grid: the same block count for every wide symbol, ~lambda rows per block on average */
+  uint64_t per = ((uint64_t) n + (uint64_t) nsym * lambda - 1) / ((uint64_t) nsym * lambda);
+  if (per < 1) per = 1;
+  const uint64_t nroots = per * nsym;
+  if (nroots >= (1ull << 32) - (1ull << 29)) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "too many blocks for the sparse-step table");
+  const uint32_t nbu = (uint32_t) per;
+  unsigned long long sc = ((((unsigned long long) nbu) << 32) - 1ull) / n;          /* largest scale with umulhi(bwtsize, scale) <= nb - 1 */
+  const uint32_t scale = sc > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t) sc;
+
   const uint64_t nrows = (uint64_t) idx->meta.nblocks * FM_SB_ROWS;
+  const uint64_t nkeys_cap = (uint64_t) n + 4096;                                    /* rows + phantom occurrences */
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = ~(size_t) 0; }
-  const uint64_t est_blocks = (uint64_t) n / lambda + nsym;
-  const uint64_t need = 16ull * n + nrows + est_blocks * bbytes + 32ull * nsym + (1ull << 30);
-  if (need > free_b) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "not enough free device memory to build the sparse-step table");
-  if (!fm_budget_allows(idx, est_blocks * bbytes + 8ull * nsym)) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "the sparse-step table would exceed the derived-table budget");
+  const uint64_t worst_tree = ((uint64_t) n / (slots - 1) + 2) * bbytes;            /* every row in an overfull bucket */
+  const uint64_t build_peak = 16ull * nkeys_cap + nrows + 16ull * nsym + 8ull * nroots + (1ull << 30);
+  const uint64_t final_peak = 4ull * nkeys_cap + 16ull * nsym + 8ull * nroots + nroots * bbytes + (1ull << 30);
+  if ((build_peak > final_peak ? build_peak : final_peak) > free_b)
+    return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "not enough free device memory to build the sparse-step table");
+  if (!fm_budget_allows(idx, nroots * bbytes)) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "the sparse-step table would exceed the derived-table budget");
+  (void) worst_tree;
 
-  uint8_t *sym = NULL; uint32_t *keys = NULL, *rows = NULL, *keys2 = NULL, *rows2 = NULL, *symstart = NULL, *nb = NULL, *first = NULL, *rank0 = NULL;
-  uint2 *dir = NULL; uint4 *sblocks = NULL; void *tmp = NULL; unsigned long long *d_novf = NULL;
+  uint8_t *sym = NULL; uint32_t *keys = NULL, *rows = NULL, *keys2 = NULL, *rows2 = NULL, *symstart = NULL, *rank0 = NULL, *ext = NULL, *extoff = NULL;
+  uint4 *sblocks = NULL; void *tmp = NULL; unsigned long long *d_stats = NULL; FmSparseVisit *visits = NULL; uint32_t *d_cnt = NULL;
   size_t tmp_bytes = 0, tmp2 = 0;
-  uint64_t total_blocks = 0; unsigned long long novf = 0;
+  unsigned long long stats[3] = { 0, 0, 0 };
+  uint32_t hcnt[2] = { 0, 0 }, total_ext = 0;
+  uint64_t nkeys = n;
+  const uint32_t max_visits = 1024, max_ph = 4096;
   cudaError_t e = cudaMalloc((void **) &sym, nrows);
-  if (e == cudaSuccess) e = cudaMalloc((void **) &keys, 4ull * n);
-  if (e == cudaSuccess) e = cudaMalloc((void **) &rows, 4ull * n);
-  if (e == cudaSuccess) e = cudaMalloc((void **) &keys2, 4ull * n);
-  if (e == cudaSuccess) e = cudaMalloc((void **) &rows2, 4ull * n);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &keys, 4ull * nkeys_cap);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &rows, 4ull * nkeys_cap);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &keys2, 4ull * nkeys_cap);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &rows2, 4ull * nkeys_cap);
   if (e == cudaSuccess) e = cudaMalloc((void **) &symstart, 4ull * (nsym + 1));
-  if (e == cudaSuccess) e = cudaMalloc((void **) &nb, 4ull * nsym);
-  if (e == cudaSuccess) e = cudaMalloc((void **) &first, 4ull * nsym);
   if (e == cudaSuccess) e = cudaMalloc((void **) &rank0, 4ull * nsym);
-  if (e == cudaSuccess) e = cudaMalloc((void **) &dir, 8ull * nsym);
-  if (e == cudaSuccess) e = cudaMalloc((void **) &d_novf, 8);
-  if (e == cudaSuccess) e = cudaMemset(d_novf, 0, 8);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &d_stats, 24);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &d_cnt, 8);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &visits, sizeof(FmSparseVisit) * max_visits);
+  if (e == cudaSuccess) e = cudaMemset(d_stats, 0, 24);
+  if (e == cudaSuccess) e = cudaMemset(d_cnt, 0, 8);
+  if (e == cudaSuccess) e = fm_row_symbols(idx, nrows, sym);
   if (e == cudaSuccess) {
-    e = fm_row_symbols(idx, nrows, sym);
-  }
-  if (e == cudaSuccess) {
-    fm_sparse_compose_kernel<<<(unsigned)(((uint64_t) n + 255) / 256), 256>>>(idx->blocks, idx->meta.nblocks, sym, n, kbits, hops, nsym, keys, rows);
+    fm_sparse_compose_kernel<<<(unsigned)(((uint64_t) n + 255) / 256), 256>>>(idx->blocks, idx->meta.nblocks, sym, n, kbits, hops, nsym,
+                                                                              qstart, qmask, visits, d_cnt, max_visits, keys, rows);
     e = cudaGetLastError();
   }
-  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(NULL, tmp_bytes, keys, keys2, rows, rows2, (int64_t) n, 0, (int)(2 * ks + 1));
-  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(NULL, tmp2, nb, first, (int) nsym);
-  if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
-  if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16);
-  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, rows, rows2, (int64_t) n, 0, (int)(2 * ks + 1));
-  if (e == cudaSuccess) {
-    fm_sparse_symstart_kernel<<<(nsym + 1 + 255) / 256, 256>>>(keys2, n, nsym, symstart);
-    e = cudaGetLastError();
-  }
-  /* uniform grid or per-symbol block counts?  $FMGPU_SPARSE_UNIFORM = 0 / 1 forces; default: uniform when no symbol occurs
-   * more than 1.6 x as often as the mean (its blocks then expect <= 8 rows at lambda 5: < 1 % of THOSE symbols' blocks
-   * overflow 15 slots, far cheaper than a directory lookup in every step) nor less than 0.4 x as often (wasted blocks) */
-  uint32_t uni_nb = 0, uni_scale = 0;
-  if (e == cudaSuccess) {
-    uint32_t range[2] = { 0xFFFFFFFFu, 0u }, carrying = 0;
-    uint32_t *d_range = first;                                 /* scratch: `first` is written by the scan below */
-    e = cudaMemcpy(d_range, range, 8, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) { fm_sparse_count_range_kernel<<<(nsym + 255) / 256, 256>>>(symstart, nsym, d_range); e = cudaGetLastError(); }
-    if (e == cudaSuccess) e = cudaMemcpy(range, d_range, 8, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) e = cudaMemcpy(&carrying, symstart + nsym, 4, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) {
-      const double mean = (double) carrying / nsym;
-      const char *env = getenv("FMGPU_SPARSE_UNIFORM");
-      const uint64_t per = ((uint64_t) carrying + (uint64_t) nsym * lambda - 1) / ((uint64_t) nsym * lambda);
-      /* rows living in symbols that cannot fit their share of the grid even if spread perfectly (count > slots x blocks) */
-      unsigned long long heavy = 0, *d_heavy = d_novf;            /* (d_novf is zero here: the fill kernel runs later) */
-      fm_sparse_heavy_rows_kernel<<<(nsym + 255) / 256, 256>>>(symstart, nsym, (uint32_t)(slots * (per ? per : 1)), d_heavy);
+  if (e == cudaSuccess && qmask && qstart != 0u) {
+    /* AltCounters padding quirk: the few phantom occurrences go behind the n real (key, row) pairs, before the sort */
+    e = cudaMemcpy(hcnt, d_cnt, 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && hcnt[0] > max_visits) e = cudaErrorInvalidValue;
+    if (e == cudaSuccess && hcnt[0]) {
+      fm_sparse_phantoms_kernel<<<1, 1>>>(idx->blocks, idx->meta.nblocks, sym, kbits, hops, qstart, qmask, visits, hcnt[0],
+                                          keys + n, rows + n, max_ph, d_cnt + 1);
       e = cudaGetLastError();
-      if (e == cudaSuccess) e = cudaMemcpy(&heavy, d_heavy, 8, cudaMemcpyDeviceToHost);
-      if (e == cudaSuccess) e = cudaMemset(d_heavy, 0, 8);
-      const bool even = mean >= lambda && range[1] <= 1.6 * mean && range[0] >= 0.4 * mean;          /* many rows per symbol: tight counts */
-      const bool sparse_even = mean >= lambda && mean < 64 && heavy * 1000ull <= carrying;           /* few rows per symbol (Poisson scatter): no heavy tail */
-      const bool want = env && *env ? atoi(env) != 0 : (even || sparse_even);
-      if (want && per >= 1 && per * nsym < (1ull << 32)) {
-        uni_nb = (uint32_t) per;
-        unsigned long long sc = ((((unsigned long long) uni_nb) << 32) - 1ull) / n;    /* as fm_sparse_dir_kernel */
-        uni_scale = sc > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t) sc;
-      }
+      if (e == cudaSuccess) e = cudaMemcpy(hcnt + 1, d_cnt + 1, 4, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess && hcnt[1] > max_ph) e = cudaErrorInvalidValue;
+      nkeys = (uint64_t) n + hcnt[1];
     }
   }
-  if (e == cudaSuccess && require_uniform && !uni_nb) {      /* the 12-base attempt of the automatic choice: counts are uneven */
-    cudaFree(sym); cudaFree(keys); cudaFree(rows); cudaFree(keys2); cudaFree(rows2); cudaFree(symstart); cudaFree(nb); cudaFree(first);
-    cudaFree(rank0); cudaFree(tmp); cudaFree(d_novf); cudaFree(dir);
-    return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "symbol counts too uneven for a uniform grid");
+  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(NULL, tmp_bytes, keys, keys2, rows, rows2, (int64_t) nkeys, 0, (int)(2 * ks + 1));
+  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(NULL, tmp2, (uint32_t *) NULL, (uint32_t *) NULL, (int64_t) nroots);
+  if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
+  if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16);
+  /* two-key order (symbol, then row): the sort is stable and the input rows ascend, but phantom pairs sit at the end, so
+   * rows are sorted first when there are any */
+  if (e == cudaSuccess && nkeys > n) {
+    e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, rows, rows2, keys, keys2, (int64_t) nkeys, 0, 32);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys2, keys, rows2, rows, (int64_t) nkeys, 0, (int)(2 * ks + 1));
+    if (e == cudaSuccess) { uint32_t *t = keys; keys = keys2; keys2 = t; t = rows; rows = rows2; rows2 = t; }     /* result in keys2 / rows2 */
+  } else if (e == cudaSuccess) {
+    e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, rows, rows2, (int64_t) nkeys, 0, (int)(2 * ks + 1));
   }
   if (e == cudaSuccess) {
-    fm_sparse_nblocks_kernel<<<(nsym + 255) / 256, 256>>>(symstart, nsym, lambda, uni_nb, nb);
-    e = cudaGetLastError();
-  }
-  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, nb, first, (int) nsym);
-  if (e == cudaSuccess) {
-    uint32_t last_first = 0, last_nb = 0;
-    e = cudaMemcpy(&last_first, first + (nsym - 1), 4, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) e = cudaMemcpy(&last_nb, nb + (nsym - 1), 4, cudaMemcpyDeviceToHost);
-    total_blocks = (uint64_t) last_first + last_nb;
-  }
-  /* the sort's input buffers are dead now: release them before the table is allocated */
-  cudaFree(keys); keys = NULL; cudaFree(rows); rows = NULL; cudaFree(sym); sym = NULL;
-  if (e == cudaSuccess && total_blocks >= (1ull << 32)) e = cudaErrorInvalidValue;
-  if (e == cudaSuccess) e = cudaMalloc((void **) &sblocks, total_blocks * bbytes);
-  if (e == cudaSuccess) {
-    fm_sparse_dir_kernel<<<(nsym + 255) / 256, 256>>>(idx->blocks, idx->meta.nblocks, kbits, hops, nsym, n, nb, first, dir, rank0);
+    fm_sparse_symstart_kernel<<<(nsym + 1 + 255) / 256, 256>>>(keys2, nkeys, nsym, symstart);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) {
-    if (uni_nb && uni_nb < 32) {                               /* many symbols, few blocks each: one thread per block */
-      const unsigned grid = (unsigned)((total_blocks + 255) / 256);
-      if (lanes == 4) fm_sparse_fill_uniform_kernel<4><<<grid, 256>>>(rows2, symstart, nsym, uni_nb, uni_scale, rank0, sblocks, d_novf);
-      else            fm_sparse_fill_uniform_kernel<2><<<grid, 256>>>(rows2, symstart, nsym, uni_nb, uni_scale, rank0, sblocks, d_novf);
-    } else if (lanes == 4) fm_sparse_fill_kernel<4><<<nsym, 128>>>(rows2, symstart, dir, nb, rank0, sblocks, d_novf);
-    else                   fm_sparse_fill_kernel<2><<<nsym, 128>>>(rows2, symstart, dir, nb, rank0, sblocks, d_novf);
+    fm_sparse_rank0_kernel<<<(nsym + 255) / 256, 256>>>(idx->blocks, idx->meta.nblocks, kbits, hops, nsym, qstart, qmask, rank0);
     e = cudaGetLastError();
   }
-  if (e == cudaSuccess) e = cudaMemcpy(&novf, d_novf, 8, cudaMemcpyDeviceToHost);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
-  cudaFree(sym); cudaFree(keys); cudaFree(rows); cudaFree(keys2); cudaFree(rows2); cudaFree(symstart); cudaFree(nb); cudaFree(first);
-  cudaFree(rank0); cudaFree(tmp); cudaFree(d_novf);
+  /* the sort's other buffers are dead now: release them before the per-root arrays and the table are allocated */
+  cudaFree(keys); keys = NULL; cudaFree(rows); rows = NULL; cudaFree(sym); sym = NULL; cudaFree(keys2); keys2 = NULL;
+  if (e == cudaSuccess) e = cudaMalloc((void **) &ext, 4ull * nroots);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &extoff, 4ull * nroots);
+  if (e == cudaSuccess) {
+    const unsigned grid = (unsigned)((nroots + 255) / 256);
+    if (lanes == 4) fm_sparse_count_kernel<4><<<grid, 256>>>(rows2, symstart, nsym, nbu, scale, ext, d_stats);
+    else            fm_sparse_count_kernel<2><<<grid, 256>>>(rows2, symstart, nsym, nbu, scale, ext, d_stats);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, ext, extoff, (int64_t) nroots);
+  if (e == cudaSuccess) {
+    uint32_t last_off = 0, last_ext = 0;
+    e = cudaMemcpy(&last_off, extoff + (nroots - 1), 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(&last_ext, ext + (nroots - 1), 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(stats, d_stats, 24, cudaMemcpyDeviceToHost);
+    total_ext = last_off + last_ext;                             /* <= n / (slots - 1) + roots: far below 2^32 */
+  }
+  cudaFree(ext); ext = NULL;
+  const uint64_t total_blocks = nroots + total_ext;
+  if (e == cudaSuccess && total_blocks >= 0xFFFFFFF0ull) e = cudaErrorInvalidValue;
+  if (e == cudaSuccess && !fm_budget_allows(idx, total_blocks * bbytes)) {
+    cudaFree(rows2); cudaFree(symstart); cudaFree(rank0); cudaFree(extoff); cudaFree(tmp); cudaFree(d_stats); cudaFree(d_cnt); cudaFree(visits);
+    return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "the sparse-step table would exceed the derived-table budget");
+  }
+  if (e == cudaSuccess) e = cudaMalloc((void **) &sblocks, total_blocks * bbytes);
+  if (e == cudaSuccess) e = lanes == 4 ? fm_sparse_fill<4>(rows2, symstart, nsym, nbu, scale, rank0, extoff, total_ext, sblocks)
+                                       : fm_sparse_fill<2>(rows2, symstart, nsym, nbu, scale, rank0, extoff, total_ext, sblocks);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaFree(sym); cudaFree(keys); cudaFree(rows); cudaFree(keys2); cudaFree(rows2); cudaFree(symstart); cudaFree(rank0); cudaFree(ext); cudaFree(extoff);
+  cudaFree(tmp); cudaFree(d_stats); cudaFree(d_cnt); cudaFree(visits);
   if (e != cudaSuccess) {
-    cudaFree(sblocks); cudaFree(dir);
+    cudaFree(sblocks);
     cudaGetLastError();                                          /* a failed cudaMalloc stays "last error" otherwise and fails the next attempt's first check */
     if (e == cudaErrorMemoryAllocation) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "not enough device memory for the sparse-step table (the plain kernels still serve this index)");
     return fm_fail(e, "fmgpu_index_sparsify", __FILE__, __LINE__);
   }
-  idx->sblocks = sblocks; idx->sdir = dir; idx->s_uni_nb = uni_nb; idx->s_uni_scale = uni_scale; idx->meta.sparse_uniform_nb = uni_nb;
+  idx->sblocks = sblocks; idx->s_uni_nb = nbu; idx->s_uni_scale = scale; idx->meta.sparse_uniform_nb = nbu;
   idx->meta.sparse_bases = ks; idx->meta.sparse_lambda = lambda; idx->meta.sparse_blocks = total_blocks;
-  idx->meta.sparse_overflow = novf; idx->meta.sparse_bytes = total_blocks * bbytes + 8ull * nsym; idx->meta.sparse_lanes = lanes;
+  idx->meta.sparse_overflow = stats[0]; idx->meta.sparse_bytes = total_blocks * bbytes; idx->meta.sparse_lanes = lanes;
+  idx->meta.sparse_tree_nodes = total_ext; idx->meta.sparse_tree_rows = stats[1]; idx->meta.sparse_tree_depth = (uint32_t) stats[2];
 
   /* start table: the sparse kernel itself searches every SB-mer once (a packed SB-mer IS its key); SB = the
    * largest whole number of sparse steps within 12 bases */
@@ -198,23 +202,24 @@ static int32_t fm_sparsify(fmgpu_index_t *idx, uint32_t sparse_bases, uint32_t l
     const bool want = env && *env ? atoi(env) != 0 : idx->meta.nbytes >= (1ull << 30);
     const uint32_t ssteps = 12 / ks, sb = ssteps * ks;
     if (want && ssteps && ((uint64_t) 1 << (2 * sb)) < n) {
-      const uint32_t nkeys = 1u << (2 * sb);
+      const uint32_t nk = 1u << (2 * sb);
       uint32_t *skeys = NULL; uint2 *table = NULL;
-      e = cudaMalloc((void **) &skeys, (size_t) nkeys * 4);
-      if (e == cudaSuccess) e = cudaMalloc((void **) &table, (size_t) nkeys * 8);
-      if (e == cudaSuccess) { fm_iota_kernel<<<(nkeys + 255) / 256, 256>>>(skeys, nkeys); e = cudaGetLastError(); }
+      e = cudaMalloc((void **) &skeys, (size_t) nk * 4);
+      if (e == cudaSuccess) e = cudaMalloc((void **) &table, (size_t) nk * 8);
+      if (e == cudaSuccess) { fm_iota_kernel<<<(nk + 255) / 256, 256>>>(skeys, nk); e = cudaGetLastError(); }
       int32_t rc = FM_SUCCESS;
-      if (e == cudaSuccess) rc = fm_launch_sparse(idx, skeys, nkeys, sb, (uint32_t *) table, FM_DEFAULT_VARIANT, 0, NULL, false);
+      if (e == cudaSuccess) rc = fm_launch_sparse(idx, skeys, nk, sb, (uint32_t *) table, FM_DEFAULT_VARIANT, 0, NULL, false);
       if (e == cudaSuccess && rc == FM_SUCCESS) e = cudaDeviceSynchronize();
       cudaFree(skeys);
       if (e != cudaSuccess || rc != FM_SUCCESS) { cudaFree(table); cudaGetLastError(); }   /* the table is optional */
-      else { idx->sstart = table; idx->meta.sparse_start_bases = sb; idx->meta.sparse_bytes += (uint64_t) nkeys * 8; }
+      else { idx->sstart = table; idx->meta.sparse_start_bases = sb; idx->meta.sparse_bytes += (uint64_t) nk * 8; }
     }
-    /* lead tables (fm_ensure_lead): the small ones now, the wide ones (12 .. 15 bases, up to 8.6 GB) when a read length asks */
+    /* lead tables (fm_build_lead): the small ones now, the wide ones (12 .. 15 bases, up to 8.6 GB) when fmgpu_index_prepare asks */
     idx->stables = want ? 1 : 0;
     if (want)
       for (uint32_t b = 1; b <= ks + 1 && b < 12; b++) fm_build_lead(idx, b);
   }
+  fm_budget_account(idx);
   return FM_SUCCESS;
 }
 
@@ -307,10 +312,10 @@ int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_packed, uin
                          uint32_t *d_results, fmgpu_variant_t v, cudaStream_t stream, unsigned long long *d_counters, bool use_lead_tables)
 {
   if (!idx->sblocks) return fm_fail_msg(FM_E_BAD_ARGUMENT, "FMGPU_MODE_SPARSE needs fmgpu_index_sparsify() on this replica first");
-  const uint32_t k = idx->meta.steps, ks = idx->meta.sparse_bases, hops = ks / k, lanes = idx->meta.sparse_lanes;
+  const uint32_t k = idx->meta.steps, ks = idx->meta.sparse_bases, lanes = idx->meta.sparse_lanes;
   if (v.queries_per_thread < 1 || v.queries_per_thread > 4) v.queries_per_thread = 4;
   FmSparseParams p;
-  p.sblocks = idx->sblocks; p.dir = idx->sdir; p.blocks = idx->blocks; p.packed = d_packed; p.results = d_results;
+  p.sblocks = idx->sblocks; p.blocks = idx->blocks; p.packed = d_packed; p.results = d_results;
   p.nblocks = idx->meta.nblocks; p.nq = (uint32_t) nq;
   /* plan (fm_sparse_plan_for); only tables that exist are used -- fmgpu_index_prepare builds the ones a length wants */
   const fm_sparse_plan pl = fm_sparse_plan_for(idx, len);
@@ -323,8 +328,9 @@ int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_packed, uin
   else if (m && S >= m) { p.start = idx->sstart; p.start_bits = 2 * ks * m; p.nsteps = S - m; p.nback = rem; }
   else p.nfront = rem;
   p.wpq = fmgpu_words_per_query(len); p.bwtsize = idx->meta.bwtsize;
-  p.sbits = 2 * ks; p.hops = hops;
-  p.uni_nb = idx->s_uni_nb; p.uni_scale = idx->s_uni_scale;
+  p.sbits = 2 * ks;
+  p.nb = idx->s_uni_nb; p.scale = idx->s_uni_scale; p.nroots = idx->s_uni_nb << (2 * ks);
+  p.quirk_start = idx->meta.quirk_start; p.quirk_mask = idx->meta.quirk_mask;
   p.fetch_counters = d_counters;
   p.has_tail = lead ? 0u : len % k;                            /* a lead table already holds the odd base */
   p.tail_row = idx->meta.tail_row; p.tail_base = idx->meta.tail_base;

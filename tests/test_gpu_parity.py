@@ -646,7 +646,8 @@ def test_fuzz_tiny_references(pkg, tmp_path, case):
             if tag != 100:
                 mine.free()
             idx = pkg.DeviceIndex.from_image(image)
-            modes = [pkg.MODE_TASK, pkg.MODE_COOP]
+            modes = [pkg.MODE_TASK, pkg.MODE_COOP, pkg.MODE_SPARSE]
+            idx.sparsify(2 * k * (1 + case % 3), 0, 2 + 2 * (case % 2))  # sparse-step table (quirk files included: phantom occurrences)
             if idx.meta.quirk_mask == 0:
                 idx.fuse(4, 2)
                 modes.append(pkg.MODE_FUSED)

@@ -1,5 +1,5 @@
-"""GPU parity tests of the sparse-step layout (csrc/fm_sparse.cuh): up to 12 bases per block fetch, blocks of
-occurrence rows + a per-symbol directory, overfull blocks served by ordinary steps on the SB96 table.  Everything
+"""GPU parity tests of the sparse-step layout (csrc/fm_sparse.cuh): up to 14 bases per block fetch, a uniform grid of
+blocks of occurrence rows, overfull buckets as search trees of blocks, one state machine per read.  Everything
 goes through the C ABI (ctypes) and is compared bit for bit with committed reference outputs, the oracle, the
 reference searcher itself, or the plain kernels on the same index at sizes the CPU cannot reach.   pytest -m gpu"""
 import ctypes as C
@@ -27,29 +27,28 @@ def widths(k):
     return [2, 3, 5, 6, 10, 12] if k == 1 else [4, 6, 10, 12]          # (14 bases: test_sparse_steps_read_lengths and the full-size test)
 
 
-@pytest.mark.parametrize("uniform", ["0", "1"], ids=["directory", "uniform_grid"])
-@pytest.mark.parametrize("path", [p for p in GOLDEN if "quirk" not in p], ids=lambda p: os.path.basename(p))
-def test_sparse_steps_golden_all_widths(pkg, monkeypatch, path, uniform):
-    """Committed outputs of the unmodified reference searchers; every width, both block sizes, every qpt,
-    lambda from 1 (almost no overflow) to the slot count (many overfull blocks -> SB96 fallback); per-symbol block
-    counts with a directory, and the uniform grid (same block count for every symbol, no directory lookup)."""
-    monkeypatch.setenv("FMGPU_SPARSE_UNIFORM", uniform)
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p))
+def test_sparse_steps_golden_all_widths(pkg, path):
+    """Committed outputs of the unmodified reference searchers, the AltCounters quirk fixtures included (phantom
+    occurrences); every width, both block sizes, every qpt, lambda from 1 (big grid, no trees) to the slot count (many
+    overfull buckets -> search trees)."""
     g = np.load(path)
     reads, length, k = g["reads"], int(g["length"]), int(g["k"])
     nq = reads.size // length
+    quirk = "quirk" in os.path.basename(path)
     b = pkg.DeviceBatch(0, nq, length, k)
     b.upload_ascii(reads)
     for tag, key in ((100, "expected_std"), (101, "expected_std"), (200, "expected_ac"), (201, "expected_ac")):
-        for ks in widths(k):
+        for ks in ([w for w in widths(k) if w <= 10] if quirk else widths(k)):
             for lanes, lams in ((2, (1, 5, 15)), (4, (12, 31))):
                 for lam in lams:
                     idx = pkg.DeviceIndex.from_image(g[f"image_{tag}"]).sparsify(ks, lam, lanes)
                     m = idx.meta
                     assert (m.sparse_bases, m.sparse_lambda, m.sparse_lanes) == (ks, lam, lanes)
-                    assert (m.sparse_uniform_nb > 0) == (uniform == "1")
-                    if m.sparse_uniform_nb:
-                        assert m.sparse_blocks == m.sparse_uniform_nb * 4 ** ks
-                    assert m.sparse_bytes == m.sparse_blocks * 32 * lanes + 8 * 4 ** ks + (8 * 4 ** m.sparse_start_bases if m.sparse_start_bases else 0)
+                    assert m.sparse_uniform_nb >= 1 and m.sparse_blocks == m.sparse_uniform_nb * 4 ** ks + m.sparse_tree_nodes
+                    assert (m.sparse_overflow > 0) == (m.sparse_tree_nodes > 0) == (m.sparse_tree_depth > 0)
+                    assert m.sparse_bytes == m.sparse_blocks * 32 * lanes + (8 * 4 ** m.sparse_start_bases if m.sparse_start_bases else 0)
+                    assert m.derived_bytes >= m.sparse_bytes
                     for qpt in (1, 2, 3, 4):
                         b.search(idx, pkg.variant(pkg.MODE_SPARSE, qpt))
                         assert np.array_equal(b.download(), g[key]), f"tag {tag} ks {ks} lanes {lanes} lambda {lam} qpt {qpt}"
@@ -87,10 +86,7 @@ def test_sparse_steps_read_lengths(pkg, k, length):
 
 def test_sparse_unavailable_and_errors(pkg):
     g = np.load(os.path.join(helpers.ROOT, "tests", "golden", "quirk_k2_n124.npz"))
-    idx = pkg.DeviceIndex.from_image(g["image_200"])           # AltCounters padding quirk: not representable
-    with pytest.raises(pkg.FMError) as ei:
-        idx.sparsify()
-    assert ei.value.code == 19
+    idx = pkg.DeviceIndex.from_image(g["image_200"])           # (AltCounters padding quirk: served since round 2)
     b = pkg.DeviceBatch(0, 4, 8, 2)
     b.upload_ascii(g["reads"][:32])
     with pytest.raises(pkg.FMError) as ei:
@@ -116,15 +112,10 @@ def test_sparse_unavailable_and_errors(pkg):
 @pytest.mark.skipif(not helpers.has_ref_tools(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("name", ["polyA", "ACGT_period4", "two_letter", "repeat_x40", "random_plus_repeat"])
 @pytest.mark.parametrize("k", [1, 2])
-@pytest.mark.parametrize("uniform", ["auto", "1"], ids=["auto", "uniform_grid_forced"])
-def test_sparse_steps_repetitive_texts_overflow_fallback(pkg, tmp_path, monkeypatch, name, k, uniform):
-    """Repeats put hundreds of occurrences of one wide symbol into consecutive BWT rows: those blocks are overfull and
-    the kernel must serve them through ordinary steps on the SB96 table.  Index files and expected (L,R) from the
-    unmodified reference tools."""
-    if uniform == "1":
-        monkeypatch.setenv("FMGPU_SPARSE_UNIFORM", "1")
-    else:
-        monkeypatch.delenv("FMGPU_SPARSE_UNIFORM", raising=False)
+def test_sparse_steps_repetitive_texts_search_trees(pkg, tmp_path, name, k):
+    """Repeats put hundreds of occurrences of one wide symbol into consecutive BWT rows: those buckets are overfull and
+    become search trees of blocks (several levels deep for poly-A), which the kernel walks one fetch per iteration.
+    Index files and expected (L,R) from the unmodified reference tools."""
     rng = np.random.default_rng(11)
     n = 30011
     unit = ACGT[rng.integers(0, 4, 700)]
@@ -146,19 +137,21 @@ def test_sparse_steps_repetitive_texts_overflow_fallback(pkg, tmp_path, monkeypa
     idx = pkg.DeviceIndex.from_image(image)
     b = pkg.DeviceBatch(0, reads.size // length, length, k)
     b.upload_ascii(reads)
-    saw_overflow = False
+    saw_overflow, deepest = False, 0
     for ks in ([5, 10] if k == 1 else [4, 10]):
         for lanes in (2, 4):
             idx.sparsify(ks, 0, lanes)
-            saw_overflow |= idx.meta.sparse_overflow > 0
-            if uniform == "auto":                                  # skewed symbol counts: never a uniform grid by default
-                assert idx.meta.sparse_uniform_nb == 0, name
+            m = idx.meta
+            saw_overflow |= m.sparse_overflow > 0
+            deepest = max(deepest, m.sparse_tree_depth)
+            assert m.sparse_tree_rows <= m.bwtsize and (m.sparse_tree_nodes > 0) == (m.sparse_overflow > 0)
             for qpt in (1, 4):
                 b.search(idx, pkg.variant(pkg.MODE_SPARSE, qpt))
                 assert np.array_equal(b.download(), want), f"{name} k={k} ks={ks} lanes={lanes} qpt={qpt}"
             idx.unsparsify()
-    # (polyA is one symbol spread evenly over all rows, and the two-letter text is random: no overfull blocks there)
-    assert saw_overflow or name in ("polyA", "two_letter"), "these texts are meant to overflow blocks"
+    assert saw_overflow or name == "two_letter", "these texts are meant to overflow buckets"
+    if name == "polyA":
+        assert deepest >= 2                                      # 30 000 occurrences of one symbol: 15 * 15 * 15 < 30 000
     b.free(); idx.free()
 
 
@@ -211,41 +204,80 @@ def test_sparse_start_table_and_fetch_counter(pkg, k):
                                                           C.byref(a), C.byref(s), C.byref(o)), "count")
             assert np.array_equal(d_res.cpu().numpy().view(np.uint32), want)
             assert 9 * nq <= a.value <= 9.05 * nq                # 10-base start table + 9 sparse steps, L and R in one bucket
-            assert s.value <= 0.2 * nq and o.value <= 0.05 * nq  # overfull blocks are rare on a random text
+            assert s.value == 0 and o.value <= 0.05 * nq         # no SB96 steps at this length; overfull buckets (tree fetches) are rare on a random text
     idx.free()
 
 
-def test_sparse_uniform_grid_is_chosen_for_even_symbol_counts_only(pkg, monkeypatch):
-    """Default choice of the layout: a uniform grid (no directory lookups) when no wide symbol occurs more than 1.6 x as
-    often as the mean (nor less than half) -- a uniformly random text with many rows per symbol -- and per-symbol block
-    counts otherwise.  Same (L,R)."""
-    monkeypatch.delenv("FMGPU_SPARSE_UNIFORM", raising=False)
-    n = 4_000_000
-    build = pkg.IndexBuild.from_synth(n, 1, 2, 64)
-    idx = build.to_index()
-    build.free()
-    reads = np.concatenate([ACGT[np.random.default_rng(3).integers(0, 4, 40_000 * 50)]])
+def test_sparse_automatic_width_follows_the_text_length(pkg):
+    """Default width: the widest multiple of k (up to 14 bases) that leaves lambda rows per wide symbol on average, so the
+    grid costs ~12.8 bytes per base whatever the text length -- and whatever the text: there is no "uneven counts" case
+    any more.  Same (L,R) as the plain kernel."""
     import torch
-    d_ascii = torch.empty(60_000 * 50, dtype=torch.uint8, device="cuda")
-    pkg.check(pkg.lib().fmgpu_synth_reads_device(0, n, 1, 60_000, 50, 2, 0, d_ascii.data_ptr(), None), "reads")
-    torch.cuda.synchronize()
-    reads = np.concatenate([d_ascii.cpu().numpy(), reads])
-    b = pkg.DeviceBatch(0, reads.size // 50, 50, 2)
-    b.upload_ascii(reads)
-    b.search(idx, pkg.variant(pkg.MODE_COOP))
-    want = b.download()
-    assert (want[1:120_000:2] > want[0:120_000:2]).all()         # the exact reads are found
-    for ks, expect_uniform in ((6, True), (10, False)):          # 977 rows per 6-mer (+-3 %), 3.8 per 10-mer (+-50 %)
-        idx.sparsify(ks, 0, 0)
+    for n, k, expect in ((4_000_000, 2, 8), (4_000_000, 1, 9), (90_000_000, 2, 12), (30_000, 2, 6)):
+        build = pkg.IndexBuild.from_synth(n, 1, k, 64)
+        idx = build.to_index()
+        build.free()
+        d_ascii = torch.empty(60_000 * 50, dtype=torch.uint8, device="cuda")
+        pkg.check(pkg.lib().fmgpu_synth_reads_device(0, n, 1, 60_000, 50, 2, 0, d_ascii.data_ptr(), None), "reads")
+        torch.cuda.synchronize()
+        reads = np.concatenate([d_ascii.cpu().numpy(), ACGT[np.random.default_rng(3).integers(0, 4, 40_000 * 50)]])
+        b = pkg.DeviceBatch(0, reads.size // 50, 50, k)
+        b.upload_ascii(reads)
+        b.search(idx, pkg.variant(pkg.MODE_COOP))
+        want = b.download()
+        assert (want[1:120_000:2] > want[0:120_000:2]).all()     # the exact reads are found
+        idx.sparsify()
         m = idx.meta
-        assert (m.sparse_uniform_nb > 0) == expect_uniform, (ks, m.sparse_uniform_nb)
-        if expect_uniform:
-            assert m.sparse_blocks == m.sparse_uniform_nb * 4 ** ks and m.sparse_overflow < m.sparse_blocks // 1000
+        assert m.sparse_bases == expect, (n, k, m.sparse_bases)
+        assert m.sparse_bytes < 26 * n + (1 << 20), "grid + trees: 12.8 .. 25.6 bytes per base on a random text (blocks per symbol round up)"
+        assert m.sparse_tree_rows < n // 100
         for qpt in (1, 4):
             b.search(idx, pkg.variant(pkg.MODE_SPARSE, qpt))
-            assert np.array_equal(b.download(), want), (ks, qpt)
-        idx.unsparsify()
-    b.free(); idx.free()
+            assert np.array_equal(b.download(), want), (n, k, qpt)
+        b.free(); idx.free()
+
+
+@pytest.mark.skipif(not helpers.has_ref_tools(), reason="oracle/_ref not built")
+def test_sparse_quirk_fuzz_against_the_altcounters_reference(pkg, tmp_path):
+    """AltCounters files whose padding-entry quirk is ACTIVE (a '$' row in the last chunk whose counter
+    lives in the padding entry) on the sparse-step path: the composed rank function then has phantom occurrences, which
+    the table stores as repeated list entries.  Tiny references make the quirk frequent; the checker is the reference's
+    own AltCounters searcher, which has the quirk by construction."""
+    rng = np.random.default_rng(77)
+    active = 0
+    for case in range(48):
+        k = 1 + case % 2
+        d = (32, 64)[(case // 2) % 2]
+        n = int(rng.integers(d + 2, 5 * d))
+        if (n + 1) % d == 0:
+            n += 1
+        alphabet = (b"ACGT", b"AC", b"AAAAAACGT")[(case // 4) % 3]
+        text = np.frombuffer(alphabet, dtype=np.uint8)[rng.integers(0, len(alphabet), n)]
+        paths = helpers.build_reference_indexes(str(tmp_path / f"c{case}"), text, k, d)
+        ref = helpers.RefSearcher(k, d, True)
+        for length in (2 * k, 4 * k, 6 * k, 12, 18):
+            starts = rng.integers(0, n - length + 1, 200)
+            reads = np.concatenate([text[s:s + length] for s in starts] + [text[:length], text[-length:],
+                                   np.frombuffer(alphabet, dtype=np.uint8)[rng.integers(0, len(alphabet), 150 * length)]])
+            want, _ = ref.search(ref.load(paths[200]), reads, length)
+            batch = pkg.DeviceBatch(0, reads.size // length, length, k)
+            batch.upload_ascii(reads)
+            for tag in (200, 201):
+                idx = pkg.DeviceIndex.from_image(np.fromfile(paths[tag], dtype=np.uint32))
+                if idx.meta.quirk_mask == 0:
+                    idx.free()
+                    continue
+                active += 1
+                for ks in ((2, 3, 4, 6) if k == 1 else (4, 6, 8)):
+                    for lanes, lam in ((2, 0), (2, 1), (4, 0)):
+                        idx.sparsify(ks, lam, lanes)
+                        for qpt in (1, 4):
+                            batch.search(idx, pkg.variant(pkg.MODE_SPARSE, qpt))
+                            assert np.array_equal(batch.download(), want), f"case {case}: k={k} d={d} n={n} len={length} tag={tag} ks={ks} lanes={lanes} lam={lam}"
+                        idx.unsparsify()
+                idx.free()
+            batch.free()
+    assert active >= 20, f"only {active} (case, length, tag) combinations had an active quirk: the fuzz does not exercise it"
 
 
 def test_sparse_config3_full_size_against_reference_checksums(pkg):
@@ -273,13 +305,13 @@ def test_sparse_config3_full_size_against_reference_checksums(pkg):
             batch.search(idx, pkg.variant(pkg.MODE_SPARSE, qpt))
             assert helpers.results_text_md5(batch.download()) == gold["md5"][key], f"tag {tag} qpt {qpt}"
         idx.unsparsify()
-        idx.sparsify(12, 0, 0)                                   # 12 bases: uniform grid too on this text
+        idx.sparsify(12, 0, 0)
         m = idx.meta
         assert (m.sparse_bases, m.sparse_start_bases) == (12, 12) and m.sparse_uniform_nb > 0
         batch.search(idx, pkg.variant(pkg.MODE_SPARSE, 4))
         assert helpers.results_text_md5(batch.download()) == gold["md5"][key], f"tag {tag} 12 bases"
         idx.unsparsify()
-        idx.sparsify(10, 0, 0)                                   # and the 10-base table (what uneven symbol counts get, with a directory then)
+        idx.sparsify(10, 0, 0)                                   # and the 10-base table
         m = idx.meta
         assert (m.sparse_bases, m.sparse_lanes, m.sparse_start_bases) == (10, 2, 10) and m.sparse_bytes < 30e9
         batch.search(idx, pkg.variant(pkg.MODE_SPARSE, 4))
@@ -323,7 +355,7 @@ def test_sparse_dropin_flow_env_modes(pkg, tmp_path):
 
 def test_dropin_auto_mode_picks_table_by_text(pkg, tmp_path, capfd):
     """transferCPUtoGPU in auto mode on indexes larger than L2: sparse-step table for a random text, fused-step table
-    when the sparse blocks of a repeat-rich text overflow (profiles/r01_repeat_text.md); same (L,R) as the plain kernel."""
+    when a large part of a repeat-rich text lives in search trees (profiles/r02_skewed_text.md); same (L,R) as the plain kernel."""
     rng = np.random.default_rng(23)
     n, length, nq = 48_000_001, 60, 20_000
     for kind in ("random", "repeats"):
