@@ -263,6 +263,28 @@ def queriesFromArray(ascii_bases, size):
     return q
 
 
+def index_from_image(image_u32):
+    """fmi_t (what loadIndex returns) around the words of an index FILE held in a numpy uint32 array: no file involved.
+    The array and the '$' tables are kept alive by the returned structure; pass C.byref(fmi) where a void* index goes."""
+    im = np.ascontiguousarray(image_u32, dtype=np.uint32)
+    tag, k, bwtsize, ncnt, nent, d = (int(v) for v in im[:6])
+    f = fmi_t()
+    f.tag, f.steps, f.bwtsize, f.ncounters, f.nentries, f.chunk = tag, k, bwtsize, ncnt, nent, d
+    f.nbitmaps = 2 * (d // 32)
+    f.entry_words = f.nbitmaps * k + ncnt
+    if im.size != 6 + 2 * k + nent * f.entry_words:
+        raise FMError(FM_E_READING_FMI, "index_from_image (image size does not match its header)")
+    f._dpos = (C.c_uint32 * k)(*[int(v) for v in im[6:6 + k]])
+    f._dbase = (C.c_uint32 * k)(*[int(v) for v in im[6 + k:6 + 2 * k]])
+    f._dmod = (C.c_uint32 * k)(*[int(v) // d for v in im[6:6 + k]])
+    f.h_dollarPositionBWT = C.cast(f._dpos, C.POINTER(C.c_uint32))
+    f.h_dollarBaseBWT = C.cast(f._dbase, C.POINTER(C.c_uint32))
+    f.h_modposdollarBWT = C.cast(f._dmod, C.POINTER(C.c_uint32))
+    f._keep = im
+    f.h_index = im[6 + 2 * k:].ctypes.data
+    return f
+
+
 def initResults(num):
     h = C.c_void_p()
     check(lib().initResults(num, C.byref(h)), "initResults")

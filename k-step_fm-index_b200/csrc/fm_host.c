@@ -433,14 +433,9 @@ int32_t transferCPUtoGPU(void *index, void *queries, void *results)
       for (g = 0; g < rs->ndev && (want_sparse || want_fused); g++) {
         t0 = fm_wall();
         err = want_sparse ? fmgpu_index_sparsify(rs->replica[g], 0, 0, 0) : FM_E_NOT_IMPLEMENTED;
-        if (!err && mode == FM_MODE_AUTO && fmgpu_index_get_meta(rs->replica[g], &meta0) == FM_SUCCESS &&
-            meta0.sparse_tree_rows * 4ull > meta0.bwtsize) {
-          /* repeat-rich text: more than a quarter of the rows live in search trees, i.e. in wide symbols that occur
-           * dozens to thousands of times; reads from those repeats keep a WIDE interval, whose two ends walk separate
-           * tree paths in every step (profiles/r02_skewed_text.md) -- the fused-step table's bitmaps are addressed by
-           * row and do not care, so it wins there whenever it fits */
-          if (fmgpu_index_fuse(rs->replica[g], 0, 0, 0) == FM_SUCCESS) fmgpu_index_unsparsify(rs->replica[g]);
-        }
+        /* (round 1 switched repeat-rich texts to the fused-step table here; with search trees and per-read state machines
+         * the sparse-step table wins on those too -- profiles/r02_skewed_text.md: 2 730 vs 1 689 and 4 034 vs 2 030 M reads/s
+         * -- so the fused table is only the fallback when the sparse one cannot be built) */
         if (err == FM_E_NOT_IMPLEMENTED && (want_fused || mode == FM_MODE_AUTO)) err = fmgpu_index_fuse(rs->replica[g], 0, 0, 0);
         g_stats.table_build_s[g] = fm_wall() - t0;
         if (err && err != FM_E_NOT_IMPLEMENTED) { for (g = 0; g < rs->ndev; g++) fmgpu_index_free(&rs->replica[g]); free(rs); return err; }

@@ -261,6 +261,127 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_kernel(const F
 }
 
 /* ------------------------------------------------------------------------ *
+ * The same search with DYNAMIC read assignment, for plans that consist of sparse steps only (start / lead table or
+ * nothing in front, no SB96 steps, no odd tail -- fm_launch_sparse picks it then): the CTA stages ROUNDS x as many
+ * reads as it has slots, and a slot (one of QPT per lane group) that finishes a read pulls the next one from a
+ * shared-memory counter.  On a skewed text reads need 7 to 40 fetches; with static assignment every warp lasts as long
+ * as its slowest read and half of the fetch slots idle (profiles/r02_skewed_text.md), here only the CTA's last reads do.
+ * The start-table lookup of a new read is one more state of the machine (aL = FM_SP_START), so every iteration still
+ * issues exactly one load per busy slot.
+ * ------------------------------------------------------------------------ */
+#define FM_SP_START 0xFFFFFFFEu
+
+template <int K, int LANES, int QPT, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_dyn_kernel(const FmSparseParams p, uint32_t reads_per_cta)
+{
+  extern __shared__ __align__(16) uint32_t fsm[];             /* [0..1]: mbarrier; [2]: next read; [4..): packed reads */
+  uint32_t *sq = fsm + 4;
+  constexpr uint32_t BU4 = 2u * LANES;
+  const uint32_t smask = (p.sbits >= 32u) ? 0xFFFFFFFFu : ((1u << p.sbits) - 1u);
+  const uint32_t kmask = (p.start_bits >= 32u) ? 0xFFFFFFFFu : ((1u << p.start_bits) - 1u);
+  const uint32_t q0 = blockIdx.x * reads_per_cta;
+  const uint32_t nqb = min(reads_per_cta, p.nq - q0);
+  const uint32_t lg = threadIdx.x % LANES;
+  {
+    const uint32_t bytes = nqb * p.wpq * 4u;
+    const uint32_t *src = p.packed + (size_t) q0 * p.wpq;
+    const bool bulk = (bytes % 16u) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+    const uint32_t mbar = (uint32_t) __cvta_generic_to_shared(fsm);
+    if (threadIdx.x == 0) fsm[2] = 0u;
+    if (bulk) {
+      if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"((uint32_t) __cvta_generic_to_shared(sq)), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+      }
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(mbar) : "memory");
+    } else {
+      for (uint32_t i = threadIdx.x; i < nqb * p.wpq; i += THREADS) sq[i] = __ldg(src + i);
+      __syncthreads();
+    }
+  }
+
+  uint32_t L[QPT], R[QPT], aL[QPT], aR[QPT], rem[QPT], rd[QPT];
+  /* takes the next read of the CTA for slot i (or parks the slot): all lanes of the warp call it together */
+  auto take = [&](int i, bool need) {
+    uint32_t r = 0;
+    if (need && lg == 0) r = atomicAdd(&fsm[2], 1u);
+    r = __shfl_sync(0xFFFFFFFFu, r, 0, LANES);
+    if (need) {
+      rd[i] = r;
+      if (r < nqb) {
+        rem[i] = p.nsteps; L[i] = 0u; R[i] = p.bwtsize;
+        if (p.start) { aL[i] = FM_SP_START; aR[i] = FM_SP_DONE; }
+        else if (rem[i]) {
+          const uint32_t first = fm_read_field(sq + r * p.wpq, 0u, smask) * p.nb;
+          aL[i] = first; aR[i] = first + __umulhi(p.bwtsize, p.scale);
+        } else { aL[i] = aR[i] = FM_SP_DONE; }
+      } else { rem[i] = 0u; aL[i] = aR[i] = FM_SP_DONE; rd[i] = 0xFFFFFFFFu; }
+    }
+  };
+  #pragma unroll
+  for (int i = 0; i < QPT; i++) { rd[i] = 0xFFFFFFFFu; rem[i] = 0u; aL[i] = aR[i] = FM_SP_DONE; L[i] = R[i] = 0u; take(i, true); }
+
+  bool busy = false;
+  #pragma unroll
+  for (int i = 0; i < QPT; i++) busy |= rd[i] != 0xFFFFFFFFu;
+  while (__any_sync(0xFFFFFFFFu, busy)) {
+    uint32_t w[QPT][8];
+    uint2 lr[QPT];
+    #pragma unroll
+    for (int i = 0; i < QPT; i++) {
+      if (rd[i] != 0xFFFFFFFFu) {
+        if (aL[i] == FM_SP_START) lr[i] = __ldg(p.start + (sq[rd[i] * p.wpq] & kmask));
+        else if (rem[i]) {
+          const uint32_t a = (aL[i] != FM_SP_DONE) ? aL[i] : aR[i];
+          fm_sparse_load<LANES>(p.sblocks + (size_t) a * BU4 + 2u * lg, w[i]);
+        }
+      }
+    }
+    busy = false;
+    #pragma unroll
+    for (int i = 0; i < QPT; i++) {
+      const bool have = rd[i] != 0xFFFFFFFFu;
+      const bool starting = have && aL[i] == FM_SP_START;
+      const bool act = have && !starting && rem[i] != 0u;
+      const bool doL = act && aL[i] != FM_SP_DONE;
+      const bool doR = act && (!doL || aR[i] == aL[i]);
+      uint32_t cL = 0, cR = 0, inner = 0;
+      if (act) {
+        cL = fm_sparse_partial(w[i], L[i], lg);
+        cR = fm_sparse_partial(w[i], R[i], lg);
+        if (lg == 0) { cL += w[i][0]; cR += w[i][0]; }
+        inner = (lg == LANES - 1 && w[i][7] == FM_SP_INNER) ? 1u : 0u;
+      }
+      const uint32_t vL = fm_group_sum<LANES>(cL), vR = fm_group_sum<LANES>(cR);
+      const bool is_inner = fm_group_sum<LANES>(inner) != 0u;
+      if (doL) { if (is_inner) aL[i] = vL; else { L[i] = vL; aL[i] = FM_SP_DONE; } }
+      if (doR) { if (is_inner) aR[i] = vR; else { R[i] = vR; aR[i] = FM_SP_DONE; } }
+      bool next_roots = false;
+      if (starting) { L[i] = lr[i].x; R[i] = lr[i].y; aL[i] = aR[i] = FM_SP_DONE; next_roots = rem[i] != 0u; }
+      else if (act && aL[i] == FM_SP_DONE && aR[i] == FM_SP_DONE) { rem[i] -= 1u; next_roots = rem[i] != 0u; }
+      if (next_roots) {
+        const uint32_t first = fm_read_field(sq + rd[i] * p.wpq, p.start_bits + (p.nsteps - rem[i]) * p.sbits, smask) * p.nb;
+        aL[i] = first + __umulhi(L[i], p.scale);
+        aR[i] = first + __umulhi(R[i], p.scale);
+      }
+      const bool finished = have && rem[i] == 0u && aL[i] == FM_SP_DONE;
+      if (finished && lg == 0) reinterpret_cast<uint2 *>(p.results)[q0 + rd[i]] = make_uint2(L[i], R[i]);
+      take(i, finished);
+      busy |= rd[i] != 0xFFFFFFFFu;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------ *
  * Construction from SB96 (all on the device)
  * ------------------------------------------------------------------------ */
 

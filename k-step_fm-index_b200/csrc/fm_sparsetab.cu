@@ -308,11 +308,32 @@ static fm_sparse_fn fm_pick_sparse(int qpt)
   return NULL;
 }
 
+typedef void (*fm_sparse_dyn_fn_t)(const FmSparseParams, uint32_t);
+template <int K, int LANES>
+static fm_sparse_dyn_fn_t fm_pick_sparse_dyn(int qpt)
+{
+  if (qpt == 1) return fm_search_sparse_dyn_kernel<K, LANES, 1, 256, 6>;
+  if (qpt == 2) return fm_search_sparse_dyn_kernel<K, LANES, 2, 256, 4>;
+  if (qpt == 3) return fm_search_sparse_dyn_kernel<K, LANES, 3, 256, 4>;
+  if (qpt == 4) return fm_search_sparse_dyn_kernel<K, LANES, 4, 256, 3>;
+  return NULL;
+}
+
+/* dynamic read assignment pays when reads differ in length of their walk, i.e. when a visible part of the text lives in
+ * search trees; on an even text the static kernel is the same speed with fewer instructions.  $FMGPU_SPARSE_DYNAMIC=0/1 forces. */
+static bool fm_sparse_dynamic_enabled(const fmgpu_index_t *idx)
+{
+  const char *env = getenv("FMGPU_SPARSE_DYNAMIC");
+  if (env && *env) return atoi(env) != 0;
+  return idx->meta.sparse_tree_rows * 100ull > idx->meta.bwtsize;      /* more than 1 % of the rows in trees */
+}
+
 int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nq, uint32_t len,
                          uint32_t *d_results, fmgpu_variant_t v, cudaStream_t stream, unsigned long long *d_counters, bool use_lead_tables)
 {
   if (!idx->sblocks) return fm_fail_msg(FM_E_BAD_ARGUMENT, "FMGPU_MODE_SPARSE needs fmgpu_index_sparsify() on this replica first");
   const uint32_t k = idx->meta.steps, ks = idx->meta.sparse_bases, lanes = idx->meta.sparse_lanes;
+  const int vq_asked = v.queries_per_thread;
   if (v.queries_per_thread < 1 || v.queries_per_thread > 4) v.queries_per_thread = 4;
   FmSparseParams p;
   p.sblocks = idx->sblocks; p.blocks = idx->blocks; p.packed = d_packed; p.results = d_results;
@@ -344,6 +365,31 @@ int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_packed, uin
     if (smem <= 200 * 1024) break;
     if (v.queries_per_thread > 1) v.queries_per_thread -= 1;
     else return fm_fail_msg(FM_E_QUERY_SHAPE, "reads too long to stage in shared memory");
+  }
+  /* a plan of sparse steps only (the benchmark's; most lengths on a large index thanks to the lead tables): reads are handed
+   * to the lane groups dynamically, so that on a skewed text a read that walks deep trees does not hold its warp back
+   * ($FMGPU_SPARSE_DYNAMIC=0 forces the static kernel).  queries_per_thread 0 = 1 here. */
+  if (!d_counters && p.nfront == 0 && p.nback == 0 && !p.has_tail && p.nsteps >= 1 && fm_sparse_dynamic_enabled(idx)) {
+    typedef void (*fm_sparse_dyn_fn)(const FmSparseParams, uint32_t);
+    const int q = vq_asked >= 1 && vq_asked <= 4 ? vq_asked : 1;       /* one read per lane group, 6 CTAs per SM: the fastest on skewed texts */
+    fm_sparse_dyn_fn dfn = NULL;
+    if (k == 2) dfn = lanes == 4 ? fm_pick_sparse_dyn<2, 4>(q) : fm_pick_sparse_dyn<2, 2>(q);
+    else        dfn = lanes == 4 ? fm_pick_sparse_dyn<1, 4>(q) : fm_pick_sparse_dyn<1, 2>(q);
+    const char *renv = getenv("FMGPU_SPARSE_ROUNDS");
+    uint32_t rounds = renv && *renv && atoi(renv) >= 1 ? (uint32_t) atoi(renv) : (q == 1 ? 8u : 4u), rpc; size_t dsmem;
+    for (;;) {
+      rpc = (256 / lanes) * q * rounds;
+      dsmem = 16 + ((size_t) rpc * p.wpq + 4) * 4;
+      if (dsmem <= 48 * 1024 || rounds == 1) break;
+      rounds--;
+    }
+    if (dfn && dsmem <= 200 * 1024) {
+      if (dsmem > 48 * 1024) CU_TRY(cudaFuncSetAttribute((const void *) dfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dsmem));
+      const uint32_t dgrid = (uint32_t)((nq + rpc - 1) / rpc);
+      void *dargs[] = { (void *) &p, (void *) &rpc };
+      CU_TRY(cudaLaunchKernel((const void *) dfn, dim3(dgrid), dim3(256), dargs, dsmem, stream));
+      return FM_SUCCESS;
+    }
   }
   const int qsel = d_counters ? 0 : v.queries_per_thread;
   fm_sparse_fn fn = k == 2 ? (lanes == 4 ? fm_pick_sparse<2, 4>(qsel) : fm_pick_sparse<2, 2>(qsel))

@@ -27,11 +27,13 @@ def widths(k):
     return [2, 3, 5, 6, 10, 12] if k == 1 else [4, 6, 10, 12]          # (14 bases: test_sparse_steps_read_lengths and the full-size test)
 
 
+@pytest.mark.parametrize("dynamic", ["0", "1"], ids=["static_assignment", "dynamic_assignment"])
 @pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p))
-def test_sparse_steps_golden_all_widths(pkg, path):
+def test_sparse_steps_golden_all_widths(pkg, monkeypatch, path, dynamic):
     """Committed outputs of the unmodified reference searchers, the AltCounters quirk fixtures included (phantom
     occurrences); every width, both block sizes, every qpt, lambda from 1 (big grid, no trees) to the slot count (many
     overfull buckets -> search trees)."""
+    monkeypatch.setenv("FMGPU_SPARSE_DYNAMIC", dynamic)         # reads handed to lane groups statically / from a queue (plans of sparse steps only)
     g = np.load(path)
     reads, length, k = g["reads"], int(g["length"]), int(g["k"])
     nq = reads.size // length
@@ -112,10 +114,12 @@ def test_sparse_unavailable_and_errors(pkg):
 @pytest.mark.skipif(not helpers.has_ref_tools(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("name", ["polyA", "ACGT_period4", "two_letter", "repeat_x40", "random_plus_repeat"])
 @pytest.mark.parametrize("k", [1, 2])
-def test_sparse_steps_repetitive_texts_search_trees(pkg, tmp_path, name, k):
+@pytest.mark.parametrize("dynamic", ["0", "1"], ids=["static_assignment", "dynamic_assignment"])
+def test_sparse_steps_repetitive_texts_search_trees(pkg, tmp_path, monkeypatch, name, k, dynamic):
     """Repeats put hundreds of occurrences of one wide symbol into consecutive BWT rows: those buckets are overfull and
     become search trees of blocks (several levels deep for poly-A), which the kernel walks one fetch per iteration.
     Index files and expected (L,R) from the unmodified reference tools."""
+    monkeypatch.setenv("FMGPU_SPARSE_DYNAMIC", dynamic)
     rng = np.random.default_rng(11)
     n = 30011
     unit = ACGT[rng.integers(0, 4, 700)]
@@ -354,8 +358,8 @@ def test_sparse_dropin_flow_env_modes(pkg, tmp_path):
 
 
 def test_dropin_auto_mode_picks_table_by_text(pkg, tmp_path, capfd):
-    """transferCPUtoGPU in auto mode on indexes larger than L2: sparse-step table for a random text, fused-step table
-    when a large part of a repeat-rich text lives in search trees (profiles/r02_skewed_text.md); same (L,R) as the plain kernel."""
+    """transferCPUtoGPU in auto mode on indexes larger than L2: the sparse-step table for a random text AND for a repeat-rich
+    one (round 1 switched the latter to the fused-step table; profiles/r02_skewed_text.md); same (L,R) as the plain kernel."""
     rng = np.random.default_rng(23)
     n, length, nq = 48_000_001, 60, 20_000
     for kind in ("random", "repeats"):
@@ -385,4 +389,4 @@ def test_dropin_auto_mode_picks_table_by_text(pkg, tmp_path, capfd):
             del os.environ["FMGPU_VERBOSE"]
         err = capfd.readouterr().err
         assert np.array_equal(got, want), kind
-        assert ("search table: sparse-step" if kind == "random" else "search table: fused-step") in err, err
+        assert "search table: sparse-step" in err, err           # on both: repeats become search trees, not a reason to change tables
