@@ -420,7 +420,7 @@ def run_single_process(args, pkg, L, torch, emit):
     reps = [first] + [first.replicate(g) for g in range(1, ndev)]
     for r in reps:
         r.sparsify()
-    var = pkg.variant(pkg.MODE_SPARSE, 4)
+    var = pkg.variant(pkg.MODE_SPARSE, 3)
     h_res = torch.empty(2 * nq_total, dtype=torch.int32, pin_memory=True)
     handles = (C.c_void_p * ndev)(*[r.handle for r in reps])
 
@@ -595,7 +595,7 @@ def main():
             index.prepare(READ_LEN)
             torch.cuda.synchronize()
             setup["sparsify_s"] = round(time.time() - t0, 3)
-            var, sparse = pkg.variant(pkg.MODE_SPARSE, int(os.environ.get("FM_BENCH_QPT", "4"))), True
+            var, sparse = pkg.variant(pkg.MODE_SPARSE, int(os.environ.get("FM_BENCH_QPT", "3"))), True
         except pkg.FMError as ex:
             setup["sparse_unavailable"] = str(ex)
     if MODE == "fused":

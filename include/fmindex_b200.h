@@ -404,7 +404,8 @@ int32_t fmgpu_host_unregister(void *p);
  * Builds, on `device`, the image of the reference's tag-100 ".fmi" FILE
  * (header + entries, byte-identical to what genFMindex writes,
  * src/genFMindex.c:155-181,457-543) for an ASCII text or for the synthetic
- * text of fm_synth.h.  k in {1,2}; any text (repetitive texts take a prefix-doubling
+ * text of fm_synth.h.  k in {1,2,3,4} (the reference builds k = 3, 4 for its CPU searchers only, makefile:226-230); any text
+ * (repetitive texts take a prefix-doubling
  * pass over their tied suffixes); 2k <= n < 2^32 - 2. */
 typedef struct fmgpu_build fmgpu_build_t;
 int32_t  fmgpu_build_from_text(int32_t device, const char *h_ascii, uint64_t n, uint32_t steps, uint32_t chunk, fmgpu_build_t **out);

@@ -43,7 +43,7 @@ struct fmgpu_build {
   int       device;
   uint32_t  tag, ncounters;   /* 100 from the builder; 101/200/201 after fmgpu_build_transform */
   uint32_t  k, d, bwtsize, nentries, entry_words;
-  uint32_t  dpos[2], dbase[2];
+  uint32_t  dpos[4], dbase[4];
   uint32_t *d_image;     /* header (6 + 2k words) + entries, as in the file */
   uint64_t  image_words;
 };
@@ -177,7 +177,7 @@ __global__ void fmb_planes_kernel(const uint64_t *__restrict__ pt, const uint32_
   const uint64_t w = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= nwords32) return;
   const uint64_t row0 = w * 32, rows = n + 1;
-  uint32_t p[4] = { 0, 0, 0, 0 };
+  uint32_t p[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };               /* 2 planes per BWT layer, k <= 4 */
   for (uint32_t i = 0; i < 32; i++) {
     const uint64_t r = row0 + i;
     if (r >= rows) break;
@@ -237,8 +237,9 @@ __global__ void fmb_counters_kernel(const uint32_t *__restrict__ scan, const uin
   for (uint32_t sigma = 0; sigma < nsym; sigma++) cnt[sigma] = scan[(size_t) sigma * nentries + e] + acc[sigma];
 }
 
-/* Counter stage shared by the builder and by the k >= 3 -> 2-step projection of fm_gpu.cu: fills cnt[] of every
- * tag-100 entry from the planes already in `entries` (device), k <= 2.  dpos / dbase are host arrays. */
+/* Counter stage shared by the builder and by the k >= 3 -> 2-step projection of fm_index.cu: fills cnt[] of every
+ * tag-100 entry from the planes already in `entries` (device), k <= 4 (src/genFMindex.c:184-260 for any K_STEPS).
+ * dpos / dbase are host arrays. */
 cudaError_t fmb_counter_stage(uint32_t *entries, uint32_t k, uint32_t d, uint32_t entry_words, uint32_t nentries, uint32_t bwtsize,
                               const uint32_t *dpos, const uint32_t *dbase)
 {
@@ -247,13 +248,13 @@ cudaError_t fmb_counter_stage(uint32_t *entries, uint32_t k, uint32_t d, uint32_
   void *d_temp = NULL;
   cudaError_t e = cudaMalloc((void **) &hist, (size_t) nsym * nentries * 4);
   if (e == cudaSuccess) e = cudaMalloc((void **) &d_acc, nsym * 4);
-  if (e == cudaSuccess) e = cudaMalloc((void **) &d_dpos, 2 * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &d_dpos, 4 * 4);
   if (e == cudaSuccess) e = cudaMemcpy(d_dpos, dpos, k * 4, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
     fmb_hist_kernel<<<(nentries + 127) / 128, 128>>>(entries, k, d, entry_words, nentries, bwtsize, d_dpos, hist);
     e = cudaGetLastError();
   }
-  uint32_t totals[16], acc[16];
+  uint32_t totals[256], acc[256];
   for (uint32_t sigma = 0; sigma < nsym && e == cudaSuccess; sigma++) {
     uint32_t *h = hist + (size_t) sigma * nentries, last_in = 0, last_out = 0;
     e = cudaMemcpy(&last_in, h + nentries - 1, 4, cudaMemcpyDeviceToHost);
@@ -442,8 +443,8 @@ pd_done:
 static int32_t fmb_build(int device, const char *h_ascii, uint64_t n, uint64_t seed, uint32_t k, uint32_t d,
                          fmgpu_build_t **out)
 {
-  if (!out || k < 1 || k > 2 || d == 0 || d % 32 || n < 2 * k || n >= 0xFFFFFFFEull) {
-    snprintf(g_berr, sizeof g_berr, "fmgpu_build: need k in {1,2}, d multiple of 32, 2k <= n < 2^32-2");
+  if (!out || k < 1 || k > 4 || d == 0 || d % 32 || n < 2 * k || n >= 0xFFFFFFFEull) {
+    snprintf(g_berr, sizeof g_berr, "fmgpu_build: need k in {1,2,3,4}, d multiple of 32, 2k <= n < 2^32-2");
     return FM_E_BAD_ARGUMENT;
   }
   CU_TRY(cudaSetDevice(device));
@@ -497,7 +498,7 @@ static int32_t fmb_build(int device, const char *h_ascii, uint64_t n, uint64_t s
     cudaFree(keys_b); keys_b = NULL;
 
     /* 3. '$' rows */
-    BTRY(cudaMalloc((void **) &d_dpos, 2 * 4)); BTRY(cudaMalloc((void **) &d_dbase, 2 * 4));
+    BTRY(cudaMalloc((void **) &d_dpos, 4 * 4)); BTRY(cudaMalloc((void **) &d_dbase, 4 * 4));
     BTRY(cudaMemset(d_dpos, 0xFF, 8));
     fmb_find_dollars_kernel<<<(unsigned)((n + 1 + 255) / 256), 256>>>(vals_b, n, k, d_dpos);
     BTRY(cudaGetLastError());
@@ -521,7 +522,7 @@ static int32_t fmb_build(int device, const char *h_ascii, uint64_t n, uint64_t s
     if (e != cudaSuccess) { rc = fmb_fail(e, "counter stage", __FILE__, __LINE__); goto done; }
 
     /* 6. header (src/genFMindex.c:167-176) */
-    uint32_t head[10];
+    uint32_t head[14];
     head[0] = 100; head[1] = k; head[2] = b->bwtsize; head[3] = nsym; head[4] = b->nentries; head[5] = d;
     for (uint32_t s = 0; s < k; s++) { head[6 + s] = b->dpos[s]; head[6 + k + s] = b->dbase[s]; }
     BTRY(cudaMemcpy(b->d_image, head, (6 + 2 * k) * 4, cudaMemcpyHostToDevice));
@@ -669,10 +670,10 @@ extern "C" int32_t fmgpu_build_transform(const fmgpu_build_t *src, uint32_t tag,
   fmb_transform_kernel<<<(src->nentries + 127) / 128, 128>>>(se, k, src->d, src->nentries, src->entry_words, tag, de, b->entry_words);
   e = cudaGetLastError();
   if (e == cudaSuccess && ac) {
-    fmb_ac_padding_kernel<<<1, 32>>>(se, k, src->d, src->nentries, src->entry_words, src->bwtsize, de, b->entry_words);
+    fmb_ac_padding_kernel<<<1, 128>>>(se, k, src->d, src->nentries, src->entry_words, src->bwtsize, de, b->entry_words);
     e = cudaGetLastError();
   }
-  uint32_t head[10];
+  uint32_t head[14];
   head[0] = tag; head[1] = k; head[2] = b->bwtsize; head[3] = b->ncounters; head[4] = b->nentries; head[5] = b->d;
   for (uint32_t s = 0; s < k; s++) { head[6 + s] = b->dpos[s]; head[6 + k + s] = b->dbase[s]; }
   if (e == cudaSuccess) e = cudaMemcpy(b->d_image, head, (6 + 2 * k) * 4, cudaMemcpyHostToDevice);

@@ -501,7 +501,7 @@ int32_t fmgpu_search_index(void *index, void *queries, void *resIntervals)
       v.mode = (mode == FM_MODE_AUTO) ? (meta.sparse_bases ? FMGPU_MODE_SPARSE : meta.fused_bases ? FMGPU_MODE_FUSED : FMGPU_MODE_COOP) : mode;
       if (v.mode == FMGPU_MODE_SPARSE && !meta.sparse_bases) v.mode = meta.fused_bases ? FMGPU_MODE_FUSED : FMGPU_MODE_COOP;
       if (v.mode == FMGPU_MODE_FUSED && !meta.fused_bases) v.mode = FMGPU_MODE_COOP;
-      if (v.mode == FMGPU_MODE_SPARSE) v.queries_per_thread = 4;
+      if (v.mode == FMGPU_MODE_SPARSE) v.queries_per_thread = 0;     /* the sparse launcher's own default */
     }
     err = fmgpu_batch_search_timed_async(rs->replica[g], ss->shard[g], &v);
   }

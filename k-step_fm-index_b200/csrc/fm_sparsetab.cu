@@ -334,7 +334,7 @@ int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_packed, uin
   if (!idx->sblocks) return fm_fail_msg(FM_E_BAD_ARGUMENT, "FMGPU_MODE_SPARSE needs fmgpu_index_sparsify() on this replica first");
   const uint32_t k = idx->meta.steps, ks = idx->meta.sparse_bases, lanes = idx->meta.sparse_lanes;
   const int vq_asked = v.queries_per_thread;
-  if (v.queries_per_thread < 1 || v.queries_per_thread > 4) v.queries_per_thread = 4;
+  if (v.queries_per_thread < 1 || v.queries_per_thread > 4) v.queries_per_thread = 3;   /* profiles/r02_sparse_qpt_sweep.jsonl */
   FmSparseParams p;
   p.sblocks = idx->sblocks; p.blocks = idx->blocks; p.packed = d_packed; p.results = d_results;
   p.nblocks = idx->meta.nblocks; p.nq = (uint32_t) nq;
@@ -376,7 +376,7 @@ int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_packed, uin
     if (k == 2) dfn = lanes == 4 ? fm_pick_sparse_dyn<2, 4>(q) : fm_pick_sparse_dyn<2, 2>(q);
     else        dfn = lanes == 4 ? fm_pick_sparse_dyn<1, 4>(q) : fm_pick_sparse_dyn<1, 2>(q);
     const char *renv = getenv("FMGPU_SPARSE_ROUNDS");
-    uint32_t rounds = renv && *renv && atoi(renv) >= 1 ? (uint32_t) atoi(renv) : (q == 1 ? 8u : 4u), rpc; size_t dsmem;
+    uint32_t rounds = renv && *renv && atoi(renv) >= 1 ? (uint32_t) atoi(renv) : 4u, rpc; size_t dsmem;
     for (;;) {
       rpc = (256 / lanes) * q * rounds;
       dsmem = 16 + ((size_t) rpc * p.wpq + 4) * 4;

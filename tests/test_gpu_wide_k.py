@@ -131,3 +131,50 @@ def test_wide_k_fuzz_tiny_references(pkg, tmp_path, case):
                 b.search(idx, v)
                 assert np.array_equal(b.download(), want), f"case {case}: k={k} d={d} n={n} tag={tag} len={length} mode={v.mode}"
             b.free(); idx.free()
+
+
+@pytest.mark.parametrize("k", [3, 4])
+@pytest.mark.parametrize("d", [32, 64, 128])
+def test_gpu_builder_writes_the_reference_files_for_k3_k4(pkg, tmp_path, k, d):
+    """fmgpu_build_from_text with k = 3, 4 (src/genFMindex.c:184-260,327-455 for any K_STEPS): the image and its three
+    transformed layouts are byte-identical to what gfmiBaseLine_<d>bases_<k>step / tfmiBMP / tfmiAC write, on a random
+    text and on a repetitive one (prefix-doubling path); gfmi_b200 writes the same file under the same name."""
+    rng = np.random.default_rng(7 * k + d)
+    unit = ACGT[rng.integers(0, 4, 500)]
+    texts = {"random": ACGT[rng.integers(0, 4, 30011 + d)],
+             "repeats": np.concatenate([ACGT[rng.integers(0, 4, 4000)], np.tile(unit, 9), np.full(700, ord("A"), dtype=np.uint8), ACGT[rng.integers(0, 4, 777)]])}
+    for name, text in texts.items():
+        if (text.size + 1) % d == 0:
+            text = text[:-1]
+        paths = helpers.build_reference_indexes(str(tmp_path / name), text, k, d)
+        b = pkg.IndexBuild.from_text(text, k, d)
+        got = b.download()
+        want = np.fromfile(paths[100], dtype=np.uint32)
+        assert np.array_equal(got[:6 + 2 * k], want[:6 + 2 * k]), f"{name}: header / '$' rows differ"
+        assert np.array_equal(got, want), f"{name}: k={k} d={d} tag-100 image differs from the reference builder's file"
+        for tag in (101, 200, 201):
+            t = b.transform(tag)
+            assert np.array_equal(t.download(), np.fromfile(paths[tag], dtype=np.uint32)), f"{name}: k={k} d={d} tag {tag}"
+            t.free()
+        # searched like any k >= 3 file: through the 2-step index its first two layers define
+        length = 4 * k
+        reads = make_reads(text, rng, length, 600, 200)
+        ref = helpers.RefSearcher(k, d, False)
+        want_lr, _ = ref.search(ref.load(paths[100]), reads, length)
+        idx = b.to_index()
+        batch = pkg.DeviceBatch(0, reads.size // length, length, 2)
+        batch.upload_ascii(reads)
+        batch.search(idx, pkg.variant(pkg.MODE_COOP))
+        assert np.array_equal(batch.download(), want_lr), f"{name}: k={k} d={d}"
+        batch.free(); idx.free(); b.free()
+    # the CLI: same file name, same bytes as the reference tool
+    text = texts["random"] if (texts["random"].size + 1) % d else texts["random"][:-1]
+    wd = tmp_path / "cli"
+    wd.mkdir()
+    helpers.write_fasta_ref(str(wd / "ref.fa"), text)
+    exe = os.path.join(helpers.ROOT, helpers.PKG_NAME, "bin", "gfmi_b200")
+    helpers.run([exe, "ref.fa", str(text.size), str(k), str(d), "--all"], cwd=str(wd))
+    ref_paths = helpers.build_reference_indexes(str(tmp_path / "random"), text, k, d)
+    for tag, suf in helpers.TAG_SUFFIX.items():
+        mine = wd / f"ref.fa.{text.size}.{d}fmi{k}steps.fmi{suf}"
+        assert mine.read_bytes() == open(ref_paths[tag], "rb").read(), f"gfmi_b200 k={k} d={d} tag {tag}"

@@ -266,3 +266,21 @@ def test_bench_and_entry_scripts_compile_without_warnings():
             compile(src, path, "exec")
     out = subprocess.run([os.sys.executable, os.path.join(helpers.ROOT, "bench.py"), "--help"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "--impl" in out.stdout
+
+
+def test_host_layer_under_asan_and_ubsan(built, tmp_path):
+    """`make sanitize`: fm_host.c, fm_ingest.c and fm_hostpack.c compiled with AddressSanitizer + UndefinedBehaviorSanitizer
+    and driven through loaders, writers, packers, error paths and handle lifetimes (tests/c/host_sanitize.c): zero findings,
+    leak check included."""
+    if not os.path.exists("/usr/bin/gcc"):
+        pytest.skip("system gcc with the sanitizer runtimes is not installed")
+    pkg = helpers.pkg()
+    helpers.run(["make", "-C", pkg.CSRC, "sanitize"])
+    g = np.load(os.path.join(helpers.ROOT, "tests", "golden", "small_k2_d64.npz"))
+    for tag in (100, 201):
+        fn = str(tmp_path / f"i{tag}.fmi")
+        g[f"image_{tag}"].tofile(fn)
+        p = subprocess.run([os.path.join(pkg.CSRC, "build", "host_sanitize"), fn, "2", str(tmp_path)], capture_output=True, text=True,
+                           env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0", UBSAN_OPTIONS="print_stacktrace=1"))
+        assert p.returncode == 0 and "host_sanitize OK" in p.stdout, p.stdout[-1500:] + p.stderr[-3000:]
+        assert "AddressSanitizer" not in p.stderr and "runtime error" not in p.stderr and "LeakSanitizer" not in p.stderr, p.stderr[-3000:]
