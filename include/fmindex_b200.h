@@ -430,12 +430,18 @@ int32_t  fmgpu_synth_reads_device(int32_t device, uint64_t n, uint64_t seed_ref,
  * fmgpu_index_build_sa derives the full suffix array SA[0 .. bwtsize) of the indexed text from the replica's own
  * table -- so it works for index FILES, which carry no SA: SA[r] = number of 1-step LF steps from row r to the '$'
  * row, by list ranking over the LF permutation on the GPU (csrc/fm_locate.cuh).  4 bytes per row stay resident
- * (8 GB for 2 Gbp), 16 bytes per row of scratch while it is built.  FM_E_NOT_IMPLEMENTED for an AltCounters index
- * carrying the padding quirk, or when memory does not suffice.
+ * (8 GB for 2 Gbp), 16 bytes per row of scratch while it is built.  AltCounters files with an active padding quirk are
+ * served too (the table holds quirk-free ranks: the text's own index).  FM_E_NOT_IMPLEMENTED when memory does not suffice.
  * fmgpu_locate_device turns intervals into text positions: positions[q * max_hits + j] = start (0-based) of the
  * j-th occurrence of read q in suffix-array order, 0xFFFFFFFF beyond min(R - L, max_hits); nhits[q] = R - L (may
  * be NULL).  d_results is what the search wrote ([2q] = L, [2q+1] = R). */
 int32_t fmgpu_index_build_sa(fmgpu_index_t *idx);
+/* Sampled suffix array: only the rows whose text position is a multiple of `rate` (0 = 32) keep their SA value; locate
+ * walks the 1-step LF mapping from an occurrence's row to the next marked row, one 64-byte fetch per step, on a table
+ * made for it (0.5 bytes per row).  1.3 GB instead of 8 GB for 2 Gbp at rate 32; a located occurrence costs
+ * (rate - 1) / 2 + 2 fetches on average instead of one.  Same positions as the full array.  Replaces whichever array
+ * the replica holds.  fmgpu_index_sa / fmgpu_index_download_sa serve the full array only. */
+int32_t fmgpu_index_build_sa_sampled(fmgpu_index_t *idx, uint32_t rate);
 int32_t fmgpu_index_drop_sa(fmgpu_index_t *idx);
 void   *fmgpu_index_sa(const fmgpu_index_t *idx);          /* device pointer to SA, or NULL */
 int32_t fmgpu_locate_device(const fmgpu_index_t *idx, const uint32_t *d_results, uint64_t nqueries, uint32_t max_hits,

@@ -131,6 +131,7 @@ PROTOTYPES = {
     "fmgpu_index_sparsify": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, C.c_uint32]),
     "fmgpu_index_unsparsify": (C.c_int32, [_VP]),
     "fmgpu_index_build_sa": (C.c_int32, [_VP]),
+    "fmgpu_index_build_sa_sampled": (C.c_int32, [_VP, C.c_uint32]),
     "fmgpu_index_drop_sa": (C.c_int32, [_VP]),
     "fmgpu_index_sa": (_VP, [_VP]),
     "fmgpu_index_download_sa": (C.c_int32, [_VP, _VP]),
@@ -384,6 +385,11 @@ class DeviceIndex:
     def build_sa(self):
         """Derives the suffix array of the indexed text from this replica's own table (needed by locate)."""
         check(lib().fmgpu_index_build_sa(self.handle), "fmgpu_index_build_sa")
+        return self
+
+    def build_sa_sampled(self, rate=32):
+        """Keeps every `rate`-th suffix array value + an LF-walk table instead of the whole array (same locate results)."""
+        check(lib().fmgpu_index_build_sa_sampled(self.handle, rate), "fmgpu_index_build_sa_sampled")
         return self
 
     def drop_sa(self):

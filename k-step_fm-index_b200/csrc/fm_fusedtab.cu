@@ -10,10 +10,14 @@
  * ------------------------------------------------------------------------ */
 static uint32_t fm_fused_rows(uint32_t lanes) { return 32u * (8u * lanes - 1u); }
 
+cudaError_t fm_table_symbols(const uint4 *table, uint32_t nblocks, uint32_t nsym, uint64_t nrows_alloc, uint8_t *d_sym)
+{
+  fm_fuse_symbols_kernel<<<(nblocks + 127) / 128, 128>>>(table, nblocks, nsym, nrows_alloc, d_sym);
+  return cudaGetLastError();
+}
 cudaError_t fm_row_symbols(const fmgpu_index_t *idx, uint64_t nrows_alloc, uint8_t *d_sym)
 {
-  fm_fuse_symbols_kernel<<<(idx->meta.nblocks + 127) / 128, 128>>>(idx->blocks, idx->meta.nblocks, idx->meta.nsymbols, nrows_alloc, d_sym);
-  return cudaGetLastError();
+  return fm_table_symbols(idx->blocks, idx->meta.nblocks, idx->meta.nsymbols, nrows_alloc, d_sym);
 }
 
 template <int LANES>

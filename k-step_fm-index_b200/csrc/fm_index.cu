@@ -182,7 +182,7 @@ static int32_t fm_index_from_device_entries(int device, uint32_t tag, uint32_t s
   if (e != cudaSuccess) { cudaFree(idx->blocks); free(idx); return fm_fail(e, "fm_reblock_kernel", __FILE__, __LINE__); }
 
   /* constants of the derived 1-step rank that serves the last base of odd-length reads on a 2-step index */
-  if (steps == 2 && idx->meta.quirk_mask == 0) {
+  if (steps == 2) {
     uint4 first[16], last[16];
     const uint32_t bl = bwtsize / FM_SB_ROWS, rl = bwtsize - bl * FM_SB_ROWS;
     for (uint32_t s = 0; s < 16 && e == cudaSuccess; s++) {
@@ -209,7 +209,9 @@ static int32_t fm_index_from_device_entries(int device, uint32_t tag, uint32_t s
       idx->meta.tail_const[c] = c1 - (at0[c] + at0[c | 4u] + at0[c | 8u] + at0[c | 12u]);
       c1 += total1[c];
     }
-    idx->meta.tail_row = dpos[1]; idx->meta.tail_base = t0; idx->meta.tail_valid = 1;
+    idx->meta.tail_row = dpos[1]; idx->meta.tail_base = t0;
+    idx->tail_consts_ok = 1;                                 /* the stored ranks are quirk-free: always the text's own 1-step index (locate) */
+    idx->meta.tail_valid = idx->meta.quirk_mask == 0;         /* odd read lengths are served on quirk-free files only */
   }
   *out = idx;
   return FM_SUCCESS;

@@ -39,8 +39,11 @@ struct fmgpu_index {
   uint2             *slead[16];    /* lead tables: (L,R) of all b-mers, or NULL */
   uint4             *tail1;        /* tail table (fm_tail_table_kernel), built by fmgpu_index_prepare for odd read lengths */
   uint32_t          *sa;           /* suffix array, full (fmgpu_index_build_sa) or sampled (fmgpu_index_build_sa_sampled), or NULL */
-  uint32_t           sa_rate;      /* 1 = full; s > 1: sa[j] = SA[j * s]... see fm_locate.cu */
-  uint32_t          *sa_marks;     /* sampled SA: bit vector + ranks of the rows whose SA value is a multiple of sa_rate */
+  uint32_t           sa_rate;      /* 1 = full: sa[row]; s > 1: sa[] = the SA values of the marked rows, in row order (fm_locate.cuh) */
+  uint32_t          *sa_marks;     /* sampled SA: the walk table (64 bytes per 128 rows: ranks, character planes, marks) */
+  uint32_t          *sa_markrank;  /* sampled SA: marked rows before each 128-row block */
+  uint32_t           sa_norow, sa_nlb;   /* the row without a BWT character; number of 128-row blocks */
+  int                tail_consts_ok;     /* meta.tail_* describe the text's 1-step index (k = 2), whether or not odd lengths are served */
   uint32_t           s_uni_nb, s_uni_scale;   /* sparse table is a uniform grid: blocks per symbol and the one scale (0 = directory) */
   int                tail1_tried;  /* 1 once that build was attempted (a failed allocation is not retried) */
   fm_phantoms        fphantoms;    /* quirk: extra occurrences of fused symbols */
@@ -76,6 +79,8 @@ void     fm_budget_account(fmgpu_index_t *idx);
 const uint4 *fm_build_tail(fmgpu_index_t *idx);
 cudaError_t fm_tail_table_into(const fmgpu_index_t *idx, uint4 *dst);   /* the same table into caller-owned memory (async, legacy stream) */
 
+/* the same for any SB96-shaped table of nsym symbols (e.g. the 4-symbol tail table) */
+cudaError_t fm_table_symbols(const uint4 *table, uint32_t nblocks, uint32_t nsym, uint64_t nrows_alloc, uint8_t *d_sym);
 /* k-step symbol of every row of the SB96 table into sym[nrows_alloc] (FM_SYM_NONE for '$' rows and rows past the end) (fm_fusedtab.cu) */
 cudaError_t fm_row_symbols(const fmgpu_index_t *idx, uint64_t nrows_alloc, uint8_t *d_sym);
 

@@ -23,10 +23,10 @@ t1=$(date +%s.%N)
 PARTS=16; PER=$(( (NQ + PARTS - 1) / PARTS ))
 for p in $(seq 0 $((PARTS - 1))); do
   first=$((p * PER)); num=$PER; [ $((first + num)) -gt $NQ ] && num=$((NQ - first))
-  [ $num -gt 0 ] && $BIN/fmsynth reads $W/reads.$(printf %02d $p) $NTEXT 1 $num $LEN 2 $first &
+  [ $num -gt 0 ] && $BIN/fmsynth reads $W/part.$(printf %02d $p) $NTEXT 1 $num $LEN 2 $first &
 done
 wait
-cat $W/reads.?? > $W/reads.fa && rm -f $W/reads.??
+cat $W/part.?? > $W/reads.fa && rm -f $W/part.??
 t2=$(date +%s.%N)
 echo "index file $(stat -c %s $IDX) B in $(awk "BEGIN{print $t1 - $t0}") s; reads file $(stat -c %s $W/reads.fa) B in $(awk "BEGIN{print $t2 - $t1}") s" >> $LOG
 first_run=1
