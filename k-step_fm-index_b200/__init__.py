@@ -21,7 +21,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfmindex_b200.so")
+LIB_PATH = os.environ.get("FMGPU_LIB") or os.path.join(_HERE, "lib", "libfmindex_b200.so")   # $FMGPU_LIB: e.g. the -DFM_DEBUG_BOUNDS build
 CSRC = os.path.join(_HERE, "csrc")
 BIN = os.path.join(_HERE, "bin")
 

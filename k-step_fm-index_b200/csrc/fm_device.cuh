@@ -26,6 +26,17 @@
 #include <cuda_runtime.h>
 
 #define FM_SB_ROWS 96u
+
+/* `make debug` (-DFM_DEBUG_BOUNDS): every table index a kernel computes is checked against the table's extent before the
+ * load; a violation prints the site and traps (the launch then fails with an error, the tests with it).  This is the
+ * stand-in for compute-sanitizer memcheck, which is closed on this GPU pool (profiles/r02_sanitizers.txt). */
+#ifdef FM_DEBUG_BOUNDS
+#include <stdio.h>
+#define FM_BOUND(index, limit, what) do { if ((unsigned long long)(index) >= (unsigned long long)(limit)) { \
+  printf("fm bounds: %s: %llu >= %llu (block %u thread %u)\n", what, (unsigned long long)(index), (unsigned long long)(limit), blockIdx.x, threadIdx.x); __trap(); } } while (0)
+#else
+#define FM_BOUND(index, limit, what) do { } while (0)
+#endif
 #define FM_SYM_NONE  0xFFu
 #define FM_FSYM_NONE 0xFFFFu
 
@@ -66,6 +77,7 @@ __device__ __forceinline__ uint32_t fm_tail_rank(const uint4 *__restrict__ block
   const uint32_t b = fm_div96(X), r = X - b * FM_SB_ROWS;
   uint4 v[4];
   #pragma unroll
+  FM_BOUND(b, nblocks, "tail rank: SB96 block");
   for (int c1 = 0; c1 < 4; c1++) v[c1] = fm_ldg16(blocks + (size_t)(c | (c1 << 2)) * nblocks + b);
   uint32_t sum = tail_const + ((X > tail_row && c == tail_base) ? 1u : 0u);
   #pragma unroll
@@ -81,6 +93,7 @@ __device__ __forceinline__ void fm_tail_step(const uint4 *__restrict__ tail1, co
   if (tail1) {
     const uint32_t bL = fm_div96(L), bR = fm_div96(R);
     const uint4 *base = tail1 + (size_t) c * nblocks;
+    FM_BOUND(bL, nblocks, "tail table block (L)"); FM_BOUND(bR, nblocks, "tail table block (R)"); FM_BOUND(c, 4u, "tail base");
     const uint4 vL = fm_ldg16(base + bL);
     const uint4 vR = (bL == bR) ? vL : fm_ldg16(base + bR);
     L = fm_block_rank(vL, L - bL * FM_SB_ROWS);

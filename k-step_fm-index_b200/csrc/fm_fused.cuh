@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_fused_kernel(const Fm
       const uint32_t sig = fm_read_field(myq[i], pos, BMASK);
       const uint32_t bL = fm_div96(L[i]), bR = fm_div96(R[i]);
       const uint4 *base = p.blocks + (size_t) sig * p.nblocks;
+      FM_BOUND(bL, p.nblocks, "fused: SB96 block (L)"); FM_BOUND(bR, p.nblocks, "fused: SB96 block (R)");
       const uint4 vL = fm_ldg16(base + bL);
       const uint4 vR = (bL == bR) ? vL : fm_ldg16(base + bR);
       if (COUNT && live[i] && lg == 0) nl_fetch += (bL == bR) ? 1 : 2;
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_fused_kernel(const Fm
       const uint4 *base = p.fblocks + ((size_t) sig * p.nfblocks) * (2 * LANES) + 2 * lg;
       same[i] = (bL == bR);
       if (COUNT && live[i] && lg == 0) nf_fetch += same[i] ? 1 : 2;
+      FM_BOUND(bL, p.nfblocks, "fused block (L)"); FM_BOUND(bR, p.nfblocks, "fused block (R)");
       fm_ldg32(base + (size_t) bL * (2 * LANES), wL[i]);
       if (!same[i]) fm_ldg32(base + (size_t) bR * (2 * LANES), wR[i]);
     }

@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_task_kernel(const FmS
       rL[i] = L[i] - bL * FM_SB_ROWS; rR[i] = R[i] - bR * FM_SB_ROWS;
       const uint4 *base = p.blocks + (size_t) sig[i] * p.nblocks;
       same[i] = (bL == bR);
+      FM_BOUND(bL, p.nblocks, "task: SB96 block (L)"); FM_BOUND(bR, p.nblocks, "task: SB96 block (R)");
       vL[i] = fm_ldg16(base + bL);
       if (!same[i]) vR[i] = fm_ldg16(base + bR);
       if (COUNT && live[i]) { nblk_fetch += same[i] ? 1 : 2; nsec_fetch += ((bL >> 1) == (bR >> 1)) ? 1 : 2; }
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_coop_kernel(const FmS
       r[i] = X[i] - b * FM_SB_ROWS;
       const uint32_t bp = __shfl_xor_sync(0xFFFFFFFFu, b, 1);
       take[i] = side && (b == bp);          /* R lane rides on the L lane's fetch */
+      FM_BOUND(b, p.nblocks, "coop: SB96 block");
       if (!take[i]) v[i] = fm_ldg16(p.blocks + (size_t) sig[i] * p.nblocks + b);
     }
     #pragma unroll
@@ -199,6 +201,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_coop_kernel(const FmS
       const uint32_t c = (myq[i][pos >> 5] >> (pos & 31u)) & 3u;
       if (p.tail1) {                                  /* the lanes of a pair share the fetch when L and R fall in one block */
         const uint32_t b = fm_div96(X[i]);
+        FM_BOUND(b, p.nblocks, "coop: tail table block");
         X[i] = fm_block_rank(fm_ldg16(p.tail1 + (size_t) c * p.nblocks + b), X[i] - b * FM_SB_ROWS);
       } else {
         X[i] = fm_tail_rank(p.blocks, p.nblocks, c, X[i], p.tail_const[c], p.tail_row, p.tail_base);

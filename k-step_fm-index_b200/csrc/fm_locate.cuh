@@ -90,6 +90,7 @@ __global__ void fm_locate_kernel(const uint32_t *__restrict__ sa, const uint2 *_
   const uint2 x = lr[q];
   const uint32_t cnt = x.y > x.x ? x.y - x.x : 0u;
   if (j == 0 && nhits) nhits[q] = cnt;
+  if (j < cnt) FM_BOUND((uint64_t) x.x + j, 0x100000000ull, "locate: row");
   positions[t] = j < cnt ? __ldg(sa + x.x + j) : 0xFFFFFFFFu;
 }
 
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(256) fm_locate_sampled_kernel(const uint4 *__r
   while (__any_sync(0xFFFFFFFFu, walking)) {
     uint32_t w[8];
     const uint32_t b = r / FM_LOC_ROWS, o = r % FM_LOC_ROWS, wi = o >> 5, bit = o & 31u;
-    if (walking) fm_ldg32(lblocks + (size_t) b * 4 + 2u * lg, w);
+    if (walking) { FM_BOUND(r, bwtsize, "sampled locate: row"); fm_ldg32(lblocks + (size_t) b * 4 + 2u * lg, w); }
     else { for (int i = 0; i < 8; i++) w[i] = 0u; }
     /* lane 0: w[0..3] ranks, w[4..7] low bits; lane 1: w[0..3] high bits, w[4..7] marks.  Exchange what the other needs. */
     uint32_t lo[4], hi[4];

@@ -66,6 +66,7 @@ struct FmSparseParams {
   const uint4 *tail1;         /* tail table (fm_tail_table_kernel) or NULL */
   uint32_t nb, scale;         /* grid: blocks per wide symbol, bucket = umulhi(X, scale)          */
   uint32_t nroots;            /* nb * 4^KS: blocks at or beyond it are tree nodes                  */
+  uint32_t total_blocks;      /* grid + tree nodes (extent of sblocks, checked by the -DFM_DEBUG_BOUNDS build) */
   const uint2 *start;         /* (L,R) after the first start_bits / 2 bases, indexed by those packed bits, or NULL: the start
                                  table (a whole number of sparse steps) or a lead table (the leftover bases, taken first) */
   uint32_t start_bits;
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_kernel(const F
         const uint32_t sg = fm_read_field(myq[i], pos, BMASK);
         const uint32_t bL = fm_div96(L[i]), bR = fm_div96(R[i]);
         const uint4 *base = p.blocks + (size_t) sg * p.nblocks;
+        FM_BOUND(bL, p.nblocks, "sparse: SB96 block (L)"); FM_BOUND(bR, p.nblocks, "sparse: SB96 block (R)");
         const uint4 vL = fm_ldg16(base + bL);
         const uint4 vR = (bL == bR) ? vL : fm_ldg16(base + bR);
         if (COUNT && live[i] && lg == 0) n_sb += (bL == bR) ? 1 : 2;
@@ -200,6 +202,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_kernel(const F
     for (int i = 0; i < QPT; i++) {
       if (rem[i]) {
         const uint32_t a = (aL[i] != FM_SP_DONE) ? aL[i] : aR[i];
+        FM_BOUND(a, p.total_blocks, "sparse: grid / tree block");
         fm_sparse_load<LANES>(p.sblocks + (size_t) a * BU4 + 2u * lg, w[i]);
         if (COUNT && lg == 0) { if (a < p.nroots) n_root++; else n_tree++; }
       }
@@ -342,6 +345,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_sparse_dyn_kernel(con
         if (aL[i] == FM_SP_START) lr[i] = __ldg(p.start + (sq[rd[i] * p.wpq] & kmask));
         else if (rem[i]) {
           const uint32_t a = (aL[i] != FM_SP_DONE) ? aL[i] : aR[i];
+          FM_BOUND(a, p.total_blocks, "sparse (dynamic): grid / tree block"); FM_BOUND(rd[i], nqb, "sparse (dynamic): read slot");
           fm_sparse_load<LANES>(p.sblocks + (size_t) a * BU4 + 2u * lg, w[i]);
         }
       }
@@ -608,6 +612,8 @@ __global__ void __launch_bounds__(256) fm_sparse_fill_ext_kernel(const uint32_t 
   const FmSparseTree<LANES> t(cnt);
   uint32_t local = e - extoff[g], v = t.D;                     /* levels are stored top-down */
   while (v > 0) { v--; if (local < t.N[v]) break; local -= t.N[v]; }
+  FM_BOUND(v, t.D, "sparse build: level of an extension node"); FM_BOUND(local, t.N[v], "sparse build: node index in its level");
+  FM_BOUND(t.level_offset(v) + local, t.below_root(), "sparse build: node offset in its root's area");
   fm_sparse_write_node<LANES>(t, v, local, rows + t0, cnt, (uint32_t) nroots + extoff[g], rank0[s] + (t0 - s0),
                               sblocks + (nroots + e) * (2u * LANES));
 }

@@ -351,6 +351,7 @@ int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_packed, uin
   p.wpq = fmgpu_words_per_query(len); p.bwtsize = idx->meta.bwtsize;
   p.sbits = 2 * ks;
   p.nb = idx->s_uni_nb; p.scale = idx->s_uni_scale; p.nroots = idx->s_uni_nb << (2 * ks);
+  p.total_blocks = (uint32_t) idx->meta.sparse_blocks;
   p.quirk_start = idx->meta.quirk_start; p.quirk_mask = idx->meta.quirk_mask;
   p.fetch_counters = d_counters;
   p.has_tail = lead ? 0u : len % k;                            /* a lead table already holds the odd base */
