@@ -250,6 +250,7 @@ typedef struct {
   double   results_d2h_s;         /* all shards: (L,R) D2H                                                         */
   float    search_ms[16];         /* [g]: kernels of the last searchIndexGPU on GPU g, CUDA events on its stream   */
   uint64_t index_file_bytes, table_bytes, query_bytes, result_bytes;
+  double   context_init_s[16];    /* [g]: first use of GPU g by this process (CUDA context), before anything is copied */
 } fmgpu_transfer_stats_t;
 int32_t fmgpu_get_transfer_stats(fmgpu_transfer_stats_t *out);
 /* searchIndexGPU with an error code instead of exit(): FM_E_BAD_ARGUMENT when transferCPUtoGPU was not called for this pair */
@@ -257,6 +258,7 @@ int32_t fmgpu_search_index(void *index, void *queries, void *resIntervals);
 
 /* devices ---------------------------------------------------------------- */
 int32_t fmgpu_device_count(void);                 /* usable sm_100 devices; 0 if none */
+int32_t fmgpu_device_warmup(int32_t device);      /* creates the device's CUDA context (first use costs 0.3-0.4 s) */
 /* devices used by transferCPUtoGPU / searchIndexGPU.  Default: the list in
  * $FMGPU_DEVICES ("0,1,2"), else device 0. */
 int32_t fmgpu_set_devices(const int32_t *devices, int32_t ndevices);
@@ -449,6 +451,16 @@ int32_t fmgpu_locate_device(const fmgpu_index_t *idx, const uint32_t *d_results,
 /* the same for a shard (its own (L,R), its stream), positions [nqueries][max_hits] and hit counts to host memory */
 int32_t fmgpu_batch_locate(const fmgpu_index_t *idx, fmgpu_batch_t *b, uint32_t max_hits, uint32_t *h_positions, uint32_t *h_nhits);
 int32_t fmgpu_index_download_sa(const fmgpu_index_t *idx, uint32_t *h_sa);   /* bwtsize words */
+
+/* one-mismatch search (the reference matches exactly only) -------------------------------
+ * Every read is searched as it is and in all its 3 * len single-substitution variants, by the ordinary exact-match kernels
+ * of variant `v` (variants are generated and reduced on the device, in chunks).  d_out[q] = the exact interval, how many of
+ * the variants occur in the text, and their occurrences in total (saturating); d_variant_lr, when not NULL, receives all
+ * variant intervals: [q][j][2] with j = 3 * t + s for packed position t (base len-1-t of the read) changed to
+ * (code + 1 + s) & 3.  Synchronous (scratch is allocated and released inside).  Any read length the index serves. */
+typedef struct { uint32_t L, R, variants_found, occurrences_1mm; } fmgpu_mm1_t;
+int32_t fmgpu_search_device_mm1(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nqueries, uint32_t len, fmgpu_mm1_t *d_out,
+                                uint32_t *d_variant_lr, const fmgpu_variant_t *v, void *stream);
 
 /* HBM random-access roofline probe: independent uniformly random 16-byte
  * loads over a table of `table_bytes`, full occupancy.  Returns loads/s. */

@@ -83,7 +83,11 @@ class fmgpu_transfer_stats_t(C.Structure):
     _fields_ = [("ndev", C.c_int32), ("searches", C.c_int32), ("index_h2d_reblock_s", C.c_double), ("peer_copy_s", C.c_double * 16),
                 ("table_build_s", C.c_double * 16), ("queries_h2d_pack_s", C.c_double), ("results_d2h_s", C.c_double),
                 ("search_ms", C.c_float * 16), ("index_file_bytes", C.c_uint64), ("table_bytes", C.c_uint64),
-                ("query_bytes", C.c_uint64), ("result_bytes", C.c_uint64)]
+                ("query_bytes", C.c_uint64), ("result_bytes", C.c_uint64), ("context_init_s", C.c_double * 16)]
+
+
+class fmgpu_mm1_t(C.Structure):
+    _fields_ = [("L", C.c_uint32), ("R", C.c_uint32), ("variants_found", C.c_uint32), ("occurrences_1mm", C.c_uint32)]
 
 
 class fmgpu_pipeline_stats_t(C.Structure):
@@ -117,6 +121,7 @@ PROTOTYPES = {
     "freeResultsGPU": (C.c_int32, [_VPP]),
     # PART 2 -- thin C ABI to CUDA
     "fmgpu_device_count": (C.c_int32, []),
+    "fmgpu_device_warmup": (C.c_int32, [C.c_int32]),
     "fmgpu_set_devices": (C.c_int32, [C.POINTER(C.c_int32), C.c_int32]),
     "fmgpu_set_variant": (C.c_int32, [C.POINTER(fmgpu_variant_t)]),
     "fmgpu_last_error": (C.c_char_p, []),
@@ -172,6 +177,7 @@ PROTOTYPES = {
     "fmgpu_pipeline_get_stats": (C.c_int32, [_VP, C.POINTER(fmgpu_pipeline_stats_t)]),
     "fmgpu_pipeline_free": (C.c_int32, [_VPP]),
     "fmgpu_index_prepare": (C.c_int32, [_VP, C.c_uint32]),
+    "fmgpu_search_device_mm1": (C.c_int32, [_VP, _VP, C.c_uint64, C.c_uint32, _VP, _VP, C.POINTER(fmgpu_variant_t), _VP]),
     "fmgpu_set_table_budget": (C.c_int32, [C.c_uint64]),
     "fmgpu_get_transfer_stats": (C.c_int32, [C.POINTER(fmgpu_transfer_stats_t)]),
     "fmgpu_search_index": (C.c_int32, [_VP, _VP, _VP]),

@@ -44,6 +44,14 @@ int32_t fm_use_device(int device)
   return FM_SUCCESS;
 }
 
+extern "C" int32_t fmgpu_device_warmup(int32_t device)
+{
+  const int32_t rc = fm_use_device(device);
+  if (rc) return rc;
+  CU_TRY(cudaFree(0));
+  return FM_SUCCESS;
+}
+
 extern "C" uint32_t fmgpu_words_per_query(uint32_t len) { return (len + 15u) / 16u; }
 
 /* ------------------------------------------------------------------------ *
