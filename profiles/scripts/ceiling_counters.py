@@ -24,7 +24,7 @@ pkg.check(L.fmgpu_synth_reads_device(0, n, 1, nq, length, 2, 0, d_ascii.data_ptr
 wpq = L.fmgpu_words_per_query(length)
 d_packed = torch.empty(nq * wpq, dtype=torch.int32, device="cuda"); d_res = torch.zeros(2 * nq, dtype=torch.int32, device="cuda")
 pkg.check(L.fmgpu_pack_queries_device(0, d_ascii.data_ptr(), nq, length, d_packed.data_ptr(), stream), "pack"); torch.cuda.synchronize()
-v = pkg.variant(pkg.MODE_SPARSE, 4)
+v = pkg.variant(pkg.MODE_SPARSE, int(os.environ.get("FM_QPT", "0")))      # 0 = the launcher default (3 reads per lane group, static assignment on this text)
 out = {"setup_s": time.time() - t0, "sparse_bases": m.sparse_bases, "sparse_gb": m.sparse_bytes / 1e9}
 ts = []
 for _ in range(3):
