@@ -719,6 +719,19 @@ def main():
     host_bw_mine = L.fm_host_read_bandwidth(h_ascii.data_ptr(), h_ascii.numel(), 0, 3)
     host_bw = sum(all_ranks(host_bw_mine))                   # what the whole box delivered to all ranks at the same time
     barrier()
+    # ... and what the DMA engines pull out of that memory: the same buffer copied H2D by every rank at once, nothing else running
+    d_land = torch.empty(min(h_ascii.numel(), 1 << 29), dtype=torch.uint8, device="cuda")
+    d_land.copy_(h_ascii[: d_land.numel()], non_blocking=True)
+    barrier()
+    he0, he1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    he0.record()
+    for a in range(0, h_ascii.numel() - d_land.numel() + 1, d_land.numel()):
+        d_land.copy_(h_ascii[a:a + d_land.numel()], non_blocking=True)
+    he1.record(); torch.cuda.synchronize()
+    copied = (h_ascii.numel() // d_land.numel()) * d_land.numel()
+    h2d_bw = sum(all_ranks(copied / (he0.elapsed_time(he1) * 1e-3) / 1e9))
+    del d_land
+    barrier()
 
     # extra (not the headline): the same end-to-end call fed with reads that already are 2-bit packed on the host
     h_packed = torch.empty(nq * wpq, dtype=torch.int32, pin_memory=True)
@@ -865,6 +878,7 @@ def main():
                     "host_pack_threads_per_rank": int(L.fm_hostpack_threads()),
                     "host_ceiling": {"host_read_gbs": host_bw, "bytes_per_read": READ_LEN, "mqueries_per_s": ceiling_mq,
                                      "e2e_over_ceiling": (e2e_value / ceiling_mq) if ceiling_mq else None,
+                                     "pinned_h2d_gbs_all_ranks": h2d_bw,
                                      "how": "fm_host_read_bandwidth over the pinned ASCII buffer, all ranks at once, all host threads: every read costs its 100 bytes of host DRAM "
                                             "reads whoever fetches them (DMA engine or packer thread), so this is the bound of any feed of ASCII reads on this host"},
                     "note": "h2d_bytes_per_step counts the ASCII reads handed to the call; host-packed chunks cross PCIe as 2-bit (25 B/read)"},

@@ -116,9 +116,8 @@ static int32_t fm_index_from_wide_file(int device, uint32_t tag, uint32_t steps,
   if (ncounters != (ac ? nsym / 2 : nsym)) return fm_fail_msg(FM_E_UNSUPPORTED_INDEX, "counter count does not match k");
   const uint32_t nstd = (uint32_t)(((uint64_t) bwtsize + chunk - 1) / chunk);
   if (nentries != nstd + (ac ? 1u : 0u) || bwtsize < 2) return fm_fail_msg(FM_E_UNSUPPORTED_INDEX, "entry count does not match bwtsize/d");
-  uint32_t qstart, qmask;
+  uint32_t qmask = 0;
   {                                                          /* padding-entry quirk of a wide AltCounters file (any symbol) */
-    qstart = 0xFFFFFFFFu; qmask = 0;
     const uint32_t elast = (bwtsize - 1) / chunk;
     for (uint32_t s = 0; ac && s < steps; s++)
       if (dpos[s] / chunk == elast) {

@@ -36,7 +36,7 @@ def launches(tag):
         a = agg.setdefault(r[ix["Kernel Name"]], [0, 0.0]); a[0] += 1; a[1] += ns; total += ns
     with open(os.path.join(PR, f"{tag}_launches.md"), "w") as f:
         f.write(f"# {tag}: ncu launch list of `python bench.py --steps 2 --warmup 3` (1 GPU, 2 Gbp index, 10 M reads)\n\n"
-                "`ncu --metrics gpu__time_duration.sum --clock-control none -c 3000` -- per-launch times are cold-cache and serialised;\n"
+                "`ncu --metrics gpu__time_duration.sum --clock-control none -c 8000` (profiles/scripts/capture_ncu.sh) -- per-launch times are cold-cache and serialised;\n"
                 "compare SHARES.  Setup kernels (index build, re-block, probe, read synthesis) are outside bench.py's timed regions.\n\n"
                 "| total ms | launches | share | kernel |\n|---:|---:|---:|---|\n")
         for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -46,11 +46,11 @@ def launches(tag):
         # is launched there), the small grids are the 512 K-read chunks of the end-to-end pipeline
         per = collections.OrderedDict()
         for r in rows[1:]:
-            if r[ix["Metric Name"]] == "gpu__time_duration.sum" and "fm_search_sparse_kernel<2, 2, 4" in r[ix["Kernel Name"]]:
+            if r[ix["Metric Name"]] == "gpu__time_duration.sum" and "fm_search_sparse_kernel<2, 2, 3, 256, 4, 0>" in r[ix["Kernel Name"]]:
                 ns = float(r[ix["Metric Value"]]) * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}.get(r[ix["Metric Unit"]], 1)
                 per.setdefault(r[ix["Grid Size"]], []).append(ns)
         if per:
-            f.write("\n## The timed kernel, `fm_search_sparse_kernel<2, 2, 4, 256, 3, 0>`, by grid\n\n"
+            f.write("\n## The timed kernel, `fm_search_sparse_kernel<2, 2, 3, 256, 4, 0>`, by grid\n\n"
                     "| grid | launches | mean ms per launch | where |\n|---|---:|---:|---|\n")
             for g, v in sorted(per.items(), key=lambda kv: -max(kv[1])):
                 big = max(v) > 1e6
