@@ -286,7 +286,8 @@ int32_t fmgpu_index_alloc_like(int32_t device, const fmgpu_index_meta_t *meta, f
 /* Fused-step table, composed on the GPU from this replica's own block table: one fused step = fused_bases/k
  * reference LF steps (exactly), one 256-bit load per lane of a `lanes`-lane group per rank.  fused_bases 0 =
  * the widest of 4,3,2 that is a multiple of k and fits `budget_bytes` (0 = ~69 GB or free memory); lanes 0 = 2.
- * FM_E_NOT_IMPLEMENTED when nothing fits or the index carries the AltCounters padding quirk. */
+ * AltCounters files with an active padding quirk are served (a few phantom occurrences ride beside the bitmaps).
+ * FM_E_NOT_IMPLEMENTED when nothing fits. */
 int32_t fmgpu_index_fuse(fmgpu_index_t *idx, uint32_t fused_bases, uint32_t lanes, uint64_t budget_bytes);
 int32_t fmgpu_index_unfuse(fmgpu_index_t *idx);
 /* Sparse-step table, built on the GPU from this replica's own block table: one sparse step = sparse_bases/k

@@ -146,4 +146,68 @@ __device__ __forceinline__ uint32_t fm_quirk_delta(uint32_t quirk_mask, uint32_t
   return X >= quirk_start ? ((quirk_mask >> (2u * sigma)) & 3u) : 0u;
 }
 
+/* rank of the reference searcher this table reproduces: SB96 value + the AltCounters padding-quirk constant */
+__device__ __forceinline__ uint32_t fm_sb96_rank_q(const uint4 *__restrict__ blocks, uint32_t nblocks, uint32_t s, uint32_t X,
+                                                   uint32_t quirk_start, uint32_t quirk_mask)
+{
+  return fm_sb96_rank(blocks, nblocks, s, X) + fm_quirk_delta(quirk_mask, quirk_start, s, X);
+}
+
+
+/* a compose kernel standing on row quirk_start - 1 at hop `hop` with the symbols `acc` so far, for the chain of row `origin` */
+struct FmQuirkVisit { uint32_t origin, hop, acc; };
+
+/* Phantom occurrences of an active AltCounters quirk (one thread; a handful of chains).
+ * The quirked rank of symbol s is rank'(s, X) = rank(s, X) + delta_s [X >= Q]: as a counting function it is
+ * "base + #{ m in M_s : m < X }" with M_s = occ(s) plus delta_s extra copies of row Q - 1.  Composing such functions
+ * gives base + #{ elements < X } again, where an element is a chain  row -> s0 -> rank'-image -> s1 -> ...  and a chain
+ * may take, at any hop where it stands on row Q - 1, a phantom copy instead of the row's real symbol.  Chains through
+ * real symbols only are what the compose kernels (fm_sparse_compose_kernel, fm_fuse_compose_kernel) emit; this kernel enumerates every chain that takes at least
+ * one phantom copy (depth-first from the recorded visits of row Q - 1) and writes its (key, origin row) pair.
+ * Image of copy c of phantom symbol s at row Q - 1:  rank(s, Q - 1) + [real symbol of the row is s] + c. */
+static __global__ void fm_quirk_phantoms_kernel(const uint4 *__restrict__ blocks, uint32_t nblocks, const uint8_t *__restrict__ sym,
+                                          uint32_t kbits, uint32_t hops, uint32_t quirk_start, uint32_t quirk_mask,
+                                          const FmQuirkVisit *__restrict__ visits, uint32_t nvisits,
+                                          uint32_t *__restrict__ keys, uint32_t *__restrict__ rows, uint32_t max_out, uint32_t *__restrict__ nout)
+{
+  if (blockIdx.x || threadIdx.x) return;
+  const uint32_t Q1 = quirk_start - 1u, nsym_k = 1u << kbits;
+  struct Item { uint32_t origin, hop, acc, row, from_visit; };
+  Item stack[64];
+  uint32_t out = 0;
+  for (uint32_t v = 0; v < nvisits; v++) {
+    int sp = 0;
+    stack[sp++] = Item{ visits[v].origin, visits[v].hop, visits[v].acc, Q1, 1u };
+    while (sp) {
+      const Item it = stack[--sp];
+      if (it.hop == hops) {                                     /* a complete chain that used a phantom copy */
+        if (out < max_out) { keys[out] = it.acc; rows[out] = it.origin; }
+        out++;
+        continue;
+      }
+      /* the row's real symbol: only for chains that already took a phantom copy (the all-real chain of a recorded
+       * visit is the compose kernel's own output) */
+      if (!it.from_visit) {
+        const uint32_t s = sym[it.row];
+        if (s != FM_SYM_NONE && sp < 63) {
+          const uint32_t nrow = it.hop + 1 < hops ? fm_sb96_rank_q(blocks, nblocks, s, it.row, quirk_start, quirk_mask) : 0u;
+          stack[sp++] = Item{ it.origin, it.hop + 1, it.acc | (s << (kbits * it.hop)), nrow, 0u };
+        }
+      }
+      if (it.row != Q1) continue;
+      /* phantom copies at row Q - 1 */
+      const uint32_t real = sym[Q1];
+      for (uint32_t s = 0; s < nsym_k; s++) {
+        const uint32_t d = (quirk_mask >> (2u * s)) & 3u;
+        for (uint32_t c = 0; c < d && sp < 63; c++) {
+          const uint32_t nrow = fm_sb96_rank(blocks, nblocks, s, Q1) + (real == s ? 1u : 0u) + c;
+          stack[sp++] = Item{ it.origin, it.hop + 1, it.acc | (s << (kbits * it.hop)), nrow, 0u };
+        }
+      }
+    }
+  }
+  *nout = out;
+}
+
+
 #endif /* FM_DEVICE_CUH_ */

@@ -23,13 +23,15 @@
  * 2 Gbp, the edge of the flat part of the footprint curve); KF=3: 8.5 B/base; KF=2: 2.1 B/base.
  * Read lengths that are not a multiple of KF do their (len/k) % m leading steps on the SB96 table.
  *
- * Not available for AltCounters files that carry the padding-entry quirk (the composed function then has a
- * jump of 2 at one row and is not a bitmap); the plain kernels serve those.
+ * AltCounters files that carry the padding-entry quirk: the composed function then jumps by 2 at a few rows, which a
+ * bitmap cannot hold -- those phantom occurrences (at most FM_MAX_FUSED_PHANTOMS) ride in the kernel parameters.
  */
 #ifndef FM_FUSED_CUH_
 #define FM_FUSED_CUH_
 
 #include "fm_device.cuh"
+
+#define FM_MAX_FUSED_PHANTOMS 16u
 
 struct FmFusedParams {
   const uint4    *fblocks;    /* fused table                                                       */
@@ -51,6 +53,11 @@ struct FmFusedParams {
    * it replaces the L2-resident steps and the first DRAM step (two fetches) by one mostly-L2 lookup */
   const uint2 *start;
   uint32_t start_steps;       /* fused steps the table stands for (FM_START_BASES / KF), 0 = no table */
+  /* AltCounters padding-entry quirk (fm_device.cuh: fm_quirk_phantoms_kernel): the composed rank function gains one for every
+   * phantom occurrence (fused symbol, row) with row < X -- a handful of them, kept beside the bitmaps (a bit cannot be set
+   * twice); the SB96 leading steps add the per-symbol constant.  nph = 0 and quirk_mask = 0 for every other index. */
+  uint32_t quirk_start, quirk_mask;
+  uint32_t nph, ph_sym[FM_MAX_FUSED_PHANTOMS], ph_row[FM_MAX_FUSED_PHANTOMS];
 };
 
 #define FM_START_BASES 12u
@@ -155,8 +162,9 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_fused_kernel(const Fm
       const uint4 vL = fm_ldg16(base + bL);
       const uint4 vR = (bL == bR) ? vL : fm_ldg16(base + bR);
       if (COUNT && live[i] && lg == 0) nl_fetch += (bL == bR) ? 1 : 2;
-      L[i] = fm_block_rank(vL, L[i] - bL * FM_SB_ROWS);
-      R[i] = fm_block_rank(vR, R[i] - bR * FM_SB_ROWS);
+      const uint32_t nL = fm_block_rank(vL, L[i] - bL * FM_SB_ROWS) + fm_quirk_delta(p.quirk_mask, p.quirk_start, sig, L[i]);
+      const uint32_t nR = fm_block_rank(vR, R[i] - bR * FM_SB_ROWS) + fm_quirk_delta(p.quirk_mask, p.quirk_start, sig, R[i]);
+      L[i] = nL; R[i] = nR;
     }
   }
 
@@ -171,11 +179,16 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_fused_kernel(const Fm
   }
 
   for (uint32_t step = step0; step < p.nfused; step++, pos += FBITS) {
-    uint32_t wL[QPT][8], wR[QPT][8], rL[QPT], rR[QPT];
+    uint32_t wL[QPT][8], wR[QPT][8], rL[QPT], rR[QPT], phL[QPT], phR[QPT];
     bool same[QPT];
     #pragma unroll
     for (int i = 0; i < QPT; i++) {
       const uint32_t sig = fm_read_field(myq[i], pos, FMASK);
+      phL[i] = 0u; phR[i] = 0u;
+      if (p.nph) {                                             /* quirk indexes only: phantom occurrences below L / R */
+        for (uint32_t j = 0; j < p.nph; j++)
+          if (p.ph_sym[j] == sig) { phL[i] += p.ph_row[j] < L[i] ? 1u : 0u; phR[i] += p.ph_row[j] < R[i] ? 1u : 0u; }
+      }
       const uint32_t bL = FmFusedGeom<LANES>::div(L[i]), bR = FmFusedGeom<LANES>::div(R[i]);
       rL[i] = L[i] - bL * ROWS; rR[i] = R[i] - bR * ROWS;
       const uint4 *base = p.fblocks + ((size_t) sig * p.nfblocks) * (2 * LANES) + 2 * lg;
@@ -195,8 +208,8 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_fused_kernel(const Fm
       if (lg == 0) { cL = wL[i][0]; cR = wR[i][0]; wL[i][0] = 0u; wR[i][0] = 0u; }   /* word 0 of the block is the sampled rank */
       cL += fm_fused_partial(wL[i], rL[i], lg);
       cR += fm_fused_partial(wR[i], rR[i], lg);
-      L[i] = fm_group_sum<LANES>(cL);
-      R[i] = fm_group_sum<LANES>(cR);
+      L[i] = fm_group_sum<LANES>(cL) + phL[i];
+      R[i] = fm_group_sum<LANES>(cR) + phR[i];
     }
   }
 
@@ -251,7 +264,8 @@ __global__ void fm_fuse_symbols_kernel(const uint4 *__restrict__ blocks, uint32_
 /* fused symbol of every row: follow the index's own LF mapping hops-1 times */
 __global__ void fm_fuse_compose_kernel(const uint4 *__restrict__ blocks, uint32_t nblocks, const uint8_t *__restrict__ sym,
                                        uint32_t bwtsize, uint32_t kbits, uint32_t hops, uint64_t nrows_alloc,
-                                       uint16_t *__restrict__ fsym)
+                                       uint32_t quirk_start, uint32_t quirk_mask, FmQuirkVisit *__restrict__ visits, uint32_t *__restrict__ nvisits,
+                                       uint32_t max_visits, uint16_t *__restrict__ fsym)
 {
   const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows_alloc) return;
@@ -260,10 +274,14 @@ __global__ void fm_fuse_compose_kernel(const uint4 *__restrict__ blocks, uint32_
     uint32_t row = (uint32_t) i, acc = 0;
     bool ok = true;
     for (uint32_t h = 0; h < hops; h++) {
+      if (quirk_mask && quirk_start != 0u && row == quirk_start - 1u) {   /* phantom copies may branch off here (fm_quirk_phantoms_kernel) */
+        const uint32_t slot = atomicAdd(nvisits, 1u);
+        if (slot < max_visits) { visits[slot].origin = (uint32_t) i; visits[slot].hop = h; visits[slot].acc = acc; }
+      }
       const uint32_t s = sym[row];
       if (s == FM_SYM_NONE) { ok = false; break; }
       acc |= s << (kbits * h);
-      if (h + 1 < hops) row = fm_sb96_rank(blocks, nblocks, s, row);       /* LF(row) */
+      if (h + 1 < hops) row = fm_sb96_rank_q(blocks, nblocks, s, row, quirk_start, quirk_mask);       /* LF(row), as the file's searcher computes it */
     }
     if (ok) f = acc;
   }
@@ -305,14 +323,15 @@ __global__ void __launch_bounds__(256) fm_fuse_write_kernel(const uint16_t *__re
  * the exclusive prefix sum of the per-block counts */
 template <int LANES>
 __global__ void __launch_bounds__(1024) fm_fuse_scan_kernel(const uint4 *__restrict__ blocks, uint32_t nblocks, uint32_t kbits,
-                                                            uint32_t hops, uint32_t nfblocks, uint4 *__restrict__ fblocks)
+                                                            uint32_t hops, uint32_t nfblocks, uint32_t quirk_start, uint32_t quirk_mask,
+                                                            uint4 *__restrict__ fblocks)
 {
   __shared__ uint32_t warp_tot[32];
   __shared__ uint32_t carry;
   const uint32_t sigma = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     uint32_t x = 0;
-    for (uint32_t h = 0; h < hops; h++) x = fm_sb96_rank(blocks, nblocks, (sigma >> (kbits * h)) & ((1u << kbits) - 1u), x);
+    for (uint32_t h = 0; h < hops; h++) x = fm_sb96_rank_q(blocks, nblocks, (sigma >> (kbits * h)) & ((1u << kbits) - 1u), x, quirk_start, quirk_mask);
     carry = x;
   }
   __syncthreads();

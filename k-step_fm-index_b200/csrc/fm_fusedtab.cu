@@ -27,7 +27,7 @@ static cudaError_t fm_fuse_build(const fmgpu_index_t *idx, const uint16_t *fsym,
   fm_fuse_write_kernel<LANES><<<nfb, 256, 256 * 8 * LANES * 4>>>(fsym, nfsym, nfb, fblocks);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  fm_fuse_scan_kernel<LANES><<<nfsym, 1024>>>(idx->blocks, idx->meta.nblocks, kbits, hops, nfb, fblocks);
+  fm_fuse_scan_kernel<LANES><<<nfsym, 1024>>>(idx->blocks, idx->meta.nblocks, kbits, hops, nfb, idx->meta.quirk_start, idx->meta.quirk_mask, fblocks);
   return cudaGetLastError();
 }
 
@@ -35,7 +35,6 @@ extern "C" int32_t fmgpu_index_fuse(fmgpu_index_t *idx, uint32_t fused_bases, ui
 {
   if (!idx) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null index");
   if (idx->fblocks) return FM_SUCCESS;
-  if (idx->meta.quirk_mask) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "fused steps are unavailable for an AltCounters index carrying the padding-entry quirk");
   CU_TRY(cudaSetDevice(idx->device));
   const uint32_t k = idx->meta.steps;
   if (lanes == 0) lanes = 2;
@@ -70,9 +69,42 @@ extern "C" int32_t fmgpu_index_fuse(fmgpu_index_t *idx, uint32_t fused_bases, ui
   if (e == cudaSuccess) {
     e = fm_row_symbols(idx, nrows, sym);
   }
+  /* AltCounters padding quirk: the chains follow the quirked rank; the phantom occurrences are listed beside the bitmaps */
+  const uint32_t qstart = idx->meta.quirk_start, qmask = idx->meta.quirk_mask, max_visits = 1024;
+  FmQuirkVisit *visits = NULL; uint32_t *d_cnt = NULL, *ph_keys = NULL, *ph_rows = NULL, hcnt[2] = { 0, 0 };
+  fm_phantoms ph; memset(&ph, 0, sizeof ph);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &visits, sizeof(FmQuirkVisit) * max_visits);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &d_cnt, 8);
+  if (e == cudaSuccess) e = cudaMemset(d_cnt, 0, 8);
   if (e == cudaSuccess) {
-    fm_fuse_compose_kernel<<<(unsigned)((nrows + 255) / 256), 256>>>(idx->blocks, idx->meta.nblocks, sym, idx->meta.bwtsize, kbits, hops, nrows, fsym);
+    fm_fuse_compose_kernel<<<(unsigned)((nrows + 255) / 256), 256>>>(idx->blocks, idx->meta.nblocks, sym, idx->meta.bwtsize, kbits, hops, nrows,
+                                                                       qstart, qmask, visits, d_cnt, max_visits, fsym);
     e = cudaGetLastError();
+  }
+  bool too_many = false;
+  if (e == cudaSuccess && qmask && qstart != 0u) {
+    e = cudaMemcpy(hcnt, d_cnt, 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && hcnt[0] > max_visits) too_many = true;
+    if (e == cudaSuccess && hcnt[0] && !too_many) {
+      e = cudaMalloc((void **) &ph_keys, 4 * 256);
+      if (e == cudaSuccess) e = cudaMalloc((void **) &ph_rows, 4 * 256);
+      if (e == cudaSuccess) {
+        fm_quirk_phantoms_kernel<<<1, 1>>>(idx->blocks, idx->meta.nblocks, sym, kbits, hops, qstart, qmask, visits, hcnt[0], ph_keys, ph_rows, 256, d_cnt + 1);
+        e = cudaGetLastError();
+      }
+      if (e == cudaSuccess) e = cudaMemcpy(hcnt + 1, d_cnt + 1, 4, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess && hcnt[1] > FM_MAX_PHANTOMS) too_many = true;
+      if (e == cudaSuccess && !too_many && hcnt[1]) {
+        ph.n = hcnt[1];
+        e = cudaMemcpy(ph.sym, ph_keys, 4 * ph.n, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(ph.row, ph_rows, 4 * ph.n, cudaMemcpyDeviceToHost);
+      }
+    }
+  }
+  cudaFree(visits); cudaFree(d_cnt); cudaFree(ph_keys); cudaFree(ph_rows);
+  if (e == cudaSuccess && too_many) {
+    cudaFree(sym); cudaFree(fsym); cudaFree(fblocks);
+    return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "too many phantom occurrences for the fused-step table (AltCounters padding quirk); the sparse-step table serves this index");
   }
   if (e == cudaSuccess) e = lanes == 1 ? fm_fuse_build<1>(idx, fsym, nfsym, nfb, kbits, hops, fblocks)
                           : lanes == 2 ? fm_fuse_build<2>(idx, fsym, nfsym, nfb, kbits, hops, fblocks)
@@ -85,7 +117,7 @@ extern "C" int32_t fmgpu_index_fuse(fmgpu_index_t *idx, uint32_t fused_bases, ui
     if (e == cudaErrorMemoryAllocation) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "not enough device memory for the fused-step table (the plain kernels still serve this index)");
     return fm_fail(e, "fmgpu_index_fuse", __FILE__, __LINE__);
   }
-  idx->fblocks = fblocks; idx->nfblocks = nfb;
+  idx->fblocks = fblocks; idx->nfblocks = nfb; idx->fphantoms = ph;
   idx->meta.fused_bases = kf; idx->meta.fused_lanes = lanes; idx->meta.fused_bytes = fbytes;
 
   /* start table: the fused kernel itself searches all 4^12 12-mers once (a packed 12-mer IS its 24-bit key);
@@ -115,6 +147,7 @@ extern "C" int32_t fmgpu_index_unfuse(fmgpu_index_t *idx)
 {
   if (!idx) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null index");
   if (idx->fblocks || idx->start) { CU_TRY(cudaSetDevice(idx->device)); cudaFree(idx->fblocks); cudaFree(idx->start); idx->fblocks = NULL; idx->start = NULL; }
+  memset(&idx->fphantoms, 0, sizeof idx->fphantoms);
   idx->nfblocks = 0; idx->meta.fused_bases = 0; idx->meta.fused_lanes = 0; idx->meta.fused_bytes = 0; idx->meta.start_bases = 0;
   return FM_SUCCESS;
 }
@@ -159,6 +192,8 @@ int32_t fm_launch_fused(const fmgpu_index_t *idx, const uint32_t *d_packed, uint
   p.wpq = fmgpu_words_per_query(len); p.wpq_pad = (p.wpq + 1) | 1u; p.bwtsize = idx->meta.bwtsize;
   p.fetch_counters = d_counters;
   p.start = idx->start; p.start_steps = idx->start ? FM_START_BASES / kf : 0u;
+  p.quirk_start = idx->meta.quirk_start; p.quirk_mask = idx->meta.quirk_mask; p.nph = idx->fphantoms.n;
+  for (uint32_t j = 0; j < FM_MAX_FUSED_PHANTOMS; j++) { p.ph_sym[j] = j < p.nph ? idx->fphantoms.sym[j] : 0u; p.ph_row[j] = j < p.nph ? idx->fphantoms.row[j] : 0u; }
   p.has_tail = len % k; p.tail_row = idx->meta.tail_row; p.tail_base = idx->meta.tail_base;
   for (int c = 0; c < 4; c++) p.tail_const[c] = idx->meta.tail_const[c];
   p.tail1 = p.has_tail ? idx->tail1 : NULL;

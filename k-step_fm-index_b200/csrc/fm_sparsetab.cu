@@ -94,7 +94,7 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
   (void) worst_tree;
 
   uint8_t *sym = NULL; uint32_t *keys = NULL, *rows = NULL, *keys2 = NULL, *rows2 = NULL, *symstart = NULL, *rank0 = NULL, *ext = NULL, *extoff = NULL;
-  uint4 *sblocks = NULL; void *tmp = NULL; unsigned long long *d_stats = NULL; FmSparseVisit *visits = NULL; uint32_t *d_cnt = NULL;
+  uint4 *sblocks = NULL; void *tmp = NULL; unsigned long long *d_stats = NULL; FmQuirkVisit *visits = NULL; uint32_t *d_cnt = NULL;
   size_t tmp_bytes = 0, tmp2 = 0;
   unsigned long long stats[3] = { 0, 0, 0 };
   uint32_t hcnt[2] = { 0, 0 }, total_ext = 0;
@@ -109,7 +109,7 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
   if (e == cudaSuccess) e = cudaMalloc((void **) &rank0, 4ull * nsym);
   if (e == cudaSuccess) e = cudaMalloc((void **) &d_stats, 24);
   if (e == cudaSuccess) e = cudaMalloc((void **) &d_cnt, 8);
-  if (e == cudaSuccess) e = cudaMalloc((void **) &visits, sizeof(FmSparseVisit) * max_visits);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &visits, sizeof(FmQuirkVisit) * max_visits);
   if (e == cudaSuccess) e = cudaMemset(d_stats, 0, 24);
   if (e == cudaSuccess) e = cudaMemset(d_cnt, 0, 8);
   if (e == cudaSuccess) e = fm_row_symbols(idx, nrows, sym);
@@ -123,7 +123,7 @@ extern "C" int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_base
     e = cudaMemcpy(hcnt, d_cnt, 4, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && hcnt[0] > max_visits) e = cudaErrorInvalidValue;
     if (e == cudaSuccess && hcnt[0]) {
-      fm_sparse_phantoms_kernel<<<1, 1>>>(idx->blocks, idx->meta.nblocks, sym, kbits, hops, qstart, qmask, visits, hcnt[0],
+      fm_quirk_phantoms_kernel<<<1, 1>>>(idx->blocks, idx->meta.nblocks, sym, kbits, hops, qstart, qmask, visits, hcnt[0],
                                           keys + n, rows + n, max_ph, d_cnt + 1);
       e = cudaGetLastError();
       if (e == cudaSuccess) e = cudaMemcpy(hcnt + 1, d_cnt + 1, 4, cudaMemcpyDeviceToHost);

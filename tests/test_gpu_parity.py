@@ -423,7 +423,7 @@ def test_config3_full_size_against_reference_checksums(pkg):
 # --------------------------------------------------------------------------- #
 # fused-step layout (fm_fused.cuh): up to 4 bases per rank, composed from the index's own LF mapping
 # --------------------------------------------------------------------------- #
-@pytest.mark.parametrize("path", [p for p in GOLDEN if "quirk" not in p], ids=lambda p: os.path.basename(p))
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p))
 def test_fused_steps_all_widths(pkg, path):
     g = np.load(path)
     reads, length, k = g["reads"], int(g["length"]), int(g["k"])
@@ -465,10 +465,7 @@ def test_fused_steps_read_lengths(pkg, k, length):
 
 def test_fused_unavailable_cases(pkg):
     g = np.load(os.path.join(helpers.ROOT, "tests", "golden", "quirk_k2_n124.npz"))
-    idx = pkg.DeviceIndex.from_image(g["image_200"])           # AltCounters padding quirk: not representable
-    with pytest.raises(pkg.FMError) as ei:
-        idx.fuse()
-    assert ei.value.code == 19
+    idx = pkg.DeviceIndex.from_image(g["image_200"])           # (AltCounters padding quirk: fusable since round 2, see the goldens test)
     b = pkg.DeviceBatch(0, 4, 8, 2)
     b.upload_ascii(g["reads"][:32])
     with pytest.raises(pkg.FMError) as ei:
@@ -648,9 +645,8 @@ def test_fuzz_tiny_references(pkg, tmp_path, case):
             idx = pkg.DeviceIndex.from_image(image)
             modes = [pkg.MODE_TASK, pkg.MODE_COOP, pkg.MODE_SPARSE]
             idx.sparsify(2 * k * (1 + case % 3), 0, 2 + 2 * (case % 2))  # sparse-step table (quirk files included: phantom occurrences)
-            if idx.meta.quirk_mask == 0:
-                idx.fuse(4, 2)
-                modes.append(pkg.MODE_FUSED)
+            idx.fuse(4, 2)                                           # fused-step table (quirk files: phantom occurrences in the kernel parameters)
+            modes.append(pkg.MODE_FUSED)
             batch = pkg.DeviceBatch(0, reads.size // length, length, k)
             batch.upload_ascii(reads)
             for mode in modes:

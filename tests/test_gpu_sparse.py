@@ -272,6 +272,12 @@ def test_sparse_quirk_fuzz_against_the_altcounters_reference(pkg, tmp_path):
                     idx.free()
                     continue
                 active += 1
+                for kf, fl in (((2, 1), (3, 2), (4, 2), (4, 4)) if k == 1 else ((4, 1), (4, 2), (4, 4))):
+                    idx.fuse(kf, fl)                                  # the fused-step table carries the quirk as a phantom list
+                    for qpt in (1, 2):
+                        batch.search(idx, pkg.variant(pkg.MODE_FUSED, qpt))
+                        assert np.array_equal(batch.download(), want), f"case {case}: k={k} d={d} n={n} len={length} tag={tag} fused kf={kf} lanes={fl}"
+                    idx.unfuse()
                 for ks in ((2, 3, 4, 6) if k == 1 else (4, 6, 8)):
                     for lanes, lam in ((2, 0), (2, 1), (4, 0)):
                         idx.sparsify(ks, lam, lanes)
