@@ -10,7 +10,10 @@
  */
 #include "fm_internal.h"
 #include <time.h>
+#include <atomic>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #define FM_PIPE_STREAMS 4
 
@@ -161,68 +164,93 @@ extern "C" int32_t fmgpu_pipeline_search_host(fmgpu_pipeline_t *pp, fmgpu_index_
    * CPU by itself and a slower CPU shifts it to the link. */
   for (int g = 0; g < nrep; g++)
     for (int s = 0; s < FM_PIPE_STREAMS; s++) pp->lane[replicas[g]->device][s].h2d_pending = 0;
-  uint64_t c = 0, n_host = 0, n_link = 0;
-  for (uint64_t q0 = 0; q0 < nq; q0 += chunk, c++) {
-    const uint64_t n = (nq - q0 < chunk) ? nq - q0 : chunk;
-    const int g = (int)(c % nrep), s = (int)((c / nrep) % FM_PIPE_STREAMS);
-    const fmgpu_index_t *idx = replicas[g];
-    fm_pipe_lane *ln = &pp->lane[idx->device][s];
-    PIPE_TRY(cudaSetDevice(idx->device));
-    bool on_host = (feed == FMGPU_FEED_HOSTPACK);
-    if (feed == FMGPU_FEED_HYBRID) {
-      uint64_t pending = 0;
-      for (int t = 0; t < FM_PIPE_STREAMS; t++) {
-        fm_pipe_lane *o = &pp->lane[idx->device][t];
-        if (o->h2d_pending && cudaEventQuery(o->h2d_done) == cudaSuccess) o->h2d_pending = 0;
-        pending += o->h2d_pending;
-      }
-      cudaGetLastError();                                             /* cudaErrorNotReady from the queries is not an error */
-      double need = FM_H2D_BYTES_PER_S * pp->pack_s_per_read * (double) n;   /* bytes the link moves while one chunk is packed */
-      const double lo = 0.5 * (double)(n * len), hi = 2.0 * (double)(n * len);
-      need = need < lo ? lo : (need > hi ? hi : need);
-      on_host = (double) pending >= need;
-    }
-    if (on_host) {
-      PIPE_TRY(cudaEventSynchronize(ln->h2d_done));                   /* staging buffer free again? */
-      ln->h2d_pending = 0;
-      const double t0 = fm_now();
-      /* the host only streams ASCII -> 2 bit (64 bases per AVX-512 iteration, no per-read work);
-       * cutting into reads, reversal and word alignment happen on the GPU (fm_unstream_kernel) */
-      const uint64_t sbytes = (((n * len + 3) / 4) + 19) & ~15ull;
-      fm_hostpack_stream(h_ascii + q0 * len, n * len, (unsigned char *) ln->h_packed, 0);
-      if (n >= 4096) pp->pack_s_per_read = 0.75 * pp->pack_s_per_read + 0.25 * (fm_now() - t0) / (double) n;
-      PIPE_TRY(cudaMemcpyAsync(ln->d_ascii, ln->h_packed, sbytes, cudaMemcpyHostToDevice, ln->stream));
-      PIPE_TRY(cudaEventRecord(ln->h2d_done, ln->stream));
-      ln->h2d_pending += sbytes;
-      rc = fmgpu_unstream_device(idx->device, (const uint32_t *) ln->d_ascii, n, len, ln->d_packed, ln->stream);
-      if (rc) goto fail;
-      n_host += n;
-    } else {
-      PIPE_TRY(cudaMemcpyAsync(ln->d_ascii, h_ascii + q0 * len, n * len, cudaMemcpyHostToDevice, ln->stream));
-      PIPE_TRY(cudaEventRecord(ln->h2d_done, ln->stream));
-      ln->h2d_pending += n * len;
-      rc = fmgpu_pack_queries_device(idx->device, ln->d_ascii, n, len, ln->d_packed, ln->stream);
-      if (rc) goto fail;
-      n_link += n;
-    }
-    rc = fm_launch_search(idx, ln->d_packed, n, len, ln->d_results, v, ln->stream, NULL);
-    if (rc) goto fail;
-    PIPE_TRY(cudaMemcpyAsync(h_results + 2 * q0, ln->d_results, n * 8, cudaMemcpyDeviceToHost, ln->stream));
-  }
-  rc = fm_pipe_drain(pp, replicas, nrep);
-  if (rc) return rc;
+  /* one feeder per GPU: with several replicas every GPU's chunks (c = g, g + nrep, ...) are issued by their own host thread,
+   * so that no link waits for the thread that is busy packing or queueing for another GPU (8 GPUs, one process: one issuing
+   * thread was the limit).  The packer threads of the box are split between the feeders. */
   {
+    const uint64_t nchunks = (nq + chunk - 1) / chunk;
+    const int pack_threads = nrep > 1 ? (fm_hostpack_threads() / nrep > 0 ? fm_hostpack_threads() / nrep : 1) : 0;
+    std::atomic<uint64_t> n_host(0), n_link(0);
+    std::atomic<int32_t> first_rc(FM_SUCCESS);
+    char first_err[512] = "";
+    std::mutex err_mutex;
+    auto feeder = [&](int g) {
+      const fmgpu_index_t *idx = replicas[g];
+      int32_t frc = FM_SUCCESS;
+      cudaError_t fe = cudaSetDevice(idx->device);
+      if (fe != cudaSuccess) frc = fm_fail(fe, "cudaSetDevice(pipeline feeder)", __FILE__, __LINE__);
+      for (uint64_t c = (uint64_t) g; c < nchunks && frc == FM_SUCCESS && first_rc.load() == FM_SUCCESS; c += (uint64_t) nrep) {
+        const uint64_t q0 = c * chunk, n = (nq - q0 < chunk) ? nq - q0 : chunk;
+        fm_pipe_lane *ln = &pp->lane[idx->device][(c / nrep) % FM_PIPE_STREAMS];
+        bool on_host = (feed == FMGPU_FEED_HOSTPACK);
+        if (feed == FMGPU_FEED_HYBRID) {
+          uint64_t pending = 0;
+          for (int t = 0; t < FM_PIPE_STREAMS; t++) {
+            fm_pipe_lane *o = &pp->lane[idx->device][t];
+            if (o->h2d_pending && cudaEventQuery(o->h2d_done) == cudaSuccess) o->h2d_pending = 0;
+            pending += o->h2d_pending;
+          }
+          cudaGetLastError();                                         /* cudaErrorNotReady from the queries is not an error */
+          double need = FM_H2D_BYTES_PER_S * pp->pack_s_per_read * (double) n;   /* bytes the link moves while one chunk is packed */
+          const double lo = 0.5 * (double)(n * len), hi = 2.0 * (double)(n * len);
+          need = need < lo ? lo : (need > hi ? hi : need);
+          on_host = (double) pending >= need;
+        }
+#define FEED_TRY(call) { fe = (call); if (fe != cudaSuccess) { frc = fm_fail(fe, #call, __FILE__, __LINE__); break; } }
+        if (on_host) {
+          FEED_TRY(cudaEventSynchronize(ln->h2d_done));               /* staging buffer free again? */
+          ln->h2d_pending = 0;
+          const double t0 = fm_now();
+          /* the host only streams ASCII -> 2 bit (64 bases per AVX-512 iteration, no per-read work);
+           * cutting into reads, reversal and word alignment happen on the GPU (fm_unstream_kernel) */
+          const uint64_t sbytes = (((n * len + 3) / 4) + 19) & ~15ull;
+          fm_hostpack_stream(h_ascii + q0 * len, n * len, (unsigned char *) ln->h_packed, pack_threads);
+          if (n >= 4096) pp->pack_s_per_read = 0.75 * pp->pack_s_per_read + 0.25 * (fm_now() - t0) / (double) n;   /* per feeder: the link it competes with is its own GPU's */
+          FEED_TRY(cudaMemcpyAsync(ln->d_ascii, ln->h_packed, sbytes, cudaMemcpyHostToDevice, ln->stream));
+          FEED_TRY(cudaEventRecord(ln->h2d_done, ln->stream));
+          ln->h2d_pending += sbytes;
+          frc = fmgpu_unstream_device(idx->device, (const uint32_t *) ln->d_ascii, n, len, ln->d_packed, ln->stream);
+          if (frc) break;
+          n_host += n;
+        } else {
+          FEED_TRY(cudaMemcpyAsync(ln->d_ascii, h_ascii + q0 * len, n * len, cudaMemcpyHostToDevice, ln->stream));
+          FEED_TRY(cudaEventRecord(ln->h2d_done, ln->stream));
+          ln->h2d_pending += n * len;
+          frc = fmgpu_pack_queries_device(idx->device, ln->d_ascii, n, len, ln->d_packed, ln->stream);
+          if (frc) break;
+          n_link += n;
+        }
+        frc = fm_launch_search(idx, ln->d_packed, n, len, ln->d_results, v, ln->stream, NULL);
+        if (frc) break;
+        FEED_TRY(cudaMemcpyAsync(h_results + 2 * q0, ln->d_results, n * 8, cudaMemcpyDeviceToHost, ln->stream));
+#undef FEED_TRY
+      }
+      if (frc != FM_SUCCESS) {                                        /* the message lives in this thread: hand it to the caller's */
+        std::lock_guard<std::mutex> lock(err_mutex);
+        if (first_rc.load() == FM_SUCCESS) { first_rc.store(frc); snprintf(first_err, sizeof first_err, "%s", fmgpu_last_error()); }
+      }
+    };
+    if (nrep == 1) feeder(0);
+    else {
+      std::vector<std::thread> th;
+      for (int g = 0; g < nrep; g++) th.emplace_back(feeder, g);
+      for (auto &t : th) t.join();
+    }
+    rc = first_rc.load();
+    if (rc != FM_SUCCESS) {
+      fm_pipe_drain(pp, replicas, nrep);                              /* queued copies still touch the caller's buffers */
+      cudaGetLastError();
+      return fm_fail_msg(rc, first_err);
+    }
+    rc = fm_pipe_drain(pp, replicas, nrep);
+    if (rc) return rc;
     const double dt = fm_now() - t_call;
     if (probe && !pp->allocated) pp->feed_rate[feed] = (double) nq / dt;   /* self-tuning of the auto feed */
     pp->stats.calls += 1; pp->stats.last_feed = feed; pp->stats.last_seconds = dt;
-    pp->stats.last_reads_host_packed = n_host; pp->stats.last_reads_ascii_over_link = n_link;
+    pp->stats.last_reads_host_packed = n_host.load(); pp->stats.last_reads_ascii_over_link = n_link.load();
     pp->stats.host_pack_seconds_per_read = pp->pack_s_per_read;
   }
   return FM_SUCCESS;
-fail:
-  fm_pipe_drain(pp, replicas, nrep);                                  /* queued copies still touch the caller's buffers */
-  cudaGetLastError();
-  return rc;
 }
 
 /* Same pipeline for reads that already are 2-bit packed on the host (binary read format: per-read reversed
