@@ -29,8 +29,9 @@ with open(os.path.join(PR, "r02_dropin_multigpu.md"), "w") as f:
     for p in par:
         f.write(f"**Parity**: {p['what']}: {p['reads_checked']} reads over {p['shards']} shards, identical = **{p['identical']}**.  "
                 f"All {len(runs)} runs wrote the same `.res.gpu` ({len(summary['distinct_res_gpu_md5'])} distinct md5), the reference's own main() included.\n\n")
-    f.write("Notes.  The index H2D runs at ~11 GB/s because `loadIndex` keeps the reference's `malloc`ed (pageable) buffer; it is one 3 GB copy per run.  The first peer "
-            "copy of a process includes enabling peer access.  `TIME:` is what the reference prints: wall clock of `searchIndexGPU` (all shards launched, then "
+    f.write("Notes.  The index H2D runs at ~11 GB/s because `loadIndex` keeps the reference's `malloc`ed (pageable) buffer; it is one 3 GB copy per run.  In these two command-line runs the peer-copy "
+            "column still includes the first use of each GPU by the process (CUDA context creation, 0.3-0.4 s); inside a warm process the same copies take 9.4-10.6 ms "
+            "(`r02_config5_n8.md`), and `transferCPUtoGPU` now creates the contexts first and reports them separately (`context_init_s`).  `TIME:` is what the reference prints: wall clock of `searchIndexGPU` (all shards launched, then "
             "waited for), so it contains 8 launches and 8 stream synchronisations (~0.1 ms); the CUDA-event column is the kernels alone.  GPUs of one box differ by up "
             "to 4 % at the same 1965 MHz (1.90 vs 1.98 ms for 12.5 M reads): the slowest one sets the pace -- this is also the 'N=1 -> N>=2 step' of round 1's "
             "scaling table (`bench.py` now prints `per_rank.ms_per_step`).\n")
