@@ -377,7 +377,7 @@ int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_packed, uin
     if (k == 2) dfn = lanes == 4 ? fm_pick_sparse_dyn<2, 4>(q) : fm_pick_sparse_dyn<2, 2>(q);
     else        dfn = lanes == 4 ? fm_pick_sparse_dyn<1, 4>(q) : fm_pick_sparse_dyn<1, 2>(q);
     const char *renv = getenv("FMGPU_SPARSE_ROUNDS");
-    uint32_t rounds = renv && *renv && atoi(renv) >= 1 ? (uint32_t) atoi(renv) : 4u, rpc; size_t dsmem;
+    uint32_t rounds = renv && *renv && atoi(renv) >= 1 ? (uint32_t) atoi(renv) : (q == 1 ? 8u : 4u), rpc; size_t dsmem;   /* profiles/r02_skewed_text.md, "rounds" */
     for (;;) {
       rpc = (256 / lanes) * q * rounds;
       dsmem = 16 + ((size_t) rpc * p.wpq + 4) * 4;

@@ -137,10 +137,12 @@ for ks, lam, lanes in [tuple(int(x) for x in c.split(":")) for c in os.environ.g
     a, s, o = C.c_uint64(), C.c_uint64(), C.c_uint64()
     pkg.check(L.fmgpu_count_fetches_sparse_device(idx.handle, d_packed.data_ptr(), nq, length, d_res.data_ptr(), stream, C.byref(a), C.byref(s), C.byref(o)), "count")
     probe = pkg.gather_probe(0, int(m.sparse_bytes), 256, 2)
-    for dyn, qpt in ((0, 4), (0, 2), (1, 4), (1, 3), (1, 2), (1, 1)):
+    rounds_list = [int(x) for x in os.environ.get("FM_ROUNDS", "0").split(",")]
+    for dyn, qpt, rounds in [(0, 4, 0), (0, 2, 0)] + [(1, q, r) for r in rounds_list for q in (4, 3, 2, 1)]:
         os.environ["FMGPU_SPARSE_DYNAMIC"] = str(dyn)
+        if rounds: os.environ["FMGPU_SPARSE_ROUNDS"] = str(rounds)
         ms = run(pkg.variant(pkg.MODE_SPARSE, qpt))
-        emit(what="sparse", bases=m.sparse_bases, lam=m.sparse_lambda, lanes=m.sparse_lanes, qpt=qpt, dynamic_assignment=dyn, ms=ms, mq_per_s=nq / ms / 1e3, equals_plain=bool(torch.equal(d_res, want)),
+        emit(what="sparse", bases=m.sparse_bases, lam=m.sparse_lambda, lanes=m.sparse_lanes, qpt=qpt, dynamic_assignment=dyn, rounds=rounds or 4, ms=ms, mq_per_s=nq / ms / 1e3, equals_plain=bool(torch.equal(d_res, want)),
              grid_fetches_per_read=a.value / nq, tree_fetches_per_read=o.value / nq, sb96_blocks_per_read=s.value / nq,
              fetches_per_s=(a.value + o.value + s.value) / (ms * 1e-3), probe_per_s=probe, fetch_rate_over_probe=(a.value + o.value + s.value) / (ms * 1e-3) / probe)
     idx.unsparsify()
