@@ -177,9 +177,10 @@ typedef struct {
                                  block fetch shared through warp shuffles;
                                  FMGPU_MODE_FUSED: fused-step table (fmgpu_index_fuse): a lane group fetches one
                                  32/64/128-byte block with 256-bit loads and consumes up to 4 bases per step;
-                                 FMGPU_MODE_SPARSE: sparse-step table (fmgpu_index_sparsify): one 128-byte block
-                                 of occurrence rows per fetch, up to 14 bases per step                         */
-  int32_t queries_per_thread; /* independent queries interleaved per thread/lane pair: 1, 2 or 4 */
+                                 FMGPU_MODE_SPARSE: sparse-step table (fmgpu_index_sparsify): one 64-byte block (grid
+                                 root or search-tree node) per fetch, up to 14 bases per step, one state machine per read */
+  int32_t queries_per_thread; /* independent queries interleaved per thread / lane pair / lane group: 1, 2 or 4 (sparse: 1..4);
+                                 0 = the kernel family's default (sparse: 3 with static, 1 with dynamic read assignment) */
   int32_t threads_per_block;  /* 128, 256 or 512                                      */
   int32_t feed;               /* fmgpu_search_host only (also $FMGPU_FEED): FMGPU_FEED_AUTO, _ASCII (upload ASCII, pack
                                  on the GPU), _HOSTPACK (pack to 2 bit on the host with OpenMP + AVX-512, upload
@@ -244,13 +245,14 @@ typedef struct {
   int32_t  ndev;
   int32_t  searches;              /* searchIndexGPU calls since the index was transferred                          */
   double   index_h2d_reblock_s;   /* file entries H2D + re-block on the first GPU                                  */
-  double   peer_copy_s[16];       /* [g]: cudaMemcpyPeer of the block table to GPU g (g >= 1)                       */
+  double   peer_copy_s[16];       /* [g]: the cudaMemcpyPeer of the block table to GPU g (g >= 1), alone             */
   double   table_build_s[16];     /* [g]: sparse-step / fused-step table built on GPU g                             */
   double   queries_h2d_pack_s;    /* all shards: ASCII H2D + 2-bit pack                                            */
   double   results_d2h_s;         /* all shards: (L,R) D2H                                                         */
   float    search_ms[16];         /* [g]: kernels of the last searchIndexGPU on GPU g, CUDA events on its stream   */
   uint64_t index_file_bytes, table_bytes, query_bytes, result_bytes;
   double   context_init_s[16];    /* [g]: first use of GPU g by this process (CUDA context), before anything is copied */
+  double   replicate_s[16];       /* [g]: whole fmgpu_index_replicate for GPU g (allocation + peer mapping + the copy in peer_copy_s) */
 } fmgpu_transfer_stats_t;
 int32_t fmgpu_get_transfer_stats(fmgpu_transfer_stats_t *out);
 /* searchIndexGPU with an error code instead of exit(): FM_E_BAD_ARGUMENT when transferCPUtoGPU was not called for this pair */
@@ -280,6 +282,7 @@ int32_t fmgpu_index_create_from_device(int32_t device, uint32_t tag, uint32_t st
                                        const uint32_t *d_entries, fmgpu_index_t **out);
 /* replica on another GPU of this process: cudaMemcpyPeer over NVLink */
 int32_t fmgpu_index_replicate(const fmgpu_index_t *src, int32_t device, fmgpu_index_t **out);
+double  fmgpu_last_peer_copy_seconds(void);       /* duration of the copy inside this thread's last fmgpu_index_replicate */
 /* replica in another PROCESS: allocate an empty table of the same shape, then
  * fill fmgpu_index_blocks() with a broadcast (NCCL) from the owner */
 int32_t fmgpu_index_alloc_like(int32_t device, const fmgpu_index_meta_t *meta, fmgpu_index_t **out);

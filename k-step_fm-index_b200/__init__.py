@@ -83,7 +83,7 @@ class fmgpu_transfer_stats_t(C.Structure):
     _fields_ = [("ndev", C.c_int32), ("searches", C.c_int32), ("index_h2d_reblock_s", C.c_double), ("peer_copy_s", C.c_double * 16),
                 ("table_build_s", C.c_double * 16), ("queries_h2d_pack_s", C.c_double), ("results_d2h_s", C.c_double),
                 ("search_ms", C.c_float * 16), ("index_file_bytes", C.c_uint64), ("table_bytes", C.c_uint64),
-                ("query_bytes", C.c_uint64), ("result_bytes", C.c_uint64), ("context_init_s", C.c_double * 16)]
+                ("query_bytes", C.c_uint64), ("result_bytes", C.c_uint64), ("context_init_s", C.c_double * 16), ("replicate_s", C.c_double * 16)]
 
 
 class fmgpu_mm1_t(C.Structure):
@@ -130,6 +130,7 @@ PROTOTYPES = {
     "fmgpu_index_create_from_device": (C.c_int32, [C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                                    C.c_uint32, _U32P, _U32P, _VP, _VPP]),
     "fmgpu_index_replicate": (C.c_int32, [_VP, C.c_int32, _VPP]),
+    "fmgpu_last_peer_copy_seconds": (C.c_double, []),
     "fmgpu_index_alloc_like": (C.c_int32, [C.c_int32, C.POINTER(fmgpu_index_meta_t), _VPP]),
     "fmgpu_index_fuse": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, C.c_uint64]),
     "fmgpu_index_unfuse": (C.c_int32, [_VP]),

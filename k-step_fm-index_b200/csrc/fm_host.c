@@ -7,7 +7,7 @@
  * from the file header), 64-bit sizes, pinned query/result buffers and a
  * multi-GPU driver (replicate the index, shard the batch) behind the same
  * six *GPU entry points.  Everything device-side goes through the fmgpu_*
- * functions of fm_gpu.cu; this file contains no search arithmetic.
+ * functions of fm_index.cu, fm_search.cu, fm_sparsetab.cu, ... (fm_internal.h); this file contains no search arithmetic.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -369,6 +369,8 @@ static void fm_dump_stats(void)
   for (g = 0; g < g_stats.ndev; g++) fprintf(fp, "%s%.4f", g ? ", " : "", g_stats.context_init_s[g]);
   fprintf(fp, "], \"peer_copy_s\": [");
   for (g = 1; g < g_stats.ndev; g++) fprintf(fp, "%s%.6f", g > 1 ? ", " : "", g_stats.peer_copy_s[g]);
+  fprintf(fp, "], \"replicate_s\": [");
+  for (g = 1; g < g_stats.ndev; g++) fprintf(fp, "%s%.6f", g > 1 ? ", " : "", g_stats.replicate_s[g]);
   fprintf(fp, "], \"peer_copy_gbs\": [");
   for (g = 1; g < g_stats.ndev; g++) fprintf(fp, "%s%.2f", g > 1 ? ", " : "", g_stats.peer_copy_s[g] > 0 ? g_stats.table_bytes / g_stats.peer_copy_s[g] / 1e9 : 0.0);
   fprintf(fp, "], \"table_build_s\": [");
@@ -425,7 +427,8 @@ int32_t transferCPUtoGPU(void *index, void *queries, void *results)
     for (g = 1; g < rs->ndev && !err; g++) {
       t0 = fm_wall();
       err = fmgpu_index_replicate(rs->replica[0], rs->dev[g], &rs->replica[g]);
-      g_stats.peer_copy_s[g] = fm_wall() - t0;
+      g_stats.replicate_s[g] = fm_wall() - t0;                /* allocation + peer mapping + copy */
+      g_stats.peer_copy_s[g] = fmgpu_last_peer_copy_seconds();   /* the cudaMemcpyPeer alone */
     }
     if (err) { for (g = 0; g < rs->ndev; g++) fmgpu_index_free(&rs->replica[g]); free(rs); return err; }
     if (fmgpu_index_get_meta(rs->replica[0], &meta0) == FM_SUCCESS) g_stats.table_bytes = meta0.nbytes;

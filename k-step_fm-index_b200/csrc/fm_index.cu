@@ -5,6 +5,7 @@
  */
 #include "fm_internal.h"
 #include <mutex>
+#include <time.h>
 #include "fm_reblock.cuh"
 
 const fmgpu_variant_t FM_DEFAULT_VARIANT = { FMGPU_MODE_TASK, 2, 256, 0 };
@@ -272,6 +273,9 @@ extern "C" int32_t fmgpu_index_alloc_like(int32_t device, const fmgpu_index_meta
   return FM_SUCCESS;
 }
 
+static thread_local double g_last_peer_copy_s = 0.0;
+extern "C" double fmgpu_last_peer_copy_seconds(void) { return g_last_peer_copy_s; }   /* the cudaMemcpyPeer of this thread's last fmgpu_index_replicate */
+
 extern "C" int32_t fmgpu_index_replicate(const fmgpu_index_t *src, int32_t device, fmgpu_index_t **out)
 {
   if (!src || !out) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
@@ -281,8 +285,13 @@ extern "C" int32_t fmgpu_index_replicate(const fmgpu_index_t *src, int32_t devic
   int can = 0;
   cudaDeviceCanAccessPeer(&can, device, src->device);
   if (can) { cudaError_t pe = cudaDeviceEnablePeerAccess(src->device, 0); if (pe != cudaSuccess) cudaGetLastError(); }
+  cudaDeviceSynchronize();                                      /* allocation and peer mapping are done: what is timed below is the copy */
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
   cudaError_t e = cudaMemcpyPeer(dst->blocks, device, src->blocks, src->device, src->meta.nbytes);
-  if (e == cudaSuccess) e = cudaDeviceSynchronize();            /* the replica is complete (and its copy timed) when this returns */
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();            /* the replica is complete when this returns */
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  g_last_peer_copy_s = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
   if (e != cudaSuccess) { cudaFree(dst->blocks); free(dst); return fm_fail(e, "cudaMemcpyPeer(index replica)", __FILE__, __LINE__); }
   *out = dst;
   return FM_SUCCESS;
