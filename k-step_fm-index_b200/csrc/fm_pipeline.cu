@@ -81,13 +81,21 @@ static int fm_feed_mode(fmgpu_pipeline_t *pp, const fmgpu_variant_t *v, uint64_t
   if (mode == FMGPU_FEED_AUTO && env && *env) mode = atoi(env);
   if (mode >= FMGPU_FEED_ASCII && mode <= FMGPU_FEED_HYBRID) return mode;
   if (!(fm_hostpack_has_simd() && fm_hostpack_threads() >= 2)) return FMGPU_FEED_ASCII;
-  if (nq < (1ull << 20)) return pp->feed_rate[FMGPU_FEED_ASCII] > pp->feed_rate[FMGPU_FEED_HYBRID] ? FMGPU_FEED_ASCII : FMGPU_FEED_HYBRID;
-  *probe = true;                                  /* large call: its rate is recorded */
+  /* a priori: the hybrid feed pays when this process has cores to pack with (16 threads: 2 x the ASCII feed; 4 threads on a
+   * host shared by 8 ranks: 10 % slower, profiles/r02_e2e_n8_torchrun_feed*.json) */
+  const int first = fm_hostpack_threads() >= 6 ? FMGPU_FEED_HYBRID : FMGPU_FEED_ASCII;
+  const int second = first == FMGPU_FEED_HYBRID ? FMGPU_FEED_ASCII : FMGPU_FEED_HYBRID;
+  if (nq < (1ull << 20)) {
+    if (pp->feed_rate[first] == 0 || pp->feed_rate[second] == 0) return first;
+    return pp->feed_rate[first] >= pp->feed_rate[second] ? first : second;
+  }
+  *probe = true;                                  /* large call: its rate is recorded (the best of a mode's measurements counts) */
   const unsigned c = pp->feed_calls++;
-  if (pp->feed_rate[FMGPU_FEED_HYBRID] == 0) return FMGPU_FEED_HYBRID;
-  if (pp->feed_rate[FMGPU_FEED_ASCII] == 0) return FMGPU_FEED_ASCII;
-  const int best = pp->feed_rate[FMGPU_FEED_ASCII] > pp->feed_rate[FMGPU_FEED_HYBRID] ? FMGPU_FEED_ASCII : FMGPU_FEED_HYBRID;
-  if (c % 64 == 63) return best == FMGPU_FEED_ASCII ? FMGPU_FEED_HYBRID : FMGPU_FEED_ASCII;     /* re-probe the loser now and then */
+  /* the first large calls measure both modes twice, alternating (a mode's first call also pays first-use costs, and the
+   * ranks of a shared host disturb each other's measurements); then the faster one, re-probing the other every 64 calls */
+  if (c < 4) return (c & 1u) ? second : first;
+  const int best = pp->feed_rate[first] >= pp->feed_rate[second] ? first : second;
+  if (c % 64 == 63) return best == first ? second : first;
   return best;
 }
 
@@ -245,7 +253,8 @@ extern "C" int32_t fmgpu_pipeline_search_host(fmgpu_pipeline_t *pp, fmgpu_index_
     rc = fm_pipe_drain(pp, replicas, nrep);
     if (rc) return rc;
     const double dt = fm_now() - t_call;
-    if (probe && !pp->allocated) pp->feed_rate[feed] = (double) nq / dt;   /* self-tuning of the auto feed */
+    if (probe && !pp->allocated && (double) nq / dt > pp->feed_rate[feed]) pp->feed_rate[feed] = (double) nq / dt;   /* self-tuning of the auto feed */
+    if (probe && pp->feed_calls % 64 == 0) { pp->feed_rate[FMGPU_FEED_ASCII] *= 0.97; pp->feed_rate[FMGPU_FEED_HYBRID] *= 0.97; }   /* old maxima fade, so a changed host is noticed */
     pp->stats.calls += 1; pp->stats.last_feed = feed; pp->stats.last_seconds = dt;
     pp->stats.last_reads_host_packed = n_host.load(); pp->stats.last_reads_ascii_over_link = n_link.load();
     pp->stats.host_pack_seconds_per_read = pp->pack_s_per_read;
