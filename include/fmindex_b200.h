@@ -168,7 +168,7 @@ int32_t freeResultsGPU(void **results);
 typedef struct fmgpu_index fmgpu_index_t;   /* device-resident re-blocked index (one GPU) */
 typedef struct fmgpu_batch fmgpu_batch_t;   /* device-resident query shard + its results  */
 
-enum { FMGPU_MODE_TASK = 0, FMGPU_MODE_COOP = 1, FMGPU_MODE_FUSED = 2, FMGPU_MODE_SPARSE = 3 };
+enum { FMGPU_MODE_TASK = 0, FMGPU_MODE_COOP = 1, FMGPU_MODE_FUSED = 2, FMGPU_MODE_SPARSE = 3, FMGPU_MODE_WIDE = 4 };
 
 /* Kernel variant.  Zero-initialised = library defaults. */
 typedef struct {
@@ -178,7 +178,9 @@ typedef struct {
                                  FMGPU_MODE_FUSED: fused-step table (fmgpu_index_fuse): a lane group fetches one
                                  32/64/128-byte block with 256-bit loads and consumes up to 4 bases per step;
                                  FMGPU_MODE_SPARSE: sparse-step table (fmgpu_index_sparsify): one 64-byte block (grid
-                                 root or search-tree node) per fetch, up to 14 bases per step, one state machine per read */
+                                 root or search-tree node) per fetch, up to 14 bases per step, one state machine per read;
+                                 FMGPU_MODE_WIDE: wide-step table (fmgpu_index_widen): one 128-byte block per fetch, up to 30
+                                 bases per step, the block computed from the read alone (both interval ends share it) */
   int32_t queries_per_thread; /* independent queries interleaved per thread / lane pair / lane group: 1, 2 or 4 (sparse: 1..4);
                                  0 = the kernel family's default (sparse: 3 with static, 1 with dynamic read assignment) */
   int32_t threads_per_block;  /* 128, 256 or 512                                      */
@@ -237,6 +239,17 @@ typedef struct {
   uint32_t reserved1;
   uint64_t derived_bytes;      /* everything this replica derived from its SB96 table: sparse + fused + tail + SA tables */
   uint64_t budget_bytes;       /* the limit derived_bytes is kept under ($FMGPU_TABLE_BUDGET_GB / fmgpu_set_table_budget), 0 = none */
+  /* wide-step table (fmgpu_index_widen), 0 = none */
+  uint32_t wide_bases;         /* bases per wide step (<= 30)                                    */
+  uint32_t wide_prefix_bits;   /* top bits of a wide symbol that select its 128-byte block (2^bits grid blocks) */
+  uint32_t wide_row_bits;      /* bits of a row number inside a 64-bit entry                     */
+  uint32_t wide_tree_depth;    /* levels below the grid of the deepest search tree               */
+  uint64_t wide_bytes;         /* blocks (+ lead tables)                                         */
+  uint64_t wide_blocks;        /* grid + tree nodes                                              */
+  uint64_t wide_overflow;      /* buckets with more than 15 rows (roots of search trees)         */
+  uint64_t wide_tree_nodes;    /* blocks below the grid                                          */
+  uint64_t wide_tree_rows;     /* rows living in trees (of bwtsize)                              */
+  uint64_t wide_exceptional;   /* buckets whose steps run on the block table (a suffix shorter than the step sorts into them) */
 } fmgpu_index_meta_t;
 
 /* what the last transferCPUtoGPU / searchIndexGPU / transferGPUtoCPU sequence of this process did (wall-clock seconds of
@@ -307,6 +320,21 @@ int32_t fmgpu_index_unfuse(fmgpu_index_t *idx);
  * does not suffice. */
 int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_bases, uint32_t lambda, uint32_t lanes);
 int32_t fmgpu_index_unsparsify(fmgpu_index_t *idx);
+/* Wide-step table, built on the GPU from this replica's own block table: one wide step = wide_bases/k reference LF steps
+ * (exactly), ONE 128-byte block fetch for both interval ends.  The rows are sorted by the wide symbol in front of them
+ * (wide_bases <= 30 bases = a 60-bit key); the top prefix_bits of the symbol select the block -- computed from the read,
+ * never looked up, the same for both ends -- and the block's 15 64-bit entries carry the rest of the symbol with the row
+ * (csrc/fm_wide.cuh).  Buckets with more than 15 rows become search trees as in the sparse-step table.  A read of
+ * len = b + S * wide_bases bases (b < 16 from a lead table of all b-mers) costs S block fetches: 3 for 100 bp, 8 for 250 bp
+ * at 30 bases per step.  wide_bases 0 = the widest the text allows (30 up to 4 G rows); prefix_bits 0 = 3.75 .. 7.5 rows per
+ * bucket on average (17 .. 34 bytes per text base).  A table serves the read lengths its width divides (after the lead
+ * bases): fmgpu_wide_bases_for(idx, len) names the width to build for a length, fmgpu_index_wide_serves(idx, len) tells
+ * whether an existing table (with its lead table, see fmgpu_index_prepare) does.  AltCounters files with an active padding
+ * quirk are refused (FM_E_NOT_IMPLEMENTED, like memory or budget shortage): the sparse-step table serves them. */
+int32_t  fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, uint32_t prefix_bits);
+int32_t  fmgpu_index_unwiden(fmgpu_index_t *idx);
+uint32_t fmgpu_wide_bases_for(const fmgpu_index_t *idx, uint32_t len);      /* 0 = no width serves this length */
+int32_t  fmgpu_index_wide_serves(const fmgpu_index_t *idx, uint32_t len);   /* 1 / 0 */
 /* Builds NOW (synchronously) whatever a search of `len`-base reads on this replica may use: the tail table for odd
  * lengths on a 2-step index, the lead tables of the sparse-step plan.  The search entry points themselves never build
  * or allocate: they pick among the tables that exist (same results, more fetches when one is missing).
@@ -480,6 +508,10 @@ int32_t fmgpu_count_fetches_fused_device(const fmgpu_index_t *idx, const uint32_
 int32_t fmgpu_count_fetches_sparse_device(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nqueries, uint32_t len,
                                           uint32_t *d_results, void *stream, uint64_t *nroot_blocks, uint64_t *nsb96_blocks,
                                           uint64_t *ntree_blocks);
+/* same for FMGPU_MODE_WIDE: grid blocks, SB96 blocks (steps of exceptional buckets), tree blocks below the grid */
+int32_t fmgpu_count_fetches_wide_device(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nqueries, uint32_t len,
+                                        uint32_t *d_results, void *stream, uint64_t *ngrid_blocks, uint64_t *nsb96_blocks,
+                                        uint64_t *ntree_blocks);
 /* locality variant: the 32 lanes of every warp-level load fall inside ONE random window of
  * `window_bytes` (e.g. one 2 MB page), random blocks inside it: isolates address-translation cost */
 int32_t fmgpu_gather_probe_local(int32_t device, uint64_t table_bytes, uint64_t window_bytes, uint64_t loads_per_thread,

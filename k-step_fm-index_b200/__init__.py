@@ -31,7 +31,7 @@ FM_E_CUDA = 50
 FM_E_BAD_ARGUMENT = 51
 FM_E_UNSUPPORTED_INDEX = 52
 FM_E_QUERY_SHAPE = 53
-MODE_TASK, MODE_COOP, MODE_FUSED, MODE_SPARSE = 0, 1, 2, 3
+MODE_TASK, MODE_COOP, MODE_FUSED, MODE_SPARSE, MODE_WIDE = 0, 1, 2, 3, 4
 
 
 def build_native(verbose=False):
@@ -76,7 +76,10 @@ class fmgpu_index_meta_t(C.Structure):
                 ("sparse_lanes", C.c_uint32), ("tail_bytes", C.c_uint64),
                 ("sparse_uniform_nb", C.c_uint32), ("sa_rate", C.c_uint32), ("sa_bytes", C.c_uint64),
                 ("sparse_tree_nodes", C.c_uint64), ("sparse_tree_rows", C.c_uint64), ("sparse_tree_depth", C.c_uint32),
-                ("reserved1", C.c_uint32), ("derived_bytes", C.c_uint64), ("budget_bytes", C.c_uint64)]
+                ("reserved1", C.c_uint32), ("derived_bytes", C.c_uint64), ("budget_bytes", C.c_uint64),
+                ("wide_bases", C.c_uint32), ("wide_prefix_bits", C.c_uint32), ("wide_row_bits", C.c_uint32), ("wide_tree_depth", C.c_uint32),
+                ("wide_bytes", C.c_uint64), ("wide_blocks", C.c_uint64), ("wide_overflow", C.c_uint64),
+                ("wide_tree_nodes", C.c_uint64), ("wide_tree_rows", C.c_uint64), ("wide_exceptional", C.c_uint64)]
 
 
 class fmgpu_transfer_stats_t(C.Structure):
@@ -136,6 +139,12 @@ PROTOTYPES = {
     "fmgpu_index_unfuse": (C.c_int32, [_VP]),
     "fmgpu_index_sparsify": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, C.c_uint32]),
     "fmgpu_index_unsparsify": (C.c_int32, [_VP]),
+    "fmgpu_index_widen": (C.c_int32, [_VP, C.c_uint32, C.c_uint32]),
+    "fmgpu_index_unwiden": (C.c_int32, [_VP]),
+    "fmgpu_wide_bases_for": (C.c_uint32, [_VP, C.c_uint32]),
+    "fmgpu_index_wide_serves": (C.c_int32, [_VP, C.c_uint32]),
+    "fmgpu_count_fetches_wide_device": (C.c_int32, [_VP, _VP, C.c_uint64, C.c_uint32, _VP, _VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                                    C.POINTER(C.c_uint64)]),
     "fmgpu_index_build_sa": (C.c_int32, [_VP]),
     "fmgpu_index_build_sa_sampled": (C.c_int32, [_VP, C.c_uint32]),
     "fmgpu_index_drop_sa": (C.c_int32, [_VP]),
@@ -388,6 +397,21 @@ class DeviceIndex:
 
     def unsparsify(self):
         check(lib().fmgpu_index_unsparsify(self.handle), "fmgpu_index_unsparsify")
+
+    def widen(self, wide_bases=0, prefix_bits=0):
+        """Builds the wide-step table (up to 30 bases per 128-byte block fetch, both interval ends in one block) for MODE_WIDE searches."""
+        check(lib().fmgpu_index_widen(self.handle, wide_bases, prefix_bits), "fmgpu_index_widen")
+        return self
+
+    def unwiden(self):
+        check(lib().fmgpu_index_unwiden(self.handle), "fmgpu_index_unwiden")
+
+    def wide_bases_for(self, length):
+        """Step width a wide-step table should have to serve reads of `length` bases with the fewest fetches (0 = none)."""
+        return int(lib().fmgpu_wide_bases_for(self.handle, length))
+
+    def wide_serves(self, length):
+        return bool(lib().fmgpu_index_wide_serves(self.handle, length))
 
     def build_sa(self):
         """Derives the suffix array of the indexed text from this replica's own table (needed by locate)."""

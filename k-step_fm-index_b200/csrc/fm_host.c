@@ -297,7 +297,7 @@ int32_t fmgpu_set_variant(const fmgpu_variant_t *v)
   return FM_SUCCESS;
 }
 
-/* $FMGPU_MODE = task | coop | fused | sparse | auto (default): kernel family used by searchIndexGPU */
+/* $FMGPU_MODE = task | coop | fused | sparse | wide | auto (default): kernel family used by searchIndexGPU */
 #define FM_MODE_AUTO (-1)
 static int fm_mode_from_env(void)
 {
@@ -307,6 +307,7 @@ static int fm_mode_from_env(void)
   if (!strcmp(env, "coop")) return FMGPU_MODE_COOP;
   if (!strcmp(env, "fused")) return FMGPU_MODE_FUSED;
   if (!strcmp(env, "sparse")) return FMGPU_MODE_SPARSE;
+  if (!strcmp(env, "wide")) return FMGPU_MODE_WIDE;
   return FM_MODE_AUTO;
 }
 
@@ -432,23 +433,30 @@ int32_t transferCPUtoGPU(void *index, void *queries, void *results)
     }
     if (err) { for (g = 0; g < rs->ndev; g++) fmgpu_index_free(&rs->replica[g]); free(rs); return err; }
     if (fmgpu_index_get_meta(rs->replica[0], &meta0) == FM_SUCCESS) g_stats.table_bytes = meta0.nbytes;
-    /* derived table on every replica unless $FMGPU_MODE asks for the plain kernels: the sparse-step table (auto and
-     * "sparse"), or the fused-step table ("fused", and auto when the sparse one cannot be built).  A table that cannot
+    /* derived table on every replica unless $FMGPU_MODE asks for the plain kernels: the wide-step table when a step
+     * width serves this read length (auto and "wide"), else the sparse-step table (auto and "sparse"; also when the wide
+     * one cannot be built), or the fused-step table ("fused", and auto when neither can be built).  A table that cannot
      * be built -- no memory, over the table budget -- is never fatal: that replica keeps the plain 2-step kernels,
      * still on the GPU.  Only a broken context (FM_E_CUDA from anything but an allocation) aborts. */
     {
       /* auto: an index whose plain table stays L2-resident (config 1/2: 10.7 MB) is not worth a table build for one
        * batch: the plain kernels already run at 3-4.6 G reads/s there */
       const int mode = fm_mode_from_env();
-      int want_sparse = (mode == FMGPU_MODE_SPARSE), want_fused = (mode == FMGPU_MODE_FUSED);
-      if (mode == FM_MODE_AUTO) want_sparse = g_stats.table_bytes > (96ull << 20);
+      int want_sparse = (mode == FMGPU_MODE_SPARSE), want_fused = (mode == FMGPU_MODE_FUSED), want_wide = (mode == FMGPU_MODE_WIDE);
+      if (mode == FM_MODE_AUTO) want_sparse = want_wide = g_stats.table_bytes > (96ull << 20);
+      if (want_wide) want_sparse = 1;                            /* the fallback when no width serves the length or memory is short */
       /* every replica builds its own table from its own copy of the block table: one host thread per GPU */
       int32_t err_g[FM_MAX_GPUS] = { 0 };
       #pragma omp parallel for schedule(static, 1) num_threads(rs->ndev) private(err, t0, meta0) if (rs->ndev > 1)
       for (g = 0; g < rs->ndev; g++) {
         if (!(want_sparse || want_fused)) continue;
         t0 = fm_wall();
-        err = want_sparse ? fmgpu_index_sparsify(rs->replica[g], 0, 0, 0) : FM_E_NOT_IMPLEMENTED;
+        err = FM_E_NOT_IMPLEMENTED;
+        if (want_wide) {
+          const uint32_t wb = fmgpu_wide_bases_for(rs->replica[g], qrys->size);
+          if (wb) err = fmgpu_index_widen(rs->replica[g], wb, 0);
+        }
+        if (err == FM_E_NOT_IMPLEMENTED && want_sparse) err = fmgpu_index_sparsify(rs->replica[g], 0, 0, 0);
         /* (round 1 switched repeat-rich texts to the fused-step table here; with search trees and per-read state machines
          * the sparse-step table wins on those too -- profiles/r02_skewed_text.md: 2 730 vs 1 689 and 4 034 vs 2 030 M reads/s
          * -- so the fused table is only the fallback when the sparse one cannot be built) */
@@ -460,7 +468,7 @@ int32_t transferCPUtoGPU(void *index, void *queries, void *results)
         if (err_g[g]) { err = err_g[g]; for (g = 0; g < rs->ndev; g++) fmgpu_index_free(&rs->replica[g]); free(rs); return err; }
       if (getenv("FMGPU_VERBOSE") && fmgpu_index_get_meta(rs->replica[0], &meta0) == FM_SUCCESS)
         fprintf(stderr, "fmindex_b200: %d replica(s), SB96 %.1f MB, search table: %s\n", rs->ndev, meta0.nbytes / 1e6,
-                meta0.sparse_bases ? "sparse-step" : meta0.fused_bases ? "fused-step" : "none (plain kernels)");
+                meta0.wide_bases ? "wide-step" : meta0.sparse_bases ? "sparse-step" : meta0.fused_bases ? "fused-step" : "none (plain kernels)");
     }
     fmi->d_index = rs;
   }
@@ -468,6 +476,18 @@ int32_t transferCPUtoGPU(void *index, void *queries, void *results)
   for (g = 0; g < rs->ndev; g++) {
     err = fmgpu_index_prepare(rs->replica[g], qrys->size);
     if (err) return err;
+    /* a resident wide-step table whose width does not serve this (new) read length: the sparse-step table joins it */
+    if (!fmgpu_index_wide_serves(rs->replica[g], qrys->size)) {
+      fmgpu_index_meta_t m;
+      const int mode = fm_mode_from_env();
+      if (fmgpu_index_get_meta(rs->replica[g], &m) == FM_SUCCESS && m.wide_bases && !m.sparse_bases &&
+          (mode == FM_MODE_AUTO || mode == FMGPU_MODE_WIDE)) {
+        err = fmgpu_index_sparsify(rs->replica[g], 0, 0, 0);
+        if (err && err != FM_E_NOT_IMPLEMENTED) return err;
+        err = fmgpu_index_prepare(rs->replica[g], qrys->size);
+        if (err) return err;
+      }
+    }
   }
 
   /* queries + results: contiguous 32-aligned shards, one per GPU.  Whatever set either handle still holds is released
@@ -516,10 +536,12 @@ int32_t fmgpu_search_index(void *index, void *queries, void *resIntervals)
       memset(&v, 0, sizeof v);
       err = fmgpu_index_get_meta(rs->replica[g], &meta);
       if (err) break;
-      v.mode = (mode == FM_MODE_AUTO) ? (meta.sparse_bases ? FMGPU_MODE_SPARSE : meta.fused_bases ? FMGPU_MODE_FUSED : FMGPU_MODE_COOP) : mode;
+      const int wide_ok = meta.wide_bases && fmgpu_index_wide_serves(rs->replica[g], qrys->size);
+      v.mode = (mode == FM_MODE_AUTO) ? (wide_ok ? FMGPU_MODE_WIDE : meta.sparse_bases ? FMGPU_MODE_SPARSE : meta.fused_bases ? FMGPU_MODE_FUSED : FMGPU_MODE_COOP) : mode;
+      if (v.mode == FMGPU_MODE_WIDE && !wide_ok) v.mode = FMGPU_MODE_SPARSE;
       if (v.mode == FMGPU_MODE_SPARSE && !meta.sparse_bases) v.mode = meta.fused_bases ? FMGPU_MODE_FUSED : FMGPU_MODE_COOP;
       if (v.mode == FMGPU_MODE_FUSED && !meta.fused_bases) v.mode = FMGPU_MODE_COOP;
-      if (v.mode == FMGPU_MODE_SPARSE) v.queries_per_thread = 0;     /* the sparse launcher's own default */
+      if (v.mode == FMGPU_MODE_SPARSE || v.mode == FMGPU_MODE_WIDE) v.queries_per_thread = 0;     /* the launcher's own default */
     }
     err = fmgpu_batch_search_timed_async(rs->replica[g], ss->shard[g], &v);
   }

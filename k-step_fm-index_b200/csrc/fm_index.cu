@@ -267,6 +267,10 @@ extern "C" int32_t fmgpu_index_alloc_like(int32_t device, const fmgpu_index_meta
   idx->meta.sparse_bases = 0; idx->meta.sparse_lambda = 0; idx->meta.sparse_bytes = 0; idx->meta.sparse_blocks = 0;
   idx->meta.sparse_overflow = 0; idx->meta.sparse_start_bases = 0; idx->meta.sparse_lanes = 0; idx->meta.tail_bytes = 0;
   idx->meta.sparse_uniform_nb = 0; idx->meta.sa_bytes = 0; idx->meta.sa_rate = 0; idx->meta.derived_bytes = 0;
+  idx->meta.sparse_tree_nodes = 0; idx->meta.sparse_tree_rows = 0; idx->meta.sparse_tree_depth = 0;
+  idx->meta.wide_bases = 0; idx->meta.wide_prefix_bits = 0; idx->meta.wide_row_bits = 0; idx->meta.wide_tree_depth = 0;
+  idx->meta.wide_bytes = 0; idx->meta.wide_blocks = 0; idx->meta.wide_overflow = 0; idx->meta.wide_tree_nodes = 0;
+  idx->meta.wide_tree_rows = 0; idx->meta.wide_exceptional = 0;
   cudaError_t e = cudaMalloc((void **) &idx->blocks, meta->nbytes);
   if (e != cudaSuccess) { free(idx); return fm_fail(e, "cudaMalloc(SB96 replica)", __FILE__, __LINE__); }
   *out = idx;
@@ -310,11 +314,13 @@ extern "C" int32_t fmgpu_index_free(fmgpu_index_t **pidx)
 {
   if (!pidx || !*pidx) return FM_SUCCESS;
   fmgpu_index_t *idx = *pidx;
-  if (idx->blocks || idx->fblocks || idx->start || idx->sblocks || idx->tail1 || idx->sa) {
+  if (idx->blocks || idx->fblocks || idx->start || idx->sblocks || idx->tail1 || idx->sa || idx->wblocks) {
     cudaSetDevice(idx->device);
     cudaFree(idx->blocks); cudaFree(idx->fblocks); cudaFree(idx->start);
     cudaFree(idx->sblocks); cudaFree(idx->sdir); cudaFree(idx->sstart); cudaFree(idx->tail1); cudaFree(idx->sa); cudaFree(idx->sa_marks);
     for (int b = 0; b < 16; b++) cudaFree(idx->slead[b]);
+    cudaFree(idx->wblocks);
+    for (int b = 0; b < 16; b++) cudaFree(idx->wlead[b]);
   }
   free(idx);
   *pidx = NULL;
@@ -373,7 +379,7 @@ static uint64_t fm_table_budget(void)
 
 static uint64_t fm_derived_bytes(const fmgpu_index_t *idx)
 {
-  return idx->meta.sparse_bytes + idx->meta.fused_bytes + (idx->start ? ((uint64_t) 8 << 24) : 0) + idx->meta.tail_bytes + idx->meta.sa_bytes;
+  return idx->meta.sparse_bytes + idx->meta.wide_bytes + idx->meta.fused_bytes + (idx->start ? ((uint64_t) 8 << 24) : 0) + idx->meta.tail_bytes + idx->meta.sa_bytes;
 }
 
 bool fm_budget_allows(const fmgpu_index_t *idx, uint64_t bytes)
@@ -398,6 +404,7 @@ extern "C" int32_t fmgpu_index_prepare(fmgpu_index_t *idx, uint32_t len)
   CU_TRY(cudaSetDevice(idx->device));
   if (idx->meta.steps == 2 && (len & 1u)) fm_build_tail(idx);
   if (idx->sblocks) fm_sparse_prepare(idx, len);
+  if (idx->wblocks) fm_wide_prepare(idx, len);
   fm_budget_account(idx);
   return FM_SUCCESS;
 }

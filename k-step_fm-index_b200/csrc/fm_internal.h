@@ -1,6 +1,6 @@
 /*
  * fm_internal.h -- declarations shared by the translation units behind PART 2 of include/fmindex_b200.h
- * (fm_index.cu, fm_fusedtab.cu, fm_sparsetab.cu, fm_locate.cu, fm_search.cu, fm_pipeline.cu, fm_probe.cu).
+ * (fm_index.cu, fm_fusedtab.cu, fm_sparsetab.cu, fm_widetab.cu, fm_locate.cu, fm_search.cu, fm_pipeline.cu, fm_probe.cu).
  * Not installed; C++ (nvcc) only.
  */
 #ifndef FM_INTERNAL_H_
@@ -47,6 +47,9 @@ struct fmgpu_index {
   uint32_t           s_uni_nb, s_uni_scale;   /* sparse table is a uniform grid: blocks per symbol and the one scale (0 = directory) */
   int                tail1_tried;  /* 1 once that build was attempted (a failed allocation is not retried) */
   fm_phantoms        fphantoms;    /* quirk: extra occurrences of fused symbols */
+  uint4             *wblocks;      /* wide-step table (fmgpu_index_widen), or NULL */
+  uint32_t           wlead_tried;  /* bit b: building wlead[b] was attempted */
+  uint2             *wlead[16];    /* its lead tables: (L,R) of all b-mers, or NULL */
 };
 
 struct fmgpu_batch {
@@ -93,5 +96,9 @@ int32_t fm_launch_sparse(const fmgpu_index_t *idx, const uint32_t *d_packed, uin
                          fmgpu_variant_t v, cudaStream_t stream, unsigned long long *d_counters, bool use_lead_tables);
 /* lead tables a sparse search of `len`-base reads would use, built if missing (synchronous; fm_sparsetab.cu) */
 void    fm_sparse_prepare(fmgpu_index_t *idx, uint32_t len);
+/* wide-step table (fm_widetab.cu): launch (FM_E_NOT_IMPLEMENTED when the table's width does not serve `len`), lead table of `len` */
+int32_t fm_launch_wide(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nq, uint32_t len, uint32_t *d_results,
+                       fmgpu_variant_t v, cudaStream_t stream, unsigned long long *d_counters);
+void    fm_wide_prepare(fmgpu_index_t *idx, uint32_t len);
 
 #endif /* FM_INTERNAL_H_ */

@@ -69,6 +69,11 @@ int32_t fm_launch_search(const fmgpu_index_t *idx, const uint32_t *d_packed, uin
   if (count) { v.mode = FMGPU_MODE_TASK; v.queries_per_thread = 1; v.threads_per_block = 256; }
   if (v.mode == FMGPU_MODE_FUSED) return fm_launch_fused(idx, d_packed, nq, len, d_results, vin ? *vin : FM_DEFAULT_VARIANT, stream, NULL);
   if (v.mode == FMGPU_MODE_SPARSE) return fm_launch_sparse(idx, d_packed, nq, len, d_results, vin ? *vin : FM_DEFAULT_VARIANT, stream, NULL, true);
+  if (v.mode == FMGPU_MODE_WIDE) {
+    fmgpu_variant_t w = vin ? *vin : FM_DEFAULT_VARIANT;
+    if (!vin) w.queries_per_thread = 0;
+    return fm_launch_wide(idx, d_packed, nq, len, d_results, w, stream, NULL);
+  }
 
   FmSearchParams p;
   p.blocks = idx->blocks; p.packed = d_packed; p.results = d_results; p.fetch_counters = d_counters;

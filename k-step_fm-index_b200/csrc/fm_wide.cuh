@@ -1,0 +1,434 @@
+/*
+ * fm_wide.cuh -- "wide-step" device layout and search kernel: up to 30 query bases per 128-byte block fetch.
+ *
+ * Why.  profiles/r02_ceiling_counters.md: the memory system accepts ~46 G miss-bound requests per second whatever
+ * they carry up to one 128-byte line, and the search is bound by nothing else.  The sparse-step table (fm_sparse.cuh)
+ * spends a 64-byte request on 14 bases because it gives every wide symbol its own blocks: 4^KS symbols must stay
+ * below the number of blocks the memory can hold.  Here the blocks belong to a PREFIX of the wide symbol and every
+ * entry carries the rest of it, so the width of a step is bounded by the entry size (64 bits), not by the table:
+ *
+ *   wide symbol of row i    F(i) = s(i) | s(LF(i)) << 2k | ...   (hops = W/k hops, W <= 30 bases: the composition of
+ *                           fm_fused.cuh / fm_sparse.cuh, so that rank_F(sigma, X) = G(sigma) + #{ i < X : F(i) = sigma }
+ *                           IS `hops` consecutive reference LF steps for every X; rows whose chain meets a '$' row
+ *                           carry no symbol).  The hop consumed last sits in the TOP bits: numeric order of F is the
+ *                           lexicographic order of the W text bases in front of the suffix.
+ *   bucket                  the top prefix_bits of sigma (all 14-mers for a 2 Gbp text: ~7.5 rows per bucket).
+ *                           Block of (sigma, X) = sigma >> sub_bits: computed from the READ alone, never looked up and
+ *                           independent of X -- both interval ends of a step always share their fetch.
+ *   entry (64 bits)         (sigma & submask) << row_bits | row, for every row of the bucket, ascending: that is the
+ *                           order of (F(i), i), i.e. one stable radix sort of the composed keys.
+ *   block (128 bytes)       16 x u64: word 0 = { value (low half), kind (high half) }, then 15 ascending entries padded
+ *                           with ~0:
+ *        leaf               value = G(first symbol of the bucket) + entries of the bucket in front of this block;
+ *                           rank_F(sigma, X) = value + #{ entries < (sub(sigma) << row_bits | X) }
+ *        inner node         value = block number of child 0, entries = 15 separators (first entry of children 1..15);
+ *                           child = value + #{ separators < key } -- the same arithmetic; fan-out 16
+ *        exceptional        kind = 2: the step runs as `hops` plain SB96 steps instead (see below)
+ *   search tree             a bucket with more than 15 rows is the root of a tree over its sorted entries (leaves of 15
+ *                           consecutive entries, all at the same depth, stored behind the grid level by level), as in
+ *                           the sparse-step table: Poisson tail on a random text (0.5 % of the buckets at 7.5 rows per
+ *                           bucket), repeats on a real one.
+ *
+ * Exactness.  A leaf answers with ONE base value for all symbols of its bucket, which is right iff
+ *   G(sigma') - G(sigma) = #{ rows with sigma <= F < sigma' }  for the symbols of one bucket.
+ * That is the suffix-array order of the W-base contexts, except where one of the (at most W) suffixes shorter than W
+ * sorts into the bucket.  Nothing is assumed: the builder carries y(i) = the row the chain of i ends in (= rank_F(F(i), i))
+ * through the sort and checks for EVERY entry that y = G(bucket's smallest symbol) + position in the bucket, and for every
+ * bucket that the next bucket's G continues the count (both composed from the SB96 table itself).  With G monotone in
+ * sigma this pins G for the absent symbols of the bucket too.  A bucket that fails is marked exceptional and the kernel
+ * takes `hops` SB96 steps there -- a handful of buckets out of 2^28.  AltCounters files with an active padding quirk
+ * (their composed rank is not a plain counting function) are refused; the sparse-step table serves them.
+ *
+ * Kernel: the per-read state machine of fm_sparse.cuh -- one block fetch per iteration and unfinished read -- on
+ * 4-lane groups (one 256-bit load per lane = the 128-byte block), 64-bit compares.
+ */
+#ifndef FM_WIDE_CUH_
+#define FM_WIDE_CUH_
+
+#include "fm_device.cuh"
+
+#define FM_WD_PAD      0xFFFFFFFFFFFFFFFFull
+#define FM_WD_LEAF     0u
+#define FM_WD_INNER    1u
+#define FM_WD_EXC      2u
+#define FM_WD_DONE     0xFFFFFFFFu
+#define FM_WD_SLOTS    15u
+#define FM_WD_FAN      16u
+#define FM_WD_MAXDEPTH 8                   /* 15 * 16^8 entries > 2^32 rows */
+#define FM_WD_LANES    4
+
+struct FmWideParams {
+  const uint4    *wblocks;    /* grid + tree nodes, 8 uint4 (128 bytes) per block                          */
+  const uint4    *blocks;     /* SB96: the steps of exceptional buckets                                     */
+  const uint32_t *packed;
+  uint32_t       *results;
+  uint32_t nblocks;           /* SB96 stride                                                               */
+  uint32_t nq;
+  uint32_t nsteps;            /* wide steps (after the lead table's bases, if one is used)                 */
+  uint32_t wpq;
+  uint32_t bwtsize;
+  uint32_t wbits;             /* 2 * W                                                                     */
+  uint32_t sub_bits;          /* bits of the wide symbol kept in the entries: wbits - prefix_bits          */
+  uint32_t row_bits;          /* bits of a row number in an entry                                          */
+  uint32_t hops, kbits;       /* W / k, 2 * k                                                              */
+  uint32_t nroots;            /* 2^prefix_bits: blocks at or beyond it are tree nodes                      */
+  uint32_t total_blocks;      /* grid + tree nodes (extent of wblocks, checked by the -DFM_DEBUG_BOUNDS build) */
+  const uint2 *start;         /* lead table: (L,R) after the first start_bits / 2 bases, or NULL = (0, bwtsize) */
+  uint32_t start_bits;
+  unsigned long long *fetch_counters;  /* COUNT only: [0] grid blocks, [1] SB96 blocks (exceptional buckets), [2] tree nodes below the grid */
+};
+
+/* the whole 128-byte line of a block is used: default fill */
+__device__ __forceinline__ void fm_wide_load(const uint4 *p, uint32_t (&w)[8])
+{
+  asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+}
+
+/* bits [pos, pos + nbits) of a packed read in shared memory, nbits <= 64 (one readable spare word behind the read) */
+__device__ __forceinline__ uint64_t fm_read_field64(const uint32_t *q, uint32_t pos, uint32_t nbits)
+{
+  const uint32_t lo = fm_read_field(q, pos, 0xFFFFFFFFu);
+  const uint32_t hi = nbits > 32u ? fm_read_field(q, pos + 32u, 0xFFFFFFFFu) : 0u;
+  const uint64_t v = (uint64_t) lo | ((uint64_t) hi << 32);
+  return nbits >= 64u ? v : (v & ((1ull << nbits) - 1ull));
+}
+
+/* this lane's share of #{ entries < key }: lane 0 skips word 0 (the header) */
+__device__ __forceinline__ uint32_t fm_wide_partial(const uint32_t (&w)[8], uint64_t key, uint32_t lg)
+{
+  uint32_t c = 0;
+  #pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const uint64_t e = (uint64_t) w[2 * j] | ((uint64_t) w[2 * j + 1] << 32);
+    if (j == 0) c += (lg != 0u && e < key) ? 1u : 0u;
+    else        c += (e < key) ? 1u : 0u;
+  }
+  return c;
+}
+
+/* packed reads of a CTA -> shared memory: one TMA bulk copy when the piece is 16-byte granular (fm_search_fused_kernel) */
+template <int THREADS>
+__device__ __forceinline__ void fm_stage_reads(uint32_t *fsm, uint32_t *sq, const uint32_t *src, uint32_t words)
+{
+  const uint32_t bytes = words * 4u;
+  const bool bulk = (bytes % 16u) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+  const uint32_t mbar = (uint32_t) __cvta_generic_to_shared(fsm);
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   :: "r"((uint32_t) __cvta_generic_to_shared(sq)), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+    }
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(mbar) : "memory");
+  } else {
+    for (uint32_t i = threadIdx.x; i < words; i += THREADS) sq[i] = __ldg(src + i);
+    __syncthreads();
+  }
+}
+
+/* one wide step of an exceptional bucket: `hops` base-k steps on SB96 for both interval ends */
+__device__ __forceinline__ void fm_wide_plain_step(const FmWideParams &p, uint64_t key, uint32_t &L, uint32_t &R)
+{
+  const uint32_t kmask = (1u << p.kbits) - 1u;
+  for (uint32_t h = 0; h < p.hops; h++) {
+    const uint32_t s = (uint32_t)(key >> (p.kbits * h)) & kmask;
+    const uint32_t bL = fm_div96(L), bR = fm_div96(R);
+    const uint4 *base = p.blocks + (size_t) s * p.nblocks;
+    FM_BOUND(bL, p.nblocks, "wide: SB96 block (L)"); FM_BOUND(bR, p.nblocks, "wide: SB96 block (R)");
+    const uint4 vL = fm_ldg16(base + bL);
+    const uint4 vR = (bL == bR) ? vL : fm_ldg16(base + bR);
+    L = fm_block_rank(vL, L - bL * FM_SB_ROWS);
+    R = fm_block_rank(vR, R - bR * FM_SB_ROWS);
+  }
+}
+
+template <int QPT, int THREADS, int MINB, bool COUNT>
+__global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_kernel(const FmWideParams p)
+{
+  extern __shared__ __align__(16) uint32_t fsm[];             /* [0..3]: mbarrier + pad; [4..): packed reads, natural stride */
+  uint32_t *sq = fsm + 4;
+  constexpr int LANES = FM_WD_LANES, GROUPS = THREADS / LANES;
+  const uint32_t q0 = blockIdx.x * (GROUPS * QPT);
+  const uint32_t nqb = min((uint32_t)(GROUPS * QPT), p.nq - q0);
+  const uint32_t lg = threadIdx.x % LANES, group = threadIdx.x / LANES;
+  const uint64_t submask = p.sub_bits >= 64u ? ~0ull : ((1ull << p.sub_bits) - 1ull);
+
+  fm_stage_reads<THREADS>(fsm, sq, p.packed + (size_t) q0 * p.wpq, nqb * p.wpq);
+
+  uint32_t L[QPT], R[QPT], aL[QPT], aR[QPT], rem[QPT];
+  uint64_t key[QPT];
+  const uint32_t *myq[QPT];
+  bool live[QPT];
+  const uint32_t kmask = (p.start_bits >= 32u) ? 0xFFFFFFFFu : ((1u << p.start_bits) - 1u);
+  bool busy = false;
+  #pragma unroll
+  for (int i = 0; i < QPT; i++) {
+    const uint32_t lq = i * GROUPS + group;
+    live[i] = lq < nqb;
+    myq[i] = sq + (live[i] ? lq : 0u) * p.wpq;
+    L[i] = 0u; R[i] = p.bwtsize;
+    if (p.start) {
+      const uint2 lr = __ldg(p.start + (myq[i][0] & kmask));
+      L[i] = lr.x; R[i] = lr.y;
+    }
+    rem[i] = live[i] ? p.nsteps : 0u;
+    aL[i] = aR[i] = FM_WD_DONE; key[i] = 0;
+    if (rem[i]) {
+      key[i] = fm_read_field64(myq[i], p.start_bits, p.wbits);
+      aL[i] = aR[i] = (uint32_t)(key[i] >> p.sub_bits);
+    }
+    busy |= rem[i] != 0u;
+  }
+
+  unsigned long long n_root = 0, n_sb = 0, n_tree = 0;
+  /* one state machine per read: aL / aR = block to fetch next for that interval end, FM_WD_DONE once the end holds its
+   * value for the next step.  Every iteration fetches one block per unfinished read: the node both ends share (always,
+   * at the grid level), else L's node, else R's. */
+  while (__any_sync(0xFFFFFFFFu, busy)) {
+    uint32_t w[QPT][8];
+    #pragma unroll
+    for (int i = 0; i < QPT; i++) {
+      if (rem[i]) {
+        const uint32_t a = (aL[i] != FM_WD_DONE) ? aL[i] : aR[i];
+        FM_BOUND(a, p.total_blocks, "wide: grid / tree block");
+        fm_wide_load(p.wblocks + (size_t) a * 8u + 2u * lg, w[i]);
+        if (COUNT && lg == 0) { if (a < p.nroots) n_root++; else n_tree++; }
+      }
+    }
+    busy = false;
+    #pragma unroll
+    for (int i = 0; i < QPT; i++) {
+      /* the lanes of a group hold the same state, so they take the same branches */
+      const bool act = rem[i] != 0u;
+      const bool doL = act && aL[i] != FM_WD_DONE;
+      const bool doR = act && (!doL || aR[i] == aL[i]);                  /* R alone, or riding on the node it shares with L */
+      const uint64_t ksub = (key[i] & submask) << p.row_bits;
+      uint32_t cL = 0, cR = 0;
+      if (act) {
+        cL = fm_wide_partial(w[i], ksub | L[i], lg);
+        cR = fm_wide_partial(w[i], ksub | R[i], lg);
+      }
+      const uint32_t hval  = __shfl_sync(0xFFFFFFFFu, w[i][0], 0, LANES);
+      const uint32_t hkind = __shfl_sync(0xFFFFFFFFu, w[i][1], 0, LANES);
+      const uint32_t vL = hval + fm_group_sum<LANES>(cL), vR = hval + fm_group_sum<LANES>(cR);
+      if (act && hkind == FM_WD_EXC) {                                   /* (only ever at a grid block: both ends are here) */
+        fm_wide_plain_step(p, key[i], L[i], R[i]);
+        if (COUNT && lg == 0) n_sb += 2ull * p.hops;
+        aL[i] = aR[i] = FM_WD_DONE;
+      } else {
+        const bool is_inner = hkind == FM_WD_INNER;
+        if (doL) { if (is_inner) aL[i] = vL; else { L[i] = vL; aL[i] = FM_WD_DONE; } }
+        if (doR) { if (is_inner) aR[i] = vR; else { R[i] = vR; aR[i] = FM_WD_DONE; } }
+      }
+      if (act && aL[i] == FM_WD_DONE && aR[i] == FM_WD_DONE) {           /* step complete: next step's block */
+        rem[i] -= 1u;
+        if (rem[i]) {
+          key[i] = fm_read_field64(myq[i], p.start_bits + (p.nsteps - rem[i]) * p.wbits, p.wbits);
+          aL[i] = aR[i] = (uint32_t)(key[i] >> p.sub_bits);
+        }
+      }
+      busy |= rem[i] != 0u;
+    }
+  }
+
+  if (lg == 0) {
+    #pragma unroll
+    for (int i = 0; i < QPT; i++)
+      if (live[i]) reinterpret_cast<uint2 *>(p.results)[q0 + i * GROUPS + group] = make_uint2(L[i], R[i]);
+  }
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) {
+      n_root += __shfl_xor_sync(0xFFFFFFFFu, n_root, o);
+      n_sb += __shfl_xor_sync(0xFFFFFFFFu, n_sb, o);
+      n_tree += __shfl_xor_sync(0xFFFFFFFFu, n_tree, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(p.fetch_counters, n_root); atomicAdd(p.fetch_counters + 1, n_sb); atomicAdd(p.fetch_counters + 2, n_tree); }
+  }
+}
+
+/* ------------------------------------------------------------------------ *
+ * Construction from SB96 (all on the device)
+ * ------------------------------------------------------------------------ */
+
+/* key[i] = wide symbol of row i (none_key for a row whose chain meets a '$' row: sorts behind every symbol),
+ * val[i] = i | y(i) << 32 with y(i) = the row the chain ends in = rank_F(F(i), i) */
+__global__ void fm_wide_compose_kernel(const uint4 *__restrict__ blocks, uint32_t nblocks, const uint8_t *__restrict__ sym,
+                                       uint32_t bwtsize, uint32_t kbits, uint32_t hops, uint64_t none_key,
+                                       uint64_t *__restrict__ keys, uint64_t *__restrict__ vals)
+{
+  const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= bwtsize) return;
+  uint32_t row = (uint32_t) i;
+  uint64_t acc = 0;
+  bool ok = true;
+  for (uint32_t h = 0; h < hops; h++) {
+    const uint32_t s = sym[row];
+    if (s == FM_SYM_NONE) { ok = false; break; }
+    acc |= (uint64_t) s << (kbits * h);
+    row = fm_sb96_rank(blocks, nblocks, s, row);
+  }
+  keys[i] = ok ? acc : none_key;
+  vals[i] = i | ((uint64_t) row << 32);
+}
+
+/* bstart[b] = first position of the sorted keys whose bucket is >= b, b = 0 .. nroots (bstart[nroots] = rows carrying a symbol) */
+__global__ void fm_wide_bstart_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint32_t sub_bits, uint32_t nroots, uint32_t *__restrict__ bstart)
+{
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nroots) return;
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) { const uint64_t mid = lo + ((hi - lo) >> 1); if ((keys[mid] >> sub_bits) < (uint64_t) b) lo = mid + 1; else hi = mid; }
+  bstart[b] = (uint32_t) lo;
+}
+
+/* g0[b] = G(smallest symbol of bucket b): the composed rank at X = 0 */
+__global__ void fm_wide_g0_kernel(const uint4 *__restrict__ blocks, uint32_t nblocks, uint32_t kbits, uint32_t hops, uint32_t sub_bits,
+                                  uint32_t nroots, uint32_t *__restrict__ g0)
+{
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nroots) return;
+  const uint64_t sigma = (uint64_t) b << sub_bits;
+  uint32_t x = 0;
+  for (uint32_t h = 0; h < hops; h++) x = fm_sb96_rank(blocks, nblocks, (uint32_t)(sigma >> (kbits * h)) & ((1u << kbits) - 1u), x);
+  g0[b] = x;
+}
+
+/* every entry must sit where the composed LF walk says: y == g0[bucket] + position in the bucket; else the bucket is exceptional */
+__global__ void fm_wide_verify_entries_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ vals, uint64_t nvalid,
+                                              uint32_t sub_bits, const uint32_t *__restrict__ bstart, const uint32_t *__restrict__ g0,
+                                              uint32_t *__restrict__ exc)
+{
+  const uint64_t j = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nvalid) return;
+  const uint32_t b = (uint32_t)(keys[j] >> sub_bits);
+  const uint32_t expect = g0[b] + ((uint32_t) j - bstart[b]);
+  if ((uint32_t)(vals[j] >> 32) != expect) atomicOr(exc + (b >> 5), 1u << (b & 31u));
+}
+
+/* the next bucket's G must continue the count (a suffix shorter than W sorting into or behind the bucket breaks it) */
+__global__ void fm_wide_verify_buckets_kernel(const uint32_t *__restrict__ bstart, const uint32_t *__restrict__ g0, uint32_t nroots,
+                                              uint32_t force_every, uint32_t *__restrict__ exc)
+{
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nroots) return;
+  bool bad = (b + 1u < nroots) && (g0[b] + (bstart[b + 1] - bstart[b]) != g0[b + 1]);
+  if (force_every && (b % force_every) == force_every - 1u) bad = true;   /* tests: exercises the exceptional path */
+  if (bad) atomicOr(exc + (b >> 5), 1u << (b & 31u));
+}
+
+/* shape of the tree over cnt > 15 entries: N[v] = nodes of level v (0 = leaves), depth D with N[D] = 1 (the root, which
+ * lives in the grid); nodes below the root = sum of N[0 .. D-1] */
+struct FmWideTree {
+  uint32_t N[FM_WD_MAXDEPTH + 1];
+  uint32_t D;
+  __host__ __device__ explicit FmWideTree(uint32_t cnt)
+  {
+    N[0] = (cnt + FM_WD_SLOTS - 1) / FM_WD_SLOTS;
+    D = 0;
+    while (N[D] > 1 && D < FM_WD_MAXDEPTH) { N[D + 1] = (N[D] + FM_WD_FAN - 1) / FM_WD_FAN; D++; }
+  }
+  __host__ __device__ uint32_t below_root() const { uint32_t t = 0; for (uint32_t v = 0; v < D; v++) t += N[v]; return t; }
+  /* offset of level v's first node inside the root's extension area (levels stored top-down: D-1 first, leaves last) */
+  __host__ __device__ uint32_t level_offset(uint32_t v) const { uint32_t t = 0; for (uint32_t u = v + 1; u < D; u++) t += N[u]; return t; }
+};
+
+struct FmWideBuild {
+  const uint64_t *keys, *vals;    /* sorted */
+  const uint32_t *bstart, *g0, *exc, *extoff;
+  uint32_t nroots, sub_bits, row_bits;
+};
+
+__device__ __forceinline__ bool fm_wide_is_exc(const FmWideBuild &x, uint32_t b) { return (x.exc[b >> 5] >> (b & 31u)) & 1u; }
+__device__ __forceinline__ uint64_t fm_wide_entry(const FmWideBuild &x, uint64_t j)
+{
+  const uint64_t submask = x.sub_bits >= 64u ? ~0ull : ((1ull << x.sub_bits) - 1ull);
+  return ((x.keys[j] & submask) << x.row_bits) | (x.vals[j] & 0xFFFFFFFFull);
+}
+
+/* pass 1: extension nodes every bucket needs (0 for a bucket that fits its block or is exceptional) */
+__global__ void __launch_bounds__(256) fm_wide_count_kernel(const FmWideBuild x, uint32_t *__restrict__ ext, unsigned long long *__restrict__ stats)
+{
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= x.nroots) return;
+  const uint32_t cnt = x.bstart[b + 1] - x.bstart[b];
+  uint32_t e = 0;
+  if (fm_wide_is_exc(x, b)) atomicAdd(stats + 3, 1ull);
+  else if (cnt > FM_WD_SLOTS) {
+    const FmWideTree t(cnt);
+    e = t.below_root();
+    atomicAdd(stats, 1ull);                                    /* overfull buckets */
+    atomicAdd(stats + 1, (unsigned long long) cnt);            /* rows living in them */
+    atomicMax(stats + 2, (unsigned long long) t.D);            /* deepest tree */
+  }
+  ext[b] = e;
+}
+
+/* one node: level v, index m, of the tree over entries [j0, j0 + cnt) of a bucket; `area` = first block of the bucket's
+ * extension area, base = G before the bucket's first entry */
+__device__ __forceinline__ void fm_wide_write_node(const FmWideBuild &x, const FmWideTree &t, uint32_t v, uint32_t m, uint64_t j0, uint32_t cnt,
+                                                   uint32_t area, uint32_t base, uint4 *__restrict__ dst)
+{
+  uint64_t w[16];
+  if (v == 0) {
+    const uint64_t first = (uint64_t) m * FM_WD_SLOTS;
+    w[0] = (uint64_t)(base + (uint32_t) first) | ((uint64_t) FM_WD_LEAF << 32);
+    #pragma unroll
+    for (uint32_t c = 1; c < 16; c++) w[c] = (first + c - 1 < cnt) ? fm_wide_entry(x, j0 + first + c - 1) : FM_WD_PAD;
+  } else {
+    uint64_t span = FM_WD_SLOTS;                               /* entries under one child: 15 * 16^(v-1) */
+    for (uint32_t u = 1; u < v; u++) span *= FM_WD_FAN;
+    w[0] = (uint64_t)(area + t.level_offset(v - 1) + m * FM_WD_FAN) | ((uint64_t) FM_WD_INNER << 32);
+    #pragma unroll
+    for (uint32_t c = 1; c < 16; c++) {
+      const uint64_t child = (uint64_t) m * FM_WD_FAN + c, at = child * span;
+      w[c] = (child < t.N[v - 1] && at < cnt) ? fm_wide_entry(x, j0 + at) : FM_WD_PAD;
+    }
+  }
+  #pragma unroll
+  for (uint32_t c = 0; c < 8; c++)
+    dst[c] = make_uint4((uint32_t) w[2 * c], (uint32_t)(w[2 * c] >> 32), (uint32_t) w[2 * c + 1], (uint32_t)(w[2 * c + 1] >> 32));
+}
+
+/* pass 2a: the grid -- a leaf, the root of a tree, or an exceptional marker; one thread per bucket */
+__global__ void __launch_bounds__(256) fm_wide_fill_roots_kernel(const FmWideBuild x, uint4 *__restrict__ wblocks)
+{
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= x.nroots) return;
+  uint4 *dst = wblocks + (size_t) b * 8u;
+  if (fm_wide_is_exc(x, b)) {
+    dst[0] = make_uint4(0u, FM_WD_EXC, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    #pragma unroll
+    for (uint32_t c = 1; c < 8; c++) dst[c] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    return;
+  }
+  const uint32_t j0 = x.bstart[b], cnt = x.bstart[b + 1] - j0;
+  const FmWideTree t(cnt);
+  fm_wide_write_node(x, t, t.D, 0u, j0, cnt, x.nroots + x.extoff[b], x.g0[b], dst);
+}
+
+/* pass 2b: the tree nodes below the grid; one thread per node.  The owning bucket is found by binary search in extoff. */
+__global__ void __launch_bounds__(256) fm_wide_fill_ext_kernel(const FmWideBuild x, uint32_t total_ext, uint4 *__restrict__ wblocks)
+{
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total_ext) return;
+  uint32_t lo = 0, hi = x.nroots;                              /* last bucket with extoff <= e: the owner (buckets without extension before it share its offset) */
+  while (hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if (x.extoff[mid] <= e) lo = mid; else hi = mid; }
+  const uint32_t b = lo;
+  const uint32_t j0 = x.bstart[b], cnt = x.bstart[b + 1] - j0;
+  const FmWideTree t(cnt);
+  uint32_t local = e - x.extoff[b], v = t.D;                   /* levels are stored top-down */
+  while (v > 0) { v--; if (local < t.N[v]) break; local -= t.N[v]; }
+  FM_BOUND(v, t.D, "wide build: level of an extension node"); FM_BOUND(local, t.N[v], "wide build: node index in its level");
+  fm_wide_write_node(x, t, v, local, j0, cnt, x.nroots + x.extoff[b], x.g0[b], wblocks + ((size_t) x.nroots + e) * 8u);
+}
+
+#endif /* FM_WIDE_CUH_ */

@@ -1,0 +1,337 @@
+/*
+ * fm_widetab.cu -- wide-step table (fm_wide.cuh): construction on the GPU, lead tables, launch plan, fetch counter.
+ * (one translation unit of libfmindex_b200.so; shared declarations in fm_internal.h)
+ */
+#include "fm_internal.h"
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <mutex>
+#include "fm_wide.cuh"
+
+extern "C" int32_t fmgpu_index_unwiden(fmgpu_index_t *idx)
+{
+  if (!idx) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null index");
+  if (idx->wblocks) {
+    CU_TRY(cudaSetDevice(idx->device));
+    cudaFree(idx->wblocks); idx->wblocks = NULL;
+    for (int b = 0; b < 16; b++) { cudaFree(idx->wlead[b]); idx->wlead[b] = NULL; }
+    idx->wlead_tried = 0;
+  }
+  idx->meta.wide_bases = 0; idx->meta.wide_prefix_bits = 0; idx->meta.wide_row_bits = 0; idx->meta.wide_bytes = 0; idx->meta.wide_blocks = 0;
+  idx->meta.wide_overflow = 0; idx->meta.wide_tree_nodes = 0; idx->meta.wide_tree_rows = 0; idx->meta.wide_tree_depth = 0;
+  idx->meta.wide_exceptional = 0;
+  fm_budget_account(idx);
+  return FM_SUCCESS;
+}
+
+static uint32_t fm_bits_for(uint32_t v) { uint32_t b = 0; while (b < 32 && (v >> b)) b++; return b ? b : 1; }
+
+/* prefix bits the automatic choice takes: the most with at least 3.75 rows per bucket on average (3.75 .. 7.5; a block holds 15) */
+static uint32_t fm_wide_auto_prefix(uint32_t n)
+{
+  uint32_t pb = 1;
+  while (pb < 30 && ((uint64_t) 15 << (pb + 1)) <= (uint64_t) n * 4) pb++;
+  return pb;
+}
+
+/* Widest step a table over this text can take: W bases, a multiple of k, at most 30 (a packed key is 60 bits), with
+ * sub_bits + row_bits <= 64 */
+static uint32_t fm_wide_max_bases(uint32_t k, uint32_t pb, uint32_t rb)
+{
+  uint32_t w = (64 + pb - rb) / 2;
+  if (w > 30) w = 30;
+  return w - w % k;
+}
+
+/* Step width for reads of `len` bases: the fewest wide steps S with len = b + S * W for a lead table of b <= 12 bases
+ * (134 MB at most), W <= wmax a multiple of k; the smallest such b (the lead table then stays in L2).  On a 2-step index
+ * an odd b ends with the derived 1-step rank (tail_ok).  0 when no such width exists (reads shorter than 16 bases are
+ * not worth a table). */
+static uint32_t fm_wide_bases_for_len(uint32_t k, uint32_t len, uint32_t wmax, bool tail_ok)
+{
+  if (len < 16 || wmax < 8) return 0;
+  for (uint32_t S = 1; S <= len / 8; S++)
+    for (uint32_t b = 0; b <= 12 && b < len; b++) {
+      if ((len - b) % S) continue;
+      const uint32_t w = (len - b) / S;
+      if (w > wmax || w < 8 || w % k) continue;
+      if (b % k && !(k == 2 && tail_ok)) continue;
+      return w;
+    }
+  return 0;
+}
+
+extern "C" uint32_t fmgpu_wide_bases_for(const fmgpu_index_t *idx, uint32_t len)
+{
+  if (!idx) return 0;
+  const uint32_t n = idx->meta.bwtsize, rb = fm_bits_for(n), pb = fm_wide_auto_prefix(n);
+  if (idx->meta.quirk_mask) return 0;
+  return fm_wide_bases_for_len(idx->meta.steps, len, fm_wide_max_bases(idx->meta.steps, pb, rb), idx->meta.tail_valid != 0);
+}
+
+extern "C" int32_t fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, uint32_t prefix_bits)
+{
+  if (!idx) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null index");
+  if (idx->wblocks) return FM_SUCCESS;
+  if (idx->meta.quirk_mask) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "AltCounters file with an active padding quirk: the sparse-step table serves it");
+  CU_TRY(cudaSetDevice(idx->device));
+  const uint32_t k = idx->meta.steps, n = idx->meta.bwtsize, kbits = 2 * k;
+  const uint32_t rb = fm_bits_for(n);
+  uint32_t pb = prefix_bits ? prefix_bits : fm_wide_auto_prefix(n);
+  if (pb > 30) return fm_fail_msg(FM_E_BAD_ARGUMENT, "at most 30 prefix bits");
+  uint32_t W = wide_bases ? wide_bases : fm_wide_max_bases(k, pb, rb);
+  if (W % k || W < 2 * k || W > 30) return fm_fail_msg(FM_E_BAD_ARGUMENT, "wide bases must be a multiple of k, at least 2k and at most 30");
+  const uint32_t wbits = 2 * W;
+  if (pb > wbits) pb = wbits;
+  const uint32_t sub_bits = wbits - pb;
+  if (sub_bits + rb > 64) return fm_fail_msg(FM_E_BAD_ARGUMENT, "wide step too wide for this text: (2 * bases - prefix_bits) + bits of a row number must fit 64");
+  const uint32_t hops = W / k, nroots = 1u << pb;
+  const uint64_t none_key = 1ull << wbits;
+
+  const uint64_t nrows = (uint64_t) idx->meta.nblocks * FM_SB_ROWS;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = ~(size_t) 0; }
+  const uint64_t build_peak = 32ull * n + nrows + 16ull * nroots + (1ull << 30);
+  const uint64_t final_peak = 16ull * n + 16ull * nroots + (uint64_t) nroots * 128 + (uint64_t) n / 14 * 128 / 8 + (1ull << 30);
+  if ((build_peak > final_peak ? build_peak : final_peak) > free_b)
+    return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "not enough free device memory to build the wide-step table");
+  if (!fm_budget_allows(idx, (uint64_t) nroots * 128)) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "the wide-step table would exceed the derived-table budget");
+
+  uint8_t *sym = NULL; uint64_t *keys = NULL, *vals = NULL, *keys2 = NULL, *vals2 = NULL;
+  uint32_t *bstart = NULL, *g0 = NULL, *exc = NULL, *ext = NULL, *extoff = NULL;
+  uint4 *wblocks = NULL; void *tmp = NULL; unsigned long long *d_stats = NULL;
+  size_t tmp_bytes = 0, tmp2 = 0;
+  unsigned long long stats[4] = { 0, 0, 0, 0 };
+  uint32_t total_ext = 0, nvalid = 0;
+  const char *fenv = getenv("FMGPU_WIDE_FORCE_EXC");           /* tests: every N-th bucket is made exceptional */
+  const uint32_t force_every = fenv && *fenv ? (uint32_t) atoi(fenv) : 0u;
+  cudaError_t e = cudaMalloc((void **) &sym, nrows);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &keys, 8ull * n);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &vals, 8ull * n);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &keys2, 8ull * n);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &vals2, 8ull * n);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &d_stats, 32);
+  if (e == cudaSuccess) e = cudaMemset(d_stats, 0, 32);
+  if (e == cudaSuccess) e = fm_row_symbols(idx, nrows, sym);
+  if (e == cudaSuccess) {
+    fm_wide_compose_kernel<<<(unsigned)(((uint64_t) n + 255) / 256), 256>>>(idx->blocks, idx->meta.nblocks, sym, n, kbits, hops, none_key, keys, vals);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(NULL, tmp_bytes, keys, keys2, vals, vals2, (int64_t) n, 0, (int)(wbits + 1));
+  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(NULL, tmp2, (uint32_t *) NULL, (uint32_t *) NULL, (int64_t) nroots);
+  if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
+  if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16);
+  /* order of (F(i), i): the sort is stable and the input rows ascend */
+  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int64_t) n, 0, (int)(wbits + 1));
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaFree(keys); keys = NULL; cudaFree(vals); vals = NULL; cudaFree(sym); sym = NULL;
+  if (e == cudaSuccess) e = cudaMalloc((void **) &bstart, 4ull * ((uint64_t) nroots + 1));
+  if (e == cudaSuccess) e = cudaMalloc((void **) &g0, 4ull * nroots);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &exc, 4ull * ((nroots + 31) / 32));
+  if (e == cudaSuccess) e = cudaMemset(exc, 0, 4ull * ((nroots + 31) / 32));
+  if (e == cudaSuccess) e = cudaMalloc((void **) &ext, 4ull * nroots);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &extoff, 4ull * nroots);
+  if (e == cudaSuccess) {
+    fm_wide_bstart_kernel<<<(nroots + 1 + 255) / 256, 256>>>(keys2, n, sub_bits, nroots, bstart);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) {
+    fm_wide_g0_kernel<<<(nroots + 255) / 256, 256>>>(idx->blocks, idx->meta.nblocks, kbits, hops, sub_bits, nroots, g0);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(&nvalid, bstart + nroots, 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && nvalid) {
+    fm_wide_verify_entries_kernel<<<(unsigned)(((uint64_t) nvalid + 255) / 256), 256>>>(keys2, vals2, nvalid, sub_bits, bstart, g0, exc);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) {
+    fm_wide_verify_buckets_kernel<<<(nroots + 255) / 256, 256>>>(bstart, g0, nroots, force_every, exc);
+    e = cudaGetLastError();
+  }
+  FmWideBuild x;
+  x.keys = keys2; x.vals = vals2; x.bstart = bstart; x.g0 = g0; x.exc = exc; x.extoff = extoff;
+  x.nroots = nroots; x.sub_bits = sub_bits; x.row_bits = rb;
+  if (e == cudaSuccess) {
+    fm_wide_count_kernel<<<(nroots + 255) / 256, 256>>>(x, ext, d_stats);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, ext, extoff, (int64_t) nroots);
+  if (e == cudaSuccess) {
+    uint32_t last_off = 0, last_ext = 0;
+    e = cudaMemcpy(&last_off, extoff + (nroots - 1), 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(&last_ext, ext + (nroots - 1), 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(stats, d_stats, 32, cudaMemcpyDeviceToHost);
+    total_ext = last_off + last_ext;                             /* <= n / 14 + ...: far below 2^32 */
+  }
+  cudaFree(ext); ext = NULL;
+  const uint64_t total_blocks = (uint64_t) nroots + total_ext;
+  if (e == cudaSuccess && total_blocks >= 0xFFFFFFF0ull) e = cudaErrorInvalidValue;
+  bool over_budget = false;
+  if (e == cudaSuccess && !fm_budget_allows(idx, total_blocks * 128)) over_budget = true;
+  if (e == cudaSuccess && !over_budget) e = cudaMalloc((void **) &wblocks, total_blocks * 128);
+  if (e == cudaSuccess && !over_budget) {
+    fm_wide_fill_roots_kernel<<<(nroots + 255) / 256, 256>>>(x, wblocks);
+    e = cudaGetLastError();
+    if (e == cudaSuccess && total_ext) {
+      fm_wide_fill_ext_kernel<<<(total_ext + 255) / 256, 256>>>(x, total_ext, wblocks);
+      e = cudaGetLastError();
+    }
+  }
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaFree(sym); cudaFree(keys); cudaFree(vals); cudaFree(keys2); cudaFree(vals2); cudaFree(bstart); cudaFree(g0); cudaFree(exc);
+  cudaFree(ext); cudaFree(extoff); cudaFree(tmp); cudaFree(d_stats);
+  if (over_budget) { cudaFree(wblocks); return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "the wide-step table would exceed the derived-table budget"); }
+  if (e != cudaSuccess) {
+    cudaFree(wblocks);
+    cudaGetLastError();                                          /* a failed cudaMalloc stays "last error" otherwise and fails the next attempt's first check */
+    if (e == cudaErrorMemoryAllocation) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "not enough device memory for the wide-step table (the other kernels still serve this index)");
+    return fm_fail(e, "fmgpu_index_widen", __FILE__, __LINE__);
+  }
+  idx->wblocks = wblocks;
+  idx->meta.wide_bases = W; idx->meta.wide_prefix_bits = pb; idx->meta.wide_row_bits = rb;
+  idx->meta.wide_blocks = total_blocks; idx->meta.wide_bytes = total_blocks * 128;
+  idx->meta.wide_overflow = stats[0]; idx->meta.wide_tree_rows = stats[1]; idx->meta.wide_tree_depth = (uint32_t) stats[2];
+  idx->meta.wide_tree_nodes = total_ext; idx->meta.wide_exceptional = stats[3];
+  fm_budget_account(idx);
+  return FM_SUCCESS;
+}
+
+/* Lead table of width b: (L,R) of every b-mer, computed by the plain Coop kernel (a packed b-mer is its own key).  On a
+ * 2-step index an odd width ends with the derived 1-step rank.  NULL when the width is not representable or memory is short. */
+static std::mutex g_wlead_mutex;
+static const uint2 *fm_wide_lead(fmgpu_index_t *idx, uint32_t b)
+{
+  if (b < 1 || b >= 16) return NULL;
+  std::lock_guard<std::mutex> lock(g_wlead_mutex);
+  if (idx->wlead[b]) return idx->wlead[b];
+  if (idx->wlead_tried & (1u << b)) return NULL;
+  idx->wlead_tried |= 1u << b;
+  const uint32_t k = idx->meta.steps;
+  if (b % k && !(k == 2 && idx->meta.tail_valid)) return NULL;
+  if (cudaSetDevice(idx->device) != cudaSuccess) { cudaGetLastError(); return NULL; }
+  const uint32_t nkeys = 1u << (2 * b);
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return NULL; }
+  if ((uint64_t) nkeys * 12 + (1ull << 30) > free_b || !fm_budget_allows(idx, (uint64_t) nkeys * 8)) return NULL;
+  if (b % k) fm_build_tail(idx);
+  uint32_t *skeys = NULL; uint2 *table = NULL;
+  cudaError_t e = cudaMalloc((void **) &skeys, (size_t) nkeys * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &table, (size_t) nkeys * 8);
+  if (e == cudaSuccess) { fm_iota_kernel<<<(nkeys + 255) / 256, 256>>>(skeys, nkeys); e = cudaGetLastError(); }
+  int32_t rc = FM_SUCCESS;
+  fmgpu_variant_t v = FM_DEFAULT_VARIANT;
+  v.mode = FMGPU_MODE_COOP; v.queries_per_thread = 1; v.threads_per_block = 256;
+  if (e == cudaSuccess) rc = fm_launch_search(idx, skeys, nkeys, b, (uint32_t *) table, &v, 0, NULL);
+  if (e == cudaSuccess && rc == FM_SUCCESS) e = cudaDeviceSynchronize();
+  cudaFree(skeys);
+  if (e != cudaSuccess || rc != FM_SUCCESS) { cudaFree(table); cudaGetLastError(); return NULL; }
+  idx->wlead[b] = table; idx->meta.wide_bytes += (uint64_t) nkeys * 8;
+  return table;
+}
+
+/* The plan of a wide search of `len`-base reads on a table of W-base steps: len = b + S * W with a lead table of b bases
+ * (0 = none: the search starts from the whole BWT), the fewest steps first.  false = this table does not serve the length. */
+struct fm_wide_plan { uint32_t S, b; };
+static bool fm_wide_plan_for(const fmgpu_index_t *idx, uint32_t len, fm_wide_plan *pl)
+{
+  const uint32_t W = idx->meta.wide_bases, k = idx->meta.steps;
+  if (!idx->wblocks || !W || len == 0) return false;
+  const char *env = getenv("FMGPU_WIDE_LEAD_MAX");             /* widest lead table a plan may use (default 15 bases = 8.6 GB; 12 = 134 MB) */
+  const uint32_t maxlead = env && *env ? (uint32_t) atoi(env) : 15u;
+  for (uint32_t S = 0; S <= len / W; S++) {
+    if (len < S * W) break;
+    const uint32_t b = len - S * W;
+    if (b >= 16 || b > maxlead) continue;
+    if (b % k && !(k == 2 && idx->meta.tail_valid)) continue;
+    if (S == 0 && b == 0) continue;
+    pl->S = S; pl->b = b;
+    return true;
+  }
+  return false;
+}
+
+extern "C" int32_t fmgpu_index_wide_serves(const fmgpu_index_t *idx, uint32_t len)
+{
+  fm_wide_plan pl;
+  if (!idx || !fm_wide_plan_for(idx, len, &pl)) return 0;
+  return (pl.b == 0 || idx->wlead[pl.b]) ? 1 : 0;
+}
+
+void fm_wide_prepare(fmgpu_index_t *idx, uint32_t len)
+{
+  fm_wide_plan pl;
+  if (!fm_wide_plan_for(idx, len, &pl)) return;
+  if (pl.b) fm_wide_lead(idx, pl.b);
+  fm_budget_account(idx);
+}
+
+typedef void (*fm_wide_fn)(const FmWideParams);
+static fm_wide_fn fm_pick_wide(int qpt)
+{
+  if (qpt == 0) return fm_search_wide_kernel<1, 256, 4, true>;         /* instrumented */
+  if (qpt == 1) return fm_search_wide_kernel<1, 256, 6, false>;
+  if (qpt == 2) return fm_search_wide_kernel<2, 256, 4, false>;
+  if (qpt == 3) return fm_search_wide_kernel<3, 256, 3, false>;
+  if (qpt == 4) return fm_search_wide_kernel<4, 256, 2, false>;
+  return NULL;
+}
+
+int32_t fm_launch_wide(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nq, uint32_t len,
+                       uint32_t *d_results, fmgpu_variant_t v, cudaStream_t stream, unsigned long long *d_counters)
+{
+  if (!idx->wblocks) return fm_fail_msg(FM_E_BAD_ARGUMENT, "FMGPU_MODE_WIDE needs fmgpu_index_widen() on this replica first");
+  fm_wide_plan pl;
+  if (!fm_wide_plan_for(idx, len, &pl))
+    return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "this wide-step table does not serve the read length (length = lead bases (< 16) + whole steps); see fmgpu_index_wide_serves");
+  if (pl.b && !idx->wlead[pl.b])
+    return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "the lead table of this read length has not been built: call fmgpu_index_prepare(idx, len) first");
+  const uint32_t k = idx->meta.steps, W = idx->meta.wide_bases;
+  if (v.queries_per_thread < 1 || v.queries_per_thread > 4) v.queries_per_thread = 2;
+  FmWideParams p;
+  p.wblocks = idx->wblocks; p.blocks = idx->blocks; p.packed = d_packed; p.results = d_results;
+  p.nblocks = idx->meta.nblocks; p.nq = (uint32_t) nq; p.nsteps = pl.S;
+  p.wpq = fmgpu_words_per_query(len); p.bwtsize = idx->meta.bwtsize;
+  p.wbits = 2 * W; p.sub_bits = 2 * W - idx->meta.wide_prefix_bits; p.row_bits = idx->meta.wide_row_bits;
+  p.hops = W / k; p.kbits = 2 * k;
+  p.nroots = 1u << idx->meta.wide_prefix_bits; p.total_blocks = (uint32_t) idx->meta.wide_blocks;
+  p.start = pl.b ? idx->wlead[pl.b] : NULL; p.start_bits = 2 * pl.b;
+  p.fetch_counters = d_counters;
+  if (d_counters) v.queries_per_thread = 1;
+  uint32_t qper; size_t smem;
+  for (;;) {
+    qper = (256 / FM_WD_LANES) * v.queries_per_thread;
+    smem = 16 + ((size_t) qper * p.wpq + 4) * 4;
+    if (smem <= 200 * 1024) break;
+    if (v.queries_per_thread > 1) v.queries_per_thread -= 1;
+    else return fm_fail_msg(FM_E_QUERY_SHAPE, "reads too long to stage in shared memory");
+  }
+  fm_wide_fn fn = fm_pick_wide(d_counters ? 0 : v.queries_per_thread);
+  if (!fn) return fm_fail_msg(FM_E_BAD_ARGUMENT, "no wide kernel for this variant");
+  if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  const uint32_t grid = (uint32_t)((nq + qper - 1) / qper);
+  void *args[] = { (void *) &p };
+  CU_TRY(cudaLaunchKernel((const void *) fn, dim3(grid), dim3(256), args, smem, stream));
+  return FM_SUCCESS;
+}
+
+extern "C" int32_t fmgpu_count_fetches_wide_device(const fmgpu_index_t *idx, const uint32_t *d_packed, uint64_t nq, uint32_t len,
+                                                   uint32_t *d_results, void *stream, uint64_t *ngrid_blocks, uint64_t *nsb96_blocks,
+                                                   uint64_t *ntree_blocks)
+{
+  if (!idx || !d_packed || !d_results) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null argument");
+  CU_TRY(cudaSetDevice(idx->device));
+  unsigned long long *d_c = NULL, h[3] = { 0, 0, 0 };
+  CU_TRY(cudaMalloc((void **) &d_c, 24));
+  CU_TRY(cudaMemsetAsync(d_c, 0, 24, (cudaStream_t) stream));
+  int32_t rc = nq ? fm_launch_wide(idx, d_packed, nq, len, d_results, FM_DEFAULT_VARIANT, (cudaStream_t) stream, d_c) : FM_SUCCESS;
+  if (rc == FM_SUCCESS) {
+    cudaError_t e = cudaMemcpyAsync(h, d_c, 24, cudaMemcpyDeviceToHost, (cudaStream_t) stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t) stream);
+    if (e != cudaSuccess) rc = fm_fail(e, "fetch counters D2H", __FILE__, __LINE__);
+  }
+  cudaFree(d_c);
+  if (ngrid_blocks) *ngrid_blocks = h[0];
+  if (nsb96_blocks) *nsb96_blocks = h[1];
+  if (ntree_blocks) *ntree_blocks = h[2];
+  return rc;
+}
