@@ -186,7 +186,7 @@ def test_wide_steps_repetitive_texts_search_trees(pkg, tmp_path, name, k):
         b = pkg.DeviceBatch(0, reads.size // length, length, k)
         b.upload_ascii(reads)
         for w in widths:
-            for pbits in (0, 4):
+            for pbits in (0, max(4, 2 * w + 15 - 64)):           # (entry = rest of the symbol + a 15-bit row number: 64 bits at most)
                 idx.widen(w, pbits)
                 m = idx.meta
                 saw_overflow |= m.wide_overflow > 0
