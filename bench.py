@@ -466,7 +466,7 @@ def run_single_process(args, pkg, L, torch, emit):
                              "table_build_s_per_gpu": [st.table_build_s[g] for g in range(ndev)], "queries_h2d_pack_s": st.queries_h2d_pack_s,
                              "results_d2h_s": d2h_s, "transferCPUtoGPU_s": transfer_s, "setup_s": round(setup_s, 1),
                              "index_md5": md5, "index_is_the_reference_builders_file": (md5 == want_md5) if want_md5 else None, "results_md5": res_md5},
-          "kernel_config": {"kernel": (f"wide: {meta.wide_bases} bases/step, 128-byte blocks, 2^{meta.wide_prefix_bits} buckets" if meta.wide_bases else
+          "kernel_config": {"kernel": (f"wide: {meta.wide_bases} bases/step, {32 * meta.wide_lanes}-byte blocks, 2^{meta.wide_prefix_bits} buckets" if meta.wide_bases else
                                        f"sparse: {meta.sparse_bases} bases/step, grid of {meta.sparse_uniform_nb} blocks per symbol"),
                             "table_gb": (meta.wide_bytes if meta.wide_bases else meta.sparse_bytes) / 1e9},
           "cpu_baseline": {"value": mq_cpu, "unit": "Mqueries/s", "cores": cores, "kind": CPU_KIND,
@@ -614,7 +614,7 @@ def main():
             wb = int(os.environ.get("FM_BENCH_WIDE_BASES", "0")) or index.wide_bases_for(READ_LEN)
             if not wb:
                 raise pkg.FMError(19, "no wide step width serves this read length")
-            index.widen(wb, int(os.environ.get("FM_BENCH_WIDE_PREFIX_BITS", "0")))
+            index.widen(wb, int(os.environ.get("FM_BENCH_WIDE_PREFIX_BITS", "0")), int(os.environ.get("FM_BENCH_WIDE_LANES", "0")))
             index.prepare(READ_LEN)
             torch.cuda.synchronize()
             setup["widen_s"] = round(time.time() - t0, 3)
@@ -666,7 +666,7 @@ def main():
         pkg.check(L.fmgpu_count_fetches_wide_device(index.handle, d_packed.data_ptr(), nq, READ_LEN, d_res.data_ptr(), stream,
                                                     C.byref(nfb), C.byref(nlb), C.byref(ntree)), "count wide fetches")
     tabled = fused or sparse or wide
-    block_bytes = 128 if wide else 32 * (meta.sparse_lanes if sparse else meta.fused_lanes) if tabled else 16
+    block_bytes = 32 * meta.wide_lanes if wide else 32 * (meta.sparse_lanes if sparse else meta.fused_lanes) if tabled else 16
     table_fetches = (nfb.value + ntree.value) if tabled else nblk.value
     sb96_fetches = nlb.value if tabled else 0
     all_fetches = table_fetches + sb96_fetches
@@ -676,7 +676,6 @@ def main():
     # measured random-access ceiling over the footprint the timed kernel walks (rank 0, once)
     footprint = int(meta.wide_bytes) if wide else int(meta.sparse_bytes) if sparse else int(meta.fused_bytes) if fused else int(meta.nbytes)
     probe = pkg.gather_probe(dev, footprint, 256, 2) if rank == 0 else 0.0
-    probe_line = pkg.gather_probe(dev, footprint, 256, 2, 128) if (rank == 0 and wide) else None   # whole 128-byte lines, one per 8 lanes
 
     # the plain 2-step kernel on the same reads, for reference next to the timed one (rank-local, not the headline); its (L,R)
     # over the WHOLE batch are the full-size parity check of the timed kernel (the plain kernel itself is pinned on the reference below)
@@ -888,10 +887,10 @@ def main():
         traffic, traffic_src = ncu_traffic("wide" if wide else "sparse" if sparse else "fused" if fused else "plain")
         e2e_value = world * nq / e2e_ms_step / 1e3
         ceiling_mq = host_bw * 1e3 / READ_LEN if host_bw > 0 else None
-        kernel_desc = (f"wide: {meta.wide_bases} bases/step, 128-byte blocks of 15 64-bit entries (rest of the symbol + row), block = top {meta.wide_prefix_bits} bits of the "
+        kernel_desc = (f"wide: {meta.wide_bases} bases/step, {32 * meta.wide_lanes}-byte blocks of {4 * meta.wide_lanes - 1} 64-bit entries (rest of the symbol + row), block = top {meta.wide_prefix_bits} bits of the "
                        f"wide symbol (computed from the read, shared by both interval ends), {READ_LEN - (READ_LEN // meta.wide_bases) * meta.wide_bases}-base lead table, "
                        f"{meta.wide_overflow} overfull buckets as search trees ({meta.wide_tree_nodes} blocks, depth {meta.wide_tree_depth}), {meta.wide_exceptional} exceptional buckets on plain steps, "
-                       f"4 x 256-bit loads, one state machine per read, qpt={var.queries_per_thread or 2}" if wide else
+                       f"{meta.wide_lanes} x 256-bit loads, one state machine per read, qpt={var.queries_per_thread or 1}" if wide else
                        f"sparse: {meta.sparse_bases} bases/step, {32 * meta.sparse_lanes}-byte blocks of occurrence rows (lambda {meta.sparse_lambda}), {meta.sparse_lanes} x 256-bit loads, "
                        + (f"{meta.sparse_start_bases}-base start table + lead tables, " if meta.sparse_start_bases else "lead tables (no start table at this width), ")
                        + f"uniform grid of {meta.sparse_uniform_nb} blocks per symbol (no directory lookup), {meta.sparse_overflow} overfull buckets as search trees "
@@ -921,7 +920,6 @@ def main():
                          "traffic_over_algorithmic": (traffic / kernel_bytes) if traffic else None,
                          "request_rate_frac": (all_fetches / (ms_step * 1e-3)) / probe if probe else None,
                          "request_rate": {"block_fetches_per_s": all_fetches / (ms_step * 1e-3), "probe_accesses_per_s": probe,
-                                          "probe_128byte_lines_per_s": probe_line,
                                           "how": "independent uniform random 16-byte loads over a table of the same footprint; the binding limit is a request RATE "
                                                  "(L2 miss path, profiles/r02_ceiling_counters.md), the same for 64- and 128-byte fills -- which is why frac of the byte "
                                                  "roofline stays near one half although the kernel wastes nothing (traffic_over_algorithmic ~ 1)"},

@@ -250,6 +250,8 @@ typedef struct {
   uint64_t wide_tree_nodes;    /* blocks below the grid                                          */
   uint64_t wide_tree_rows;     /* rows living in trees (of bwtsize)                              */
   uint64_t wide_exceptional;   /* buckets whose steps run on the block table (a suffix shorter than the step sorts into them) */
+  uint32_t wide_lanes;         /* lanes per block: 2 = 64-byte blocks (7 entries), 4 = 128-byte blocks (15 entries) */
+  uint32_t reserved2;
 } fmgpu_index_meta_t;
 
 /* what the last transferCPUtoGPU / searchIndexGPU / transferGPUtoCPU sequence of this process did (wall-clock seconds of
@@ -331,7 +333,7 @@ int32_t fmgpu_index_unsparsify(fmgpu_index_t *idx);
  * bases): fmgpu_wide_bases_for(idx, len) names the width to build for a length, fmgpu_index_wide_serves(idx, len) tells
  * whether an existing table (with its lead table, see fmgpu_index_prepare) does.  AltCounters files with an active padding
  * quirk are refused (FM_E_NOT_IMPLEMENTED, like memory or budget shortage): the sparse-step table serves them. */
-int32_t  fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, uint32_t prefix_bits);
+int32_t  fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, uint32_t prefix_bits, uint32_t lanes);
 int32_t  fmgpu_index_unwiden(fmgpu_index_t *idx);
 uint32_t fmgpu_wide_bases_for(const fmgpu_index_t *idx, uint32_t len);      /* 0 = no width serves this length */
 int32_t  fmgpu_index_wide_serves(const fmgpu_index_t *idx, uint32_t len);   /* 1 / 0 */

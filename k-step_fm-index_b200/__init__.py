@@ -79,7 +79,8 @@ class fmgpu_index_meta_t(C.Structure):
                 ("reserved1", C.c_uint32), ("derived_bytes", C.c_uint64), ("budget_bytes", C.c_uint64),
                 ("wide_bases", C.c_uint32), ("wide_prefix_bits", C.c_uint32), ("wide_row_bits", C.c_uint32), ("wide_tree_depth", C.c_uint32),
                 ("wide_bytes", C.c_uint64), ("wide_blocks", C.c_uint64), ("wide_overflow", C.c_uint64),
-                ("wide_tree_nodes", C.c_uint64), ("wide_tree_rows", C.c_uint64), ("wide_exceptional", C.c_uint64)]
+                ("wide_tree_nodes", C.c_uint64), ("wide_tree_rows", C.c_uint64), ("wide_exceptional", C.c_uint64),
+                ("wide_lanes", C.c_uint32), ("reserved2", C.c_uint32)]
 
 
 class fmgpu_transfer_stats_t(C.Structure):
@@ -139,7 +140,7 @@ PROTOTYPES = {
     "fmgpu_index_unfuse": (C.c_int32, [_VP]),
     "fmgpu_index_sparsify": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, C.c_uint32]),
     "fmgpu_index_unsparsify": (C.c_int32, [_VP]),
-    "fmgpu_index_widen": (C.c_int32, [_VP, C.c_uint32, C.c_uint32]),
+    "fmgpu_index_widen": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, C.c_uint32]),
     "fmgpu_index_unwiden": (C.c_int32, [_VP]),
     "fmgpu_wide_bases_for": (C.c_uint32, [_VP, C.c_uint32]),
     "fmgpu_index_wide_serves": (C.c_int32, [_VP, C.c_uint32]),
@@ -398,9 +399,9 @@ class DeviceIndex:
     def unsparsify(self):
         check(lib().fmgpu_index_unsparsify(self.handle), "fmgpu_index_unsparsify")
 
-    def widen(self, wide_bases=0, prefix_bits=0):
-        """Builds the wide-step table (up to 30 bases per 128-byte block fetch, both interval ends in one block) for MODE_WIDE searches."""
-        check(lib().fmgpu_index_widen(self.handle, wide_bases, prefix_bits), "fmgpu_index_widen")
+    def widen(self, wide_bases=0, prefix_bits=0, lanes=0):
+        """Builds the wide-step table (up to 30 bases per 64/128-byte block fetch, both interval ends in one block) for MODE_WIDE searches."""
+        check(lib().fmgpu_index_widen(self.handle, wide_bases, prefix_bits, lanes), "fmgpu_index_widen")
         return self
 
     def unwiden(self):

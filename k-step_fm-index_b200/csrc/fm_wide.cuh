@@ -52,13 +52,13 @@
 #define FM_WD_INNER    1u
 #define FM_WD_EXC      2u
 #define FM_WD_DONE     0xFFFFFFFFu
-#define FM_WD_SLOTS    15u
-#define FM_WD_FAN      16u
-#define FM_WD_MAXDEPTH 8                   /* 15 * 16^8 entries > 2^32 rows */
-#define FM_WD_LANES    4
+#define FM_WD_MAXDEPTH 11                  /* 7 * 8^11 entries > 2^32 rows (64-byte blocks); 15 * 16^8 for 128-byte blocks */
+/* block = 32 * LANES bytes = 4 * LANES u64: a header + SLOTS = 4 * LANES - 1 entries; inner nodes have SLOTS + 1 children.
+ * LANES = 4: 128-byte blocks (15 entries), LANES = 2: 64-byte blocks (7 entries, 64-byte L2 fills): half the lanes,
+ * instructions and DRAM bytes per read for the same number of requests, but twice the buckets for the same occupancy. */
 
 struct FmWideParams {
-  const uint4    *wblocks;    /* grid + tree nodes, 8 uint4 (128 bytes) per block                          */
+  const uint4    *wblocks;    /* grid + tree nodes, 2 * LANES uint4 (64 or 128 bytes) per block            */
   const uint4    *blocks;     /* SB96: the steps of exceptional buckets                                     */
   const uint32_t *packed;
   uint32_t       *results;
@@ -78,11 +78,12 @@ struct FmWideParams {
   unsigned long long *fetch_counters;  /* COUNT only: [0] grid blocks, [1] SB96 blocks (exceptional buckets), [2] tree nodes below the grid */
 };
 
-/* the whole 128-byte line of a block is used: default fill */
-__device__ __forceinline__ void fm_wide_load(const uint4 *p, uint32_t (&w)[8])
+/* one 256-bit load per lane.  128-byte blocks use the whole line (default fill); 64-byte blocks ask for a 64-byte fill */
+template <int LANES> __device__ __forceinline__ void fm_wide_load(const uint4 *p, uint32_t (&w)[8])
 {
-  asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+  if (LANES == 2) fm_ldg32(p, w);
+  else asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                    : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
 }
 
 /* bits [pos, pos + nbits) of a packed read in shared memory, nbits <= 64 (one readable spare word behind the read) */
@@ -151,12 +152,12 @@ __device__ __forceinline__ void fm_wide_plain_step(const FmWideParams &p, uint64
   }
 }
 
-template <int QPT, int THREADS, int MINB, bool COUNT>
+template <int LANES, int QPT, int THREADS, int MINB, bool COUNT>
 __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_kernel(const FmWideParams p)
 {
   extern __shared__ __align__(16) uint32_t fsm[];             /* [0..3]: mbarrier + pad; [4..): packed reads, natural stride */
   uint32_t *sq = fsm + 4;
-  constexpr int LANES = FM_WD_LANES, GROUPS = THREADS / LANES;
+  constexpr int GROUPS = THREADS / LANES;
   const uint32_t q0 = blockIdx.x * (GROUPS * QPT);
   const uint32_t nqb = min((uint32_t)(GROUPS * QPT), p.nq - q0);
   const uint32_t lg = threadIdx.x % LANES, group = threadIdx.x / LANES;
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_kernel(const FmW
       if (rem[i]) {
         const uint32_t a = (aL[i] != FM_WD_DONE) ? aL[i] : aR[i];
         FM_BOUND(a, p.total_blocks, "wide: grid / tree block");
-        fm_wide_load(p.wblocks + (size_t) a * 8u + 2u * lg, w[i]);
+        fm_wide_load<LANES>(p.wblocks + (size_t) a * (2u * LANES) + 2u * lg, w[i]);
         if (COUNT && lg == 0) { if (a < p.nroots) n_root++; else n_tree++; }
       }
     }
@@ -237,6 +238,128 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_kernel(const FmW
         }
       }
       busy |= rem[i] != 0u;
+    }
+  }
+
+  if (lg == 0) {
+    #pragma unroll
+    for (int i = 0; i < QPT; i++)
+      if (live[i]) reinterpret_cast<uint2 *>(p.results)[q0 + i * GROUPS + group] = make_uint2(L[i], R[i]);
+  }
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) {
+      n_root += __shfl_xor_sync(0xFFFFFFFFu, n_root, o);
+      n_sb += __shfl_xor_sync(0xFFFFFFFFu, n_sb, o);
+      n_tree += __shfl_xor_sync(0xFFFFFFFFu, n_tree, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(p.fetch_counters, n_root); atomicAdd(p.fetch_counters + 1, n_sb); atomicAdd(p.fetch_counters + 2, n_tree); }
+  }
+}
+
+/* ------------------------------------------------------------------------ *
+ * Burst kernel.  The block of a wide step is a function of the READ alone (the top bits of that step's 2W-bit field),
+ * not of the interval: the S grid blocks a read needs are known before its search starts.  So a lane group issues its
+ * lead-table lookup and up to PF block loads of each of its QPT reads back to back -- S independent requests in flight
+ * per read instead of a chain of S dependent ones -- and then evaluates the steps in order from registers.  Only a step
+ * whose grid block is the root of a search tree (or exceptional) continues with dependent fetches (fm_wide_slow_step),
+ * 1 % of the steps on a random text.  Reads with more than PF steps run in chunks of PF.
+ * ------------------------------------------------------------------------ */
+template <int LANES> __device__ __forceinline__ uint32_t fm_wide_group_sum(uint32_t v, uint32_t gmask)
+{
+  #pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+  return v;
+}
+
+/* a step whose grid block (w, already loaded) is not a leaf: exceptional -> plain steps; inner -> walk the tree, the two
+ * interval ends apart once they leave a node.  Called by the lanes of ONE group (others may be elsewhere): shuffles are
+ * confined to the group's mask. */
+template <int LANES, bool COUNT>
+__device__ __forceinline__ void fm_wide_slow_step(const FmWideParams &p, const uint32_t (&w)[8], uint32_t hval, uint32_t hkind, uint64_t key,
+                                                  uint64_t ksub, uint32_t lg, uint32_t gmask, uint32_t &L, uint32_t &R,
+                                                  unsigned long long &n_sb, unsigned long long &n_tree)
+{
+  if (hkind == FM_WD_EXC) {
+    fm_wide_plain_step(p, key, L, R);
+    if (COUNT && lg == 0) n_sb += 2ull * p.hops;
+    return;
+  }
+  uint32_t aL = hval + fm_wide_group_sum<LANES>(fm_wide_partial(w, ksub | L, lg), gmask);
+  uint32_t aR = hval + fm_wide_group_sum<LANES>(fm_wide_partial(w, ksub | R, lg), gmask);
+  while (aL != FM_WD_DONE || aR != FM_WD_DONE) {
+    const uint32_t a = (aL != FM_WD_DONE) ? aL : aR;
+    uint32_t t[8];
+    FM_BOUND(a, p.total_blocks, "wide (burst): tree block");
+    fm_wide_load<LANES>(p.wblocks + (size_t) a * (2u * LANES) + 2u * lg, t);
+    if (COUNT && lg == 0) n_tree++;
+    const bool doL = aL != FM_WD_DONE;
+    const bool doR = !doL || aR == aL;
+    const uint32_t hv = __shfl_sync(gmask, t[0], 0, LANES), hk = __shfl_sync(gmask, t[1], 0, LANES);
+    const uint32_t vL = hv + fm_wide_group_sum<LANES>(fm_wide_partial(t, ksub | L, lg), gmask);
+    const uint32_t vR = hv + fm_wide_group_sum<LANES>(fm_wide_partial(t, ksub | R, lg), gmask);
+    const bool is_inner = hk == FM_WD_INNER;
+    if (doL) { if (is_inner) aL = vL; else { L = vL; aL = FM_WD_DONE; } }
+    if (doR) { if (is_inner) aR = vR; else { R = vR; aR = FM_WD_DONE; } }
+  }
+}
+
+template <int LANES, int QPT, int PF, int THREADS, int MINB, bool COUNT>
+__global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_burst_kernel(const FmWideParams p)
+{
+  extern __shared__ __align__(16) uint32_t fsm[];             /* [0..3]: mbarrier + pad; [4..): packed reads, natural stride */
+  uint32_t *sq = fsm + 4;
+  constexpr int GROUPS = THREADS / LANES;
+  const uint32_t q0 = blockIdx.x * (GROUPS * QPT);
+  const uint32_t nqb = min((uint32_t)(GROUPS * QPT), p.nq - q0);
+  const uint32_t lg = threadIdx.x % LANES, group = threadIdx.x / LANES;
+  const uint32_t gmask = ((1u << LANES) - 1u) << ((threadIdx.x & 31u) & ~(uint32_t)(LANES - 1));
+  const uint64_t submask = p.sub_bits >= 64u ? ~0ull : ((1ull << p.sub_bits) - 1ull);
+
+  fm_stage_reads<THREADS>(fsm, sq, p.packed + (size_t) q0 * p.wpq, nqb * p.wpq);
+
+  uint32_t L[QPT], R[QPT];
+  const uint32_t *myq[QPT];
+  bool live[QPT];
+  const uint32_t kmask = (p.start_bits >= 32u) ? 0xFFFFFFFFu : ((1u << p.start_bits) - 1u);
+  #pragma unroll
+  for (int i = 0; i < QPT; i++) {
+    const uint32_t lq = i * GROUPS + group;
+    live[i] = lq < nqb;
+    myq[i] = sq + (live[i] ? lq : 0u) * p.wpq;                 /* a dead slot repeats the CTA's first read (valid addresses, no store) */
+    uint2 lr = make_uint2(0u, p.bwtsize);
+    if (p.start) lr = __ldg(p.start + (myq[i][0] & kmask));    /* (in flight together with the block loads below: first used by the first compare) */
+    L[i] = lr.x; R[i] = lr.y;
+  }
+  unsigned long long n_root = 0, n_sb = 0, n_tree = 0;
+  for (uint32_t base = 0; base < p.nsteps; base += PF) {
+    uint32_t w[QPT][PF][8];
+    #pragma unroll
+    for (int s = 0; s < PF; s++) {
+      if (base + s < p.nsteps) {
+        #pragma unroll
+        for (int i = 0; i < QPT; i++) {
+          const uint32_t a = (uint32_t)(fm_read_field64(myq[i], p.start_bits + (base + s) * p.wbits, p.wbits) >> p.sub_bits);
+          FM_BOUND(a, p.nroots, "wide (burst): grid block");
+          fm_wide_load<LANES>(p.wblocks + (size_t) a * (2u * LANES) + 2u * lg, w[i][s]);
+        }
+      }
+    }
+    #pragma unroll
+    for (int s = 0; s < PF; s++) {
+      if (base + s < p.nsteps) {                                /* uniform over the grid: all lanes of a warp take it together */
+        #pragma unroll
+        for (int i = 0; i < QPT; i++) {
+          const uint64_t key = fm_read_field64(myq[i], p.start_bits + (base + s) * p.wbits, p.wbits);
+          const uint64_t ksub = (key & submask) << p.row_bits;
+          const uint32_t cL = fm_wide_partial(w[i][s], ksub | L[i], lg), cR = fm_wide_partial(w[i][s], ksub | R[i], lg);
+          const uint32_t hval  = __shfl_sync(0xFFFFFFFFu, w[i][s][0], 0, LANES);
+          const uint32_t hkind = __shfl_sync(0xFFFFFFFFu, w[i][s][1], 0, LANES);
+          const uint32_t sL = fm_group_sum<LANES>(cL), sR = fm_group_sum<LANES>(cR);
+          if (COUNT && lg == 0 && live[i]) n_root++;
+          if (hkind == FM_WD_LEAF) { L[i] = hval + sL; R[i] = hval + sR; }
+          else fm_wide_slow_step<LANES, COUNT>(p, w[i][s], hval, hkind, key, ksub, lg, gmask, L[i], R[i], n_sb, n_tree);
+        }
+      }
     }
   }
 
@@ -327,14 +450,15 @@ __global__ void fm_wide_verify_buckets_kernel(const uint32_t *__restrict__ bstar
 
 /* shape of the tree over cnt > 15 entries: N[v] = nodes of level v (0 = leaves), depth D with N[D] = 1 (the root, which
  * lives in the grid); nodes below the root = sum of N[0 .. D-1] */
-struct FmWideTree {
+template <int LANES> struct FmWideTree {
+  static constexpr uint32_t SLOTS = 4u * LANES - 1u, FAN = 4u * LANES;
   uint32_t N[FM_WD_MAXDEPTH + 1];
   uint32_t D;
   __host__ __device__ explicit FmWideTree(uint32_t cnt)
   {
-    N[0] = (cnt + FM_WD_SLOTS - 1) / FM_WD_SLOTS;
+    N[0] = (cnt + SLOTS - 1) / SLOTS;
     D = 0;
-    while (N[D] > 1 && D < FM_WD_MAXDEPTH) { N[D + 1] = (N[D] + FM_WD_FAN - 1) / FM_WD_FAN; D++; }
+    while (N[D] > 1 && D < FM_WD_MAXDEPTH) { N[D + 1] = (N[D] + FAN - 1) / FAN; D++; }
   }
   __host__ __device__ uint32_t below_root() const { uint32_t t = 0; for (uint32_t v = 0; v < D; v++) t += N[v]; return t; }
   /* offset of level v's first node inside the root's extension area (levels stored top-down: D-1 first, leaves last) */
@@ -355,6 +479,7 @@ __device__ __forceinline__ uint64_t fm_wide_entry(const FmWideBuild &x, uint64_t
 }
 
 /* pass 1: extension nodes every bucket needs (0 for a bucket that fits its block or is exceptional) */
+template <int LANES>
 __global__ void __launch_bounds__(256) fm_wide_count_kernel(const FmWideBuild x, uint32_t *__restrict__ ext, unsigned long long *__restrict__ stats)
 {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -362,8 +487,8 @@ __global__ void __launch_bounds__(256) fm_wide_count_kernel(const FmWideBuild x,
   const uint32_t cnt = x.bstart[b + 1] - x.bstart[b];
   uint32_t e = 0;
   if (fm_wide_is_exc(x, b)) atomicAdd(stats + 3, 1ull);
-  else if (cnt > FM_WD_SLOTS) {
-    const FmWideTree t(cnt);
+  else if (cnt > FmWideTree<LANES>::SLOTS) {
+    const FmWideTree<LANES> t(cnt);
     e = t.below_root();
     atomicAdd(stats, 1ull);                                    /* overfull buckets */
     atomicAdd(stats + 1, (unsigned long long) cnt);            /* rows living in them */
@@ -374,48 +499,52 @@ __global__ void __launch_bounds__(256) fm_wide_count_kernel(const FmWideBuild x,
 
 /* one node: level v, index m, of the tree over entries [j0, j0 + cnt) of a bucket; `area` = first block of the bucket's
  * extension area, base = G before the bucket's first entry */
-__device__ __forceinline__ void fm_wide_write_node(const FmWideBuild &x, const FmWideTree &t, uint32_t v, uint32_t m, uint64_t j0, uint32_t cnt,
+template <int LANES>
+__device__ __forceinline__ void fm_wide_write_node(const FmWideBuild &x, const FmWideTree<LANES> &t, uint32_t v, uint32_t m, uint64_t j0, uint32_t cnt,
                                                    uint32_t area, uint32_t base, uint4 *__restrict__ dst)
 {
-  uint64_t w[16];
+  constexpr uint32_t WORDS = 4u * LANES, SLOTS = WORDS - 1u, FAN = WORDS;
+  uint64_t w[WORDS];
   if (v == 0) {
-    const uint64_t first = (uint64_t) m * FM_WD_SLOTS;
+    const uint64_t first = (uint64_t) m * SLOTS;
     w[0] = (uint64_t)(base + (uint32_t) first) | ((uint64_t) FM_WD_LEAF << 32);
     #pragma unroll
-    for (uint32_t c = 1; c < 16; c++) w[c] = (first + c - 1 < cnt) ? fm_wide_entry(x, j0 + first + c - 1) : FM_WD_PAD;
+    for (uint32_t c = 1; c < WORDS; c++) w[c] = (first + c - 1 < cnt) ? fm_wide_entry(x, j0 + first + c - 1) : FM_WD_PAD;
   } else {
-    uint64_t span = FM_WD_SLOTS;                               /* entries under one child: 15 * 16^(v-1) */
-    for (uint32_t u = 1; u < v; u++) span *= FM_WD_FAN;
-    w[0] = (uint64_t)(area + t.level_offset(v - 1) + m * FM_WD_FAN) | ((uint64_t) FM_WD_INNER << 32);
+    uint64_t span = SLOTS;                                     /* entries under one child: SLOTS * FAN^(v-1) */
+    for (uint32_t u = 1; u < v; u++) span *= FAN;
+    w[0] = (uint64_t)(area + t.level_offset(v - 1) + m * FAN) | ((uint64_t) FM_WD_INNER << 32);
     #pragma unroll
-    for (uint32_t c = 1; c < 16; c++) {
-      const uint64_t child = (uint64_t) m * FM_WD_FAN + c, at = child * span;
+    for (uint32_t c = 1; c < WORDS; c++) {
+      const uint64_t child = (uint64_t) m * FAN + c, at = child * span;
       w[c] = (child < t.N[v - 1] && at < cnt) ? fm_wide_entry(x, j0 + at) : FM_WD_PAD;
     }
   }
   #pragma unroll
-  for (uint32_t c = 0; c < 8; c++)
+  for (uint32_t c = 0; c < 2u * LANES; c++)
     dst[c] = make_uint4((uint32_t) w[2 * c], (uint32_t)(w[2 * c] >> 32), (uint32_t) w[2 * c + 1], (uint32_t)(w[2 * c + 1] >> 32));
 }
 
 /* pass 2a: the grid -- a leaf, the root of a tree, or an exceptional marker; one thread per bucket */
+template <int LANES>
 __global__ void __launch_bounds__(256) fm_wide_fill_roots_kernel(const FmWideBuild x, uint4 *__restrict__ wblocks)
 {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= x.nroots) return;
-  uint4 *dst = wblocks + (size_t) b * 8u;
+  uint4 *dst = wblocks + (size_t) b * (2u * LANES);
   if (fm_wide_is_exc(x, b)) {
     dst[0] = make_uint4(0u, FM_WD_EXC, 0xFFFFFFFFu, 0xFFFFFFFFu);
     #pragma unroll
-    for (uint32_t c = 1; c < 8; c++) dst[c] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    for (uint32_t c = 1; c < 2u * LANES; c++) dst[c] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
     return;
   }
   const uint32_t j0 = x.bstart[b], cnt = x.bstart[b + 1] - j0;
-  const FmWideTree t(cnt);
-  fm_wide_write_node(x, t, t.D, 0u, j0, cnt, x.nroots + x.extoff[b], x.g0[b], dst);
+  const FmWideTree<LANES> t(cnt);
+  fm_wide_write_node<LANES>(x, t, t.D, 0u, j0, cnt, x.nroots + x.extoff[b], x.g0[b], dst);
 }
 
 /* pass 2b: the tree nodes below the grid; one thread per node.  The owning bucket is found by binary search in extoff. */
+template <int LANES>
 __global__ void __launch_bounds__(256) fm_wide_fill_ext_kernel(const FmWideBuild x, uint32_t total_ext, uint4 *__restrict__ wblocks)
 {
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -424,11 +553,11 @@ __global__ void __launch_bounds__(256) fm_wide_fill_ext_kernel(const FmWideBuild
   while (hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if (x.extoff[mid] <= e) lo = mid; else hi = mid; }
   const uint32_t b = lo;
   const uint32_t j0 = x.bstart[b], cnt = x.bstart[b + 1] - j0;
-  const FmWideTree t(cnt);
+  const FmWideTree<LANES> t(cnt);
   uint32_t local = e - x.extoff[b], v = t.D;                   /* levels are stored top-down */
   while (v > 0) { v--; if (local < t.N[v]) break; local -= t.N[v]; }
   FM_BOUND(v, t.D, "wide build: level of an extension node"); FM_BOUND(local, t.N[v], "wide build: node index in its level");
-  fm_wide_write_node(x, t, v, local, j0, cnt, x.nroots + x.extoff[b], x.g0[b], wblocks + ((size_t) x.nroots + e) * 8u);
+  fm_wide_write_node<LANES>(x, t, v, local, j0, cnt, x.nroots + x.extoff[b], x.g0[b], wblocks + ((size_t) x.nroots + e) * (2u * LANES));
 }
 
 #endif /* FM_WIDE_CUH_ */

@@ -19,19 +19,25 @@ extern "C" int32_t fmgpu_index_unwiden(fmgpu_index_t *idx)
   }
   idx->meta.wide_bases = 0; idx->meta.wide_prefix_bits = 0; idx->meta.wide_row_bits = 0; idx->meta.wide_bytes = 0; idx->meta.wide_blocks = 0;
   idx->meta.wide_overflow = 0; idx->meta.wide_tree_nodes = 0; idx->meta.wide_tree_rows = 0; idx->meta.wide_tree_depth = 0;
-  idx->meta.wide_exceptional = 0;
+  idx->meta.wide_exceptional = 0; idx->meta.wide_lanes = 0;
   fm_budget_account(idx);
   return FM_SUCCESS;
 }
 
 static uint32_t fm_bits_for(uint32_t v) { uint32_t b = 0; while (b < 32 && (v >> b)) b++; return b ? b : 1; }
 
-/* prefix bits the automatic choice takes: the most with at least 3.75 rows per bucket on average (3.75 .. 7.5; a block holds 15) */
-static uint32_t fm_wide_auto_prefix(uint32_t n)
+/* prefix bits the automatic choice takes: the most with at least a quarter of a block's slots filled on average (3.75 .. 7.5
+ * rows per 15-slot block, 1.875 .. 3.75 per 7-slot block: ~17 .. 34 bytes per text base either way) */
+static uint32_t fm_wide_auto_prefix(uint32_t n, uint32_t lanes)
 {
   uint32_t pb = 1;
-  while (pb < 30 && ((uint64_t) 15 << (pb + 1)) <= (uint64_t) n * 4) pb++;
-  return pb;
+  while (pb < 29 && ((uint64_t) 15 << (pb + 1)) <= (uint64_t) n * 4) pb++;
+  return pb + (lanes == 2 ? 1u : 0u);
+}
+static uint32_t fm_wide_default_lanes(void)
+{
+  const char *env = getenv("FMGPU_WIDE_LANES");
+  return env && *env && atoi(env) == 4 ? 4u : 2u;
 }
 
 /* Widest step a table over this text can take: W bases, a multiple of k, at most 30 (a packed key is 60 bits), with
@@ -64,12 +70,24 @@ static uint32_t fm_wide_bases_for_len(uint32_t k, uint32_t len, uint32_t wmax, b
 extern "C" uint32_t fmgpu_wide_bases_for(const fmgpu_index_t *idx, uint32_t len)
 {
   if (!idx) return 0;
-  const uint32_t n = idx->meta.bwtsize, rb = fm_bits_for(n), pb = fm_wide_auto_prefix(n);
+  const uint32_t n = idx->meta.bwtsize, rb = fm_bits_for(n), pb = fm_wide_auto_prefix(n, fm_wide_default_lanes());
   if (idx->meta.quirk_mask) return 0;
   return fm_wide_bases_for_len(idx->meta.steps, len, fm_wide_max_bases(idx->meta.steps, pb, rb), idx->meta.tail_valid != 0);
 }
 
-extern "C" int32_t fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, uint32_t prefix_bits)
+template <int LANES>
+static cudaError_t fm_wide_fill(const FmWideBuild &x, uint32_t total_ext, uint4 *wblocks)
+{
+  fm_wide_fill_roots_kernel<LANES><<<(x.nroots + 255) / 256, 256>>>(x, wblocks);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && total_ext) {
+    fm_wide_fill_ext_kernel<LANES><<<(total_ext + 255) / 256, 256>>>(x, total_ext, wblocks);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+extern "C" int32_t fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, uint32_t prefix_bits, uint32_t lanes)
 {
   if (!idx) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null index");
   if (idx->wblocks) return FM_SUCCESS;
@@ -77,7 +95,10 @@ extern "C" int32_t fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, ui
   CU_TRY(cudaSetDevice(idx->device));
   const uint32_t k = idx->meta.steps, n = idx->meta.bwtsize, kbits = 2 * k;
   const uint32_t rb = fm_bits_for(n);
-  uint32_t pb = prefix_bits ? prefix_bits : fm_wide_auto_prefix(n);
+  if (lanes == 0) lanes = fm_wide_default_lanes();
+  if (lanes != 2 && lanes != 4) return fm_fail_msg(FM_E_BAD_ARGUMENT, "wide block lanes must be 2 (64-byte blocks, 7 entries) or 4 (128-byte blocks, 15 entries)");
+  const uint32_t bbytes = 32 * lanes;
+  uint32_t pb = prefix_bits ? prefix_bits : fm_wide_auto_prefix(n, lanes);
   if (pb > 30) return fm_fail_msg(FM_E_BAD_ARGUMENT, "at most 30 prefix bits");
   uint32_t W = wide_bases ? wide_bases : fm_wide_max_bases(k, pb, rb);
   if (W % k || W < 2 * k || W > 30) return fm_fail_msg(FM_E_BAD_ARGUMENT, "wide bases must be a multiple of k, at least 2k and at most 30");
@@ -92,10 +113,10 @@ extern "C" int32_t fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, ui
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = ~(size_t) 0; }
   const uint64_t build_peak = 32ull * n + nrows + 16ull * nroots + (1ull << 30);
-  const uint64_t final_peak = 16ull * n + 16ull * nroots + (uint64_t) nroots * 128 + (uint64_t) n / 14 * 128 / 8 + (1ull << 30);
+  const uint64_t final_peak = 16ull * n + 16ull * nroots + (uint64_t) nroots * bbytes + (uint64_t) n / 6 * bbytes / 8 + (1ull << 30);
   if ((build_peak > final_peak ? build_peak : final_peak) > free_b)
     return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "not enough free device memory to build the wide-step table");
-  if (!fm_budget_allows(idx, (uint64_t) nroots * 128)) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "the wide-step table would exceed the derived-table budget");
+  if (!fm_budget_allows(idx, (uint64_t) nroots * bbytes)) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "the wide-step table would exceed the derived-table budget");
 
   uint8_t *sym = NULL; uint64_t *keys = NULL, *vals = NULL, *keys2 = NULL, *vals2 = NULL;
   uint32_t *bstart = NULL, *g0 = NULL, *exc = NULL, *ext = NULL, *extoff = NULL;
@@ -152,7 +173,8 @@ extern "C" int32_t fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, ui
   x.keys = keys2; x.vals = vals2; x.bstart = bstart; x.g0 = g0; x.exc = exc; x.extoff = extoff;
   x.nroots = nroots; x.sub_bits = sub_bits; x.row_bits = rb;
   if (e == cudaSuccess) {
-    fm_wide_count_kernel<<<(nroots + 255) / 256, 256>>>(x, ext, d_stats);
+    if (lanes == 4) fm_wide_count_kernel<4><<<(nroots + 255) / 256, 256>>>(x, ext, d_stats);
+    else            fm_wide_count_kernel<2><<<(nroots + 255) / 256, 256>>>(x, ext, d_stats);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, ext, extoff, (int64_t) nroots);
@@ -167,16 +189,9 @@ extern "C" int32_t fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, ui
   const uint64_t total_blocks = (uint64_t) nroots + total_ext;
   if (e == cudaSuccess && total_blocks >= 0xFFFFFFF0ull) e = cudaErrorInvalidValue;
   bool over_budget = false;
-  if (e == cudaSuccess && !fm_budget_allows(idx, total_blocks * 128)) over_budget = true;
-  if (e == cudaSuccess && !over_budget) e = cudaMalloc((void **) &wblocks, total_blocks * 128);
-  if (e == cudaSuccess && !over_budget) {
-    fm_wide_fill_roots_kernel<<<(nroots + 255) / 256, 256>>>(x, wblocks);
-    e = cudaGetLastError();
-    if (e == cudaSuccess && total_ext) {
-      fm_wide_fill_ext_kernel<<<(total_ext + 255) / 256, 256>>>(x, total_ext, wblocks);
-      e = cudaGetLastError();
-    }
-  }
+  if (e == cudaSuccess && !fm_budget_allows(idx, total_blocks * bbytes)) over_budget = true;
+  if (e == cudaSuccess && !over_budget) e = cudaMalloc((void **) &wblocks, total_blocks * bbytes);
+  if (e == cudaSuccess && !over_budget) e = lanes == 4 ? fm_wide_fill<4>(x, total_ext, wblocks) : fm_wide_fill<2>(x, total_ext, wblocks);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   cudaFree(sym); cudaFree(keys); cudaFree(vals); cudaFree(keys2); cudaFree(vals2); cudaFree(bstart); cudaFree(g0); cudaFree(exc);
   cudaFree(ext); cudaFree(extoff); cudaFree(tmp); cudaFree(d_stats);
@@ -189,7 +204,7 @@ extern "C" int32_t fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, ui
   }
   idx->wblocks = wblocks;
   idx->meta.wide_bases = W; idx->meta.wide_prefix_bits = pb; idx->meta.wide_row_bits = rb;
-  idx->meta.wide_blocks = total_blocks; idx->meta.wide_bytes = total_blocks * 128;
+  idx->meta.wide_blocks = total_blocks; idx->meta.wide_bytes = total_blocks * bbytes; idx->meta.wide_lanes = lanes;
   idx->meta.wide_overflow = stats[0]; idx->meta.wide_tree_rows = stats[1]; idx->meta.wide_tree_depth = (uint32_t) stats[2];
   idx->meta.wide_tree_nodes = total_ext; idx->meta.wide_exceptional = stats[3];
   fm_budget_account(idx);
@@ -266,13 +281,33 @@ void fm_wide_prepare(fmgpu_index_t *idx, uint32_t len)
 }
 
 typedef void (*fm_wide_fn)(const FmWideParams);
+template <int LANES>
 static fm_wide_fn fm_pick_wide(int qpt)
 {
-  if (qpt == 0) return fm_search_wide_kernel<1, 256, 4, true>;         /* instrumented */
-  if (qpt == 1) return fm_search_wide_kernel<1, 256, 6, false>;
-  if (qpt == 2) return fm_search_wide_kernel<2, 256, 4, false>;
-  if (qpt == 3) return fm_search_wide_kernel<3, 256, 3, false>;
-  if (qpt == 4) return fm_search_wide_kernel<4, 256, 2, false>;
+  if (qpt == 0) return fm_search_wide_kernel<LANES, 1, 256, 4, true>;         /* instrumented */
+  if (qpt == 1) return fm_search_wide_kernel<LANES, 1, 256, 6, false>;
+  if (qpt == 2) return fm_search_wide_kernel<LANES, 2, 256, 4, false>;
+  if (qpt == 3) return fm_search_wide_kernel<LANES, 3, 256, 3, false>;
+  if (qpt == 4) return fm_search_wide_kernel<LANES, 4, 256, 2, false>;
+  return NULL;
+}
+
+/* burst kernels (all grid blocks of a read in flight at once): QPT reads per lane group x up to PF blocks per read and chunk */
+template <int LANES>
+static fm_wide_fn fm_pick_wide_burst(int qpt, int pf)
+{
+  if (qpt == 0) return fm_search_wide_burst_kernel<LANES, 1, 3, 256, 4, true>;   /* instrumented */
+  if (pf <= 3) {
+    if (qpt == 1) return fm_search_wide_burst_kernel<LANES, 1, 3, 256, 4, false>;
+    if (qpt == 2) return fm_search_wide_burst_kernel<LANES, 2, 3, 256, 2, false>;
+    if (qpt == 3) return fm_search_wide_burst_kernel<LANES, 3, 3, 256, 2, false>;
+    if (qpt == 4) return fm_search_wide_burst_kernel<LANES, 4, 3, 256, 1, false>;
+  } else {
+    if (qpt == 1) return fm_search_wide_burst_kernel<LANES, 1, 4, 256, 4, false>;
+    if (qpt == 2) return fm_search_wide_burst_kernel<LANES, 2, 4, 256, 2, false>;
+    if (qpt == 3) return fm_search_wide_burst_kernel<LANES, 3, 4, 256, 2, false>;
+    if (qpt == 4) return fm_search_wide_burst_kernel<LANES, 4, 4, 256, 1, false>;
+  }
   return NULL;
 }
 
@@ -285,8 +320,8 @@ int32_t fm_launch_wide(const fmgpu_index_t *idx, const uint32_t *d_packed, uint6
     return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "this wide-step table does not serve the read length (length = lead bases (< 16) + whole steps); see fmgpu_index_wide_serves");
   if (pl.b && !idx->wlead[pl.b])
     return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "the lead table of this read length has not been built: call fmgpu_index_prepare(idx, len) first");
-  const uint32_t k = idx->meta.steps, W = idx->meta.wide_bases;
-  if (v.queries_per_thread < 1 || v.queries_per_thread > 4) v.queries_per_thread = 2;
+  const uint32_t k = idx->meta.steps, W = idx->meta.wide_bases, lanes = idx->meta.wide_lanes;
+  if (v.queries_per_thread < 1 || v.queries_per_thread > 4) v.queries_per_thread = 1;
   FmWideParams p;
   p.wblocks = idx->wblocks; p.blocks = idx->blocks; p.packed = d_packed; p.results = d_results;
   p.nblocks = idx->meta.nblocks; p.nq = (uint32_t) nq; p.nsteps = pl.S;
@@ -299,13 +334,21 @@ int32_t fm_launch_wide(const fmgpu_index_t *idx, const uint32_t *d_packed, uint6
   if (d_counters) v.queries_per_thread = 1;
   uint32_t qper; size_t smem;
   for (;;) {
-    qper = (256 / FM_WD_LANES) * v.queries_per_thread;
+    qper = (256 / lanes) * v.queries_per_thread;
     smem = 16 + ((size_t) qper * p.wpq + 4) * 4;
     if (smem <= 200 * 1024) break;
     if (v.queries_per_thread > 1) v.queries_per_thread -= 1;
     else return fm_fail_msg(FM_E_QUERY_SHAPE, "reads too long to stage in shared memory");
   }
-  fm_wide_fn fn = fm_pick_wide(d_counters ? 0 : v.queries_per_thread);
+  /* $FMGPU_WIDE_BURST=1: the burst kernel instead of the chained state-machine kernel (one dependent fetch per iteration) --
+   * measured slower so far (profiles/r02_wide_sweep.jsonl): fewer reads fit an SM with all their blocks in registers;
+   * $FMGPU_WIDE_PF: blocks per read and chunk the burst kernel keeps in flight (3 or 4; default: 3 up to three steps, else 4) */
+  const char *benv = getenv("FMGPU_WIDE_BURST"), *penv = getenv("FMGPU_WIDE_PF");
+  const bool burst = benv && *benv && atoi(benv) != 0;
+  const int pf = penv && *penv ? atoi(penv) : (pl.S <= 3 ? 3 : 4);
+  const int qsel = d_counters ? 0 : v.queries_per_thread;
+  fm_wide_fn fn = burst ? (lanes == 4 ? fm_pick_wide_burst<4>(qsel, pf) : fm_pick_wide_burst<2>(qsel, pf))
+                        : (lanes == 4 ? fm_pick_wide<4>(qsel) : fm_pick_wide<2>(qsel));
   if (!fn) return fm_fail_msg(FM_E_BAD_ARGUMENT, "no wide kernel for this variant");
   if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   const uint32_t grid = (uint32_t)((nq + qper - 1) / qper);
