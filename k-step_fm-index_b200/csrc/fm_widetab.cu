@@ -100,6 +100,20 @@ extern "C" int32_t fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, ui
   const uint32_t bbytes = 32 * lanes;
   uint32_t pb = prefix_bits ? prefix_bits : fm_wide_auto_prefix(n, lanes);
   if (pb > 30) return fm_fail_msg(FM_E_BAD_ARGUMENT, "at most 30 prefix bits");
+  if (!prefix_bits && pb < 30) {
+    /* roomy grid: one more prefix bit (half the rows per bucket: 0.3 % instead of 8 % of the steps meet a search tree on a
+     * random text, +9 % reads/s at 2 Gbp, profiles/r02_wide_sweep.jsonl) when the doubled grid still is a modest share of
+     * this device's memory (40 %: 68.7 GB of a B200 for 2 Gbp) and fits the table budget; $FMGPU_WIDE_ROOMY=0/1 forces */
+    size_t fb = 0, tb = 0;
+    const char *renv = getenv("FMGPU_WIDE_ROOMY");
+    bool roomy = false;
+    if (renv && *renv) roomy = atoi(renv) != 0;
+    else if (cudaMemGetInfo(&fb, &tb) == cudaSuccess)
+      roomy = ((uint64_t) bbytes << (pb + 1)) <= (uint64_t) tb * 2 / 5 && ((uint64_t) bbytes << (pb + 1)) + 16ull * n + (2ull << 30) <= fb &&
+              fm_budget_allows(idx, ((uint64_t) bbytes << (pb + 1)) + ((uint64_t) bbytes << (pb - 3)));
+    else cudaGetLastError();
+    if (roomy) pb += 1;
+  }
   uint32_t W = wide_bases ? wide_bases : fm_wide_max_bases(k, pb, rb);
   if (W % k || W < 2 * k || W > 30) return fm_fail_msg(FM_E_BAD_ARGUMENT, "wide bases must be a multiple of k, at least 2k and at most 30");
   const uint32_t wbits = 2 * W;

@@ -264,7 +264,7 @@ def test_wide_lead_table_and_fetch_counter(pkg, k):
     idx = bld.to_index().widen()
     bld.free()
     m = idx.meta
-    assert (m.wide_bases, m.wide_lanes, m.wide_prefix_bits, m.wide_row_bits) == (30, 2, 23, 25)
+    assert (m.wide_bases, m.wide_lanes, m.wide_prefix_bits, m.wide_row_bits) == (30, 2, 24, 25)   # (roomy grid: 1.2 rows per 7-entry bucket)
     assert m.wide_exceptional <= 64 and m.wide_tree_rows < n // 20
     L = pkg.lib()
     rng = np.random.default_rng(5)
@@ -325,15 +325,19 @@ def test_wide_config3_full_size_against_reference_checksums(pkg):
         assert idx.wide_bases_for(length) == 30
         idx.widen()
         m = idx.meta
-        assert (m.wide_bases, m.wide_lanes, m.wide_prefix_bits, m.wide_row_bits) == (30, 2, 29, 31) and m.wide_bytes < 42e9
-        assert m.wide_exceptional <= 64 and m.wide_tree_rows < n // 8
+        assert (m.wide_bases, m.wide_lanes, m.wide_prefix_bits, m.wide_row_bits) == (30, 2, 30, 31) and m.wide_bytes < 72e9   # roomy grid
+        assert m.wide_exceptional <= 64 and m.wide_tree_rows < n // 100
         for qpt in (1, 2, 3):
             batch.search(idx, pkg.variant(pkg.MODE_WIDE, qpt))
             assert helpers.results_text_md5(batch.download()) == gold["md5"][key], f"tag {tag} qpt {qpt}"
         idx.unwiden()
-        idx.widen(0, 0, 4)                                      # 128-byte blocks: 2^28 buckets of 15 entries
+        os.environ["FMGPU_WIDE_ROOMY"] = "0"
+        try:
+            idx.widen(0, 0, 4)                                  # 128-byte blocks, compact grid: 2^28 buckets of 15 entries
+        finally:
+            del os.environ["FMGPU_WIDE_ROOMY"]
         m = idx.meta
-        assert (m.wide_bases, m.wide_lanes, m.wide_prefix_bits) == (30, 4, 28)
+        assert (m.wide_bases, m.wide_lanes, m.wide_prefix_bits) == (30, 4, 28) and m.wide_bytes < 36e9
         batch.search(idx, pkg.variant(pkg.MODE_WIDE, 1))
         assert helpers.results_text_md5(batch.download()) == gold["md5"][key], f"tag {tag} 128-byte blocks"
         idx.free()
