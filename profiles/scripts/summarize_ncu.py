@@ -10,6 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 GO = os.path.join(ROOT, "gpurun_out")
+TIMED = os.environ.get("FM_TIMED_KERNEL", "fm_search_wide_kernel<2, 1, 256, 6, 0>")     # bench.py's timed kernel (r01 / early r02: fm_search_sparse_kernel<2, 2, 3, 256, 4, 0>)
 PR = os.path.join(ROOT, "profiles")
 
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__sectors_read.sum",
@@ -46,11 +47,11 @@ def launches(tag):
         # is launched there), the small grids are the 512 K-read chunks of the end-to-end pipeline
         per = collections.OrderedDict()
         for r in rows[1:]:
-            if r[ix["Metric Name"]] == "gpu__time_duration.sum" and "fm_search_sparse_kernel<2, 2, 3, 256, 4, 0>" in r[ix["Kernel Name"]]:
+            if r[ix["Metric Name"]] == "gpu__time_duration.sum" and TIMED in r[ix["Kernel Name"]]:
                 ns = float(r[ix["Metric Value"]]) * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}.get(r[ix["Metric Unit"]], 1)
                 per.setdefault(r[ix["Grid Size"]], []).append(ns)
         if per:
-            f.write("\n## The timed kernel, `fm_search_sparse_kernel<2, 2, 3, 256, 4, 0>`, by grid\n\n"
+            f.write(f"\n## The timed kernel, `{TIMED}`, by grid\n\n"
                     "| grid | launches | mean ms per launch | where |\n|---|---:|---:|---|\n")
             for g, v in sorted(per.items(), key=lambda kv: -max(kv[1])):
                 big = max(v) > 1e6
