@@ -53,11 +53,14 @@ def launches(tag):
         if per:
             f.write(f"\n## The timed kernel, `{TIMED}`, by grid\n\n"
                     "| grid | launches | mean ms per launch | where |\n|---|---:|---:|---|\n")
-            for g, v in sorted(per.items(), key=lambda kv: -max(kv[1])):
-                big = max(v) > 1e6
-                f.write(f"| {g} | {len(v)} | {sum(v) / len(v) / 1e6:.3f} | "
-                        + ("`value` region: one launch over the rank's 10 M reads = one step (warm-up + timed steps); it is the only kernel "
-                           "launched there, i.e. 100 % of the step" if big else "end-to-end pipeline (`e2e`), one launch per 512 K-read chunk (or tail chunk)") + " |\n")
+            def blocks(g): return int(g.strip("()").split(",")[0])
+            top = max(blocks(g) for g in per)
+            for g, v in sorted(per.items(), key=lambda kv: -blocks(kv[0])):
+                where = ("`value` region: one launch over the rank's 10 M reads = one step (warm-up + timed steps); it is the only kernel "
+                         "launched there, i.e. 100 % of the step" if blocks(g) == top else
+                         "`skewed_text` extra key (4 M reads on the 400 Mbp repeat-rich text)" if blocks(g) * 10 > top * 3 else
+                         "end-to-end pipeline (`e2e`), one launch per 512 K-read chunk (or tail chunk)")
+                f.write(f"| {g} | {len(v)} | {sum(v) / len(v) / 1e6:.3f} | {where} |\n")
 
 
 def full(tag, name):
