@@ -238,7 +238,13 @@ extern "C" int32_t fmgpu_pipeline_search_host(fmgpu_pipeline_t *pp, fmgpu_index_
         if (first_rc.load() == FM_SUCCESS) { first_rc.store(frc); snprintf(first_err, sizeof first_err, "%s", fmgpu_last_error()); }
       }
     };
+    /* replicas that share a device share its lanes (a test arrangement: "logical shards"): one thread then issues all chunks,
+     * in order -- two feeders would interleave their copies into the same staging buffers */
+    bool shared_device = false;
+    for (int a = 0; a < nrep; a++)
+      for (int b = a + 1; b < nrep; b++) shared_device |= replicas[a]->device == replicas[b]->device;
     if (nrep == 1) feeder(0);
+    else if (shared_device) { for (int g = 0; g < nrep; g++) feeder(g); }
     else {
       std::vector<std::thread> th;
       for (int g = 0; g < nrep; g++) th.emplace_back(feeder, g);

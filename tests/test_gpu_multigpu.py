@@ -61,7 +61,7 @@ def _devices_env(pkg):
     return ndev, ",".join(str(i) for i in range(ndev))
 
 
-@pytest.mark.parametrize("mode", ["auto", "sparse", "fused", "task"])
+@pytest.mark.parametrize("mode", ["auto", "wide", "sparse", "fused", "task"])
 def test_reference_main_linked_against_the_library_on_all_gpus(pkg, dataset, mode, tmp_path):
     """common/searchQueries.c, unmodified, -DCUDA, linked against libfmindex_b200.so: its .res.gpu equals the .res.cpu
     the reference's own CPU searcher writes for the same index and reads (std and AltCounters layouts)."""
@@ -141,9 +141,14 @@ def test_replicas_are_bit_identical_and_every_gpu_answers_alone(pkg, dataset):
             want = oracle.search(oh, dataset["reads"], dataset["length"])
             oracle.free(oh)
         assert np.array_equal(got, want), f"GPU {g}"
+        rep.widen(rep.wide_bases_for(dataset["length"]))
+        b.search(rep, pkg.variant(pkg.MODE_WIDE))
+        assert np.array_equal(b.download(), want), f"GPU {g}, wide-step table"
         b.free()
     # end to end over all replicas at once: chunks go round-robin over the GPUs
     got = pkg.search_host(reps, dataset["reads"], dataset["length"], pkg.variant(pkg.MODE_SPARSE, 4))
+    assert np.array_equal(got, want)
+    got = pkg.search_host(reps, dataset["reads"], dataset["length"], pkg.variant(pkg.MODE_WIDE))
     assert np.array_equal(got, want)
     for rep in reps:
         rep.free()

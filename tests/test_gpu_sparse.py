@@ -364,8 +364,8 @@ def test_sparse_dropin_flow_env_modes(pkg, tmp_path):
 
 
 def test_dropin_auto_mode_picks_table_by_text(pkg, tmp_path, capfd):
-    """transferCPUtoGPU in auto mode on indexes larger than L2: the sparse-step table for a random text AND for a repeat-rich
-    one (round 1 switched the latter to the fused-step table; profiles/r02_skewed_text.md); same (L,R) as the plain kernel."""
+    """transferCPUtoGPU in auto mode on indexes larger than L2: the wide-step table (a step width serves 60-bp reads: 2 x 30)
+    for a random text AND for a repeat-rich one, the sparse-step table when $FMGPU_MODE asks for it; same (L,R) as the plain kernel."""
     rng = np.random.default_rng(23)
     n, length, nq = 48_000_001, 60, 20_000
     for kind in ("random", "repeats"):
@@ -395,4 +395,12 @@ def test_dropin_auto_mode_picks_table_by_text(pkg, tmp_path, capfd):
             del os.environ["FMGPU_VERBOSE"]
         err = capfd.readouterr().err
         assert np.array_equal(got, want), kind
-        assert "search table: sparse-step" in err, err           # on both: repeats become search trees, not a reason to change tables
+        assert "search table: wide-step" in err, err             # on both: repeats become search trees, not a reason to change tables
+        os.environ["FMGPU_VERBOSE"] = "1"; os.environ["FMGPU_MODE"] = "sparse"
+        try:
+            got = pkg.search_files(fn, qfa, length, nq, devices=[0], var=None)
+        finally:
+            del os.environ["FMGPU_VERBOSE"], os.environ["FMGPU_MODE"]
+        err = capfd.readouterr().err
+        assert np.array_equal(got, want), kind
+        assert "search table: sparse-step" in err, err
