@@ -1,33 +1,34 @@
 /*
- * fm_wide.cuh -- "wide-step" device layout and search kernel: up to 30 query bases per 128-byte block fetch.
+ * fm_wide.cuh -- "wide-step" device layout and search kernels: up to 30 query bases per 64- or 128-byte block fetch.
  *
  * Why.  profiles/r02_ceiling_counters.md: the memory system accepts ~46 G miss-bound requests per second whatever
  * they carry up to one 128-byte line, and the search is bound by nothing else.  The sparse-step table (fm_sparse.cuh)
- * spends a 64-byte request on 14 bases because it gives every wide symbol its own blocks: 4^KS symbols must stay
- * below the number of blocks the memory can hold.  Here the blocks belong to a PREFIX of the wide symbol and every
- * entry carries the rest of it, so the width of a step is bounded by the entry size (64 bits), not by the table:
+ * spends a request on 14 bases because it gives every wide symbol its own blocks: 4^KS symbols must stay below the
+ * number of blocks the memory can hold.  Here the blocks belong to a PREFIX of the wide symbol and every entry carries
+ * the rest of it, so the width of a step is bounded by the entry size (64 bits), not by the table:
  *
  *   wide symbol of row i    F(i) = s(i) | s(LF(i)) << 2k | ...   (hops = W/k hops, W <= 30 bases: the composition of
  *                           fm_fused.cuh / fm_sparse.cuh, so that rank_F(sigma, X) = G(sigma) + #{ i < X : F(i) = sigma }
  *                           IS `hops` consecutive reference LF steps for every X; rows whose chain meets a '$' row
  *                           carry no symbol).  The hop consumed last sits in the TOP bits: numeric order of F is the
  *                           lexicographic order of the W text bases in front of the suffix.
- *   bucket                  the top prefix_bits of sigma (all 14-mers for a 2 Gbp text: ~7.5 rows per bucket).
+ *   bucket                  the top prefix_bits of sigma (all 15-mers for a 2 Gbp text: 1.9 rows per bucket).
  *                           Block of (sigma, X) = sigma >> sub_bits: computed from the READ alone, never looked up and
  *                           independent of X -- both interval ends of a step always share their fetch.
  *   entry (64 bits)         (sigma & submask) << row_bits | row, for every row of the bucket, ascending: that is the
  *                           order of (F(i), i), i.e. one stable radix sort of the composed keys.
- *   block (128 bytes)       16 x u64: word 0 = { value (low half), kind (high half) }, then 15 ascending entries padded
- *                           with ~0:
+ *   block (32 * LANES B)    4 * LANES x u64: word 0 = { value (low half), kind (high half) }, then SLOTS = 4 * LANES - 1
+ *                           ascending entries padded with ~0 (LANES = 2: 64 bytes, 7 entries, the default; LANES = 4:
+ *                           128 bytes, 15 entries):
  *        leaf               value = G(first symbol of the bucket) + entries of the bucket in front of this block;
  *                           rank_F(sigma, X) = value + #{ entries < (sub(sigma) << row_bits | X) }
- *        inner node         value = block number of child 0, entries = 15 separators (first entry of children 1..15);
- *                           child = value + #{ separators < key } -- the same arithmetic; fan-out 16
+ *        inner node         value = block number of child 0, entries = SLOTS separators (first entry of children 1..);
+ *                           child = value + #{ separators < key } -- the same arithmetic; fan-out SLOTS + 1
  *        exceptional        kind = 2: the step runs as `hops` plain SB96 steps instead (see below)
- *   search tree             a bucket with more than 15 rows is the root of a tree over its sorted entries (leaves of 15
- *                           consecutive entries, all at the same depth, stored behind the grid level by level), as in
- *                           the sparse-step table: Poisson tail on a random text (0.5 % of the buckets at 7.5 rows per
- *                           bucket), repeats on a real one.
+ *   search tree             a bucket with more than SLOTS rows is the root of a tree over its sorted entries (leaves of
+ *                           SLOTS consecutive entries, all at the same depth, stored behind the grid level by level), as
+ *                           in the sparse-step table: the Poisson tail on a random text (0.3 % of the steps at 1.9 rows per
+ *                           7-entry bucket, 8 % at 3.7), repeats on a real one.
  *
  * Exactness.  A leaf answers with ONE base value for all symbols of its bucket, which is right iff
  *   G(sigma') - G(sigma) = #{ rows with sigma <= F < sigma' }  for the symbols of one bucket.
@@ -36,11 +37,15 @@
  * through the sort and checks for EVERY entry that y = G(bucket's smallest symbol) + position in the bucket, and for every
  * bucket that the next bucket's G continues the count (both composed from the SB96 table itself).  With G monotone in
  * sigma this pins G for the absent symbols of the bucket too.  A bucket that fails is marked exceptional and the kernel
- * takes `hops` SB96 steps there -- a handful of buckets out of 2^28.  AltCounters files with an active padding quirk
- * (their composed rank is not a plain counting function) are refused; the sparse-step table serves them.
+ * takes `hops` SB96 steps there -- 28 buckets out of 2^30 on the benchmark text.  AltCounters files with an active padding
+ * quirk (their composed rank is not a plain counting function) are refused; the sparse-step table serves them.
  *
- * Kernel: the per-read state machine of fm_sparse.cuh -- one block fetch per iteration and unfinished read -- on
- * 4-lane groups (one 256-bit load per lane = the 128-byte block), 64-bit compares.
+ * Kernels.  fm_search_wide_kernel: the per-read state machine of fm_sparse.cuh -- one block fetch per iteration and
+ * unfinished read -- on LANES-lane groups (one 256-bit load per lane), 64-bit compares; the timed kernel of bench.py
+ * (LANES = 2, one read per lane pair, 32 registers).  Per read the kernel's instructions scale with the lanes it occupies:
+ * the 128-byte form is issue-bound (72 % of the issue slots, profiles/r02w_*), the 64-byte form is not (43 %) and runs
+ * at 0.96 of the request-rate ceiling.  fm_search_wide_burst_kernel issues all block loads of a read at once (their
+ * addresses do not depend on the interval); it holds fewer reads per SM and measured slower ($FMGPU_WIDE_BURST=1).
  */
 #ifndef FM_WIDE_CUH_
 #define FM_WIDE_CUH_
