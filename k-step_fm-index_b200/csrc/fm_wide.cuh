@@ -57,7 +57,7 @@
 #define FM_WD_INNER    1u
 #define FM_WD_EXC      2u
 #define FM_WD_DONE     0xFFFFFFFFu
-#define FM_WD_MAXDEPTH 11                  /* 7 * 8^11 entries > 2^32 rows (64-byte blocks); 15 * 16^8 for 128-byte blocks */
+#define FM_WD_MAXDEPTH 14                  /* 4 * 5^14 entries > 2^32 rows (64-byte blocks of 96-bit entries); 7 * 8^11, 15 * 16^8 for the others */
 /* block = 32 * LANES bytes = 4 * LANES u64: a header + SLOTS = 4 * LANES - 1 entries; inner nodes have SLOTS + 1 children.
  * LANES = 4: 128-byte blocks (15 entries), LANES = 2: 64-byte blocks (7 entries, 64-byte L2 fills): half the lanes,
  * instructions and DRAM bytes per read for the same number of requests, but twice the buckets for the same occupancy. */
@@ -98,6 +98,43 @@ __device__ __forceinline__ uint64_t fm_read_field64(const uint32_t *q, uint32_t 
   const uint32_t hi = nbits > 32u ? fm_read_field(q, pos + 32u, 0xFFFFFFFFu) : 0u;
   const uint64_t v = (uint64_t) lo | ((uint64_t) hi << 32);
   return nbits >= 64u ? v : (v & ((1ull << nbits) - 1ull));
+}
+
+/* Entry width.  EW = 2: 64-bit entries, steps up to 30 bases.  EW = 3: 96-bit entries { lo, mid, hi } -- steps up to 46 bases
+ * (100 bp = 8 + 2 x 46: two fetches instead of three), two entries per lane behind a two-word lane header (the block header
+ * in lane 0), i.e. 2 * LANES entries per block and a fan-out of 2 * LANES + 1. */
+typedef unsigned __int128 fm_u128;
+template <int EW> struct FmWideKey { typedef uint64_t type; };
+template <> struct FmWideKey<3> { typedef fm_u128 type; };
+
+/* bits [pos, pos + nbits) of a packed read in shared memory, nbits <= 96 */
+__device__ __forceinline__ fm_u128 fm_read_field96(const uint32_t *q, uint32_t pos, uint32_t nbits)
+{
+  const uint32_t w0 = fm_read_field(q, pos, 0xFFFFFFFFu);
+  const uint32_t w1 = nbits > 32u ? fm_read_field(q, pos + 32u, 0xFFFFFFFFu) : 0u;
+  const uint32_t w2 = nbits > 64u ? fm_read_field(q, pos + 64u, 0xFFFFFFFFu) : 0u;
+  const fm_u128 v = (fm_u128) w0 | ((fm_u128) w1 << 32) | ((fm_u128) w2 << 64);
+  return v & ((((fm_u128) 1) << nbits) - 1);
+}
+template <int EW> __device__ __forceinline__ typename FmWideKey<EW>::type fm_wide_read_key(const uint32_t *q, uint32_t pos, uint32_t nbits)
+{
+  if constexpr (EW == 3) return fm_read_field96(q, pos, nbits);
+  else return fm_read_field64(q, pos, nbits);
+}
+
+/* this lane's share of #{ entries < key }, 96-bit entries: words [2..4] and [5..7] of the lane */
+__device__ __forceinline__ uint32_t fm_wide_partial3(const uint32_t (&w)[8], fm_u128 key)
+{
+  const uint32_t klo = (uint32_t) key;
+  const uint64_t khi = (uint64_t)(key >> 32);
+  uint32_t c = 0;
+  #pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const uint32_t elo = w[2 + 3 * j];
+    const uint64_t ehi = (uint64_t) w[3 + 3 * j] | ((uint64_t) w[4 + 3 * j] << 32);
+    c += (ehi < khi || (ehi == khi && elo < klo)) ? 1u : 0u;
+  }
+  return c;
 }
 
 /* this lane's share of #{ entries < key }: lane 0 skips word 0 (the header) */
@@ -141,8 +178,15 @@ __device__ __forceinline__ void fm_stage_reads(uint32_t *fsm, uint32_t *sq, cons
   }
 }
 
+template <int EW> __device__ __forceinline__ uint32_t fm_wide_count(const uint32_t (&w)[8], typename FmWideKey<EW>::type key, uint32_t lg)
+{
+  if constexpr (EW == 3) return fm_wide_partial3(w, key);
+  else return fm_wide_partial(w, key, lg);
+}
+
 /* one wide step of an exceptional bucket: `hops` base-k steps on SB96 for both interval ends */
-__device__ __forceinline__ void fm_wide_plain_step(const FmWideParams &p, uint64_t key, uint32_t &L, uint32_t &R)
+template <typename KeyT>
+__device__ __forceinline__ void fm_wide_plain_step(const FmWideParams &p, KeyT key, uint32_t &L, uint32_t &R)
 {
   const uint32_t kmask = (1u << p.kbits) - 1u;
   for (uint32_t h = 0; h < p.hops; h++) {
@@ -157,21 +201,22 @@ __device__ __forceinline__ void fm_wide_plain_step(const FmWideParams &p, uint64
   }
 }
 
-template <int LANES, int QPT, int THREADS, int MINB, bool COUNT>
+template <int LANES, int EW, int QPT, int THREADS, int MINB, bool COUNT>
 __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_kernel(const FmWideParams p)
 {
   extern __shared__ __align__(16) uint32_t fsm[];             /* [0..3]: mbarrier + pad; [4..): packed reads, natural stride */
   uint32_t *sq = fsm + 4;
+  typedef typename FmWideKey<EW>::type KeyT;
   constexpr int GROUPS = THREADS / LANES;
   const uint32_t q0 = blockIdx.x * (GROUPS * QPT);
   const uint32_t nqb = min((uint32_t)(GROUPS * QPT), p.nq - q0);
   const uint32_t lg = threadIdx.x % LANES, group = threadIdx.x / LANES;
-  const uint64_t submask = p.sub_bits >= 64u ? ~0ull : ((1ull << p.sub_bits) - 1ull);
+  const KeyT submask = p.sub_bits >= 8u * sizeof(KeyT) ? ~(KeyT) 0 : ((((KeyT) 1) << p.sub_bits) - 1);
 
   fm_stage_reads<THREADS>(fsm, sq, p.packed + (size_t) q0 * p.wpq, nqb * p.wpq);
 
   uint32_t L[QPT], R[QPT], aL[QPT], aR[QPT], rem[QPT];
-  uint64_t key[QPT];
+  KeyT key[QPT];
   const uint32_t *myq[QPT];
   bool live[QPT];
   const uint32_t kmask = (p.start_bits >= 32u) ? 0xFFFFFFFFu : ((1u << p.start_bits) - 1u);
@@ -189,7 +234,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_kernel(const FmW
     rem[i] = live[i] ? p.nsteps : 0u;
     aL[i] = aR[i] = FM_WD_DONE; key[i] = 0;
     if (rem[i]) {
-      key[i] = fm_read_field64(myq[i], p.start_bits, p.wbits);
+      key[i] = fm_wide_read_key<EW>(myq[i], p.start_bits, p.wbits);
       aL[i] = aR[i] = (uint32_t)(key[i] >> p.sub_bits);
     }
     busy |= rem[i] != 0u;
@@ -217,17 +262,17 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_kernel(const FmW
       const bool act = rem[i] != 0u;
       const bool doL = act && aL[i] != FM_WD_DONE;
       const bool doR = act && (!doL || aR[i] == aL[i]);                  /* R alone, or riding on the node it shares with L */
-      const uint64_t ksub = (key[i] & submask) << p.row_bits;
+      const KeyT ksub = (key[i] & submask) << p.row_bits;
       uint32_t cL = 0, cR = 0;
       if (act) {
-        cL = fm_wide_partial(w[i], ksub | L[i], lg);
-        cR = fm_wide_partial(w[i], ksub | R[i], lg);
+        cL = fm_wide_count<EW>(w[i], ksub | L[i], lg);
+        cR = fm_wide_count<EW>(w[i], ksub | R[i], lg);
       }
       const uint32_t hval  = __shfl_sync(0xFFFFFFFFu, w[i][0], 0, LANES);
       const uint32_t hkind = __shfl_sync(0xFFFFFFFFu, w[i][1], 0, LANES);
       const uint32_t vL = hval + fm_group_sum<LANES>(cL), vR = hval + fm_group_sum<LANES>(cR);
       if (act && hkind == FM_WD_EXC) {                                   /* (only ever at a grid block: both ends are here) */
-        fm_wide_plain_step(p, key[i], L[i], R[i]);
+        fm_wide_plain_step<KeyT>(p, key[i], L[i], R[i]);
         if (COUNT && lg == 0) n_sb += 2ull * p.hops;
         aL[i] = aR[i] = FM_WD_DONE;
       } else {
@@ -238,7 +283,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_kernel(const FmW
       if (act && aL[i] == FM_WD_DONE && aR[i] == FM_WD_DONE) {           /* step complete: next step's block */
         rem[i] -= 1u;
         if (rem[i]) {
-          key[i] = fm_read_field64(myq[i], p.start_bits + (p.nsteps - rem[i]) * p.wbits, p.wbits);
+          key[i] = fm_wide_read_key<EW>(myq[i], p.start_bits + (p.nsteps - rem[i]) * p.wbits, p.wbits);
           aL[i] = aR[i] = (uint32_t)(key[i] >> p.sub_bits);
         }
       }
@@ -285,7 +330,7 @@ __device__ __forceinline__ void fm_wide_slow_step(const FmWideParams &p, const u
                                                   unsigned long long &n_sb, unsigned long long &n_tree)
 {
   if (hkind == FM_WD_EXC) {
-    fm_wide_plain_step(p, key, L, R);
+    fm_wide_plain_step<uint64_t>(p, key, L, R);
     if (COUNT && lg == 0) n_sb += 2ull * p.hops;
     return;
   }
@@ -384,54 +429,59 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_burst_kernel(con
 }
 
 /* ------------------------------------------------------------------------ *
- * Construction from SB96 (all on the device)
+ * Construction from SB96 (all on the device).  KeyT = uint64_t (steps up to 30 bases, 64-bit entries) or fm_u128 (up to 46
+ * bases, 96-bit entries).
  * ------------------------------------------------------------------------ */
 
 /* key[i] = wide symbol of row i (none_key for a row whose chain meets a '$' row: sorts behind every symbol),
  * val[i] = i | y(i) << 32 with y(i) = the row the chain ends in = rank_F(F(i), i) */
+template <typename KeyT>
 __global__ void fm_wide_compose_kernel(const uint4 *__restrict__ blocks, uint32_t nblocks, const uint8_t *__restrict__ sym,
-                                       uint32_t bwtsize, uint32_t kbits, uint32_t hops, uint64_t none_key,
-                                       uint64_t *__restrict__ keys, uint64_t *__restrict__ vals)
+                                       uint32_t bwtsize, uint32_t kbits, uint32_t hops, uint32_t wbits,
+                                       KeyT *__restrict__ keys, uint64_t *__restrict__ vals)
 {
   const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= bwtsize) return;
   uint32_t row = (uint32_t) i;
-  uint64_t acc = 0;
+  KeyT acc = 0;
   bool ok = true;
   for (uint32_t h = 0; h < hops; h++) {
     const uint32_t s = sym[row];
     if (s == FM_SYM_NONE) { ok = false; break; }
-    acc |= (uint64_t) s << (kbits * h);
+    acc |= (KeyT) s << (kbits * h);
     row = fm_sb96_rank(blocks, nblocks, s, row);
   }
-  keys[i] = ok ? acc : none_key;
+  keys[i] = ok ? acc : (((KeyT) 1) << wbits);
   vals[i] = i | ((uint64_t) row << 32);
 }
 
 /* bstart[b] = first position of the sorted keys whose bucket is >= b, b = 0 .. nroots (bstart[nroots] = rows carrying a symbol) */
-__global__ void fm_wide_bstart_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint32_t sub_bits, uint32_t nroots, uint32_t *__restrict__ bstart)
+template <typename KeyT>
+__global__ void fm_wide_bstart_kernel(const KeyT *__restrict__ keys, uint64_t n, uint32_t sub_bits, uint32_t nroots, uint32_t *__restrict__ bstart)
 {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b > nroots) return;
   uint64_t lo = 0, hi = n;
-  while (lo < hi) { const uint64_t mid = lo + ((hi - lo) >> 1); if ((keys[mid] >> sub_bits) < (uint64_t) b) lo = mid + 1; else hi = mid; }
+  while (lo < hi) { const uint64_t mid = lo + ((hi - lo) >> 1); if ((uint64_t)(keys[mid] >> sub_bits) < (uint64_t) b) lo = mid + 1; else hi = mid; }
   bstart[b] = (uint32_t) lo;
 }
 
 /* g0[b] = G(smallest symbol of bucket b): the composed rank at X = 0 */
+template <typename KeyT>
 __global__ void fm_wide_g0_kernel(const uint4 *__restrict__ blocks, uint32_t nblocks, uint32_t kbits, uint32_t hops, uint32_t sub_bits,
                                   uint32_t nroots, uint32_t *__restrict__ g0)
 {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nroots) return;
-  const uint64_t sigma = (uint64_t) b << sub_bits;
+  const KeyT sigma = (KeyT) b << sub_bits;
   uint32_t x = 0;
   for (uint32_t h = 0; h < hops; h++) x = fm_sb96_rank(blocks, nblocks, (uint32_t)(sigma >> (kbits * h)) & ((1u << kbits) - 1u), x);
   g0[b] = x;
 }
 
 /* every entry must sit where the composed LF walk says: y == g0[bucket] + position in the bucket; else the bucket is exceptional */
-__global__ void fm_wide_verify_entries_kernel(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ vals, uint64_t nvalid,
+template <typename KeyT>
+__global__ void fm_wide_verify_entries_kernel(const KeyT *__restrict__ keys, const uint64_t *__restrict__ vals, uint64_t nvalid,
                                               uint32_t sub_bits, const uint32_t *__restrict__ bstart, const uint32_t *__restrict__ g0,
                                               uint32_t *__restrict__ exc)
 {
@@ -442,21 +492,22 @@ __global__ void fm_wide_verify_entries_kernel(const uint64_t *__restrict__ keys,
   if ((uint32_t)(vals[j] >> 32) != expect) atomicOr(exc + (b >> 5), 1u << (b & 31u));
 }
 
-/* the next bucket's G must continue the count (a suffix shorter than W sorting into or behind the bucket breaks it) */
+/* the next bucket's G must continue the count (a suffix shorter than W sorting into or behind the bucket breaks it); behind
+ * the last bucket the count must have reached every row of the BWT */
 __global__ void fm_wide_verify_buckets_kernel(const uint32_t *__restrict__ bstart, const uint32_t *__restrict__ g0, uint32_t nroots,
-                                              uint32_t force_every, uint32_t *__restrict__ exc)
+                                              uint32_t bwtsize, uint32_t force_every, uint32_t *__restrict__ exc)
 {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nroots) return;
-  bool bad = (b + 1u < nroots) && (g0[b] + (bstart[b + 1] - bstart[b]) != g0[b + 1]);
+  bool bad = g0[b] + (bstart[b + 1] - bstart[b]) != (b + 1u < nroots ? g0[b + 1] : bwtsize);
   if (force_every && (b % force_every) == force_every - 1u) bad = true;   /* tests: exercises the exceptional path */
   if (bad) atomicOr(exc + (b >> 5), 1u << (b & 31u));
 }
 
-/* shape of the tree over cnt > 15 entries: N[v] = nodes of level v (0 = leaves), depth D with N[D] = 1 (the root, which
+/* shape of the tree over cnt > SLOTS entries: N[v] = nodes of level v (0 = leaves), depth D with N[D] = 1 (the root, which
  * lives in the grid); nodes below the root = sum of N[0 .. D-1] */
-template <int LANES> struct FmWideTree {
-  static constexpr uint32_t SLOTS = 4u * LANES - 1u, FAN = 4u * LANES;
+template <int LANES, int EW> struct FmWideTree {
+  static constexpr uint32_t SLOTS = EW == 3 ? 2u * LANES : 4u * LANES - 1u, FAN = SLOTS + 1u;
   uint32_t N[FM_WD_MAXDEPTH + 1];
   uint32_t D;
   __host__ __device__ explicit FmWideTree(uint32_t cnt)
@@ -470,30 +521,32 @@ template <int LANES> struct FmWideTree {
   __host__ __device__ uint32_t level_offset(uint32_t v) const { uint32_t t = 0; for (uint32_t u = v + 1; u < D; u++) t += N[u]; return t; }
 };
 
-struct FmWideBuild {
-  const uint64_t *keys, *vals;    /* sorted */
+template <typename KeyT> struct FmWideBuild {
+  const KeyT *keys;               /* sorted */
+  const uint64_t *vals;
   const uint32_t *bstart, *g0, *exc, *extoff;
   uint32_t nroots, sub_bits, row_bits;
 };
 
-__device__ __forceinline__ bool fm_wide_is_exc(const FmWideBuild &x, uint32_t b) { return (x.exc[b >> 5] >> (b & 31u)) & 1u; }
-__device__ __forceinline__ uint64_t fm_wide_entry(const FmWideBuild &x, uint64_t j)
+template <typename KeyT> __device__ __forceinline__ bool fm_wide_is_exc(const FmWideBuild<KeyT> &x, uint32_t b) { return (x.exc[b >> 5] >> (b & 31u)) & 1u; }
+template <typename KeyT> __device__ __forceinline__ KeyT fm_wide_entry(const FmWideBuild<KeyT> &x, uint64_t j)
 {
-  const uint64_t submask = x.sub_bits >= 64u ? ~0ull : ((1ull << x.sub_bits) - 1ull);
-  return ((x.keys[j] & submask) << x.row_bits) | (x.vals[j] & 0xFFFFFFFFull);
+  const KeyT submask = x.sub_bits >= 8u * sizeof(KeyT) ? ~(KeyT) 0 : ((((KeyT) 1) << x.sub_bits) - 1);
+  return ((x.keys[j] & submask) << x.row_bits) | (KeyT)(x.vals[j] & 0xFFFFFFFFull);
 }
 
 /* pass 1: extension nodes every bucket needs (0 for a bucket that fits its block or is exceptional) */
-template <int LANES>
-__global__ void __launch_bounds__(256) fm_wide_count_kernel(const FmWideBuild x, uint32_t *__restrict__ ext, unsigned long long *__restrict__ stats)
+template <int LANES, int EW>
+__global__ void __launch_bounds__(256) fm_wide_count_kernel(const FmWideBuild<typename FmWideKey<EW>::type> x, uint32_t *__restrict__ ext,
+                                                            unsigned long long *__restrict__ stats)
 {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= x.nroots) return;
   const uint32_t cnt = x.bstart[b + 1] - x.bstart[b];
   uint32_t e = 0;
   if (fm_wide_is_exc(x, b)) atomicAdd(stats + 3, 1ull);
-  else if (cnt > FmWideTree<LANES>::SLOTS) {
-    const FmWideTree<LANES> t(cnt);
+  else if (cnt > FmWideTree<LANES, EW>::SLOTS) {
+    const FmWideTree<LANES, EW> t(cnt);
     e = t.below_root();
     atomicAdd(stats, 1ull);                                    /* overfull buckets */
     atomicAdd(stats + 1, (unsigned long long) cnt);            /* rows living in them */
@@ -502,37 +555,59 @@ __global__ void __launch_bounds__(256) fm_wide_count_kernel(const FmWideBuild x,
   ext[b] = e;
 }
 
+/* slot j (1 .. SLOTS) of a node image: 64-bit entries follow the header word pair; 96-bit entries sit two per lane behind
+ * each lane's two-word header */
+template <int LANES, int EW, typename KeyT>
+__device__ __forceinline__ void fm_wide_put(uint32_t (&w)[8 * LANES], uint32_t j, KeyT e, bool pad)
+{
+  if constexpr (EW == 3) {
+    const uint32_t at = 8u * ((j - 1u) >> 1) + 2u + 3u * ((j - 1u) & 1u);
+    w[at] = pad ? 0xFFFFFFFFu : (uint32_t) e;
+    w[at + 1] = pad ? 0xFFFFFFFFu : (uint32_t)(e >> 32);
+    w[at + 2] = pad ? 0xFFFFFFFFu : (uint32_t)((fm_u128) e >> 64);
+  } else {
+    w[2 * j] = pad ? 0xFFFFFFFFu : (uint32_t) e;
+    w[2 * j + 1] = pad ? 0xFFFFFFFFu : (uint32_t)(e >> 32);
+  }
+}
+
 /* one node: level v, index m, of the tree over entries [j0, j0 + cnt) of a bucket; `area` = first block of the bucket's
  * extension area, base = G before the bucket's first entry */
-template <int LANES>
-__device__ __forceinline__ void fm_wide_write_node(const FmWideBuild &x, const FmWideTree<LANES> &t, uint32_t v, uint32_t m, uint64_t j0, uint32_t cnt,
-                                                   uint32_t area, uint32_t base, uint4 *__restrict__ dst)
+template <int LANES, int EW>
+__device__ __forceinline__ void fm_wide_write_node(const FmWideBuild<typename FmWideKey<EW>::type> &x, const FmWideTree<LANES, EW> &t, uint32_t v, uint32_t m,
+                                                   uint64_t j0, uint32_t cnt, uint32_t area, uint32_t base, uint4 *__restrict__ dst)
 {
-  constexpr uint32_t WORDS = 4u * LANES, SLOTS = WORDS - 1u, FAN = WORDS;
-  uint64_t w[WORDS];
+  typedef typename FmWideKey<EW>::type KeyT;
+  constexpr uint32_t SLOTS = FmWideTree<LANES, EW>::SLOTS, FAN = FmWideTree<LANES, EW>::FAN;
+  uint32_t w[8 * LANES];
+  #pragma unroll
+  for (uint32_t c = 0; c < 8u * LANES; c++) w[c] = 0xFFFFFFFFu;
   if (v == 0) {
     const uint64_t first = (uint64_t) m * SLOTS;
-    w[0] = (uint64_t)(base + (uint32_t) first) | ((uint64_t) FM_WD_LEAF << 32);
+    w[0] = base + (uint32_t) first; w[1] = FM_WD_LEAF;
     #pragma unroll
-    for (uint32_t c = 1; c < WORDS; c++) w[c] = (first + c - 1 < cnt) ? fm_wide_entry(x, j0 + first + c - 1) : FM_WD_PAD;
+    for (uint32_t c = 1; c <= SLOTS; c++) {
+      const bool have = first + c - 1 < cnt;
+      fm_wide_put<LANES, EW, KeyT>(w, c, have ? fm_wide_entry(x, j0 + first + c - 1) : (KeyT) 0, !have);
+    }
   } else {
     uint64_t span = SLOTS;                                     /* entries under one child: SLOTS * FAN^(v-1) */
     for (uint32_t u = 1; u < v; u++) span *= FAN;
-    w[0] = (uint64_t)(area + t.level_offset(v - 1) + m * FAN) | ((uint64_t) FM_WD_INNER << 32);
+    w[0] = area + t.level_offset(v - 1) + m * FAN; w[1] = FM_WD_INNER;
     #pragma unroll
-    for (uint32_t c = 1; c < WORDS; c++) {
+    for (uint32_t c = 1; c <= SLOTS; c++) {
       const uint64_t child = (uint64_t) m * FAN + c, at = child * span;
-      w[c] = (child < t.N[v - 1] && at < cnt) ? fm_wide_entry(x, j0 + at) : FM_WD_PAD;
+      const bool have = child < t.N[v - 1] && at < cnt;
+      fm_wide_put<LANES, EW, KeyT>(w, c, have ? fm_wide_entry(x, j0 + at) : (KeyT) 0, !have);
     }
   }
   #pragma unroll
-  for (uint32_t c = 0; c < 2u * LANES; c++)
-    dst[c] = make_uint4((uint32_t) w[2 * c], (uint32_t)(w[2 * c] >> 32), (uint32_t) w[2 * c + 1], (uint32_t)(w[2 * c + 1] >> 32));
+  for (uint32_t c = 0; c < 2u * LANES; c++) dst[c] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
 }
 
 /* pass 2a: the grid -- a leaf, the root of a tree, or an exceptional marker; one thread per bucket */
-template <int LANES>
-__global__ void __launch_bounds__(256) fm_wide_fill_roots_kernel(const FmWideBuild x, uint4 *__restrict__ wblocks)
+template <int LANES, int EW>
+__global__ void __launch_bounds__(256) fm_wide_fill_roots_kernel(const FmWideBuild<typename FmWideKey<EW>::type> x, uint4 *__restrict__ wblocks)
 {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= x.nroots) return;
@@ -544,13 +619,13 @@ __global__ void __launch_bounds__(256) fm_wide_fill_roots_kernel(const FmWideBui
     return;
   }
   const uint32_t j0 = x.bstart[b], cnt = x.bstart[b + 1] - j0;
-  const FmWideTree<LANES> t(cnt);
-  fm_wide_write_node<LANES>(x, t, t.D, 0u, j0, cnt, x.nroots + x.extoff[b], x.g0[b], dst);
+  const FmWideTree<LANES, EW> t(cnt);
+  fm_wide_write_node<LANES, EW>(x, t, t.D, 0u, j0, cnt, x.nroots + x.extoff[b], x.g0[b], dst);
 }
 
 /* pass 2b: the tree nodes below the grid; one thread per node.  The owning bucket is found by binary search in extoff. */
-template <int LANES>
-__global__ void __launch_bounds__(256) fm_wide_fill_ext_kernel(const FmWideBuild x, uint32_t total_ext, uint4 *__restrict__ wblocks)
+template <int LANES, int EW>
+__global__ void __launch_bounds__(256) fm_wide_fill_ext_kernel(const FmWideBuild<typename FmWideKey<EW>::type> x, uint32_t total_ext, uint4 *__restrict__ wblocks)
 {
   const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total_ext) return;
@@ -558,11 +633,11 @@ __global__ void __launch_bounds__(256) fm_wide_fill_ext_kernel(const FmWideBuild
   while (hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if (x.extoff[mid] <= e) lo = mid; else hi = mid; }
   const uint32_t b = lo;
   const uint32_t j0 = x.bstart[b], cnt = x.bstart[b + 1] - j0;
-  const FmWideTree<LANES> t(cnt);
+  const FmWideTree<LANES, EW> t(cnt);
   uint32_t local = e - x.extoff[b], v = t.D;                   /* levels are stored top-down */
   while (v > 0) { v--; if (local < t.N[v]) break; local -= t.N[v]; }
   FM_BOUND(v, t.D, "wide build: level of an extension node"); FM_BOUND(local, t.N[v], "wide build: node index in its level");
-  fm_wide_write_node<LANES>(x, t, v, local, j0, cnt, x.nroots + x.extoff[b], x.g0[b], wblocks + ((size_t) x.nroots + e) * (2u * LANES));
+  fm_wide_write_node<LANES, EW>(x, t, v, local, j0, cnt, x.nroots + x.extoff[b], x.g0[b], wblocks + ((size_t) x.nroots + e) * (2u * LANES));
 }
 
 #endif /* FM_WIDE_CUH_ */

@@ -19,7 +19,7 @@ extern "C" int32_t fmgpu_index_unwiden(fmgpu_index_t *idx)
   }
   idx->meta.wide_bases = 0; idx->meta.wide_prefix_bits = 0; idx->meta.wide_row_bits = 0; idx->meta.wide_bytes = 0; idx->meta.wide_blocks = 0;
   idx->meta.wide_overflow = 0; idx->meta.wide_tree_nodes = 0; idx->meta.wide_tree_rows = 0; idx->meta.wide_tree_depth = 0;
-  idx->meta.wide_exceptional = 0; idx->meta.wide_lanes = 0;
+  idx->meta.wide_exceptional = 0; idx->meta.wide_lanes = 0; idx->meta.wide_entry_words = 0;
   fm_budget_account(idx);
   return FM_SUCCESS;
 }
@@ -40,21 +40,25 @@ static uint32_t fm_wide_default_lanes(void)
   return env && *env && atoi(env) == 4 ? 4u : 2u;
 }
 
-/* Widest step a table over this text can take: W bases, a multiple of k, at most 30 (a packed key is 60 bits), with
- * sub_bits + row_bits <= 64 */
-static uint32_t fm_wide_max_bases(uint32_t k, uint32_t pb, uint32_t rb)
+#define FM_WIDE_MAX_BASES 46
+/* Widest step a table over this text can take with 64-bit entries: W bases, a multiple of k, at most 30, with
+ * sub_bits + row_bits <= 64; with 96-bit entries: at most 46 bases (a 92-bit key), sub_bits + row_bits <= 96 */
+static uint32_t fm_wide_max_bases_ew(uint32_t k, uint32_t pb, uint32_t rb, uint32_t ew)
 {
-  uint32_t w = (64 + pb - rb) / 2;
-  if (w > 30) w = 30;
+  uint32_t w = (32 * ew + pb - rb) / 2;
+  const uint32_t cap = ew == 3 ? FM_WIDE_MAX_BASES : 30u;
+  if (w > cap) w = cap;
   return w - w % k;
 }
+static uint32_t fm_wide_max_bases(uint32_t k, uint32_t pb, uint32_t rb) { return fm_wide_max_bases_ew(k, pb, rb, 2); }
 
 /* Step width for reads of `len` bases: the fewest wide steps S with len = b + S * W for a lead table of b <= 12 bases
  * (134 MB at most), W <= wmax a multiple of k; the smallest such b (the lead table then stays in L2).  On a 2-step index
  * an odd b ends with the derived 1-step rank (tail_ok).  0 when no such width exists (reads shorter than 16 bases are
  * not worth a table). */
-static uint32_t fm_wide_bases_for_len(uint32_t k, uint32_t len, uint32_t wmax, bool tail_ok)
+static uint32_t fm_wide_bases_for_len(uint32_t k, uint32_t len, uint32_t wmax, bool tail_ok, uint32_t *steps)
 {
+  *steps = 0;
   if (len < 16 || wmax < 8) return 0;
   for (uint32_t S = 1; S <= len / 8; S++)
     for (uint32_t b = 0; b <= 12 && b < len; b++) {
@@ -62,6 +66,7 @@ static uint32_t fm_wide_bases_for_len(uint32_t k, uint32_t len, uint32_t wmax, b
       const uint32_t w = (len - b) / S;
       if (w > wmax || w < 8 || w % k) continue;
       if (b % k && !(k == 2 && tail_ok)) continue;
+      *steps = S;
       return w;
     }
   return 0;
@@ -72,84 +77,48 @@ extern "C" uint32_t fmgpu_wide_bases_for(const fmgpu_index_t *idx, uint32_t len)
   if (!idx) return 0;
   const uint32_t n = idx->meta.bwtsize, rb = fm_bits_for(n), pb = fm_wide_auto_prefix(n, fm_wide_default_lanes());
   if (idx->meta.quirk_mask) return 0;
-  return fm_wide_bases_for_len(idx->meta.steps, len, fm_wide_max_bases(idx->meta.steps, pb, rb), idx->meta.tail_valid != 0);
+  const uint32_t k = idx->meta.steps;
+  const bool tail_ok = idx->meta.tail_valid != 0;
+  uint32_t s2 = 0, s3 = 0;
+  const uint32_t w2 = fm_wide_bases_for_len(k, len, fm_wide_max_bases_ew(k, pb, rb, 2), tail_ok, &s2);
+  /* 96-bit entries (4 instead of 7 per 64-byte block: 12 % instead of 0.3 % of the steps meet a search tree on a random text)
+   * when they save a whole step: 100 bp = 8 + 2 x 46 instead of 10 + 3 x 30.  $FMGPU_WIDE_ENTRY_WORDS=2 keeps 64-bit entries. */
+  const char *env = getenv("FMGPU_WIDE_ENTRY_WORDS");
+  if (env && *env && atoi(env) == 2) return w2;
+  const uint32_t w3 = fm_wide_bases_for_len(k, len, fm_wide_max_bases_ew(k, pb, rb, 3), tail_ok, &s3);
+  if (!w2) return w3;
+  if (!w3) return w2;
+  return s3 < s2 ? w3 : w2;
 }
 
-template <int LANES>
-static cudaError_t fm_wide_fill(const FmWideBuild &x, uint32_t total_ext, uint4 *wblocks)
-{
-  fm_wide_fill_roots_kernel<LANES><<<(x.nroots + 255) / 256, 256>>>(x, wblocks);
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess && total_ext) {
-    fm_wide_fill_ext_kernel<LANES><<<(total_ext + 255) / 256, 256>>>(x, total_ext, wblocks);
-    e = cudaGetLastError();
-  }
-  return e;
-}
+struct fm_wide_shape { uint32_t W, pb, rb, lanes, ew, force_every; };
+struct fm_wide_built { uint4 *wblocks; uint64_t total_blocks; uint32_t total_ext; unsigned long long stats[4]; };
 
-extern "C" int32_t fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, uint32_t prefix_bits, uint32_t lanes)
+/* the whole construction for one block shape; *over_budget is set when the finished size (grid + trees) exceeds the table budget */
+template <int LANES, int EW>
+static cudaError_t fm_wide_build(fmgpu_index_t *idx, const fm_wide_shape &sh, fm_wide_built *out, bool *over_budget)
 {
-  if (!idx) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null index");
-  if (idx->wblocks) return FM_SUCCESS;
-  if (idx->meta.quirk_mask) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "AltCounters file with an active padding quirk: the sparse-step table serves it");
-  CU_TRY(cudaSetDevice(idx->device));
-  const uint32_t k = idx->meta.steps, n = idx->meta.bwtsize, kbits = 2 * k;
-  const uint32_t rb = fm_bits_for(n);
-  if (lanes == 0) lanes = fm_wide_default_lanes();
-  if (lanes != 2 && lanes != 4) return fm_fail_msg(FM_E_BAD_ARGUMENT, "wide block lanes must be 2 (64-byte blocks, 7 entries) or 4 (128-byte blocks, 15 entries)");
-  const uint32_t bbytes = 32 * lanes;
-  uint32_t pb = prefix_bits ? prefix_bits : fm_wide_auto_prefix(n, lanes);
-  if (pb > 30) return fm_fail_msg(FM_E_BAD_ARGUMENT, "at most 30 prefix bits");
-  if (!prefix_bits && pb < 30) {
-    /* roomy grid: one more prefix bit (half the rows per bucket: 0.3 % instead of 8 % of the steps meet a search tree on a
-     * random text, +9 % reads/s at 2 Gbp, profiles/r02_wide_sweep.jsonl) when the doubled grid still is a modest share of
-     * this device's memory (40 %: 68.7 GB of a B200 for 2 Gbp) and fits the table budget; $FMGPU_WIDE_ROOMY=0/1 forces */
-    size_t fb = 0, tb = 0;
-    const char *renv = getenv("FMGPU_WIDE_ROOMY");
-    bool roomy = false;
-    if (renv && *renv) roomy = atoi(renv) != 0;
-    else if (cudaMemGetInfo(&fb, &tb) == cudaSuccess)
-      roomy = ((uint64_t) bbytes << (pb + 1)) <= (uint64_t) tb * 2 / 5 && ((uint64_t) bbytes << (pb + 1)) + 16ull * n + (2ull << 30) <= fb &&
-              fm_budget_allows(idx, ((uint64_t) bbytes << (pb + 1)) + ((uint64_t) bbytes << (pb - 3)));
-    else cudaGetLastError();
-    if (roomy) pb += 1;
-  }
-  uint32_t W = wide_bases ? wide_bases : fm_wide_max_bases(k, pb, rb);
-  if (W % k || W < 2 * k || W > 30) return fm_fail_msg(FM_E_BAD_ARGUMENT, "wide bases must be a multiple of k, at least 2k and at most 30");
-  const uint32_t wbits = 2 * W;
-  if (pb > wbits) pb = wbits;
-  const uint32_t sub_bits = wbits - pb;
-  if (sub_bits + rb > 64) return fm_fail_msg(FM_E_BAD_ARGUMENT, "wide step too wide for this text: (2 * bases - prefix_bits) + bits of a row number must fit 64");
-  const uint32_t hops = W / k, nroots = 1u << pb;
-  const uint64_t none_key = 1ull << wbits;
-
+  typedef typename FmWideKey<EW>::type KeyT;
+  const uint32_t k = idx->meta.steps, n = idx->meta.bwtsize, kbits = 2 * k, wbits = 2 * sh.W, sub_bits = wbits - sh.pb;
+  const uint32_t hops = sh.W / k, nroots = 1u << sh.pb, bbytes = 32 * LANES;
   const uint64_t nrows = (uint64_t) idx->meta.nblocks * FM_SB_ROWS;
-  size_t free_b = 0, total_b = 0;
-  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = ~(size_t) 0; }
-  const uint64_t build_peak = 32ull * n + nrows + 16ull * nroots + (1ull << 30);
-  const uint64_t final_peak = 16ull * n + 16ull * nroots + (uint64_t) nroots * bbytes + (uint64_t) n / 6 * bbytes / 8 + (1ull << 30);
-  if ((build_peak > final_peak ? build_peak : final_peak) > free_b)
-    return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "not enough free device memory to build the wide-step table");
-  if (!fm_budget_allows(idx, (uint64_t) nroots * bbytes)) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "the wide-step table would exceed the derived-table budget");
-
-  uint8_t *sym = NULL; uint64_t *keys = NULL, *vals = NULL, *keys2 = NULL, *vals2 = NULL;
+  uint8_t *sym = NULL; KeyT *keys = NULL, *keys2 = NULL; uint64_t *vals = NULL, *vals2 = NULL;
   uint32_t *bstart = NULL, *g0 = NULL, *exc = NULL, *ext = NULL, *extoff = NULL;
   uint4 *wblocks = NULL; void *tmp = NULL; unsigned long long *d_stats = NULL;
   size_t tmp_bytes = 0, tmp2 = 0;
-  unsigned long long stats[4] = { 0, 0, 0, 0 };
   uint32_t total_ext = 0, nvalid = 0;
-  const char *fenv = getenv("FMGPU_WIDE_FORCE_EXC");           /* tests: every N-th bucket is made exceptional */
-  const uint32_t force_every = fenv && *fenv ? (uint32_t) atoi(fenv) : 0u;
+  memset(out, 0, sizeof *out);
+  *over_budget = false;
   cudaError_t e = cudaMalloc((void **) &sym, nrows);
-  if (e == cudaSuccess) e = cudaMalloc((void **) &keys, 8ull * n);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &keys, sizeof(KeyT) * (size_t) n);
   if (e == cudaSuccess) e = cudaMalloc((void **) &vals, 8ull * n);
-  if (e == cudaSuccess) e = cudaMalloc((void **) &keys2, 8ull * n);
+  if (e == cudaSuccess) e = cudaMalloc((void **) &keys2, sizeof(KeyT) * (size_t) n);
   if (e == cudaSuccess) e = cudaMalloc((void **) &vals2, 8ull * n);
   if (e == cudaSuccess) e = cudaMalloc((void **) &d_stats, 32);
   if (e == cudaSuccess) e = cudaMemset(d_stats, 0, 32);
   if (e == cudaSuccess) e = fm_row_symbols(idx, nrows, sym);
   if (e == cudaSuccess) {
-    fm_wide_compose_kernel<<<(unsigned)(((uint64_t) n + 255) / 256), 256>>>(idx->blocks, idx->meta.nblocks, sym, n, kbits, hops, none_key, keys, vals);
+    fm_wide_compose_kernel<KeyT><<<(unsigned)(((uint64_t) n + 255) / 256), 256>>>(idx->blocks, idx->meta.nblocks, sym, n, kbits, hops, wbits, keys, vals);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(NULL, tmp_bytes, keys, keys2, vals, vals2, (int64_t) n, 0, (int)(wbits + 1));
@@ -167,28 +136,27 @@ extern "C" int32_t fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, ui
   if (e == cudaSuccess) e = cudaMalloc((void **) &ext, 4ull * nroots);
   if (e == cudaSuccess) e = cudaMalloc((void **) &extoff, 4ull * nroots);
   if (e == cudaSuccess) {
-    fm_wide_bstart_kernel<<<(nroots + 1 + 255) / 256, 256>>>(keys2, n, sub_bits, nroots, bstart);
+    fm_wide_bstart_kernel<KeyT><<<(nroots + 1 + 255) / 256, 256>>>(keys2, n, sub_bits, nroots, bstart);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) {
-    fm_wide_g0_kernel<<<(nroots + 255) / 256, 256>>>(idx->blocks, idx->meta.nblocks, kbits, hops, sub_bits, nroots, g0);
+    fm_wide_g0_kernel<KeyT><<<(nroots + 255) / 256, 256>>>(idx->blocks, idx->meta.nblocks, kbits, hops, sub_bits, nroots, g0);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(&nvalid, bstart + nroots, 4, cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && nvalid) {
-    fm_wide_verify_entries_kernel<<<(unsigned)(((uint64_t) nvalid + 255) / 256), 256>>>(keys2, vals2, nvalid, sub_bits, bstart, g0, exc);
+    fm_wide_verify_entries_kernel<KeyT><<<(unsigned)(((uint64_t) nvalid + 255) / 256), 256>>>(keys2, vals2, nvalid, sub_bits, bstart, g0, exc);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) {
-    fm_wide_verify_buckets_kernel<<<(nroots + 255) / 256, 256>>>(bstart, g0, nroots, force_every, exc);
+    fm_wide_verify_buckets_kernel<<<(nroots + 255) / 256, 256>>>(bstart, g0, nroots, n, sh.force_every, exc);
     e = cudaGetLastError();
   }
-  FmWideBuild x;
+  FmWideBuild<KeyT> x;
   x.keys = keys2; x.vals = vals2; x.bstart = bstart; x.g0 = g0; x.exc = exc; x.extoff = extoff;
-  x.nroots = nroots; x.sub_bits = sub_bits; x.row_bits = rb;
+  x.nroots = nroots; x.sub_bits = sub_bits; x.row_bits = sh.rb;
   if (e == cudaSuccess) {
-    if (lanes == 4) fm_wide_count_kernel<4><<<(nroots + 255) / 256, 256>>>(x, ext, d_stats);
-    else            fm_wide_count_kernel<2><<<(nroots + 255) / 256, 256>>>(x, ext, d_stats);
+    fm_wide_count_kernel<LANES, EW><<<(nroots + 255) / 256, 256>>>(x, ext, d_stats);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, ext, extoff, (int64_t) nroots);
@@ -196,31 +164,95 @@ extern "C" int32_t fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, ui
     uint32_t last_off = 0, last_ext = 0;
     e = cudaMemcpy(&last_off, extoff + (nroots - 1), 4, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(&last_ext, ext + (nroots - 1), 4, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) e = cudaMemcpy(stats, d_stats, 32, cudaMemcpyDeviceToHost);
-    total_ext = last_off + last_ext;                             /* <= n / 14 + ...: far below 2^32 */
+    if (e == cudaSuccess) e = cudaMemcpy(out->stats, d_stats, 32, cudaMemcpyDeviceToHost);
+    total_ext = last_off + last_ext;                             /* <= n / (slots - 1) + ...: far below 2^32 */
   }
   cudaFree(ext); ext = NULL;
   const uint64_t total_blocks = (uint64_t) nroots + total_ext;
   if (e == cudaSuccess && total_blocks >= 0xFFFFFFF0ull) e = cudaErrorInvalidValue;
-  bool over_budget = false;
-  if (e == cudaSuccess && !fm_budget_allows(idx, total_blocks * bbytes)) over_budget = true;
-  if (e == cudaSuccess && !over_budget) e = cudaMalloc((void **) &wblocks, total_blocks * bbytes);
-  if (e == cudaSuccess && !over_budget) e = lanes == 4 ? fm_wide_fill<4>(x, total_ext, wblocks) : fm_wide_fill<2>(x, total_ext, wblocks);
+  if (e == cudaSuccess && !fm_budget_allows(idx, total_blocks * bbytes)) *over_budget = true;
+  if (e == cudaSuccess && !*over_budget) e = cudaMalloc((void **) &wblocks, total_blocks * bbytes);
+  if (e == cudaSuccess && !*over_budget) {
+    fm_wide_fill_roots_kernel<LANES, EW><<<(nroots + 255) / 256, 256>>>(x, wblocks);
+    e = cudaGetLastError();
+    if (e == cudaSuccess && total_ext) {
+      fm_wide_fill_ext_kernel<LANES, EW><<<(total_ext + 255) / 256, 256>>>(x, total_ext, wblocks);
+      e = cudaGetLastError();
+    }
+  }
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   cudaFree(sym); cudaFree(keys); cudaFree(vals); cudaFree(keys2); cudaFree(vals2); cudaFree(bstart); cudaFree(g0); cudaFree(exc);
   cudaFree(ext); cudaFree(extoff); cudaFree(tmp); cudaFree(d_stats);
-  if (over_budget) { cudaFree(wblocks); return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "the wide-step table would exceed the derived-table budget"); }
+  if (e != cudaSuccess || *over_budget) { cudaFree(wblocks); wblocks = NULL; }
+  out->wblocks = wblocks; out->total_blocks = total_blocks; out->total_ext = total_ext;
+  return e;
+}
+
+extern "C" int32_t fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, uint32_t prefix_bits, uint32_t lanes)
+{
+  if (!idx) return fm_fail_msg(FM_E_BAD_ARGUMENT, "null index");
+  if (idx->wblocks) return FM_SUCCESS;
+  if (idx->meta.quirk_mask) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "AltCounters file with an active padding quirk: the sparse-step table serves it");
+  CU_TRY(cudaSetDevice(idx->device));
+  const uint32_t k = idx->meta.steps, n = idx->meta.bwtsize;
+  const uint32_t rb = fm_bits_for(n);
+  if (lanes == 0) lanes = fm_wide_default_lanes();
+  if (lanes != 2 && lanes != 4) return fm_fail_msg(FM_E_BAD_ARGUMENT, "wide block lanes must be 2 (64-byte blocks) or 4 (128-byte blocks)");
+  const uint32_t bbytes = 32 * lanes;
+  uint32_t pb = prefix_bits ? prefix_bits : fm_wide_auto_prefix(n, lanes);
+  if (pb > 30) return fm_fail_msg(FM_E_BAD_ARGUMENT, "at most 30 prefix bits");
+  if (!prefix_bits && pb < 30) {
+    /* roomy grid: one more prefix bit (half the rows per bucket: 0.3 % instead of 8 % of the steps meet a search tree on a
+     * random text, +9 % reads/s at 2 Gbp, profiles/r02w_wide_sweep.jsonl) when the doubled grid still is a modest share of
+     * this device's memory (40 %: 68.7 GB of a B200 for 2 Gbp) and fits the table budget; $FMGPU_WIDE_ROOMY=0/1 forces */
+    size_t fb = 0, tb = 0;
+    const char *renv = getenv("FMGPU_WIDE_ROOMY");
+    bool roomy = false;
+    if (renv && *renv) roomy = atoi(renv) != 0;
+    else if (cudaMemGetInfo(&fb, &tb) == cudaSuccess)
+      roomy = ((uint64_t) bbytes << (pb + 1)) <= (uint64_t) tb * 2 / 5 && ((uint64_t) bbytes << (pb + 1)) + 24ull * n + (2ull << 30) <= fb &&
+              fm_budget_allows(idx, ((uint64_t) bbytes << (pb + 1)) + ((uint64_t) bbytes << (pb - 3)));
+    else cudaGetLastError();
+    if (roomy) pb += 1;
+  }
+  uint32_t W = wide_bases ? wide_bases : fm_wide_max_bases(k, pb, rb);
+  if (W % k || W < 2 * k || W > FM_WIDE_MAX_BASES) return fm_fail_msg(FM_E_BAD_ARGUMENT, "wide bases must be a multiple of k, at least 2k and at most 46");
+  const uint32_t wbits = 2 * W;
+  if (pb > wbits) pb = wbits;
+  const uint32_t sub_bits = wbits - pb;
+  /* entry = rest of the symbol + row number: 64 bits up to 30 bases per step (at 2 Gbp), 96 bits beyond */
+  const uint32_t ew = (sub_bits + rb <= 64 && wbits <= 62) ? 2u : 3u;   /* (a 64-bit key also holds the "no symbol" value 2^wbits) */
+  if (sub_bits + rb > 96) return fm_fail_msg(FM_E_BAD_ARGUMENT, "wide step too wide for this text: (2 * bases - prefix_bits) + bits of a row number must fit 96");
+  const uint32_t nroots = 1u << pb;
+
+  const uint64_t nrows = (uint64_t) idx->meta.nblocks * FM_SB_ROWS;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = ~(size_t) 0; }
+  const uint64_t kv = ew == 3 ? 24 : 16;                              /* sorted (key, value) bytes per row */
+  const uint64_t build_peak = 2 * kv * n + nrows + 16ull * nroots + (1ull << 30);
+  const uint64_t final_peak = kv * n + 16ull * nroots + (uint64_t) nroots * bbytes + (uint64_t) n / 4 * bbytes / 4 + (1ull << 30);
+  if ((build_peak > final_peak ? build_peak : final_peak) > free_b)
+    return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "not enough free device memory to build the wide-step table");
+  if (!fm_budget_allows(idx, (uint64_t) nroots * bbytes)) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "the wide-step table would exceed the derived-table budget");
+
+  const char *fenv = getenv("FMGPU_WIDE_FORCE_EXC");           /* tests: every N-th bucket is made exceptional */
+  fm_wide_shape sh;
+  sh.W = W; sh.pb = pb; sh.rb = rb; sh.lanes = lanes; sh.ew = ew; sh.force_every = fenv && *fenv ? (uint32_t) atoi(fenv) : 0u;
+  fm_wide_built bt;
+  bool over_budget = false;
+  cudaError_t e = lanes == 4 ? (ew == 3 ? fm_wide_build<4, 3>(idx, sh, &bt, &over_budget) : fm_wide_build<4, 2>(idx, sh, &bt, &over_budget))
+                             : (ew == 3 ? fm_wide_build<2, 3>(idx, sh, &bt, &over_budget) : fm_wide_build<2, 2>(idx, sh, &bt, &over_budget));
+  if (over_budget) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "the wide-step table would exceed the derived-table budget");
   if (e != cudaSuccess) {
-    cudaFree(wblocks);
     cudaGetLastError();                                          /* a failed cudaMalloc stays "last error" otherwise and fails the next attempt's first check */
     if (e == cudaErrorMemoryAllocation) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "not enough device memory for the wide-step table (the other kernels still serve this index)");
     return fm_fail(e, "fmgpu_index_widen", __FILE__, __LINE__);
   }
-  idx->wblocks = wblocks;
+  idx->wblocks = bt.wblocks;
   idx->meta.wide_bases = W; idx->meta.wide_prefix_bits = pb; idx->meta.wide_row_bits = rb;
-  idx->meta.wide_blocks = total_blocks; idx->meta.wide_bytes = total_blocks * bbytes; idx->meta.wide_lanes = lanes;
-  idx->meta.wide_overflow = stats[0]; idx->meta.wide_tree_rows = stats[1]; idx->meta.wide_tree_depth = (uint32_t) stats[2];
-  idx->meta.wide_tree_nodes = total_ext; idx->meta.wide_exceptional = stats[3];
+  idx->meta.wide_blocks = bt.total_blocks; idx->meta.wide_bytes = bt.total_blocks * bbytes; idx->meta.wide_lanes = lanes; idx->meta.wide_entry_words = ew;
+  idx->meta.wide_overflow = bt.stats[0]; idx->meta.wide_tree_rows = bt.stats[1]; idx->meta.wide_tree_depth = (uint32_t) bt.stats[2];
+  idx->meta.wide_tree_nodes = bt.total_ext; idx->meta.wide_exceptional = bt.stats[3];
   fm_budget_account(idx);
   return FM_SUCCESS;
 }
@@ -295,14 +327,14 @@ void fm_wide_prepare(fmgpu_index_t *idx, uint32_t len)
 }
 
 typedef void (*fm_wide_fn)(const FmWideParams);
-template <int LANES>
+template <int LANES, int EW>
 static fm_wide_fn fm_pick_wide(int qpt)
 {
-  if (qpt == 0) return fm_search_wide_kernel<LANES, 1, 256, 4, true>;         /* instrumented */
-  if (qpt == 1) return fm_search_wide_kernel<LANES, 1, 256, 6, false>;
-  if (qpt == 2) return fm_search_wide_kernel<LANES, 2, 256, 4, false>;
-  if (qpt == 3) return fm_search_wide_kernel<LANES, 3, 256, 3, false>;
-  if (qpt == 4) return fm_search_wide_kernel<LANES, 4, 256, 2, false>;
+  if (qpt == 0) return fm_search_wide_kernel<LANES, EW, 1, 256, 4, true>;         /* instrumented */
+  if (qpt == 1) return fm_search_wide_kernel<LANES, EW, 1, 256, 6, false>;
+  if (qpt == 2) return fm_search_wide_kernel<LANES, EW, 2, 256, EW == 3 ? 3 : 4, false>;
+  if (qpt == 3) return fm_search_wide_kernel<LANES, EW, 3, 256, EW == 3 ? 2 : 3, false>;
+  if (qpt == 4) return fm_search_wide_kernel<LANES, EW, 4, 256, 2, false>;
   return NULL;
 }
 
@@ -358,11 +390,13 @@ int32_t fm_launch_wide(const fmgpu_index_t *idx, const uint32_t *d_packed, uint6
    * measured slower so far (profiles/r02_wide_sweep.jsonl): fewer reads fit an SM with all their blocks in registers;
    * $FMGPU_WIDE_PF: blocks per read and chunk the burst kernel keeps in flight (3 or 4; default: 3 up to three steps, else 4) */
   const char *benv = getenv("FMGPU_WIDE_BURST"), *penv = getenv("FMGPU_WIDE_PF");
-  const bool burst = benv && *benv && atoi(benv) != 0;
+  const uint32_t ew = idx->meta.wide_entry_words;
+  const bool burst = benv && *benv && atoi(benv) != 0 && ew == 2;
   const int pf = penv && *penv ? atoi(penv) : (pl.S <= 3 ? 3 : 4);
   const int qsel = d_counters ? 0 : v.queries_per_thread;
   fm_wide_fn fn = burst ? (lanes == 4 ? fm_pick_wide_burst<4>(qsel, pf) : fm_pick_wide_burst<2>(qsel, pf))
-                        : (lanes == 4 ? fm_pick_wide<4>(qsel) : fm_pick_wide<2>(qsel));
+                        : ew == 3 ? (lanes == 4 ? fm_pick_wide<4, 3>(qsel) : fm_pick_wide<2, 3>(qsel))
+                                  : (lanes == 4 ? fm_pick_wide<4, 2>(qsel) : fm_pick_wide<2, 2>(qsel));
   if (!fn) return fm_fail_msg(FM_E_BAD_ARGUMENT, "no wide kernel for this variant");
   if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   const uint32_t grid = (uint32_t)((nq + qper - 1) / qper);

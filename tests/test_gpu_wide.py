@@ -27,9 +27,9 @@ def pkg(built):
 
 
 def serving_widths(k, length, lead_max):
-    """step widths W (multiples of k, 2k..30) with length = b + S*W, S >= 1, b <= lead_max"""
+    """step widths W (multiples of k, 2k..46) with length = b + S*W, S >= 1, b <= lead_max"""
     out = []
-    for w in range(2 * k, 31, k):
+    for w in range(2 * k, 47, k):
         if any((length - s * w) >= 0 and (length - s * w) <= lead_max for s in range(1, length // w + 1)):
             out.append(w)
     return out
@@ -64,8 +64,8 @@ def test_wide_steps_golden_all_widths(pkg, monkeypatch, path):
             ws = serving_widths(k, length, lead_max)
             for w in sorted(set(ws[:: max(1, len(ws) // 3)] + ws[-1:])):
                 for pbits, force in ((0, 0), (1, 0), (5, 0), (2 * w, 0), (0, 3)):
-                    if pbits and 2 * w - min(pbits, 16, 2 * w) + (int(g["n"]) + 1).bit_length() > 64:
-                        continue                                 # entry = rest of the symbol + row number must fit 64 bits
+                    if 2 * w - min(pbits or 16, 16, 2 * w) + (int(g["n"]) + 1).bit_length() > 96:
+                        continue                                 # entry = rest of the symbol + row number: 64 bits, else 96, at most
                     if force:
                         monkeypatch.setenv("FMGPU_WIDE_FORCE_EXC", str(force))
                     else:
@@ -76,6 +76,8 @@ def test_wide_steps_golden_all_widths(pkg, monkeypatch, path):
                     assert m.wide_bases == w and m.wide_lanes == lanes and m.wide_blocks == (1 << m.wide_prefix_bits) + m.wide_tree_nodes
                     assert (m.wide_overflow > 0) == (m.wide_tree_nodes > 0) == (m.wide_tree_depth > 0)
                     assert m.wide_bytes == m.wide_blocks * 32 * lanes and m.derived_bytes >= m.wide_bytes
+                    bits = 2 * w - m.wide_prefix_bits + m.wide_row_bits
+                    assert m.wide_entry_words == (2 if bits <= 64 and w <= 31 else 3)
                     if force:
                         assert m.wide_exceptional >= (1 << m.wide_prefix_bits) // 3
                     idx.prepare(length)
@@ -112,7 +114,7 @@ def test_wide_steps_read_lengths(pkg, k, length):
     proposed = idx.wide_bases_for(length)
     assert (proposed != 0) == (length >= 16)
     tried = 0
-    for w in sorted({proposed, 30, 8 * k, 14, 22} - {0}):
+    for w in sorted({proposed, 30, 8 * k, 14, 22, 46, 40, 36} - {0}):
         idx.widen(w, 0, (2, 4)[(w // 2) % 2])
         idx.prepare(length)
         if idx.wide_serves(length):
@@ -139,7 +141,7 @@ def test_wide_unavailable_and_errors(pkg):
     with pytest.raises(pkg.FMError) as ei:
         b.search(idx, pkg.variant(pkg.MODE_WIDE))              # no table: loud failure, no silent fallback
     assert ei.value.code == pkg.FM_E_BAD_ARGUMENT
-    for bad in ((3, 0, 0), (2, 0, 0), (32, 0, 0), (16, 31, 0), (16, 0, 3), (16, 0, 8)):
+    for bad in ((3, 0, 0), (2, 0, 0), (48, 0, 0), (16, 31, 0), (16, 0, 3), (16, 0, 8)):
         with pytest.raises(pkg.FMError) as ei:
             idx.widen(*bad)
         assert ei.value.code == pkg.FM_E_BAD_ARGUMENT, bad
@@ -180,14 +182,14 @@ def test_wide_steps_repetitive_texts_search_trees(pkg, tmp_path, name, k):
     image = np.fromfile(paths[101], dtype=np.uint32)
     idx = pkg.DeviceIndex.from_image(image)
     saw_overflow, deepest = False, 0
-    for length, widths in ((20, (10, 20)), (40, (30, 10)), (66, (30,))):
+    for length, widths in ((20, (10, 20)), (40, (30, 10)), (66, (30,)), (98, (46,))):
         starts = rng.integers(0, text.size - length + 1, 2000)
         reads = np.concatenate([text[s:s + length] for s in starts] + [ACGT[rng.integers(0, 4, 500 * length)]])
         want, _ = ref.search(ref.load(paths[100]), reads, length)
         b = pkg.DeviceBatch(0, reads.size // length, length, k)
         b.upload_ascii(reads)
         for w in widths:
-            for pbits in (0, max(4, 2 * w + 15 - 64)):           # (entry = rest of the symbol + a 15-bit row number: 64 bits at most)
+            for pbits in (0, 4, max(4, 2 * w + 15 - 64)) if w <= 30 else (0, 12):   # (few prefix bits: deep trees, and 96-bit entries when 64 do not hold the rest of the symbol + a 15-bit row)
                 idx.widen(w, pbits, (2, 4)[(w + pbits + length) % 2])
                 m = idx.meta
                 saw_overflow |= m.wide_overflow > 0
@@ -227,7 +229,8 @@ def test_wide_fuzz_tiny_references_against_the_reference_searcher(pkg, tmp_path)
                 idx.free()
                 continue
             ref = helpers.RefSearcher(k, d, ac)
-            for length, w, pbits in ((8, 8, 0), (12, 6, 0), (12, 12, 3), (24, 12, 0), (30, 30, 0), (34, 30, 0), (40, 20, 6), (60, 30, 6)):
+            for length, w, pbits in ((8, 8, 0), (12, 6, 0), (12, 12, 3), (24, 12, 0), (30, 30, 0), (34, 30, 0), (40, 20, 6), (60, 30, 6),
+                                     (60, 30, 2), (46, 46, 0), (50, 46, 0), (92, 46, 6), (80, 40, 0)):
                 if length > n:
                     continue
                 starts = rng.integers(0, n - length + 1, 200)
@@ -250,7 +253,7 @@ def test_wide_fuzz_tiny_references_against_the_reference_searcher(pkg, tmp_path)
                 cases += 1
             idx.free()
     print(f"wide fuzz: {cases} (index, length, width) cases, {exceptional} exceptional buckets")
-    assert cases >= 200 and exceptional >= 1, (cases, exceptional)
+    assert cases >= 300 and exceptional >= 1, (cases, exceptional)
 
 
 @pytest.mark.parametrize("k", [1, 2])
@@ -300,6 +303,36 @@ def test_wide_lead_table_and_fetch_counter(pkg, k):
             assert np.array_equal(d_res.cpu().numpy().view(np.uint32), want)
             assert a.value == 3 * nq                              # 10-base lead table + 3 wide steps, one grid block each
             assert s.value <= 0.001 * nq * 60 and o.value <= 0.2 * nq   # exceptional buckets: a handful; overfull buckets: the Poisson tail
+    # 96-bit entries: 46 bases per step, four entries per 64-byte block
+    assert idx.wide_bases_for(100) == 46
+    idx.unwiden()
+    idx.widen(46)
+    m = idx.meta
+    assert (m.wide_bases, m.wide_lanes, m.wide_entry_words, m.wide_prefix_bits) == (46, 2, 3, 24)
+    for length in (100, 92, 46, 50, 101, 146):
+        nq = 200_000
+        d_ascii = torch.empty(nq * length, dtype=torch.uint8, device="cuda")
+        pkg.check(L.fmgpu_synth_reads_device(0, n, 3, nq, length, 2, 0, d_ascii.data_ptr(), None), "reads")
+        torch.cuda.synchronize()
+        reads = d_ascii.cpu().numpy().copy()
+        mut = rng.integers(0, nq * length, nq // 3)
+        reads[mut] = ACGT[rng.integers(0, 4, mut.size)]
+        batch = pkg.DeviceBatch(0, nq, length, k)
+        batch.upload_ascii(reads)
+        batch.search(idx, pkg.variant(pkg.MODE_COOP))
+        want = batch.download()
+        assert idx.wide_serves(length)
+        for qpt in (1, 2, 3, 4):
+            batch.search(idx, pkg.variant(pkg.MODE_WIDE, qpt))
+            assert np.array_equal(batch.download(), want), f"k={k} len={length} qpt={qpt} (46 bases per step)"
+        if length == 100:
+            d_packed = torch.from_numpy(np.zeros(1, dtype=np.int32))   # (the shard's own packed reads are used below)
+            a, s, o = C.c_uint64(), C.c_uint64(), C.c_uint64()
+            pkg.check(L.fmgpu_count_fetches_wide_device(idx.handle, L.fmgpu_batch_packed(batch.handle), nq, length, L.fmgpu_batch_results(batch.handle),
+                                                        L.fmgpu_batch_stream(batch.handle), C.byref(a), C.byref(s), C.byref(o)), "count")
+            assert np.array_equal(batch.download(), want)
+            assert a.value == 2 * nq and o.value <= 0.3 * nq      # 8-base lead table + 2 wide steps
+        batch.free()
     idx.free()
 
 
@@ -322,10 +355,18 @@ def test_wide_config3_full_size_against_reference_checksums(pkg):
     for tag, key in ((100, "res_cpu_std_text"), (201, "res_cpu_ac_text")):
         t = b if tag == 100 else b.transform(tag)
         idx = t.to_index()
-        assert idx.wide_bases_for(length) == 30
-        idx.widen()
+        assert idx.wide_bases_for(length) == 46                  # 100 = 8 + 2 x 46: 96-bit entries
+        idx.widen(46)
         m = idx.meta
-        assert (m.wide_bases, m.wide_lanes, m.wide_prefix_bits, m.wide_row_bits) == (30, 2, 30, 31) and m.wide_bytes < 72e9   # roomy grid
+        assert (m.wide_bases, m.wide_lanes, m.wide_entry_words, m.wide_prefix_bits, m.wide_row_bits) == (46, 2, 3, 30, 31) and m.wide_bytes < 76e9
+        assert m.wide_exceptional <= 96 and m.wide_tree_rows < n // 5
+        for qpt in (1, 2):
+            batch.search(idx, pkg.variant(pkg.MODE_WIDE, qpt))
+            assert helpers.results_text_md5(batch.download()) == gold["md5"][key], f"tag {tag} qpt {qpt} (46 bases per step)"
+        idx.unwiden()
+        idx.widen()                                             # widest step with 64-bit entries: 100 = 10 + 3 x 30
+        m = idx.meta
+        assert (m.wide_bases, m.wide_lanes, m.wide_entry_words, m.wide_prefix_bits, m.wide_row_bits) == (30, 2, 2, 30, 31) and m.wide_bytes < 72e9   # roomy grid
         assert m.wide_exceptional <= 64 and m.wide_tree_rows < n // 100
         for qpt in (1, 2, 3):
             batch.search(idx, pkg.variant(pkg.MODE_WIDE, qpt))
