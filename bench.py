@@ -308,9 +308,14 @@ def skewed_text_extra(pkg, L, torch, dev, stream):
         m = index.meta
         pkg.check(L.fmgpu_count_fetches_wide_device(index.handle, d_packed.data_ptr(), nq, length, d_res.data_ptr(), stream, C.byref(a), C.byref(s), C.byref(o)), "count")
         probe = pkg.gather_probe(dev, int(m.wide_bytes), 256, 2)
-        ms = min(timed(pkg.variant(pkg.MODE_WIDE, q)) for q in (1, 2, 3))
+        by_assignment = {}
+        for dyn in ("0", "1"):
+            os.environ["FMGPU_WIDE_DYNAMIC"] = dyn
+            by_assignment["dynamic" if dyn == "1" else "static"] = min(timed(pkg.variant(pkg.MODE_WIDE, q)) for q in (1, 2))
+        del os.environ["FMGPU_WIDE_DYNAMIC"]
+        ms = min(timed(pkg.variant(pkg.MODE_WIDE, q)) for q in (1, 2))          # the library's own choice of read assignment
         fetches = a.value + s.value + o.value
-        out["wide"] = {"ms": ms, "mqueries_per_s": nq / ms / 1e3, "equals_plain": bool(torch.equal(d_res, want)), "bases_per_step": m.wide_bases,
+        out["wide"] = {"ms": ms, "ms_by_read_assignment": by_assignment, "entry_words": m.wide_entry_words, "mqueries_per_s": nq / ms / 1e3, "equals_plain": bool(torch.equal(d_res, want)), "bases_per_step": m.wide_bases,
                        "table_gb": m.wide_bytes / 1e9, "rows_in_search_trees": m.wide_tree_rows / m.bwtsize, "tree_depth": m.wide_tree_depth,
                        "exceptional_buckets": m.wide_exceptional,
                        "grid_fetches_per_read": a.value / nq, "tree_fetches_per_read": o.value / nq, "sb96_fetches_per_read": s.value / nq,

@@ -240,7 +240,8 @@ class FMError(RuntimeError):
     def __init__(self, code, where):
         self.code = code
         msg = lib().errorCommon(code)
-        super().__init__(f"{where}: error {code}: {msg.decode() if msg else '?'}")
+        detail = lib().fmgpu_last_error() if code >= 19 else None       # the fmgpu_* layer says why (per thread)
+        super().__init__(f"{where}: error {code}: {msg.decode() if msg else '?'}" + (f" ({detail.decode()})" if detail and detail != b"no error" else ""))
 
 
 def check(code, where):

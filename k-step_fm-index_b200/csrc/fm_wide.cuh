@@ -307,6 +307,109 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_kernel(const FmW
 }
 
 /* ------------------------------------------------------------------------ *
+ * The same search with DYNAMIC read assignment (fm_search_sparse_dyn_kernel's scheme): the CTA stages `reads_per_cta` reads
+ * (several rounds of its slots) with one bulk copy and a lane group that finishes a read pulls the next one from a
+ * shared-memory counter; the lead-table lookup of a new read is one more state (aL = FM_WD_START), so every iteration
+ * issues exactly one load per busy slot.  With static assignment a warp lasts as long as the slowest of its reads:
+ * that is nothing on the roomy 64-bit grid (0.3 % of the steps meet a tree), but with 96-bit entries (four per block,
+ * 12 % of the steps continue into a tree) and on repeat-rich texts half of the fetch slots would idle.
+ * ------------------------------------------------------------------------ */
+#define FM_WD_START 0xFFFFFFFEu
+
+template <int LANES, int EW, int QPT, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_dyn_kernel(const FmWideParams p, uint32_t reads_per_cta)
+{
+  extern __shared__ __align__(16) uint32_t fsm[];             /* [0..1]: mbarrier; [2]: next read; [4..): packed reads */
+  uint32_t *sq = fsm + 4;
+  typedef typename FmWideKey<EW>::type KeyT;
+  const KeyT submask = p.sub_bits >= 8u * sizeof(KeyT) ? ~(KeyT) 0 : ((((KeyT) 1) << p.sub_bits) - 1);
+  const uint32_t kmask = (p.start_bits >= 32u) ? 0xFFFFFFFFu : ((1u << p.start_bits) - 1u);
+  const uint32_t q0 = blockIdx.x * reads_per_cta;
+  const uint32_t nqb = min(reads_per_cta, p.nq - q0);
+  const uint32_t lg = threadIdx.x % LANES;
+  if (threadIdx.x == 0) fsm[2] = 0u;
+  fm_stage_reads<THREADS>(fsm, sq, p.packed + (size_t) q0 * p.wpq, nqb * p.wpq);   /* (its barrier also publishes fsm[2]) */
+
+  uint32_t L[QPT], R[QPT], aL[QPT], aR[QPT], rem[QPT], rd[QPT];
+  KeyT key[QPT];
+  /* takes the next read of the CTA for slot i (or parks the slot): all lanes of the warp call it together */
+  auto take = [&](int i, bool need) {
+    uint32_t r = 0;
+    if (need && lg == 0) r = atomicAdd(&fsm[2], 1u);
+    r = __shfl_sync(0xFFFFFFFFu, r, 0, LANES);
+    if (need) {
+      rd[i] = r;
+      if (r < nqb) {
+        rem[i] = p.nsteps; L[i] = 0u; R[i] = p.bwtsize;
+        if (p.start) { aL[i] = FM_WD_START; aR[i] = FM_WD_DONE; }
+        else if (rem[i]) {
+          key[i] = fm_wide_read_key<EW>(sq + r * p.wpq, 0u, p.wbits);
+          aL[i] = aR[i] = (uint32_t)(key[i] >> p.sub_bits);
+        } else { aL[i] = aR[i] = FM_WD_DONE; }
+      } else { rem[i] = 0u; aL[i] = aR[i] = FM_WD_DONE; rd[i] = 0xFFFFFFFFu; }
+    }
+  };
+  #pragma unroll
+  for (int i = 0; i < QPT; i++) { rd[i] = 0xFFFFFFFFu; rem[i] = 0u; aL[i] = aR[i] = FM_WD_DONE; L[i] = R[i] = 0u; key[i] = 0; take(i, true); }
+
+  bool busy = false;
+  #pragma unroll
+  for (int i = 0; i < QPT; i++) busy |= rd[i] != 0xFFFFFFFFu;
+  while (__any_sync(0xFFFFFFFFu, busy)) {
+    uint32_t w[QPT][8];
+    uint2 lr[QPT];
+    #pragma unroll
+    for (int i = 0; i < QPT; i++) {
+      if (rd[i] != 0xFFFFFFFFu) {
+        if (aL[i] == FM_WD_START) lr[i] = __ldg(p.start + (sq[rd[i] * p.wpq] & kmask));
+        else if (rem[i]) {
+          const uint32_t a = (aL[i] != FM_WD_DONE) ? aL[i] : aR[i];
+          FM_BOUND(a, p.total_blocks, "wide (dynamic): grid / tree block"); FM_BOUND(rd[i], nqb, "wide (dynamic): read slot");
+          fm_wide_load<LANES>(p.wblocks + (size_t) a * (2u * LANES) + 2u * lg, w[i]);
+        }
+      }
+    }
+    busy = false;
+    #pragma unroll
+    for (int i = 0; i < QPT; i++) {
+      const bool have = rd[i] != 0xFFFFFFFFu;
+      const bool starting = have && aL[i] == FM_WD_START;
+      const bool act = have && !starting && rem[i] != 0u;
+      const bool doL = act && aL[i] != FM_WD_DONE;
+      const bool doR = act && (!doL || aR[i] == aL[i]);
+      const KeyT ksub = (key[i] & submask) << p.row_bits;
+      uint32_t cL = 0, cR = 0;
+      if (act) {
+        cL = fm_wide_count<EW>(w[i], ksub | L[i], lg);
+        cR = fm_wide_count<EW>(w[i], ksub | R[i], lg);
+      }
+      const uint32_t hval  = __shfl_sync(0xFFFFFFFFu, w[i][0], 0, LANES);
+      const uint32_t hkind = __shfl_sync(0xFFFFFFFFu, w[i][1], 0, LANES);
+      const uint32_t vL = hval + fm_group_sum<LANES>(cL), vR = hval + fm_group_sum<LANES>(cR);
+      if (act && hkind == FM_WD_EXC) {
+        fm_wide_plain_step<KeyT>(p, key[i], L[i], R[i]);
+        aL[i] = aR[i] = FM_WD_DONE;
+      } else {
+        const bool is_inner = hkind == FM_WD_INNER;
+        if (doL) { if (is_inner) aL[i] = vL; else { L[i] = vL; aL[i] = FM_WD_DONE; } }
+        if (doR) { if (is_inner) aR[i] = vR; else { R[i] = vR; aR[i] = FM_WD_DONE; } }
+      }
+      bool next_block = false;
+      if (starting) { L[i] = lr[i].x; R[i] = lr[i].y; aL[i] = aR[i] = FM_WD_DONE; next_block = rem[i] != 0u; }
+      else if (act && aL[i] == FM_WD_DONE && aR[i] == FM_WD_DONE) { rem[i] -= 1u; next_block = rem[i] != 0u; }
+      if (next_block) {
+        key[i] = fm_wide_read_key<EW>(sq + rd[i] * p.wpq, p.start_bits + (p.nsteps - rem[i]) * p.wbits, p.wbits);
+        aL[i] = aR[i] = (uint32_t)(key[i] >> p.sub_bits);
+      }
+      const bool finished = have && rem[i] == 0u && aL[i] == FM_WD_DONE;
+      if (finished && lg == 0) reinterpret_cast<uint2 *>(p.results)[q0 + rd[i]] = make_uint2(L[i], R[i]);
+      take(i, finished);
+      busy |= rd[i] != 0xFFFFFFFFu;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------ *
  * Burst kernel.  The block of a wide step is a function of the READ alone (the top bits of that step's 2W-bit field),
  * not of the interval: the S grid blocks a read needs are known before its search starts.  So a lane group issues its
  * lead-table lookup and up to PF block loads of each of its QPT reads back to back -- S independent requests in flight

@@ -331,11 +331,33 @@ template <int LANES, int EW>
 static fm_wide_fn fm_pick_wide(int qpt)
 {
   if (qpt == 0) return fm_search_wide_kernel<LANES, EW, 1, 256, 4, true>;         /* instrumented */
-  if (qpt == 1) return fm_search_wide_kernel<LANES, EW, 1, 256, 6, false>;
+  if (qpt == 1) return fm_search_wide_kernel<LANES, EW, 1, 256, EW == 3 ? 8 : 6, false>;   /* (96-bit entries: 32 registers, 8 CTAs per SM: 0.640 vs 0.649 ms at 38) */
   if (qpt == 2) return fm_search_wide_kernel<LANES, EW, 2, 256, EW == 3 ? 3 : 4, false>;
   if (qpt == 3) return fm_search_wide_kernel<LANES, EW, 3, 256, EW == 3 ? 2 : 3, false>;
   if (qpt == 4) return fm_search_wide_kernel<LANES, EW, 4, 256, 2, false>;
   return NULL;
+}
+
+typedef void (*fm_wide_dyn_fn)(const FmWideParams, uint32_t);
+template <int LANES, int EW>
+static fm_wide_dyn_fn fm_pick_wide_dyn(int qpt)
+{
+  if (qpt == 1) return fm_search_wide_dyn_kernel<LANES, EW, 1, 256, EW == 3 ? 5 : 6>;
+  if (qpt == 2) return fm_search_wide_dyn_kernel<LANES, EW, 2, 256, 3>;
+  if (qpt == 3) return fm_search_wide_dyn_kernel<LANES, EW, 3, 256, 2>;
+  if (qpt == 4) return fm_search_wide_dyn_kernel<LANES, EW, 4, 256, 2>;
+  return NULL;
+}
+
+/* dynamic read assignment pays when reads differ much in the length of their walk: trees two or more levels deep holding
+ * more than 1 % of the rows (repeat-rich texts).  The one-level trees of a random text's Poisson tail -- 12 % of the steps
+ * with 96-bit entries -- do not: the static kernel's prologue overlaps the lead-table lookup with the first block fetch,
+ * the dynamic one spends an iteration on it (0.65 vs 0.88 ms per 10 M reads at 46 bases per step).  $FMGPU_WIDE_DYNAMIC=0/1 forces. */
+static bool fm_wide_dynamic_enabled(const fmgpu_index_t *idx)
+{
+  const char *env = getenv("FMGPU_WIDE_DYNAMIC");
+  if (env && *env) return atoi(env) != 0;
+  return idx->meta.wide_tree_depth >= 2 && idx->meta.wide_tree_rows * 100ull > idx->meta.bwtsize;
 }
 
 /* burst kernels (all grid blocks of a read in flight at once): QPT reads per lane group x up to PF blocks per read and chunk */
@@ -393,6 +415,26 @@ int32_t fm_launch_wide(const fmgpu_index_t *idx, const uint32_t *d_packed, uint6
   const uint32_t ew = idx->meta.wide_entry_words;
   const bool burst = benv && *benv && atoi(benv) != 0 && ew == 2;
   const int pf = penv && *penv ? atoi(penv) : (pl.S <= 3 ? 3 : 4);
+  if (!d_counters && !burst && p.nsteps >= 1 && fm_wide_dynamic_enabled(idx)) {
+    const int q = v.queries_per_thread;
+    fm_wide_dyn_fn dfn = ew == 3 ? (lanes == 4 ? fm_pick_wide_dyn<4, 3>(q) : fm_pick_wide_dyn<2, 3>(q))
+                                 : (lanes == 4 ? fm_pick_wide_dyn<4, 2>(q) : fm_pick_wide_dyn<2, 2>(q));
+    const char *renv = getenv("FMGPU_WIDE_ROUNDS");
+    uint32_t rounds = renv && *renv && atoi(renv) >= 1 ? (uint32_t) atoi(renv) : 8u, rpc; size_t dsmem;
+    for (;;) {
+      rpc = (256 / lanes) * q * rounds;
+      dsmem = 16 + ((size_t) rpc * p.wpq + 4) * 4;
+      if (dsmem <= 48 * 1024 || rounds == 1) break;
+      rounds--;
+    }
+    if (dfn && dsmem <= 200 * 1024) {
+      if (dsmem > 48 * 1024) CU_TRY(cudaFuncSetAttribute((const void *) dfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dsmem));
+      const uint32_t dgrid = (uint32_t)((nq + rpc - 1) / rpc);
+      void *dargs[] = { (void *) &p, (void *) &rpc };
+      CU_TRY(cudaLaunchKernel((const void *) dfn, dim3(dgrid), dim3(256), dargs, dsmem, stream));
+      return FM_SUCCESS;
+    }
+  }
   const int qsel = d_counters ? 0 : v.queries_per_thread;
   fm_wide_fn fn = burst ? (lanes == 4 ? fm_pick_wide_burst<4>(qsel, pf) : fm_pick_wide_burst<2>(qsel, pf))
                         : ew == 3 ? (lanes == 4 ? fm_pick_wide<4, 3>(qsel) : fm_pick_wide<2, 3>(qsel))

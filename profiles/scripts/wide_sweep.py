@@ -20,7 +20,11 @@ variants = [tuple(int(x) for x in v.split(":")) for v in os.environ["FM_VARIANTS
     [(l_, b_, pf_, q_) for l_ in (2, 4) for b_, pf_ in ((0, 0), (1, 3)) for q_ in (1, 2, 3, 4)]      # lanes:burst:pf:qpt
 reps = int(os.environ.get("FM_REPS", "10"))
 cur_lanes = 0
-for lanes, burst, pf, qpt in variants:
+for var in variants:
+    lanes, burst, pf, qpt = var[:4]
+    dyn = var[4] if len(var) > 4 else -1                      # lanes:burst:pf:qpt[:dynamic]  (dynamic -1 = the library's choice)
+    if dyn >= 0: os.environ["FMGPU_WIDE_DYNAMIC"] = str(dyn)
+    else: os.environ.pop("FMGPU_WIDE_DYNAMIC", None)
     if lanes != cur_lanes:
         if cur_lanes: idx.unwiden()
         idx.widen(int(os.environ.get("FM_W", "0")) or idx.wide_bases_for(length), int(os.environ.get("FM_PB", "0")), lanes); idx.prepare(length)
@@ -38,6 +42,6 @@ for lanes, burst, pf, qpt in variants:
             e0.record(); pkg.check(L.fmgpu_search_device(idx.handle, d_packed.data_ptr(), nq, length, d_res.data_ptr(), C.byref(v), stream), "search"); e1.record()
             torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
         if want is None: want = d_res.clone()
-        rec = {"len": length, "lanes": lanes, "burst": burst, "pf": pf, "qpt": qpt, "ms_best": min(ts[-8:]), "ms_mean": sum(ts[-8:]) / len(ts[-8:]), "mq_per_s": nq / min(ts[-8:]) / 1e3, "equal": bool(torch.equal(d_res, want))}
+        rec = {"len": length, "bases": idx.meta.wide_bases, "lanes": lanes, "dynamic": dyn, "rounds": os.environ.get("FMGPU_WIDE_ROUNDS"), "burst": burst, "pf": pf, "qpt": qpt, "ms_best": min(ts[-8:]), "ms_mean": sum(ts[-8:]) / len(ts[-8:]), "mq_per_s": nq / min(ts[-8:]) / 1e3, "equal": bool(torch.equal(d_res, want))}
         print(json.dumps(rec), flush=True); out.write(json.dumps(rec) + "\n")
         d_res.zero_()

@@ -35,12 +35,14 @@ def serving_widths(k, length, lead_max):
     return out
 
 
+@pytest.mark.parametrize("dynamic", ["0", "1"], ids=["static_assignment", "dynamic_assignment"])
 @pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p))
-def test_wide_steps_golden_all_widths(pkg, monkeypatch, path):
+def test_wide_steps_golden_all_widths(pkg, monkeypatch, path, dynamic):
     """Committed outputs of the unmodified reference searchers; every serving width, prefix sizes from one bit (everything
     in two buckets: deep search trees) over the automatic choice to the whole symbol (one symbol per bucket), every qpt,
     lead tables of several widths, and every 3rd bucket forced onto the exceptional path.  AltCounters files with an
     active padding quirk are refused (the sparse-step table serves them)."""
+    monkeypatch.setenv("FMGPU_WIDE_DYNAMIC", dynamic)           # reads handed to the lane groups statically / from a queue
     g = np.load(path)
     reads, length, k = g["reads"], int(g["length"]), int(g["k"])
     nq = reads.size // length
@@ -93,7 +95,7 @@ def test_wide_steps_golden_all_widths(pkg, monkeypatch, path):
 
 @pytest.mark.parametrize("k,length", [(1, 8), (1, 17), (1, 33), (1, 100), (2, 16), (2, 20), (2, 30), (2, 34), (2, 60), (2, 100), (2, 126),
                                       (2, 128), (2, 250), (1, 251), (2, 25), (2, 101), (2, 45), (2, 61)])
-def test_wide_steps_read_lengths(pkg, k, length):
+def test_wide_steps_read_lengths(pkg, monkeypatch, k, length):
     """length = lead bases + whole wide steps, bit fields of the packed read straddle 32-bit words (60-bit keys span three);
     odd lengths on a 2-step index take an odd lead table (derived 1-step rank).  The width the library proposes for the
     length, the widest, and a narrow one; a table whose width does not serve the length says so instead of answering."""
@@ -111,6 +113,7 @@ def test_wide_steps_read_lengths(pkg, k, length):
     else:                                                        # defined by the plain kernels (tested against the 1-step reference elsewhere)
         b.search(idx, pkg.variant(pkg.MODE_COOP))
         want = b.download()
+    monkeypatch.setenv("FMGPU_WIDE_DYNAMIC", str(length % 2))   # (the default follows the share of rows in trees)
     proposed = idx.wide_bases_for(length)
     assert (proposed != 0) == (length >= 16)
     tried = 0
@@ -162,10 +165,12 @@ def test_wide_unavailable_and_errors(pkg):
 @pytest.mark.skipif(not helpers.has_ref_tools(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("name", ["polyA", "ACGT_period4", "two_letter", "repeat_x40", "random_plus_repeat"])
 @pytest.mark.parametrize("k", [1, 2])
-def test_wide_steps_repetitive_texts_search_trees(pkg, tmp_path, name, k):
+@pytest.mark.parametrize("dynamic", ["0", "1"], ids=["static_assignment", "dynamic_assignment"])
+def test_wide_steps_repetitive_texts_search_trees(pkg, tmp_path, monkeypatch, name, k, dynamic):
     """Repeats put thousands of rows into one bucket: those become search trees of 128-byte blocks (three levels for
     poly-A), walked one fetch per iteration, the two interval ends apart once they leave the root.  Index files and
     expected (L,R) from the unmodified reference tools."""
+    monkeypatch.setenv("FMGPU_WIDE_DYNAMIC", dynamic)
     rng = np.random.default_rng(11)
     n = 30011
     unit = ACGT[rng.integers(0, 4, 700)]
@@ -240,6 +245,7 @@ def test_wide_fuzz_tiny_references_against_the_reference_searcher(pkg, tmp_path)
                 batch = pkg.DeviceBatch(0, reads.size // length, length, k)
                 batch.upload_ascii(reads)
                 os.environ["FMGPU_WIDE_LEAD_MAX"] = "5"
+                os.environ["FMGPU_WIDE_DYNAMIC"] = str((case + length) % 2)
                 try:
                     idx.widen(w, pbits, (2, 4)[(case // 2 + length) % 2])
                     exceptional += idx.meta.wide_exceptional
@@ -247,7 +253,7 @@ def test_wide_fuzz_tiny_references_against_the_reference_searcher(pkg, tmp_path)
                         batch.search(idx, pkg.variant(pkg.MODE_WIDE, qpt))
                         assert np.array_equal(batch.download(), want), f"case {case}: k={k} d={d} n={n} tag={tag} len={length} W={w} prefix={pbits} qpt={qpt}"
                 finally:
-                    del os.environ["FMGPU_WIDE_LEAD_MAX"]
+                    del os.environ["FMGPU_WIDE_LEAD_MAX"], os.environ["FMGPU_WIDE_DYNAMIC"]
                 idx.unwiden()
                 batch.free()
                 cases += 1
