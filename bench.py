@@ -13,7 +13,7 @@ rank's 10 M reads -- in BOTH arms: `--impl reference` runs the reference's own s
 
   value      Mqueries/s, whole job, kernels only, reads packed and resident in HBM (the reference's own
              timed region, common/searchQueries.c:78-98), CUDA events on the launching stream.  Timed
-             kernel: the wide-step kernel (30 bases per 128-byte block fetch, table built on the GPU from
+             kernel: the wide-step kernel (46 bases per 64-byte block fetch: 100 bp = 8 + 2 x 46; table built on the GPU from
              the 2-step index); the sparse-step kernel (14 bases per 64-byte fetch), the fused-step kernel
              (4 bases per fetch) and the plain 2-step Coop kernel are timed beside it as sparse_14base_kernel /
              fused_4base_kernel / plain_2step_kernel; $FM_BENCH_MODE=sparse|fused|coop|task makes one of
@@ -36,7 +36,7 @@ $FM_BENCH_SINGLE_PROCESS=1: ONE process drives all N GPUs through the reference'
 (transferCPUtoGPU: one H2D + cudaMemcpyPeer replicas, N x 10 M reads sharded; searchIndexGPU; transferGPUtoCPU) --
 the drop-in host driver of csrc/fm_host.c instead of one rank per GPU.  Under torchrun only rank 0 works.
 
-Inputs are larger than L2 (34 GB wide table / 34 GB sparse table / 68 GB fused table / 5.33 GB index, 280 MB packed
+Inputs are larger than L2 (74 GB wide table / 34 GB sparse table / 68 GB fused table / 5.33 GB index, 280 MB packed
 reads vs 126 MB L2), so no flush between steps.
 """
 import argparse
@@ -471,7 +471,7 @@ def run_single_process(args, pkg, L, torch, emit):
                              "table_build_s_per_gpu": [st.table_build_s[g] for g in range(ndev)], "queries_h2d_pack_s": st.queries_h2d_pack_s,
                              "results_d2h_s": d2h_s, "transferCPUtoGPU_s": transfer_s, "setup_s": round(setup_s, 1),
                              "index_md5": md5, "index_is_the_reference_builders_file": (md5 == want_md5) if want_md5 else None, "results_md5": res_md5},
-          "kernel_config": {"kernel": (f"wide: {meta.wide_bases} bases/step, {32 * meta.wide_lanes}-byte blocks, 2^{meta.wide_prefix_bits} buckets" if meta.wide_bases else
+          "kernel_config": {"kernel": (f"wide: {meta.wide_bases} bases/step, {32 * meta.wide_lanes}-byte blocks of {32 * meta.wide_entry_words}-bit entries, 2^{meta.wide_prefix_bits} buckets" if meta.wide_bases else
                                        f"sparse: {meta.sparse_bases} bases/step, grid of {meta.sparse_uniform_nb} blocks per symbol"),
                             "table_gb": (meta.wide_bytes if meta.wide_bases else meta.sparse_bytes) / 1e9},
           "cpu_baseline": {"value": mq_cpu, "unit": "Mqueries/s", "cores": cores, "kind": CPU_KIND,
@@ -892,7 +892,8 @@ def main():
         traffic, traffic_src = ncu_traffic("wide" if wide else "sparse" if sparse else "fused" if fused else "plain")
         e2e_value = world * nq / e2e_ms_step / 1e3
         ceiling_mq = host_bw * 1e3 / READ_LEN if host_bw > 0 else None
-        kernel_desc = (f"wide: {meta.wide_bases} bases/step, {32 * meta.wide_lanes}-byte blocks of {4 * meta.wide_lanes - 1} 64-bit entries (rest of the symbol + row), block = top {meta.wide_prefix_bits} bits of the "
+        kernel_desc = (f"wide: {meta.wide_bases} bases/step, {32 * meta.wide_lanes}-byte blocks of {(4 * meta.wide_lanes - 1) if meta.wide_entry_words == 2 else 2 * meta.wide_lanes} "
+                       f"{32 * meta.wide_entry_words}-bit entries (rest of the symbol + row), block = top {meta.wide_prefix_bits} bits of the "
                        f"wide symbol (computed from the read, shared by both interval ends), {READ_LEN - (READ_LEN // meta.wide_bases) * meta.wide_bases}-base lead table, "
                        f"{meta.wide_overflow} overfull buckets as search trees ({meta.wide_tree_nodes} blocks, depth {meta.wide_tree_depth}), {meta.wide_exceptional} exceptional buckets on plain steps, "
                        f"{meta.wide_lanes} x 256-bit loads, one state machine per read, qpt={var.queries_per_thread or 1}" if wide else

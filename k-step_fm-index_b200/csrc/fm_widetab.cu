@@ -121,13 +121,18 @@ static cudaError_t fm_wide_build(fmgpu_index_t *idx, const fm_wide_shape &sh, fm
     fm_wide_compose_kernel<KeyT><<<(unsigned)(((uint64_t) n + 255) / 256), 256>>>(idx->blocks, idx->meta.nblocks, sym, n, kbits, hops, wbits, keys, vals);
     e = cudaGetLastError();
   }
-  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(NULL, tmp_bytes, keys, keys2, vals, vals2, (int64_t) n, 0, (int)(wbits + 1));
+  /* order of (F(i), i): the sort is stable and the input rows ascend.  Double-buffer form: the two key / value arrays are the
+   * sort's only big buffers (the plain form would add a third pair inside its temporary storage: 48 GB at 2 Gbp) */
+  cub::DoubleBuffer<KeyT> dk(keys, keys2);
+  cub::DoubleBuffer<uint64_t> dv(vals, vals2);
+  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(NULL, tmp_bytes, dk, dv, (int64_t) n, 0, (int)(wbits + 1));
   if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(NULL, tmp2, (uint32_t *) NULL, (uint32_t *) NULL, (int64_t) nroots);
   if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
   if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16);
-  /* order of (F(i), i): the sort is stable and the input rows ascend */
-  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int64_t) n, 0, (int)(wbits + 1));
+  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int64_t) n, 0, (int)(wbits + 1));
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess && dk.Current() != keys2) { KeyT *t = keys; keys = keys2; keys2 = t; }       /* sorted pairs end up in keys2 / vals2 */
+  if (e == cudaSuccess && dv.Current() != vals2) { uint64_t *t = vals; vals = vals2; vals2 = t; }
   cudaFree(keys); keys = NULL; cudaFree(vals); vals = NULL; cudaFree(sym); sym = NULL;
   if (e == cudaSuccess) e = cudaMalloc((void **) &bstart, 4ull * ((uint64_t) nroots + 1));
   if (e == cudaSuccess) e = cudaMalloc((void **) &g0, 4ull * nroots);
