@@ -11,7 +11,8 @@ python bench.py --steps 2 --warmup 3 > gpurun_out/bench_plain.json 2> gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 > gpurun_out/bench_under_ncu.json 2> gpurun_out/bench_under_ncu.err
 echo "launch list rc=$? ($(wc -l < gpurun_out/launches.csv) lines)"
-# the timed kernel since the wide-step table: fm_search_wide_kernel<2, 1, ...> (64-byte blocks, one read per lane pair) on the benchmark workload
+# the timed kernel since the wide-step table: fm_search_wide_kernel<2, 3, 1, ...> (64-byte blocks of 96-bit entries, 46 bases per step, one read
+# per lane pair) on the benchmark workload; FM_W=30 profiles the 64-bit-entry form
 FM_VARIANTS=2:0:0:1 FM_REPS=3 ncu --set full --import-source on --clock-control none -k regex:fm_search_wide_kernel -f -o gpurun_out/prof_wide \
     python profiles/scripts/wide_sweep.py > gpurun_out/prof_wide.log 2>&1
 echo "set full rc=$?"; ls -la gpurun_out/prof_wide.ncu-rep
