@@ -892,7 +892,7 @@ def main():
         traffic, traffic_src = ncu_traffic("wide" if wide else "sparse" if sparse else "fused" if fused else "plain")
         e2e_value = world * nq / e2e_ms_step / 1e3
         ceiling_mq = host_bw * 1e3 / READ_LEN if host_bw > 0 else None
-        kernel_desc = (f"wide: {meta.wide_bases} bases/step, {32 * meta.wide_lanes}-byte blocks of {(4 * meta.wide_lanes - 1) if meta.wide_entry_words == 2 else 2 * meta.wide_lanes} "
+        kernel_desc = (f"wide: {meta.wide_bases} bases/step, {32 * meta.wide_lanes}-byte blocks of {meta.wide_block_entries} "
                        f"{32 * meta.wide_entry_words}-bit entries (rest of the symbol + row), block = top {meta.wide_prefix_bits} bits of the "
                        f"wide symbol (computed from the read, shared by both interval ends), {READ_LEN - (READ_LEN // meta.wide_bases) * meta.wide_bases}-base lead table, "
                        f"{meta.wide_overflow} overfull buckets as search trees ({meta.wide_tree_nodes} blocks, depth {meta.wide_tree_depth}), {meta.wide_exceptional} exceptional buckets on plain steps, "

@@ -251,7 +251,9 @@ typedef struct {
   uint64_t wide_tree_rows;     /* rows living in trees (of bwtsize)                              */
   uint64_t wide_exceptional;   /* buckets whose steps run on the block table (a suffix shorter than the step sorts into them) */
   uint32_t wide_lanes;         /* lanes per block: 2 = 64-byte blocks (7 entries), 4 = 128-byte blocks (15 entries) */
-  uint32_t wide_entry_words;   /* 2 = 64-bit entries (steps up to 30 bases), 3 = 96-bit entries (steps up to 46 bases, 2 * lanes entries per block) */
+  uint32_t wide_entry_words;   /* 2 = 64-bit entries (steps up to 30 bases), 3 = 96-bit entries (steps up to 46 bases) */
+  uint32_t wide_block_entries; /* entries per block: 7 / 15 (64-bit entries, 64- / 128-byte blocks), 5 (96-bit entries packed into 64 bytes), 4 / 8 (96-bit, unpacked) */
+  uint32_t reserved3;
 } fmgpu_index_meta_t;
 
 /* what the last transferCPUtoGPU / searchIndexGPU / transferGPUtoCPU sequence of this process did (wall-clock seconds of

@@ -80,7 +80,8 @@ class fmgpu_index_meta_t(C.Structure):
                 ("wide_bases", C.c_uint32), ("wide_prefix_bits", C.c_uint32), ("wide_row_bits", C.c_uint32), ("wide_tree_depth", C.c_uint32),
                 ("wide_bytes", C.c_uint64), ("wide_blocks", C.c_uint64), ("wide_overflow", C.c_uint64),
                 ("wide_tree_nodes", C.c_uint64), ("wide_tree_rows", C.c_uint64), ("wide_exceptional", C.c_uint64),
-                ("wide_lanes", C.c_uint32), ("wide_entry_words", C.c_uint32)]
+                ("wide_lanes", C.c_uint32), ("wide_entry_words", C.c_uint32),
+                ("wide_block_entries", C.c_uint32), ("reserved3", C.c_uint32)]
 
 
 class fmgpu_transfer_stats_t(C.Structure):

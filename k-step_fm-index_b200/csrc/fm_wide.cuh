@@ -104,8 +104,13 @@ __device__ __forceinline__ uint64_t fm_read_field64(const uint32_t *q, uint32_t 
  * (100 bp = 8 + 2 x 46: two fetches instead of three), two entries per lane behind a two-word lane header (the block header
  * in lane 0), i.e. 2 * LANES entries per block and a fan-out of 2 * LANES + 1. */
 typedef unsigned __int128 fm_u128;
+/* EW = 5: 96-bit entries PACKED five to a 64-byte block (LANES = 2 only): a one-word header { inner flag : 1, value : 31 } --
+ * 0xFFFFFFFF = exceptional -- then the entries back to back, the third one straddling the two lanes (one shuffle).  4 % instead
+ * of 12 % of the steps continue into a search tree on a random text.  Needs bwtsize and the block count below 2^31. */
 template <int EW> struct FmWideKey { typedef uint64_t type; };
 template <> struct FmWideKey<3> { typedef fm_u128 type; };
+template <> struct FmWideKey<5> { typedef fm_u128 type; };
+template <int LANES, int EW> struct FmWideSlots { static constexpr uint32_t value = EW == 5 ? 5u : EW == 3 ? 2u * LANES : 4u * LANES - 1u; };
 
 /* bits [pos, pos + nbits) of a packed read in shared memory, nbits <= 96 */
 __device__ __forceinline__ fm_u128 fm_read_field96(const uint32_t *q, uint32_t pos, uint32_t nbits)
@@ -118,7 +123,7 @@ __device__ __forceinline__ fm_u128 fm_read_field96(const uint32_t *q, uint32_t p
 }
 template <int EW> __device__ __forceinline__ typename FmWideKey<EW>::type fm_wide_read_key(const uint32_t *q, uint32_t pos, uint32_t nbits)
 {
-  if constexpr (EW == 3) return fm_read_field96(q, pos, nbits);
+  if constexpr (EW != 2) return fm_read_field96(q, pos, nbits);
   else return fm_read_field64(q, pos, nbits);
 }
 
@@ -134,6 +139,23 @@ __device__ __forceinline__ uint32_t fm_wide_partial3(const uint32_t (&w)[8], fm_
     const uint64_t ehi = (uint64_t) w[3 + 3 * j] | ((uint64_t) w[4 + 3 * j] << 32);
     c += (ehi < khi || (ehi == khi && elo < klo)) ? 1u : 0u;
   }
+  return c;
+}
+
+__device__ __forceinline__ uint32_t fm_wide_lt96(uint32_t elo, uint32_t emid, uint32_t ehi, uint64_t khi, uint32_t klo)
+{
+  const uint64_t eh = (uint64_t) emid | ((uint64_t) ehi << 32);
+  return (eh < khi || (eh == khi && elo < klo)) ? 1u : 0u;
+}
+/* packed form: lane 0 holds the header word, entries 1, 2 and the low word of entry 3 (handed over in xw); lane 1 the rest */
+__device__ __forceinline__ uint32_t fm_wide_partial5(const uint32_t (&w)[8], fm_u128 key, uint32_t lg, uint32_t xw)
+{
+  const uint32_t klo = (uint32_t) key;
+  const uint64_t khi = (uint64_t)(key >> 32);
+  const bool hi = lg != 0u;
+  uint32_t c = fm_wide_lt96(hi ? xw : w[1], hi ? w[0] : w[2], hi ? w[1] : w[3], khi, klo);
+  c += fm_wide_lt96(hi ? w[2] : w[4], hi ? w[3] : w[5], hi ? w[4] : w[6], khi, klo);
+  c += hi ? fm_wide_lt96(w[5], w[6], w[7], khi, klo) : 0u;
   return c;
 }
 
@@ -178,10 +200,17 @@ __device__ __forceinline__ void fm_stage_reads(uint32_t *fsm, uint32_t *sq, cons
   }
 }
 
-template <int EW> __device__ __forceinline__ uint32_t fm_wide_count(const uint32_t (&w)[8], typename FmWideKey<EW>::type key, uint32_t lg)
+template <int EW> __device__ __forceinline__ uint32_t fm_wide_count(const uint32_t (&w)[8], typename FmWideKey<EW>::type key, uint32_t lg, uint32_t xw)
 {
-  if constexpr (EW == 3) return fm_wide_partial3(w, key);
+  if constexpr (EW == 5) return fm_wide_partial5(w, key, lg, xw);
+  else if constexpr (EW == 3) return fm_wide_partial3(w, key);
   else return fm_wide_partial(w, key, lg);
+}
+/* header of a block from lane 0's first two words */
+template <int EW> __device__ __forceinline__ void fm_wide_header(uint32_t w0, uint32_t w1, uint32_t &value, uint32_t &kind)
+{
+  if constexpr (EW == 5) { value = w0 & 0x7FFFFFFFu; kind = w0 == 0xFFFFFFFFu ? FM_WD_EXC : (w0 >> 31); }
+  else { value = w0; kind = w1; }
 }
 
 /* one wide step of an exceptional bucket: `hops` base-k steps on SB96 for both interval ends */
@@ -263,13 +292,14 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_kernel(const FmW
       const bool doL = act && aL[i] != FM_WD_DONE;
       const bool doR = act && (!doL || aR[i] == aL[i]);                  /* R alone, or riding on the node it shares with L */
       const KeyT ksub = (key[i] & submask) << p.row_bits;
-      uint32_t cL = 0, cR = 0;
+      uint32_t cL = 0, cR = 0, xw = 0;
+      if constexpr (EW == 5) xw = __shfl_xor_sync(0xFFFFFFFFu, w[i][7], 1);
       if (act) {
-        cL = fm_wide_count<EW>(w[i], ksub | L[i], lg);
-        cR = fm_wide_count<EW>(w[i], ksub | R[i], lg);
+        cL = fm_wide_count<EW>(w[i], ksub | L[i], lg, xw);
+        cR = fm_wide_count<EW>(w[i], ksub | R[i], lg, xw);
       }
-      const uint32_t hval  = __shfl_sync(0xFFFFFFFFu, w[i][0], 0, LANES);
-      const uint32_t hkind = __shfl_sync(0xFFFFFFFFu, w[i][1], 0, LANES);
+      uint32_t hval, hkind;
+      fm_wide_header<EW>(__shfl_sync(0xFFFFFFFFu, w[i][0], 0, LANES), EW == 5 ? 0u : __shfl_sync(0xFFFFFFFFu, w[i][1], 0, LANES), hval, hkind);
       const uint32_t vL = hval + fm_group_sum<LANES>(cL), vR = hval + fm_group_sum<LANES>(cR);
       if (act && hkind == FM_WD_EXC) {                                   /* (only ever at a grid block: both ends are here) */
         fm_wide_plain_step<KeyT>(p, key[i], L[i], R[i]);
@@ -309,13 +339,12 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_kernel(const FmW
 /* ------------------------------------------------------------------------ *
  * The same search with DYNAMIC read assignment (fm_search_sparse_dyn_kernel's scheme): the CTA stages `reads_per_cta` reads
  * (several rounds of its slots) with one bulk copy and a lane group that finishes a read pulls the next one from a
- * shared-memory counter; the lead-table lookup of a new read is one more state (aL = FM_WD_START), so every iteration
- * issues exactly one load per busy slot.  With static assignment a warp lasts as long as the slowest of its reads:
+ * shared-memory counter.  The lead-table lookup of a new read is issued TOGETHER with the read's first block fetch -- both
+ * addresses are functions of the read alone -- so a read costs exactly its block fetches in iterations, as in the static
+ * kernel.  With static assignment a warp lasts as long as the slowest of its reads:
  * that is nothing on the roomy 64-bit grid (0.3 % of the steps meet a tree), but with 96-bit entries (four per block,
  * 12 % of the steps continue into a tree) and on repeat-rich texts half of the fetch slots would idle.
  * ------------------------------------------------------------------------ */
-#define FM_WD_START 0xFFFFFFFEu
-
 template <int LANES, int EW, int QPT, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_dyn_kernel(const FmWideParams p, uint32_t reads_per_cta)
 {
@@ -332,6 +361,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_dyn_kernel(const
 
   uint32_t L[QPT], R[QPT], aL[QPT], aR[QPT], rem[QPT], rd[QPT];
   KeyT key[QPT];
+  bool fresh[QPT];                                             /* the read was just taken: its (L,R) still come from the lead table */
   /* takes the next read of the CTA for slot i (or parks the slot): all lanes of the warp call it together */
   auto take = [&](int i, bool need) {
     uint32_t r = 0;
@@ -341,16 +371,16 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_dyn_kernel(const
       rd[i] = r;
       if (r < nqb) {
         rem[i] = p.nsteps; L[i] = 0u; R[i] = p.bwtsize;
-        if (p.start) { aL[i] = FM_WD_START; aR[i] = FM_WD_DONE; }
-        else if (rem[i]) {
-          key[i] = fm_wide_read_key<EW>(sq + r * p.wpq, 0u, p.wbits);
+        fresh[i] = p.start != NULL;
+        if (rem[i]) {
+          key[i] = fm_wide_read_key<EW>(sq + r * p.wpq, p.start_bits, p.wbits);
           aL[i] = aR[i] = (uint32_t)(key[i] >> p.sub_bits);
         } else { aL[i] = aR[i] = FM_WD_DONE; }
-      } else { rem[i] = 0u; aL[i] = aR[i] = FM_WD_DONE; rd[i] = 0xFFFFFFFFu; }
+      } else { rem[i] = 0u; aL[i] = aR[i] = FM_WD_DONE; rd[i] = 0xFFFFFFFFu; fresh[i] = false; }
     }
   };
   #pragma unroll
-  for (int i = 0; i < QPT; i++) { rd[i] = 0xFFFFFFFFu; rem[i] = 0u; aL[i] = aR[i] = FM_WD_DONE; L[i] = R[i] = 0u; key[i] = 0; take(i, true); }
+  for (int i = 0; i < QPT; i++) { rd[i] = 0xFFFFFFFFu; rem[i] = 0u; aL[i] = aR[i] = FM_WD_DONE; L[i] = R[i] = 0u; key[i] = 0; fresh[i] = false; take(i, true); }
 
   bool busy = false;
   #pragma unroll
@@ -361,8 +391,8 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_dyn_kernel(const
     #pragma unroll
     for (int i = 0; i < QPT; i++) {
       if (rd[i] != 0xFFFFFFFFu) {
-        if (aL[i] == FM_WD_START) lr[i] = __ldg(p.start + (sq[rd[i] * p.wpq] & kmask));
-        else if (rem[i]) {
+        if (fresh[i]) lr[i] = __ldg(p.start + (sq[rd[i] * p.wpq] & kmask));   /* in flight together with the first block */
+        if (rem[i]) {
           const uint32_t a = (aL[i] != FM_WD_DONE) ? aL[i] : aR[i];
           FM_BOUND(a, p.total_blocks, "wide (dynamic): grid / tree block"); FM_BOUND(rd[i], nqb, "wide (dynamic): read slot");
           fm_wide_load<LANES>(p.wblocks + (size_t) a * (2u * LANES) + 2u * lg, w[i]);
@@ -373,18 +403,19 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_dyn_kernel(const
     #pragma unroll
     for (int i = 0; i < QPT; i++) {
       const bool have = rd[i] != 0xFFFFFFFFu;
-      const bool starting = have && aL[i] == FM_WD_START;
-      const bool act = have && !starting && rem[i] != 0u;
+      if (have && fresh[i]) { L[i] = lr[i].x; R[i] = lr[i].y; fresh[i] = false; }
+      const bool act = have && rem[i] != 0u;
       const bool doL = act && aL[i] != FM_WD_DONE;
       const bool doR = act && (!doL || aR[i] == aL[i]);
       const KeyT ksub = (key[i] & submask) << p.row_bits;
-      uint32_t cL = 0, cR = 0;
+      uint32_t cL = 0, cR = 0, xw = 0;
+      if constexpr (EW == 5) xw = __shfl_xor_sync(0xFFFFFFFFu, w[i][7], 1);
       if (act) {
-        cL = fm_wide_count<EW>(w[i], ksub | L[i], lg);
-        cR = fm_wide_count<EW>(w[i], ksub | R[i], lg);
+        cL = fm_wide_count<EW>(w[i], ksub | L[i], lg, xw);
+        cR = fm_wide_count<EW>(w[i], ksub | R[i], lg, xw);
       }
-      const uint32_t hval  = __shfl_sync(0xFFFFFFFFu, w[i][0], 0, LANES);
-      const uint32_t hkind = __shfl_sync(0xFFFFFFFFu, w[i][1], 0, LANES);
+      uint32_t hval, hkind;
+      fm_wide_header<EW>(__shfl_sync(0xFFFFFFFFu, w[i][0], 0, LANES), EW == 5 ? 0u : __shfl_sync(0xFFFFFFFFu, w[i][1], 0, LANES), hval, hkind);
       const uint32_t vL = hval + fm_group_sum<LANES>(cL), vR = hval + fm_group_sum<LANES>(cR);
       if (act && hkind == FM_WD_EXC) {
         fm_wide_plain_step<KeyT>(p, key[i], L[i], R[i]);
@@ -395,8 +426,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_dyn_kernel(const
         if (doR) { if (is_inner) aR[i] = vR; else { R[i] = vR; aR[i] = FM_WD_DONE; } }
       }
       bool next_block = false;
-      if (starting) { L[i] = lr[i].x; R[i] = lr[i].y; aL[i] = aR[i] = FM_WD_DONE; next_block = rem[i] != 0u; }
-      else if (act && aL[i] == FM_WD_DONE && aR[i] == FM_WD_DONE) { rem[i] -= 1u; next_block = rem[i] != 0u; }
+      if (act && aL[i] == FM_WD_DONE && aR[i] == FM_WD_DONE) { rem[i] -= 1u; next_block = rem[i] != 0u; }
       if (next_block) {
         key[i] = fm_wide_read_key<EW>(sq + rd[i] * p.wpq, p.start_bits + (p.nsteps - rem[i]) * p.wbits, p.wbits);
         aL[i] = aR[i] = (uint32_t)(key[i] >> p.sub_bits);
@@ -610,7 +640,7 @@ __global__ void fm_wide_verify_buckets_kernel(const uint32_t *__restrict__ bstar
 /* shape of the tree over cnt > SLOTS entries: N[v] = nodes of level v (0 = leaves), depth D with N[D] = 1 (the root, which
  * lives in the grid); nodes below the root = sum of N[0 .. D-1] */
 template <int LANES, int EW> struct FmWideTree {
-  static constexpr uint32_t SLOTS = EW == 3 ? 2u * LANES : 4u * LANES - 1u, FAN = SLOTS + 1u;
+  static constexpr uint32_t SLOTS = FmWideSlots<LANES, EW>::value, FAN = SLOTS + 1u;
   uint32_t N[FM_WD_MAXDEPTH + 1];
   uint32_t D;
   __host__ __device__ explicit FmWideTree(uint32_t cnt)
@@ -663,7 +693,12 @@ __global__ void __launch_bounds__(256) fm_wide_count_kernel(const FmWideBuild<ty
 template <int LANES, int EW, typename KeyT>
 __device__ __forceinline__ void fm_wide_put(uint32_t (&w)[8 * LANES], uint32_t j, KeyT e, bool pad)
 {
-  if constexpr (EW == 3) {
+  if constexpr (EW == 5) {
+    const uint32_t at = 1u + 3u * (j - 1u);
+    w[at] = pad ? 0xFFFFFFFFu : (uint32_t) e;
+    w[at + 1] = pad ? 0xFFFFFFFFu : (uint32_t)(e >> 32);
+    w[at + 2] = pad ? 0xFFFFFFFFu : (uint32_t)((fm_u128) e >> 64);
+  } else if constexpr (EW == 3) {
     const uint32_t at = 8u * ((j - 1u) >> 1) + 2u + 3u * ((j - 1u) & 1u);
     w[at] = pad ? 0xFFFFFFFFu : (uint32_t) e;
     w[at + 1] = pad ? 0xFFFFFFFFu : (uint32_t)(e >> 32);
@@ -687,7 +722,7 @@ __device__ __forceinline__ void fm_wide_write_node(const FmWideBuild<typename Fm
   for (uint32_t c = 0; c < 8u * LANES; c++) w[c] = 0xFFFFFFFFu;
   if (v == 0) {
     const uint64_t first = (uint64_t) m * SLOTS;
-    w[0] = base + (uint32_t) first; w[1] = FM_WD_LEAF;
+    if (EW == 5) w[0] = base + (uint32_t) first; else { w[0] = base + (uint32_t) first; w[1] = FM_WD_LEAF; }
     #pragma unroll
     for (uint32_t c = 1; c <= SLOTS; c++) {
       const bool have = first + c - 1 < cnt;
@@ -696,7 +731,7 @@ __device__ __forceinline__ void fm_wide_write_node(const FmWideBuild<typename Fm
   } else {
     uint64_t span = SLOTS;                                     /* entries under one child: SLOTS * FAN^(v-1) */
     for (uint32_t u = 1; u < v; u++) span *= FAN;
-    w[0] = area + t.level_offset(v - 1) + m * FAN; w[1] = FM_WD_INNER;
+    if (EW == 5) w[0] = (area + t.level_offset(v - 1) + m * FAN) | 0x80000000u; else { w[0] = area + t.level_offset(v - 1) + m * FAN; w[1] = FM_WD_INNER; }
     #pragma unroll
     for (uint32_t c = 1; c <= SLOTS; c++) {
       const uint64_t child = (uint64_t) m * FAN + c, at = child * span;
@@ -716,7 +751,7 @@ __global__ void __launch_bounds__(256) fm_wide_fill_roots_kernel(const FmWideBui
   if (b >= x.nroots) return;
   uint4 *dst = wblocks + (size_t) b * (2u * LANES);
   if (fm_wide_is_exc(x, b)) {
-    dst[0] = make_uint4(0u, FM_WD_EXC, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    dst[0] = EW == 5 ? make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu) : make_uint4(0u, FM_WD_EXC, 0xFFFFFFFFu, 0xFFFFFFFFu);
     #pragma unroll
     for (uint32_t c = 1; c < 2u * LANES; c++) dst[c] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
     return;

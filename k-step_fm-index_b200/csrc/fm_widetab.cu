@@ -19,7 +19,7 @@ extern "C" int32_t fmgpu_index_unwiden(fmgpu_index_t *idx)
   }
   idx->meta.wide_bases = 0; idx->meta.wide_prefix_bits = 0; idx->meta.wide_row_bits = 0; idx->meta.wide_bytes = 0; idx->meta.wide_blocks = 0;
   idx->meta.wide_overflow = 0; idx->meta.wide_tree_nodes = 0; idx->meta.wide_tree_rows = 0; idx->meta.wide_tree_depth = 0;
-  idx->meta.wide_exceptional = 0; idx->meta.wide_lanes = 0; idx->meta.wide_entry_words = 0;
+  idx->meta.wide_exceptional = 0; idx->meta.wide_lanes = 0; idx->meta.wide_entry_words = 0; idx->meta.wide_block_entries = 0;
   fm_budget_account(idx);
   return FM_SUCCESS;
 }
@@ -245,8 +245,12 @@ extern "C" int32_t fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, ui
   sh.W = W; sh.pb = pb; sh.rb = rb; sh.lanes = lanes; sh.ew = ew; sh.force_every = fenv && *fenv ? (uint32_t) atoi(fenv) : 0u;
   fm_wide_built bt;
   bool over_budget = false;
+  /* 96-bit entries on 64-byte blocks: packed five to a block (one-word header) when row numbers and block numbers fit 31 bits */
+  const char *penv = getenv("FMGPU_WIDE_PACK");
+  const bool packed = ew == 3 && lanes == 2 && n < 0x7FFFFFF0u && (uint64_t) nroots + n / 4 + n / 16 < 0x7FFFFF00ull && !(penv && *penv && atoi(penv) == 0);
   cudaError_t e = lanes == 4 ? (ew == 3 ? fm_wide_build<4, 3>(idx, sh, &bt, &over_budget) : fm_wide_build<4, 2>(idx, sh, &bt, &over_budget))
-                             : (ew == 3 ? fm_wide_build<2, 3>(idx, sh, &bt, &over_budget) : fm_wide_build<2, 2>(idx, sh, &bt, &over_budget));
+                             : (packed ? fm_wide_build<2, 5>(idx, sh, &bt, &over_budget) :
+                                ew == 3 ? fm_wide_build<2, 3>(idx, sh, &bt, &over_budget) : fm_wide_build<2, 2>(idx, sh, &bt, &over_budget));
   if (over_budget) return fm_fail_msg(FM_E_NOT_IMPLEMENTED, "the wide-step table would exceed the derived-table budget");
   if (e != cudaSuccess) {
     cudaGetLastError();                                          /* a failed cudaMalloc stays "last error" otherwise and fails the next attempt's first check */
@@ -258,6 +262,7 @@ extern "C" int32_t fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, ui
   idx->meta.wide_blocks = bt.total_blocks; idx->meta.wide_bytes = bt.total_blocks * bbytes; idx->meta.wide_lanes = lanes; idx->meta.wide_entry_words = ew;
   idx->meta.wide_overflow = bt.stats[0]; idx->meta.wide_tree_rows = bt.stats[1]; idx->meta.wide_tree_depth = (uint32_t) bt.stats[2];
   idx->meta.wide_tree_nodes = bt.total_ext; idx->meta.wide_exceptional = bt.stats[3];
+  idx->meta.wide_block_entries = packed ? 5u : ew == 3 ? 2u * lanes : 4u * lanes - 1u;
   fm_budget_account(idx);
   return FM_SUCCESS;
 }
@@ -332,13 +337,23 @@ void fm_wide_prepare(fmgpu_index_t *idx, uint32_t len)
 }
 
 typedef void (*fm_wide_fn)(const FmWideParams);
+/* one read per lane group in CTAs of 128 or 64 threads: a CTA's registers and warp slots are free again when ITS slowest
+ * read is done, so smaller CTAs waste less of the SM on the reads that walk a tree */
+template <int LANES, int EW>
+static fm_wide_fn fm_pick_wide_small(int tpb)
+{
+  if (tpb == 128) return fm_search_wide_kernel<LANES, EW, 1, 128, EW != 2 ? 16 : 12, false>;
+  if (tpb == 64)  return fm_search_wide_kernel<LANES, EW, 1, 64, 32, false>;
+  return NULL;
+}
+
 template <int LANES, int EW>
 static fm_wide_fn fm_pick_wide(int qpt)
 {
   if (qpt == 0) return fm_search_wide_kernel<LANES, EW, 1, 256, 4, true>;         /* instrumented */
-  if (qpt == 1) return fm_search_wide_kernel<LANES, EW, 1, 256, EW == 3 ? 8 : 6, false>;   /* (96-bit entries: 32 registers, 8 CTAs per SM: 0.640 vs 0.649 ms at 38) */
-  if (qpt == 2) return fm_search_wide_kernel<LANES, EW, 2, 256, EW == 3 ? 3 : 4, false>;
-  if (qpt == 3) return fm_search_wide_kernel<LANES, EW, 3, 256, EW == 3 ? 2 : 3, false>;
+  if (qpt == 1) return (EW != 2 && getenv("FMGPU_WIDE_MINB6")) ? fm_search_wide_kernel<LANES, EW, 1, 256, 6, false> : fm_search_wide_kernel<LANES, EW, 1, 256, EW != 2 ? 8 : 6, false>;   /* (96-bit entries: 32 registers, 8 CTAs per SM: 0.640 vs 0.649 ms at 38) */
+  if (qpt == 2) return fm_search_wide_kernel<LANES, EW, 2, 256, EW != 2 ? 3 : 4, false>;
+  if (qpt == 3) return fm_search_wide_kernel<LANES, EW, 3, 256, EW != 2 ? 2 : 3, false>;
   if (qpt == 4) return fm_search_wide_kernel<LANES, EW, 4, 256, 2, false>;
   return NULL;
 }
@@ -347,7 +362,7 @@ typedef void (*fm_wide_dyn_fn)(const FmWideParams, uint32_t);
 template <int LANES, int EW>
 static fm_wide_dyn_fn fm_pick_wide_dyn(int qpt)
 {
-  if (qpt == 1) return fm_search_wide_dyn_kernel<LANES, EW, 1, 256, EW == 3 ? 5 : 6>;
+  if (qpt == 1) return fm_search_wide_dyn_kernel<LANES, EW, 1, 256, EW != 2 ? 5 : 6>;
   if (qpt == 2) return fm_search_wide_dyn_kernel<LANES, EW, 2, 256, 3>;
   if (qpt == 3) return fm_search_wide_dyn_kernel<LANES, EW, 3, 256, 2>;
   if (qpt == 4) return fm_search_wide_dyn_kernel<LANES, EW, 4, 256, 2>;
@@ -405,9 +420,15 @@ int32_t fm_launch_wide(const fmgpu_index_t *idx, const uint32_t *d_packed, uint6
   p.start = pl.b ? idx->wlead[pl.b] : NULL; p.start_bits = 2 * pl.b;
   p.fetch_counters = d_counters;
   if (d_counters) v.queries_per_thread = 1;
+  const char *tenv = getenv("FMGPU_WIDE_TPB");
+  uint32_t tpb = 256;
+  if (!d_counters && v.queries_per_thread == 1) {
+    tpb = tenv && *tenv ? (uint32_t) atoi(tenv) : (v.threads_per_block == 64 || v.threads_per_block == 128 ? (uint32_t) v.threads_per_block : 256u);
+    if (tpb != 64 && tpb != 128) tpb = 256;
+  }
   uint32_t qper; size_t smem;
   for (;;) {
-    qper = (256 / lanes) * v.queries_per_thread;
+    qper = (tpb / lanes) * v.queries_per_thread;
     smem = 16 + ((size_t) qper * p.wpq + 4) * 4;
     if (smem <= 200 * 1024) break;
     if (v.queries_per_thread > 1) v.queries_per_thread -= 1;
@@ -418,11 +439,12 @@ int32_t fm_launch_wide(const fmgpu_index_t *idx, const uint32_t *d_packed, uint6
    * $FMGPU_WIDE_PF: blocks per read and chunk the burst kernel keeps in flight (3 or 4; default: 3 up to three steps, else 4) */
   const char *benv = getenv("FMGPU_WIDE_BURST"), *penv = getenv("FMGPU_WIDE_PF");
   const uint32_t ew = idx->meta.wide_entry_words;
+  const bool packed = ew == 3 && idx->meta.wide_block_entries == 5;
   const bool burst = benv && *benv && atoi(benv) != 0 && ew == 2;
   const int pf = penv && *penv ? atoi(penv) : (pl.S <= 3 ? 3 : 4);
   if (!d_counters && !burst && p.nsteps >= 1 && fm_wide_dynamic_enabled(idx)) {
     const int q = v.queries_per_thread;
-    fm_wide_dyn_fn dfn = ew == 3 ? (lanes == 4 ? fm_pick_wide_dyn<4, 3>(q) : fm_pick_wide_dyn<2, 3>(q))
+    fm_wide_dyn_fn dfn = packed ? fm_pick_wide_dyn<2, 5>(q) : ew == 3 ? (lanes == 4 ? fm_pick_wide_dyn<4, 3>(q) : fm_pick_wide_dyn<2, 3>(q))
                                  : (lanes == 4 ? fm_pick_wide_dyn<4, 2>(q) : fm_pick_wide_dyn<2, 2>(q));
     const char *renv = getenv("FMGPU_WIDE_ROUNDS");
     uint32_t rounds = renv && *renv && atoi(renv) >= 1 ? (uint32_t) atoi(renv) : 8u, rpc; size_t dsmem;
@@ -442,13 +464,18 @@ int32_t fm_launch_wide(const fmgpu_index_t *idx, const uint32_t *d_packed, uint6
   }
   const int qsel = d_counters ? 0 : v.queries_per_thread;
   fm_wide_fn fn = burst ? (lanes == 4 ? fm_pick_wide_burst<4>(qsel, pf) : fm_pick_wide_burst<2>(qsel, pf))
+                        : packed ? fm_pick_wide<2, 5>(qsel)
                         : ew == 3 ? (lanes == 4 ? fm_pick_wide<4, 3>(qsel) : fm_pick_wide<2, 3>(qsel))
                                   : (lanes == 4 ? fm_pick_wide<4, 2>(qsel) : fm_pick_wide<2, 2>(qsel));
+  if (tpb != 256 && !burst)
+    fn = packed ? fm_pick_wide_small<2, 5>(tpb) : ew == 3 ? (lanes == 4 ? fm_pick_wide_small<4, 3>(tpb) : fm_pick_wide_small<2, 3>(tpb))
+                                                          : (lanes == 4 ? fm_pick_wide_small<4, 2>(tpb) : fm_pick_wide_small<2, 2>(tpb));
+  else tpb = 256;
   if (!fn) return fm_fail_msg(FM_E_BAD_ARGUMENT, "no wide kernel for this variant");
   if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute((const void *) fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   const uint32_t grid = (uint32_t)((nq + qper - 1) / qper);
   void *args[] = { (void *) &p };
-  CU_TRY(cudaLaunchKernel((const void *) fn, dim3(grid), dim3(256), args, smem, stream));
+  CU_TRY(cudaLaunchKernel((const void *) fn, dim3(grid), dim3(tpb), args, smem, stream));
   return FM_SUCCESS;
 }
 

@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 GO = os.path.join(ROOT, "gpurun_out")
-TIMED = os.environ.get("FM_TIMED_KERNEL", "fm_search_wide_kernel<2, 3, 1, 256, 8, 0>")     # bench.py's timed kernel (r01 / early r02: fm_search_sparse_kernel<2, 2, 3, 256, 4, 0>)
+TIMED = os.environ.get("FM_TIMED_KERNEL", "fm_search_wide_kernel<2, 5, 1, 256, 8, 0>")     # bench.py's timed kernel (r01 / early r02: fm_search_sparse_kernel<2, 2, 3, 256, 4, 0>)
 PR = os.path.join(ROOT, "profiles")
 
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__sectors_read.sum",

@@ -11,7 +11,7 @@ def nbytes(s):
     return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
 big = max(recs, key=lambda r: num(r["launch__grid_size"]) * (1 if "Lb0" in r["kernel"] or ", 0>" in r["kernel"] or "false" in r["kernel"] else 0.001))
 what = {"sparse": "14 bases per 64-byte block, uniform grid of 2 blocks per symbol + search trees, one state machine per read, 2-base lead table, 34.4 GB table",
-        "wide": "46 bases per 64-byte block of 4 96-bit entries, block = top 30 bits of the wide symbol, 8-base lead table, 74.4 GB table"}[key]
+        "wide": "46 bases per 64-byte block of 5 packed 96-bit entries, block = top 30 bits of the wide symbol, 8-base lead table, 70.4 GB table"}[key]
 summ = json.load(open(os.path.join(PR, "ncu_summary.json")))
 summ[key] = {"source": f"profiles/{tag}_prof_{key}.json (ncu --set full via profiles/scripts/capture_ncu.sh, {big['kernel'][:90]}, grid {big['launch__grid_size']}: {what}, 10 M x 100 bp reads)",
              "dram_bytes_per_launch_10m_reads": nbytes(big["dram__bytes_read.sum"]) + nbytes(big["dram__bytes_write.sum"]),

@@ -187,6 +187,7 @@ def test_wide_steps_repetitive_texts_search_trees(pkg, tmp_path, monkeypatch, na
     image = np.fromfile(paths[101], dtype=np.uint32)
     idx = pkg.DeviceIndex.from_image(image)
     saw_overflow, deepest = False, 0
+    monkeypatch.setenv("FMGPU_WIDE_PACK", str(k % 2))          # (k = 2: the unpacked form of the 96-bit entries)
     for length, widths in ((20, (10, 20)), (40, (30, 10)), (66, (30,)), (98, (46,))):
         starts = rng.integers(0, text.size - length + 1, 2000)
         reads = np.concatenate([text[s:s + length] for s in starts] + [ACGT[rng.integers(0, 4, 500 * length)]])
@@ -246,6 +247,7 @@ def test_wide_fuzz_tiny_references_against_the_reference_searcher(pkg, tmp_path)
                 batch.upload_ascii(reads)
                 os.environ["FMGPU_WIDE_LEAD_MAX"] = "5"
                 os.environ["FMGPU_WIDE_DYNAMIC"] = str((case + length) % 2)
+                os.environ["FMGPU_WIDE_PACK"] = str((case // 3 + w) % 2)      # 96-bit entries on 64-byte blocks: five packed / four per block
                 try:
                     idx.widen(w, pbits, (2, 4)[(case // 2 + length) % 2])
                     exceptional += idx.meta.wide_exceptional
@@ -253,7 +255,7 @@ def test_wide_fuzz_tiny_references_against_the_reference_searcher(pkg, tmp_path)
                         batch.search(idx, pkg.variant(pkg.MODE_WIDE, qpt))
                         assert np.array_equal(batch.download(), want), f"case {case}: k={k} d={d} n={n} tag={tag} len={length} W={w} prefix={pbits} qpt={qpt}"
                 finally:
-                    del os.environ["FMGPU_WIDE_LEAD_MAX"], os.environ["FMGPU_WIDE_DYNAMIC"]
+                    del os.environ["FMGPU_WIDE_LEAD_MAX"], os.environ["FMGPU_WIDE_DYNAMIC"], os.environ["FMGPU_WIDE_PACK"]
                 idx.unwiden()
                 batch.free()
                 cases += 1
@@ -314,7 +316,7 @@ def test_wide_lead_table_and_fetch_counter(pkg, k):
     idx.unwiden()
     idx.widen(46)
     m = idx.meta
-    assert (m.wide_bases, m.wide_lanes, m.wide_entry_words, m.wide_prefix_bits) == (46, 2, 3, 24)
+    assert (m.wide_bases, m.wide_lanes, m.wide_entry_words, m.wide_block_entries, m.wide_prefix_bits) == (46, 2, 3, 5, 24)
     for length in (100, 92, 46, 50, 101, 146):
         nq = 200_000
         d_ascii = torch.empty(nq * length, dtype=torch.uint8, device="cuda")
@@ -364,8 +366,8 @@ def test_wide_config3_full_size_against_reference_checksums(pkg):
         assert idx.wide_bases_for(length) == 46                  # 100 = 8 + 2 x 46: 96-bit entries
         idx.widen(46)
         m = idx.meta
-        assert (m.wide_bases, m.wide_lanes, m.wide_entry_words, m.wide_prefix_bits, m.wide_row_bits) == (46, 2, 3, 30, 31) and m.wide_bytes < 76e9
-        assert m.wide_exceptional <= 96 and m.wide_tree_rows < n // 5
+        assert (m.wide_bases, m.wide_lanes, m.wide_entry_words, m.wide_block_entries, m.wide_prefix_bits, m.wide_row_bits) == (46, 2, 3, 5, 30, 31)
+        assert m.wide_bytes < 76e9 and m.wide_exceptional <= 96 and m.wide_tree_rows < n // 10
         for qpt in (1, 2):
             batch.search(idx, pkg.variant(pkg.MODE_WIDE, qpt))
             assert helpers.results_text_md5(batch.download()) == gold["md5"][key], f"tag {tag} qpt {qpt} (46 bases per step)"
