@@ -179,7 +179,7 @@ typedef struct {
                                  32/64/128-byte block with 256-bit loads and consumes up to 4 bases per step;
                                  FMGPU_MODE_SPARSE: sparse-step table (fmgpu_index_sparsify): one 64-byte block (grid
                                  root or search-tree node) per fetch, up to 14 bases per step, one state machine per read;
-                                 FMGPU_MODE_WIDE: wide-step table (fmgpu_index_widen): one 128-byte block per fetch, up to 30
+                                 FMGPU_MODE_WIDE: wide-step table (fmgpu_index_widen): one 64-byte block per fetch, up to 46
                                  bases per step, the block computed from the read alone (both interval ends share it) */
   int32_t queries_per_thread; /* independent queries interleaved per thread / lane pair / lane group: 1, 2 or 4 (sparse: 1..4);
                                  0 = the kernel family's default (sparse: 3 with static, 1 with dynamic read assignment) */
@@ -325,16 +325,20 @@ int32_t fmgpu_index_unfuse(fmgpu_index_t *idx);
 int32_t fmgpu_index_sparsify(fmgpu_index_t *idx, uint32_t sparse_bases, uint32_t lambda, uint32_t lanes);
 int32_t fmgpu_index_unsparsify(fmgpu_index_t *idx);
 /* Wide-step table, built on the GPU from this replica's own block table: one wide step = wide_bases/k reference LF steps
- * (exactly), ONE 128-byte block fetch for both interval ends.  The rows are sorted by the wide symbol in front of them
- * (wide_bases <= 30 bases = a 60-bit key); the top prefix_bits of the symbol select the block -- computed from the read,
- * never looked up, the same for both ends -- and the block's 15 64-bit entries carry the rest of the symbol with the row
- * (csrc/fm_wide.cuh).  Buckets with more than 15 rows become search trees as in the sparse-step table.  A read of
- * len = b + S * wide_bases bases (b < 16 from a lead table of all b-mers) costs S block fetches: 3 for 100 bp, 8 for 250 bp
- * at 30 bases per step.  wide_bases 0 = the widest the text allows (30 up to 4 G rows); prefix_bits 0 = 3.75 .. 7.5 rows per
- * bucket on average (17 .. 34 bytes per text base).  A table serves the read lengths its width divides (after the lead
- * bases): fmgpu_wide_bases_for(idx, len) names the width to build for a length, fmgpu_index_wide_serves(idx, len) tells
- * whether an existing table (with its lead table, see fmgpu_index_prepare) does.  AltCounters files with an active padding
- * quirk are refused (FM_E_NOT_IMPLEMENTED, like memory or budget shortage): the sparse-step table serves them. */
+ * (exactly), ONE block fetch for both interval ends.  The rows are sorted by the wide symbol in front of them (wide_bases <= 46
+ * bases = a 92-bit key); the top prefix_bits of the symbol select the block -- computed from the read, never looked up, the same
+ * for both ends -- and the block's entries carry the rest of the symbol with the row (csrc/fm_wide.cuh): 64-bit entries (7 per
+ * 64-byte block) for steps up to 30 bases, 96-bit entries (5 per block) up to 46.  Buckets with more rows than a block holds
+ * become search trees as in the sparse-step table; the few buckets a suffix shorter than the step sorts into are detected by
+ * the builder (every entry and every bucket is verified against the composed LF walk) and answered with plain steps.
+ * A read of len = b + S * wide_bases bases (b < 16 from a lead table of all b-mers) costs S block fetches: 2 for 100 bp at 46
+ * bases per step, 3 at 30.  wide_bases 0 = the widest 64-bit entries allow (30 up to 4 G rows); prefix_bits 0 = 1.9 .. 3.75 rows
+ * per 64-byte bucket on average (17 .. 34 bytes per text base), one bit more ("roomy", 0.9 .. 1.9 rows) when that grid is at most
+ * 40 % of the device's memory; lanes 0 = 2 (64-byte blocks; 4 = 128-byte blocks).  A table serves the read lengths its width
+ * divides (after the lead bases): fmgpu_wide_bases_for(idx, len) names the width to build for a length,
+ * fmgpu_index_wide_serves(idx, len) tells whether an existing table (with its lead table, see fmgpu_index_prepare) does.
+ * AltCounters files with an active padding quirk are refused (FM_E_NOT_IMPLEMENTED, like memory or budget shortage): the
+ * sparse-step table serves them. */
 int32_t  fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, uint32_t prefix_bits, uint32_t lanes);
 int32_t  fmgpu_index_unwiden(fmgpu_index_t *idx);
 uint32_t fmgpu_wide_bases_for(const fmgpu_index_t *idx, uint32_t len);      /* 0 = no width serves this length */
