@@ -81,9 +81,6 @@ struct FmWideParams {
   const uint2 *start;         /* lead table: (L,R) after the first start_bits / 2 bases, or NULL = (0, bwtsize) */
   uint32_t start_bits;
   unsigned long long *fetch_counters;  /* COUNT only: [0] grid blocks, [1] SB96 blocks (exceptional buckets), [2] tree nodes below the grid */
-  /* 96-bit keys, precomputed by the launcher: word masks of the wbits-bit field and of its low sub_bits, and where the block number starts */
-  uint32_t km[3], sm[3];
-  uint32_t bidx, bsh;         /* block = (key >> sub_bits): word sub_bits / 32, bit sub_bits % 32 */
 };
 
 /* one 256-bit load per lane.  128-byte blocks use the whole line (default fill); 64-byte blocks ask for a 64-byte fill */
@@ -131,8 +128,10 @@ template <int EW> __device__ __forceinline__ typename FmWideKey<EW>::type fm_wid
 }
 
 /* this lane's share of #{ entries < key }, 96-bit entries: words [2..4] and [5..7] of the lane */
-__device__ __forceinline__ uint32_t fm_wide_partial3(const uint32_t (&w)[8], uint64_t khi, uint32_t klo)
+__device__ __forceinline__ uint32_t fm_wide_partial3(const uint32_t (&w)[8], fm_u128 key)
 {
+  const uint32_t klo = (uint32_t) key;
+  const uint64_t khi = (uint64_t)(key >> 32);
   uint32_t c = 0;
   #pragma unroll
   for (int j = 0; j < 2; j++) {
@@ -143,32 +142,16 @@ __device__ __forceinline__ uint32_t fm_wide_partial3(const uint32_t (&w)[8], uin
   return c;
 }
 
-/* A 96-bit step key in 32-bit words (no __int128 arithmetic in the hot loop): what a step needs of the wbits-bit field at
- * `pos` of the read -- its block (returned) and (sub << row_bits) as { kh = bits 32 .. 95, kl = bits 0 .. 31 }; the interval
- * end X (< 2^row_bits, row_bits <= 32) is OR-ed into kl when the key is compared. */
-struct FmWideKey96 { uint64_t kh; uint32_t kl; };
-__device__ __forceinline__ uint32_t fm_wide_key96(const uint32_t *q, uint32_t pos, const FmWideParams &p, FmWideKey96 &k)
-{
-  const uint32_t w0 = fm_read_field(q, pos, p.km[0]);
-  const uint32_t w1 = p.km[1] ? fm_read_field(q, pos + 32u, p.km[1]) : 0u;
-  const uint32_t w2 = p.km[2] ? fm_read_field(q, pos + 64u, p.km[2]) : 0u;
-  const uint32_t lo = p.bidx == 0u ? w0 : p.bidx == 1u ? w1 : w2, hi = p.bidx == 0u ? w1 : p.bidx == 1u ? w2 : 0u;
-  const uint32_t block = __funnelshift_r(lo, hi, p.bsh);        /* key >> sub_bits (fits 32 bits) */
-  const uint32_t s0 = w0 & p.sm[0], s1 = w1 & p.sm[1], s2 = w2 & p.sm[2];
-  const uint32_t r = p.row_bits;                               /* (sub << row_bits): 96-bit shift left by 1 .. 32 */
-  k.kl = __funnelshift_lc(0u, s0, r);
-  k.kh = (uint64_t) __funnelshift_lc(s0, s1, r) | ((uint64_t) __funnelshift_lc(s1, s2, r) << 32);
-  return block;
-}
-
 __device__ __forceinline__ uint32_t fm_wide_lt96(uint32_t elo, uint32_t emid, uint32_t ehi, uint64_t khi, uint32_t klo)
 {
   const uint64_t eh = (uint64_t) emid | ((uint64_t) ehi << 32);
   return (eh < khi || (eh == khi && elo < klo)) ? 1u : 0u;
 }
 /* packed form: lane 0 holds the header word, entries 1, 2 and the low word of entry 3 (handed over in xw); lane 1 the rest */
-__device__ __forceinline__ uint32_t fm_wide_partial5(const uint32_t (&w)[8], uint64_t khi, uint32_t klo, uint32_t lg, uint32_t xw)
+__device__ __forceinline__ uint32_t fm_wide_partial5(const uint32_t (&w)[8], fm_u128 key, uint32_t lg, uint32_t xw)
 {
+  const uint32_t klo = (uint32_t) key;
+  const uint64_t khi = (uint64_t)(key >> 32);
   const bool hi = lg != 0u;
   uint32_t c = fm_wide_lt96(hi ? xw : w[1], hi ? w[0] : w[2], hi ? w[1] : w[3], khi, klo);
   c += fm_wide_lt96(hi ? w[2] : w[4], hi ? w[3] : w[5], hi ? w[4] : w[6], khi, klo);
@@ -217,11 +200,11 @@ __device__ __forceinline__ void fm_stage_reads(uint32_t *fsm, uint32_t *sq, cons
   }
 }
 
-/* 96-bit entries: this lane's share of #{ entries < (kh : kl) } */
-template <int EW> __device__ __forceinline__ uint32_t fm_wide_count96(const uint32_t (&w)[8], uint64_t kh, uint32_t kl, uint32_t lg, uint32_t xw)
+template <int EW> __device__ __forceinline__ uint32_t fm_wide_count(const uint32_t (&w)[8], typename FmWideKey<EW>::type key, uint32_t lg, uint32_t xw)
 {
-  if constexpr (EW == 5) return fm_wide_partial5(w, kh, kl, lg, xw);
-  else return fm_wide_partial3(w, kh, kl);
+  if constexpr (EW == 5) return fm_wide_partial5(w, key, lg, xw);
+  else if constexpr (EW == 3) return fm_wide_partial3(w, key);
+  else return fm_wide_partial(w, key, lg);
 }
 /* header of a block from lane 0's first two words */
 template <int EW> __device__ __forceinline__ void fm_wide_header(uint32_t w0, uint32_t w1, uint32_t &value, uint32_t &kind)
@@ -262,17 +245,11 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_kernel(const FmW
   fm_stage_reads<THREADS>(fsm, sq, p.packed + (size_t) q0 * p.wpq, nqb * p.wpq);
 
   uint32_t L[QPT], R[QPT], aL[QPT], aR[QPT], rem[QPT];
-  KeyT key[QPT];                                               /* 64-bit entries: the step's key */
-  FmWideKey96 k96[QPT];                                        /* 96-bit entries: its compare words */
+  KeyT key[QPT];
   const uint32_t *myq[QPT];
   bool live[QPT];
   const uint32_t kmask = (p.start_bits >= 32u) ? 0xFFFFFFFFu : ((1u << p.start_bits) - 1u);
   bool busy = false;
-  /* key of the step at bit `pos` of read slot i; returns its block */
-  auto set_step = [&](int i, const uint32_t *q, uint32_t pos) -> uint32_t {
-    if constexpr (EW == 2) { key[i] = fm_read_field64(q, pos, p.wbits); return (uint32_t)(key[i] >> p.sub_bits); }
-    else return fm_wide_key96(q, pos, p, k96[i]);
-  };
   #pragma unroll
   for (int i = 0; i < QPT; i++) {
     const uint32_t lq = i * GROUPS + group;
@@ -284,8 +261,11 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_kernel(const FmW
       L[i] = lr.x; R[i] = lr.y;
     }
     rem[i] = live[i] ? p.nsteps : 0u;
-    aL[i] = aR[i] = FM_WD_DONE; key[i] = 0; k96[i].kh = 0; k96[i].kl = 0;
-    if (rem[i]) aL[i] = aR[i] = set_step(i, myq[i], p.start_bits);
+    aL[i] = aR[i] = FM_WD_DONE; key[i] = 0;
+    if (rem[i]) {
+      key[i] = fm_wide_read_key<EW>(myq[i], p.start_bits, p.wbits);
+      aL[i] = aR[i] = (uint32_t)(key[i] >> p.sub_bits);
+    }
     busy |= rem[i] != 0u;
   }
 
@@ -311,24 +291,18 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_kernel(const FmW
       const bool act = rem[i] != 0u;
       const bool doL = act && aL[i] != FM_WD_DONE;
       const bool doR = act && (!doL || aR[i] == aL[i]);                  /* R alone, or riding on the node it shares with L */
+      const KeyT ksub = (key[i] & submask) << p.row_bits;
       uint32_t cL = 0, cR = 0, xw = 0;
       if constexpr (EW == 5) xw = __shfl_xor_sync(0xFFFFFFFFu, w[i][7], 1);
       if (act) {
-        if constexpr (EW == 2) {
-          const KeyT ksub = (key[i] & submask) << p.row_bits;
-          cL = fm_wide_partial(w[i], ksub | L[i], lg);
-          cR = fm_wide_partial(w[i], ksub | R[i], lg);
-        } else {
-          cL = fm_wide_count96<EW>(w[i], k96[i].kh, k96[i].kl | L[i], lg, xw);
-          cR = fm_wide_count96<EW>(w[i], k96[i].kh, k96[i].kl | R[i], lg, xw);
-        }
+        cL = fm_wide_count<EW>(w[i], ksub | L[i], lg, xw);
+        cR = fm_wide_count<EW>(w[i], ksub | R[i], lg, xw);
       }
       uint32_t hval, hkind;
       fm_wide_header<EW>(__shfl_sync(0xFFFFFFFFu, w[i][0], 0, LANES), EW == 5 ? 0u : __shfl_sync(0xFFFFFFFFu, w[i][1], 0, LANES), hval, hkind);
       const uint32_t vL = hval + fm_group_sum<LANES>(cL), vR = hval + fm_group_sum<LANES>(cR);
       if (act && hkind == FM_WD_EXC) {                                   /* (only ever at a grid block: both ends are here) */
-        if constexpr (EW == 2) fm_wide_plain_step<KeyT>(p, key[i], L[i], R[i]);
-        else fm_wide_plain_step<KeyT>(p, fm_read_field96(myq[i], p.start_bits + (p.nsteps - rem[i]) * p.wbits, p.wbits), L[i], R[i]);
+        fm_wide_plain_step<KeyT>(p, key[i], L[i], R[i]);
         if (COUNT && lg == 0) n_sb += 2ull * p.hops;
         aL[i] = aR[i] = FM_WD_DONE;
       } else {
@@ -338,7 +312,10 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_kernel(const FmW
       }
       if (act && aL[i] == FM_WD_DONE && aR[i] == FM_WD_DONE) {           /* step complete: next step's block */
         rem[i] -= 1u;
-        if (rem[i]) aL[i] = aR[i] = set_step(i, myq[i], p.start_bits + (p.nsteps - rem[i]) * p.wbits);
+        if (rem[i]) {
+          key[i] = fm_wide_read_key<EW>(myq[i], p.start_bits + (p.nsteps - rem[i]) * p.wbits, p.wbits);
+          aL[i] = aR[i] = (uint32_t)(key[i] >> p.sub_bits);
+        }
       }
       busy |= rem[i] != 0u;
     }
@@ -384,12 +361,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_dyn_kernel(const
 
   uint32_t L[QPT], R[QPT], aL[QPT], aR[QPT], rem[QPT], rd[QPT];
   KeyT key[QPT];
-  FmWideKey96 k96[QPT];
   bool fresh[QPT];                                             /* the read was just taken: its (L,R) still come from the lead table */
-  auto set_step = [&](int i, const uint32_t *q, uint32_t pos) -> uint32_t {
-    if constexpr (EW == 2) { key[i] = fm_read_field64(q, pos, p.wbits); return (uint32_t)(key[i] >> p.sub_bits); }
-    else return fm_wide_key96(q, pos, p, k96[i]);
-  };
   /* takes the next read of the CTA for slot i (or parks the slot): all lanes of the warp call it together */
   auto take = [&](int i, bool need) {
     uint32_t r = 0;
@@ -400,13 +372,15 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_dyn_kernel(const
       if (r < nqb) {
         rem[i] = p.nsteps; L[i] = 0u; R[i] = p.bwtsize;
         fresh[i] = p.start != NULL;
-        if (rem[i]) aL[i] = aR[i] = set_step(i, sq + r * p.wpq, p.start_bits);
-        else { aL[i] = aR[i] = FM_WD_DONE; }
+        if (rem[i]) {
+          key[i] = fm_wide_read_key<EW>(sq + r * p.wpq, p.start_bits, p.wbits);
+          aL[i] = aR[i] = (uint32_t)(key[i] >> p.sub_bits);
+        } else { aL[i] = aR[i] = FM_WD_DONE; }
       } else { rem[i] = 0u; aL[i] = aR[i] = FM_WD_DONE; rd[i] = 0xFFFFFFFFu; fresh[i] = false; }
     }
   };
   #pragma unroll
-  for (int i = 0; i < QPT; i++) { rd[i] = 0xFFFFFFFFu; rem[i] = 0u; aL[i] = aR[i] = FM_WD_DONE; L[i] = R[i] = 0u; key[i] = 0; k96[i].kh = 0; k96[i].kl = 0; fresh[i] = false; take(i, true); }
+  for (int i = 0; i < QPT; i++) { rd[i] = 0xFFFFFFFFu; rem[i] = 0u; aL[i] = aR[i] = FM_WD_DONE; L[i] = R[i] = 0u; key[i] = 0; fresh[i] = false; take(i, true); }
 
   bool busy = false;
   #pragma unroll
@@ -433,24 +407,18 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_dyn_kernel(const
       const bool act = have && rem[i] != 0u;
       const bool doL = act && aL[i] != FM_WD_DONE;
       const bool doR = act && (!doL || aR[i] == aL[i]);
+      const KeyT ksub = (key[i] & submask) << p.row_bits;
       uint32_t cL = 0, cR = 0, xw = 0;
       if constexpr (EW == 5) xw = __shfl_xor_sync(0xFFFFFFFFu, w[i][7], 1);
       if (act) {
-        if constexpr (EW == 2) {
-          const KeyT ksub = (key[i] & submask) << p.row_bits;
-          cL = fm_wide_partial(w[i], ksub | L[i], lg);
-          cR = fm_wide_partial(w[i], ksub | R[i], lg);
-        } else {
-          cL = fm_wide_count96<EW>(w[i], k96[i].kh, k96[i].kl | L[i], lg, xw);
-          cR = fm_wide_count96<EW>(w[i], k96[i].kh, k96[i].kl | R[i], lg, xw);
-        }
+        cL = fm_wide_count<EW>(w[i], ksub | L[i], lg, xw);
+        cR = fm_wide_count<EW>(w[i], ksub | R[i], lg, xw);
       }
       uint32_t hval, hkind;
       fm_wide_header<EW>(__shfl_sync(0xFFFFFFFFu, w[i][0], 0, LANES), EW == 5 ? 0u : __shfl_sync(0xFFFFFFFFu, w[i][1], 0, LANES), hval, hkind);
       const uint32_t vL = hval + fm_group_sum<LANES>(cL), vR = hval + fm_group_sum<LANES>(cR);
       if (act && hkind == FM_WD_EXC) {
-        if constexpr (EW == 2) fm_wide_plain_step<KeyT>(p, key[i], L[i], R[i]);
-        else fm_wide_plain_step<KeyT>(p, fm_read_field96(sq + rd[i] * p.wpq, p.start_bits + (p.nsteps - rem[i]) * p.wbits, p.wbits), L[i], R[i]);
+        fm_wide_plain_step<KeyT>(p, key[i], L[i], R[i]);
         aL[i] = aR[i] = FM_WD_DONE;
       } else {
         const bool is_inner = hkind == FM_WD_INNER;
@@ -459,7 +427,10 @@ __global__ void __launch_bounds__(THREADS, MINB) fm_search_wide_dyn_kernel(const
       }
       bool next_block = false;
       if (act && aL[i] == FM_WD_DONE && aR[i] == FM_WD_DONE) { rem[i] -= 1u; next_block = rem[i] != 0u; }
-      if (next_block) aL[i] = aR[i] = set_step(i, sq + rd[i] * p.wpq, p.start_bits + (p.nsteps - rem[i]) * p.wbits);
+      if (next_block) {
+        key[i] = fm_wide_read_key<EW>(sq + rd[i] * p.wpq, p.start_bits + (p.nsteps - rem[i]) * p.wbits, p.wbits);
+        aL[i] = aR[i] = (uint32_t)(key[i] >> p.sub_bits);
+      }
       const bool finished = have && rem[i] == 0u && aL[i] == FM_WD_DONE;
       if (finished && lg == 0) reinterpret_cast<uint2 *>(p.results)[q0 + rd[i]] = make_uint2(L[i], R[i]);
       take(i, finished);

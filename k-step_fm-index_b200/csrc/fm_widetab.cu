@@ -419,12 +419,6 @@ int32_t fm_launch_wide(const fmgpu_index_t *idx, const uint32_t *d_packed, uint6
   p.nroots = 1u << idx->meta.wide_prefix_bits; p.total_blocks = (uint32_t) idx->meta.wide_blocks;
   p.start = pl.b ? idx->wlead[pl.b] : NULL; p.start_bits = 2 * pl.b;
   p.fetch_counters = d_counters;
-  for (uint32_t j = 0; j < 3; j++) {
-    const uint32_t kb = p.wbits > 32 * j ? p.wbits - 32 * j : 0, sb = p.sub_bits > 32 * j ? p.sub_bits - 32 * j : 0;
-    p.km[j] = kb >= 32 ? 0xFFFFFFFFu : ((1u << kb) - 1u);
-    p.sm[j] = sb >= 32 ? 0xFFFFFFFFu : ((1u << sb) - 1u);
-  }
-  p.bidx = p.sub_bits >> 5; p.bsh = p.sub_bits & 31u;
   if (d_counters) v.queries_per_thread = 1;
   const char *tenv = getenv("FMGPU_WIDE_TPB");
   uint32_t tpb = 256;
