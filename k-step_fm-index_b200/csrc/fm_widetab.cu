@@ -351,7 +351,7 @@ template <int LANES, int EW>
 static fm_wide_fn fm_pick_wide(int qpt)
 {
   if (qpt == 0) return fm_search_wide_kernel<LANES, EW, 1, 256, 4, true>;         /* instrumented */
-  if (qpt == 1) return (EW != 2 && getenv("FMGPU_WIDE_MINB6")) ? fm_search_wide_kernel<LANES, EW, 1, 256, 6, false> : fm_search_wide_kernel<LANES, EW, 1, 256, EW != 2 ? 8 : 6, false>;   /* (96-bit entries: 32 registers, 8 CTAs per SM: 0.640 vs 0.649 ms at 38) */
+  if (qpt == 1) return fm_search_wide_kernel<LANES, EW, 1, 256, EW != 2 ? 8 : 6, false>;   /* 96-bit entries at 32 registers, 8 CTAs per SM: 0.615 vs 0.640 ms at 40 registers */   /* (96-bit entries: 32 registers, 8 CTAs per SM: 0.640 vs 0.649 ms at 38) */
   if (qpt == 2) return fm_search_wide_kernel<LANES, EW, 2, 256, EW != 2 ? 3 : 4, false>;
   if (qpt == 3) return fm_search_wide_kernel<LANES, EW, 3, 256, EW != 2 ? 2 : 3, false>;
   if (qpt == 4) return fm_search_wide_kernel<LANES, EW, 4, 256, 2, false>;
