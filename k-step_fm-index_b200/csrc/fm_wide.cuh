@@ -19,7 +19,8 @@
  *                           order of (F(i), i), i.e. one stable radix sort of the composed keys.
  *   block (32 * LANES B)    4 * LANES x u64: word 0 = { value (low half), kind (high half) }, then SLOTS = 4 * LANES - 1
  *                           ascending entries padded with ~0 (LANES = 2: 64 bytes, 7 entries, the default; LANES = 4:
- *                           128 bytes, 15 entries):
+ *                           128 bytes, 15 entries).  Steps wider than 30 bases need 96-bit entries: five to a 64-byte block
+ *                           behind a one-word header (EW = 5, see FmWideKey below), else two per lane (EW = 3):
  *        leaf               value = G(first symbol of the bucket) + entries of the bucket in front of this block;
  *                           rank_F(sigma, X) = value + #{ entries < (sub(sigma) << row_bits | X) }
  *        inner node         value = block number of child 0, entries = SLOTS separators (first entry of children 1..);
@@ -41,10 +42,11 @@
  * quirk (their composed rank is not a plain counting function) are refused; the sparse-step table serves them.
  *
  * Kernels.  fm_search_wide_kernel: the per-read state machine of fm_sparse.cuh -- one block fetch per iteration and
- * unfinished read -- on LANES-lane groups (one 256-bit load per lane), 64-bit compares; the timed kernel of bench.py
- * (LANES = 2, one read per lane pair, 32 registers).  Per read the kernel's instructions scale with the lanes it occupies:
+ * unfinished read -- on LANES-lane groups (one 256-bit load per lane), 64- or 96-bit compares; the timed kernel of bench.py
+ * (LANES = 2, EW = 5: 46 bases per step, one read per lane pair, 32 registers; 100 bp = an 8-base lead table + 2 fetches).  Per read the kernel's instructions scale with the lanes it occupies:
  * the 128-byte form is issue-bound (72 % of the issue slots, profiles/r02w_*), the 64-byte form is not (43 %) and runs
- * at 0.96 of the request-rate ceiling.  fm_search_wide_burst_kernel issues all block loads of a read at once (their
+ * at 0.96 of the request-rate ceiling (30 bases per step; 0.77 at 46, where the per-read work around two fetches weighs more).
+ * fm_search_wide_dyn_kernel hands reads to the lane groups from a CTA queue (repeat-rich texts).  fm_search_wide_burst_kernel issues all block loads of a read at once (their
  * addresses do not depend on the interval); it holds fewer reads per SM and measured slower ($FMGPU_WIDE_BURST=1).
  */
 #ifndef FM_WIDE_CUH_

@@ -81,7 +81,7 @@ extern "C" uint32_t fmgpu_wide_bases_for(const fmgpu_index_t *idx, uint32_t len)
   const bool tail_ok = idx->meta.tail_valid != 0;
   uint32_t s2 = 0, s3 = 0;
   const uint32_t w2 = fm_wide_bases_for_len(k, len, fm_wide_max_bases_ew(k, pb, rb, 2), tail_ok, &s2);
-  /* 96-bit entries (4 instead of 7 per 64-byte block: 12 % instead of 0.3 % of the steps meet a search tree on a random text)
+  /* 96-bit entries (5 instead of 7 per 64-byte block: 4 % instead of 0.3 % of the steps meet a search tree on a random text)
    * when they save a whole step: 100 bp = 8 + 2 x 46 instead of 10 + 3 x 30.  $FMGPU_WIDE_ENTRY_WORDS=2 keeps 64-bit entries. */
   const char *env = getenv("FMGPU_WIDE_ENTRY_WORDS");
   if (env && *env && atoi(env) == 2) return w2;
