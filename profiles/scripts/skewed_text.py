@@ -124,6 +124,28 @@ if os.environ.get("FM_FUSED", "1") != "0":
         emit(what="fused", ms=ms, mq_per_s=nq / ms / 1e3, fused_gb=idx.meta.fused_bytes / 1e9, equals_plain=bool(torch.equal(d_res, want))); idx.unfuse()
     except pkg.FMError as ex:
         emit(what="fused unavailable", err=str(ex))
+# the wide-step table (second half of round 2): the width that serves this read length, and 30 bases per step (64-bit entries)
+for wb in ([int(x) for x in os.environ["FM_WIDE"].split(",")] if os.environ.get("FM_WIDE") else [idx.wide_bases_for(length), 30]):
+    t0 = time.time()
+    try:
+        idx.widen(wb); idx.prepare(length); torch.cuda.synchronize()
+    except pkg.FMError as ex:
+        emit(what="widen failed", bases=wb, err=str(ex)); continue
+    m = idx.meta
+    emit(what="widen", bases=m.wide_bases, entry_words=m.wide_entry_words, block_entries=m.wide_block_entries, prefix_bits=m.wide_prefix_bits, seconds=time.time() - t0,
+         wide_gb=m.wide_bytes / 1e9, overfull_buckets=m.wide_overflow, tree_nodes=m.wide_tree_nodes, tree_rows_fraction=m.wide_tree_rows / m.bwtsize,
+         tree_depth=m.wide_tree_depth, exceptional_buckets=m.wide_exceptional)
+    a, s_, o = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    pkg.check(L.fmgpu_count_fetches_wide_device(idx.handle, d_packed.data_ptr(), nq, length, d_res.data_ptr(), stream, C.byref(a), C.byref(s_), C.byref(o)), "count")
+    probe = pkg.gather_probe(0, int(m.wide_bytes), 256, 2)
+    for dyn, qpt in ((0, 1), (1, 1), (1, 2)):
+        os.environ["FMGPU_WIDE_DYNAMIC"] = str(dyn)
+        ms = run(pkg.variant(pkg.MODE_WIDE, qpt))
+        emit(what="wide", bases=m.wide_bases, qpt=qpt, dynamic_assignment=dyn, ms=ms, mq_per_s=nq / ms / 1e3, equals_plain=bool(torch.equal(d_res, want)),
+             grid_fetches_per_read=a.value / nq, tree_fetches_per_read=o.value / nq, sb96_blocks_per_read=s_.value / nq,
+             fetches_per_s=(a.value + o.value + s_.value) / (ms * 1e-3), probe_per_s=probe, fetch_rate_over_probe=(a.value + o.value + s_.value) / (ms * 1e-3) / probe)
+    del os.environ["FMGPU_WIDE_DYNAMIC"]
+    idx.unwiden()
 for ks, lam, lanes in [tuple(int(x) for x in c.split(":")) for c in os.environ.get("FM_SPARSE", "0:0:0,0:0:4").split(",")]:
     t0 = time.time()
     try:
