@@ -616,10 +616,11 @@ def main():
         # width is the one that serves this read length with the fewest fetches (30 bases for 100-bp reads)
         try:
             t0 = time.time()
-            wb = int(os.environ.get("FM_BENCH_WIDE_BASES", "0")) or index.wide_bases_for(READ_LEN)
-            if not wb:
-                raise pkg.FMError(19, "no wide step width serves this read length")
-            index.widen(wb, int(os.environ.get("FM_BENCH_WIDE_PREFIX_BITS", "0")), int(os.environ.get("FM_BENCH_WIDE_LANES", "0")))
+            wb = int(os.environ.get("FM_BENCH_WIDE_BASES", "0"))
+            if wb:
+                index.widen(wb, int(os.environ.get("FM_BENCH_WIDE_PREFIX_BITS", "0")), int(os.environ.get("FM_BENCH_WIDE_LANES", "0")))
+            else:
+                index.widen_for(READ_LEN)                       # the width with the fewest steps (the 64-bit-entry one when memory is short)
             index.prepare(READ_LEN)
             torch.cuda.synchronize()
             setup["widen_s"] = round(time.time() - t0, 3)

@@ -342,6 +342,9 @@ int32_t fmgpu_index_unsparsify(fmgpu_index_t *idx);
 int32_t  fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, uint32_t prefix_bits, uint32_t lanes);
 int32_t  fmgpu_index_unwiden(fmgpu_index_t *idx);
 uint32_t fmgpu_wide_bases_for(const fmgpu_index_t *idx, uint32_t len);      /* 0 = no width serves this length */
+/* the same restricted to entries of at most max_entry_words 32-bit words (2: steps up to 30 bases, whose table needs a third
+ * less scratch memory to build): the width to retry with when the 96-bit table does not fit */
+uint32_t fmgpu_wide_bases_for_words(const fmgpu_index_t *idx, uint32_t len, uint32_t max_entry_words);
 int32_t  fmgpu_index_wide_serves(const fmgpu_index_t *idx, uint32_t len);   /* 1 / 0 */
 /* Builds NOW (synchronously) whatever a search of `len`-base reads on this replica may use: the tail table for odd
  * lengths on a 2-step index, the lead tables of the sparse-step plan.  The search entry points themselves never build

@@ -144,6 +144,7 @@ PROTOTYPES = {
     "fmgpu_index_widen": (C.c_int32, [_VP, C.c_uint32, C.c_uint32, C.c_uint32]),
     "fmgpu_index_unwiden": (C.c_int32, [_VP]),
     "fmgpu_wide_bases_for": (C.c_uint32, [_VP, C.c_uint32]),
+    "fmgpu_wide_bases_for_words": (C.c_uint32, [_VP, C.c_uint32, C.c_uint32]),
     "fmgpu_index_wide_serves": (C.c_int32, [_VP, C.c_uint32]),
     "fmgpu_count_fetches_wide_device": (C.c_int32, [_VP, _VP, C.c_uint64, C.c_uint32, _VP, _VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                                     C.POINTER(C.c_uint64)]),
@@ -409,9 +410,23 @@ class DeviceIndex:
     def unwiden(self):
         check(lib().fmgpu_index_unwiden(self.handle), "fmgpu_index_unwiden")
 
-    def wide_bases_for(self, length):
-        """Step width a wide-step table should have to serve reads of `length` bases with the fewest fetches (0 = none)."""
-        return int(lib().fmgpu_wide_bases_for(self.handle, length))
+    def wide_bases_for(self, length, max_entry_words=3):
+        """Step width a wide-step table should have to serve reads of `length` bases with the fewest fetches (0 = none);
+        max_entry_words=2 keeps 64-bit entries (steps up to 30 bases; less memory to build)."""
+        return int(lib().fmgpu_wide_bases_for_words(self.handle, length, max_entry_words))
+
+    def widen_for(self, length):
+        """The wide-step table for reads of `length` bases: the best width, else the 64-bit-entry width when memory is short."""
+        wb = self.wide_bases_for(length)
+        if not wb:
+            raise FMError(19, "fmgpu_wide_bases_for (no step width serves this read length)")
+        try:
+            return self.widen(wb)
+        except FMError as ex:
+            wb2 = self.wide_bases_for(length, 2)
+            if ex.code != 19 or not wb2 or wb2 == wb:
+                raise
+            return self.widen(wb2)
 
     def wide_serves(self, length):
         return bool(lib().fmgpu_index_wide_serves(self.handle, length))

@@ -455,6 +455,10 @@ int32_t transferCPUtoGPU(void *index, void *queries, void *results)
         if (want_wide) {
           const uint32_t wb = fmgpu_wide_bases_for(rs->replica[g], qrys->size);
           if (wb) err = fmgpu_index_widen(rs->replica[g], wb, 0, 0);
+          if (wb && err == FM_E_NOT_IMPLEMENTED) {               /* no room for the 96-bit table: the 64-bit width (a third less scratch) */
+            const uint32_t wb2 = fmgpu_wide_bases_for_words(rs->replica[g], qrys->size, 2);
+            if (wb2 && wb2 != wb) err = fmgpu_index_widen(rs->replica[g], wb2, 0, 0);
+          }
         }
         if (err == FM_E_NOT_IMPLEMENTED && want_sparse) err = fmgpu_index_sparsify(rs->replica[g], 0, 0, 0);
         /* (round 1 switched repeat-rich texts to the fused-step table here; with search trees and per-read state machines

@@ -72,7 +72,7 @@ static uint32_t fm_wide_bases_for_len(uint32_t k, uint32_t len, uint32_t wmax, b
   return 0;
 }
 
-extern "C" uint32_t fmgpu_wide_bases_for(const fmgpu_index_t *idx, uint32_t len)
+extern "C" uint32_t fmgpu_wide_bases_for_words(const fmgpu_index_t *idx, uint32_t len, uint32_t max_entry_words)
 {
   if (!idx) return 0;
   const uint32_t n = idx->meta.bwtsize, rb = fm_bits_for(n), pb = fm_wide_auto_prefix(n, fm_wide_default_lanes());
@@ -84,12 +84,14 @@ extern "C" uint32_t fmgpu_wide_bases_for(const fmgpu_index_t *idx, uint32_t len)
   /* 96-bit entries (5 instead of 7 per 64-byte block: 4 % instead of 0.3 % of the steps meet a search tree on a random text)
    * when they save a whole step: 100 bp = 8 + 2 x 46 instead of 10 + 3 x 30.  $FMGPU_WIDE_ENTRY_WORDS=2 keeps 64-bit entries. */
   const char *env = getenv("FMGPU_WIDE_ENTRY_WORDS");
-  if (env && *env && atoi(env) == 2) return w2;
+  if (max_entry_words < 3 || (env && *env && atoi(env) == 2)) return w2;
   const uint32_t w3 = fm_wide_bases_for_len(k, len, fm_wide_max_bases_ew(k, pb, rb, 3), tail_ok, &s3);
   if (!w2) return w3;
   if (!w3) return w2;
   return s3 < s2 ? w3 : w2;
 }
+
+extern "C" uint32_t fmgpu_wide_bases_for(const fmgpu_index_t *idx, uint32_t len) { return fmgpu_wide_bases_for_words(idx, len, 3); }
 
 struct fm_wide_shape { uint32_t W, pb, rb, lanes, ew, force_every; };
 struct fm_wide_built { uint4 *wblocks; uint64_t total_blocks; uint32_t total_ext; unsigned long long stats[4]; };
