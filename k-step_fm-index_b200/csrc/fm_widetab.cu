@@ -6,6 +6,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <mutex>
+#include <math.h>
 #include "fm_wide.cuh"
 
 extern "C" int32_t fmgpu_index_unwiden(fmgpu_index_t *idx)
@@ -88,7 +89,16 @@ extern "C" uint32_t fmgpu_wide_bases_for_words(const fmgpu_index_t *idx, uint32_
   const uint32_t w3 = fm_wide_bases_for_len(k, len, fm_wide_max_bases_ew(k, pb, rb, 3), tail_ok, &s3);
   if (!w2) return w3;
   if (!w3) return w2;
-  return s3 < s2 ? w3 : w2;
+  if (s3 >= s2) return w2;
+  /* fewer steps, but fewer entries per block as well: expected fetches = steps x (1 + share of the steps that continue into a
+   * search tree), and a tree step costs about twice its fetch (it is a dependent one, and its warp waits for it).  Rows per
+   * bucket on the roomy grid, Poisson tail at the block's capacity: 5 packed / 4 unpacked 96-bit entries against 7 64-bit ones
+   * (2 Gbp: 2 x 1.08 against 3 x 1.01 -> 46 bases per step; 3.1 Gbp, unpacked: 2 x 1.66 against 3 x 1.06 -> 30). */
+  const uint32_t pbr = pb < 30 ? pb + 1 : pb;
+  const double mean = (double) n / (double) (1ull << pbr);
+  const uint32_t cap3 = (fm_wide_default_lanes() == 2 && n < 0x7FFFFFF0u) ? 5u : 2u * fm_wide_default_lanes(), cap2 = 4u * fm_wide_default_lanes() - 1u;
+  auto tail = [&](uint32_t cap) { double p = exp(-mean), acc = 0; for (uint32_t j = 0; j < cap; j++) { acc += p; p *= mean / (double)(j + 1); } return 1.0 - acc; };
+  return (double) s3 * (1.0 + 2.0 * tail(cap3)) < (double) s2 * (1.0 + 2.0 * tail(cap2)) ? w3 : w2;
 }
 
 extern "C" uint32_t fmgpu_wide_bases_for(const fmgpu_index_t *idx, uint32_t len) { return fmgpu_wide_bases_for_words(idx, len, 3); }

@@ -15,7 +15,10 @@ L = pkg.lib()
 t0 = time.time(); b = pkg.IndexBuild.from_synth(n, 1, 2, 64); idx = b.to_index(); b.free(); torch.cuda.synchronize()
 emit(what="build + reblock", n=n, seconds=time.time() - t0, sb96_gb=idx.meta.nbytes / 1e9, bwtsize=int(idx.meta.bwtsize))
 emit(what="widths", best=idx.wide_bases_for(length), with_64_bit_entries=idx.wide_bases_for(length, 2))
-t0 = time.time(); idx.widen_for(length); idx.prepare(length); torch.cuda.synchronize(); m = idx.meta
+t0 = time.time()
+if os.environ.get("FM_W"): idx.widen(int(os.environ["FM_W"]))        # a given width instead of the library's choice
+else: idx.widen_for(length)
+idx.prepare(length); torch.cuda.synchronize(); m = idx.meta
 emit(what="widen_for", seconds=time.time() - t0, bases=m.wide_bases, entry_words=m.wide_entry_words, block_entries=m.wide_block_entries, prefix_bits=m.wide_prefix_bits,
      row_bits=m.wide_row_bits, wide_gb=m.wide_bytes / 1e9, overfull_buckets=int(m.wide_overflow), tree_rows_fraction=m.wide_tree_rows / m.bwtsize, exceptional=int(m.wide_exceptional))
 stream = torch.cuda.current_stream().cuda_stream
