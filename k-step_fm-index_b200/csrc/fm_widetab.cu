@@ -228,7 +228,7 @@ extern "C" int32_t fmgpu_index_widen(fmgpu_index_t *idx, uint32_t wide_bases, ui
     if (renv && *renv) roomy = atoi(renv) != 0;
     else if (cudaMemGetInfo(&fb, &tb) == cudaSuccess)
       roomy = ((uint64_t) bbytes << (pb + 1)) <= (uint64_t) tb * 2 / 5 && ((uint64_t) bbytes << (pb + 1)) + 24ull * n + (2ull << 30) <= fb &&
-              fm_budget_allows(idx, ((uint64_t) bbytes << (pb + 1)) + ((uint64_t) bbytes << (pb - 3)));
+              fm_budget_allows(idx, ((uint64_t) bbytes << (pb + 1)) + (pb >= 3 ? (uint64_t) bbytes << (pb - 3) : 0));
     else cudaGetLastError();
     if (roomy) pb += 1;
   }
